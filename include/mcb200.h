@@ -1,0 +1,232 @@
+/*
+ * mcb200.h -- C ABI of libmocassin_b200.so: the B200 (sm_100a) implementation of
+ * mocassin's energy-packet transport hot path.
+ *
+ * The reference (rwesson/mocassin, Fortran 90 + MPI) has no FFI for this path; the
+ * seam is a set of Fortran calls inside the Lucy iteration `iterateMC`
+ * (source/iteration_mod.f90).  Each entry point below names the reference
+ * interface it replaces.  Signatures are plain C (pointers + sizes, no C++/torch
+ * types) so the reference's Fortran driver binds them with ISO_C_BINDING
+ * (fortran/mcb200_mod.f90).
+ *
+ * Conventions
+ *  - All host arrays stay owned by the caller; the library copies in/out.
+ *  - Arrays use the reference's own layouts (column major, see each function), and
+ *    indices stored inside arrays (active, starIndeces) are 1-based, so a Fortran
+ *    caller passes c_loc(array) unchanged.
+ *  - Every function returns 0 on success or a negative MCB200_E* code;
+ *    mcb200_last_error() gives the message.  The reference's behaviour on the same
+ *    conditions is `print*; stop` (e.g. photon_mod.f90:826-832); the Fortran shim
+ *    turns a non-zero status into exactly that.
+ *  - One host thread per context; all calls are synchronous on return unless noted.
+ *  - There is no CPU fallback: without a CUDA device mcb200_create fails.
+ */
+#ifndef MCB200_H
+#define MCB200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define MCB200_OK            0
+#define MCB200_ENODEV       -1   /* no CUDA device / CUDA runtime error            */
+#define MCB200_EINVAL       -2   /* bad argument                                    */
+#define MCB200_ESTATE       -3   /* call sequence error (e.g. transport before set) */
+#define MCB200_ENOMEM       -4   /* device allocation failed                        */
+#define MCB200_EPACKET      -5   /* a packet hit one of the reference's `stop`s     */
+#define MCB200_EUNSUPPORTED -6   /* lgPlaneIonization / lg1D                        */
+#define MCB200_ETABLE       -7   /* CDF table not monotone / bad range              */
+
+typedef struct mcb200_ctx mcb200_ctx;   /* opaque */
+
+/* Global flags and scalars of common_mod read by photon_mod (set once, after
+ * setStarPosition, mocassin.f90:83).  Logical flags are 0/1. */
+typedef struct mcb200_config {
+    int32_t nGrids;                /* common_mod nGrids                                 */
+    int32_t nbins;                 /* number of frequency bins                          */
+    int32_t nStars;
+    int32_t nAngleBins;            /* viewing angles (`inclination` keyword)            */
+    int32_t totAngleBinsTheta;     /* common_mod.f90:399 (10)                           */
+    int32_t totAngleBinsPhi;       /* common_mod.f90:400 (20, or 1: grid_mod.f90:416-429)*/
+    int32_t nLines;                /* size of linePackets/linePDF 2nd dim (debug only)  */
+    int32_t lgDust, lgGas, lgSymmetricXYZ, lgIsotropic, lgPlaneIonization, lgDebug,
+            lgMultistars, lgMultiDustChemistry;
+    int32_t nSpeciesMax, nSizes, nDustComp;   /* Tdust / grainAbun extents              */
+    float dTheta, dPhi;            /* grid_mod.f90:416-431                              */
+    float R_out;                   /* outer radius [cm], 0 = unset                      */
+    float ionEdge1;                /* ionEdge(1) [Ryd]                                  */
+} mcb200_config;
+
+/* Counters of one transport call (photon_mod module variables Qphot, absInt,
+ * scaInt, trapped, photon_mod.f90:16,126,1702,1720,1803), as exact integers. */
+typedef struct mcb200_counters {
+    int64_t nPackets;              /* packets this rank transported                     */
+    int64_t nAbs, nSca;            /* absInt, scaInt                                    */
+    int64_t trapped;               /* recursionLimit hits                               */
+    int64_t nLinePackets;          /* packets that left as non-ionising line packets    */
+    int64_t nDropped;              /* safeLimit / outer-wall returns (no tally)         */
+    int64_t nSegments;             /* trips of the cell-crossing loop :1194             */
+    int64_t nFlights;              /* pathSegment calls                                 */
+    int64_t nEscaped;              /* escape tallies                                    */
+    int64_t nEarlyEscaped;         /* of which at energyPacketRun :370                  */
+    double  Qphot;                 /* sum deltaE/(2.1799153e-11*nu), nu>1 Ryd (:859-861)*/
+    double  kernel_ms;             /* device time of the transport kernel(s)            */
+} mcb200_counters;
+
+/* ---- lifecycle ---------------------------------------------------------------- */
+
+/* Create a context on CUDA device `device` for rank `rank` of `nranks`
+ * (replaces nothing in the reference; called where mocassin.f90:54-56 has
+ * mpi_comm_rank/size).  `seed` keys the Philox4x32-10 packet streams (the reference
+ * reseeds from the wall clock, photon_mod.f90:68-87). */
+int mcb200_create(mcb200_ctx **ctx, int32_t device, int32_t rank, int32_t nranks, uint64_t seed);
+int mcb200_destroy(mcb200_ctx *ctx);                 /* before mpi_finalize         */
+const char *mcb200_last_error(const mcb200_ctx *ctx);
+int mcb200_set_config(mcb200_ctx *ctx, const mcb200_config *cfg);
+
+/* ---- static inputs -------------------------------------------------------------- */
+
+/* Geometry of grid iG (1-based): grid_type members nx,ny,nz,nCells,motherP,
+ * xAxis,yAxis,zAxis,active (common_mod.f90:241-302) as built by fillGrid /
+ * setMotherGrid / setSubGrids (grid_mod.f90:488,898,1804).  active(nx,ny,nz) int32,
+ * x fastest.  geoCorr is recomputed as in grid_mod.f90:809-812. */
+int mcb200_set_grid(mcb200_ctx *ctx, int32_t iG, int32_t nx, int32_t ny, int32_t nz,
+                    int32_t nCells, int32_t motherP, const float *xAxis, const float *yAxis,
+                    const float *zAxis, const int32_t *active);
+
+/* Frequency-indexed globals: nuArray(nbins), gSca(nbins) (may be NULL without dust),
+ * inSpectrumProbDen(0:nStars,nbins) (Fortran layout, star index fastest),
+ * deltaE is passed per transport call. */
+int mcb200_set_spectra(mcb200_ctx *ctx, const float *nuArray, const float *gSca,
+                       const float *inSpectrumProbDen);
+
+/* starPosition(nStars) as x,y,z triplets [cm] and starIndeces(nStars,4) (Fortran
+ * layout, star index fastest) from setStarPosition (grid_mod.f90:3569-3648). */
+int mcb200_set_stars(mcb200_ctx *ctx, const float *starPosition, const int32_t *starIndeces);
+
+/* Viewing-angle tables of initCartesianGrid (grid_mod.f90:433-468):
+ * viewPointPtheta(0:totAngleBinsTheta), viewPointPphi(0:totAngleBinsPhi),
+ * viewPointTheta(0:nAngleBins), viewPointPhi(0:nAngleBins).  Only needed when
+ * nAngleBins>0. */
+int mcb200_set_viewpoints(mcb200_ctx *ctx, const int32_t *viewPointPtheta,
+                          const int32_t *viewPointPphi, const float *viewPointTheta,
+                          const float *viewPointPhi);
+
+/* Dust species tables used by the sublimation test at scattering
+ * (photon_mod.f90:1722-1748): nSpeciesPart(nDustComp), grainAbun(nDustComp,
+ * nSpeciesMax), dustComPoint(nDustComp), TdustSublime(nSpecies). */
+int mcb200_set_dust_species(mcb200_ctx *ctx, const int32_t *nSpeciesPart, const float *grainAbun,
+                            const int32_t *dustComPoint, const float *TdustSublime,
+                            int32_t nSpecies);
+
+/* ---- per-iteration inputs --------------------------------------------------------- */
+
+/* Host-assembled opacities of grid iG: opacity, scaOpac (0:nCells,nbins)
+ * (scaOpac may be NULL without dust).  Use instead of mcb200_assemble_opacity when
+ * the host keeps ionizationDriver (iteration_mod.f90:117-227). */
+int mcb200_set_opacity(mcb200_ctx *ctx, int32_t iG, const float *opacity, const float *scaOpac);
+
+/* Device opacity assembly (K1), replaces the ionizationDriver loop + dust add of
+ * iteration_mod.f90:117-227 for grid iG:
+ *   opacity(c,nu) = ff1(c)*[nu==1] + sum_b den(c, bandSpecies(b)) * xSec(nu + bandOff(b))
+ *                   for bandLow(b) <= nu <= min(bandHigh(b),nbins)
+ *                 + scaOpac(c,nu) + absOpac(c,nu)
+ *   scaOpac/absOpac(c,nu) = sum_{s,a: Tdust(s,a,c)<TdustSublime(s)} grainAbun*grainWeight(a)
+ *                            *Ndust(c)*xSec(dustSca/AbsXsecP(s,a)+nu-1)
+ * The band list is the flattened (species,shell) list of addOpacity
+ * (ionization_mod.f90:396-443): bandSpecies(b) indexes columns of den
+ * (0:nCells, nSpeciesDen), i.e. density(elem,ion)=ionDen*elemAbun*Hden of
+ * ionization_mod.f90:65-80.  ff1 (0:nCells) is the bin-1 free-free opacity of
+ * addOpacity :369-393 (the only bin the reference ever fills), computed by the host's
+ * BoltGaunt so its cell-order-dependent Gaunt-factor cache is preserved. All band
+ * indices are 1-based Fortran values; xSecArray is passed once with its length. */
+int mcb200_set_xsec(mcb200_ctx *ctx, const float *xSecArray, int64_t nXsec);
+int mcb200_assemble_opacity(mcb200_ctx *ctx, int32_t iG,
+                            int32_t nBands, const int32_t *bandSpecies, const int32_t *bandOff,
+                            const int32_t *bandLow, const int32_t *bandHigh,
+                            int32_t nSpeciesDen, const float *den, const float *ff1,
+                            /* dust part, all NULL/0 without dust */
+                            const float *Ndust, const float *Tdust, const int32_t *dustAbunIndex,
+                            const float *grainWeight, const int32_t *dustScaXsecP,
+                            const int32_t *dustAbsXsecP, int32_t nSpeciesTot);
+/* Read back opacity / scaOpac / absOpac (0:nCells,nbins) of grid iG (any may be NULL). */
+int mcb200_get_opacity(mcb200_ctx *ctx, int32_t iG, float *opacity, float *scaOpac, float *absOpac);
+
+/* Re-emission tables of grid iG built by emissionDriver (iteration_mod.f90:279-424):
+ * recPDF or dustPDF (0:nCells,nbins), totalLines(0:nCells) (NULL for dust-only),
+ * linePDF (0:nCells,nLines) (debug only, else NULL).  Tables must be non-decreasing
+ * along nu (they are cumulative sums); MCB200_ETABLE otherwise. */
+int mcb200_set_pdfs(mcb200_ctx *ctx, int32_t iG, const float *recPDF, const float *dustPDF,
+                    const float *totalLines, const float *linePDF);
+
+/* Dust temperatures Tdust(0:nSpeciesMax,0:nSizes,0:nCells) and dustAbunIndex(0:nCells)
+ * of grid iG, read by the sublimation test at scattering. */
+int mcb200_set_dust_state(mcb200_ctx *ctx, int32_t iG, const float *Tdust,
+                          const int32_t *dustAbunIndex);
+
+/* ---- the hot path ------------------------------------------------------------------ */
+
+/* Zero Jste, Jdif, linePackets, escapedPackets of all grids
+ * (iteration_mod.f90:458-472). */
+int mcb200_zero_estimators(mcb200_ctx *ctx);
+
+/* Transport.  Replaces `call energyPacketDriver(iStar, load, grid)` for all ranks
+ * (iteration_mod.f90:474-496): nPacketsGlobal is nPhotons(iStar); this rank takes
+ * the reference's share, load=int(N/nranks), +1 if rank<mod(N,nranks), with
+ * contiguous global packet ids, so results do not depend on nranks.
+ * deltaE is deltaE(iStar).  The path-length and escape tallies of this call are
+ * folded into the float32 estimators (Jste += L*deltaE/dV etc.) on return when
+ * nranks==1; with nranks>1 the integer tallies stay pending until
+ * mcb200_reduce (so the cross-rank sum is exact and order independent). */
+int mcb200_transport(mcb200_ctx *ctx, int32_t iStar, int64_t nPacketsGlobal, float deltaE,
+                     mcb200_counters *counters);
+
+/* Extra diffuse source, replaces `call energyPacketDriver(iStar=0, n=load, grid,
+ * gpLoc, cellLoc)` (iteration_mod.f90:498-550); deltaE is
+ * LdiffuseLoc(cell)/NphotonsDiffuseLoc (photon_mod.f90:64-66). */
+int mcb200_transport_diffuse(mcb200_ctx *ctx, int32_t gpLoc, const int32_t *cellLoc,
+                             int64_t nPacketsGlobal, float deltaE, mcb200_counters *counters);
+
+/* Device pointers and element counts of the pending integer tallies of grid iG so
+ * the caller's communicator can sum them across ranks (NCCL allreduce, int64 sum)
+ * -- replaces MPI_ALLREDUCE at iteration_mod.f90:627,649,653,659.  which: 0 JsteQ,
+ * 1 escapedQ, 2 JdifQ, 3 linePacketsQ. */
+int mcb200_tally_buffer(mcb200_ctx *ctx, int32_t iG, int32_t which, void **devPtr, int64_t *count);
+/* After the allreduce: fold the (now global) integer tallies of the last transport
+ * call into the float32 estimators. No-op when nothing is pending. */
+int mcb200_reduce(mcb200_ctx *ctx);
+
+/* Copy the raw estimator sums of grid iG into the caller's arrays, laid out as
+ * Jste(0:nCells,nbins), escapedPackets(0:nCells,0:nbins,0:nAngleBins),
+ * Jdif(0:nCells,nbins), linePackets(0:nCells,nLines) (NULL = skip).  These are the
+ * values the reference holds after its MPI_ALLREDUCE block (iteration_mod.f90:
+ * 583-703), *before* the host's own scaling (:705-724), which therefore stays
+ * unchanged.  Row 0 of Jste/Jdif (the inactive-cell sink, never read by the
+ * reference) is left zero. */
+int mcb200_fetch_estimators(mcb200_ctx *ctx, int32_t iG, float *Jste, float *escapedPackets,
+                            float *Jdif, float *linePackets);
+
+/* Diagnostics: raw integer tallies (same shapes as above, int64) and the
+ * path-length unit [cm] of grid iG's fixed-point J tally. */
+int mcb200_fetch_tallies(mcb200_ctx *ctx, int32_t iG, int64_t *JsteQ, int64_t *escapedQ,
+                         int64_t *JdifQ, int64_t *linePacketsQ);
+int mcb200_len_unit(mcb200_ctx *ctx, int32_t iG, double *lenUnit);
+/* Number of stellar emissions per frequency bin with nu>1 Ryd of the last transport
+ * call (Qphot = sum counts*deltaE/(2.1799153e-11*nu)). */
+int mcb200_fetch_qphot_counts(mcb200_ctx *ctx, int64_t *counts);
+/* Per-packet fate records of the last call (4 int32 each: segments, generations,
+ * last nuP, fate); enable with mcb200_set_option("trace",1) before transport. */
+int mcb200_fetch_fates(mcb200_ctx *ctx, int32_t *fates, int64_t nPackets);
+int mcb200_set_option(mcb200_ctx *ctx, const char *name, int64_t value);
+
+/* unit-test hooks: run device primitives on n inputs (host arrays in/out). */
+int mcb200_test_detmath(mcb200_ctx *ctx, int32_t which, const float *in, float *out, int64_t n);
+int mcb200_test_uniforms(mcb200_ctx *ctx, uint64_t seed, uint64_t pid, uint32_t stream,
+                         int32_t n, float *out);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* MCB200_H */

@@ -1,0 +1,87 @@
+"""ctypes binding of the C ABI in include/mcb200.h (no torch types cross it)."""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(HERE, "libmocassin_b200.so")
+
+c_float_p = C.POINTER(C.c_float)
+c_int32_p = C.POINTER(C.c_int32)
+c_int64_p = C.POINTER(C.c_int64)
+
+
+class Config(C.Structure):
+    _fields_ = [(n, C.c_int32) for n in (
+        "nGrids", "nbins", "nStars", "nAngleBins", "totAngleBinsTheta", "totAngleBinsPhi", "nLines",
+        "lgDust", "lgGas", "lgSymmetricXYZ", "lgIsotropic", "lgPlaneIonization", "lgDebug",
+        "lgMultistars", "lgMultiDustChemistry", "nSpeciesMax", "nSizes", "nDustComp")] + [
+        (n, C.c_float) for n in ("dTheta", "dPhi", "R_out", "ionEdge1")]
+
+
+class Counters(C.Structure):
+    _fields_ = [(n, C.c_int64) for n in (
+        "nPackets", "nAbs", "nSca", "trapped", "nLinePackets", "nDropped", "nSegments", "nFlights",
+        "nEscaped", "nEarlyEscaped")] + [("Qphot", C.c_double), ("kernel_ms", C.c_double)]
+
+    def as_dict(self):
+        return {n: getattr(self, n) for n, _ in self._fields_}
+
+
+_SIGS = {
+    "mcb200_create": [C.POINTER(C.c_void_p), C.c_int32, C.c_int32, C.c_int32, C.c_uint64],
+    "mcb200_destroy": [C.c_void_p],
+    "mcb200_set_config": [C.c_void_p, C.POINTER(Config)],
+    "mcb200_set_grid": [C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32,
+                        c_float_p, c_float_p, c_float_p, c_int32_p],
+    "mcb200_set_spectra": [C.c_void_p, c_float_p, c_float_p, c_float_p],
+    "mcb200_set_stars": [C.c_void_p, c_float_p, c_int32_p],
+    "mcb200_set_viewpoints": [C.c_void_p, c_int32_p, c_int32_p, c_float_p, c_float_p],
+    "mcb200_set_dust_species": [C.c_void_p, c_int32_p, c_float_p, c_int32_p, c_float_p, C.c_int32],
+    "mcb200_set_opacity": [C.c_void_p, C.c_int32, c_float_p, c_float_p],
+    "mcb200_set_xsec": [C.c_void_p, c_float_p, C.c_int64],
+    "mcb200_assemble_opacity": [C.c_void_p, C.c_int32, C.c_int32, c_int32_p, c_int32_p, c_int32_p, c_int32_p,
+                                C.c_int32, c_float_p, c_float_p, c_float_p, c_float_p, c_int32_p, c_float_p,
+                                c_int32_p, c_int32_p, C.c_int32],
+    "mcb200_get_opacity": [C.c_void_p, C.c_int32, c_float_p, c_float_p, c_float_p],
+    "mcb200_set_pdfs": [C.c_void_p, C.c_int32, c_float_p, c_float_p, c_float_p, c_float_p],
+    "mcb200_set_dust_state": [C.c_void_p, C.c_int32, c_float_p, c_int32_p],
+    "mcb200_zero_estimators": [C.c_void_p],
+    "mcb200_transport": [C.c_void_p, C.c_int32, C.c_int64, C.c_float, C.POINTER(Counters)],
+    "mcb200_transport_diffuse": [C.c_void_p, C.c_int32, c_int32_p, C.c_int64, C.c_float, C.POINTER(Counters)],
+    "mcb200_tally_buffer": [C.c_void_p, C.c_int32, C.c_int32, C.POINTER(C.c_void_p), c_int64_p],
+    "mcb200_reduce": [C.c_void_p],
+    "mcb200_fetch_estimators": [C.c_void_p, C.c_int32, c_float_p, c_float_p, c_float_p, c_float_p],
+    "mcb200_fetch_tallies": [C.c_void_p, C.c_int32, c_int64_p, c_int64_p, c_int64_p, c_int64_p],
+    "mcb200_len_unit": [C.c_void_p, C.c_int32, C.POINTER(C.c_double)],
+    "mcb200_fetch_qphot_counts": [C.c_void_p, c_int64_p],
+    "mcb200_fetch_fates": [C.c_void_p, c_int32_p, C.c_int64],
+    "mcb200_set_option": [C.c_void_p, C.c_char_p, C.c_int64],
+    "mcb200_test_detmath": [C.c_void_p, C.c_int32, c_float_p, c_float_p, C.c_int64],
+    "mcb200_test_uniforms": [C.c_void_p, C.c_uint64, C.c_uint64, C.c_uint32, C.c_int32, c_float_p],
+}
+
+EXPORTS = sorted(list(_SIGS) + ["mcb200_last_error"])
+
+_lib = None
+
+
+def load() -> C.CDLL:
+    """Load the CUDA library; there is no fallback -- a missing .so is an error."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise ImportError(
+            f"{LIB_PATH} is missing: build it with `python -m mocassin_b200.build` "
+            "(nvcc, sm_100a). mocassin_b200 has no CPU fallback.")
+    lib = C.CDLL(LIB_PATH)
+    for name, args in _SIGS.items():
+        fn = getattr(lib, name)
+        fn.argtypes = args
+        fn.restype = C.c_int
+    lib.mcb200_last_error.argtypes = [C.c_void_p]
+    lib.mcb200_last_error.restype = C.c_char_p
+    _lib = lib
+    return lib

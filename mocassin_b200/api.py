@@ -1,0 +1,350 @@
+"""Host-side mirror of the reference's interface to the transport hot path.
+
+The reference's seam is a handful of Fortran calls inside ``iterateMC``
+(``source/iteration_mod.f90``); :class:`PacketEngine` exposes the same operations with
+the same names, argument meaning and error behaviour, on top of the C ABI
+(``include/mcb200.h``):
+
+=============================================  ==========================================
+reference                                      here
+=============================================  ==========================================
+``call ionizationDriver`` loop + dust add      :meth:`PacketEngine.assemble_opacity` /
+(iteration_mod.f90:117-227)                    :meth:`PacketEngine.set_opacity`
+recPDF/dustPDF/totalLines after emissionDriver :meth:`PacketEngine.set_pdfs`
+(:279-424)
+zero Jste/escapedPackets (:458-472)            :meth:`PacketEngine.zero_estimators`
+``call energyPacketDriver(iStar, load, grid)`` :meth:`PacketEngine.energyPacketDriver`
+(:474-550, photon_mod.f90:26)
+``MPI_ALLREDUCE`` block (:583-703)             :meth:`PacketEngine.reduce`
+copy back + scaling (:664-724)                 :meth:`PacketEngine.fetch` (raw sums) and
+                                               :func:`scale_estimators` (host scaling)
+=============================================  ==========================================
+
+Errors: the reference does ``print*; stop``; here every failing call raises
+:class:`MocassinError` carrying the library's message (the Fortran shim turns the
+same status codes into ``stop``).  There is no CPU fallback.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Optional
+
+import numpy as np
+
+from . import _lib
+from .model import F32, I32, Grid, Model
+
+
+class MocassinError(RuntimeError):
+    def __init__(self, code: int, msg: str):
+        super().__init__(f"mcb200 error {code}: {msg}")
+        self.code = code
+
+
+def _fp(a: Optional[np.ndarray]):
+    if a is None:
+        return None
+    assert a.dtype == np.float32
+    return a.ctypes.data_as(_lib.c_float_p)
+
+
+def _ip(a: Optional[np.ndarray]):
+    if a is None:
+        return None
+    assert a.dtype == np.int32
+    return a.ctypes.data_as(_lib.c_int32_p)
+
+
+def _lp(a: Optional[np.ndarray]):
+    if a is None:
+        return None
+    assert a.dtype == np.int64
+    return a.ctypes.data_as(_lib.c_int64_p)
+
+
+def _f(a, dtype=F32):
+    """Fortran-contiguous array of the given dtype (no copy when already so)."""
+    if a is None:
+        return None
+    return np.asfortranarray(a, dtype=dtype)
+
+
+def partition(n_global: int, rank: int, nranks: int) -> tuple[int, int]:
+    """The reference's packet split over MPI ranks (iteration_mod.f90:477-493):
+    ``load=int(n/numtasks)``, ranks below ``mod(n,numtasks)`` take one more.
+    Returns (first global packet id, count) of `rank`; ids are contiguous per rank so the
+    Philox streams, and therefore the results, do not depend on `nranks`."""
+    load, rest = divmod(int(n_global), int(nranks))
+    mine = load + (1 if rank < rest else 0)
+    first = rank * load + min(rank, rest)
+    return first, mine
+
+
+class PacketEngine:
+    """One rank's (one GPU's) transport engine for a :class:`Model`."""
+
+    def __init__(self, model: Model, device: int = 0, rank: int = 0, nranks: int = 1, seed: int = 12345):
+        self.lib = _lib.load()
+        self.model = model
+        self.rank, self.nranks = rank, nranks
+        h = C.c_void_p()
+        rc = self.lib.mcb200_create(C.byref(h), device, rank, nranks, C.c_uint64(seed))
+        if rc != 0:
+            raise MocassinError(rc, "mcb200_create failed (no CUDA device? this library has no CPU fallback)")
+        self.h = h
+        self._keep = []
+        self._upload_static()
+
+    # -- plumbing ---------------------------------------------------------------------
+    def _check(self, rc: int):
+        if rc != 0:
+            raise MocassinError(rc, self.lib.mcb200_last_error(self.h).decode())
+
+    def close(self):
+        if getattr(self, "h", None):
+            self.lib.mcb200_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def set_option(self, name: str, value: int):
+        self._check(self.lib.mcb200_set_option(self.h, name.encode(), int(value)))
+
+    # -- static inputs ------------------------------------------------------------------
+    def _upload_static(self):
+        m = self.model
+        at = m.angle_tables()
+        cfg = _lib.Config(
+            nGrids=m.nGrids, nbins=m.nbins, nStars=m.nStars, nAngleBins=m.nAngleBins,
+            totAngleBinsTheta=at["totAngleBinsTheta"], totAngleBinsPhi=at["totAngleBinsPhi"],
+            nLines=m.nLines, lgDust=int(m.lgDust), lgGas=int(m.lgGas),
+            lgSymmetricXYZ=int(m.lgSymmetricXYZ), lgIsotropic=int(m.lgIsotropic),
+            lgPlaneIonization=int(m.lgPlaneIonization), lgDebug=int(m.lgDebug),
+            lgMultistars=int(m.lgMultistars), lgMultiDustChemistry=int(m.lgMultiDustChemistry),
+            nSpeciesMax=m.nSpeciesMax, nSizes=m.nSizes, nDustComp=int(m.nSpeciesPart.shape[0]),
+            dTheta=float(at["dTheta"]), dPhi=float(at["dPhi"]), R_out=float(m.R_out),
+            ionEdge1=float(m.ionEdge1))
+        self._check(self.lib.mcb200_set_config(self.h, C.byref(cfg)))
+        for i, g in enumerate(m.grids, start=1):
+            act = _f(g.active, I32)
+            self._check(self.lib.mcb200_set_grid(
+                self.h, i, g.nx, g.ny, g.nz, g.nCells, g.motherP,
+                _fp(_f(g.xAxis)), _fp(_f(g.yAxis)), _fp(_f(g.zAxis)), _ip(act)))
+        cdf = _f(np.asarray(m.inSpectrumProbDen, dtype=F32))      # (0:nStars, nbins) star fastest
+        self._check(self.lib.mcb200_set_spectra(self.h, _fp(_f(m.nuArray)),
+                                                _fp(_f(m.gSca)) if m.gSca is not None else None, _fp(cdf)))
+        if m.nStars > 0:
+            pos = np.ascontiguousarray(m.starPosition, dtype=F32)     # x,y,z triplets per star
+            idx = _f(np.asarray(m.starIndeces, dtype=I32))            # (nStars,4) star fastest
+            self._check(self.lib.mcb200_set_stars(self.h, _fp(pos), _ip(idx)))
+        if m.nAngleBins > 0:
+            self._check(self.lib.mcb200_set_viewpoints(
+                self.h, _ip(at["viewPointPtheta"]), _ip(at["viewPointPphi"]),
+                _fp(at["viewPointTheta"]), _fp(at["viewPointPhi"])))
+        if m.lgDust:
+            self._check(self.lib.mcb200_set_dust_species(
+                self.h, _ip(_f(m.nSpeciesPart, I32)), _fp(_f(m.grainAbun)), _ip(_f(m.dustComPoint, I32)),
+                _fp(_f(m.TdustSublime)), int(m.TdustSublime.shape[0])))
+
+    # -- per-iteration inputs -----------------------------------------------------------
+    def set_opacity(self, iG: int = 0):
+        """Upload host-assembled ``opacity``/``scaOpac`` (all grids when iG==0)."""
+        for i, g in self._grids(iG):
+            self._check(self.lib.mcb200_set_opacity(self.h, i, _fp(_f(g.opacity)),
+                                                    _fp(_f(g.scaOpac)) if self.model.lgDust else None))
+
+    def set_pdfs(self, iG: int = 0):
+        m = self.model
+        for i, g in self._grids(iG):
+            self._check(self.lib.mcb200_set_pdfs(
+                self.h, i,
+                _fp(_f(g.recPDF)) if m.lgGas else None,
+                _fp(_f(g.dustPDF)) if not m.lgGas else None,
+                _fp(_f(g.totalLines)) if m.lgGas else None,
+                _fp(_f(g.linePDF)) if (m.lgDebug and m.lgGas) else None))
+
+    def set_dust_state(self, iG: int = 0):
+        m = self.model
+        if not m.lgDust:
+            return
+        for i, g in self._grids(iG):
+            self._check(self.lib.mcb200_set_dust_state(
+                self.h, i, _fp(_f(g.Tdust)),
+                _ip(_f(g.dustAbunIndex, I32)) if g.dustAbunIndex is not None else None))
+
+    def upload_iteration_inputs(self):
+        self.set_opacity()
+        self.set_pdfs()
+        self.set_dust_state()
+
+    def set_xsec(self, xSecArray: np.ndarray):
+        x = _f(xSecArray)
+        self._check(self.lib.mcb200_set_xsec(self.h, _fp(x), int(x.shape[0])))
+
+    def assemble_opacity(self, iG: int, bands, den: np.ndarray, ff1: Optional[np.ndarray] = None, dust=None):
+        """K1 on device.  `bands` = dict(species, off, low, high) int32 arrays (1-based
+        Fortran values as in addOpacity); `den` (nCells+1, nSpeciesDen) F-order; `dust` =
+        dict(Ndust, Tdust, dustAbunIndex, grainWeight, dustScaXsecP, dustAbsXsecP) or None."""
+        sp, off, lo, hi = (_f(bands[k], I32) for k in ("species", "off", "low", "high"))
+        den = _f(den)
+        nsd = int(den.shape[1]) if den.ndim == 2 else 0
+        d = dust or {}
+        nTot = int(np.asarray(d["dustScaXsecP"]).shape[0]) if dust else 0
+        self._check(self.lib.mcb200_assemble_opacity(
+            self.h, iG, int(sp.shape[0]), _ip(sp), _ip(off), _ip(lo), _ip(hi), nsd, _fp(den),
+            _fp(_f(ff1)) if ff1 is not None else None,
+            _fp(_f(d["Ndust"])) if dust else None, _fp(_f(d["Tdust"])) if dust else None,
+            _ip(_f(d["dustAbunIndex"], I32)) if dust and d.get("dustAbunIndex") is not None else None,
+            _fp(_f(d["grainWeight"])) if dust else None,
+            _ip(_f(d["dustScaXsecP"], I32)) if dust else None,
+            _ip(_f(d["dustAbsXsecP"], I32)) if dust else None, nTot))
+
+    def get_opacity(self, iG: int, want_abs: bool = False):
+        g = self.model.grids[iG - 1]
+        shape = (g.nCells + 1, self.model.nbins)
+        op = np.zeros(shape, dtype=F32, order="F")
+        sca = np.zeros(shape, dtype=F32, order="F") if self.model.lgDust else None
+        ab = np.zeros(shape, dtype=F32, order="F") if want_abs else None
+        self._check(self.lib.mcb200_get_opacity(self.h, iG, _fp(op), _fp(sca) if sca is not None else None,
+                                                _fp(ab) if ab is not None else None))
+        return op, sca, ab
+
+    # -- the hot path -------------------------------------------------------------------
+    def zero_estimators(self):
+        self._check(self.lib.mcb200_zero_estimators(self.h))
+
+    def energyPacketDriver(self, iStar: int, n: int, gpLoc: Optional[int] = None, cellLoc=None,
+                           deltaE: Optional[float] = None) -> dict:
+        """``call energyPacketDriver(iStar, n, grid[, gpLoc, cellLoc])`` (photon_mod.f90:26)
+        for *all* ranks at once: `n` is the global packet count ``nPhotons(iStar)``, this
+        rank transports its :func:`partition` share."""
+        cnt = _lib.Counters()
+        if deltaE is None:
+            deltaE = float(self.model.deltaE[iStar])
+        if iStar >= 1:
+            rc = self.lib.mcb200_transport(self.h, iStar, int(n), C.c_float(deltaE), C.byref(cnt))
+        else:
+            cl = np.asarray(cellLoc, dtype=I32)
+            rc = self.lib.mcb200_transport_diffuse(self.h, int(gpLoc), _ip(cl), int(n), C.c_float(deltaE), C.byref(cnt))
+        self._check(rc)
+        return cnt.as_dict()
+
+    def tally_buffer(self, iG: int, which: int) -> tuple[int, int]:
+        p = C.c_void_p()
+        n = C.c_int64()
+        self._check(self.lib.mcb200_tally_buffer(self.h, iG, which, C.byref(p), C.byref(n)))
+        return int(p.value or 0), int(n.value)
+
+    def reduce(self, group=None):
+        """Sum the pending integer tallies over ranks (NCCL allreduce over NVLink,
+        replacing MPI_ALLREDUCE at iteration_mod.f90:627-659) and fold them into the
+        float32 estimators.  Exact integer sums -> identical bits on every rank and for
+        every rank count."""
+        if self.nranks > 1:
+            import torch
+            import torch.distributed as dist
+
+            whichs = [0, 1] + ([2, 3] if self.model.lgDebug else [])
+            for iG in range(1, self.model.nGrids + 1):
+                for w in whichs:
+                    ptr, n = self.tally_buffer(iG, w)
+                    if n == 0:
+                        continue
+                    t = _as_cuda_tensor(ptr, n, torch.int64, self._device_index())
+                    dist.all_reduce(t, op=dist.ReduceOp.SUM, group=group)
+            torch.cuda.synchronize()
+        self._check(self.lib.mcb200_reduce(self.h))
+
+    def _device_index(self):
+        import torch
+
+        return torch.cuda.current_device()
+
+    def fetch(self, iG: int = 1, want=("Jste", "escapedPackets")) -> dict:
+        """Raw estimator sums in the reference's layouts (before the host scaling of
+        iteration_mod.f90:705-724)."""
+        m = self.model
+        g = m.grids[iG - 1]
+        out = {}
+        J = np.zeros((g.nCells + 1, m.nbins), dtype=F32, order="F") if "Jste" in want else None
+        E = np.zeros((g.nCells + 1, m.nbins + 1, m.nAngleBins + 1), dtype=F32, order="F") if "escapedPackets" in want else None
+        D = np.zeros((g.nCells + 1, m.nbins), dtype=F32, order="F") if "Jdif" in want else None
+        Lp = np.zeros((g.nCells + 1, max(m.nLines, 1)), dtype=F32, order="F") if "linePackets" in want else None
+        self._check(self.lib.mcb200_fetch_estimators(self.h, iG, _fp(J), _fp(E), _fp(D), _fp(Lp)))
+        for k, v in (("Jste", J), ("escapedPackets", E), ("Jdif", D), ("linePackets", Lp)):
+            if v is not None:
+                out[k] = v
+        return out
+
+    def fetch_tallies(self, iG: int = 1) -> dict:
+        m = self.model
+        g = m.grids[iG - 1]
+        JQ = np.zeros((g.nCells + 1, m.nbins), dtype=np.int64, order="F")
+        EQ = np.zeros((g.nCells + 1, m.nbins + 1, m.nAngleBins + 1), dtype=np.int64, order="F")
+        DQ = np.zeros((g.nCells + 1, m.nbins), dtype=np.int64, order="F") if m.lgDebug else None
+        LQ = np.zeros((g.nCells + 1, max(m.nLines, 1)), dtype=np.int64, order="F") if m.lgDebug else None
+        self._check(self.lib.mcb200_fetch_tallies(self.h, iG, _lp(JQ), _lp(EQ), _lp(DQ), _lp(LQ)))
+        return dict(JsteQ=JQ, escapedQ=EQ, JdifQ=DQ, linePacketsQ=LQ)
+
+    def len_unit(self, iG: int = 1) -> float:
+        v = C.c_double()
+        self._check(self.lib.mcb200_len_unit(self.h, iG, C.byref(v)))
+        return float(v.value)
+
+    def qphot_counts(self) -> np.ndarray:
+        q = np.zeros(self.model.nbins, dtype=np.int64)
+        self._check(self.lib.mcb200_fetch_qphot_counts(self.h, _lp(q)))
+        return q
+
+    def fates(self, n: int) -> np.ndarray:
+        f = np.zeros((n, 4), dtype=I32)
+        self._check(self.lib.mcb200_fetch_fates(self.h, _ip(f), int(n)))
+        return f
+
+    def _grids(self, iG: int):
+        if iG:
+            return [(iG, self.model.grids[iG - 1])]
+        return list(enumerate(self.model.grids, start=1))
+
+    # -- the packet loop of iterateMC (iteration_mod.f90:458-726) -----------------------
+    def lucy_transport(self, nPhotons, group=None) -> list[dict]:
+        """zero estimators; for every star energyPacketDriver; reduce.  `nPhotons[i]` is
+        the global packet count of star i+1."""
+        self.zero_estimators()
+        out = []
+        for iStar in range(1, self.model.nStars + 1):
+            out.append(self.energyPacketDriver(iStar, int(nPhotons[iStar - 1])))
+            if self.nranks > 1:
+                self.reduce(group)
+        if self.nranks == 1:
+            self.reduce()
+        return out
+
+
+def _as_cuda_tensor(ptr: int, n: int, dtype, device_index: int):
+    """Wrap a raw device pointer as a torch tensor (no copy) via __cuda_array_interface__."""
+    import torch
+
+    class _Holder:
+        pass
+
+    h = _Holder()
+    h.__cuda_array_interface__ = {
+        "shape": (n,), "typestr": "<i8", "data": (ptr, False), "version": 3, "strides": None,
+    }
+    return torch.as_tensor(h, device=f"cuda:{device_index}")
+
+
+def scale_estimators(model: Model, Jste: np.ndarray, escapedPackets: np.ndarray):
+    """The host's own post-scaling, iteration_mod.f90:705-724 (unchanged by this work):
+    ``Jste*1e-9``, ``/8`` for symmetricXYZ (also escapedPackets)."""
+    J = (Jste * F32(1.0e-9)).astype(F32)
+    E = escapedPackets.copy()
+    if model.lgSymmetricXYZ:
+        J = (J / F32(8.0)).astype(F32)
+        E = (E / F32(8.0)).astype(F32)
+    return J, E

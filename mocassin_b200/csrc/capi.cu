@@ -1,0 +1,981 @@
+// capi.cu -- the C ABI of libmocassin_b200.so (include/mcb200.h): context, device
+// memory, uploads in the reference's layouts, kernel launches, fold, downloads.
+#include "../../include/mcb200.h"
+#include "types.h"
+#include "detmath.cuh"
+#include "philox.cuh"
+
+#include <cuda_runtime.h>
+
+#include <cmath>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+namespace mcb {
+cudaError_t launch_transport(const TransportArgs &a, bool multi, int gridBlocks, cudaStream_t stream);
+int transport_blocks_per_sm(bool multi);
+cudaError_t launch_transpose_pdf(const float *src, float *dst, int nRows, int nb, cudaStream_t s);
+cudaError_t launch_check_monotone(const float *pdfT, int nRows, int nb, int *bad, cudaStream_t s);
+cudaError_t launch_fold_j(unsigned long long *Q, float *J, const float *dV, int nRows, size_t total,
+                          double lenUnit, float deltaE, int blocks, cudaStream_t s);
+cudaError_t launch_fold_count(unsigned long long *Q, float *E, size_t total, float deltaE, int blocks,
+                              cudaStream_t s);
+struct OpacityArgs {
+    int nRows, nb;
+    int nSpeciesDen;
+    const float *den;
+    const float *ff1;
+    const float *xSec;
+    const int *nuStart;
+    const int *nuBandSpecies;
+    const int *nuBandXs;
+    int nDustTerms;
+    const float *Ndust;
+    const unsigned char *dustOn;
+    const float *dustCoef;
+    const int *dustCompOfCell;
+    const int *dustTermOn;
+    const int *dustScaP, *dustAbsP;
+    float *opacity, *scaOpac, *absOpac;
+};
+cudaError_t launch_opacity(const OpacityArgs &A, cudaStream_t s);
+}  // namespace mcb
+
+using namespace mcb;
+
+namespace {
+
+template <typename T>
+struct DevBuf {
+    T *p = nullptr;
+    size_t n = 0;
+    cudaError_t alloc(size_t count)
+    {
+        if (p && n == count) return cudaSuccess;
+        release();
+        n = count;
+        if (count == 0) return cudaSuccess;
+        return cudaMalloc((void **)&p, count * sizeof(T));
+    }
+    cudaError_t upload(const T *h, size_t count, cudaStream_t s)
+    {
+        cudaError_t e = alloc(count);
+        if (e != cudaSuccess || count == 0) return e;
+        return cudaMemcpyAsync(p, h, count * sizeof(T), cudaMemcpyHostToDevice, s);
+    }
+    cudaError_t zero(cudaStream_t s) { return n ? cudaMemsetAsync(p, 0, n * sizeof(T), s) : cudaSuccess; }
+    void release()
+    {
+        if (p) cudaFree(p);
+        p = nullptr;
+        n = 0;
+    }
+    ~DevBuf() { release(); }
+};
+
+struct GridState {
+    bool set = false;
+    int nx = 0, ny = 0, nz = 0, nCells = 0, motherP = 0, dense = 0;
+    float geo[3] = {0, 0, 0};
+    int lenExp = 0;                       // path-length unit = 2^lenExp cm
+    std::vector<float> hx, hy, hz;        // host copies of the axes
+    std::vector<int> hactive;
+    DevBuf<float> xAxis, yAxis, zAxis, xWall, yWall, zWall;
+    DevBuf<int> active;
+    DevBuf<float> opacity, scaOpac, absOpac, pdfT, totalLines, linePDF, dV, stage;
+    DevBuf<unsigned char> canScatter;
+    DevBuf<unsigned long long> JsteQ, JdifQ, escQ, lineQ;
+    DevBuf<float> Jste, Jdif, esc, linePk;
+    bool haveOpacity = false, havePdf = false;
+};
+
+}  // namespace
+
+struct mcb200_ctx {
+    int device = 0, rank = 0, nranks = 1;
+    uint64_t seed = 0;
+    cudaStream_t stream = nullptr;
+    int numSMs = 0;
+    bool haveCfg = false;
+    mcb200_config cfg{};
+    std::vector<GridState> grids;
+    DevBuf<DevGrid> dGrids;
+    std::vector<DevGrid> hGrids;
+    bool gridsDirty = true;
+    DevBuf<float> nuArray, gSca, starCdf, starPos, vpTheta, vpPhi, xSec;
+    DevBuf<int> starIdx, starCell, vpPtheta, vpPphi;
+    std::vector<float> hNu, hStarPos;
+    std::vector<int> hStarIdx;
+    bool haveSpectra = false, haveStars = false, haveView = false;
+    // dust species tables (host)
+    std::vector<int> nSpeciesPart, dustComPoint;
+    std::vector<float> grainAbun, TdustSublime;
+    bool haveDustSpecies = false;
+    // work buffers
+    DevBuf<unsigned long long> nextPacket, counters, qphot;
+    DevBuf<int> errFlag, fates, flag;
+    bool trace = false;
+    int blocksPerSM = 0;                  // 0 = occupancy default
+    // pending fold
+    bool pending = false;
+    float pendingDeltaE = 0.f;
+    std::string err;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+};
+
+namespace {
+
+int fail(mcb200_ctx *c, int code, const char *fmt, ...)
+{
+    char buf[512];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof(buf), fmt, ap);
+    va_end(ap);
+    if (c) c->err = buf;
+    return code;
+}
+
+#define CU(call)                                                                              \
+    do {                                                                                      \
+        cudaError_t e__ = (call);                                                             \
+        if (e__ != cudaSuccess)                                                               \
+            return fail(ctx, e__ == cudaErrorMemoryAllocation ? MCB200_ENOMEM : MCB200_ENODEV, \
+                        "%s: %s", #call, cudaGetErrorString(e__));                            \
+    } while (0)
+
+#define NEED_CTX()                                   \
+    do {                                             \
+        if (!ctx) return MCB200_EINVAL;              \
+        cudaSetDevice(ctx->device);                  \
+    } while (0)
+
+GridState *grid_of(mcb200_ctx *ctx, int iG)
+{
+    if (!ctx->haveCfg || iG < 1 || iG > ctx->cfg.nGrids) return nullptr;
+    return &ctx->grids[iG - 1];
+}
+
+size_t tsize(const mcb200_ctx *ctx, const GridState &g) { return (size_t)(g.nCells + 1) * (size_t)ctx->cfg.nbins; }
+size_t esize(const mcb200_ctx *ctx, const GridState &g)
+{
+    return (size_t)(g.nCells + 1) * (size_t)(ctx->cfg.nbins + 1) * (size_t)(ctx->cfg.nAngleBins + 1);
+}
+size_t lsize(const mcb200_ctx *ctx, const GridState &g) { return (size_t)(g.nCells + 1) * (size_t)ctx->cfg.nLines; }
+
+// mid-point walls, same float32 expression as photon_mod.f90:1266 / :1281
+std::vector<float> make_walls(const std::vector<float> &a)
+{
+    size_t n = a.size();
+    std::vector<float> w(n + 1);
+    w[0] = a[0];
+    for (size_t i = 1; i < n; ++i) {
+        volatile float s = a[i] + a[i - 1];
+        w[i] = s / 2.f;
+    }
+    w[n] = a[n - 1];
+    return w;
+}
+
+// cell width / 1e15 per axis, photon_mod.f90:1469-1508
+std::vector<float> make_widths(const std::vector<float> &a, bool sym)
+{
+    size_t n = a.size();
+    std::vector<float> w(n, 0.f);
+    for (size_t i = 0; i < n; ++i) {
+        volatile float d;
+        if (i > 0 && i + 1 < n) { d = std::fabs(a[i + 1] - a[i - 1]); d = d / 2.f; }
+        else if (i == 0) { d = std::fabs(a[1] - a[0]); if (sym) d = d / 2.f; }
+        else d = std::fabs(a[n - 1] - a[n - 2]);
+        w[i] = d / 1.e15f;
+    }
+    return w;
+}
+
+int sync_grids(mcb200_ctx *ctx)
+{
+    if (!ctx->gridsDirty) return MCB200_OK;
+    int nG = ctx->cfg.nGrids;
+    ctx->hGrids.assign(nG, DevGrid{});
+    for (int i = 0; i < nG; ++i) {
+        GridState &g = ctx->grids[i];
+        DevGrid &d = ctx->hGrids[i];
+        d.nx = g.nx; d.ny = g.ny; d.nz = g.nz; d.nCells = g.nCells; d.motherP = g.motherP;
+        d.dense = g.dense;
+        d.geoX = g.geo[0]; d.geoY = g.geo[1]; d.geoZ = g.geo[2];
+        d.invLenUnit = std::ldexp(1.0f, -g.lenExp);
+        d.xAxis = g.xAxis.p; d.yAxis = g.yAxis.p; d.zAxis = g.zAxis.p;
+        d.xWall = g.xWall.p; d.yWall = g.yWall.p; d.zWall = g.zWall.p;
+        d.active = g.active.p;
+        d.opacity = g.opacity.p; d.scaOpac = g.scaOpac.p;
+        d.pdfT = g.pdfT.p; d.totalLines = g.totalLines.p; d.linePDF = g.linePDF.p;
+        d.canScatter = g.canScatter.p;
+        d.JsteQ = g.JsteQ.p; d.JdifQ = g.JdifQ.p; d.escQ = g.escQ.p; d.lineQ = g.lineQ.p;
+    }
+    CU(ctx->dGrids.upload(ctx->hGrids.data(), nG, ctx->stream));
+    CU(cudaStreamSynchronize(ctx->stream));
+    ctx->gridsDirty = false;
+    return MCB200_OK;
+}
+
+int ensure_estimators(mcb200_ctx *ctx, GridState &g)
+{
+    size_t ts = tsize(ctx, g), es = esize(ctx, g);
+    bool fresh = (g.JsteQ.n != ts);
+    if (!fresh) return MCB200_OK;
+    CU(g.JsteQ.alloc(ts)); CU(g.JsteQ.zero(ctx->stream));
+    CU(g.Jste.alloc(ts));  CU(g.Jste.zero(ctx->stream));
+    CU(g.escQ.alloc(es));  CU(g.escQ.zero(ctx->stream));
+    CU(g.esc.alloc(es));   CU(g.esc.zero(ctx->stream));
+    if (ctx->cfg.lgDebug) {
+        CU(g.JdifQ.alloc(ts)); CU(g.JdifQ.zero(ctx->stream));
+        CU(g.Jdif.alloc(ts));  CU(g.Jdif.zero(ctx->stream));
+        size_t ls = lsize(ctx, g);
+        CU(g.lineQ.alloc(ls)); CU(g.lineQ.zero(ctx->stream));
+        CU(g.linePk.alloc(ls)); CU(g.linePk.zero(ctx->stream));
+    }
+    ctx->gridsDirty = true;
+    return MCB200_OK;
+}
+
+int fold_pending(mcb200_ctx *ctx)
+{
+    if (!ctx->pending) return MCB200_OK;
+    int blocks = ctx->numSMs * 8;
+    for (auto &g : ctx->grids) {
+        size_t ts = tsize(ctx, g), es = esize(ctx, g);
+        double lenUnit = std::ldexp(1.0, g.lenExp);
+        CU(launch_fold_j(g.JsteQ.p, g.Jste.p, g.dV.p, g.nCells + 1, ts, lenUnit, ctx->pendingDeltaE, blocks, ctx->stream));
+        CU(launch_fold_count(g.escQ.p, g.esc.p, es, ctx->pendingDeltaE, blocks, ctx->stream));
+        if (ctx->cfg.lgDebug) {
+            CU(launch_fold_j(g.JdifQ.p, g.Jdif.p, g.dV.p, g.nCells + 1, ts, lenUnit, ctx->pendingDeltaE, blocks, ctx->stream));
+            if (g.lineQ.n) CU(launch_fold_count(g.lineQ.p, g.linePk.p, g.lineQ.n, ctx->pendingDeltaE, blocks, ctx->stream));
+        }
+    }
+    CU(cudaStreamSynchronize(ctx->stream));
+    ctx->pending = false;
+    return MCB200_OK;
+}
+
+int run_transport(mcb200_ctx *ctx, int iStar, int difGrid, const int32_t *cellLoc, int64_t nGlobal,
+                  float deltaE, mcb200_counters *out)
+{
+    const mcb200_config &cfg = ctx->cfg;
+    if (!ctx->haveCfg) return fail(ctx, MCB200_ESTATE, "mcb200_set_config not called");
+    if (cfg.lgPlaneIonization) return fail(ctx, MCB200_EUNSUPPORTED, "lgPlaneIonization is not supported");
+    if (!ctx->haveSpectra || !ctx->haveStars) return fail(ctx, MCB200_ESTATE, "spectra/stars not set");
+    if (cfg.nAngleBins > 0 && !ctx->haveView) return fail(ctx, MCB200_ESTATE, "viewpoints not set");
+    if (nGlobal < 0) return fail(ctx, MCB200_EINVAL, "negative packet count");
+    if (iStar < 0 || iStar > cfg.nStars) return fail(ctx, MCB200_EINVAL, "iStar out of range");
+    for (int i = 0; i < cfg.nGrids; ++i) {
+        GridState &g = ctx->grids[i];
+        if (!g.set) return fail(ctx, MCB200_ESTATE, "grid %d not set", i + 1);
+        if (!g.haveOpacity) return fail(ctx, MCB200_ESTATE, "opacity of grid %d not set", i + 1);
+        if (cfg.lgDust && !g.scaOpac.p) return fail(ctx, MCB200_ESTATE, "scaOpac of grid %d not set", i + 1);
+        if (cfg.lgDust && !g.canScatter.p) return fail(ctx, MCB200_ESTATE, "dust state of grid %d not set", i + 1);
+        if (!g.havePdf) return fail(ctx, MCB200_ESTATE, "re-emission PDFs of grid %d not set", i + 1);
+        int rc = ensure_estimators(ctx, g);
+        if (rc) return rc;
+    }
+    // a previous call with a different deltaE must be folded first (single rank), or
+    // reduced by the caller (multi rank)
+    if (ctx->pending) {
+        if (ctx->nranks == 1) { int rc = fold_pending(ctx); if (rc) return rc; }
+        else if (ctx->pendingDeltaE != deltaE)
+            return fail(ctx, MCB200_ESTATE, "pending tallies with a different deltaE: call mcb200_reduce first");
+    }
+    int rc = sync_grids(ctx);
+    if (rc) return rc;
+
+    // the reference's split over ranks, iteration_mod.f90:477-493
+    int64_t load = nGlobal / ctx->nranks, rest = nGlobal % ctx->nranks;
+    int64_t mine = load + (ctx->rank < rest ? 1 : 0);
+    int64_t first = (int64_t)ctx->rank * load + (ctx->rank < rest ? ctx->rank : rest);
+
+    TransportArgs a{};
+    DevParams &P = a.P;
+    P.nGrids = cfg.nGrids; P.nbins = cfg.nbins; P.nStars = cfg.nStars; P.nAngleBins = cfg.nAngleBins;
+    P.totT = cfg.totAngleBinsTheta; P.totP = cfg.totAngleBinsPhi; P.nLines = cfg.nLines;
+    P.lgDust = cfg.lgDust; P.lgGas = cfg.lgGas; P.lgSym = cfg.lgSymmetricXYZ; P.lgIso = cfg.lgIsotropic;
+    P.lgDebug = cfg.lgDebug; P.lgMultistars = cfg.lgMultistars;
+    P.dTheta = cfg.dTheta; P.dPhi = cfg.dPhi; P.R_out = cfg.R_out; P.ionEdge1 = cfg.ionEdge1;
+    P.nuArray = ctx->nuArray.p; P.gSca = ctx->gSca.p; P.starCdf = ctx->starCdf.p;
+    P.starPos = ctx->starPos.p; P.starIdx = ctx->starIdx.p; P.starCell = ctx->starCell.p;
+    P.vpPtheta = ctx->vpPtheta.p; P.vpPphi = ctx->vpPphi.p; P.vpTheta = ctx->vpTheta.p; P.vpPhi = ctx->vpPhi.p;
+    a.g1 = ctx->hGrids[0];
+    a.grids = ctx->dGrids.p;
+    a.iStar = iStar;
+    if (iStar == 0) {
+        if (!cellLoc || difGrid < 1 || difGrid > cfg.nGrids) return fail(ctx, MCB200_EINVAL, "bad diffuse source");
+        const GridState &g = ctx->grids[difGrid - 1];
+        if (cellLoc[0] < 1 || cellLoc[0] > g.nx || cellLoc[1] < 1 || cellLoc[1] > g.ny || cellLoc[2] < 1 || cellLoc[2] > g.nz)
+            return fail(ctx, MCB200_EINVAL, "diffuse source cell out of range");
+        a.difGrid = difGrid; a.difX = cellLoc[0]; a.difY = cellLoc[1]; a.difZ = cellLoc[2];
+    }
+    a.firstId = first; a.n = mine; a.seed = ctx->seed;
+    CU(ctx->nextPacket.alloc(1)); CU(ctx->nextPacket.zero(ctx->stream));
+    CU(ctx->counters.alloc(C_COUNT)); CU(ctx->counters.zero(ctx->stream));
+    CU(ctx->qphot.alloc(cfg.nbins)); CU(ctx->qphot.zero(ctx->stream));
+    CU(ctx->errFlag.alloc(1)); CU(ctx->errFlag.zero(ctx->stream));
+    a.nextPacket = ctx->nextPacket.p; a.counters = ctx->counters.p; a.qphotCounts = ctx->qphot.p;
+    a.errFlag = ctx->errFlag.p;
+    a.fates = nullptr;
+    if (ctx->trace) {
+        CU(ctx->fates.alloc((size_t)4 * (size_t)(mine > 0 ? mine : 1)));
+        CU(ctx->fates.zero(ctx->stream));
+        a.fates = ctx->fates.p;
+    }
+    bool multi = cfg.nGrids > 1;
+    int bps = ctx->blocksPerSM > 0 ? ctx->blocksPerSM : transport_blocks_per_sm(multi);
+    if (bps < 1) bps = 1;
+    int blocks = ctx->numSMs * bps;
+    int64_t maxUseful = (mine + 255) / 256;
+    if (maxUseful < 1) maxUseful = 1;
+    if (blocks > maxUseful) blocks = (int)maxUseful;
+
+    CU(cudaEventRecord(ctx->ev0, ctx->stream));
+    if (mine > 0) CU(launch_transport(a, multi, blocks, ctx->stream));
+    CU(cudaEventRecord(ctx->ev1, ctx->stream));
+    CU(cudaStreamSynchronize(ctx->stream));
+    float ms = 0.f;
+    CU(cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev1));
+
+    unsigned long long hc[C_COUNT];
+    int herr = 0;
+    CU(cudaMemcpy(hc, ctx->counters.p, sizeof(hc), cudaMemcpyDeviceToHost));
+    CU(cudaMemcpy(&herr, ctx->errFlag.p, sizeof(int), cudaMemcpyDeviceToHost));
+    if (out) {
+        std::vector<unsigned long long> q(cfg.nbins);
+        CU(cudaMemcpy(q.data(), ctx->qphot.p, sizeof(unsigned long long) * cfg.nbins, cudaMemcpyDeviceToHost));
+        double Q = 0.0;
+        for (int i = 0; i < cfg.nbins; ++i)
+            if (q[i]) Q += (double)q[i] * ((double)deltaE / (2.1799153e-11 * (double)ctx->hNu[i]));
+        out->nPackets = mine;
+        out->nAbs = (int64_t)hc[C_ABS]; out->nSca = (int64_t)hc[C_SCA]; out->trapped = (int64_t)hc[C_TRAPPED];
+        out->nLinePackets = (int64_t)hc[C_LINE]; out->nDropped = (int64_t)hc[C_DROPPED];
+        out->nSegments = (int64_t)hc[C_SEGMENTS]; out->nFlights = (int64_t)hc[C_FLIGHTS];
+        out->nEscaped = (int64_t)hc[C_ESCAPED]; out->nEarlyEscaped = (int64_t)hc[C_EARLY];
+        out->Qphot = Q;
+        out->kernel_ms = ms;
+    }
+    ctx->pending = true;
+    ctx->pendingDeltaE = deltaE;
+    if (herr) return fail(ctx, MCB200_EPACKET, "a packet hit reference stop condition %d (see oracle/mc_oracle.c ERR_STOP codes)", herr);
+    if (ctx->nranks == 1) return fold_pending(ctx);
+    return MCB200_OK;
+}
+
+__global__ void detmath_kernel(int which, const float *in, float *out, long long n)
+{
+    long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    float s, c;
+    switch (which) {
+    case 0: out[i] = dm_logf(in[i]); break;
+    case 1: dm_sincosf(in[i], s, c); out[i] = s; break;
+    case 2: dm_sincosf(in[i], s, c); out[i] = c; break;
+    case 3: out[i] = dm_acosf(in[i]); break;
+    case 4: out[i] = dm_atanf(in[i]); break;
+    default: out[i] = 0.f;
+    }
+}
+
+__global__ void uniforms_kernel(unsigned long long seed, unsigned long long pid, unsigned int stream, int n, float *out)
+{
+    if (threadIdx.x || blockIdx.x) return;
+    Rng r;
+    r.init(seed, pid, stream);
+    for (int i = 0; i < n; ++i) out[i] = r.uniform();
+}
+
+}  // namespace
+
+extern "C" {
+
+int mcb200_create(mcb200_ctx **pctx, int32_t device, int32_t rank, int32_t nranks, uint64_t seed)
+{
+    if (!pctx || nranks < 1 || rank < 0 || rank >= nranks) return MCB200_EINVAL;
+    *pctx = nullptr;
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev <= 0) return MCB200_ENODEV;
+    if (device < 0 || device >= ndev) return MCB200_ENODEV;
+    if (cudaSetDevice(device) != cudaSuccess) return MCB200_ENODEV;
+    mcb200_ctx *ctx = new mcb200_ctx();
+    ctx->device = device; ctx->rank = rank; ctx->nranks = nranks; ctx->seed = seed;
+    cudaDeviceProp prop;
+    if (cudaGetDeviceProperties(&prop, device) != cudaSuccess) { delete ctx; return MCB200_ENODEV; }
+    ctx->numSMs = prop.multiProcessorCount;
+    if (cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) != cudaSuccess) { delete ctx; return MCB200_ENODEV; }
+    cudaEventCreate(&ctx->ev0);
+    cudaEventCreate(&ctx->ev1);
+    *pctx = ctx;
+    return MCB200_OK;
+}
+
+int mcb200_destroy(mcb200_ctx *ctx)
+{
+    if (!ctx) return MCB200_EINVAL;
+    cudaSetDevice(ctx->device);
+    cudaStreamSynchronize(ctx->stream);
+    if (ctx->ev0) cudaEventDestroy(ctx->ev0);
+    if (ctx->ev1) cudaEventDestroy(ctx->ev1);
+    ctx->grids.clear();
+    cudaStream_t s = ctx->stream;
+    delete ctx;
+    if (s) cudaStreamDestroy(s);
+    return MCB200_OK;
+}
+
+const char *mcb200_last_error(const mcb200_ctx *ctx) { return ctx ? ctx->err.c_str() : "null context"; }
+
+int mcb200_set_config(mcb200_ctx *ctx, const mcb200_config *cfg)
+{
+    NEED_CTX();
+    if (!cfg) return fail(ctx, MCB200_EINVAL, "null config");
+    if (cfg->nGrids < 1 || cfg->nbins < 3 || cfg->nStars < 0 || cfg->nAngleBins < 0)
+        return fail(ctx, MCB200_EINVAL, "bad sizes in config");
+    if (cfg->lgPlaneIonization) return fail(ctx, MCB200_EUNSUPPORTED, "lgPlaneIonization is not supported");
+    if (cfg->totAngleBinsTheta < 1 || cfg->totAngleBinsPhi < 1 || !(cfg->dTheta > 0.f) || !(cfg->dPhi > 0.f))
+        return fail(ctx, MCB200_EINVAL, "bad angle bins in config");
+    ctx->cfg = *cfg;
+    ctx->grids.clear();
+    ctx->grids.resize(cfg->nGrids);
+    ctx->haveCfg = true;
+    ctx->gridsDirty = true;
+    ctx->pending = false;
+    return MCB200_OK;
+}
+
+int mcb200_set_grid(mcb200_ctx *ctx, int32_t iG, int32_t nx, int32_t ny, int32_t nz, int32_t nCells,
+                    int32_t motherP, const float *xAxis, const float *yAxis, const float *zAxis,
+                    const int32_t *active)
+{
+    NEED_CTX();
+    GridState *g = grid_of(ctx, iG);
+    if (!g) return fail(ctx, MCB200_EINVAL, "grid index %d out of range (set_config first)", iG);
+    if (nx < 2 || ny < 2 || nz < 2 || nCells < 0 || !xAxis || !yAxis || !zAxis || !active)
+        return fail(ctx, MCB200_EINVAL, "bad grid arguments");
+    if (iG > 1 && motherP != 1) return fail(ctx, MCB200_EUNSUPPORTED, "nested sub-grids (motherP != 1) are not supported (photon_mod.f90:2551-2554)");
+    g->nx = nx; g->ny = ny; g->nz = nz; g->nCells = nCells; g->motherP = motherP;
+    g->hx.assign(xAxis, xAxis + nx); g->hy.assign(yAxis, yAxis + ny); g->hz.assign(zAxis, zAxis + nz);
+    for (auto *ax : {&g->hx, &g->hy, &g->hz})
+        for (size_t i = 1; i < ax->size(); ++i)
+            if (!((*ax)[i] > (*ax)[i - 1])) return fail(ctx, MCB200_EINVAL, "grid %d: axes must be strictly ascending", iG);
+    size_t nTot = (size_t)nx * ny * nz;
+    g->hactive.assign(active, active + nTot);
+    // validate and detect the dense numbering (k fastest, grid_mod.f90:1227-1262)
+    int dense = 1;
+    for (int z = 0; z < nz && dense >= 0; ++z)
+        for (int y = 0; y < ny; ++y)
+            for (int x = 0; x < nx; ++x) {
+                int a = active[(size_t)x + (size_t)nx * ((size_t)y + (size_t)ny * (size_t)z)];
+                if (a > nCells) return fail(ctx, MCB200_EINVAL, "grid %d: active id %d > nCells", iG, a);
+                if (a < 0 && (iG != 1 || -a > ctx->cfg.nGrids || -a < 2))
+                    return fail(ctx, MCB200_EINVAL, "grid %d: bad sub-grid pointer %d in active", iG, a);
+                if (a != 1 + z + nz * (y + ny * x)) dense = 0;
+            }
+    g->dense = dense;
+    g->geo[0] = (g->hx[nx - 1] - g->hx[nx - 2]) / 2.f;
+    g->geo[1] = (g->hy[ny - 1] - g->hy[ny - 2]) / 2.f;
+    g->geo[2] = (g->hz[nz - 1] - g->hz[nz - 2]) / 2.f;
+    // path-length quantum: smallest cell width / 2^24, rounded down to a power of two
+    double wmin = 1e300;
+    for (auto *ax : {&g->hx, &g->hy, &g->hz})
+        for (size_t i = 1; i < ax->size(); ++i) wmin = std::fmin(wmin, (double)(*ax)[i] - (double)(*ax)[i - 1]);
+    wmin *= 0.5;
+    g->lenExp = (int)std::floor(std::log2(wmin)) - 24;
+    cudaStream_t s = ctx->stream;
+    CU(g->xAxis.upload(g->hx.data(), nx, s)); CU(g->yAxis.upload(g->hy.data(), ny, s)); CU(g->zAxis.upload(g->hz.data(), nz, s));
+    auto wx = make_walls(g->hx), wy = make_walls(g->hy), wz = make_walls(g->hz);
+    CU(g->xWall.upload(wx.data(), wx.size(), s)); CU(g->yWall.upload(wy.data(), wy.size(), s)); CU(g->zWall.upload(wz.data(), wz.size(), s));
+    CU(g->active.upload(g->hactive.data(), nTot, s));
+    // dV(0:nCells) in 1e45 cm^3 (photon_mod.f90:1469-1512)
+    bool sym = ctx->cfg.lgSymmetricXYZ != 0;
+    auto dxs = make_widths(g->hx, sym), dys = make_widths(g->hy, sym), dzs = make_widths(g->hz, sym);
+    std::vector<float> dV((size_t)nCells + 1, 1.f);
+    for (int z = 0; z < nz; ++z)
+        for (int y = 0; y < ny; ++y)
+            for (int x = 0; x < nx; ++x) {
+                int a = active[(size_t)x + (size_t)nx * ((size_t)y + (size_t)ny * (size_t)z)];
+                if (a > 0) {
+                    volatile float v = dxs[x] * dys[y];
+                    dV[a] = v * dzs[z];
+                }
+            }
+    CU(g->dV.upload(dV.data(), dV.size(), s));
+    CU(cudaStreamSynchronize(s));
+    g->set = true;
+    g->haveOpacity = false;
+    g->havePdf = false;
+    // (re)size estimator storage lazily
+    g->JsteQ.release(); g->Jste.release(); g->escQ.release(); g->esc.release();
+    g->JdifQ.release(); g->Jdif.release(); g->lineQ.release(); g->linePk.release();
+    ctx->gridsDirty = true;
+    return MCB200_OK;
+}
+
+int mcb200_set_spectra(mcb200_ctx *ctx, const float *nuArray, const float *gSca, const float *inSpectrumProbDen)
+{
+    NEED_CTX();
+    if (!ctx->haveCfg) return fail(ctx, MCB200_ESTATE, "set_config first");
+    if (!nuArray || !inSpectrumProbDen) return fail(ctx, MCB200_EINVAL, "null spectra");
+    int nb = ctx->cfg.nbins, ns = ctx->cfg.nStars + 1;
+    ctx->hNu.assign(nuArray, nuArray + nb);
+    CU(ctx->nuArray.upload(nuArray, nb, ctx->stream));
+    if (gSca) CU(ctx->gSca.upload(gSca, nb, ctx->stream));
+    else if (ctx->cfg.lgDust && !ctx->cfg.lgIsotropic) return fail(ctx, MCB200_EINVAL, "gSca required with dust");
+    // Fortran (0:nStars, nbins), star fastest -> rows [s][nu]; rows s>=1 must be non-decreasing
+    std::vector<float> rows((size_t)ns * nb);
+    for (int s = 0; s < ns; ++s)
+        for (int i = 0; i < nb; ++i) rows[(size_t)s * nb + i] = inSpectrumProbDen[(size_t)s + (size_t)ns * i];
+    for (int s = 1; s < ns; ++s)
+        for (int i = 1; i < nb; ++i)
+            if (!(rows[(size_t)s * nb + i] >= rows[(size_t)s * nb + i - 1]))
+                return fail(ctx, MCB200_ETABLE, "inSpectrumProbDen(%d,:) is not non-decreasing at bin %d", s, i + 1);
+    CU(ctx->starCdf.upload(rows.data(), rows.size(), ctx->stream));
+    CU(cudaStreamSynchronize(ctx->stream));
+    ctx->haveSpectra = true;
+    return MCB200_OK;
+}
+
+int mcb200_set_stars(mcb200_ctx *ctx, const float *starPosition, const int32_t *starIndeces)
+{
+    NEED_CTX();
+    if (!ctx->haveCfg) return fail(ctx, MCB200_ESTATE, "set_config first");
+    int ns = ctx->cfg.nStars;
+    if (ns > 0 && (!starPosition || !starIndeces)) return fail(ctx, MCB200_EINVAL, "null stars");
+    std::vector<int> idx((size_t)4 * (ns > 0 ? ns : 1), 1), cells(ns > 0 ? ns : 1, 0);
+    std::vector<float> pos((size_t)3 * (ns > 0 ? ns : 1), 0.f);
+    for (int i = 0; i < ns; ++i) {
+        for (int k = 0; k < 4; ++k) idx[4 * i + k] = starIndeces[(size_t)i + (size_t)ns * k];
+        for (int k = 0; k < 3; ++k) pos[3 * i + k] = starPosition[3 * i + k];
+        int gP = idx[4 * i + 3];
+        GridState *g = grid_of(ctx, gP);
+        if (!g || !g->set) return fail(ctx, MCB200_ESTATE, "star %d: grid %d not set", i + 1, gP);
+        int x = idx[4 * i], y = idx[4 * i + 1], z = idx[4 * i + 2];
+        if (x < 1 || x > g->nx || y < 1 || y > g->ny || z < 1 || z > g->nz)
+            return fail(ctx, MCB200_EINVAL, "star %d: indices outside grid %d", i + 1, gP);
+        cells[i] = g->hactive[(size_t)(x - 1) + (size_t)g->nx * ((size_t)(y - 1) + (size_t)g->ny * (size_t)(z - 1))];
+    }
+    ctx->hStarPos = pos; ctx->hStarIdx = idx;
+    CU(ctx->starPos.upload(pos.data(), pos.size(), ctx->stream));
+    CU(ctx->starIdx.upload(idx.data(), idx.size(), ctx->stream));
+    CU(ctx->starCell.upload(cells.data(), cells.size(), ctx->stream));
+    CU(cudaStreamSynchronize(ctx->stream));
+    ctx->haveStars = true;
+    return MCB200_OK;
+}
+
+int mcb200_set_viewpoints(mcb200_ctx *ctx, const int32_t *pT, const int32_t *pP, const float *vT, const float *vP)
+{
+    NEED_CTX();
+    if (!ctx->haveCfg) return fail(ctx, MCB200_ESTATE, "set_config first");
+    if (!pT || !pP || !vT || !vP) return fail(ctx, MCB200_EINVAL, "null viewpoint tables");
+    const mcb200_config &c = ctx->cfg;
+    for (int i = 0; i <= c.totAngleBinsTheta; ++i) if (pT[i] < 0 || pT[i] > c.nAngleBins) return fail(ctx, MCB200_EINVAL, "viewPointPtheta out of range");
+    for (int i = 0; i <= c.totAngleBinsPhi; ++i) if (pP[i] < 0 || pP[i] > c.nAngleBins) return fail(ctx, MCB200_EINVAL, "viewPointPphi out of range");
+    CU(ctx->vpPtheta.upload(pT, c.totAngleBinsTheta + 1, ctx->stream));
+    CU(ctx->vpPphi.upload(pP, c.totAngleBinsPhi + 1, ctx->stream));
+    CU(ctx->vpTheta.upload(vT, c.nAngleBins + 1, ctx->stream));
+    CU(ctx->vpPhi.upload(vP, c.nAngleBins + 1, ctx->stream));
+    CU(cudaStreamSynchronize(ctx->stream));
+    ctx->haveView = true;
+    return MCB200_OK;
+}
+
+int mcb200_set_dust_species(mcb200_ctx *ctx, const int32_t *nSpeciesPart, const float *grainAbun,
+                            const int32_t *dustComPoint, const float *TdustSublime, int32_t nSpecies)
+{
+    NEED_CTX();
+    if (!ctx->haveCfg) return fail(ctx, MCB200_ESTATE, "set_config first");
+    const mcb200_config &c = ctx->cfg;
+    if (!nSpeciesPart || !grainAbun || !dustComPoint || !TdustSublime || nSpecies < 1 || c.nDustComp < 1 || c.nSpeciesMax < 1)
+        return fail(ctx, MCB200_EINVAL, "bad dust species tables");
+    ctx->nSpeciesPart.assign(nSpeciesPart, nSpeciesPart + c.nDustComp);
+    ctx->dustComPoint.assign(dustComPoint, dustComPoint + c.nDustComp);
+    ctx->grainAbun.assign(grainAbun, grainAbun + (size_t)c.nDustComp * c.nSpeciesMax);
+    ctx->TdustSublime.assign(TdustSublime, TdustSublime + nSpecies);
+    for (int k = 0; k < c.nDustComp; ++k)
+        if (nSpeciesPart[k] < 0 || nSpeciesPart[k] > c.nSpeciesMax || dustComPoint[k] < 1 || dustComPoint[k] - 1 + nSpeciesPart[k] > nSpecies)
+            return fail(ctx, MCB200_EINVAL, "dust component %d inconsistent", k + 1);
+    ctx->haveDustSpecies = true;
+    return MCB200_OK;
+}
+
+int mcb200_set_opacity(mcb200_ctx *ctx, int32_t iG, const float *opacity, const float *scaOpac)
+{
+    NEED_CTX();
+    GridState *g = grid_of(ctx, iG);
+    if (!g || !g->set) return fail(ctx, MCB200_ESTATE, "grid %d not set", iG);
+    if (!opacity) return fail(ctx, MCB200_EINVAL, "null opacity");
+    size_t ts = tsize(ctx, *g);
+    bool re = (g->opacity.n != ts) || (scaOpac && g->scaOpac.n != ts);
+    CU(g->opacity.upload(opacity, ts, ctx->stream));
+    if (scaOpac) CU(g->scaOpac.upload(scaOpac, ts, ctx->stream));
+    CU(cudaStreamSynchronize(ctx->stream));
+    g->haveOpacity = true;
+    if (re) ctx->gridsDirty = true;
+    return MCB200_OK;
+}
+
+int mcb200_set_pdfs(mcb200_ctx *ctx, int32_t iG, const float *recPDF, const float *dustPDF,
+                    const float *totalLines, const float *linePDF)
+{
+    NEED_CTX();
+    GridState *g = grid_of(ctx, iG);
+    if (!g || !g->set) return fail(ctx, MCB200_ESTATE, "grid %d not set", iG);
+    const mcb200_config &c = ctx->cfg;
+    const float *src = c.lgGas ? recPDF : dustPDF;
+    if (!src) return fail(ctx, MCB200_EINVAL, "%s required", c.lgGas ? "recPDF" : "dustPDF");
+    if (c.lgGas && !totalLines) return fail(ctx, MCB200_EINVAL, "totalLines required with gas");
+    if (c.lgDebug && c.lgGas && !linePDF) return fail(ctx, MCB200_EINVAL, "linePDF required in debug mode");
+    size_t ts = tsize(ctx, *g);
+    int nRows = g->nCells + 1;
+    bool re = (g->pdfT.n != ts);
+    CU(g->stage.upload(src, ts, ctx->stream));
+    CU(g->pdfT.alloc(ts));
+    CU(launch_transpose_pdf(g->stage.p, g->pdfT.p, nRows, c.nbins, ctx->stream));
+    CU(ctx->flag.alloc(1)); CU(ctx->flag.zero(ctx->stream));
+    CU(launch_check_monotone(g->pdfT.p, nRows, c.nbins, ctx->flag.p, ctx->stream));
+    int bad = 0;
+    CU(cudaMemcpyAsync(&bad, ctx->flag.p, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+    CU(cudaStreamSynchronize(ctx->stream));
+    g->stage.release();
+    if (bad) { g->havePdf = false; return fail(ctx, MCB200_ETABLE, "grid %d: re-emission PDF is not non-decreasing along nu", iG); }
+    if (c.lgGas) {
+        if (g->totalLines.n != (size_t)nRows) re = true;
+        CU(g->totalLines.upload(totalLines, nRows, ctx->stream));
+    }
+    if (c.lgDebug && c.lgGas) {
+        if (g->linePDF.n != lsize(ctx, *g)) re = true;
+        CU(g->linePDF.upload(linePDF, lsize(ctx, *g), ctx->stream));
+    }
+    CU(cudaStreamSynchronize(ctx->stream));
+    g->havePdf = true;
+    if (re) ctx->gridsDirty = true;
+    return MCB200_OK;
+}
+
+int mcb200_set_dust_state(mcb200_ctx *ctx, int32_t iG, const float *Tdust, const int32_t *dustAbunIndex)
+{
+    NEED_CTX();
+    GridState *g = grid_of(ctx, iG);
+    if (!g || !g->set) return fail(ctx, MCB200_ESTATE, "grid %d not set", iG);
+    if (!ctx->haveDustSpecies) return fail(ctx, MCB200_ESTATE, "set_dust_species first");
+    const mcb200_config &c = ctx->cfg;
+    if (!Tdust) return fail(ctx, MCB200_EINVAL, "null Tdust");
+    if (c.lgMultiDustChemistry && !dustAbunIndex) return fail(ctx, MCB200_EINVAL, "dustAbunIndex required with multiChemistry");
+    // sublimation test of photon_mod.f90:1722-1748 evaluated once per cell
+    std::vector<unsigned char> can((size_t)g->nCells + 1, 0);
+    size_t s0 = (size_t)c.nSpeciesMax + 1, s1 = (size_t)c.nSizes + 1;
+    for (int cell = 1; cell <= g->nCells; ++cell) {
+        int comp = c.lgMultiDustChemistry ? dustAbunIndex[cell] : 1;
+        if (comp < 1 || comp > c.nDustComp) continue;
+        int nSp = ctx->nSpeciesPart[comp - 1];
+        for (int nS = 1; nS <= nSp; ++nS) {
+            float ab = ctx->grainAbun[(size_t)(comp - 1) + (size_t)c.nDustComp * (nS - 1)];
+            float Td = Tdust[(size_t)nS + s0 * (0 + s1 * (size_t)cell)];
+            if (ab > 0.f && Td < ctx->TdustSublime[ctx->dustComPoint[comp - 1] - 1 + nS - 1]) { can[cell] = 1; break; }
+        }
+    }
+    bool re = (g->canScatter.n != can.size());
+    CU(g->canScatter.upload(can.data(), can.size(), ctx->stream));
+    CU(cudaStreamSynchronize(ctx->stream));
+    if (re) ctx->gridsDirty = true;
+    return MCB200_OK;
+}
+
+int mcb200_zero_estimators(mcb200_ctx *ctx)
+{
+    NEED_CTX();
+    if (!ctx->haveCfg) return fail(ctx, MCB200_ESTATE, "set_config first");
+    for (auto &g : ctx->grids) {
+        if (!g.set) continue;
+        int rc = ensure_estimators(ctx, g);
+        if (rc) return rc;
+        CU(g.JsteQ.zero(ctx->stream)); CU(g.Jste.zero(ctx->stream));
+        CU(g.escQ.zero(ctx->stream));  CU(g.esc.zero(ctx->stream));
+        CU(g.JdifQ.zero(ctx->stream)); CU(g.Jdif.zero(ctx->stream));
+        CU(g.lineQ.zero(ctx->stream)); CU(g.linePk.zero(ctx->stream));
+    }
+    CU(cudaStreamSynchronize(ctx->stream));
+    ctx->pending = false;
+    return MCB200_OK;
+}
+
+int mcb200_transport(mcb200_ctx *ctx, int32_t iStar, int64_t nPacketsGlobal, float deltaE, mcb200_counters *counters)
+{
+    NEED_CTX();
+    if (iStar < 1) return fail(ctx, MCB200_EINVAL, "iStar must be >= 1 (use mcb200_transport_diffuse for iStar=0)");
+    return run_transport(ctx, iStar, 0, nullptr, nPacketsGlobal, deltaE, counters);
+}
+
+int mcb200_transport_diffuse(mcb200_ctx *ctx, int32_t gpLoc, const int32_t *cellLoc, int64_t nPacketsGlobal,
+                             float deltaE, mcb200_counters *counters)
+{
+    NEED_CTX();
+    return run_transport(ctx, 0, gpLoc, cellLoc, nPacketsGlobal, deltaE, counters);
+}
+
+int mcb200_tally_buffer(mcb200_ctx *ctx, int32_t iG, int32_t which, void **devPtr, int64_t *count)
+{
+    NEED_CTX();
+    GridState *g = grid_of(ctx, iG);
+    if (!g || !g->set || !devPtr || !count) return fail(ctx, MCB200_EINVAL, "bad tally_buffer arguments");
+    int rc = ensure_estimators(ctx, *g);
+    if (rc) return rc;
+    CU(cudaStreamSynchronize(ctx->stream));
+    DevBuf<unsigned long long> *b = which == 0 ? &g->JsteQ : which == 1 ? &g->escQ : which == 2 ? &g->JdifQ : which == 3 ? &g->lineQ : nullptr;
+    if (!b) return fail(ctx, MCB200_EINVAL, "bad tally selector %d", which);
+    *devPtr = b->p;
+    *count = (int64_t)b->n;
+    return MCB200_OK;
+}
+
+int mcb200_reduce(mcb200_ctx *ctx)
+{
+    NEED_CTX();
+    return fold_pending(ctx);
+}
+
+int mcb200_fetch_estimators(mcb200_ctx *ctx, int32_t iG, float *Jste, float *escapedPackets, float *Jdif, float *linePackets)
+{
+    NEED_CTX();
+    GridState *g = grid_of(ctx, iG);
+    if (!g || !g->set) return fail(ctx, MCB200_ESTATE, "grid %d not set", iG);
+    if (ctx->pending) return fail(ctx, MCB200_ESTATE, "tallies pending: call mcb200_reduce first");
+    int rc = ensure_estimators(ctx, *g);
+    if (rc) return rc;
+    CU(cudaStreamSynchronize(ctx->stream));
+    if (Jste) CU(cudaMemcpy(Jste, g->Jste.p, g->Jste.n * sizeof(float), cudaMemcpyDeviceToHost));
+    if (escapedPackets) CU(cudaMemcpy(escapedPackets, g->esc.p, g->esc.n * sizeof(float), cudaMemcpyDeviceToHost));
+    if (Jdif) {
+        if (!g->Jdif.p) return fail(ctx, MCB200_ESTATE, "Jdif only exists in debug mode");
+        CU(cudaMemcpy(Jdif, g->Jdif.p, g->Jdif.n * sizeof(float), cudaMemcpyDeviceToHost));
+    }
+    if (linePackets) {
+        if (!g->linePk.p) return fail(ctx, MCB200_ESTATE, "linePackets only exists in debug mode");
+        CU(cudaMemcpy(linePackets, g->linePk.p, g->linePk.n * sizeof(float), cudaMemcpyDeviceToHost));
+    }
+    return MCB200_OK;
+}
+
+int mcb200_fetch_tallies(mcb200_ctx *ctx, int32_t iG, int64_t *JsteQ, int64_t *escapedQ, int64_t *JdifQ, int64_t *linePacketsQ)
+{
+    NEED_CTX();
+    GridState *g = grid_of(ctx, iG);
+    if (!g || !g->set) return fail(ctx, MCB200_ESTATE, "grid %d not set", iG);
+    int rc = ensure_estimators(ctx, *g);
+    if (rc) return rc;
+    CU(cudaStreamSynchronize(ctx->stream));
+    if (JsteQ) CU(cudaMemcpy(JsteQ, g->JsteQ.p, g->JsteQ.n * 8, cudaMemcpyDeviceToHost));
+    if (escapedQ) CU(cudaMemcpy(escapedQ, g->escQ.p, g->escQ.n * 8, cudaMemcpyDeviceToHost));
+    if (JdifQ && g->JdifQ.p) CU(cudaMemcpy(JdifQ, g->JdifQ.p, g->JdifQ.n * 8, cudaMemcpyDeviceToHost));
+    if (linePacketsQ && g->lineQ.p) CU(cudaMemcpy(linePacketsQ, g->lineQ.p, g->lineQ.n * 8, cudaMemcpyDeviceToHost));
+    return MCB200_OK;
+}
+
+int mcb200_len_unit(mcb200_ctx *ctx, int32_t iG, double *lenUnit)
+{
+    NEED_CTX();
+    GridState *g = grid_of(ctx, iG);
+    if (!g || !g->set || !lenUnit) return fail(ctx, MCB200_EINVAL, "bad len_unit arguments");
+    *lenUnit = std::ldexp(1.0, g->lenExp);
+    return MCB200_OK;
+}
+
+int mcb200_fetch_qphot_counts(mcb200_ctx *ctx, int64_t *counts)
+{
+    NEED_CTX();
+    if (!counts || !ctx->qphot.p) return fail(ctx, MCB200_ESTATE, "no transport call yet");
+    CU(cudaMemcpy(counts, ctx->qphot.p, ctx->qphot.n * 8, cudaMemcpyDeviceToHost));
+    return MCB200_OK;
+}
+
+int mcb200_fetch_fates(mcb200_ctx *ctx, int32_t *fates, int64_t nPackets)
+{
+    NEED_CTX();
+    if (!fates || !ctx->fates.p || (size_t)nPackets * 4 > ctx->fates.n) return fail(ctx, MCB200_ESTATE, "no fate trace available");
+    CU(cudaMemcpy(fates, ctx->fates.p, (size_t)nPackets * 4 * sizeof(int), cudaMemcpyDeviceToHost));
+    return MCB200_OK;
+}
+
+int mcb200_set_option(mcb200_ctx *ctx, const char *name, int64_t value)
+{
+    NEED_CTX();
+    if (!name) return MCB200_EINVAL;
+    if (!strcmp(name, "trace")) { ctx->trace = value != 0; return MCB200_OK; }
+    if (!strcmp(name, "blocks_per_sm")) { ctx->blocksPerSM = (int)value; return MCB200_OK; }
+    if (!strcmp(name, "seed")) { ctx->seed = (uint64_t)value; return MCB200_OK; }
+    return fail(ctx, MCB200_EINVAL, "unknown option %s", name);
+}
+
+int mcb200_test_detmath(mcb200_ctx *ctx, int32_t which, const float *in, float *out, int64_t n)
+{
+    NEED_CTX();
+    DevBuf<float> a, b;
+    CU(a.upload(in, (size_t)n, ctx->stream));
+    CU(b.alloc((size_t)n));
+    detmath_kernel<<<(unsigned)((n + 255) / 256), 256, 0, ctx->stream>>>(which, a.p, b.p, (long long)n);
+    CU(cudaGetLastError());
+    CU(cudaMemcpyAsync(out, b.p, (size_t)n * sizeof(float), cudaMemcpyDeviceToHost, ctx->stream));
+    CU(cudaStreamSynchronize(ctx->stream));
+    return MCB200_OK;
+}
+
+int mcb200_test_uniforms(mcb200_ctx *ctx, uint64_t seed, uint64_t pid, uint32_t stream, int32_t n, float *out)
+{
+    NEED_CTX();
+    DevBuf<float> b;
+    CU(b.alloc((size_t)n));
+    uniforms_kernel<<<1, 32, 0, ctx->stream>>>(seed, pid, stream, n, b.p);
+    CU(cudaGetLastError());
+    CU(cudaMemcpyAsync(out, b.p, (size_t)n * sizeof(float), cudaMemcpyDeviceToHost, ctx->stream));
+    CU(cudaStreamSynchronize(ctx->stream));
+    return MCB200_OK;
+}
+
+
+int mcb200_set_xsec(mcb200_ctx *ctx, const float *xSecArray, int64_t nXsec)
+{
+    NEED_CTX();
+    if (!xSecArray || nXsec < 1) return fail(ctx, MCB200_EINVAL, "bad xSecArray");
+    CU(ctx->xSec.upload(xSecArray, (size_t)nXsec, ctx->stream));
+    CU(cudaStreamSynchronize(ctx->stream));
+    return MCB200_OK;
+}
+
+int mcb200_assemble_opacity(mcb200_ctx *ctx, int32_t iG, int32_t nBands, const int32_t *bandSpecies,
+                            const int32_t *bandOff, const int32_t *bandLow, const int32_t *bandHigh,
+                            int32_t nSpeciesDen, const float *den, const float *ff1, const float *Ndust,
+                            const float *Tdust, const int32_t *dustAbunIndex, const float *grainWeight,
+                            const int32_t *dustScaXsecP, const int32_t *dustAbsXsecP, int32_t nSpeciesTot)
+{
+    NEED_CTX();
+    GridState *g = grid_of(ctx, iG);
+    if (!g || !g->set) return fail(ctx, MCB200_ESTATE, "grid %d not set", iG);
+    if (!ctx->xSec.p) return fail(ctx, MCB200_ESTATE, "mcb200_set_xsec first");
+    const mcb200_config &c = ctx->cfg;
+    int nb = c.nbins, nRows = g->nCells + 1;
+    if (nBands < 0 || nSpeciesDen < 0 || (nBands > 0 && (!bandSpecies || !bandOff || !bandLow || !bandHigh || !den)))
+        return fail(ctx, MCB200_EINVAL, "bad band list");
+    int64_t nXs = (int64_t)ctx->xSec.n;
+    // CSR over nu of the bands covering each bin, in the reference's band order
+    // (inOpacity, ionization_mod.f90:448-482: i = nuLowP .. max(nuLowP, min(nuHighP, nbins)))
+    std::vector<int> nuStart(nb + 1, 0), spec, xs;
+    for (int nu = 1; nu <= nb; ++nu) {
+        for (int b = 0; b < nBands; ++b) {
+            int lo = bandLow[b], up = bandHigh[b] < nb ? bandHigh[b] : nb;
+            if (up < lo) up = lo;
+            if (nu < lo || nu > up) continue;
+            int sp = bandSpecies[b];
+            int64_t xi = (int64_t)nu + bandOff[b];
+            if (sp < 1 || sp > nSpeciesDen) return fail(ctx, MCB200_EINVAL, "band %d: species column out of range", b + 1);
+            if (xi < 1 || xi > nXs) return fail(ctx, MCB200_EINVAL, "band %d: xSecArray index out of range", b + 1);
+            spec.push_back(sp - 1);
+            xs.push_back((int)xi);
+        }
+        nuStart[nu] = (int)spec.size();
+    }
+    size_t ts = tsize(ctx, *g);
+    bool re = (g->opacity.n != ts);
+    DevBuf<float> dDen, dFf, dNd, dCoef;
+    DevBuf<int> dStart, dSpec, dXs, dComp, dTermOn, dScaP, dAbsP;
+    DevBuf<unsigned char> dOn;
+    cudaStream_t s = ctx->stream;
+    OpacityArgs A{};
+    A.nRows = nRows; A.nb = nb; A.nSpeciesDen = nSpeciesDen;
+    if (nSpeciesDen > 0) CU(dDen.upload(den, (size_t)nRows * nSpeciesDen, s));
+    if (ff1) CU(dFf.upload(ff1, nRows, s));
+    CU(dStart.upload(nuStart.data(), nuStart.size(), s));
+    if (!spec.empty()) { CU(dSpec.upload(spec.data(), spec.size(), s)); CU(dXs.upload(xs.data(), xs.size(), s)); }
+    A.den = dDen.p; A.ff1 = dFf.p; A.xSec = ctx->xSec.p;
+    A.nuStart = dStart.p; A.nuBandSpecies = dSpec.p; A.nuBandXs = dXs.p;
+    CU(g->opacity.alloc(ts));
+    A.opacity = g->opacity.p;
+    std::vector<unsigned char> on;
+    std::vector<float> coef;
+    std::vector<int> termOn, scaP, absP, comps;
+    if (c.lgDust && Ndust) {
+        if (!ctx->haveDustSpecies) return fail(ctx, MCB200_ESTATE, "set_dust_species first");
+        if (!Tdust || !grainWeight || !dustScaXsecP || !dustAbsXsecP || nSpeciesTot < 1 || c.nSizes < 1)
+            return fail(ctx, MCB200_EINVAL, "bad dust arguments");
+        if (c.lgMultiDustChemistry && !dustAbunIndex) return fail(ctx, MCB200_EINVAL, "dustAbunIndex required");
+        int nT = nSpeciesTot * c.nSizes, nC = c.nDustComp;
+        coef.assign((size_t)nC * nT, 0.f); termOn.assign((size_t)nC * nT, 0);
+        scaP.resize(nT); absP.resize(nT);
+        for (int sg = 1; sg <= nSpeciesTot; ++sg)
+            for (int ai = 1; ai <= c.nSizes; ++ai) {
+                int t = (sg - 1) * c.nSizes + (ai - 1);
+                scaP[t] = dustScaXsecP[(size_t)(sg - 1) + (size_t)nSpeciesTot * (ai - 1)];
+                absP[t] = dustAbsXsecP[(size_t)(sg - 1) + (size_t)nSpeciesTot * (ai - 1)];
+                if (scaP[t] < 1 || scaP[t] + nb - 1 > nXs || absP[t] < 1 || absP[t] + nb - 1 > nXs)
+                    return fail(ctx, MCB200_EINVAL, "dust cross-section pointer out of range");
+                for (int k = 1; k <= nC; ++k) {
+                    int dcp = ctx->dustComPoint[k - 1], nS = sg - dcp + 1;
+                    if (nS < 1 || nS > ctx->nSpeciesPart[k - 1]) continue;
+                    termOn[(size_t)(k - 1) * nT + t] = 1;
+                    volatile float cf = ctx->grainAbun[(size_t)(k - 1) + (size_t)nC * (nS - 1)] * grainWeight[ai - 1];
+                    coef[(size_t)(k - 1) * nT + t] = cf;
+                }
+            }
+        // sublimation mask Tdust(nS,ai,cell) < TdustSublime(dcp-1+nS), iteration_mod.f90:189
+        on.assign((size_t)nT * nRows, 0);
+        comps.assign(nRows, 0);
+        size_t s0 = (size_t)c.nSpeciesMax + 1, s1 = (size_t)c.nSizes + 1;
+        for (int cell = 1; cell < nRows; ++cell) {
+            int k = c.lgMultiDustChemistry ? dustAbunIndex[cell] : 1;
+            if (k < 1 || k > nC) { comps[cell] = -1; continue; }
+            comps[cell] = k - 1;
+            int dcp = ctx->dustComPoint[k - 1];
+            for (int nS = 1; nS <= ctx->nSpeciesPart[k - 1]; ++nS)
+                for (int ai = 1; ai <= c.nSizes; ++ai) {
+                    int sg = dcp - 1 + nS, t = (sg - 1) * c.nSizes + (ai - 1);
+                    float Td = Tdust[(size_t)nS + s0 * ((size_t)ai + s1 * (size_t)cell)];
+                    on[(size_t)t * nRows + cell] = Td < ctx->TdustSublime[sg - 1] ? 1 : 0;
+                }
+        }
+        CU(dNd.upload(Ndust, nRows, s)); CU(dOn.upload(on.data(), on.size(), s));
+        CU(dCoef.upload(coef.data(), coef.size(), s)); CU(dTermOn.upload(termOn.data(), termOn.size(), s));
+        CU(dScaP.upload(scaP.data(), nT, s)); CU(dAbsP.upload(absP.data(), nT, s));
+        CU(dComp.upload(comps.data(), nRows, s));
+        if (g->scaOpac.n != ts) re = true;
+        CU(g->scaOpac.alloc(ts)); CU(g->absOpac.alloc(ts));
+        A.nDustTerms = nT; A.Ndust = dNd.p; A.dustOn = dOn.p; A.dustCoef = dCoef.p;
+        A.dustCompOfCell = dComp.p; A.dustTermOn = dTermOn.p; A.dustScaP = dScaP.p; A.dustAbsP = dAbsP.p;
+        A.scaOpac = g->scaOpac.p; A.absOpac = g->absOpac.p;
+    } else if (c.lgDust) {
+        // lgEquivalentTau first iteration (iteration_mod.f90:169-171): dust opacities stay zero
+        if (g->scaOpac.n != ts) re = true;
+        CU(g->scaOpac.alloc(ts)); CU(g->absOpac.alloc(ts));
+        CU(g->scaOpac.zero(s)); CU(g->absOpac.zero(s));
+    }
+    CU(launch_opacity(A, s));
+    CU(cudaStreamSynchronize(s));
+    g->haveOpacity = true;
+    if (re) ctx->gridsDirty = true;
+    return MCB200_OK;
+}
+
+int mcb200_get_opacity(mcb200_ctx *ctx, int32_t iG, float *opacity, float *scaOpac, float *absOpac)
+{
+    NEED_CTX();
+    GridState *g = grid_of(ctx, iG);
+    if (!g || !g->set || !g->haveOpacity) return fail(ctx, MCB200_ESTATE, "opacity of grid %d not set", iG);
+    CU(cudaStreamSynchronize(ctx->stream));
+    if (opacity) CU(cudaMemcpy(opacity, g->opacity.p, g->opacity.n * sizeof(float), cudaMemcpyDeviceToHost));
+    if (scaOpac) {
+        if (!g->scaOpac.p) return fail(ctx, MCB200_ESTATE, "no scaOpac on device");
+        CU(cudaMemcpy(scaOpac, g->scaOpac.p, g->scaOpac.n * sizeof(float), cudaMemcpyDeviceToHost));
+    }
+    if (absOpac) {
+        if (!g->absOpac.p) return fail(ctx, MCB200_ESTATE, "no absOpac on device (host-assembled opacity)");
+        CU(cudaMemcpy(absOpac, g->absOpac.p, g->absOpac.n * sizeof(float), cudaMemcpyDeviceToHost));
+    }
+    return MCB200_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,198 @@
+// tables.cu -- table preparation, K4 fold epilogue and K1 opacity assembly kernels.
+#include "types.h"
+
+#include <cuda_runtime.h>
+#include <cstdint>
+
+namespace mcb {
+
+// ---------------------------------------------------------------------------------------
+// PDF upload: reference layout T(0:nCells,nbins) (cell fastest) -> [cell][nu] rows.
+// 32x32 shared-memory tile transpose, both sides coalesced.  HBM-bound:
+// 8 B per element (4 read + 4 write).
+// ---------------------------------------------------------------------------------------
+__global__ void transpose_pdf_kernel(const float *__restrict__ src, float *__restrict__ dst,
+                                     int nRows /*nCells+1*/, int nb)
+{
+    __shared__ float tile[32][33];
+    int c0 = blockIdx.x * 32, n0 = blockIdx.y * 32;
+    for (int j = threadIdx.y; j < 32; j += blockDim.y) {
+        int nu = n0 + j, cell = c0 + threadIdx.x;
+        if (nu < nb && cell < nRows) tile[j][threadIdx.x] = src[(size_t)nu * nRows + cell];
+    }
+    __syncthreads();
+    for (int j = threadIdx.y; j < 32; j += blockDim.y) {
+        int cell = c0 + j, nu = n0 + threadIdx.x;
+        if (nu < nb && cell < nRows) dst[(size_t)cell * nb + nu] = tile[threadIdx.x][j];
+    }
+}
+
+// getNu2's linear scan equals a binary search only on non-decreasing rows: verify.
+__global__ void check_monotone_kernel(const float *__restrict__ pdfT, int nRows, int nb, int *bad)
+{
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    size_t total = (size_t)nRows * (size_t)(nb - 1);
+    if (i >= total) return;
+    size_t row = i / (nb - 1), k = i % (nb - 1);
+    if (row == 0) return;                 // row 0 (inactive sink) is never sampled
+    float a = pdfT[row * nb + k], b = pdfT[row * nb + k + 1];
+    if (!(b >= a)) atomicExch(bad, 1);
+}
+
+cudaError_t launch_transpose_pdf(const float *src, float *dst, int nRows, int nb, cudaStream_t s)
+{
+    dim3 grid((nRows + 31) / 32, (nb + 31) / 32), block(32, 8);
+    transpose_pdf_kernel<<<grid, block, 0, s>>>(src, dst, nRows, nb);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_check_monotone(const float *pdfT, int nRows, int nb, int *bad, cudaStream_t s)
+{
+    size_t total = (size_t)nRows * (size_t)(nb - 1);
+    unsigned blocks = (unsigned)((total + 255) / 256);
+    check_monotone_kernel<<<blocks, 256, 0, s>>>(pdfT, nRows, nb, bad);
+    return cudaGetLastError();
+}
+
+// ---------------------------------------------------------------------------------------
+// K4 fold epilogue: integer tallies of one transport call -> float32 estimators of the
+// reference, then clear the integer tallies.
+//   Jste(c,nu) += float(Q * lenUnit) * deltaE / dV(c)      (photon_mod.f90:1563-1574)
+//   escapedPackets(c,nu,a) += float(count) * deltaE          (photon_mod.f90:414-462)
+// One thread per element, each element touched by exactly one thread -> deterministic.
+// HBM-bound: 8 B (Q) read + 8 B (Q clear) + 4 B read + 4 B write per element.
+// ---------------------------------------------------------------------------------------
+__global__ void fold_j_kernel(unsigned long long *__restrict__ Q, float *__restrict__ J,
+                              const float *__restrict__ dV, int nRows, size_t total,
+                              double lenUnit, float deltaE)
+{
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    size_t stride = (size_t)gridDim.x * blockDim.x;
+    for (; i < total; i += stride) {
+        long long q = (long long)Q[i];
+        if (q != 0) {
+            int cell = (int)(i % (size_t)nRows);
+            float len = (float)((double)q * lenUnit);
+            J[i] = J[i] + len * deltaE / dV[cell];
+            Q[i] = 0ull;
+        }
+    }
+}
+
+__global__ void fold_count_kernel(unsigned long long *__restrict__ Q, float *__restrict__ E,
+                                  size_t total, float deltaE)
+{
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    size_t stride = (size_t)gridDim.x * blockDim.x;
+    for (; i < total; i += stride) {
+        unsigned long long q = Q[i];
+        if (q != 0ull) {
+            E[i] = E[i] + (float)q * deltaE;
+            Q[i] = 0ull;
+        }
+    }
+}
+
+cudaError_t launch_fold_j(unsigned long long *Q, float *J, const float *dV, int nRows, size_t total,
+                          double lenUnit, float deltaE, int blocks, cudaStream_t s)
+{
+    fold_j_kernel<<<blocks, 256, 0, s>>>(Q, J, dV, nRows, total, lenUnit, deltaE);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_fold_count(unsigned long long *Q, float *E, size_t total, float deltaE, int blocks,
+                              cudaStream_t s)
+{
+    fold_count_kernel<<<blocks, 256, 0, s>>>(Q, E, total, deltaE);
+    return cudaGetLastError();
+}
+
+// ---------------------------------------------------------------------------------------
+// K1: opacity assembly (ionization_mod.f90:349-484 + iteration_mod.f90:166-227).
+// One CTA per tile of kTile cells, all frequencies; the tile's species densities are
+// staged once in shared memory ([species][cell], conflict-free), cross-sections are
+// warp-uniform loads (same address for every lane, served by L1), the output rows are
+// written as coalesced kTile*4-byte runs.  Bands covering a frequency are visited in the
+// reference's order (CSR over nu built on the host) with separate mul and add
+// (-fmad=false) so the sums are bit-identical to the reference's sequential loop.
+// Bound: HBM writes, (nCells+1)*nbins*4 B per output table.
+// ---------------------------------------------------------------------------------------
+struct OpacityArgs {
+    int nRows, nb;                        // nCells+1, nbins
+    int nSpeciesDen;
+    const float *den;                     // (0:nCells, nSpeciesDen) cell fastest
+    const float *ff1;                     // (0:nCells) or NULL
+    const float *xSec;                    // xSecArray, 1-based offsets
+    const int *nuStart;                   // [nb+1] CSR offsets into nuBand*
+    const int *nuBandSpecies;             // species column (0-based) per entry
+    const int *nuBandXs;                  // 1-based xSecArray index for this (band, nu)
+    // dust
+    int nDustTerms;                       // flattened (species,size) terms for this call
+    const float *Ndust;                   // (0:nCells)
+    const unsigned char *dustOn;          // [term][cell]: Tdust(s,a,c) < TdustSublime(s)
+    const float *dustCoef;                // [comp][term]: grainAbun(comp,s)*grainWeight(a)
+    const int *dustCompOfCell;            // (0:nCells) 0-based component, or NULL (=0)
+    const int *dustTermOn;                // [comp][term]: term belongs to component
+    const int *dustScaP, *dustAbsP;       // [term] 1-based xSecArray offsets
+    float *opacity, *scaOpac, *absOpac;   // outputs (0:nCells, nbins)
+};
+
+constexpr int kTile = 128;
+
+__global__ void __launch_bounds__(kTile) opacity_kernel(const OpacityArgs A)
+{
+    extern __shared__ float sden[];       // [nSpeciesDen][kTile]
+    int cell = blockIdx.x * kTile + threadIdx.x;
+    bool ok = cell < A.nRows && cell >= 1;
+    for (int s = 0; s < A.nSpeciesDen; ++s)
+        sden[s * kTile + threadIdx.x] = ok ? A.den[(size_t)s * A.nRows + cell] : 0.f;
+    float nd = 0.f;
+    int comp = 0;
+    if (A.nDustTerms > 0 && ok) {
+        nd = A.Ndust[cell];
+        if (A.dustCompOfCell) comp = A.dustCompOfCell[cell];
+    }
+    float ff = (A.ff1 && ok) ? A.ff1[cell] : 0.f;
+    __syncthreads();
+    if (cell >= A.nRows) return;
+    for (int nu = 0; nu < A.nb; ++nu) {
+        float op = 0.f;
+        if (ok) {
+            if (nu == 0) op = op + ff;
+            int b0 = A.nuStart[nu], b1 = A.nuStart[nu + 1];
+            for (int b = b0; b < b1; ++b) {
+                float d = sden[A.nuBandSpecies[b] * kTile + threadIdx.x];
+                if (d > 0.f) op = op + __ldg(&A.xSec[A.nuBandXs[b] - 1]) * d;
+            }
+        }
+        size_t o = (size_t)nu * A.nRows + cell;
+        if (A.nDustTerms > 0) {
+            float sca = 0.f, ab = 0.f;
+            if (ok && comp >= 0) {
+                for (int t = 0; t < A.nDustTerms; ++t) {
+                    if (!A.dustTermOn[comp * A.nDustTerms + t]) continue;
+                    if (!A.dustOn[(size_t)t * A.nRows + cell]) continue;
+                    float coef = A.dustCoef[comp * A.nDustTerms + t] * nd;
+                    sca = sca + coef * __ldg(&A.xSec[A.dustScaP[t] + nu - 1]);
+                    ab = ab + coef * __ldg(&A.xSec[A.dustAbsP[t] + nu - 1]);
+                }
+                op = op + (sca + ab);
+            }
+            A.scaOpac[o] = sca;
+            A.absOpac[o] = ab;
+        }
+        A.opacity[o] = op;
+    }
+}
+
+cudaError_t launch_opacity(const OpacityArgs &A, cudaStream_t s)
+{
+    int blocks = (A.nRows + kTile - 1) / kTile;
+    size_t smem = (size_t)A.nSpeciesDen * kTile * sizeof(float);
+    if (smem < 4) smem = 4;
+    cudaFuncSetAttribute(opacity_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    opacity_kernel<<<blocks, kTile, smem, s>>>(A);
+    return cudaGetLastError();
+}
+
+}  // namespace mcb

@@ -1,0 +1,67 @@
+// types.h -- device-side views of the reference's grid_type / common_mod globals.
+#pragma once
+#include <cstdint>
+
+namespace mcb {
+
+// Hot members of grid_type (common_mod.f90:241-302) as device pointers.
+// Layout in HBM (all as in the reference unless noted):
+//   active   int32 [x-1 + nx*((y-1) + ny*(z-1))]            (4 B / cell)
+//   opacity, scaOpac float [(nu-1)*(nCells+1) + cell]       (nu-planes, cell fastest)
+//   pdfT     float [cell*nbins + (nu-1)]                    TRANSPOSED on upload so one
+//            re-emission CDF row is contiguous (binary search touches <=2 lines/probe)
+//   xWall[i] i=0..nx: W[0]=x(1), W[i]=(x(i+1)+x(i))/2, W[nx]=x(nx)  -- the mid-point cell
+//            walls of photon_mod.f90:1263-1295 precomputed with the same float32 expression
+//   JsteQ/JdifQ  uint64 [(nu-1)*(nCells+1) + cell]  fixed-point path length (2^-e cm units)
+//   escQ     uint64 [cell + (nCells+1)*(nu + (nbins+1)*ang)] escaped packet counts
+//   lineQ    uint64 [(line-1)*(nCells+1) + cell]    line packet counts (debug)
+struct DevGrid {
+    int nx, ny, nz, nCells, motherP;
+    int dense;                       // 1: every cell active, id = 1 + (z-1) + nz*((y-1) + ny*(x-1))
+    float geoX, geoY, geoZ;          // geoCorr (grid_mod.f90:809-812)
+    float invLenUnit;                // 2^-e, path-length quantum of the J tally
+    const float *xAxis, *yAxis, *zAxis;
+    const float *xWall, *yWall, *zWall;
+    const int *active;
+    const float *opacity, *scaOpac;
+    const float *pdfT;               // recPDF (gas) or dustPDF (dust only), transposed
+    const float *totalLines;
+    const float *linePDF;            // reference layout, debug only
+    const unsigned char *canScatter; // per cell: an unsublimated species exists (photon_mod.f90:1722-1748)
+    unsigned long long *JsteQ, *JdifQ, *escQ, *lineQ;
+};
+
+struct DevParams {
+    int nGrids, nbins, nStars, nAngleBins, totT, totP, nLines;
+    int lgDust, lgGas, lgSym, lgIso, lgDebug, lgMultistars;
+    float dTheta, dPhi, R_out, ionEdge1;
+    const float *nuArray, *gSca;
+    const float *starCdf;            // [(s)*nbins + nu-1], s = 0..nStars
+    const float *starPos;            // [3*(i-1)+k]
+    const int *starIdx;              // [4*(i-1)+k]
+    const int *starCell;             // active id of the star cell, per star
+    const int *vpPtheta, *vpPphi;    // 0:totT, 0:totP
+    const float *vpTheta, *vpPhi;    // 0:nAngleBins
+};
+
+enum Counter {
+    C_ABS = 0, C_SCA, C_TRAPPED, C_LINE, C_DROPPED, C_SEGMENTS, C_FLIGHTS, C_ESCAPED, C_EARLY,
+    C_COUNT
+};
+
+struct TransportArgs {
+    DevParams P;
+    DevGrid g1;                      // copy of grids[0] (constant-bank access for the mother grid)
+    const DevGrid *grids;            // device array [nGrids]
+    int iStar;                       // >=1 stellar, 0 extra diffuse source
+    int difGrid, difX, difY, difZ;   // diffuse source cell (iStar==0)
+    long long firstId, n;            // global id of this rank's first packet, packets of this rank
+    unsigned long long seed;
+    unsigned long long *nextPacket;  // work counter
+    unsigned long long *counters;    // [C_COUNT]
+    unsigned long long *qphotCounts; // [nbins]
+    int *errFlag;
+    int *fates;                      // optional [4*n]
+};
+
+}  // namespace mcb

@@ -1,0 +1,121 @@
+/*
+ * oracle/mc_oracle.h -- TEST INFRASTRUCTURE, not product code.
+ *
+ * Data contract of the CPU oracle: a plain-C restatement of the energy-packet
+ * transport of the reference (source/photon_mod.f90:26-2974) and of the per-cell
+ * opacity assembly (source/ionization_mod.f90:349-484, iteration_mod.f90:166-227).
+ *
+ * PARITY UNPINNED: the reference ships no golden vectors / tests for this path
+ *  and cannot be compiled here (no Fortran compiler), so
+ * this oracle is pinned only by its own unit tests (geometry, locate, getNu2, hg,
+ * conservation, analytic limits) -- see DESIGN.md.
+ *
+ * Array layouts follow the Fortran reference (column major, 1-based unless noted):
+ *   active(nx,ny,nz)               -> active[(x-1) + nx*((y-1) + ny*(z-1))]
+ *   T(0:nCells, 1:nbins)           -> T[(nu-1)*(nCells+1) + cell]
+ *   escapedPackets(0:nCells,0:nbins,0:nAngleBins)
+ *                                  -> E[cell + (nCells+1)*(nu + (nbins+1)*ang)]
+ *   Tdust(0:nSpeciesMax,0:nSizes,0:nCells)
+ *                                  -> Td[nS + (nSpeciesMax+1)*(ai + (nSizes+1)*cell)]
+ *   linePackets/linePDF(0:nCells,1:nLines) like T with nLines
+ */
+#ifndef MC_ORACLE_H
+#define MC_ORACLE_H
+
+#include <stdint.h>
+
+typedef struct OrGrid {
+    int32_t nx, ny, nz, nCells, motherP;
+    float geoCorrX, geoCorrY, geoCorrZ;
+    float invLenUnit;              /* 1/unit of the fixed-point path-length tally (power of two) */
+    const float *xAxis, *yAxis, *zAxis;
+    const int32_t *active;
+    const float *opacity, *scaOpac;
+    const float *recPDF, *dustPDF, *linePDF, *totalLines;
+    const float *Tdust;
+    const int32_t *dustAbunIndex;
+    /* outputs, faithful float32 sequential accumulation (may be NULL) */
+    float *Jste, *Jdif, *escapedPackets, *linePackets;
+    /* outputs, order-independent integer tallies (may be NULL):
+     *   JsteQ/JdifQ: sum of llrintf(pathlength * invLenUnit)
+     *   escapedQ/linePacketsQ: packet counts */
+    int64_t *JsteQ, *JdifQ, *escapedQ, *linePacketsQ;
+} OrGrid;
+
+typedef struct OrParams {
+    int32_t nGrids, nbins, nAngleBins, totAngleBinsTheta, totAngleBinsPhi, nLines, nStars;
+    int32_t lgDust, lgGas, lgSymmetricXYZ, lgIsotropic, lgPlaneIonization, lgDebug,
+            lgMultistars, lgMultiDustChemistry;
+    int32_t nSpeciesMax, nSizes, nDustComp;
+    float dTheta, dPhi, R_out, ionEdge1;
+    const float *nuArray;          /* 1:nbins */
+    const float *gSca;             /* 1:nbins */
+    const int32_t *viewPointPtheta; /* 0:totAngleBinsTheta */
+    const int32_t *viewPointPphi;   /* 0:totAngleBinsPhi */
+    const float *viewPointTheta;   /* 0:nAngleBins */
+    const float *viewPointPhi;     /* 0:nAngleBins */
+    const float *starPosition;     /* [3*(i-1)+k], cm */
+    const int32_t *starIndeces;    /* [4*(i-1)+k] = xP,yP,zP,grid (1-based values) */
+    const float *deltaE;           /* 0:nStars */
+    const float *inSpectrumProbDen;/* [(s)*nbins + (nu-1)], s=0..nStars */
+    const int32_t *nSpeciesPart;   /* 1:nDustComp */
+    const float *grainAbun;        /* (nDustComp,nSpeciesMax) column major */
+    const int32_t *dustComPoint;   /* 1:nDustComp */
+    const float *TdustSublime;     /* 1:nSpecies */
+} OrParams;
+
+typedef struct OrCounters {
+    float Qphot;                   /* faithful fp32 sequential sum (photon_mod.f90:859-861) */
+    float absInt, scaInt;          /* faithful fp32 counters (photon_mod.f90:1702,1720,1803) */
+    int64_t nAbs, nSca;            /* exact event counts */
+    int64_t trapped;               /* photon_mod.f90:126 */
+    int64_t nLinePackets;          /* packets that ended as non-ionising line packets */
+    int64_t nDropped;              /* packets dropped by safeLimit / wall return (no tally) */
+    int64_t nSegments;             /* trips of the cell-crossing loop (photon_mod.f90:1194) */
+    int64_t nFlights;              /* calls of pathSegment */
+    int64_t nEscaped;              /* escape tallies */
+    int64_t nEarlyEscaped;         /* escapes at energyPacketRun :370 (no dust, nu<ionEdge) */
+} OrCounters;
+
+/* per-packet fate record, 4 int32 per packet (optional):
+ * [0] total segments, [1] generations (energyPacketRun calls), [2] last nuP,
+ * [3] fate: 1 escaped, 2 line packet, 3 dropped, 4 trapped(recursion limit), 5 early escape */
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* Transport n packets with global ids [firstId, firstId+n) of source iStar
+ * (iStar>=1 stellar; iStar==0 extra diffuse source in cell cellLoc of grid gpLoc).
+ * qphotCounts (nbins int64, may be NULL) receives the number of stellar emissions
+ * per frequency bin with nu>1 Ryd.  Returns 0, or a negative code for the
+ * reference's "print; stop" conditions. */
+int oracle_transport(const OrParams *P, OrGrid *grids, int32_t iStar,
+                     int64_t firstId, int64_t n, uint64_t seed,
+                     int32_t gpLoc, const int32_t *cellLoc,
+                     OrCounters *C, int64_t *qphotCounts, int32_t *fate);
+
+/* Same packets, nThreads host threads, integer tallies only (atomic adds);
+ * used as the CPU baseline in bench.py. */
+int oracle_transport_mt(const OrParams *P, OrGrid *grids, int32_t iStar,
+                        int64_t firstId, int64_t n, uint64_t seed,
+                        int32_t nThreads, OrCounters *C, int64_t *qphotCounts);
+
+/* unit-test hooks */
+void oracle_philox(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3,
+                   uint32_t k0, uint32_t k1, uint32_t *out4);
+void oracle_uniforms(uint64_t seed, uint64_t pid, uint32_t stream, int32_t n, float *out);
+int32_t oracle_locate(const float *xa, int32_t n, float x);
+int32_t oracle_getnu2(const float *probDen, int64_t stride, int32_t nbins,
+                      uint64_t seed, uint64_t pid, uint32_t stream);
+void oracle_random_unit_vector(uint64_t seed, uint64_t pid, uint32_t stream, float *out3);
+int32_t oracle_hg(float g, const float *vin, uint64_t seed, uint64_t pid, uint32_t stream,
+                  float *vout);
+void oracle_detmath(int32_t which, const float *in, float *out, int64_t n);
+int32_t oracle_escape_bins(const OrParams *P, const float *dir, int32_t *idirT, int32_t *idirP);
+float oracle_cell_volume(const OrParams *P, const OrGrid *g, int32_t xP, int32_t yP, int32_t zP);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

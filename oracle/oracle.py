@@ -1,0 +1,234 @@
+"""ctypes binding of the CPU oracle (oracle/libmc_oracle.so).
+
+TEST INFRASTRUCTURE: only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline /
+--impl reference legs may import this module.  The product package (mocassin_b200)
+never does.  PARITY UNPINNED (see oracle/mc_oracle.h).
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(HERE, "libmc_oracle.so")
+
+fp = C.POINTER(C.c_float)
+ip = C.POINTER(C.c_int32)
+lp = C.POINTER(C.c_int64)
+
+
+class OrGrid(C.Structure):
+    _fields_ = [("nx", C.c_int32), ("ny", C.c_int32), ("nz", C.c_int32), ("nCells", C.c_int32),
+                ("motherP", C.c_int32), ("geoCorrX", C.c_float), ("geoCorrY", C.c_float),
+                ("geoCorrZ", C.c_float), ("invLenUnit", C.c_float),
+                ("xAxis", fp), ("yAxis", fp), ("zAxis", fp), ("active", ip),
+                ("opacity", fp), ("scaOpac", fp), ("recPDF", fp), ("dustPDF", fp), ("linePDF", fp),
+                ("totalLines", fp), ("Tdust", fp), ("dustAbunIndex", ip),
+                ("Jste", fp), ("Jdif", fp), ("escapedPackets", fp), ("linePackets", fp),
+                ("JsteQ", lp), ("JdifQ", lp), ("escapedQ", lp), ("linePacketsQ", lp)]
+
+
+class OrParams(C.Structure):
+    _fields_ = [(n, C.c_int32) for n in (
+        "nGrids", "nbins", "nAngleBins", "totAngleBinsTheta", "totAngleBinsPhi", "nLines", "nStars",
+        "lgDust", "lgGas", "lgSymmetricXYZ", "lgIsotropic", "lgPlaneIonization", "lgDebug",
+        "lgMultistars", "lgMultiDustChemistry", "nSpeciesMax", "nSizes", "nDustComp")] + [
+        (n, C.c_float) for n in ("dTheta", "dPhi", "R_out", "ionEdge1")] + [
+        ("nuArray", fp), ("gSca", fp), ("viewPointPtheta", ip), ("viewPointPphi", ip),
+        ("viewPointTheta", fp), ("viewPointPhi", fp), ("starPosition", fp), ("starIndeces", ip),
+        ("deltaE", fp), ("inSpectrumProbDen", fp), ("nSpeciesPart", ip), ("grainAbun", fp),
+        ("dustComPoint", ip), ("TdustSublime", fp)]
+
+
+class OrCounters(C.Structure):
+    _fields_ = [("Qphot", C.c_float), ("absInt", C.c_float), ("scaInt", C.c_float)] + [
+        (n, C.c_int64) for n in ("nAbs", "nSca", "trapped", "nLinePackets", "nDropped", "nSegments",
+                                 "nFlights", "nEscaped", "nEarlyEscaped")]
+
+    def as_dict(self):
+        return {n: getattr(self, n) for n, _ in self._fields_}
+
+
+def build(force: bool = False) -> str:
+    src = [os.path.join(HERE, f) for f in ("mc_oracle.c", "mc_oracle.h", "detmath.h", "Makefile")]
+    stale = force or not os.path.exists(LIB_PATH) or any(
+        os.path.getmtime(s) > os.path.getmtime(LIB_PATH) for s in src)
+    if stale:
+        res = subprocess.run(["make", "-C", HERE, "-B", "libmc_oracle.so"], capture_output=True, text=True)
+        if res.returncode != 0:
+            raise RuntimeError("oracle build failed:\n" + res.stdout + res.stderr)
+    return LIB_PATH
+
+
+_lib = None
+
+
+def load() -> C.CDLL:
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            build()
+        lib = C.CDLL(LIB_PATH)
+        lib.oracle_transport.restype = C.c_int
+        lib.oracle_transport.argtypes = [C.POINTER(OrParams), C.POINTER(OrGrid), C.c_int32, C.c_int64,
+                                         C.c_int64, C.c_uint64, C.c_int32, ip, C.POINTER(OrCounters), lp, ip]
+        lib.oracle_transport_mt.restype = C.c_int
+        lib.oracle_transport_mt.argtypes = [C.POINTER(OrParams), C.POINTER(OrGrid), C.c_int32, C.c_int64,
+                                            C.c_int64, C.c_uint64, C.c_int32, C.POINTER(OrCounters), lp]
+        lib.oracle_philox.argtypes = [C.c_uint32] * 6 + [C.POINTER(C.c_uint32)]
+        lib.oracle_uniforms.argtypes = [C.c_uint64, C.c_uint64, C.c_uint32, C.c_int32, fp]
+        lib.oracle_locate.restype = C.c_int32
+        lib.oracle_locate.argtypes = [fp, C.c_int32, C.c_float]
+        lib.oracle_getnu2.restype = C.c_int32
+        lib.oracle_getnu2.argtypes = [fp, C.c_int64, C.c_int32, C.c_uint64, C.c_uint64, C.c_uint32]
+        lib.oracle_random_unit_vector.argtypes = [C.c_uint64, C.c_uint64, C.c_uint32, fp]
+        lib.oracle_hg.restype = C.c_int32
+        lib.oracle_hg.argtypes = [C.c_float, fp, C.c_uint64, C.c_uint64, C.c_uint32, fp]
+        lib.oracle_detmath.argtypes = [C.c_int32, fp, fp, C.c_int64]
+        lib.oracle_escape_bins.restype = C.c_int32
+        lib.oracle_escape_bins.argtypes = [C.POINTER(OrParams), fp, ip, ip]
+        lib.oracle_cell_volume.restype = C.c_float
+        lib.oracle_cell_volume.argtypes = [C.POINTER(OrParams), C.POINTER(OrGrid), C.c_int32, C.c_int32, C.c_int32]
+        _lib = lib
+    return _lib
+
+
+def _p(a, typ):
+    if a is None:
+        return typ()
+    return a.ctypes.data_as(typ)
+
+
+def _F(a, dtype):
+    return None if a is None else np.asfortranarray(a, dtype=dtype)
+
+
+class Oracle:
+    """Runs the CPU restatement on a mocassin_b200.model.Model-shaped object (duck typed:
+    only attribute access, so the oracle does not import the product package)."""
+
+    def __init__(self, model, len_unit=None, fp32_tallies: bool = True, int_tallies: bool = True):
+        self.lib = load()
+        self.m = m = model
+        self._keep = []
+        at = m.angle_tables()
+        self.at = at
+        P = OrParams()
+        P.nGrids, P.nbins, P.nAngleBins = m.nGrids, m.nbins, m.nAngleBins
+        P.totAngleBinsTheta, P.totAngleBinsPhi = at["totAngleBinsTheta"], at["totAngleBinsPhi"]
+        P.nLines, P.nStars = m.nLines, m.nStars
+        P.lgDust, P.lgGas, P.lgSymmetricXYZ = int(m.lgDust), int(m.lgGas), int(m.lgSymmetricXYZ)
+        P.lgIsotropic, P.lgPlaneIonization, P.lgDebug = int(m.lgIsotropic), int(m.lgPlaneIonization), int(m.lgDebug)
+        P.lgMultistars, P.lgMultiDustChemistry = int(m.lgMultistars), int(m.lgMultiDustChemistry)
+        P.nSpeciesMax, P.nSizes, P.nDustComp = m.nSpeciesMax, m.nSizes, int(m.nSpeciesPart.shape[0])
+        P.dTheta, P.dPhi, P.R_out, P.ionEdge1 = float(at["dTheta"]), float(at["dPhi"]), float(m.R_out), float(m.ionEdge1)
+
+        def keep(a, dtype):
+            a = np.ascontiguousarray(a, dtype=dtype)
+            self._keep.append(a)
+            return a
+
+        P.nuArray = _p(keep(m.nuArray, np.float32), fp)
+        P.gSca = _p(keep(m.gSca, np.float32), fp) if m.gSca is not None else fp()
+        P.viewPointPtheta = _p(keep(at["viewPointPtheta"], np.int32), ip)
+        P.viewPointPphi = _p(keep(at["viewPointPphi"], np.int32), ip)
+        P.viewPointTheta = _p(keep(at["viewPointTheta"], np.float32), fp)
+        P.viewPointPhi = _p(keep(at["viewPointPhi"], np.float32), fp)
+        P.starPosition = _p(keep(np.asarray(m.starPosition).reshape(-1), np.float32), fp)
+        P.starIndeces = _p(keep(np.asarray(m.starIndeces).reshape(-1), np.int32), ip)   # row-major [i][k]
+        self.deltaE = keep(m.deltaE, np.float32)
+        P.deltaE = _p(self.deltaE, fp)
+        P.inSpectrumProbDen = _p(keep(np.asarray(m.inSpectrumProbDen).reshape(-1), np.float32), fp)
+        P.nSpeciesPart = _p(keep(m.nSpeciesPart, np.int32), ip)
+        self._ga = _F(m.grainAbun, np.float32); P.grainAbun = _p(self._ga, fp)
+        P.dustComPoint = _p(keep(m.dustComPoint, np.int32), ip)
+        P.TdustSublime = _p(keep(m.TdustSublime, np.float32), fp)
+        self.P = P
+
+        G = (OrGrid * m.nGrids)()
+        self.out = []
+        for i, g in enumerate(m.grids):
+            og = G[i]
+            og.nx, og.ny, og.nz, og.nCells, og.motherP = g.nx, g.ny, g.nz, g.nCells, g.motherP
+            gx, gy, gz = g.geoCorr
+            og.geoCorrX, og.geoCorrY, og.geoCorrZ = float(gx), float(gy), float(gz)
+            e = m.len_unit_exponent(g) if len_unit is None else int(round(np.log2(len_unit[i])))
+            og.invLenUnit = float(np.ldexp(1.0, -e))
+            arrs = dict(xAxis=keep(g.xAxis, np.float32), yAxis=keep(g.yAxis, np.float32), zAxis=keep(g.zAxis, np.float32))
+            og.xAxis, og.yAxis, og.zAxis = (_p(arrs[k], fp) for k in ("xAxis", "yAxis", "zAxis"))
+            act = _F(g.active, np.int32); self._keep.append(act); og.active = _p(act, ip)
+            for name in ("opacity", "scaOpac", "recPDF", "dustPDF", "linePDF", "totalLines", "Tdust"):
+                a = _F(getattr(g, name), np.float32)
+                self._keep.append(a)
+                setattr(og, name, _p(a, fp))
+            dai = _F(g.dustAbunIndex, np.int32); self._keep.append(dai); og.dustAbunIndex = _p(dai, ip)
+            tshape = (g.nCells + 1, m.nbins)
+            eshape = (g.nCells + 1, m.nbins + 1, m.nAngleBins + 1)
+            lshape = (g.nCells + 1, max(m.nLines, 1))
+            o = dict(lenExp=e)
+            if fp32_tallies:
+                o["Jste"] = np.zeros(tshape, np.float32, order="F")
+                o["escapedPackets"] = np.zeros(eshape, np.float32, order="F")
+                og.Jste, og.escapedPackets = _p(o["Jste"], fp), _p(o["escapedPackets"], fp)
+                if m.lgDebug:
+                    o["Jdif"] = np.zeros(tshape, np.float32, order="F")
+                    o["linePackets"] = np.zeros(lshape, np.float32, order="F")
+                    og.Jdif, og.linePackets = _p(o["Jdif"], fp), _p(o["linePackets"], fp)
+            if int_tallies:
+                o["JsteQ"] = np.zeros(tshape, np.int64, order="F")
+                o["escapedQ"] = np.zeros(eshape, np.int64, order="F")
+                og.JsteQ, og.escapedQ = _p(o["JsteQ"], lp), _p(o["escapedQ"], lp)
+                if m.lgDebug:
+                    o["JdifQ"] = np.zeros(tshape, np.int64, order="F")
+                    o["linePacketsQ"] = np.zeros(lshape, np.int64, order="F")
+                    og.JdifQ, og.linePacketsQ = _p(o["JdifQ"], lp), _p(o["linePacketsQ"], lp)
+            self.out.append(o)
+        self.G = G
+        self.qphotCounts = np.zeros(m.nbins, np.int64)
+
+    def transport(self, iStar: int, first: int, n: int, seed: int = 12345, gpLoc: int = 0, cellLoc=None,
+                  want_fates: bool = False, deltaE=None):
+        if deltaE is not None:
+            self.deltaE[iStar] = np.float32(deltaE)
+        cnt = OrCounters()
+        fates = np.zeros((n, 4), np.int32) if want_fates else None
+        cl = np.asarray(cellLoc, np.int32) if cellLoc is not None else None
+        rc = self.lib.oracle_transport(C.byref(self.P), self.G, iStar, first, n, C.c_uint64(seed), gpLoc,
+                                       _p(cl, ip), C.byref(cnt), _p(self.qphotCounts, lp), _p(fates, ip))
+        if rc != 0:
+            raise RuntimeError(f"oracle stop condition {rc}")
+        return cnt.as_dict(), fates
+
+    def transport_mt(self, iStar: int, first: int, n: int, seed: int = 12345, threads: int = 1):
+        cnt = OrCounters()
+        rc = self.lib.oracle_transport_mt(C.byref(self.P), self.G, iStar, first, n, C.c_uint64(seed), threads,
+                                          C.byref(cnt), _p(self.qphotCounts, lp))
+        if rc != 0:
+            raise RuntimeError(f"oracle stop condition {rc}")
+        return cnt.as_dict()
+
+    # the K4 fold in numpy: integer tallies -> float32 estimators, same arithmetic as
+    # mocassin_b200/csrc/tables.cu fold_j_kernel / fold_count_kernel
+    def folded(self, iG: int, deltaE: float, symmetric=None):
+        m = self.m
+        g = m.grids[iG - 1]
+        o = self.out[iG - 1]
+        sym = m.lgSymmetricXYZ if symmetric is None else symmetric
+        dV = g.cell_volumes(sym)
+        dV[0] = 1.0
+        unit = np.ldexp(1.0, o["lenExp"])
+        res = {}
+        for name in ("JsteQ", "JdifQ"):
+            if name in o:
+                length = (o[name].astype(np.float64) * unit).astype(np.float32)
+                J = (length * np.float32(deltaE)).astype(np.float32) / dV[:, None]
+                J = J.astype(np.float32)
+                J[0, :] = 0
+                res[name[:-1]] = np.asfortranarray(J)
+        res["escapedPackets"] = np.asfortranarray((o["escapedQ"].astype(np.float32) * np.float32(deltaE)).astype(np.float32))
+        if "linePacketsQ" in o:
+            res["linePackets"] = np.asfortranarray((o["linePacketsQ"].astype(np.float32) * np.float32(deltaE)).astype(np.float32))
+        return res

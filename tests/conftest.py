@@ -1,0 +1,29 @@
+import os
+import sys
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+
+def pytest_configure(config):
+    config.addinivalue_line("markers", "gpu: needs a CUDA device (run on the B200 box with -m gpu)")
+
+
+@pytest.fixture(scope="session")
+def oracle_lib():
+    from oracle import oracle as orc
+
+    orc.build()
+    return orc.load()
+
+
+@pytest.fixture(scope="session")
+def cuda_lib():
+    """The product library; GPU tests must run the CUDA path, never a fallback."""
+    from mocassin_b200 import _lib, build
+
+    build.build()
+    return _lib.load()

@@ -1,0 +1,58 @@
+"""The C-ABI library loads without a GPU and exports every symbol include/mcb200.h
+declares; without a device it fails loudly instead of falling back to the CPU."""
+import os
+import re
+import subprocess
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _declared():
+    src = open(os.path.join(ROOT, "include", "mcb200.h")).read()
+    src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+    return sorted(set(re.findall(r"\b(mcb200_[a-z_0-9]+)\s*\(", src)))
+
+
+def test_every_declared_symbol_is_exported(cuda_lib):
+    from mocassin_b200 import _lib
+
+    names = _declared()
+    assert len(names) >= 25
+    out = subprocess.run(["nm", "-D", "--defined-only", _lib.LIB_PATH], capture_output=True, text=True).stdout
+    exported = set(re.findall(r" T (mcb200_[a-z_0-9]+)", out))
+    assert set(names) <= exported, sorted(set(names) - exported)
+    assert sorted(_lib.EXPORTS) == names
+    for n in names:
+        assert hasattr(cuda_lib, n)
+
+
+def test_library_contains_sm100a_code_only(cuda_lib):
+    from mocassin_b200 import _lib
+
+    out = subprocess.run(["cuobjdump", "-lelf", _lib.LIB_PATH], capture_output=True, text=True).stdout
+    assert "sm_100a" in out
+    assert not re.search(r"sm_(?!100a)\d+", out)
+
+
+def test_no_cpu_fallback_without_device():
+    import torch
+
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    from mocassin_b200 import workloads as W
+    from mocassin_b200.api import MocassinError, PacketEngine
+
+    with pytest.raises(MocassinError):
+        PacketEngine(W.hii_region())
+
+
+def test_product_package_never_imports_oracle():
+    pkg = os.path.join(ROOT, "mocassin_b200")
+    for dirpath, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".h")):
+                text = open(os.path.join(dirpath, f)).read()
+                assert "import oracle" not in text and "from oracle" not in text and "oracle/" not in text.replace(
+                    "oracle/mc_oracle.c ERR_STOP", ""), f

@@ -1,0 +1,218 @@
+"""GPU parity tests: the CUDA path, called through the C ABI, against the CPU oracle on
+the same seeded inputs.  Bar: bit exact -- per-packet fates, every counter, every integer
+tally and the folded float32 estimators are identical."""
+import ctypes as C
+
+import numpy as np
+import pytest
+
+from cases import CASES, make
+from mocassin_b200 import _lib
+from mocassin_b200 import workloads as W
+from mocassin_b200.api import MocassinError, PacketEngine, partition
+from oracle.oracle import Oracle
+
+pytestmark = pytest.mark.gpu
+
+SEED = 12345
+
+
+def _engine(m, **kw):
+    e = PacketEngine(m, seed=SEED, **kw)
+    e.upload_iteration_inputs()
+    return e
+
+
+@pytest.fixture(scope="module")
+def ctx(cuda_lib):
+    h = C.c_void_p()
+    assert cuda_lib.mcb200_create(C.byref(h), 0, 0, 1, C.c_uint64(1)) == 0
+    yield h
+    cuda_lib.mcb200_destroy(h)
+
+
+@pytest.mark.parametrize("which,lo,hi", [(0, 2.0 ** -24, 1.0), (1, -7.0, 7.0), (2, -7.0, 7.0), (3, -1.0, 1.0), (4, -1e4, 1e4)])
+def test_device_detmath_is_bit_identical_to_oracle(cuda_lib, oracle_lib, ctx, which, lo, hi):
+    rng = np.random.default_rng(which + 10)
+    x = rng.uniform(lo, hi, 1 << 20).astype(np.float32)
+    x[:8] = np.float32([lo, hi, 1.0, 0.5, 0.70710677, 0.41421357, 0.99999994, 2.0 ** -24])[:8].clip(lo, hi)
+    a, b = np.zeros_like(x), np.zeros_like(x)
+    fp = _lib.c_float_p
+    assert cuda_lib.mcb200_test_detmath(ctx, which, x.ctypes.data_as(fp), a.ctypes.data_as(fp), x.shape[0]) == 0
+    oracle_lib.oracle_detmath(which, x.ctypes.data_as(fp), b.ctypes.data_as(fp), x.shape[0])
+    assert np.array_equal(a.view(np.uint32), b.view(np.uint32))
+
+
+def test_device_philox_stream_is_identical_to_oracle(cuda_lib, oracle_lib, ctx):
+    fp = _lib.c_float_p
+    for seed, pid, stream in [(12345, 0, 1), (2 ** 40 + 3, 2 ** 33 + 17, 0), (0, 999999937, 7)]:
+        a, b = np.zeros(1001, np.float32), np.zeros(1001, np.float32)
+        assert cuda_lib.mcb200_test_uniforms(ctx, seed, pid, stream, a.shape[0], a.ctypes.data_as(fp)) == 0
+        oracle_lib.oracle_uniforms(seed, pid, stream, b.shape[0], b.ctypes.data_as(fp))
+        assert np.array_equal(a, b)
+
+
+def _compare(m, n, e, o, iStar=1):
+    e.set_option("trace", 1)
+    e.zero_estimators()
+    cg = e.energyPacketDriver(iStar, n)
+    co, fo = o.transport(iStar, 0, n, seed=SEED, want_fates=True)
+    fg = e.fates(n)
+    bad = np.flatnonzero((fg != fo).any(axis=1))
+    assert bad.size == 0, f"{bad.size} packets differ, first {bad[:5]}: gpu {fg[bad[:5]]} oracle {fo[bad[:5]]}"
+    for k in ("nAbs", "nSca", "trapped", "nLinePackets", "nDropped", "nSegments", "nFlights", "nEscaped", "nEarlyEscaped"):
+        assert cg[k] == co[k], k
+    assert cg["nPackets"] == n
+    assert np.array_equal(e.qphot_counts(), o.qphotCounts)
+    dE = float(m.deltaE[iStar])
+    want = ["Jste", "escapedPackets"] + (["Jdif", "linePackets"] if m.lgDebug else [])
+    for iG in range(1, m.nGrids + 1):
+        assert e.len_unit(iG) == np.ldexp(1.0, o.out[iG - 1]["lenExp"])
+        fold = o.folded(iG, dE)
+        got = e.fetch(iG, want=want)
+        for k in want:
+            a, b = got[k], fold[k]
+            if k in ("Jste", "Jdif"):
+                a, b = a[1:], b[1:]
+            assert np.array_equal(a.view(np.uint32), b.view(np.uint32)), (iG, k)
+        # the fold cleared the integer tallies
+        t = e.fetch_tallies(iG)
+        assert not t["JsteQ"].any() and not t["escapedQ"].any()
+    return cg, co
+
+
+@pytest.mark.parametrize("name", list(CASES))
+def test_transport_bit_exact_vs_oracle(name):
+    m, n = make(name)
+    e = _engine(m)
+    o = Oracle(m)
+    cg, co = _compare(m, n, e, o)
+    # Qphot (float64 from exact counts) agrees with the reference's float32 running sum
+    if co["Qphot"] > 0:
+        assert abs(cg["Qphot"] / co["Qphot"] - 1) < 1e-3
+    e.close()
+
+
+def test_integer_tallies_before_fold_match_oracle():
+    """nranks=2 keeps the integer tallies pending: compare them raw (rows >= 1 of J; row 0
+    is the inactive-cell sink the device skips), then reduce."""
+    m, n = make("dust_shell_hg")
+    e0 = _engine(m, rank=0, nranks=2)
+    e1 = _engine(m, rank=1, nranks=2)
+    o = Oracle(m, fp32_tallies=False)
+    o.transport(1, 0, n, seed=SEED)
+    e0.zero_estimators(); e1.zero_estimators()
+    c0 = e0.energyPacketDriver(1, n)
+    c1 = e1.energyPacketDriver(1, n)
+    assert c0["nPackets"] == partition(n, 0, 2)[1] and c1["nPackets"] == partition(n, 1, 2)[1]
+    t0, t1 = e0.fetch_tallies(1), e1.fetch_tallies(1)
+    assert np.array_equal((t0["JsteQ"] + t1["JsteQ"])[1:], o.out[0]["JsteQ"][1:])
+    assert np.array_equal(t0["escapedQ"] + t1["escapedQ"], o.out[0]["escapedQ"])
+    with pytest.raises(MocassinError):
+        e0.fetch(1)                      # pending tallies must be reduced first
+    e0.close(); e1.close()
+
+
+def test_determinism_and_seed_sensitivity():
+    m, n = make("cube_clumpy_gasdust")
+    res = []
+    for seed, bps in ((SEED, 0), (SEED, 1), (SEED + 1, 0)):
+        e = PacketEngine(m, seed=seed)
+        e.upload_iteration_inputs()
+        if bps:
+            e.set_option("blocks_per_sm", bps)      # different schedule, same answer
+        e.zero_estimators()
+        e.energyPacketDriver(1, n)
+        res.append(e.fetch(1))
+        e.close()
+    assert np.array_equal(res[0]["Jste"], res[1]["Jste"])
+    assert np.array_equal(res[0]["escapedPackets"], res[1]["escapedPackets"])
+    assert not np.array_equal(res[0]["Jste"], res[2]["Jste"])
+
+
+def test_two_calls_accumulate_like_the_reference():
+    """Two stars' worth of transport calls accumulate into the same estimators
+    (iteration_mod.f90:474-496 loops over iStar without zeroing in between)."""
+    m, n = make("hii_sym_gas")
+    e = _engine(m)
+    o = Oracle(m)
+    e.zero_estimators()
+    e.energyPacketDriver(1, n)
+    a = e.fetch(1)
+    e.energyPacketDriver(1, n, deltaE=float(m.deltaE[1]) * 0.5)
+    b = e.fetch(1)
+    o.transport(1, 0, n, seed=SEED)
+    f = o.folded(1, float(m.deltaE[1]))
+    h = o.folded(1, float(m.deltaE[1]) * 0.5)
+    assert np.array_equal(a["Jste"][1:], f["Jste"][1:])
+    assert np.array_equal(b["Jste"][1:], (f["Jste"] + h["Jste"]).astype(np.float32)[1:])
+    assert np.array_equal(b["escapedPackets"], (f["escapedPackets"] + h["escapedPackets"]).astype(np.float32))
+    e.zero_estimators()
+    assert not e.fetch(1)["Jste"].any()
+    e.close()
+
+
+def test_diffuse_external_source():
+    """energyPacketDriver(iStar=0, n, grid, gpLoc, cellLoc) (iteration_mod.f90:498-550)."""
+    m, n = make("cube_clumpy_gasdust")
+    m.inSpectrumProbDen[0, :] = W.blackbody_cdf(20000.0, m.nuArray, np.gradient(m.nuArray).astype(np.float32))
+    m.deltaE[0] = 3.0e-6
+    e = _engine(m)
+    o = Oracle(m)
+    e.set_option("trace", 1)
+    e.zero_estimators()
+    cell = [5, 7, 9]
+    cg = e.energyPacketDriver(0, 4000, gpLoc=1, cellLoc=cell)
+    co, fo = o.transport(0, 0, 4000, seed=SEED, gpLoc=1, cellLoc=cell, want_fates=True)
+    assert np.array_equal(e.fates(4000), fo)
+    assert cg["nSegments"] == co["nSegments"]
+    got, want = e.fetch(1), o.folded(1, float(m.deltaE[0]))
+    assert np.array_equal(got["Jste"][1:], want["Jste"][1:])
+    assert np.array_equal(got["escapedPackets"], want["escapedPackets"])
+    e.close()
+
+
+def test_error_behaviour():
+    m, n = make("hii_sym_gas")
+    e = PacketEngine(m, seed=SEED)
+    with pytest.raises(MocassinError) as ei:          # transport before opacities are set
+        e.energyPacketDriver(1, 10)
+    assert ei.value.code == -3
+    e.set_opacity()
+    bad = m.grids[0].recPDF.copy(order="F")
+    bad[5, 100] = 2.0                                  # non-monotone CDF row
+    good = m.grids[0].recPDF
+    m.grids[0].recPDF = bad
+    with pytest.raises(MocassinError) as ei:
+        e.set_pdfs()
+    assert ei.value.code == -7
+    m.grids[0].recPDF = good
+    e.set_pdfs()
+    with pytest.raises(MocassinError):
+        e.energyPacketDriver(2, 10)                    # iStar out of range
+    with pytest.raises(MocassinError):
+        e.energyPacketDriver(1, -1)
+    assert e.energyPacketDriver(1, 0)["nPackets"] == 0  # empty input
+    assert e.energyPacketDriver(1, 1)["nPackets"] == 1  # ragged: fewer packets than a warp
+    e.close()
+    m2 = W.hii_region()
+    m2.lgPlaneIonization = True
+    with pytest.raises(MocassinError) as ei:
+        PacketEngine(m2)
+    assert ei.value.code == -6
+
+
+def test_packet_reaching_a_reference_stop_is_reported():
+    """nuP >= nbins is fatal in the reference (photon_mod.f90:826-832): a stellar CDF that
+    reaches 1 only in its last bin can return nbins-1 at most, so force the condition with
+    a CDF that is 0 everywhere (u >= cdf for all bins -> nuP = nbins)."""
+    m, n = make("hii_sym_gas")
+    m.inSpectrumProbDen[1, :] = 0.0
+    e = _engine(m)
+    with pytest.raises(MocassinError) as ei:
+        e.energyPacketDriver(1, 100)
+    assert ei.value.code == -5
+    o = Oracle(m)
+    with pytest.raises(RuntimeError):
+        o.transport(1, 0, 100, seed=SEED)
+    e.close()
