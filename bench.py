@@ -1,0 +1,398 @@
+#!/usr/bin/env python
+"""bench.py -- propagated energy packets per second of the transport hot path.
+
+Workload (config.workload): BASELINE.md "S-clumpy": 128^3 full cube, star at the centre,
+log-normal clumpy gas + dust, nbins=600, Philox seed 12345.  One *step* = one pass of
+the hot path over one batch of packets: `mcb200_transport` (emission + transport kernel)
+followed by the fold epilogue, i.e. `call energyPacketDriver` + the estimator merge of one
+Lucy iteration (iteration_mod.f90:474-726).  Weak scaling: every GPU transports
+--packets packets per step against a replicated grid; for N>1 the integer tallies are
+summed with an NCCL all-reduce inside the step (the path's one real exchange).
+
+  python bench.py [--gpus N] [--steps K] [--warmup W]            # this implementation
+  python bench.py --impl reference ...                            # CPU arm (oracle port)
+
+Prints ONE JSON line (rank 0).
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+SEED = 12345
+ALG_BYTES_PER_SEGMENT = 16       # active 4 + opacity 4 + Jste 4 read + 4 write
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--grid", type=int, default=128)
+    ap.add_argument("--nbins", type=int, default=600)
+    ap.add_argument("--packets", type=int, default=0, help="packets per GPU per step (0 = default)")
+    ap.add_argument("--workload", default="clumpy", choices=["clumpy", "uniform"])
+    ap.add_argument("--cpu-seconds", type=float, default=15.0, help="target CPU-baseline sample time")
+    ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-cpu", action="store_true")
+    return ap.parse_args()
+
+
+def build_model(args, tables: bool):
+    from mocassin_b200 import workloads as W
+
+    return W.synthetic_cube(n=args.grid, nbins=args.nbins, clumpy=(args.workload == "clumpy"), dust=True,
+                            nPhotons=10 ** 9, seed=2024, build_tables=tables)
+
+
+def compact_inputs(model):
+    """The per-cell inputs of K1 for this workload: 3 gas species columns + dust."""
+    from mocassin_b200 import workloads as W
+    from mocassin_b200.model import F32, I32
+
+    g = model.grids[0]
+    f = model._fields3d
+    nu = model.nuArray
+    sH, sHe, sHe2 = W.gas_cross_sections(nu)
+    cabs, csca, gs = W.dust_optics(nu)
+    model.gSca = gs
+    nb = model.nbins
+    xsec = np.concatenate([sH, sHe, sHe2, csca, cabs]).astype(F32)
+    Hd, x = f["Hden"], f["xH0"]
+    den = np.zeros((g.nCells + 1, 3), dtype=F32, order="F")
+    den[:, 0] = W._per_cell(g.active, Hd * x, g.nCells)
+    den[:, 1] = W._per_cell(g.active, 0.1 * Hd * np.minimum(1.0, 3.0 * x), g.nCells)
+    den[:, 2] = W._per_cell(g.active, 0.1 * Hd * (1.0 - np.minimum(1.0, 3.0 * x)) * 0.9, g.nCells)
+    bands = dict(species=np.array([1, 2, 3], I32), off=np.array([0, nb, 2 * nb], I32),
+                 low=np.array([1, 1, 1], I32), high=np.array([nb, nb, nb], I32))
+    Nd = W._per_cell(g.active, f["Ndust"], g.nCells)
+    Td = np.full((2, 2, g.nCells + 1), 50.0, dtype=F32, order="F")
+    dust = dict(Ndust=Nd, Tdust=Td, dustAbunIndex=None, grainWeight=np.ones(1, F32),
+                dustScaXsecP=np.array([[3 * nb + 1]], I32), dustAbsXsecP=np.array([[4 * nb + 1]], I32))
+    g.Tdust = Td
+    g.dustAbunIndex = np.ones(g.nCells + 1, dtype=I32)
+    return xsec, bands, den, dust
+
+
+def rec_tables(model, rng):
+    from mocassin_b200 import workloads as W
+    from mocassin_b200.model import F32
+
+    g = model.grids[0]
+    nu = model.nuArray
+    wid = np.gradient(nu).astype(F32)
+    Tes = np.linspace(6000.0, 12000.0, 16)
+    table = np.stack([W.recombination_cdf(nu, wid, T) for T in Tes]).astype(F32)
+    idx = rng.integers(0, 16, size=g.nCells + 1)
+    tl = np.zeros(g.nCells + 1, dtype=F32)
+    tl[1:] = (0.55 + 0.2 * rng.random(g.nCells)).astype(F32)
+    return table, idx, tl
+
+
+class ClockSampler(threading.Thread):
+    """nvidia-smi clocks/throttle reasons during the timed region (B200_PROFILING.md)."""
+
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index: int):
+        super().__init__(daemon=True)
+        self.index = index
+        self.rows = []
+        self.stop_flag = False
+        self.proc = None
+
+    def run(self):
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "200"],
+                stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            for line in self.proc.stdout:
+                self.rows.append([c.strip() for c in line.split(",")])
+                if self.stop_flag:
+                    break
+        except Exception:
+            pass
+
+    def finish(self):
+        self.stop_flag = True
+        if self.proc:
+            self.proc.terminate()
+        sm, mx, reasons = [], [], set()
+        for r in self.rows:
+            try:
+                sm.append(float(r[0])); mx.append(float(r[1]))
+                for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[3:7]):
+                    if v.lower().startswith("active"):
+                        reasons.add(name)
+            except Exception:
+                continue
+        if not sm:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
+        return {"sm_mhz": float(np.median(sm)), "sm_max_mhz": float(max(mx)), "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def measured_peak():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        try:
+            return float(json.load(open(p))["hbm_gbs"]), "measured"
+        except Exception:
+            pass
+    return 6650.0, "fallback"
+
+
+def ncu_traffic():
+    p = os.path.join(ROOT, "profiles", "transport_traffic.json")
+    if os.path.exists(p):
+        try:
+            return json.load(open(p))
+        except Exception:
+            return None
+    return None
+
+
+def default_packets(args):
+    return args.packets if args.packets > 0 else 16_000_000
+
+
+# ---------------------------------------------------------------------------------------
+def run_reference(args):
+    """CPU arm: the oracle port (faithful restatement of photon_mod.f90, -O2) on all host
+    cores, packets split with the reference's load/rest rule, replicated read-only tables,
+    shared integer tallies.  The reference binary itself cannot be built here (no Fortran
+    compiler)."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    from mocassin_b200 import workloads as W
+    from oracle.oracle import Oracle
+
+    cores = os.cpu_count() or 1
+    t0 = time.time()
+    model = build_model(args, tables=True)
+    g = model.grids[0]
+    g.absOpac = None
+    o = Oracle(model, fp32_tallies=False)
+    build_s = time.time() - t0
+    # size the per-step sample for ~cpu-seconds of work
+    t = time.time(); c = o.transport_mt(1, 0, 20000, seed=SEED, threads=cores); dt = time.time() - t
+    rate = 20000 / max(dt, 1e-6)
+    sample = int(max(20000, min(rate * args.cpu_seconds, 50_000_000)))
+    first = 20000
+    for _ in range(args.warmup):
+        o.transport_mt(1, first, sample, seed=SEED, threads=cores); first += sample
+    segs = 0
+    t = time.time()
+    for _ in range(args.steps):
+        c = o.transport_mt(1, first, sample, seed=SEED, threads=cores); first += sample
+        segs += c["nSegments"]
+    dt = time.time() - t
+    value = sample * args.steps / dt
+    line = {
+        "impl": "reference", "metric": "energy packets/sec", "value": value, "unit": "packets/s",
+        "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": workload_config(args, sample),
+        "cpu_baseline": {"value": value, "unit": "packets/s", "cores": cores, "kind": "port",
+                         "sample": f"{sample} packets/step x {args.steps} steps of the same 128^3 workload, "
+                                   f"oracle port (-O2), {cores} threads; table build {build_s:.0f}s untimed"},
+        "e2e": {"value": value, "unit": "packets/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "segments_per_packet": segs / (sample * args.steps),
+    }
+    print(json.dumps(line), flush=True)
+
+
+def workload_config(args, packets):
+    return {"workload": f"S-{args.workload} {args.grid}^3 gas+dust nebula, nbins={args.nbins}, star at centre, "
+                        f"Philox seed {SEED}", "grid": args.grid, "nbins": args.nbins,
+            "packets_per_gpu_per_step": int(packets),
+            "cache": "inputs larger than L2 (opacity/scaOpac/recPDF/Jste tables 5-10 GB each)",
+            "parallelism": f"packets sharded over {args.gpus} GPU(s), grid replicated"}
+
+
+# ---------------------------------------------------------------------------------------
+def run_b200(args):
+    import torch
+    import torch.distributed as dist
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        torch.cuda.set_device(local)
+        dist.init_process_group("nccl", device_id=torch.device(f"cuda:{local}"))
+    else:
+        torch.cuda.set_device(local)
+    from mocassin_b200.api import PacketEngine
+    from mocassin_b200.model import F32
+
+    P = default_packets(args)
+    model = build_model(args, tables=False)
+    g = model.grids[0]
+    xsec, bands, den, dust = compact_inputs(model)
+    rng = np.random.default_rng(2025)
+    table, idx, tl = rec_tables(model, rng)
+    nRows, nb = g.nCells + 1, model.nbins
+
+    # pinned host buffers for the per-iteration inputs/outputs of the e2e path
+    def pinned(shape, dtype=torch.float32):
+        n = int(np.prod(shape))
+        t = torch.empty(n, dtype=dtype, pin_memory=True)
+        return t, t.numpy().reshape(shape, order="F")
+
+    keep = []
+    t_rec, recPDF = pinned((nRows, nb)); keep.append(t_rec)
+    np.take(table.T, idx, axis=1, out=recPDF.T)
+    recPDF[0, :] = 0.0
+    g.recPDF, g.totalLines = recPDF, tl
+
+    eng = PacketEngine(model, device=local, rank=rank, nranks=world, seed=SEED)
+    eng.set_xsec(xsec)
+
+    def upload_inputs():
+        eng.assemble_opacity(1, bands, den, None, dust)       # K1 on device
+        eng.set_pdfs()
+        eng.set_dust_state()
+
+    upload_inputs()
+    nGlobal = P * world
+    dE = float(model.deltaE[1])
+
+    def step():
+        c = eng.energyPacketDriver(1, nGlobal, deltaE=dE)
+        if world > 1:
+            eng.reduce()
+        return c
+
+    eng.zero_estimators()
+    for _ in range(args.warmup):
+        step()
+    sampler = ClockSampler(local) if rank == 0 else None
+    if sampler:
+        sampler.start()
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    kms, tms, segs, flights = 0.0, 0.0, 0, 0
+    for _ in range(args.steps):
+        ts = time.perf_counter()
+        c = step()
+        wall_ms = 1e3 * (time.perf_counter() - ts)
+        kms += c["kernel_ms"]
+        tms += c["total_ms"] if world == 1 else wall_ms      # N>1: include the all-reduce + fold
+        segs += c["nSegments"]; flights += c["nFlights"]
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    wall = time.perf_counter() - t0
+    clocks = sampler.finish() if sampler else None
+    # max over ranks of the device-timed step time
+    tt = torch.tensor([tms, kms, float(segs), wall], dtype=torch.float64, device="cuda")
+    if world > 1:
+        mx = tt.clone(); dist.all_reduce(mx, op=dist.ReduceOp.MAX)
+        sm = tt.clone(); dist.all_reduce(sm, op=dist.ReduceOp.SUM)
+        tms_max, kms_max, wall_max = float(mx[0]), float(mx[1]), float(mx[3])
+        segs_all = float(sm[2])
+    else:
+        tms_max, kms_max, wall_max, segs_all = tms, kms, wall, float(segs)
+    value = nGlobal * args.steps / (tms_max / 1e3)
+
+    # ---- e2e through the public API with host buffers (rank-local copies inside) -------
+    e2e = None
+    if not args.no_e2e:
+        t_J, Jh = pinned((nRows, nb)); t_E, Eh = pinned((nRows, nb + 1, 1)); keep += [t_J, t_E]
+        nE = 2 if args.steps > 2 else args.steps
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+        te = time.perf_counter()
+        for _ in range(nE):
+            upload_inputs()                                   # H2D: den, Ndust, Tdust, recPDF, totalLines
+            eng.zero_estimators()
+            step()
+            eng.fetch(1, out={"Jste": Jh, "escapedPackets": Eh})   # D2H
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        dte = time.perf_counter() - te
+        if world > 1:
+            tmax = torch.tensor([dte], dtype=torch.float64, device="cuda"); dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
+            dte = float(tmax[0])
+        h2d = recPDF.nbytes + tl.nbytes + den.nbytes + dust["Ndust"].nbytes + dust["Tdust"].nbytes + 4 * (g.nCells + 1)
+        d2h = Jh.nbytes + Eh.nbytes
+        e2e = {"value": nGlobal * nE / dte, "unit": "packets/s", "h2d_bytes_per_step": int(h2d),
+               "d2h_bytes_per_step": int(d2h), "steps": nE,
+               "path": "assemble_opacity+set_pdfs+set_dust_state (H2D from pinned host) -> zero_estimators -> "
+                       "energyPacketDriver -> fetch Jste+escapedPackets (D2H to pinned host)"}
+
+    if rank != 0:
+        if world > 1:
+            dist.barrier(); dist.destroy_process_group()
+        return
+
+    peak, peak_kind = measured_peak()
+    ach = ALG_BYTES_PER_SEGMENT * segs / (kms / 1e3) / 1e9        # rank 0's kernel
+    tr = ncu_traffic()
+    roofline = {"bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak,
+                "traffic": (tr or {}).get("dram_bytes_per_launch"), "peak_kind": f"of {peak_kind}",
+                "kernel": "mcb::transport_kernel<false>", "algorithmic_bytes_per_segment": ALG_BYTES_PER_SEGMENT,
+                "segments_per_launch": segs / args.steps, "kernel_ms_per_launch": kms / args.steps,
+                "segments_per_s": segs / (kms / 1e3)}
+    cpu = None
+    if not args.no_cpu and world == 1:
+        cpu = cpu_baseline(args, eng, model, g)
+    line = {
+        "metric": "energy packets/sec", "value": value, "unit": "packets/s", "n_gpus": world,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": tms_max / args.steps,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": workload_config(args, P), "clocks": clocks, "e2e": e2e,
+        "gpu_launches": int(args.steps * 3),      # transport_kernel + fold_j_kernel + fold_count_kernel per step
+        "roofline": roofline, "cpu_baseline": cpu,
+        "segments_per_packet": segs_all / (nGlobal * args.steps),
+        "flights_per_packet": flights / (P * args.steps),
+        "kernel_ms_per_step": kms_max / args.steps, "wall_ms_per_step": 1e3 * wall_max / args.steps,
+    }
+    print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.barrier(); dist.destroy_process_group()
+
+
+def cpu_baseline(args, eng, model, g):
+    """Oracle port timed on this box's host cores on a bounded sample of the same workload
+    (tables read back from the device so both sides use identical inputs)."""
+    from oracle.oracle import Oracle
+
+    cores = os.cpu_count() or 1
+    op, sca, _ = eng.get_opacity(1)
+    g.opacity, g.scaOpac = op, sca
+    o = Oracle(model, fp32_tallies=False)
+    t = time.time(); o.transport_mt(1, 0, 20000, seed=SEED, threads=cores); dt = time.time() - t
+    rate = 20000 / max(dt, 1e-6)
+    sample = int(max(20000, min(rate * args.cpu_seconds, 50_000_000)))
+    t = time.time(); c = o.transport_mt(1, 20000, sample, seed=SEED, threads=cores); dt = time.time() - t
+    return {"value": sample / dt, "unit": "packets/s", "cores": cores, "kind": "port",
+            "sample": f"{sample} packets of the same workload in {dt:.1f}s, oracle port (-O2) on {cores} threads",
+            "segments_per_packet": c["nSegments"] / sample}
+
+
+if __name__ == "__main__":
+    a = parse()
+    if a.impl == "reference":
+        run_reference(a)
+    else:
+        run_b200(a)

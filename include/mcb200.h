@@ -72,7 +72,8 @@ typedef struct mcb200_counters {
     int64_t nEscaped;              /* escape tallies                                    */
     int64_t nEarlyEscaped;         /* of which at energyPacketRun :370                  */
     double  Qphot;                 /* sum deltaE/(2.1799153e-11*nu), nu>1 Ryd (:859-861)*/
-    double  kernel_ms;             /* device time of the transport kernel(s)            */
+    double  kernel_ms;             /* device time of the transport kernel (CUDA events)  */
+    double  total_ms;              /* device time transport kernel + fold epilogue        */
 } mcb200_counters;
 
 /* ---- lifecycle ---------------------------------------------------------------- */

@@ -139,7 +139,7 @@ class PacketEngine:
                                                 _fp(_f(m.gSca)) if m.gSca is not None else None, _fp(cdf)))
         if m.nStars > 0:
             pos = np.ascontiguousarray(m.starPosition, dtype=F32)     # x,y,z triplets per star
-            idx = _f(np.asarray(m.starIndeces, dtype=I32))            # (nStars,4) star fastest
+            idx = _f(np.asarray(m.starIndeces, dtype=I32), I32)       # (nStars,4) star fastest
             self._check(self.lib.mcb200_set_stars(self.h, _fp(pos), _ip(idx)))
         if m.nAngleBins > 0:
             self._check(self.lib.mcb200_set_viewpoints(
@@ -264,14 +264,20 @@ class PacketEngine:
 
         return torch.cuda.current_device()
 
-    def fetch(self, iG: int = 1, want=("Jste", "escapedPackets")) -> dict:
+    def fetch(self, iG: int = 1, want=("Jste", "escapedPackets"), out: Optional[dict] = None) -> dict:
         """Raw estimator sums in the reference's layouts (before the host scaling of
-        iteration_mod.f90:705-724)."""
+        iteration_mod.f90:705-724).  `out` may hold preallocated (e.g. pinned) F-order
+        arrays for "Jste" / "escapedPackets"."""
         m = self.model
         g = m.grids[iG - 1]
+        pre = out or {}
         out = {}
-        J = np.zeros((g.nCells + 1, m.nbins), dtype=F32, order="F") if "Jste" in want else None
-        E = np.zeros((g.nCells + 1, m.nbins + 1, m.nAngleBins + 1), dtype=F32, order="F") if "escapedPackets" in want else None
+        J = pre.get("Jste") if "Jste" in want else None
+        E = pre.get("escapedPackets") if "escapedPackets" in want else None
+        if J is None and "Jste" in want:
+            J = np.zeros((g.nCells + 1, m.nbins), dtype=F32, order="F")
+        if E is None and "escapedPackets" in want:
+            E = np.zeros((g.nCells + 1, m.nbins + 1, m.nAngleBins + 1), dtype=F32, order="F")
         D = np.zeros((g.nCells + 1, m.nbins), dtype=F32, order="F") if "Jdif" in want else None
         Lp = np.zeros((g.nCells + 1, max(m.nLines, 1)), dtype=F32, order="F") if "linePackets" in want else None
         self._check(self.lib.mcb200_fetch_estimators(self.h, iG, _fp(J), _fp(E), _fp(D), _fp(Lp)))

@@ -123,7 +123,7 @@ struct mcb200_ctx {
     bool pending = false;
     float pendingDeltaE = 0.f;
     std::string err;
-    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr, ev2 = nullptr;
 };
 
 namespace {
@@ -360,11 +360,20 @@ int run_transport(mcb200_ctx *ctx, int iStar, int difGrid, const int32_t *cellLo
         out->nEscaped = (int64_t)hc[C_ESCAPED]; out->nEarlyEscaped = (int64_t)hc[C_EARLY];
         out->Qphot = Q;
         out->kernel_ms = ms;
+        out->total_ms = ms;
     }
     ctx->pending = true;
     ctx->pendingDeltaE = deltaE;
     if (herr) return fail(ctx, MCB200_EPACKET, "a packet hit reference stop condition %d (see oracle/mc_oracle.c ERR_STOP codes)", herr);
-    if (ctx->nranks == 1) return fold_pending(ctx);
+    if (ctx->nranks == 1) {
+        int rcf = fold_pending(ctx);
+        if (rcf) return rcf;
+        CU(cudaEventRecord(ctx->ev2, ctx->stream));
+        CU(cudaEventSynchronize(ctx->ev2));
+        float ms2 = 0.f;
+        CU(cudaEventElapsedTime(&ms2, ctx->ev0, ctx->ev2));
+        if (out) out->total_ms = ms2;
+    }
     return MCB200_OK;
 }
 
@@ -411,6 +420,7 @@ int mcb200_create(mcb200_ctx **pctx, int32_t device, int32_t rank, int32_t nrank
     if (cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) != cudaSuccess) { delete ctx; return MCB200_ENODEV; }
     cudaEventCreate(&ctx->ev0);
     cudaEventCreate(&ctx->ev1);
+    cudaEventCreate(&ctx->ev2);
     *pctx = ctx;
     return MCB200_OK;
 }
@@ -422,6 +432,7 @@ int mcb200_destroy(mcb200_ctx *ctx)
     cudaStreamSynchronize(ctx->stream);
     if (ctx->ev0) cudaEventDestroy(ctx->ev0);
     if (ctx->ev1) cudaEventDestroy(ctx->ev1);
+    if (ctx->ev2) cudaEventDestroy(ctx->ev2);
     ctx->grids.clear();
     cudaStream_t s = ctx->stream;
     delete ctx;
@@ -531,9 +542,12 @@ int mcb200_set_spectra(mcb200_ctx *ctx, const float *nuArray, const float *gSca,
     std::vector<float> rows((size_t)ns * nb);
     for (int s = 0; s < ns; ++s)
         for (int i = 0; i < nb; ++i) rows[(size_t)s * nb + i] = inSpectrumProbDen[(size_t)s + (size_t)ns * i];
+    // Uniforms are < 1, so only min(cdf,1) matters to getNu2's scan: setProbDen forces just
+    // the entries >= max to 1 (continuum_mod.f90:454-467) and a float32 running sum that
+    // overshoots 1 legitimately leaves e.g. [.., 1.0000001, 1, 1] behind.
     for (int s = 1; s < ns; ++s)
         for (int i = 1; i < nb; ++i)
-            if (!(rows[(size_t)s * nb + i] >= rows[(size_t)s * nb + i - 1]))
+            if (!(std::fmin(rows[(size_t)s * nb + i], 1.f) >= std::fmin(rows[(size_t)s * nb + i - 1], 1.f)))
                 return fail(ctx, MCB200_ETABLE, "inSpectrumProbDen(%d,:) is not non-decreasing at bin %d", s, i + 1);
     CU(ctx->starCdf.upload(rows.data(), rows.size(), ctx->stream));
     CU(cudaStreamSynchronize(ctx->stream));

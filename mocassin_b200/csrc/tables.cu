@@ -35,7 +35,8 @@ __global__ void check_monotone_kernel(const float *__restrict__ pdfT, int nRows,
     if (i >= total) return;
     size_t row = i / (nb - 1), k = i % (nb - 1);
     if (row == 0) return;                 // row 0 (inactive sink) is never sampled
-    float a = pdfT[row * nb + k], b = pdfT[row * nb + k + 1];
+    // uniforms are < 1: only min(cdf,1) matters to the scan (see mcb200_set_spectra)
+    float a = fminf(pdfT[row * nb + k], 1.f), b = fminf(pdfT[row * nb + k + 1], 1.f);
     if (!(b >= a)) atomicExch(bad, 1);
 }
 

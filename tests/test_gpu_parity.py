@@ -189,7 +189,7 @@ def test_error_behaviour():
     m.grids[0].recPDF = good
     e.set_pdfs()
     with pytest.raises(MocassinError):
-        e.energyPacketDriver(2, 10)                    # iStar out of range
+        e.energyPacketDriver(2, 10, deltaE=1.0)        # iStar out of range
     with pytest.raises(MocassinError):
         e.energyPacketDriver(1, -1)
     assert e.energyPacketDriver(1, 0)["nPackets"] == 0  # empty input
