@@ -100,6 +100,31 @@ def rec_tables(model, rng):
     return table, idx, tl
 
 
+def host_tables(model):
+    """The same tables the device path builds (K1 + rec_tables), assembled with numpy in the
+    same float32 operation order, for the CPU arm."""
+    from mocassin_b200 import workloads as W
+    from mocassin_b200.model import F32
+
+    g = model.grids[0]
+    nb = model.nbins
+    xsec, bands, den, dust = compact_inputs(model)
+    sH, sHe, sHe2, csca, cabs = (xsec[i * nb:(i + 1) * nb] for i in range(5))
+    op = W._expand(den[:, 0], sH)
+    op += W._expand(den[:, 1], sHe)
+    op += W._expand(den[:, 2], sHe2)
+    sca = W._expand(dust["Ndust"], csca)
+    ab = W._expand(dust["Ndust"], cabs)
+    ab += sca
+    op += ab
+    del ab
+    g.opacity, g.scaOpac, g.absOpac = op, sca, None
+    table, idx, tl = rec_tables(model, np.random.default_rng(2025))
+    g.recPDF = W._rows_from_table(idx, table)
+    g.recPDF[0, :] = 0.0
+    g.totalLines = tl
+
+
 class ClockSampler(threading.Thread):
     """nvidia-smi clocks/throttle reasons during the timed region (B200_PROFILING.md)."""
 
@@ -182,9 +207,9 @@ def run_reference(args):
 
     cores = os.cpu_count() or 1
     t0 = time.time()
-    model = build_model(args, tables=True)
+    model = build_model(args, tables=False)
     g = model.grids[0]
-    g.absOpac = None
+    host_tables(model)
     o = Oracle(model, fp32_tallies=False)
     build_s = time.time() - t0
     # size the per-step sample for ~cpu-seconds of work

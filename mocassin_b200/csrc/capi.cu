@@ -206,6 +206,13 @@ int sync_grids(mcb200_ctx *ctx)
         d.nx = g.nx; d.ny = g.ny; d.nz = g.nz; d.nCells = g.nCells; d.motherP = g.motherP;
         d.dense = g.dense;
         d.geoX = g.geo[0]; d.geoY = g.geo[1]; d.geoZ = g.geo[2];
+        d.x1 = g.hx.front(); d.y1 = g.hy.front(); d.z1 = g.hz.front();
+        d.xN = g.hx.back();  d.yN = g.hy.back();  d.zN = g.hz.back();
+        {
+            volatile float t;
+            t = d.x1 - d.geoX; d.xLo = t; t = d.y1 - d.geoY; d.yLo = t; t = d.z1 - d.geoZ; d.zLo = t;
+            t = d.xN + d.geoX; d.xHi = t; t = d.yN + d.geoY; d.yHi = t; t = d.zN + d.geoZ; d.zHi = t;
+        }
         d.invLenUnit = std::ldexp(1.0f, -g.lenExp);
         d.xAxis = g.xAxis.p; d.yAxis = g.yAxis.p; d.zAxis = g.zAxis.p;
         d.xWall = g.xWall.p; d.yWall = g.yWall.p; d.zWall = g.zWall.p;

@@ -9,8 +9,12 @@
 //    immediately pulls the next global packet index (warp-aggregated atomic), so the
 //    32 lanes of a warp stay busy although packets live for 1..5000 generations;
 //  * the three nested loops of the reference (packets / generations / cell crossings)
-//    are flattened into one warp-level loop over a per-lane phase (NEED, EMIT, FLY):
-//    every trip executes at most one emission and exactly one cell crossing per lane;
+//    are flattened into one warp-level loop over a per-lane phase (NEED, EMIT, FLY,
+//    SCATTER, ESCAPE): every trip executes exactly one cell crossing for the flying
+//    lanes; the rare, expensive phases (emission = Philox + CDF search + sincos + log,
+//    scattering = Henyey-Greenstein, escape = acos/atan binning) are *deferred* until
+//    kBatch lanes of the warp wait for the same phase (or nothing is left to fly), so
+//    they run with many active lanes instead of one (ncu: 1.2 -> see profiles/);
 //  * counter-based Philox4x32-10 stream per packet (philox.cuh): results do not depend
 //    on the thread/CTA/GPU that runs a packet;
 //  * tallies are order-independent 64-bit integer reductions (RED.E.ADD.64 at L2):
@@ -35,12 +39,13 @@
 namespace mcb {
 
 enum { CH_STELLAR = 0, CH_DIFFEXT = 1, CH_DIFFUSE = 2, CH_DUSTEMI = 3 };
-enum { PH_NEED = 0, PH_EMIT = 1, PH_FLY = 2, PH_DONE = 3 };
+enum { PH_NEED = 0, PH_EMIT = 1, PH_FLY = 2, PH_SCATTER = 3, PH_ESCAPE = 4, PH_DONE = 5 };
 enum { FATE_ESCAPED = 1, FATE_LINE = 2, FATE_DROPPED = 3, FATE_TRAPPED = 4, FATE_EARLY = 5 };
 
 constexpr int kThreads = 256;
 constexpr int kSafeLimit = 500000;       // photon_mod.f90:1190
 constexpr int kRecursionLimit = 5000;    // constants_mod.f90:56
+constexpr int kBatch = 8;                // lanes that must wait for a rare phase before it runs
 
 struct Lane {
     Rng rng;
@@ -57,7 +62,7 @@ struct Lane {
     int chType;
     int istep, gen;
     unsigned int segs;
-    int lastNuP, fate;
+    int lastNuP, fate, pendFate;
     long long k;
     int phase;
 };
@@ -214,30 +219,35 @@ struct Transport {
         if (fate == FATE_DROPPED) count(C_DROPPED);
         cnt[C_SEGMENTS * kThreads + threadIdx.x] += L.segs;
         if (a.fates) {
-            int *f = a.fates + 4 * L.k;
-            f[0] = (int)L.segs; f[1] = L.gen; f[2] = L.lastNuP; f[3] = fate;
+            int4 f = make_int4((int)L.segs, L.gen, L.lastNuP, fate);
+            reinterpret_cast<int4 *>(a.fates)[L.k] = f;
         }
         L.phase = PH_NEED;
     }
+    // leave through the (deferred) escape tally
+    __device__ __forceinline__ void escape(Lane &L, int fate)
+    {
+        L.pendFate = fate;
+        L.phase = PH_ESCAPE;
+    }
 
-    // escape tally (photon_mod.f90:373-462 and the six copies in pathSegment)
-    __device__ __forceinline__ void escape_tally(Lane &L)
+    // ---- PH_ESCAPE: escape tally (photon_mod.f90:373-462 and the six copies in pathSegment)
+    __device__ __forceinline__ void do_escape(Lane &L)
     {
         const DevParams &P = a.P;
         int idirT, idirP;
         if (P.lgSym) idirT = (int)(dm_acosf(fabsf(L.dz)) / P.dTheta) + 1;
         else         idirT = (int)(dm_acosf(L.dz) / P.dTheta) + 1;
         if (idirT > P.totT) idirT = P.totT;
-        if (idirT < 1) { atomicMax(a.errFlag, 10); return; }
         if (fabsf(L.dx) < 1.e-35f) idirP = 0;
         else if (P.lgSym) idirP = (int)(dm_atanf(fabsf(L.dy) / fabsf(L.dx)) / P.dPhi);
         else              idirP = (int)(dm_atanf(L.dy / L.dx) / P.dPhi);
         if (idirP < 0) idirP = P.totP + idirP;
         idirP = idirP + 1;
         if (idirP > P.totP) idirP = P.totP;
-        if (idirP < 1) { atomicMax(a.errFlag, 10); return; }
-        if (L.orgG < 1 || L.orgG > P.nGrids) { atomicMax(a.errFlag, 11); return; }
-        if (L.orgC < 0) { atomicMax(a.errFlag, 12); return; }
+        if (idirT < 1 || idirP < 1) { fail(L, 10); return; }
+        if (L.orgG < 1 || L.orgG > P.nGrids) { fail(L, 11); return; }
+        if (L.orgC < 0) { fail(L, 12); return; }
         const DevGrid &g = G(L.orgG);
         size_t plane = (size_t)(g.nCells + 1) * (size_t)(P.nbins + 1);
         size_t base = (size_t)L.orgC + (size_t)(g.nCells + 1) * (size_t)L.nuP;
@@ -257,6 +267,8 @@ struct Transport {
             atomicAdd(&g.escQ[base], 1ull);
         }
         count(C_ESCAPED);
+        if (L.pendFate == FATE_EARLY) count(C_EARLY);
+        finish(L, L.pendFate);
     }
 
     // J estimator add (photon_mod.f90:1563-1574, 1822-1833) in fixed point
@@ -300,81 +312,58 @@ struct Transport {
         L.phase = PH_EMIT;
     }
 
-    // ---- energyPacketRun up to the head of pathSegment (photon_mod.f90:289-487, 768-1059,
-    //      1098-1192) -------------------------------------------------------------------
-    __device__ __forceinline__ void emit(Lane &L)
+    // ---- PH_EMIT: energyPacketRun up to the head of pathSegment (photon_mod.f90:289-487,
+    //      768-1059, 1098-1192) ---------------------------------------------------------
+    __device__ __forceinline__ void do_emit(Lane &L)
     {
         const DevParams &P = a.P;
         L.gen++;
         int igp = (L.gP == 1) ? 0 : 1;
         int ex = igp ? L.sx : L.mx, ey = igp ? L.sy : L.my, ez = igp ? L.sz : L.mz;
-        bool line = false;
-        int nuP = 0;
-        switch (L.chType) {
-        case CH_STELLAR: {
-            nuP = sample_cdf(L.rng, P.starCdf + (size_t)a.iStar * P.nbins, P.nbins);
-            if (nuP >= P.nbins) { fail(L, 33); return; }
-            int sc = __ldg(&P.starCell[a.iStar - 1]);
-            if (sc < 0) { fail(L, 35); return; }
-            L.lgStellar = 1;
-            new_direction(P, L, true);
-            L.orgG = L.gP; L.orgC = sc;
-            if (__ldg(&P.nuArray[nuP - 1]) > 1.f) atomicAdd(&qph[nuP - 1], 1u);
-            break;
-        }
-        case CH_DIFFEXT: {
-            nuP = sample_cdf(L.rng, P.starCdf, P.nbins);
-            if (nuP >= P.nbins) { fail(L, 36); return; }
-            int c = active_at(G(L.gP), ex, ey, ez);
-            if (c < 0) { fail(L, 38); return; }
-            L.lgStellar = 0;
-            new_direction(P, L, false);
-            L.orgG = L.gP; L.orgC = c;
-            break;
-        }
-        case CH_DIFFUSE: {
+        const float *cdf;                // contiguous CDF row to sample
+        int cell = 0;
+        bool stellar = false;
+        if (L.chType == CH_STELLAR) {
+            cdf = P.starCdf + (size_t)a.iStar * P.nbins;
+            cell = __ldg(&P.starCell[a.iStar - 1]);
+            if (cell < 0) { fail(L, 35); return; }
+            stellar = true;
+        } else if (L.chType == CH_DIFFEXT) {
+            cdf = P.starCdf;
+            cell = active_at(G(L.gP), ex, ey, ez);
+            if (cell < 0) { fail(L, 38); return; }
+        } else {                         // CH_DIFFUSE / CH_DUSTEMI: re-emission in the absorbing cell
             const DevGrid &g = G(L.gP);
-            int cell = active_at(g, ex, ey, ez);
+            cell = active_at(g, ex, ey, ez);
             if (cell <= 0) { fail(L, 40); return; }
-            float random = 1.f - L.rng.uniform();
-            if (random <= __ldg(&g.totalLines[cell])) {
-                line = true;
-                if (P.lgDebug) {
-                    nuP = sample_cdf_strided(L.rng, g.linePDF + cell, (size_t)(g.nCells + 1), P.nLines);
-                    atomicAdd(&g.lineQ[(size_t)(nuP - 1) * (size_t)(g.nCells + 1) + (size_t)cell], 1ull);
+            if (L.chType == CH_DIFFUSE) {
+                float random = 1.f - L.rng.uniform();
+                if (random <= __ldg(&g.totalLines[cell])) {
+                    // non-ionising line packet: leaves silently (:923-957, :475-485)
+                    int nuL = 0;
+                    if (P.lgDebug) {
+                        nuL = sample_cdf_strided(L.rng, g.linePDF + cell, (size_t)(g.nCells + 1), P.nLines);
+                        atomicAdd(&g.lineQ[(size_t)(nuL - 1) * (size_t)(g.nCells + 1) + (size_t)cell], 1ull);
+                    }
+                    L.lastNuP = nuL;
+                    count(C_LINE);
+                    finish(L, FATE_LINE);
+                    return;
                 }
-            } else {
-                nuP = sample_cdf(L.rng, g.pdfT + (size_t)cell * P.nbins, P.nbins);
-                if (nuP >= P.nbins) { fail(L, 42); return; }
-                L.lgStellar = 0;
-                new_direction(P, L, false);
-                L.orgG = L.gP; L.orgC = cell;
             }
-            break;
+            cdf = g.pdfT + (size_t)cell * P.nbins;
         }
-        default: {  // CH_DUSTEMI
-            const DevGrid &g = G(L.gP);
-            int cell = active_at(g, ex, ey, ez);
-            if (cell <= 0) { fail(L, 46); return; }
-            nuP = sample_cdf(L.rng, g.pdfT + (size_t)cell * P.nbins, P.nbins);
-            if (nuP >= P.nbins) { fail(L, 47); return; }
-            L.lgStellar = 0;
-            new_direction(P, L, false);
-            L.orgG = L.gP; L.orgC = cell;
-            break;
-        }
-        }
+        int nuP = sample_cdf(L.rng, cdf, P.nbins);
         L.lastNuP = nuP;
-        if (line) {                      // line packets leave silently (:475-485)
-            count(C_LINE);
-            finish(L, FATE_LINE);
-            return;
-        }
+        if (nuP >= P.nbins) { fail(L, 33); return; }   // fatal in the reference (:826,868,962,1018)
+        L.lgStellar = stellar ? 1 : 0;
+        new_direction(P, L, stellar);
+        L.orgG = L.gP; L.orgC = cell;
         L.nuP = nuP;
-        if (!P.lgDust && __ldg(&P.nuArray[nuP - 1]) < P.ionEdge1) {   // :370-465
-            escape_tally(L);
-            count(C_EARLY);
-            finish(L, FATE_EARLY);
+        float nu = __ldg(&P.nuArray[nuP - 1]);
+        if (stellar && nu > 1.f) atomicAdd(&qph[nuP - 1], 1u);     // Qphot, :859-861
+        if (!P.lgDust && nu < P.ionEdge1) {                         // :370-465
+            escape(L, FATE_EARLY);
             return;
         }
         // head of pathSegment (:1098-1192)
@@ -392,27 +381,46 @@ struct Transport {
         L.phase = PH_FLY;
     }
 
-    // distance to the wall ahead on one axis (photon_mod.f90:1263-1295); returns false
-    // if the packet sits on the outermost wall of the mother grid (`return`, no tally)
+    // ---- PH_SCATTER: new direction after a dust scattering (photon_mod.f90:1750-1799) ----
+    __device__ __forceinline__ void do_scatter(Lane &L)
+    {
+        const DevParams &P = a.P;
+        const DevGrid &g = G(L.gP);
+        // initPhotonPacket(..., lgHG=.true.) (:1753-1766): slots, origin, non-stellar
+        if (L.igpp) { L.sx = L.xP; L.sy = L.yP; L.sz = L.zP; } else { L.mx = L.xP; L.my = L.yP; L.mz = L.zP; }
+        L.lgStellar = 0;
+        if (P.lgIso) new_direction(P, L, false);
+        L.orgG = L.gP;
+        {
+            int igpi = (L.gP == 1) ? 0 : 1;
+            int ox = igpi ? L.sx : L.mx, oy = igpi ? L.sy : L.my, oz = igpi ? L.sz : L.mz;
+            if (ox < 1 || ox > g.nx || oy < 1 || oy > g.ny || oz < 1 || oz > g.nz) { fail(L, 24); return; }
+            L.orgC = active_at(g, ox, oy, oz);
+        }
+        if (!P.lgIso) {
+            for (int ihg = 1; ihg <= 10; ++ihg) { if (hg(P, L) == 0) break; }
+        }
+        L.vx = L.dx; L.vy = L.dy; L.vz = L.dz;
+        if (!(L.dx >= 0.f || L.dx < 0.f)) { fail(L, 71); return; }
+        L.absTau = 0.f;
+        L.passProb = -dm_logf(1.f - L.rng.uniform());
+        L.phase = PH_FLY;
+    }
+
+    // distance to the wall ahead on one axis (photon_mod.f90:1263-1295), branch free on the
+    // sign of v: W[iP] is the wall ahead for v>0, W[iP-1] for v<0.  Returns false if the
+    // packet sits on the outermost wall of the mother grid (`return`, no tally).
     __device__ __forceinline__ bool wall(const float *W, int n, float v, float &r, int &iP, int gP, float &dS)
     {
-        if (v > 1.e-10f) {
-            float w = __ldg(&W[iP]);
-            dS = (w - r) / v;
-            if (fabsf(dS) < 1.e-10f) {
-                r = w;
-                if (iP < n) iP = iP + 1;
-                else if (gP == 1) return false;
-            }
-        } else if (v < -1.e-10f) {
-            float w = __ldg(&W[iP - 1]);
-            dS = (w - r) / v;
-            if (fabsf(dS) < 1.e-10f) {
-                r = w;
-                if (iP > 1) iP = iP - 1;
-            }
-        } else {
-            dS = 1.e35f;
+        bool pos = v > 1.e-10f, neg = v < -1.e-10f;
+        float w = __ldg(&W[pos ? iP : iP - 1]);
+        float d = (w - r) / v;
+        bool moving = pos || neg;
+        dS = moving ? d : 1.e35f;
+        if (moving && fabsf(d) < 1.e-10f) {          // sitting on the wall: snap and step over
+            r = w;
+            if (pos) { if (iP < n) iP = iP + 1; else if (gP == 1) return false; }
+            else     { if (iP > 1) iP = iP - 1; }
         }
         return true;
     }
@@ -429,7 +437,7 @@ struct Transport {
         L.phase = PH_EMIT;
     }
 
-    // ---- one trip of the cell-crossing loop (photon_mod.f90:1194-2836) -----------------
+    // ---- PH_FLY: one trip of the cell-crossing loop (photon_mod.f90:1194-2836) ----------
     __device__ __forceinline__ void step(Lane &L)
     {
         const DevParams &P = a.P;
@@ -462,27 +470,28 @@ struct Transport {
             const DevGrid &g = G(L.gP);
             if (P.lgSym) {               // :1248-1261 (always against the mother grid's first point)
                 const DevGrid &m = G(1);
-                float x1 = __ldg(&m.xAxis[0]), y1 = __ldg(&m.yAxis[0]), z1 = __ldg(&m.zAxis[0]);
-                if (L.rx <= x1) { if (L.vx < 0.f) L.vx = -L.vx; L.rx = x1; }
-                if (L.ry <= y1) { if (L.vy < 0.f) L.vy = -L.vy; L.ry = y1; }
-                if (L.rz <= z1) { if (L.vz < 0.f) L.vz = -L.vz; L.rz = z1; }
+                if (L.rx <= m.x1) { L.vx = fabsf(L.vx); L.rx = m.x1; }
+                if (L.ry <= m.y1) { L.vy = fabsf(L.vy); L.ry = m.y1; }
+                if (L.rz <= m.z1) { L.vz = fabsf(L.vz); L.rz = m.z1; }
             }
-            if (!wall(g.xWall, g.nx, L.vx, L.rx, L.xP, L.gP, dSx)) { finish(L, FATE_DROPPED); return; }
-            if (!(dSx >= 0.f || dSx < 0.f)) { fail(L, 60); return; }
-            if (!wall(g.yWall, g.ny, L.vy, L.ry, L.yP, L.gP, dSy)) { finish(L, FATE_DROPPED); return; }
-            if (!(dSy >= 0.f || dSy < 0.f)) { fail(L, 61); return; }
-            if (!wall(g.zWall, g.nz, L.vz, L.rz, L.zP, L.gP, dSz)) { finish(L, FATE_DROPPED); return; }
-            if (!(dSz >= 0.f || dSz < 0.f)) { fail(L, 62); return; }
+            // the reference returns at the first axis found on the outer wall, i.e. before
+            // the later axes are looked at; nothing after a `return` is observable
+            if (!wall(g.xWall, g.nx, L.vx, L.rx, L.xP, L.gP, dSx) ||
+                !wall(g.yWall, g.ny, L.vy, L.ry, L.yP, L.gP, dSy) ||
+                !wall(g.zWall, g.nz, L.vz, L.rz, L.zP, L.gP, dSz)) { finish(L, FATE_DROPPED); return; }
+            if (!(dSx >= 0.f || dSx < 0.f) || !(dSy >= 0.f || dSy < 0.f) || !(dSz >= 0.f || dSz < 0.f)) { fail(L, 60); return; }
             cell = active_at(g, L.xP, L.yP, L.zP);
             if (!MULTI || cell >= 0) break;
             if (j >= kSafeLimit) { fail(L, 63); return; }
         }
         const DevGrid &g = G(L.gP);
+        size_t tix = (size_t)(L.nuP - 1) * (size_t)(g.nCells + 1) + (size_t)cell;
+        float opac = __ldg(&g.opacity[tix]);
 
         // cells on a wall (:1395-1397): the axis end coordinate replaces a zero distance
-        if (fabsf(dSx) < 1.e-10f) dSx = __ldg(&g.xWall[g.nx]);
-        if (fabsf(dSy) < 1.e-10f) dSy = __ldg(&g.yWall[g.ny]);
-        if (fabsf(dSz) < 1.e-10f) dSz = __ldg(&g.zWall[g.nz]);
+        if (fabsf(dSx) < 1.e-10f) dSx = g.xN;
+        if (fabsf(dSy) < 1.e-10f) dSy = g.yN;
+        if (fabsf(dSz) < 1.e-10f) dSz = g.zN;
         dSx = fabsf(dSx); dSy = fabsf(dSy); dSz = fabsf(dSz);
         float dS;
         if (dSx <= 0.f)      dS = fminf(dSy, dSz);
@@ -491,8 +500,6 @@ struct Transport {
         else { dS = fminf(dSx, dSy); dS = fminf(dS, dSz); }
         if (dS <= 0.f) { fail(L, 64); return; }
 
-        size_t tix = (size_t)(L.nuP - 1) * (size_t)(g.nCells + 1) + (size_t)cell;
-        float opac = __ldg(&g.opacity[tix]);
         float tauCell = dS * opac;
 
         if ((L.absTau + tauCell > L.passProb) && (cell > 0)) {
@@ -503,20 +510,15 @@ struct Transport {
             L.rz = L.rz + dlLoc * L.vz;
             if (!(L.rx >= 0.f || L.rx < 0.f) || !(L.ry >= 0.f || L.ry < 0.f) || !(L.rz >= 0.f || L.rz < 0.f)) { fail(L, 65); return; }
             if (P.lgSym && L.gP == 1) {
-                float x1 = __ldg(&g.xAxis[0]), y1 = __ldg(&g.yAxis[0]), z1 = __ldg(&g.zAxis[0]);
-                if (L.rx <= x1) { if (L.vx < 0.f) L.vx = -L.vx; L.rx = x1; }
-                if (L.ry <= y1) { if (L.vy < 0.f) L.vy = -L.vy; L.ry = y1; }
-                if (L.rz <= z1) { if (L.vz < 0.f) L.vz = -L.vz; L.rz = z1; }
+                if (L.rx <= g.x1) { L.vx = fabsf(L.vx); L.rx = g.x1; }
+                if (L.ry <= g.y1) { L.vy = fabsf(L.vy); L.ry = g.y1; }
+                if (L.rz <= g.z1) { L.vz = fabsf(L.vz); L.rz = g.z1; }
             }
             j_add(g, L, cell, dlLoc);
-            {
+            if (P.R_out > 0.f) {                          // :1577
                 float tx = L.rx / 1.e10f, ty = L.ry / 1.e10f, tz = L.rz / 1.e10f;
                 float rr = sqrtf(tx * tx + ty * ty + tz * tz) * 1.e10f;
-                if (rr >= P.R_out && P.R_out > 0.f) {     // :1577
-                    escape_tally(L);
-                    finish(L, FATE_ESCAPED);
-                    return;
-                }
+                if (rr >= P.R_out) { escape(L, FATE_ESCAPED); return; }
             }
             if (P.lgDust) {
                 float probSca = __ldg(&g.scaOpac[tix]) / opac;
@@ -531,173 +533,143 @@ struct Transport {
                 }
                 count(C_SCA);
                 if (!__ldg(&g.canScatter[cell])) { fail(L, 69); return; }
-                // initPhotonPacket(..., lgHG=.true.) (:1753-1766)
-                if (L.igpp) { L.sx = L.xP; L.sy = L.yP; L.sz = L.zP; } else { L.mx = L.xP; L.my = L.yP; L.mz = L.zP; }
-                L.lgStellar = 0;
-                if (P.lgIso) new_direction(P, L, false);
-                L.orgG = L.gP;
-                if (MULTI) {
-                    int igpi = (L.gP == 1) ? 0 : 1;
-                    int ox = igpi ? L.sx : L.mx, oy = igpi ? L.sy : L.my, oz = igpi ? L.sz : L.mz;
-                    if (ox < 1 || ox > g.nx || oy < 1 || oy > g.ny || oz < 1 || oz > g.nz) { fail(L, 24); return; }
-                    L.orgC = active_at(g, ox, oy, oz);
-                } else {
-                    L.orgC = cell;
-                }
-                if (!P.lgIso) {
-                    for (int ihg = 1; ihg <= 10; ++ihg) { if (hg(P, L) == 0) break; }
-                }
-                L.vx = L.dx; L.vy = L.dy; L.vz = L.dz;
-                if (!(L.dx >= 0.f || L.dx < 0.f)) { fail(L, 71); return; }
-                L.absTau = 0.f;
-                L.passProb = -dm_logf(1.f - L.rng.uniform());
-            } else {
-                if (!P.lgGas) { fail(L, 72); return; }
-                absorb(L, CH_DIFFUSE);
+                if (L.istep >= kSafeLimit) { finish(L, FATE_DROPPED); return; }   // loop ends: :2838
+                L.phase = PH_SCATTER;
                 return;
             }
-        } else {
-            // ---- no interaction in this cell (:1817-2731) ----
-            j_add(g, L, cell, dS);
-            L.absTau = L.absTau + tauCell;
-            L.rx = L.rx + dS * L.vx;
-            L.ry = L.ry + dS * L.vy;
-            L.rz = L.rz + dS * L.vz;
+            if (!P.lgGas) { fail(L, 72); return; }
+            absorb(L, CH_DIFFUSE);
+            return;
+        }
 
-            if (MULTI && L.gP > 1) track_mother(L);
+        // ---- no interaction in this cell (:1817-2731) ----
+        j_add(g, L, cell, dS);
+        L.absTau = L.absTau + tauCell;
+        L.rx = L.rx + dS * L.vx;
+        L.ry = L.ry + dS * L.vy;
+        L.rz = L.rz + dS * L.vz;
 
-            // :1961-1976
-            if (dS == dSx && L.vx > 0.f) L.xP = L.xP + 1;
-            else if (dS == dSx && L.vx < 0.f) L.xP = L.xP - 1;
-            else if (dS == dSy && L.vy > 0.f) L.yP = L.yP + 1;
-            else if (dS == dSy && L.vy < 0.f) L.yP = L.yP - 1;
-            else if (dS == dSz && L.vz > 0.f) L.zP = L.zP + 1;
-            else if (dS == dSz && L.vz < 0.f) L.zP = L.zP - 1;
+        if (MULTI && L.gP > 1) track_mother(L);
 
-            if (!P.lgSym) {              // "be 6/6/06" block (:1986-2194)
-                bool lgReturn = false;
-                {
-                    const DevGrid &c = G(L.gP);
-                    if (L.ry <= __ldg(&c.yAxis[0]) - c.geoY || L.yP < 1) {
-                        if (L.gP == 1) { L.yP = 1; lgReturn = true; }
-                        else to_mother_stale(L);
-                    }
-                }
-                {
-                    const DevGrid &c = G(L.gP);
-                    if (L.ry > __ldg(&c.yAxis[c.ny - 1]) + c.geoY || L.yP > c.ny) {
-                        if (L.gP == 1) { L.yP = c.ny; lgReturn = true; }
-                        else to_mother_stale(L);
-                    }
-                }
-                {
-                    const DevGrid &c = G(L.gP);
-                    bool cond = (L.rx <= __ldg(&c.xAxis[0]) - c.geoX || L.xP < 1);
-                    if (cond && L.gP == 1) { L.xP = 1; lgReturn = true; }
-                    // the reference re-evaluates the condition with the (unchanged) grid
-                    if ((L.rx <= __ldg(&c.xAxis[0]) - c.geoX || L.xP < 1) && L.gP > 1) to_mother_stale(L);
-                }
-                {
-                    const DevGrid &c = G(L.gP);
-                    if ((L.rx >= __ldg(&c.xAxis[c.nx - 1]) + c.geoX || L.xP > c.nx) && L.gP == 1) { L.xP = c.nx; lgReturn = true; }
-                    if ((L.rx >= __ldg(&c.xAxis[c.nx - 1]) + c.geoX || L.xP > c.nx) && L.gP > 1) to_mother_stale(L);
-                }
-                {
-                    const DevGrid &c = G(L.gP);
-                    if ((L.rz <= __ldg(&c.zAxis[0]) - c.geoZ || L.zP < 1) && L.gP == 1) { L.zP = 1; lgReturn = true; }
-                    if ((L.rz <= __ldg(&c.zAxis[0]) - c.geoZ || L.zP < 1) && L.gP > 1) to_mother_stale(L);
-                }
-                {
-                    const DevGrid &c = G(L.gP);
-                    if ((L.rz >= __ldg(&c.zAxis[c.nz - 1]) + c.geoZ || L.zP > c.nz) && L.gP == 1) { L.zP = c.nz; lgReturn = true; }
-                    if ((L.rz >= __ldg(&c.zAxis[c.nz - 1]) + c.geoZ || L.zP > c.nz) && L.gP > 1) to_mother_stale(L);
-                }
-                if (lgReturn) {
-                    escape_tally(L);
-                    finish(L, FATE_ESCAPED);
-                    return;
-                }
-            }
+        // :1961-1976
+        if (dS == dSx && L.vx > 0.f) L.xP = L.xP + 1;
+        else if (dS == dSx && L.vx < 0.f) L.xP = L.xP - 1;
+        else if (dS == dSy && L.vy > 0.f) L.yP = L.yP + 1;
+        else if (dS == dSy && L.vy < 0.f) L.yP = L.yP - 1;
+        else if (dS == dSz && L.vz > 0.f) L.zP = L.zP + 1;
+        else if (dS == dSz && L.vz < 0.f) L.zP = L.zP - 1;
 
-            // still inside the simulation region? (:2417-2671)
-            {
-                const DevGrid &m = G(1);
-                const DevGrid &c = G(L.gP);
-                bool lowOut = !P.lgSym && (L.rx <= __ldg(&m.xAxis[0]) - m.geoX ||
-                                           L.ry <= __ldg(&m.yAxis[0]) - m.geoY ||
-                                           L.rz <= __ldg(&m.zAxis[0]) - m.geoZ);
-                if (lowOut ||
-                    (L.rx >= __ldg(&c.xAxis[c.nx - 1]) + c.geoX) ||
-                    (L.ry >= __ldg(&c.yAxis[c.ny - 1]) + c.geoY) ||
-                    (L.rz >= __ldg(&c.zAxis[c.nz - 1]) + c.geoZ) ||
-                    L.xP > c.nx || L.yP > c.ny || L.zP > c.nz) {
-                    if (L.gP == 1) {
-                        escape_tally(L);
-                        finish(L, FATE_ESCAPED);
-                        return;
-                    } else {
-                        L.xP = L.mx; L.yP = L.my; L.zP = L.mz;
-                        L.gP = 1;
-                        L.igpp = 0;
-                        float tx = L.rx / 1.e10f, ty = L.ry / 1.e10f, tz = L.rz / 1.e10f;
-                        float radius = 1.e10f * sqrtf(tx * tx + ty * ty + tz * tz);
-                        if ((radius >= P.R_out && P.R_out >= 0.f) ||
-                            (L.rx >= __ldg(&m.xAxis[m.nx - 1]) + m.geoX) ||
-                            (L.ry >= __ldg(&m.yAxis[m.ny - 1]) + m.geoY) ||
-                            (L.rz >= __ldg(&m.zAxis[m.nz - 1]) + m.geoZ) || lowOut) {
-                            escape_tally(L);
-                            finish(L, FATE_ESCAPED);
-                            return;
-                        }
-                    }
-                }
-            }
-
+        if (!MULTI) {
+            // single grid: every test of :1986-2194, :2417-2540 and :2733-2834 that is true
+            // ends in the same escape tally, so they collapse into one predicate
+            bool out = (L.rx >= g.xHi) || (L.ry >= g.yHi) || (L.rz >= g.zHi) ||
+                       L.xP > g.nx || L.yP > g.ny || L.zP > g.nz;
+            if (!P.lgSym)
+                out = out || (L.rx <= g.xLo) || (L.ry <= g.yLo) || (L.rz <= g.zLo) ||
+                      L.xP < 1 || L.yP < 1 || L.zP < 1;
+            if (out) { escape(L, FATE_ESCAPED); return; }
             if (P.lgSym) {               // :2674-2699
-                const DevGrid &m = G(1);
+                if (L.rx <= g.x1 || L.xP < 1) { L.vx = fabsf(L.vx); L.xP = 1; L.rx = g.x1; }
+                if (L.ry <= g.y1 || L.yP < 1) { L.vy = fabsf(L.vy); L.yP = 1; L.ry = g.y1; }
+                if (L.rz <= g.z1 || L.zP < 1) { L.vz = fabsf(L.vz); L.zP = 1; L.rz = g.z1; }
+            }
+        } else {
+            if (!step_tail_multi(L)) return;
+        }
+        if (L.istep >= kSafeLimit) finish(L, FATE_DROPPED);   // :2838-2846
+    }
+
+    // multi-grid tail of a non-interacting step (:1986-2834); false = packet left FLY
+    __device__ __forceinline__ bool step_tail_multi(Lane &L)
+    {
+        const DevParams &P = a.P;
+        if (!P.lgSym) {                  // "be 6/6/06" block (:1986-2194)
+            bool lgReturn = false;
+            {
                 const DevGrid &c = G(L.gP);
-                if (L.rx <= __ldg(&m.xAxis[0]) || (L.gP == 1 && L.xP < 1)) {
-                    if (L.vx < 0.f) L.vx = -L.vx;
-                    L.mx = 1; L.xP = 1;
-                    L.rx = __ldg(&c.xAxis[0]);
-                }
-                if (L.ry <= __ldg(&m.yAxis[0]) || (L.gP == 1 && L.yP < 1)) {
-                    if (L.vy < 0.f) L.vy = -L.vy;
-                    L.my = 1; L.yP = 1;
-                    L.ry = __ldg(&c.yAxis[0]);
-                }
-                if (L.rz <= __ldg(&m.zAxis[0]) || (L.gP == 1 && L.zP < 1)) {
-                    if (L.vz < 0.f) L.vz = -L.vz;
-                    L.mz = 1; L.zP = 1;
-                    L.rz = __ldg(&m.zAxis[0]);
+                if (L.ry <= c.yLo || L.yP < 1) {
+                    if (L.gP == 1) { L.yP = 1; lgReturn = true; }
+                    else to_mother_stale(L);
                 }
             }
+            {
+                const DevGrid &c = G(L.gP);
+                if (L.ry > c.yHi || L.yP > c.ny) {
+                    if (L.gP == 1) { L.yP = c.ny; lgReturn = true; }
+                    else to_mother_stale(L);
+                }
+            }
+            {
+                const DevGrid &c = G(L.gP);
+                if ((L.rx <= c.xLo || L.xP < 1) && L.gP == 1) { L.xP = 1; lgReturn = true; }
+                if ((L.rx <= c.xLo || L.xP < 1) && L.gP > 1) to_mother_stale(L);
+            }
+            {
+                const DevGrid &c = G(L.gP);
+                if ((L.rx >= c.xHi || L.xP > c.nx) && L.gP == 1) { L.xP = c.nx; lgReturn = true; }
+                if ((L.rx >= c.xHi || L.xP > c.nx) && L.gP > 1) to_mother_stale(L);
+            }
+            {
+                const DevGrid &c = G(L.gP);
+                if ((L.rz <= c.zLo || L.zP < 1) && L.gP == 1) { L.zP = 1; lgReturn = true; }
+                if ((L.rz <= c.zLo || L.zP < 1) && L.gP > 1) to_mother_stale(L);
+            }
+            {
+                const DevGrid &c = G(L.gP);
+                if ((L.rz >= c.zHi || L.zP > c.nz) && L.gP == 1) { L.zP = c.nz; lgReturn = true; }
+                if ((L.rz >= c.zHi || L.zP > c.nz) && L.gP > 1) to_mother_stale(L);
+            }
+            if (lgReturn) { escape(L, FATE_ESCAPED); return false; }
+        }
 
-            if (MULTI && L.gP > 1) {     // leaving the sub-grid (:2703-2726)
-                const DevGrid &s = G(L.gP);
-                if (((L.rx <= __ldg(&s.xAxis[0]) || L.xP < 1) && L.vx <= 0.f) ||
-                    ((L.ry <= __ldg(&s.yAxis[0]) || L.yP < 1) && L.vy <= 0.f) ||
-                    ((L.rz <= __ldg(&s.zAxis[0]) || L.zP < 1) && L.vz <= 0.f) ||
-                    ((L.rx >= __ldg(&s.xAxis[s.nx - 1]) || L.xP > s.nx) && L.vx >= 0.f) ||
-                    ((L.ry >= __ldg(&s.yAxis[s.ny - 1]) || L.yP > s.ny) && L.vy >= 0.f) ||
-                    ((L.rz >= __ldg(&s.zAxis[s.nz - 1]) || L.zP > s.nz) && L.vz >= 0.f)) {
-                    L.xP = L.mx; L.yP = L.my; L.zP = L.mz;
-                    L.gP = 1;
-                    L.igpp = 0;
+        // still inside the simulation region? (:2417-2671)
+        {
+            const DevGrid &m = G(1);
+            const DevGrid &c = G(L.gP);
+            bool lowOut = !P.lgSym && (L.rx <= m.xLo || L.ry <= m.yLo || L.rz <= m.zLo);
+            if (lowOut || (L.rx >= c.xHi) || (L.ry >= c.yHi) || (L.rz >= c.zHi) ||
+                L.xP > c.nx || L.yP > c.ny || L.zP > c.nz) {
+                if (L.gP == 1) { escape(L, FATE_ESCAPED); return false; }
+                L.xP = L.mx; L.yP = L.my; L.zP = L.mz;
+                L.gP = 1;
+                L.igpp = 0;
+                float tx = L.rx / 1.e10f, ty = L.ry / 1.e10f, tz = L.rz / 1.e10f;
+                float radius = 1.e10f * sqrtf(tx * tx + ty * ty + tz * tz);
+                if ((radius >= P.R_out && P.R_out >= 0.f) ||
+                    (L.rx >= m.xHi) || (L.ry >= m.yHi) || (L.rz >= m.zHi) || lowOut) {
+                    escape(L, FATE_ESCAPED);
+                    return false;
                 }
             }
         }
 
+        if (P.lgSym) {                   // :2674-2699
+            const DevGrid &m = G(1);
+            const DevGrid &c = G(L.gP);
+            if (L.rx <= m.x1 || (L.gP == 1 && L.xP < 1)) { L.vx = fabsf(L.vx); L.mx = 1; L.xP = 1; L.rx = c.x1; }
+            if (L.ry <= m.y1 || (L.gP == 1 && L.yP < 1)) { L.vy = fabsf(L.vy); L.my = 1; L.yP = 1; L.ry = c.y1; }
+            if (L.rz <= m.z1 || (L.gP == 1 && L.zP < 1)) { L.vz = fabsf(L.vz); L.mz = 1; L.zP = 1; L.rz = m.z1; }
+        }
+
+        if (L.gP > 1) {                  // leaving the sub-grid (:2703-2726)
+            const DevGrid &s = G(L.gP);
+            if (((L.rx <= s.x1 || L.xP < 1) && L.vx <= 0.f) ||
+                ((L.ry <= s.y1 || L.yP < 1) && L.vy <= 0.f) ||
+                ((L.rz <= s.z1 || L.zP < 1) && L.vz <= 0.f) ||
+                ((L.rx >= s.xN || L.xP > s.nx) && L.vx >= 0.f) ||
+                ((L.ry >= s.yN || L.yP > s.ny) && L.vy >= 0.f) ||
+                ((L.rz >= s.zN || L.zP > s.nz) && L.vz >= 0.f)) {
+                L.xP = L.mx; L.yP = L.my; L.zP = L.mz;
+                L.gP = 1;
+                L.igpp = 0;
+            }
+        }
         // :2733-2834
         if (L.gP == 1) {
             const DevGrid &m = G(1);
-            if (L.xP > m.nx || L.yP > m.ny || L.zP > m.nz) {
-                escape_tally(L);
-                finish(L, FATE_ESCAPED);
-                return;
-            }
+            if (L.xP > m.nx || L.yP > m.ny || L.zP > m.nz) { escape(L, FATE_ESCAPED); return false; }
         }
-        if (L.istep >= kSafeLimit) finish(L, FATE_DROPPED);   // :2838-2846
+        return true;
     }
 
     // gP>1 branch of the 6/6/06 block: back to the mother grid *without* resetting igpp
@@ -745,22 +717,31 @@ transport_kernel(const __grid_constant__ TransportArgs a)
     Lane L;
     L.phase = PH_NEED;
     const unsigned int lane = threadIdx.x & 31u;
+    const unsigned int FULL = 0xffffffffu;
 
     for (;;) {
         // refill: lanes without a packet claim the next global packet index
-        unsigned int need = __ballot_sync(0xffffffffu, L.phase == PH_NEED);
+        unsigned int need = __ballot_sync(FULL, L.phase == PH_NEED);
         if (need) {
             unsigned long long base = 0;
             int leader = __ffs(need) - 1;
             if ((int)lane == leader) base = atomicAdd(a.nextPacket, (unsigned long long)__popc(need));
-            base = __shfl_sync(0xffffffffu, base, leader);
+            base = __shfl_sync(FULL, base, leader);
             if (L.phase == PH_NEED) {
                 long long k = (long long)(base + __popc(need & ((1u << lane) - 1u)));
                 if (k < a.n) T.start_packet(L, k); else L.phase = PH_DONE;
             }
         }
-        if (__ballot_sync(0xffffffffu, L.phase != PH_DONE) == 0u) break;
-        if (L.phase == PH_EMIT) T.emit(L);
+        unsigned int fly = __ballot_sync(FULL, L.phase == PH_FLY);
+        unsigned int pe = __ballot_sync(FULL, L.phase == PH_EMIT);
+        unsigned int ps = __ballot_sync(FULL, L.phase == PH_SCATTER);
+        unsigned int px = __ballot_sync(FULL, L.phase == PH_ESCAPE);
+        if ((fly | pe | ps | px) == 0u) break;       // every lane is DONE
+        // deferred rare phases: run when enough lanes wait, or nothing is left to fly
+        bool flush = (fly == 0u) || (__popc(pe | ps | px) >= 2 * kBatch);
+        if (px && (flush || __popc(px) >= kBatch)) { if (L.phase == PH_ESCAPE) T.do_escape(L); }
+        if (ps && (flush || __popc(ps) >= kBatch)) { if (L.phase == PH_SCATTER) T.do_scatter(L); }
+        if (pe && (flush || __popc(pe) >= kBatch)) { if (L.phase == PH_EMIT) T.do_emit(L); }
         if (L.phase == PH_FLY) T.step(L);
     }
 

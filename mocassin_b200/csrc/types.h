@@ -19,6 +19,10 @@ struct DevGrid {
     int nx, ny, nz, nCells, motherP;
     int dense;                       // 1: every cell active, id = 1 + (z-1) + nz*((y-1) + ny*(x-1))
     float geoX, geoY, geoZ;          // geoCorr (grid_mod.f90:809-812)
+    // per-axis constants of the escape tests, same float32 expressions as the reference:
+    // a1 = axis(1), aN = axis(n), lo = axis(1)-geoCorr, hi = axis(n)+geoCorr
+    float x1, y1, z1, xN, yN, zN;
+    float xLo, yLo, zLo, xHi, yHi, zHi;
     float invLenUnit;                // 2^-e, path-length quantum of the J tally
     const float *xAxis, *yAxis, *zAxis;
     const float *xWall, *yWall, *zWall;
