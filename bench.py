@@ -190,7 +190,7 @@ def ncu_traffic():
 
 
 def default_packets(args):
-    return args.packets if args.packets > 0 else 16_000_000
+    return args.packets if args.packets > 0 else 125_000_000   # 1e9 packets per iteration over 8 GPUs (BASELINE.json)
 
 
 # ---------------------------------------------------------------------------------------
@@ -213,10 +213,10 @@ def run_reference(args):
     o = Oracle(model, fp32_tallies=False)
     build_s = time.time() - t0
     # size the per-step sample for ~cpu-seconds of work
-    t = time.time(); c = o.transport_mt(1, 0, 20000, seed=SEED, threads=cores); dt = time.time() - t
-    rate = 20000 / max(dt, 1e-6)
-    sample = int(max(20000, min(rate * args.cpu_seconds, 50_000_000)))
-    first = 20000
+    t = time.time(); c = o.transport_mt(1, 0, 400000, seed=SEED, threads=cores); dt = time.time() - t
+    rate = 400000 / max(dt, 1e-6)
+    sample = int(max(400000, min(rate * args.cpu_seconds, 200_000_000)))
+    first = 400000
     for _ in range(args.warmup):
         o.transport_mt(1, first, sample, seed=SEED, threads=cores); first += sample
     segs = 0
@@ -287,6 +287,9 @@ def run_b200(args):
 
     eng = PacketEngine(model, device=local, rank=rank, nranks=world, seed=SEED)
     eng.set_xsec(xsec)
+    for opt in ("order", "agg_steps", "batch", "blocks_per_sm"):
+        if os.environ.get("MCB_" + opt.upper()):
+            eng.set_option(opt, int(os.environ["MCB_" + opt.upper()]))
 
     def upload_inputs():
         eng.assemble_opacity(1, bands, den, None, dust)       # K1 on device
@@ -406,10 +409,10 @@ def cpu_baseline(args, eng, model, g):
     op, sca, _ = eng.get_opacity(1)
     g.opacity, g.scaOpac = op, sca
     o = Oracle(model, fp32_tallies=False)
-    t = time.time(); o.transport_mt(1, 0, 20000, seed=SEED, threads=cores); dt = time.time() - t
-    rate = 20000 / max(dt, 1e-6)
-    sample = int(max(20000, min(rate * args.cpu_seconds, 50_000_000)))
-    t = time.time(); c = o.transport_mt(1, 20000, sample, seed=SEED, threads=cores); dt = time.time() - t
+    t = time.time(); o.transport_mt(1, 0, 400000, seed=SEED, threads=cores); dt = time.time() - t
+    rate = 400000 / max(dt, 1e-6)
+    sample = int(max(400000, min(rate * args.cpu_seconds, 200_000_000)))
+    t = time.time(); c = o.transport_mt(1, 400000, sample, seed=SEED, threads=cores); dt = time.time() - t
     return {"value": sample / dt, "unit": "packets/s", "cores": cores, "kind": "port",
             "sample": f"{sample} packets of the same workload in {dt:.1f}s, oracle port (-O2) on {cores} threads",
             "segments_per_packet": c["nSegments"] / sample}

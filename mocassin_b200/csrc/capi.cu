@@ -17,6 +17,8 @@
 namespace mcb {
 cudaError_t launch_transport(const TransportArgs &a, bool multi, int gridBlocks, cudaStream_t stream);
 int transport_blocks_per_sm(bool multi);
+cudaError_t launch_order(const TransportArgs &a, unsigned short *key, unsigned int *hist, unsigned int *cursor,
+                         unsigned int *order, int numSMs, cudaStream_t stream);
 cudaError_t launch_transpose_pdf(const float *src, float *dst, int nRows, int nb, cudaStream_t s);
 cudaError_t launch_check_monotone(const float *pdfT, int nRows, int nb, int *bad, cudaStream_t s);
 cudaError_t launch_fold_j(unsigned long long *Q, float *J, const float *dV, int nRows, size_t total,
@@ -117,6 +119,10 @@ struct mcb200_ctx {
     // work buffers
     DevBuf<unsigned long long> nextPacket, counters, qphot;
     DevBuf<int> errFlag, fates, flag;
+    DevBuf<unsigned short> sortKey;
+    DevBuf<unsigned int> sortHist, sortCursor, sortOrder;
+    int orderMode = -1;                   // -1 auto, 0 off, 1 on: process packets in frequency order
+    int aggSteps = 0, batch = 12;
     bool trace = false;
     int blocksPerSM = 0;                  // 0 = occupancy default
     // pending fold
@@ -343,7 +349,22 @@ int run_transport(mcb200_ctx *ctx, int iStar, int difGrid, const int32_t *cellLo
     if (maxUseful < 1) maxUseful = 1;
     if (blocks > maxUseful) blocks = (int)maxUseful;
 
+    // frequency-ordered processing pays when the nu-planes do not all fit in L2 anyway
+    size_t tableBytes = 0;
+    for (auto &g : ctx->grids) tableBytes += tsize(ctx, g) * 12;       // opacity 4 B + JsteQ 8 B
+    bool ordered = ctx->orderMode == 1 || (ctx->orderMode < 0 && tableBytes > (size_t)48 << 20 && mine >= (1 << 16));
+    if (mine >= ((int64_t)1 << 32)) return fail(ctx, MCB200_EINVAL, "more than 2^32 packets per rank in one call: split the call");
     CU(cudaEventRecord(ctx->ev0, ctx->stream));
+    a.order = nullptr;
+    a.batch = ctx->batch < 1 ? 1 : ctx->batch;
+    a.aggSteps = 0;
+    if (ordered && mine > 0) {
+        CU(ctx->sortKey.alloc((size_t)mine)); CU(ctx->sortOrder.alloc((size_t)mine));
+        CU(ctx->sortHist.alloc(cfg.nbins + 1)); CU(ctx->sortCursor.alloc(cfg.nbins + 1));
+        CU(launch_order(a, ctx->sortKey.p, ctx->sortHist.p, ctx->sortCursor.p, ctx->sortOrder.p, ctx->numSMs, ctx->stream));
+        a.order = ctx->sortOrder.p;
+        a.aggSteps = ctx->aggSteps;
+    }
     if (mine > 0) CU(launch_transport(a, multi, blocks, ctx->stream));
     CU(cudaEventRecord(ctx->ev1, ctx->stream));
     CU(cudaStreamSynchronize(ctx->stream));
@@ -831,6 +852,9 @@ int mcb200_set_option(mcb200_ctx *ctx, const char *name, int64_t value)
     if (!strcmp(name, "trace")) { ctx->trace = value != 0; return MCB200_OK; }
     if (!strcmp(name, "blocks_per_sm")) { ctx->blocksPerSM = (int)value; return MCB200_OK; }
     if (!strcmp(name, "seed")) { ctx->seed = (uint64_t)value; return MCB200_OK; }
+    if (!strcmp(name, "order")) { ctx->orderMode = (int)value; return MCB200_OK; }
+    if (!strcmp(name, "agg_steps")) { ctx->aggSteps = (int)value; return MCB200_OK; }
+    if (!strcmp(name, "batch")) { ctx->batch = (int)value; return MCB200_OK; }
     return fail(ctx, MCB200_EINVAL, "unknown option %s", name);
 }
 

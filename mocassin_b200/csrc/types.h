@@ -62,6 +62,9 @@ struct TransportArgs {
     long long firstId, n;            // global id of this rank's first packet, packets of this rank
     unsigned long long seed;
     unsigned long long *nextPacket;  // work counter
+    const unsigned int *order;       // optional: packet indices sorted by first frequency bin
+    int aggSteps;                    // first steps of a flight with warp-aggregated tallies (0 = off)
+    int batch;                       // lanes that must wait for a rare phase before it runs
     unsigned long long *counters;    // [C_COUNT]
     unsigned long long *qphotCounts; // [nbins]
     int *errFlag;

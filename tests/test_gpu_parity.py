@@ -81,10 +81,14 @@ def _compare(m, n, e, o, iStar=1):
     return cg, co
 
 
+@pytest.mark.parametrize("order", [0, 1])
 @pytest.mark.parametrize("name", list(CASES))
-def test_transport_bit_exact_vs_oracle(name):
+def test_transport_bit_exact_vs_oracle(name, order):
+    """order=1: packets are processed sorted by their first frequency bin with
+    warp-aggregated tallies (the large-grid schedule); the answer must not change."""
     m, n = make(name)
     e = _engine(m)
+    e.set_option("order", order)
     o = Oracle(m)
     cg, co = _compare(m, n, e, o)
     # Qphot (float64 from exact counts) agrees with the reference's float32 running sum
