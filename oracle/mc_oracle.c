@@ -1137,6 +1137,93 @@ int oracle_transport_mt(const OrParams *P, OrGrid *grids, int32_t iStar, int64_t
 }
 
 /* ------------------------------------------------------------------------- */
+/* opacity assembly: ionization_mod.f90:26-129,349-484 + iteration_mod.f90:166-227 */
+/* ------------------------------------------------------------------------- */
+static void in_opacity(float *opacity /*1-based*/, const float *xSecArray /*1-based*/, int nbins,
+                       int xSecP, int nuLowP, int nuHighP, float den)
+{
+    /* inOpacity with b = 0 (ionization_mod.f90:448-482) */
+    int k = xSecP - nuLowP;
+    int iup = nuHighP < nbins ? nuHighP : nbins;
+    if (iup < nuLowP) iup = nuLowP;
+    for (int i = nuLowP; i <= iup; ++i) opacity[i] = opacity[i] + xSecArray[i + k] * den;
+}
+
+void oracle_opacity(const OrOpacityIn *in, float *opacityOut, float *scaOut, float *absOut)
+{
+    const int nR = in->nCells + 1, nb = in->nbins;
+    const float *xs = in->xSecArray - 1;
+    float *row = (float *)malloc(sizeof(float) * (nb + 2));
+    float density[31][31];
+    for (size_t i = 0; i < (size_t)nR * nb; ++i) opacityOut[i] = 0.f;
+    for (int cell = 1; cell <= in->nCells; ++cell) {
+        /* density(n,i), ionization_mod.f90:65-80 */
+        memset(density, 0, sizeof(density));
+        for (int n = 1; n <= 30; ++n) {
+            int imax = n < in->nstages ? n : in->nstages;
+            for (int i = 1; i <= imax; ++i) {
+                if (!in->lgElementOn[n - 1]) break;
+                int xr = in->elementXref[n - 1];
+                float ion = in->ionDen[(size_t)cell + (size_t)nR * ((size_t)(xr - 1) + (size_t)in->nElementsUsed * (size_t)(i - 1))];
+                float ab = in->elemAbun[(size_t)(in->abIndex[cell] - 1) + (size_t)in->nAbComp * (size_t)(n - 1)];
+                density[n][i] = ion * ab * in->Hden[cell];
+            }
+        }
+        for (int i = 0; i <= nb + 1; ++i) row[i] = 0.f;
+        /* addOpacity, :349-443 */
+        if (in->ff1) row[1] = row[1] + in->ff1[cell];
+        in_opacity(row, xs, nb, in->HlevXSecP1, in->HlevNuP1, nb, density[1][1]);
+        in_opacity(row, xs, nb, in->HeISingXSecP1, in->HeIlevNuP1, nb, density[2][1]);
+        in_opacity(row, xs, nb, in->HeIIXSecP1, in->HeIIlevNuP1, nb, density[2][2]);
+        for (int el = 3; el <= 30; ++el) {
+            if (!in->lgElementOn[el - 1]) continue;
+            int imax = el < in->nstages ? el : in->nstages;
+            for (int ion = 1; ion <= imax; ++ion) {       /* putOpacity, :418-443 */
+                if (density[el][ion] > 0.f) {
+                    int ns = in->nShells[(el - 1) + 30 * (ion - 1)];
+                    for (int sh = 1; sh <= ns; ++sh) {
+                        size_t b = (size_t)(el - 1) + 30 * ((size_t)(ion - 1) + 30 * (size_t)(sh - 1));
+                        int nuLowP = in->elementP[b + 0 * 30 * 30 * 7];
+                        int nuHighP = in->elementP[b + 1 * 30 * 30 * 7];
+                        int xSecP = in->elementP[b + 2 * 30 * 30 * 7];
+                        in_opacity(row, xs, nb, xSecP, nuLowP, nuHighP, density[el][ion]);
+                    }
+                }
+            }
+        }
+        for (int i = 1; i <= nb; ++i) opacityOut[(size_t)(i - 1) * nR + cell] = row[i];
+    }
+    free(row);
+    if (!in->lgDust) return;
+    /* dust contribution, iteration_mod.f90:166-227 */
+    for (size_t i = 0; i < (size_t)nR * nb; ++i) { scaOut[i] = 0.f; absOut[i] = 0.f; }
+    for (int cell = 1; cell <= in->nCells; ++cell) {
+        int nsp = in->lgMultiDustChemistry ? in->dustAbunIndex[cell] : 1;
+        if (nsp < 1 || nsp > in->nDustComp) continue;
+        int dcp = in->dustComPoint[nsp - 1];
+        for (int nS = 1; nS <= in->nSpeciesPart[nsp - 1]; ++nS) {
+            for (int ai = 1; ai <= in->nSizes; ++ai) {
+                float Td = in->Tdust[(size_t)nS + (size_t)(in->nSpeciesMax + 1) * ((size_t)ai + (size_t)(in->nSizes + 1) * (size_t)cell)];
+                if (Td < in->TdustSublime[dcp - 1 + nS - 1]) {
+                    float ga = in->grainAbun[(size_t)(nsp - 1) + (size_t)in->nDustComp * (size_t)(nS - 1)];
+                    int sp = in->dustScaXsecP[(size_t)(nS + dcp - 1 - 1) + (size_t)in->nSpeciesTot * (size_t)(ai - 1)];
+                    int ap = in->dustAbsXsecP[(size_t)(nS + dcp - 1 - 1) + (size_t)in->nSpeciesTot * (size_t)(ai - 1)];
+                    for (int f = 1; f <= nb; ++f) {
+                        size_t o = (size_t)(f - 1) * nR + cell;
+                        scaOut[o] = scaOut[o] + ga * in->grainWeight[ai - 1] * in->Ndust[cell] * xs[sp + f - 1];
+                        absOut[o] = absOut[o] + ga * in->grainWeight[ai - 1] * in->Ndust[cell] * xs[ap + f - 1];
+                    }
+                }
+            }
+        }
+        for (int f = 1; f <= nb; ++f) {
+            size_t o = (size_t)(f - 1) * nR + cell;
+            opacityOut[o] = opacityOut[o] + (scaOut[o] + absOut[o]);
+        }
+    }
+}
+
+/* ------------------------------------------------------------------------- */
 /* unit-test hooks                                                            */
 /* ------------------------------------------------------------------------- */
 void oracle_philox(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3, uint32_t k0, uint32_t k1, uint32_t *out4)

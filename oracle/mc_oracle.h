@@ -101,6 +101,29 @@ int oracle_transport_mt(const OrParams *P, OrGrid *grids, int32_t iStar,
                         int64_t firstId, int64_t n, uint64_t seed,
                         int32_t nThreads, OrCounters *C, int64_t *qphotCounts);
 
+/* Opacity assembly for every active cell of one grid: restatement of ionizationDriver's
+ * density computation (ionization_mod.f90:65-80), addOpacity/putOpacity/inOpacity
+ * (:349-484; the free-free term only ever exists in bin 1, :369-393, and is passed in as
+ * ff1 because it depends on the host's BoltGaunt cache) and of the dust loop of
+ * iteration_mod.f90:166-227.  Layouts: ionDen(0:nCells,nElementsUsed,nstages),
+ * elemAbun(nAbComp,30), elementP(30,30,7,3), nShells(30,30), all Fortran column major;
+ * abIndex/Hden/ff1/Ndust/dustAbunIndex are (0:nCells). */
+typedef struct OrOpacityIn {
+    int32_t nCells, nbins, nstages, nElementsUsed, nAbComp;
+    const int32_t *lgElementOn;   /* 1:30 */
+    const int32_t *elementXref;   /* 1:30 */
+    const float *ionDen, *elemAbun, *Hden, *ff1;
+    const int32_t *abIndex;
+    const float *xSecArray;
+    int32_t HlevXSecP1, HlevNuP1, HeISingXSecP1, HeIlevNuP1, HeIIXSecP1, HeIIlevNuP1;
+    const int32_t *elementP, *nShells;
+    /* dust (lgDust): */
+    int32_t lgDust, lgMultiDustChemistry, nSpeciesMax, nSizes, nDustComp, nSpeciesTot;
+    const int32_t *nSpeciesPart, *dustComPoint, *dustAbunIndex, *dustScaXsecP, *dustAbsXsecP;
+    const float *grainAbun, *grainWeight, *TdustSublime, *Tdust, *Ndust;
+} OrOpacityIn;
+void oracle_opacity(const OrOpacityIn *in, float *opacity, float *scaOpac, float *absOpac);
+
 /* unit-test hooks */
 void oracle_philox(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3,
                    uint32_t k0, uint32_t k1, uint32_t *out4);

@@ -52,6 +52,58 @@ class OrCounters(C.Structure):
         return {n: getattr(self, n) for n, _ in self._fields_}
 
 
+class OrOpacityIn(C.Structure):
+    _fields_ = [(n, C.c_int32) for n in ("nCells", "nbins", "nstages", "nElementsUsed", "nAbComp")] + [
+        ("lgElementOn", ip), ("elementXref", ip), ("ionDen", fp), ("elemAbun", fp), ("Hden", fp), ("ff1", fp),
+        ("abIndex", ip), ("xSecArray", fp)] + [
+        (n, C.c_int32) for n in ("HlevXSecP1", "HlevNuP1", "HeISingXSecP1", "HeIlevNuP1", "HeIIXSecP1", "HeIIlevNuP1")] + [
+        ("elementP", ip), ("nShells", ip)] + [
+        (n, C.c_int32) for n in ("lgDust", "lgMultiDustChemistry", "nSpeciesMax", "nSizes", "nDustComp", "nSpeciesTot")] + [
+        ("nSpeciesPart", ip), ("dustComPoint", ip), ("dustAbunIndex", ip), ("dustScaXsecP", ip), ("dustAbsXsecP", ip),
+        ("grainAbun", fp), ("grainWeight", fp), ("TdustSublime", fp), ("Tdust", fp), ("Ndust", fp)]
+
+
+def opacity(t, nbins, ionDen, elemAbun, abIndex, Hden, ff1=None, dust=None, model=None):
+    """oracle_opacity on reference-form inputs; returns (opacity, scaOpac, absOpac)."""
+    lib = load()
+    keep = []
+
+    def A(a, dt):
+        a = np.asfortranarray(a, dtype=dt)
+        keep.append(a)
+        return a
+
+    I = OrOpacityIn()
+    nR = Hden.shape[0]
+    I.nCells, I.nbins, I.nstages = nR - 1, nbins, t.nstages
+    I.nElementsUsed, I.nAbComp = ionDen.shape[1], elemAbun.shape[0]
+    I.lgElementOn = _p(A(t.lgElementOn, np.int32), ip); I.elementXref = _p(A(t.elementXref, np.int32), ip)
+    I.ionDen = _p(A(ionDen, np.float32), fp); I.elemAbun = _p(A(elemAbun, np.float32), fp)
+    I.Hden = _p(A(Hden, np.float32), fp); I.ff1 = _p(A(ff1, np.float32), fp) if ff1 is not None else fp()
+    I.abIndex = _p(A(abIndex, np.int32), ip); I.xSecArray = _p(A(t.xSecArray, np.float32), fp)
+    I.HlevXSecP1, I.HlevNuP1 = t.HlevXSecP1, t.HlevNuP1
+    I.HeISingXSecP1, I.HeIlevNuP1, I.HeIIXSecP1, I.HeIIlevNuP1 = t.HeISingXSecP1, t.HeIlevNuP1, t.HeIIXSecP1, t.HeIIlevNuP1
+    I.elementP = _p(A(t.elementP, np.int32), ip); I.nShells = _p(A(t.nShells, np.int32), ip)
+    op = np.zeros((nR, nbins), np.float32, order="F")
+    sca = ab = None
+    if dust is not None:
+        I.lgDust, I.lgMultiDustChemistry = 1, int(model.lgMultiDustChemistry)
+        I.nSpeciesMax, I.nSizes, I.nDustComp = model.nSpeciesMax, model.nSizes, int(model.nSpeciesPart.shape[0])
+        I.nSpeciesTot = int(np.asarray(dust["dustScaXsecP"]).shape[0])
+        I.nSpeciesPart = _p(A(model.nSpeciesPart, np.int32), ip); I.dustComPoint = _p(A(model.dustComPoint, np.int32), ip)
+        I.dustAbunIndex = _p(A(dust["dustAbunIndex"], np.int32), ip) if dust.get("dustAbunIndex") is not None else ip()
+        I.dustScaXsecP = _p(A(dust["dustScaXsecP"], np.int32), ip); I.dustAbsXsecP = _p(A(dust["dustAbsXsecP"], np.int32), ip)
+        I.grainAbun = _p(A(model.grainAbun, np.float32), fp); I.grainWeight = _p(A(dust["grainWeight"], np.float32), fp)
+        I.TdustSublime = _p(A(model.TdustSublime, np.float32), fp); I.Tdust = _p(A(dust["Tdust"], np.float32), fp)
+        I.Ndust = _p(A(dust["Ndust"], np.float32), fp)
+        sca = np.zeros((nR, nbins), np.float32, order="F")
+        ab = np.zeros((nR, nbins), np.float32, order="F")
+    lib.oracle_opacity.argtypes = [C.POINTER(OrOpacityIn), fp, fp, fp]
+    lib.oracle_opacity.restype = None
+    lib.oracle_opacity(C.byref(I), _p(op, fp), _p(sca, fp), _p(ab, fp))
+    return op, sca, ab
+
+
 def build(force: bool = False) -> str:
     src = [os.path.join(HERE, f) for f in ("mc_oracle.c", "mc_oracle.h", "detmath.h", "Makefile")]
     stale = force or not os.path.exists(LIB_PATH) or any(

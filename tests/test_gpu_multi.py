@@ -1,0 +1,79 @@
+"""Multi-GPU path: one process per GPU, packets sharded with the reference's load/rest rule,
+integer tallies summed by an NCCL all-reduce (replacing MPI_ALLREDUCE,
+iteration_mod.f90:627-659), then folded.  Result must equal the single-GPU run bit for bit
+on every rank.  Needs >= 2 GPUs (skipped otherwise)."""
+import os
+import socket
+import sys
+
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    p = s.getsockname()[1]
+    s.close()
+    return p
+
+
+def _worker(rank, world, port, name, n, q):
+    sys.path.insert(0, ROOT)
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import torch
+    import torch.distributed as dist
+
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    torch.cuda.set_device(rank)
+    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device(f"cuda:{rank}"))
+    from cases import make
+    from mocassin_b200.api import PacketEngine
+
+    m, _ = make(name)
+    e = PacketEngine(m, device=rank, rank=rank, nranks=world, seed=12345)
+    e.upload_iteration_inputs()
+    e.lucy_transport([n])
+    out = [e.fetch(iG) for iG in range(1, m.nGrids + 1)]
+    q.put((rank, out))
+    dist.barrier()
+    e.close()
+    dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("name", ["multigrid_sym", "cube_clumpy_gasdust"])
+def test_nccl_allreduce_matches_single_gpu(name):
+    import torch
+    import torch.multiprocessing as mp
+
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    from cases import make
+    from mocassin_b200.api import PacketEngine
+
+    n = 20001
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_worker, args=(r, 2, port, name, n, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    got = dict(q.get(timeout=600) for _ in range(2))
+    for p in procs:
+        p.join(timeout=120)
+        assert p.exitcode == 0
+    m, _ = make(name)
+    e = PacketEngine(m, seed=12345)
+    e.upload_iteration_inputs()
+    e.lucy_transport([n])
+    for iG in range(1, m.nGrids + 1):
+        ref = e.fetch(iG)
+        for r in (0, 1):
+            assert np.array_equal(got[r][iG - 1]["Jste"], ref["Jste"])
+            assert np.array_equal(got[r][iG - 1]["escapedPackets"], ref["escapedPackets"])
+    e.close()
