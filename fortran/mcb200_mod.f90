@@ -1,0 +1,121 @@
+! mcb200_mod.f90 -- ISO_C_BINDING interface to libmocassin_b200.so (include/mcb200.h).
+!
+! This file is the binding a maintainer of the reference (rwesson/mocassin) adds to
+! source/ so that iterateMC (source/iteration_mod.f90) drives the B200 transport instead
+! of `call energyPacketDriver`.  It is shipped as source: the build image has no Fortran
+! compiler, so it is compiled where the reference is (add it to SOURCES in the Makefile,
+! link with -L<repo>/mocassin_b200 -lmocassin_b200).  See INTEGRATION.md for the edits to
+! iteration_mod.f90.
+!
+! Every interface below is a 1:1 declaration of a C entry point; arrays are passed with
+! c_loc of the reference's own allocatable components (their layout is already what the
+! library expects: column major, cell index fastest, 1-based indices inside `active`).
+module mcb200_mod
+    use iso_c_binding
+    implicit none
+
+    type, bind(C) :: mcb200_config
+        integer(c_int32_t) :: nGrids, nbins, nStars, nAngleBins, totAngleBinsTheta, totAngleBinsPhi, nLines
+        integer(c_int32_t) :: lgDust, lgGas, lgSymmetricXYZ, lgIsotropic, lgPlaneIonization, lgDebug, &
+             & lgMultistars, lgMultiDustChemistry
+        integer(c_int32_t) :: nSpeciesMax, nSizes, nDustComp
+        real(c_float)      :: dTheta, dPhi, R_out, ionEdge1
+    end type mcb200_config
+
+    type, bind(C) :: mcb200_counters
+        integer(c_int64_t) :: nPackets, nAbs, nSca, trapped, nLinePackets, nDropped, nSegments, &
+             & nFlights, nEscaped, nEarlyEscaped
+        real(c_double)     :: Qphot, kernel_ms, total_ms
+    end type mcb200_counters
+
+    type(c_ptr), save :: mcb_ctx = c_null_ptr
+
+    interface
+       integer(c_int) function mcb200_create(ctx, device, rank, nranks, seed) bind(C, name="mcb200_create")
+         import; type(c_ptr), intent(out) :: ctx
+         integer(c_int32_t), value :: device, rank, nranks; integer(c_int64_t), value :: seed
+       end function
+       integer(c_int) function mcb200_destroy(ctx) bind(C, name="mcb200_destroy")
+         import; type(c_ptr), value :: ctx
+       end function
+       type(c_ptr) function mcb200_last_error(ctx) bind(C, name="mcb200_last_error")
+         import; type(c_ptr), value :: ctx
+       end function
+       integer(c_int) function mcb200_set_config(ctx, cfg) bind(C, name="mcb200_set_config")
+         import; type(c_ptr), value :: ctx; type(mcb200_config), intent(in) :: cfg
+       end function
+       integer(c_int) function mcb200_set_grid(ctx, iG, nx, ny, nz, nCells, motherP, xAxis, yAxis, zAxis, active) &
+            & bind(C, name="mcb200_set_grid")
+         import; type(c_ptr), value :: ctx, xAxis, yAxis, zAxis, active
+         integer(c_int32_t), value :: iG, nx, ny, nz, nCells, motherP
+       end function
+       integer(c_int) function mcb200_set_spectra(ctx, nuArray, gSca, inSpectrumProbDen) bind(C, name="mcb200_set_spectra")
+         import; type(c_ptr), value :: ctx, nuArray, gSca, inSpectrumProbDen
+       end function
+       integer(c_int) function mcb200_set_stars(ctx, starPosition, starIndeces) bind(C, name="mcb200_set_stars")
+         import; type(c_ptr), value :: ctx, starPosition, starIndeces
+       end function
+       integer(c_int) function mcb200_set_viewpoints(ctx, pTheta, pPhi, vTheta, vPhi) bind(C, name="mcb200_set_viewpoints")
+         import; type(c_ptr), value :: ctx, pTheta, pPhi, vTheta, vPhi
+       end function
+       integer(c_int) function mcb200_set_dust_species(ctx, nSpeciesPart, grainAbun, dustComPoint, TdustSublime, nSpecies) &
+            & bind(C, name="mcb200_set_dust_species")
+         import; type(c_ptr), value :: ctx, nSpeciesPart, grainAbun, dustComPoint, TdustSublime
+         integer(c_int32_t), value :: nSpecies
+       end function
+       integer(c_int) function mcb200_set_opacity(ctx, iG, opacity, scaOpac) bind(C, name="mcb200_set_opacity")
+         import; type(c_ptr), value :: ctx, opacity, scaOpac; integer(c_int32_t), value :: iG
+       end function
+       integer(c_int) function mcb200_set_pdfs(ctx, iG, recPDF, dustPDF, totalLines, linePDF) bind(C, name="mcb200_set_pdfs")
+         import; type(c_ptr), value :: ctx, recPDF, dustPDF, totalLines, linePDF; integer(c_int32_t), value :: iG
+       end function
+       integer(c_int) function mcb200_set_dust_state(ctx, iG, Tdust, dustAbunIndex) bind(C, name="mcb200_set_dust_state")
+         import; type(c_ptr), value :: ctx, Tdust, dustAbunIndex; integer(c_int32_t), value :: iG
+       end function
+       integer(c_int) function mcb200_zero_estimators(ctx) bind(C, name="mcb200_zero_estimators")
+         import; type(c_ptr), value :: ctx
+       end function
+       integer(c_int) function mcb200_transport(ctx, iStar, nPacketsGlobal, deltaE, counters) bind(C, name="mcb200_transport")
+         import; type(c_ptr), value :: ctx; integer(c_int32_t), value :: iStar
+         integer(c_int64_t), value :: nPacketsGlobal; real(c_float), value :: deltaE
+         type(mcb200_counters), intent(out) :: counters
+       end function
+       integer(c_int) function mcb200_transport_diffuse(ctx, gpLoc, cellLoc, nPacketsGlobal, deltaE, counters) &
+            & bind(C, name="mcb200_transport_diffuse")
+         import; type(c_ptr), value :: ctx, cellLoc; integer(c_int32_t), value :: gpLoc
+         integer(c_int64_t), value :: nPacketsGlobal; real(c_float), value :: deltaE
+         type(mcb200_counters), intent(out) :: counters
+       end function
+       integer(c_int) function mcb200_tally_buffer(ctx, iG, which, devPtr, count) bind(C, name="mcb200_tally_buffer")
+         import; type(c_ptr), value :: ctx; integer(c_int32_t), value :: iG, which
+         type(c_ptr), intent(out) :: devPtr; integer(c_int64_t), intent(out) :: count
+       end function
+       integer(c_int) function mcb200_reduce(ctx) bind(C, name="mcb200_reduce")
+         import; type(c_ptr), value :: ctx
+       end function
+       integer(c_int) function mcb200_fetch_estimators(ctx, iG, Jste, escapedPackets, Jdif, linePackets) &
+            & bind(C, name="mcb200_fetch_estimators")
+         import; type(c_ptr), value :: ctx, Jste, escapedPackets, Jdif, linePackets; integer(c_int32_t), value :: iG
+       end function
+    end interface
+
+contains
+
+    ! the reference's error behaviour: print and stop (e.g. photon_mod.f90:826-832)
+    subroutine mcb_check(rc, where)
+        integer(c_int), intent(in) :: rc
+        character(len=*), intent(in) :: where
+        character(kind=c_char), pointer :: msg(:)
+        integer :: i
+        if (rc == 0) return
+        call c_f_pointer(mcb200_last_error(mcb_ctx), msg, [512])
+        write(*, '(a)', advance='no') '! '//where//': '
+        do i = 1, 512
+           if (msg(i) == c_null_char) exit
+           write(*, '(a)', advance='no') msg(i)
+        end do
+        print*, ' [mcb200 status ', rc, ']'
+        stop
+    end subroutine mcb_check
+
+end module mcb200_mod
