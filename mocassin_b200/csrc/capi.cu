@@ -25,6 +25,28 @@ cudaError_t launch_fold_j(unsigned long long *Q, float *J, const float *dV, int 
                           double lenUnit, float deltaE, int blocks, cudaStream_t s);
 cudaError_t launch_fold_count(unsigned long long *Q, float *E, size_t total, float deltaE, int blocks,
                               cudaStream_t s);
+struct PacketRec;
+struct PacketRecX;
+struct WfArgs {
+    TransportArgs t;
+    PacketRec *recA, *recB;
+    PacketRecX *recxA, *recxB;
+    const unsigned int *inList;
+    const unsigned int *inCount;
+    unsigned short *flyKey;
+    unsigned int *flyCount;
+    unsigned int *evList[4];
+    unsigned int *evCount;
+    int stepBudget;
+    unsigned int *hist, *cursor;
+    unsigned long long *nextFlight;
+};
+cudaError_t wf_launch_event(const WfArgs &w, bool multi, int ev, int blocks, cudaStream_t s);
+cudaError_t wf_launch_fly(const WfArgs &w, bool multi, int blocks, cudaStream_t s);
+cudaError_t wf_launch_sort(const WfArgs &w, bool multi, int numSMs, cudaStream_t s);
+int wf_fly_blocks_per_sm(bool multi);
+size_t wf_rec_bytes();
+size_t wf_recx_bytes();
 struct OpacityArgs {
     int nRows, nb;
     int nSpeciesDen;
@@ -122,6 +144,13 @@ struct mcb200_ctx {
     DevBuf<unsigned short> sortKey;
     DevBuf<unsigned int> sortHist, sortCursor, sortOrder;
     int orderMode = -1;                   // -1 auto, 0 off, 1 on: process packets in frequency order
+    int waveMode = -1;                    // -1 auto, 0 persistent kernel, 1 wave-front pipeline
+    DevBuf<unsigned char> wfRecA, wfRecB, wfRecXA, wfRecXB;
+    DevBuf<unsigned int> wfEv0, wfEv1, wfEv2, wfEv3, wfCounts, wfHist, wfCursor, wfSegs;
+    int stepBudget = 96;
+    DevBuf<unsigned short> wfFlyKey;
+    DevBuf<unsigned long long> wfNext;
+    int lastWaves = 0, lastLaunches = 0;
     int aggSteps = 0, batch = 12;
     bool trace = false;
     int blocksPerSM = 0;                  // 0 = occupancy default
@@ -273,6 +302,65 @@ int fold_pending(mcb200_ctx *ctx)
     return MCB200_OK;
 }
 
+// wave-front schedule (wavefront.cu): event kernels + frequency sort + FLY kernel per wave
+int run_wavefront(mcb200_ctx *ctx, const TransportArgs &a, bool multi, int64_t mine)
+{
+    const int nb = ctx->cfg.nbins;
+    cudaStream_t s = ctx->stream;
+    size_t n = (size_t)mine;
+    CU(ctx->wfRecA.alloc(n * wf_rec_bytes())); CU(ctx->wfRecB.alloc(n * wf_rec_bytes()));
+    if (multi) { CU(ctx->wfRecXA.alloc(n * wf_recx_bytes())); CU(ctx->wfRecXB.alloc(n * wf_recx_bytes())); }
+    CU(ctx->wfFlyKey.alloc(n));
+    CU(ctx->wfEv0.alloc(n)); CU(ctx->wfEv1.alloc(n)); CU(ctx->wfEv2.alloc(n)); CU(ctx->wfEv3.alloc(n));
+    CU(ctx->wfCounts.alloc(8)); CU(ctx->wfNext.alloc(1));
+    CU(ctx->wfHist.alloc(nb + 1)); CU(ctx->wfCursor.alloc(nb + 1));
+    CU(ctx->wfHist.zero(s));
+    WfArgs w{};
+    w.t = a;
+    w.recA = reinterpret_cast<PacketRec *>(ctx->wfRecA.p); w.recB = reinterpret_cast<PacketRec *>(ctx->wfRecB.p);
+    w.recxA = reinterpret_cast<PacketRecX *>(ctx->wfRecXA.p); w.recxB = reinterpret_cast<PacketRecX *>(ctx->wfRecXB.p);
+    w.flyKey = ctx->wfFlyKey.p;
+    w.flyCount = ctx->wfCounts.p; w.evCount = ctx->wfCounts.p + 1;
+    w.evList[0] = ctx->wfEv0.p; w.evList[1] = ctx->wfEv1.p; w.evList[2] = ctx->wfEv2.p; w.evList[3] = ctx->wfEv3.p;
+    w.stepBudget = ctx->stepBudget < 1 ? 1 : ctx->stepBudget;
+    if (a.fates) { CU(ctx->wfSegs.alloc(n)); CU(ctx->wfSegs.zero(s)); w.t.segsArr = ctx->wfSegs.p; }
+    w.hist = ctx->wfHist.p; w.cursor = ctx->wfCursor.p; w.nextFlight = ctx->wfNext.p;
+    int flyBps = ctx->blocksPerSM > 0 ? ctx->blocksPerSM : wf_fly_blocks_per_sm(multi);
+    if (flyBps < 1) flyBps = 1;
+    const int flyBlocks = ctx->numSMs * flyBps;
+    auto evBlocks = [&](uint64_t cnt) {
+        uint64_t b = (cnt + 255) / 256, cap = (uint64_t)ctx->numSMs * 16;
+        return (int)(b < 1 ? 1 : (b > cap ? cap : b));
+    };
+    ctx->lastWaves = 0; ctx->lastLaunches = 0;
+    // wave 0: every packet is emitted
+    CU(ctx->wfCounts.zero(s));
+    w.inList = nullptr; w.inCount = nullptr;
+    CU(wf_launch_event(w, multi, 0, evBlocks((uint64_t)mine), s));
+    ctx->lastLaunches++;
+    for (;;) {
+        CU(wf_launch_sort(w, multi, ctx->numSMs, s));
+        CU(cudaMemsetAsync(w.evCount, 0, 4 * sizeof(unsigned int), s));
+        CU(ctx->wfNext.zero(s));
+        CU(wf_launch_fly(w, multi, flyBlocks, s));
+        ctx->lastLaunches += 4;
+        ctx->lastWaves++;
+        unsigned int hc[5];
+        CU(cudaMemcpyAsync(hc, ctx->wfCounts.p, sizeof(hc), cudaMemcpyDeviceToHost, s));
+        CU(cudaStreamSynchronize(s));
+        if (hc[1] + hc[2] + hc[3] + hc[4] == 0) break;
+        CU(cudaMemsetAsync(w.flyCount, 0, sizeof(unsigned int), s));
+        for (int ev = 3; ev >= 0; --ev) {
+            if (!hc[1 + ev]) continue;
+            w.inList = w.evList[ev]; w.inCount = &w.evCount[ev];
+            CU(wf_launch_event(w, multi, ev, evBlocks(hc[1 + ev]), s));
+            ctx->lastLaunches++;
+        }
+        if (hc[1] + hc[2] + hc[4] == 0) break;   // only escapes were pending: nothing can fly any more
+    }
+    return MCB200_OK;
+}
+
 int run_transport(mcb200_ctx *ctx, int iStar, int difGrid, const int32_t *cellLoc, int64_t nGlobal,
                   float deltaE, mcb200_counters *out)
 {
@@ -336,6 +424,7 @@ int run_transport(mcb200_ctx *ctx, int iStar, int difGrid, const int32_t *cellLo
     a.nextPacket = ctx->nextPacket.p; a.counters = ctx->counters.p; a.qphotCounts = ctx->qphot.p;
     a.errFlag = ctx->errFlag.p;
     a.fates = nullptr;
+    a.segsArr = nullptr;
     if (ctx->trace) {
         CU(ctx->fates.alloc((size_t)4 * (size_t)(mine > 0 ? mine : 1)));
         CU(ctx->fates.zero(ctx->stream));
@@ -358,14 +447,23 @@ int run_transport(mcb200_ctx *ctx, int iStar, int difGrid, const int32_t *cellLo
     a.order = nullptr;
     a.batch = ctx->batch < 1 ? 1 : ctx->batch;
     a.aggSteps = 0;
-    if (ordered && mine > 0) {
+    bool waveSel = ctx->waveMode == 1 || (ctx->waveMode < 0 && mine >= (1 << 17));
+    if (ordered && mine > 0 && !waveSel) {
         CU(ctx->sortKey.alloc((size_t)mine)); CU(ctx->sortOrder.alloc((size_t)mine));
         CU(ctx->sortHist.alloc(cfg.nbins + 1)); CU(ctx->sortCursor.alloc(cfg.nbins + 1));
         CU(launch_order(a, ctx->sortKey.p, ctx->sortHist.p, ctx->sortCursor.p, ctx->sortOrder.p, ctx->numSMs, ctx->stream));
         a.order = ctx->sortOrder.p;
         a.aggSteps = ctx->aggSteps;
     }
-    if (mine > 0) CU(launch_transport(a, multi, blocks, ctx->stream));
+    bool wave = ctx->waveMode == 1 || (ctx->waveMode < 0 && mine >= (1 << 17));
+    if (mine > 0 && wave) {
+        if (mine >= ((int64_t)1 << 31)) return fail(ctx, MCB200_EINVAL, "more than 2^31 packets per rank in one wave-front call: split the call");
+        a.order = nullptr;
+        int rcw = run_wavefront(ctx, a, multi, mine);
+        if (rcw) return rcw;
+    } else if (mine > 0) {
+        CU(launch_transport(a, multi, blocks, ctx->stream));
+    }
     CU(cudaEventRecord(ctx->ev1, ctx->stream));
     CU(cudaStreamSynchronize(ctx->stream));
     float ms = 0.f;
@@ -853,6 +951,8 @@ int mcb200_set_option(mcb200_ctx *ctx, const char *name, int64_t value)
     if (!strcmp(name, "blocks_per_sm")) { ctx->blocksPerSM = (int)value; return MCB200_OK; }
     if (!strcmp(name, "seed")) { ctx->seed = (uint64_t)value; return MCB200_OK; }
     if (!strcmp(name, "order")) { ctx->orderMode = (int)value; return MCB200_OK; }
+    if (!strcmp(name, "wavefront")) { ctx->waveMode = (int)value; return MCB200_OK; }
+    if (!strcmp(name, "step_budget")) { ctx->stepBudget = (int)value; return MCB200_OK; }
     if (!strcmp(name, "agg_steps")) { ctx->aggSteps = (int)value; return MCB200_OK; }
     if (!strcmp(name, "batch")) { ctx->batch = (int)value; return MCB200_OK; }
     return fail(ctx, MCB200_EINVAL, "unknown option %s", name);

@@ -28,19 +28,21 @@ __device__ __forceinline__ void philox4x32_10(uint32_t (&c)[4], uint32_t k0, uin
 
 struct Rng {
     uint32_t k0, k1, p0, p1, stream, n;
-    uint32_t buf[4];
+    uint32_t blk;            // block index held in buf (0xffffffff = none): lets a stream be
+    uint32_t buf[4];         // resumed from its draw counter n alone (wave-front kernels)
 
-    __device__ __forceinline__ void init(uint64_t seed, uint64_t pid, uint32_t s)
+    __device__ __forceinline__ void init(uint64_t seed, uint64_t pid, uint32_t s, uint32_t n0 = 0)
     {
         k0 = (uint32_t)seed; k1 = (uint32_t)(seed >> 32);
         p0 = (uint32_t)pid;  p1 = (uint32_t)(pid >> 32);
-        stream = s; n = 0;
+        stream = s; n = n0; blk = 0xffffffffu;
     }
     __device__ __forceinline__ float uniform()
     {
         uint32_t lane = n & 3u;
-        if (lane == 0) {
-            buf[0] = p0; buf[1] = p1; buf[2] = n >> 2; buf[3] = stream;
+        if ((n >> 2) != blk) {
+            blk = n >> 2;
+            buf[0] = p0; buf[1] = p1; buf[2] = blk; buf[3] = stream;
             philox4x32_10(buf, k0, k1);
         }
         ++n;

@@ -69,6 +69,7 @@ struct TransportArgs {
     unsigned long long *qphotCounts; // [nbins]
     int *errFlag;
     int *fates;                      // optional [4*n]
+    unsigned int *segsArr;           // wave-front + trace: segments of earlier flights per packet
 };
 
 }  // namespace mcb

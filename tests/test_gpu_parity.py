@@ -81,14 +81,23 @@ def _compare(m, n, e, o, iStar=1):
     return cg, co
 
 
-@pytest.mark.parametrize("order", [0, 1])
+SCHEDULES = {
+    "persistent": dict(wavefront=0, order=0),          # one thread carries a packet through all phases
+    "persistent_ordered": dict(wavefront=0, order=1, agg_steps=6),   # + packets sorted by first nu, aggregated tallies
+    "wavefront": dict(wavefront=1),                    # per-wave event kernels + nu-sorted FLY kernel
+    "wavefront_budget3": dict(wavefront=1, step_budget=3),   # flights continue across many waves
+}
+
+
+@pytest.mark.parametrize("schedule", list(SCHEDULES))
 @pytest.mark.parametrize("name", list(CASES))
-def test_transport_bit_exact_vs_oracle(name, order):
-    """order=1: packets are processed sorted by their first frequency bin with
-    warp-aggregated tallies (the large-grid schedule); the answer must not change."""
+def test_transport_bit_exact_vs_oracle(name, schedule):
+    """Every schedule must give the oracle's answer bit for bit (tallies are
+    order-independent integers, every packet owns its Philox stream)."""
     m, n = make(name)
     e = _engine(m)
-    e.set_option("order", order)
+    for k, v in SCHEDULES[schedule].items():
+        e.set_option(k, v)
     o = Oracle(m)
     cg, co = _compare(m, n, e, o)
     # Qphot (float64 from exact counts) agrees with the reference's float32 running sum
@@ -164,6 +173,7 @@ def test_diffuse_external_source():
     e = _engine(m)
     o = Oracle(m)
     e.set_option("trace", 1)
+    e.set_option("wavefront", 1)
     e.zero_estimators()
     cell = [5, 7, 9]
     cg = e.energyPacketDriver(0, 4000, gpLoc=1, cellLoc=cell)
