@@ -602,6 +602,7 @@ int mcb200_set_grid(mcb200_ctx *ctx, int32_t iG, int32_t nx, int32_t ny, int32_t
         for (size_t i = 1; i < ax->size(); ++i)
             if (!((*ax)[i] > (*ax)[i - 1])) return fail(ctx, MCB200_EINVAL, "grid %d: axes must be strictly ascending", iG);
     size_t nTot = (size_t)nx * ny * nz;
+    if (nTot >= ((size_t)1 << 31) || nx > 32000 || ny > 32000 || nz > 32000) return fail(ctx, MCB200_EINVAL, "grid %d too large for 32-bit cell indexing", iG);
     g->hactive.assign(active, active + nTot);
     // validate and detect the dense numbering (k fastest, grid_mod.f90:1227-1262)
     int dense = 1;

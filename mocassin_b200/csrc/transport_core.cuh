@@ -43,7 +43,8 @@ struct Lane {
 __device__ __forceinline__ int active_at(const DevGrid &g, int x, int y, int z)
 {
     if (g.dense) return 1 + (z - 1) + g.nz * ((y - 1) + g.ny * (x - 1));
-    return __ldg(&g.active[(size_t)(x - 1) + (size_t)g.nx * ((size_t)(y - 1) + (size_t)g.ny * (size_t)(z - 1))]);
+    // nx*ny*nz < 2^31 (checked at upload): 32-bit index arithmetic
+    return __ldg(&g.active[(x - 1) + g.nx * ((y - 1) + g.ny * (z - 1))]);
 }
 
 // interpolation_mod.f90:48-81 for an ascending axis
@@ -255,7 +256,7 @@ struct Transport {
     {
         long long q = __float2ll_rn(len * g.invLenUnit);
         unsigned long long *Q = (!L.lgStellar && a.P.lgDebug) ? g.JdifQ : g.JsteQ;
-        unsigned long long *addr = &Q[(size_t)(L.nuP - 1) * (size_t)(g.nCells + 1) + (size_t)cell];
+        unsigned long long *addr = &Q[(size_t)((unsigned long long)(unsigned int)(L.nuP - 1) * (unsigned int)(g.nCells + 1)) + (size_t)(unsigned int)(cell > 0 ? cell : 0)];
         bool live = cell > 0;            // sink row 0: never read by the reference
         if (aggregate) {
             // one round: the lanes that share the address of the first live lane are summed
@@ -404,22 +405,28 @@ struct Transport {
         L.phase = PH_FLY;
     }
 
-    // distance to the wall ahead on one axis (photon_mod.f90:1263-1295), branch free on the
-    // sign of v: W[iP] is the wall ahead for v>0, W[iP-1] for v<0.  Returns false if the
-    // packet sits on the outermost wall of the mother grid (`return`, no tally).
-    __device__ __forceinline__ bool wall(const float *W, int n, float v, float &r, int &iP, int gP, float &dS)
+    // distance to the wall ahead on one axis (photon_mod.f90:1263-1295), completely branch
+    // free: W[iP] is the wall ahead for v>0, W[iP-1] for v<0.  A packet sitting exactly on
+    // the wall (|dS|<1e-10, in float32 at these magnitudes: w==r) is snapped and stepped
+    // over; on the outermost wall of the mother grid the reference `return`s without a
+    // tally -> `drop`.  The zero numerator is kept away from the divider (it would take the
+    // IEEE slow path and, like any rare branch here, split one lane off the warp for the
+    // rest of the step: ncu showed 58 % of the warp trips running a 1-lane straggler).
+    __device__ __forceinline__ void wall(const float *W, int n, float v, float &r, int &iP, int gP, float &dS, bool &drop)
     {
         bool pos = v > 1.e-10f, neg = v < -1.e-10f;
-        float w = __ldg(&W[pos ? iP : iP - 1]);
-        float d = (w - r) / v;
         bool moving = pos || neg;
+        float w = __ldg(&W[pos ? iP : iP - 1]);
+        float num = w - r;
+        bool zero = num == 0.f;
+        float d = (zero ? 1.f : num) / (moving ? v : 1.f);
+        d = zero ? 0.f : d;
         dS = moving ? d : 1.e35f;
-        if (moving && fabsf(d) < 1.e-10f) {          // sitting on the wall: snap and step over
-            r = w;
-            if (pos) { if (iP < n) iP = iP + 1; else if (gP == 1) return false; }
-            else     { if (iP > 1) iP = iP - 1; }
-        }
-        return true;
+        bool snap = moving && fabsf(d) < 1.e-10f;
+        r = snap ? w : r;
+        int step = pos ? (iP < n ? 1 : 0) : (iP > 1 ? -1 : 0);
+        drop = drop || (snap && pos && iP >= n && gP == 1);
+        iP += snap ? step : 0;
     }
 
     // absorbed: hand over to the next generation (photon_mod.f90:2848-2870)
@@ -473,16 +480,19 @@ struct Transport {
             }
             // the reference returns at the first axis found on the outer wall, i.e. before
             // the later axes are looked at; nothing after a `return` is observable
-            if (!wall(g.xWall, g.nx, L.vx, L.rx, L.xP, L.gP, dSx) ||
-                !wall(g.yWall, g.ny, L.vy, L.ry, L.yP, L.gP, dSy) ||
-                !wall(g.zWall, g.nz, L.vz, L.rz, L.zP, L.gP, dSz)) { finish(L, FATE_DROPPED); return; }
-            if (!(dSx >= 0.f || dSx < 0.f) || !(dSy >= 0.f || dSy < 0.f) || !(dSz >= 0.f || dSz < 0.f)) { fail(L, 60); return; }
+            bool drop = false;
+            wall(g.xWall, g.nx, L.vx, L.rx, L.xP, L.gP, dSx, drop);
+            wall(g.yWall, g.ny, L.vy, L.ry, L.yP, L.gP, dSy, drop);
+            wall(g.zWall, g.nz, L.vz, L.rz, L.zP, L.gP, dSz, drop);
+            if (drop) { finish(L, FATE_DROPPED); return; }
+            if ((dSx != dSx) | (dSy != dSy) | (dSz != dSz)) { fail(L, 60); return; }
             cell = active_at(g, L.xP, L.yP, L.zP);
             if (!MULTI || cell >= 0) break;
             if (j >= kSafeLimit) { fail(L, 63); return; }
         }
         const DevGrid &g = G(L.gP);
-        size_t tix = (size_t)(L.nuP - 1) * (size_t)(g.nCells + 1) + (size_t)cell;
+        // one IMAD.WIDE: 32 x 32 -> 64 bit
+        size_t tix = (size_t)((unsigned long long)(unsigned int)(L.nuP - 1) * (unsigned int)(g.nCells + 1)) + (size_t)(unsigned int)cell;
         float opac = __ldg(&g.opacity[tix]);
 
         // cells on a wall (:1395-1397): the axis end coordinate replaces a zero distance
@@ -551,21 +561,22 @@ struct Transport {
         if (MULTI && L.gP > 1) track_mother(L);
 
         // :1961-1976
-        if (dS == dSx && L.vx > 0.f) L.xP = L.xP + 1;
-        else if (dS == dSx && L.vx < 0.f) L.xP = L.xP - 1;
-        else if (dS == dSy && L.vy > 0.f) L.yP = L.yP + 1;
-        else if (dS == dSy && L.vy < 0.f) L.yP = L.yP - 1;
-        else if (dS == dSz && L.vz > 0.f) L.zP = L.zP + 1;
-        else if (dS == dSz && L.vz < 0.f) L.zP = L.zP - 1;
+        // (the reference's if / else-if chain, evaluated without branches)
+        {
+            int ax = (dS == dSx) ? ((L.vx > 0.f) - (L.vx < 0.f)) : 0;
+            int ay = (ax == 0 && dS == dSy) ? ((L.vy > 0.f) - (L.vy < 0.f)) : 0;
+            int az = (ax == 0 && ay == 0 && dS == dSz) ? ((L.vz > 0.f) - (L.vz < 0.f)) : 0;
+            L.xP += ax; L.yP += ay; L.zP += az;
+        }
 
         if (!MULTI) {
             // single grid: every test of :1986-2194, :2417-2540 and :2733-2834 that is true
             // ends in the same escape tally, so they collapse into one predicate
-            bool out = (L.rx >= g.xHi) || (L.ry >= g.yHi) || (L.rz >= g.zHi) ||
-                       L.xP > g.nx || L.yP > g.ny || L.zP > g.nz;
-            if (!P.lgSym)
-                out = out || (L.rx <= g.xLo) || (L.ry <= g.yLo) || (L.rz <= g.zLo) ||
-                      L.xP < 1 || L.yP < 1 || L.zP < 1;
+            bool out = (L.rx >= g.xHi) | (L.ry >= g.yHi) | (L.rz >= g.zHi) |
+                       (L.xP > g.nx) | (L.yP > g.ny) | (L.zP > g.nz);
+            bool low = (L.rx <= g.xLo) | (L.ry <= g.yLo) | (L.rz <= g.zLo) |
+                       (L.xP < 1) | (L.yP < 1) | (L.zP < 1);
+            out = out | (low & !P.lgSym);
             if (out) { escape(L, FATE_ESCAPED); return; }
             if (P.lgSym) {               // :2674-2699
                 if (L.rx <= g.x1 || L.xP < 1) { L.vx = fabsf(L.vx); L.xP = 1; L.rx = g.x1; }
