@@ -252,11 +252,11 @@ struct Transport {
     // steps (everything starts in the star's cell): those adds are pre-reduced inside the
     // warp (MATCH.ANY + REDUX) so the L2 atomic unit of that one address is not hammered
     // by 32 separate reductions per warp.  Integer sums are exact -> same result.
-    __device__ __forceinline__ void j_add(const DevGrid &g, const Lane &L, int cell, float len, bool aggregate)
+    __device__ __forceinline__ void j_add(const DevGrid &g, const Lane &L, int cell, size_t tix, float len, bool aggregate)
     {
         long long q = __float2ll_rn(len * g.invLenUnit);
         unsigned long long *Q = (!L.lgStellar && a.P.lgDebug) ? g.JdifQ : g.JsteQ;
-        unsigned long long *addr = &Q[(size_t)((unsigned long long)(unsigned int)(L.nuP - 1) * (unsigned int)(g.nCells + 1)) + (size_t)(unsigned int)(cell > 0 ? cell : 0)];
+        unsigned long long *addr = &Q[tix];
         bool live = cell > 0;            // sink row 0: never read by the reference
         if (aggregate) {
             // one round: the lanes that share the address of the first live lane are summed
@@ -412,21 +412,26 @@ struct Transport {
     // tally -> `drop`.  The zero numerator is kept away from the divider (it would take the
     // IEEE slow path and, like any rare branch here, split one lane off the warp for the
     // rest of the step: ncu showed 58 % of the warp trips running a 1-lane straggler).
-    __device__ __forceinline__ void wall(const float *W, int n, float v, float &r, int &iP, int gP, float &dS, bool &drop)
+    __device__ __forceinline__ void wall(const float *W, int n, float v, float &r, int &iP, int gP, float &dS,
+                                         bool &drop, bool &pos)
     {
-        bool pos = v > 1.e-10f, neg = v < -1.e-10f;
+        pos = v > 1.e-10f;
+        bool neg = v < -1.e-10f;
         bool moving = pos || neg;
         float w = __ldg(&W[pos ? iP : iP - 1]);
         float num = w - r;
         bool zero = num == 0.f;
-        float d = (zero ? 1.f : num) / (moving ? v : 1.f);
+        // zero numerator -> 1.0 by OR-ing the exponent bits in (opaque to the optimiser, which
+        // would otherwise fold the select back into num / v and call the divider's slow path)
+        float numSafe = __uint_as_float(__float_as_uint(num) | (zero ? 0x3f800000u : 0u));
+        float d = numSafe / (moving ? v : 1.f);
         d = zero ? 0.f : d;
         dS = moving ? d : 1.e35f;
-        bool snap = moving && fabsf(d) < 1.e-10f;
-        r = snap ? w : r;
-        int step = pos ? (iP < n ? 1 : 0) : (iP > 1 ? -1 : 0);
-        drop = drop || (snap && pos && iP >= n && gP == 1);
-        iP += snap ? step : 0;
+        if (moving && fabsf(d) < 1.e-10f) {          // sitting on the wall: snap and step over (rare,
+            r = w;                                   // tiny body: reconverges immediately)
+            if (pos) { if (iP < n) iP = iP + 1; else drop = drop || (gP == 1); }
+            else     { if (iP > 1) iP = iP - 1; }
+        }
     }
 
     // absorbed: hand over to the next generation (photon_mod.f90:2848-2870)
@@ -448,6 +453,7 @@ struct Transport {
         L.istep++;
         L.segs++;
         float dSx = 0.f, dSy = 0.f, dSz = 0.f;
+        bool posx = false, posy = false, posz = false;
         int cell;
         for (int j = 1;; ++j) {
             if (MULTI) {
@@ -481,9 +487,9 @@ struct Transport {
             // the reference returns at the first axis found on the outer wall, i.e. before
             // the later axes are looked at; nothing after a `return` is observable
             bool drop = false;
-            wall(g.xWall, g.nx, L.vx, L.rx, L.xP, L.gP, dSx, drop);
-            wall(g.yWall, g.ny, L.vy, L.ry, L.yP, L.gP, dSy, drop);
-            wall(g.zWall, g.nz, L.vz, L.rz, L.zP, L.gP, dSz, drop);
+            wall(g.xWall, g.nx, L.vx, L.rx, L.xP, L.gP, dSx, drop, posx);
+            wall(g.yWall, g.ny, L.vy, L.ry, L.yP, L.gP, dSy, drop, posy);
+            wall(g.zWall, g.nz, L.vz, L.rz, L.zP, L.gP, dSz, drop, posz);
             if (drop) { finish(L, FATE_DROPPED); return; }
             if ((dSx != dSx) | (dSy != dSy) | (dSz != dSz)) { fail(L, 60); return; }
             cell = active_at(g, L.xP, L.yP, L.zP);
@@ -500,19 +506,20 @@ struct Transport {
         if (fabsf(dSy) < 1.e-10f) dSy = g.yN;
         if (fabsf(dSz) < 1.e-10f) dSz = g.zN;
         dSx = fabsf(dSx); dSy = fabsf(dSy); dSz = fabsf(dSz);
-        float dS;
-        if (dSx <= 0.f)      dS = fminf(dSy, dSz);
-        else if (dSy <= 0.f) dS = fminf(dSx, dSz);
-        else if (dSz <= 0.f) dS = fminf(dSx, dSy);
-        else { dS = fminf(dSx, dSy); dS = fminf(dS, dSz); }
-        if (dS <= 0.f) { fail(L, 64); return; }
+        float dS = fminf(fminf(dSx, dSy), dSz);
+        if (dS <= 0.f) {                             // :1404-1432, only if an axis end coordinate is <= 0
+            if (dSx <= 0.f)      dS = fminf(dSy, dSz);
+            else if (dSy <= 0.f) dS = fminf(dSx, dSz);
+            else                 dS = fminf(dSx, dSy);
+            if (dS <= 0.f) { fail(L, 64); return; }
+        }
 
         float tauCell = dS * opac;
         const bool interacts = (L.absTau + tauCell > L.passProb) && (cell > 0);
         // path length inside this cell: up to the interaction point or to the wall
         float dlLoc = dS;
         if (interacts) dlLoc = (L.passProb - L.absTau) / opac;
-        j_add(g, L, cell, dlLoc, aggEarly);
+        j_add(g, L, cell, tix, dlLoc, aggEarly);
 
         if (interacts) {
             // ---- interaction (:1517-1814) ----
@@ -561,12 +568,22 @@ struct Transport {
         if (MULTI && L.gP > 1) track_mother(L);
 
         // :1961-1976
-        // (the reference's if / else-if chain, evaluated without branches)
-        {
-            int ax = (dS == dSx) ? ((L.vx > 0.f) - (L.vx < 0.f)) : 0;
-            int ay = (ax == 0 && dS == dSy) ? ((L.vy > 0.f) - (L.vy < 0.f)) : 0;
-            int az = (ax == 0 && ay == 0 && dS == dSz) ? ((L.vz > 0.f) - (L.vz < 0.f)) : 0;
-            L.xP += ax; L.yP += ay; L.zP += az;
+        // The reference's if / else-if chain on (dS == dSa .and. vHat_a > 0 / < 0).  An axis whose
+        // distance is the (finite) minimum is moving, so v_a > 0 <=> pos_a from the wall stage;
+        // only a packet with no moving axis at all (dS = 1e35, impossible for a unit vector)
+        // needs the literal chain.
+        if (dS < 1.e35f) {
+            bool ex = dS == dSx, ey = (dS == dSy) & !ex, ez = (dS == dSz) & !ex & !ey;
+            L.xP += ex ? (posx ? 1 : -1) : 0;
+            L.yP += ey ? (posy ? 1 : -1) : 0;
+            L.zP += ez ? (posz ? 1 : -1) : 0;
+        } else {
+            if (dS == dSx && L.vx > 0.f) L.xP = L.xP + 1;
+            else if (dS == dSx && L.vx < 0.f) L.xP = L.xP - 1;
+            else if (dS == dSy && L.vy > 0.f) L.yP = L.yP + 1;
+            else if (dS == dSy && L.vy < 0.f) L.yP = L.yP - 1;
+            else if (dS == dSz && L.vz > 0.f) L.zP = L.zP + 1;
+            else if (dS == dSz && L.vz < 0.f) L.zP = L.zP - 1;
         }
 
         if (!MULTI) {
