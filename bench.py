@@ -316,14 +316,14 @@ def run_b200(args):
         dist.barrier()
     torch.cuda.synchronize()
     t0 = time.perf_counter()
-    kms, tms, segs, flights = 0.0, 0.0, 0, 0
+    kms, tms, segs, flights, launches, waves = 0.0, 0.0, 0, 0, 0, 0
     for _ in range(args.steps):
         ts = time.perf_counter()
         c = step()
         wall_ms = 1e3 * (time.perf_counter() - ts)
         kms += c["kernel_ms"]
         tms += c["total_ms"] if world == 1 else wall_ms      # N>1: include the all-reduce + fold
-        segs += c["nSegments"]; flights += c["nFlights"]
+        segs += c["nSegments"]; flights += c["nFlights"]; launches += c["nLaunches"]; waves += c["nWaves"]
     torch.cuda.synchronize()
     if world > 1:
         dist.barrier()
@@ -378,7 +378,7 @@ def run_b200(args):
     tr = ncu_traffic()
     roofline = {"bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak,
                 "traffic": (tr or {}).get("dram_bytes_per_launch"), "peak_kind": f"of {peak_kind}",
-                "kernel": "mcb::transport_kernel<false>", "algorithmic_bytes_per_segment": ALG_BYTES_PER_SEGMENT,
+                "kernel": "mcb::wf_fly_kernel<false> (+ event/sort kernels of the wave-front pipeline)", "algorithmic_bytes_per_segment": ALG_BYTES_PER_SEGMENT,
                 "segments_per_launch": segs / args.steps, "kernel_ms_per_launch": kms / args.steps,
                 "segments_per_s": segs / (kms / 1e3)}
     cpu = None
@@ -389,7 +389,8 @@ def run_b200(args):
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": tms_max / args.steps,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": workload_config(args, P), "clocks": clocks, "e2e": e2e,
-        "gpu_launches": int(args.steps * 3),      # transport_kernel + fold_j_kernel + fold_count_kernel per step
+        "gpu_launches": int(launches),            # counted by the library: wave-front kernels + fold kernels
+        "waves_per_step": waves / args.steps,
         "roofline": roofline, "cpu_baseline": cpu,
         "segments_per_packet": segs_all / (nGlobal * args.steps),
         "flights_per_packet": flights / (P * args.steps),

@@ -26,6 +26,7 @@ module mcb200_mod
         integer(c_int64_t) :: nPackets, nAbs, nSca, trapped, nLinePackets, nDropped, nSegments, &
              & nFlights, nEscaped, nEarlyEscaped
         real(c_double)     :: Qphot, kernel_ms, total_ms
+        integer(c_int64_t) :: nLaunches, nWaves
     end type mcb200_counters
 
     type(c_ptr), save :: mcb_ctx = c_null_ptr

@@ -74,6 +74,8 @@ typedef struct mcb200_counters {
     double  Qphot;                 /* sum deltaE/(2.1799153e-11*nu), nu>1 Ryd (:859-861)*/
     double  kernel_ms;             /* device time of the transport kernel (CUDA events)  */
     double  total_ms;              /* device time transport kernel + fold epilogue        */
+    int64_t nLaunches;             /* kernels launched by this call (transport + fold)    */
+    int64_t nWaves;                /* wave-front schedule: waves (0 = persistent kernel)  */
 } mcb200_counters;
 
 /* ---- lifecycle ---------------------------------------------------------------- */

@@ -332,7 +332,6 @@ int run_wavefront(mcb200_ctx *ctx, const TransportArgs &a, bool multi, int64_t m
         uint64_t b = (cnt + 255) / 256, cap = (uint64_t)ctx->numSMs * 16;
         return (int)(b < 1 ? 1 : (b > cap ? cap : b));
     };
-    ctx->lastWaves = 0; ctx->lastLaunches = 0;
     // wave 0: every packet is emitted
     CU(ctx->wfCounts.zero(s));
     w.inList = nullptr; w.inCount = nullptr;
@@ -456,6 +455,7 @@ int run_transport(mcb200_ctx *ctx, int iStar, int difGrid, const int32_t *cellLo
         a.aggSteps = ctx->aggSteps;
     }
     bool wave = ctx->waveMode == 1 || (ctx->waveMode < 0 && mine >= (1 << 17));
+    ctx->lastWaves = 0; ctx->lastLaunches = (ordered && mine > 0 && !wave ? 3 : 0) + (mine > 0 && !wave ? 1 : 0);
     if (mine > 0 && wave) {
         if (mine >= ((int64_t)1 << 31)) return fail(ctx, MCB200_EINVAL, "more than 2^31 packets per rank in one wave-front call: split the call");
         a.order = nullptr;
@@ -487,6 +487,8 @@ int run_transport(mcb200_ctx *ctx, int iStar, int difGrid, const int32_t *cellLo
         out->Qphot = Q;
         out->kernel_ms = ms;
         out->total_ms = ms;
+        out->nLaunches = ctx->lastLaunches;
+        out->nWaves = ctx->lastWaves;
     }
     ctx->pending = true;
     ctx->pendingDeltaE = deltaE;
@@ -498,7 +500,7 @@ int run_transport(mcb200_ctx *ctx, int iStar, int difGrid, const int32_t *cellLo
         CU(cudaEventSynchronize(ctx->ev2));
         float ms2 = 0.f;
         CU(cudaEventElapsedTime(&ms2, ctx->ev0, ctx->ev2));
-        if (out) out->total_ms = ms2;
+        if (out) { out->total_ms = ms2; out->nLaunches += 2 * (int64_t)ctx->grids.size() * (ctx->cfg.lgDebug ? 2 : 1); }
     }
     return MCB200_OK;
 }
