@@ -193,9 +193,10 @@ int mcb200_transport_diffuse(mcb200_ctx *ctx, int32_t gpLoc, const int32_t *cell
                              int64_t nPacketsGlobal, float deltaE, mcb200_counters *counters);
 
 /* Device pointers and element counts of the pending integer tallies of grid iG so
- * the caller's communicator can sum them across ranks (NCCL allreduce, int64 sum)
+ * the caller's communicator can sum them across ranks in place (NCCL allreduce, sum)
  * -- replaces MPI_ALLREDUCE at iteration_mod.f90:627,649,653,659.  which: 0 JsteQ,
- * 1 escapedQ, 2 JdifQ, 3 linePacketsQ. */
+ * 2 JdifQ (int64 fixed-point path lengths); 1 escapedQ, 3 linePacketsQ (uint32 packet
+ * counts: the global packet count of one call must stay below 2^32). */
 int mcb200_tally_buffer(mcb200_ctx *ctx, int32_t iG, int32_t which, void **devPtr, int64_t *count);
 /* After the allreduce: fold the (now global) integer tallies of the last transport
  * call into the float32 estimators. No-op when nothing is pending. */

@@ -254,7 +254,8 @@ class PacketEngine:
                     ptr, n = self.tally_buffer(iG, w)
                     if n == 0:
                         continue
-                    t = _as_cuda_tensor(ptr, n, torch.int64, self._device_index())
+                    # path lengths are int64; packet counts uint32 (summed as int32 bit patterns)
+                    t = _as_cuda_tensor(ptr, n, "<i8" if w in (0, 2) else "<i4", self._device_index())
                     dist.all_reduce(t, op=dist.ReduceOp.SUM, group=group)
             torch.cuda.synchronize()
         self._check(self.lib.mcb200_reduce(self.h))
@@ -331,7 +332,7 @@ class PacketEngine:
         return out
 
 
-def _as_cuda_tensor(ptr: int, n: int, dtype, device_index: int):
+def _as_cuda_tensor(ptr: int, n: int, typestr: str, device_index: int):
     """Wrap a raw device pointer as a torch tensor (no copy) via __cuda_array_interface__."""
     import torch
 
@@ -340,7 +341,7 @@ def _as_cuda_tensor(ptr: int, n: int, dtype, device_index: int):
 
     h = _Holder()
     h.__cuda_array_interface__ = {
-        "shape": (n,), "typestr": "<i8", "data": (ptr, False), "version": 3, "strides": None,
+        "shape": (n,), "typestr": typestr, "data": (ptr, False), "version": 3, "strides": None,
     }
     return torch.as_tensor(h, device=f"cuda:{device_index}")
 

@@ -23,7 +23,7 @@ cudaError_t launch_transpose_pdf(const float *src, float *dst, int nRows, int nb
 cudaError_t launch_check_monotone(const float *pdfT, int nRows, int nb, int *bad, cudaStream_t s);
 cudaError_t launch_fold_j(unsigned long long *Q, float *J, const float *dV, int nRows, size_t total,
                           double lenUnit, float deltaE, int blocks, cudaStream_t s);
-cudaError_t launch_fold_count(unsigned long long *Q, float *E, size_t total, float deltaE, int blocks,
+cudaError_t launch_fold_count(unsigned int *Q, float *E, size_t total, float deltaE, int blocks,
                               cudaStream_t s);
 struct PacketRec;
 struct PacketRecX;
@@ -111,7 +111,8 @@ struct GridState {
     DevBuf<int> active;
     DevBuf<float> opacity, scaOpac, absOpac, pdfT, totalLines, linePDF, dV, stage;
     DevBuf<unsigned char> canScatter;
-    DevBuf<unsigned long long> JsteQ, JdifQ, escQ, lineQ;
+    DevBuf<unsigned long long> JsteQ, JdifQ;
+    DevBuf<unsigned int> escQ, lineQ;
     DevBuf<float> Jste, Jdif, esc, linePk;
     bool haveOpacity = false, havePdf = false;
 };
@@ -369,6 +370,7 @@ int run_transport(mcb200_ctx *ctx, int iStar, int difGrid, const int32_t *cellLo
     if (!ctx->haveSpectra || !ctx->haveStars) return fail(ctx, MCB200_ESTATE, "spectra/stars not set");
     if (cfg.nAngleBins > 0 && !ctx->haveView) return fail(ctx, MCB200_ESTATE, "viewpoints not set");
     if (nGlobal < 0) return fail(ctx, MCB200_EINVAL, "negative packet count");
+    if (nGlobal >= ((int64_t)1 << 32)) return fail(ctx, MCB200_EINVAL, "more than 2^32 packets in one call (packet counts are 32-bit): split the call");
     if (iStar < 0 || iStar > cfg.nStars) return fail(ctx, MCB200_EINVAL, "iStar out of range");
     for (int i = 0; i < cfg.nGrids; ++i) {
         GridState &g = ctx->grids[i];
@@ -871,10 +873,15 @@ int mcb200_tally_buffer(mcb200_ctx *ctx, int32_t iG, int32_t which, void **devPt
     int rc = ensure_estimators(ctx, *g);
     if (rc) return rc;
     CU(cudaStreamSynchronize(ctx->stream));
-    DevBuf<unsigned long long> *b = which == 0 ? &g->JsteQ : which == 1 ? &g->escQ : which == 2 ? &g->JdifQ : which == 3 ? &g->lineQ : nullptr;
-    if (!b) return fail(ctx, MCB200_EINVAL, "bad tally selector %d", which);
-    *devPtr = b->p;
-    *count = (int64_t)b->n;
+    if (which == 0 || which == 2) {
+        DevBuf<unsigned long long> *b = which == 0 ? &g->JsteQ : &g->JdifQ;
+        *devPtr = b->p; *count = (int64_t)b->n;
+    } else if (which == 1 || which == 3) {
+        DevBuf<unsigned int> *b = which == 1 ? &g->escQ : &g->lineQ;
+        *devPtr = b->p; *count = (int64_t)b->n;
+    } else {
+        return fail(ctx, MCB200_EINVAL, "bad tally selector %d", which);
+    }
     return MCB200_OK;
 }
 
@@ -915,9 +922,15 @@ int mcb200_fetch_tallies(mcb200_ctx *ctx, int32_t iG, int64_t *JsteQ, int64_t *e
     if (rc) return rc;
     CU(cudaStreamSynchronize(ctx->stream));
     if (JsteQ) CU(cudaMemcpy(JsteQ, g->JsteQ.p, g->JsteQ.n * 8, cudaMemcpyDeviceToHost));
-    if (escapedQ) CU(cudaMemcpy(escapedQ, g->escQ.p, g->escQ.n * 8, cudaMemcpyDeviceToHost));
+    auto widen = [&](DevBuf<unsigned int> &b, int64_t *dst) -> cudaError_t {
+        std::vector<unsigned int> tmp(b.n);
+        cudaError_t e = cudaMemcpy(tmp.data(), b.p, b.n * sizeof(unsigned int), cudaMemcpyDeviceToHost);
+        for (size_t i = 0; i < b.n; ++i) dst[i] = (int64_t)tmp[i];
+        return e;
+    };
+    if (escapedQ) CU(widen(g->escQ, escapedQ));
     if (JdifQ && g->JdifQ.p) CU(cudaMemcpy(JdifQ, g->JdifQ.p, g->JdifQ.n * 8, cudaMemcpyDeviceToHost));
-    if (linePacketsQ && g->lineQ.p) CU(cudaMemcpy(linePacketsQ, g->lineQ.p, g->lineQ.n * 8, cudaMemcpyDeviceToHost));
+    if (linePacketsQ && g->lineQ.p) CU(widen(g->lineQ, linePacketsQ));
     return MCB200_OK;
 }
 

@@ -61,7 +61,7 @@ cudaError_t launch_check_monotone(const float *pdfT, int nRows, int nb, int *bad
 //   Jste(c,nu) += float(Q * lenUnit) * deltaE / dV(c)      (photon_mod.f90:1563-1574)
 //   escapedPackets(c,nu,a) += float(count) * deltaE          (photon_mod.f90:414-462)
 // One thread per element, each element touched by exactly one thread -> deterministic.
-// HBM-bound: 8 B (Q) read + 8 B (Q clear) + 4 B read + 4 B write per element.
+// HBM-bound: J: 8 B (Q) read + 4 B read; counts: 4 B (Q) read + 4 B read; writes only where Q != 0.
 // ---------------------------------------------------------------------------------------
 __global__ void fold_j_kernel(unsigned long long *__restrict__ Q, float *__restrict__ J,
                               const float *__restrict__ dV, int nRows, size_t total,
@@ -80,16 +80,16 @@ __global__ void fold_j_kernel(unsigned long long *__restrict__ Q, float *__restr
     }
 }
 
-__global__ void fold_count_kernel(unsigned long long *__restrict__ Q, float *__restrict__ E,
+__global__ void fold_count_kernel(unsigned int *__restrict__ Q, float *__restrict__ E,
                                   size_t total, float deltaE)
 {
     size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     size_t stride = (size_t)gridDim.x * blockDim.x;
     for (; i < total; i += stride) {
-        unsigned long long q = Q[i];
-        if (q != 0ull) {
+        unsigned int q = Q[i];
+        if (q != 0u) {
             E[i] = E[i] + (float)q * deltaE;
-            Q[i] = 0ull;
+            Q[i] = 0u;
         }
     }
 }
@@ -101,7 +101,7 @@ cudaError_t launch_fold_j(unsigned long long *Q, float *J, const float *dV, int 
     return cudaGetLastError();
 }
 
-cudaError_t launch_fold_count(unsigned long long *Q, float *E, size_t total, float deltaE, int blocks,
+cudaError_t launch_fold_count(unsigned int *Q, float *E, size_t total, float deltaE, int blocks,
                               cudaStream_t s)
 {
     fold_count_kernel<<<blocks, 256, 0, s>>>(Q, E, total, deltaE);

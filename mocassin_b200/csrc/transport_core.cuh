@@ -229,17 +229,17 @@ struct Transport {
         if (P.nAngleBins > 0) {
             int vt = __ldg(&P.vpPtheta[idirT]), vp = __ldg(&P.vpPphi[idirP]);
             if (vt > 0 && __ldg(&P.vpPhi[vt]) < 0.f) {
-                atomicAdd(&g.escQ[base + plane * vt], 1ull);
-                atomicAdd(&g.escQ[base], 1ull);
+                atomicAdd(&g.escQ[base + plane * vt], 1u);
+                atomicAdd(&g.escQ[base], 1u);
             } else if (vt == vp || __ldg(&P.vpTheta[vp]) == __ldg(&P.vpTheta[vt]) ||
                        __ldg(&P.vpPhi[vt]) == __ldg(&P.vpPhi[vp])) {
-                atomicAdd(&g.escQ[base + plane * vt], 1ull);
-                if (vt != 0) atomicAdd(&g.escQ[base], 1ull);
+                atomicAdd(&g.escQ[base + plane * vt], 1u);
+                if (vt != 0) atomicAdd(&g.escQ[base], 1u);
             } else {
-                atomicAdd(&g.escQ[base], 1ull);
+                atomicAdd(&g.escQ[base], 1u);
             }
         } else {
-            atomicAdd(&g.escQ[base], 1ull);
+            atomicAdd(&g.escQ[base], 1u);
         }
         count(C_ESCAPED);
         if (L.pendFate == FATE_EARLY) count(C_EARLY);
@@ -341,7 +341,7 @@ struct Transport {
                     int nuL = 0;
                     if (P.lgDebug) {
                         nuL = sample_cdf_strided(L.rng, g.linePDF + cell, (size_t)(g.nCells + 1), P.nLines);
-                        atomicAdd(&g.lineQ[(size_t)(nuL - 1) * (size_t)(g.nCells + 1) + (size_t)cell], 1ull);
+                        atomicAdd(&g.lineQ[(size_t)(nuL - 1) * (size_t)(g.nCells + 1) + (size_t)cell], 1u);
                     }
                     L.lastNuP = nuL;
                     count(C_LINE);

@@ -13,8 +13,8 @@ namespace mcb {
 //   xWall[i] i=0..nx: W[0]=x(1), W[i]=(x(i+1)+x(i))/2, W[nx]=x(nx)  -- the mid-point cell
 //            walls of photon_mod.f90:1263-1295 precomputed with the same float32 expression
 //   JsteQ/JdifQ  uint64 [(nu-1)*(nCells+1) + cell]  fixed-point path length (2^-e cm units)
-//   escQ     uint64 [cell + (nCells+1)*(nu + (nbins+1)*ang)] escaped packet counts
-//   lineQ    uint64 [(line-1)*(nCells+1) + cell]    line packet counts (debug)
+//   escQ     uint32 [cell + (nCells+1)*(nu + (nbins+1)*ang)] escaped packet counts
+//   lineQ    uint32 [(line-1)*(nCells+1) + cell]    line packet counts (debug)
 struct DevGrid {
     int nx, ny, nz, nCells, motherP;
     int dense;                       // 1: every cell active, id = 1 + (z-1) + nz*((y-1) + ny*(x-1))
@@ -32,7 +32,8 @@ struct DevGrid {
     const float *totalLines;
     const float *linePDF;            // reference layout, debug only
     const unsigned char *canScatter; // per cell: an unsublimated species exists (photon_mod.f90:1722-1748)
-    unsigned long long *JsteQ, *JdifQ, *escQ, *lineQ;
+    unsigned long long *JsteQ, *JdifQ;
+    unsigned int *escQ, *lineQ;      // packet counts: < 2^32 per rank and call
 };
 
 struct DevParams {
