@@ -36,13 +36,16 @@ struct Lane {
     int istep, gen;
     unsigned int segs;
     int lastNuP, fate, pendFate;
+    unsigned long long planeBase;   // (nuP-1)*(nCells+1) of grid planeG: index of the packet's nu-plane
+    int planeG;                     // grid the cached planeBase belongs to (0 = none)
     long long k;
     int phase;
 };
 
+template <bool DENSE = false>
 __device__ __forceinline__ int active_at(const DevGrid &g, int x, int y, int z)
 {
-    if (g.dense) return 1 + (z - 1) + g.nz * ((y - 1) + g.ny * (x - 1));
+    if (DENSE || g.dense) return 1 + (z - 1) + g.nz * ((y - 1) + g.ny * (x - 1));
     // nx*ny*nz < 2^31 (checked at upload): 32-bit index arithmetic
     return __ldg(&g.active[(x - 1) + g.nx * ((y - 1) + g.ny * (z - 1))]);
 }
@@ -164,7 +167,7 @@ __device__ __forceinline__ int hg(const DevParams &P, Lane &L)
     return 1;
 }
 
-template <bool MULTI>
+template <bool MULTI, bool DENSE = false>
 struct Transport {
     const TransportArgs &a;
     unsigned int *cnt;                   // per-thread event counters in shared memory
@@ -284,7 +287,7 @@ struct Transport {
         const DevParams &P = a.P;
         L.k = k;
         L.rng.init(a.seed, (unsigned long long)(a.firstId + k), (uint32_t)a.iStar);
-        L.segs = 0; L.gen = 0; L.fate = 0; L.lastNuP = 0;
+        L.segs = 0; L.gen = 0; L.fate = 0; L.lastNuP = 0; L.planeG = 0;
         L.mx = L.my = L.mz = -1;
         L.sx = L.sy = L.sz = -1;
         if (a.iStar >= 1) {
@@ -358,6 +361,7 @@ struct Transport {
         new_direction(P, L, stellar);
         L.orgG = L.gP; L.orgC = cell;
         L.nuP = nuP;
+        L.planeG = 0;
         float nu = __ldg(&P.nuArray[nuP - 1]);
         if (stellar && nu > 1.f) atomicAdd(&qph[nuP - 1], 1u);     // Qphot, :859-861
         if (!P.lgDust && nu < P.ionEdge1) {                         // :370-465
@@ -492,13 +496,18 @@ struct Transport {
             wall(g.zWall, g.nz, L.vz, L.rz, L.zP, L.gP, dSz, drop, posz);
             if (drop) { finish(L, FATE_DROPPED); return; }
             if ((dSx != dSx) | (dSy != dSy) | (dSz != dSz)) { fail(L, 60); return; }
-            cell = active_at(g, L.xP, L.yP, L.zP);
+            cell = active_at<DENSE>(g, L.xP, L.yP, L.zP);
             if (!MULTI || cell >= 0) break;
             if (j >= kSafeLimit) { fail(L, 63); return; }
         }
         const DevGrid &g = G(L.gP);
-        // one IMAD.WIDE: 32 x 32 -> 64 bit
-        size_t tix = (size_t)((unsigned long long)(unsigned int)(L.nuP - 1) * (unsigned int)(g.nCells + 1)) + (size_t)(unsigned int)cell;
+        // index of (cell, nuP) in the (0:nCells, nbins) tables: the nu-plane offset is constant
+        // during a flight inside one grid and cached in the lane
+        if (L.planeG != L.gP) {
+            L.planeBase = (unsigned long long)(unsigned int)(L.nuP - 1) * (unsigned int)(g.nCells + 1);
+            L.planeG = L.gP;
+        }
+        size_t tix = (size_t)L.planeBase + (size_t)(unsigned int)cell;
         float opac = __ldg(&g.opacity[tix]);
 
         // cells on a wall (:1395-1397): the axis end coordinate replaces a zero distance

@@ -121,7 +121,7 @@ __device__ __forceinline__ void rec_load(const TransportArgs &t, const PacketRec
     L.lastNuP = r.nuP;                       // a stored packet's last emission is its current nu
     L.xP = r.xP; L.yP = r.yP; L.zP = r.zP;
     L.orgG = r.orgG; L.orgC = r.orgC;
-    L.fate = 0; L.pendFate = FATE_ESCAPED;
+    L.fate = 0; L.pendFate = FATE_ESCAPED; L.planeG = 0;
     if (MULTI) {
         PacketRecX x;
         *reinterpret_cast<uint4 *>(&x) = *reinterpret_cast<const uint4 *>(&recx[pos]);
@@ -205,12 +205,12 @@ __global__ void __launch_bounds__(kThreads) wf_event_kernel(const __grid_constan
 // atomic per chunk, records of the chunk prefetched into L2) and cross cells until the next
 // event; ended flights are written back in place and their positions staged per warp in
 // shared memory, flushed 32 at a time (one global atomic per 32 events, coalesced stores).
-template <bool MULTI>
+template <bool MULTI, bool DENSE>
 __global__ void __launch_bounds__(kThreads, 4) wf_fly_kernel(const __grid_constant__ WfArgs w)
 {
     extern __shared__ unsigned int smem[];
     scratch_init(smem, w.t.P.nbins);
-    Transport<MULTI> T(w.t, smem, smem + C_COUNT * kThreads);
+    Transport<MULTI, DENSE> T(w.t, smem, smem + C_COUNT * kThreads);
     unsigned int *stage = smem + C_COUNT * kThreads + w.t.P.nbins + (threadIdx.x >> 5) * (EV_COUNT * kStage);
     const unsigned int FULL = 0xffffffffu;
     const unsigned int lane = threadIdx.x & 31u;
@@ -388,25 +388,28 @@ cudaError_t wf_launch_event(const WfArgs &w, bool multi, int ev, int blocks, cud
 
 static size_t fly_smem(int nbins) { return scratch_bytes(nbins) + (size_t)(kThreads / 32) * EV_COUNT * kStage * sizeof(unsigned int); }
 
-cudaError_t wf_launch_fly(const WfArgs &w, bool multi, int blocks, cudaStream_t s)
+template <bool MULTI, bool DENSE>
+static cudaError_t launch_fly_t(const WfArgs &w, int blocks, cudaStream_t s)
 {
     size_t smem = fly_smem(w.t.P.nbins);
-    if (multi) {
-        cudaFuncSetAttribute(wf_fly_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        wf_fly_kernel<true><<<blocks, kThreads, smem, s>>>(w);
-    } else {
-        cudaFuncSetAttribute(wf_fly_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        wf_fly_kernel<false><<<blocks, kThreads, smem, s>>>(w);
-    }
+    cudaFuncSetAttribute(wf_fly_kernel<MULTI, DENSE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    wf_fly_kernel<MULTI, DENSE><<<blocks, kThreads, smem, s>>>(w);
     return cudaGetLastError();
+}
+
+cudaError_t wf_launch_fly(const WfArgs &w, bool multi, int blocks, cudaStream_t s)
+{
+    if (multi) return launch_fly_t<true, false>(w, blocks, s);
+    if (w.t.g1.dense) return launch_fly_t<false, true>(w, blocks, s);
+    return launch_fly_t<false, false>(w, blocks, s);
 }
 
 int wf_fly_blocks_per_sm(bool multi)
 {
     int nb = 0;
     size_t smem = fly_smem(1024);
-    if (multi) cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, wf_fly_kernel<true>, kThreads, smem);
-    else       cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, wf_fly_kernel<false>, kThreads, smem);
+    if (multi) cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, wf_fly_kernel<true, false>, kThreads, smem);
+    else       cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, wf_fly_kernel<false, false>, kThreads, smem);
     return nb;
 }
 
