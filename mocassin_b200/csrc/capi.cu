@@ -15,7 +15,7 @@
 #include <vector>
 
 namespace mcb {
-cudaError_t launch_transport(const TransportArgs &a, bool multi, int gridBlocks, cudaStream_t stream);
+cudaError_t launch_transport(const TransportArgs &a, bool multi, int gridBlocks, cudaStream_t stream, const WfArgs *resume);
 int transport_blocks_per_sm(bool multi);
 cudaError_t launch_order(const TransportArgs &a, unsigned short *key, unsigned int *hist, unsigned int *cursor,
                          unsigned int *order, int numSMs, cudaStream_t stream);
@@ -25,22 +25,6 @@ cudaError_t launch_fold_j(unsigned long long *Q, float *J, const float *dV, int 
                           double lenUnit, float deltaE, int blocks, cudaStream_t s);
 cudaError_t launch_fold_count(unsigned int *Q, float *E, size_t total, float deltaE, int blocks,
                               cudaStream_t s);
-struct PacketRec;
-struct PacketRecX;
-struct WfArgs {
-    TransportArgs t;
-    PacketRec *recA, *recB;
-    PacketRecX *recxA, *recxB;
-    const unsigned int *inList;
-    const unsigned int *inCount;
-    unsigned short *flyKey;
-    unsigned int *flyCount;
-    unsigned int *evList[4];
-    unsigned int *evCount;
-    int stepBudget;
-    unsigned int *hist, *cursor;
-    unsigned long long *nextFlight;
-};
 cudaError_t wf_launch_event(const WfArgs &w, bool multi, int ev, int blocks, cudaStream_t s);
 cudaError_t wf_launch_fly(const WfArgs &w, bool multi, int blocks, cudaStream_t s);
 cudaError_t wf_launch_sort(const WfArgs &w, bool multi, int numSMs, cudaStream_t s);
@@ -149,6 +133,8 @@ struct mcb200_ctx {
     DevBuf<unsigned char> wfRecA, wfRecB, wfRecXA, wfRecXB;
     DevBuf<unsigned int> wfEv0, wfEv1, wfEv2, wfEv3, wfCounts, wfHist, wfCursor, wfSegs;
     int stepBudget = 96;
+    int64_t tailThreshold = 32768;        // alive packets below which the persistent kernel finishes the batch
+    DevBuf<unsigned char> wfArgsDev;
     DevBuf<unsigned short> wfFlyKey;
     DevBuf<unsigned long long> wfNext;
     int lastWaves = 0, lastLaunches = 0;
@@ -348,7 +334,21 @@ int run_wavefront(mcb200_ctx *ctx, const TransportArgs &a, bool multi, int64_t m
         unsigned int hc[5];
         CU(cudaMemcpyAsync(hc, ctx->wfCounts.p, sizeof(hc), cudaMemcpyDeviceToHost, s));
         CU(cudaStreamSynchronize(s));
-        if (hc[1] + hc[2] + hc[3] + hc[4] == 0) break;
+        uint64_t alive = (uint64_t)hc[1] + hc[2] + hc[3] + hc[4];
+        if (alive == 0) break;
+        if ((int64_t)alive <= ctx->tailThreshold) {
+            // thin tail: one persistent kernel carries the remaining packets to completion
+            CU(ctx->wfArgsDev.alloc(sizeof(WfArgs)));
+            CU(cudaMemcpyAsync(ctx->wfArgsDev.p, &w, sizeof(WfArgs), cudaMemcpyHostToDevice, s));
+            TransportArgs ta = w.t;
+            ta.n = (long long)alive; ta.order = nullptr; ta.batch = ctx->batch < 1 ? 1 : ctx->batch; ta.aggSteps = 0;
+            CU(ctx->nextPacket.zero(s));
+            int tb = (int)((alive + 255) / 256);
+            int cap = ctx->numSMs * 3;
+            CU(launch_transport(ta, multi, tb < cap ? tb : cap, s, reinterpret_cast<const WfArgs *>(ctx->wfArgsDev.p)));
+            ctx->lastLaunches++;
+            break;
+        }
         CU(cudaMemsetAsync(w.flyCount, 0, sizeof(unsigned int), s));
         for (int ev = 3; ev >= 0; --ev) {
             if (!hc[1 + ev]) continue;
@@ -464,7 +464,7 @@ int run_transport(mcb200_ctx *ctx, int iStar, int difGrid, const int32_t *cellLo
         int rcw = run_wavefront(ctx, a, multi, mine);
         if (rcw) return rcw;
     } else if (mine > 0) {
-        CU(launch_transport(a, multi, blocks, ctx->stream));
+        CU(launch_transport(a, multi, blocks, ctx->stream, nullptr));
     }
     CU(cudaEventRecord(ctx->ev1, ctx->stream));
     CU(cudaStreamSynchronize(ctx->stream));
@@ -969,6 +969,7 @@ int mcb200_set_option(mcb200_ctx *ctx, const char *name, int64_t value)
     if (!strcmp(name, "order")) { ctx->orderMode = (int)value; return MCB200_OK; }
     if (!strcmp(name, "wavefront")) { ctx->waveMode = (int)value; return MCB200_OK; }
     if (!strcmp(name, "step_budget")) { ctx->stepBudget = (int)value; return MCB200_OK; }
+    if (!strcmp(name, "tail")) { ctx->tailThreshold = value; return MCB200_OK; }
     if (!strcmp(name, "agg_steps")) { ctx->aggSteps = (int)value; return MCB200_OK; }
     if (!strcmp(name, "batch")) { ctx->batch = (int)value; return MCB200_OK; }
     return fail(ctx, MCB200_EINVAL, "unknown option %s", name);

@@ -31,12 +31,36 @@
 //  * float32 arithmetic with -fmad=false and the detmath.cuh transcendentals so that
 //    every branch decision is bit-identical to the CPU oracle.
 #include "transport_core.cuh"
+#include "wf_rec.cuh"
 
 namespace mcb {
 
+// Work source of the persistent kernel: fresh packets 0..n-1, or (resume != NULL) the packets
+// a wave-front run left alive, taken from its four event lists -- used to finish the long,
+// thin tail of a batch (a few packets with thousands of generations) without paying a
+// kernel-launch round trip per wave.
+template <bool MULTI>
+__device__ __forceinline__ void claim_packet(const TransportArgs &a, const WfArgs *resume, Transport<MULTI> &T,
+                                             Lane &L, long long k)
+{
+    if (!resume) {
+        T.start_packet(L, a.order ? (long long)__ldg(&a.order[k]) : k);
+        return;
+    }
+    unsigned int j = (unsigned int)k;
+    int ev = 0;
+    for (; ev < EV_COUNT - 1; ++ev) {
+        unsigned int c = resume->evCount[ev];
+        if (j < c) break;
+        j -= c;
+    }
+    rec_load<MULTI>(a, resume->recA, resume->recxA, L, resume->evList[ev][j]);
+    L.phase = ev == EV_EMIT ? PH_EMIT : ev == EV_SCATTER ? PH_SCATTER : ev == EV_ESCAPE ? PH_ESCAPE : PH_FLY;
+}
+
 template <bool MULTI>
 __global__ void __launch_bounds__(kThreads)
-transport_kernel(const __grid_constant__ TransportArgs a)
+transport_kernel(const __grid_constant__ TransportArgs a, const WfArgs *resume)
 {
     extern __shared__ unsigned int smem[];
     unsigned int *cnt = smem;                        // [C_COUNT][kThreads]
@@ -59,7 +83,7 @@ transport_kernel(const __grid_constant__ TransportArgs a)
             base = __shfl_sync(FULL, base, leader);
             if (L.phase == PH_NEED) {
                 long long k = (long long)(base + __popc(need & ((1u << lane) - 1u)));
-                if (k < a.n) T.start_packet(L, a.order ? (long long)__ldg(&a.order[k]) : k);
+                if (k < a.n) claim_packet<MULTI>(a, resume, T, L, k);
                 else L.phase = PH_DONE;
             }
         }
@@ -162,15 +186,15 @@ cudaError_t launch_order(const TransportArgs &a, unsigned short *key, unsigned i
     return cudaGetLastError();
 }
 
-cudaError_t launch_transport(const TransportArgs &a, bool multi, int gridBlocks, cudaStream_t stream)
+cudaError_t launch_transport(const TransportArgs &a, bool multi, int gridBlocks, cudaStream_t stream, const WfArgs *resume)
 {
     size_t smem = (size_t)(C_COUNT * kThreads + a.P.nbins) * sizeof(unsigned int);
     if (multi) {
         cudaFuncSetAttribute(transport_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        transport_kernel<true><<<gridBlocks, kThreads, smem, stream>>>(a);
+        transport_kernel<true><<<gridBlocks, kThreads, smem, stream>>>(a, resume);
     } else {
         cudaFuncSetAttribute(transport_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        transport_kernel<false><<<gridBlocks, kThreads, smem, stream>>>(a);
+        transport_kernel<false><<<gridBlocks, kThreads, smem, stream>>>(a, resume);
     }
     return cudaGetLastError();
 }

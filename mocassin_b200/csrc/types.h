@@ -73,4 +73,50 @@ struct TransportArgs {
     unsigned int *segsArr;           // wave-front + trace: segments of earlier flights per packet
 };
 
+// ---- wave-front pipeline (wavefront.cu) --------------------------------------------------
+enum { EV_EMIT = 0, EV_SCATTER = 1, EV_ESCAPE = 2, EV_CONT = 3, EV_COUNT = 4 };
+
+constexpr int kChunk = 32;               // flights a warp claims at a time (one atomic per chunk); small, so
+                                         // that all resident warps work inside a narrow window of the nu order
+constexpr int kStage = 64;               // per-warp staging slots per event list
+
+// One packet between two flights, 64 B = two 32 B sectors.
+struct alignas(16) PacketRec {
+    float rx, ry, rz, passProb;
+    float dx, dy, dz;
+    unsigned int rngn;
+    float absTau;                        // optical depth so far (non-zero only for continued flights)
+    unsigned int istepGen;               // istep (19 bits) | gen << 19 (13 bits)
+    unsigned int k;                      // packet index within the call
+    int orgC;
+    unsigned short nuP, gP;
+    unsigned short flagsLast;            // bits 0-1 chType, 2 lgStellar, 3 igpp, 4-6 vHat = -direction
+                                         // on x,y,z (mirror reflections only flip signs)
+    short xP, yP, zP;
+    unsigned short orgG, pad;
+};
+static_assert(sizeof(PacketRec) == 64, "PacketRec must be 64 bytes");
+struct alignas(16) PacketRecX {          // 16 B, multi-grid only: enPacket%xP(1:2) slots
+    short mx, my, mz, sx, sy, sz;
+    unsigned int pad;
+};
+
+// recB: flights in arrival order (written by the event kernels); recA: the same flights
+// moved into frequency order (read and updated in place by the FLY kernel).
+struct WfArgs {
+    TransportArgs t;
+    PacketRec *recA, *recB;
+    PacketRecX *recxA, *recxB;
+    const unsigned int *inList;          // event kernels: positions in recA (NULL: wave 0, packets 0..n-1)
+    const unsigned int *inCount;
+    unsigned short *flyKey;              // nu key of recB[i]
+    unsigned int *flyCount;              // entries in recB / recA
+    unsigned int *evList[EV_COUNT];      // positions in recA of flights that ended, per event
+    unsigned int *evCount;               // [EV_COUNT]
+    int stepBudget;                      // cell crossings per flight per wave (longer flights continue
+                                         // in the next wave, so one straggler cannot hold a wave open)
+    unsigned int *hist, *cursor;         // [nbins+1]
+    unsigned long long *nextFlight;      // FLY work counter
+};
+
 }  // namespace mcb

@@ -23,114 +23,9 @@
 // (two 32 B sectors per flight boundary).  Results are bit-identical to the persistent
 // kernel: tallies are order-independent integers and every packet owns its Philox stream.
 #include "transport_core.cuh"
+#include "wf_rec.cuh"
 
 namespace mcb {
-
-enum { EV_EMIT = 0, EV_SCATTER = 1, EV_ESCAPE = 2, EV_CONT = 3, EV_COUNT = 4 };
-
-constexpr int kChunk = 32;               // flights a warp claims at a time (one atomic per chunk); small, so
-                                         // that all resident warps work inside a narrow window of the nu order
-constexpr int kStage = 64;               // per-warp staging slots per event list
-
-// One packet between two flights, 64 B = two 32 B sectors.
-struct alignas(16) PacketRec {
-    float rx, ry, rz, passProb;
-    float dx, dy, dz;
-    unsigned int rngn;
-    float absTau;                        // optical depth so far (non-zero only for continued flights)
-    unsigned int istepGen;               // istep (19 bits) | gen << 19 (13 bits)
-    unsigned int k;                      // packet index within the call
-    int orgC;
-    unsigned short nuP, gP;
-    unsigned short flagsLast;            // bits 0-1 chType, 2 lgStellar, 3 igpp, 4-6 vHat = -direction
-                                         // on x,y,z (mirror reflections only flip signs)
-    short xP, yP, zP;
-    unsigned short orgG, pad;
-};
-static_assert(sizeof(PacketRec) == 64, "PacketRec must be 64 bytes");
-struct alignas(16) PacketRecX {          // 16 B, multi-grid only: enPacket%xP(1:2) slots
-    short mx, my, mz, sx, sy, sz;
-    unsigned int pad;
-};
-
-// recB: flights in arrival order (written by the event kernels); recA: the same flights
-// moved into frequency order (read and updated in place by the FLY kernel).
-struct WfArgs {
-    TransportArgs t;
-    PacketRec *recA, *recB;
-    PacketRecX *recxA, *recxB;
-    const unsigned int *inList;          // event kernels: positions in recA (NULL: wave 0, packets 0..n-1)
-    const unsigned int *inCount;
-    unsigned short *flyKey;              // nu key of recB[i]
-    unsigned int *flyCount;              // entries in recB / recA
-    unsigned int *evList[EV_COUNT];      // positions in recA of flights that ended, per event
-    unsigned int *evCount;               // [EV_COUNT]
-    int stepBudget;                      // cell crossings per flight per wave (longer flights continue
-                                         // in the next wave, so one straggler cannot hold a wave open)
-    unsigned int *hist, *cursor;         // [nbins+1]
-    unsigned long long *nextFlight;      // FLY work counter
-};
-
-template <bool MULTI>
-__device__ __forceinline__ void rec_store(PacketRec *rec, PacketRecX *recx, const Lane &L, unsigned int pos)
-{
-    PacketRec r;
-    r.rx = L.rx; r.ry = L.ry; r.rz = L.rz; r.passProb = L.passProb;
-    r.dx = L.dx; r.dy = L.dy; r.dz = L.dz;
-    r.rngn = L.rng.n;
-    r.absTau = L.absTau;
-    r.istepGen = ((unsigned int)L.istep & 0x7ffffu) | ((unsigned int)L.gen << 19);
-    r.k = (unsigned int)L.k;
-    r.orgC = L.orgC;
-    r.nuP = (unsigned short)L.nuP; r.gP = (unsigned short)L.gP;
-    r.flagsLast = (unsigned short)((L.chType & 3) | (L.lgStellar ? 4 : 0) | (L.igpp ? 8 : 0) |
-                                   (L.vx != L.dx ? 16 : 0) | (L.vy != L.dy ? 32 : 0) | (L.vz != L.dz ? 64 : 0));
-    r.xP = (short)L.xP; r.yP = (short)L.yP; r.zP = (short)L.zP;
-    r.orgG = (unsigned short)L.orgG; r.pad = 0;
-    const uint4 *src = reinterpret_cast<const uint4 *>(&r);
-    uint4 *dst = reinterpret_cast<uint4 *>(&rec[pos]);
-    dst[0] = src[0]; dst[1] = src[1]; dst[2] = src[2]; dst[3] = src[3];
-    if (MULTI) {
-        PacketRecX x;
-        x.mx = (short)L.mx; x.my = (short)L.my; x.mz = (short)L.mz;
-        x.sx = (short)L.sx; x.sy = (short)L.sy; x.sz = (short)L.sz; x.pad = 0;
-        *reinterpret_cast<uint4 *>(&recx[pos]) = *reinterpret_cast<const uint4 *>(&x);
-    }
-}
-
-template <bool MULTI>
-__device__ __forceinline__ void rec_load(const TransportArgs &t, const PacketRec *rec, const PacketRecX *recx,
-                                         Lane &L, unsigned int pos)
-{
-    PacketRec r;
-    const uint4 *src = reinterpret_cast<const uint4 *>(&rec[pos]);
-    uint4 *dst = reinterpret_cast<uint4 *>(&r);
-    dst[0] = src[0]; dst[1] = src[1]; dst[2] = src[2]; dst[3] = src[3];
-    L.k = (long long)r.k;
-    L.rng.init(t.seed, (unsigned long long)(t.firstId + (long long)r.k), (uint32_t)t.iStar, r.rngn);
-    L.rx = r.rx; L.ry = r.ry; L.rz = r.rz; L.passProb = r.passProb;
-    L.dx = r.dx; L.dy = r.dy; L.dz = r.dz;
-    // vHat = direction, except for the signs a mirror reflection flipped (continued flights)
-    L.vx = (r.flagsLast & 16) ? -r.dx : r.dx;
-    L.vy = (r.flagsLast & 32) ? -r.dy : r.dy;
-    L.vz = (r.flagsLast & 64) ? -r.dz : r.dz;
-    L.absTau = r.absTau;
-    L.segs = 0; L.istep = (int)(r.istepGen & 0x7ffffu); L.gen = (int)(r.istepGen >> 19);
-    L.nuP = r.nuP; L.gP = r.gP;
-    L.chType = r.flagsLast & 3; L.lgStellar = (r.flagsLast >> 2) & 1; L.igpp = (r.flagsLast >> 3) & 1;
-    L.lastNuP = r.nuP;                       // a stored packet's last emission is its current nu
-    L.xP = r.xP; L.yP = r.yP; L.zP = r.zP;
-    L.orgG = r.orgG; L.orgC = r.orgC;
-    L.fate = 0; L.pendFate = FATE_ESCAPED; L.planeG = 0;
-    if (MULTI) {
-        PacketRecX x;
-        *reinterpret_cast<uint4 *>(&x) = *reinterpret_cast<const uint4 *>(&recx[pos]);
-        L.mx = x.mx; L.my = x.my; L.mz = x.mz; L.sx = x.sx; L.sy = x.sy; L.sz = x.sz;
-    } else {
-        L.mx = L.xP; L.my = L.yP; L.mz = L.zP;       // single grid: the mother slot is the cell
-        L.sx = L.sy = L.sz = -1;
-    }
-}
 
 // append the lanes with `pred` to a list (one atomic per warp)
 __device__ __forceinline__ unsigned int warp_append(bool pred, unsigned int *count)
@@ -309,8 +204,14 @@ __global__ void wf_hist_kernel(const unsigned short *key, const unsigned int *co
     for (int i = threadIdx.x; i <= nb; i += blockDim.x) sh[i] = 0u;
     __syncthreads();
     const unsigned int n = *count;
-    for (unsigned int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x)
-        atomicAdd(&sh[key[i]], 1u);
+    const unsigned int stride = gridDim.x * blockDim.x;
+    for (unsigned int i0 = blockIdx.x * blockDim.x; i0 < n; i0 += stride) {
+        unsigned int i = i0 + threadIdx.x;
+        bool valid = i < n;
+        unsigned int b = valid ? key[i] : 0u;
+        unsigned int peers = __match_any_sync(0xffffffffu, valid ? b : 0xffffffffu);
+        if (valid && (int)(threadIdx.x & 31u) == __ffs(peers) - 1) atomicAdd(&sh[b], (unsigned int)__popc(peers));
+    }
     __syncthreads();
     for (int i = threadIdx.x; i <= nb; i += blockDim.x)
         if (sh[i]) atomicAdd(&hist[i], sh[i]);
@@ -329,6 +230,22 @@ __global__ void wf_scan_kernel(unsigned int *hist, unsigned int *cursor, int nb)
     }
 }
 
+// Keys arrive clustered (the event lists follow the previous wave's frequency order), so
+// plain shared-memory atomics would serialise on a handful of bins: lanes with equal keys
+// are aggregated first (MATCH.ANY), one shared atomic per distinct key per warp.
+__device__ __forceinline__ unsigned int smem_count_aggregated(unsigned int *cntb, unsigned int b, bool valid)
+{
+    const unsigned int FULL = 0xffffffffu;
+    unsigned int lane = threadIdx.x & 31u;
+    unsigned int peers = __match_any_sync(FULL, valid ? b : 0xffffffffu);
+    unsigned int rank = __popc(peers & ((1u << lane) - 1u));
+    int leader = __ffs(peers) - 1;
+    unsigned int base = 0;
+    if (valid && (int)lane == leader) base = atomicAdd(&cntb[b], (unsigned int)__popc(peers));
+    base = __shfl_sync(FULL, base, leader);
+    return base + rank;
+}
+
 template <bool MULTI>
 __global__ void wf_scatter_kernel(const WfArgs w, int nb)
 {
@@ -340,21 +257,30 @@ __global__ void wf_scatter_kernel(const WfArgs w, int nb)
         unsigned int c1 = c0 + chunk < n ? c0 + chunk : n;
         for (int i = threadIdx.x; i <= nb; i += blockDim.x) cntb[i] = 0u;
         __syncthreads();
-        for (unsigned int i = c0 + threadIdx.x; i < c1; i += blockDim.x) atomicAdd(&cntb[w.flyKey[i]], 1u);
+        for (unsigned int i0 = c0; i0 < c1; i0 += blockDim.x) {
+            unsigned int i = i0 + threadIdx.x;
+            bool valid = i < c1;
+            smem_count_aggregated(cntb, valid ? w.flyKey[i] : 0u, valid);
+        }
         __syncthreads();
         for (int i = threadIdx.x; i <= nb; i += blockDim.x) {
             base[i] = cntb[i] ? atomicAdd(&w.cursor[i], cntb[i]) : 0u;
             cntb[i] = 0u;
         }
         __syncthreads();
-        for (unsigned int i = c0 + threadIdx.x; i < c1; i += blockDim.x) {
-            unsigned int b = w.flyKey[i];
-            unsigned int dst = base[b] + atomicAdd(&cntb[b], 1u);
-            const uint4 *src = reinterpret_cast<const uint4 *>(&w.recB[i]);
-            uint4 *d = reinterpret_cast<uint4 *>(&w.recA[dst]);
-            uint4 v0 = src[0], v1 = src[1], v2 = src[2], v3 = src[3];
-            d[0] = v0; d[1] = v1; d[2] = v2; d[3] = v3;
-            if (MULTI) *reinterpret_cast<uint4 *>(&w.recxA[dst]) = *reinterpret_cast<const uint4 *>(&w.recxB[i]);
+        for (unsigned int i0 = c0; i0 < c1; i0 += blockDim.x) {
+            unsigned int i = i0 + threadIdx.x;
+            bool valid = i < c1;
+            unsigned int b = valid ? w.flyKey[i] : 0u;
+            unsigned int off = smem_count_aggregated(cntb, b, valid);
+            if (valid) {
+                unsigned int dst = base[b] + off;
+                const uint4 *src = reinterpret_cast<const uint4 *>(&w.recB[i]);
+                uint4 *d = reinterpret_cast<uint4 *>(&w.recA[dst]);
+                uint4 v0 = src[0], v1 = src[1], v2 = src[2], v3 = src[3];
+                d[0] = v0; d[1] = v1; d[2] = v2; d[3] = v3;
+                if (MULTI) *reinterpret_cast<uint4 *>(&w.recxA[dst]) = *reinterpret_cast<const uint4 *>(&w.recxB[i]);
+            }
         }
         __syncthreads();
     }
