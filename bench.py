@@ -395,6 +395,7 @@ def run_b200(args):
         "segments_per_packet": segs_all / (nGlobal * args.steps),
         "flights_per_packet": flights / (P * args.steps),
         "kernel_ms_per_step": kms_max / args.steps, "wall_ms_per_step": 1e3 * wall_max / args.steps,
+        "exchange_planes": getattr(eng, "last_exchange_planes", None),
     }
     print(json.dumps(line), flush=True)
     if world > 1:

@@ -196,7 +196,12 @@ int mcb200_transport_diffuse(mcb200_ctx *ctx, int32_t gpLoc, const int32_t *cell
  * the caller's communicator can sum them across ranks in place (NCCL allreduce, sum)
  * -- replaces MPI_ALLREDUCE at iteration_mod.f90:627,649,653,659.  which: 0 JsteQ,
  * 2 JdifQ (int64 fixed-point path lengths); 1 escapedQ, 3 linePacketsQ (uint32 packet
- * counts: the global packet count of one call must stay below 2^32). */
+ * counts: the global packet count of one call must stay below 2^32); 4 nuTouched
+ * (int32[nbins+1], 1 = a packet was emitted in that frequency bin since the last fold:
+ * only those nu-planes of the tallies can be non-zero, so an exchange may max-reduce the
+ * flags first and then sum only the flagged planes -- plane nu of JsteQ is the contiguous
+ * run [(nu-1)*(nCells+1), nu*(nCells+1)), plane (nu,ang) of escapedQ starts at
+ * (nCells+1)*(nu + (nbins+1)*ang)). */
 int mcb200_tally_buffer(mcb200_ctx *ctx, int32_t iG, int32_t which, void **devPtr, int64_t *count);
 /* After the allreduce: fold the (now global) integer tallies of the last transport
  * call into the float32 estimators. No-op when nothing is pending. */

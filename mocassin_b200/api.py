@@ -248,15 +248,34 @@ class PacketEngine:
             import torch
             import torch.distributed as dist
 
-            whichs = [0, 1] + ([2, 3] if self.model.lgDebug else [])
-            for iG in range(1, self.model.nGrids + 1):
-                for w in whichs:
+            m = self.model
+            dev = self._device_index()
+            for iG in range(1, m.nGrids + 1):
+                nR = m.grids[iG - 1].nCells + 1
+                # 1) which frequency bins were touched on any rank (tiny max-reduce)
+                fptr, fn = self.tally_buffer(iG, 4)
+                flags = _as_cuda_tensor(fptr, fn, "<i4", dev)
+                dist.all_reduce(flags, op=dist.ReduceOp.MAX, group=group)
+                ranges = _touched_ranges(flags.cpu().numpy())
+                self.last_exchange_planes = (sum(b - a + 1 for a, b in ranges), m.nbins + 1, len(ranges))
+                # 2) sum only those nu-planes: int64 path lengths, uint32 counts (as int32 bits)
+                for w in [0, 1] + ([2] if m.lgDebug else []):
                     ptr, n = self.tally_buffer(iG, w)
                     if n == 0:
                         continue
-                    # path lengths are int64; packet counts uint32 (summed as int32 bit patterns)
-                    t = _as_cuda_tensor(ptr, n, "<i8" if w in (0, 2) else "<i4", self._device_index())
-                    dist.all_reduce(t, op=dist.ReduceOp.SUM, group=group)
+                    t = _as_cuda_tensor(ptr, n, "<i8" if w in (0, 2) else "<i4", dev)
+                    for p0, p1 in ranges:
+                        if w == 1:
+                            for ang in range(m.nAngleBins + 1):
+                                off = nR * (p0 + (m.nbins + 1) * ang)
+                                dist.all_reduce(t[off:off + (p1 - p0 + 1) * nR], op=dist.ReduceOp.SUM, group=group)
+                        elif p1 >= max(p0, 1):
+                            q0 = max(p0, 1)
+                            dist.all_reduce(t[(q0 - 1) * nR:p1 * nR], op=dist.ReduceOp.SUM, group=group)
+                if m.lgDebug:
+                    ptr, n = self.tally_buffer(iG, 3)
+                    if n:
+                        dist.all_reduce(_as_cuda_tensor(ptr, n, "<i4", dev), op=dist.ReduceOp.SUM, group=group)
             torch.cuda.synchronize()
         self._check(self.lib.mcb200_reduce(self.h))
 
@@ -330,6 +349,20 @@ class PacketEngine:
         if self.nranks == 1:
             self.reduce()
         return out
+
+
+def _touched_ranges(flag) -> list:
+    """Contiguous runs [first,last] of touched frequency bins; gaps of <= 2 bins are bridged
+    (same rule as the fold in capi.cu)."""
+    out = []
+    for i, f in enumerate(flag):
+        if not f:
+            continue
+        if out and i - out[-1][1] <= 3:
+            out[-1][1] = i
+        else:
+            out.append([i, i])
+    return [(a, b) for a, b in out]
 
 
 def _as_cuda_tensor(ptr: int, n: int, typestr: str, device_index: int):

@@ -97,6 +97,7 @@ struct GridState {
     DevBuf<unsigned char> canScatter;
     DevBuf<unsigned long long> JsteQ, JdifQ;
     DevBuf<unsigned int> escQ, lineQ;
+    DevBuf<int> nuTouched;
     DevBuf<float> Jste, Jdif, esc, linePk;
     bool haveOpacity = false, havePdf = false;
 };
@@ -137,7 +138,7 @@ struct mcb200_ctx {
     DevBuf<unsigned char> wfArgsDev;
     DevBuf<unsigned short> wfFlyKey;
     DevBuf<unsigned long long> wfNext;
-    int lastWaves = 0, lastLaunches = 0;
+    int lastWaves = 0, lastLaunches = 0, lastFoldLaunches = 0;
     int aggSteps = 0, batch = 12;
     bool trace = false;
     int blocksPerSM = 0;                  // 0 = occupancy default
@@ -243,6 +244,7 @@ int sync_grids(mcb200_ctx *ctx)
         d.pdfT = g.pdfT.p; d.totalLines = g.totalLines.p; d.linePDF = g.linePDF.p;
         d.canScatter = g.canScatter.p;
         d.JsteQ = g.JsteQ.p; d.JdifQ = g.JdifQ.p; d.escQ = g.escQ.p; d.lineQ = g.lineQ.p;
+        d.nuTouched = g.nuTouched.p;
     }
     CU(ctx->dGrids.upload(ctx->hGrids.data(), nG, ctx->stream));
     CU(cudaStreamSynchronize(ctx->stream));
@@ -258,6 +260,7 @@ int ensure_estimators(mcb200_ctx *ctx, GridState &g)
     CU(g.JsteQ.alloc(ts)); CU(g.JsteQ.zero(ctx->stream));
     CU(g.Jste.alloc(ts));  CU(g.Jste.zero(ctx->stream));
     CU(g.escQ.alloc(es));  CU(g.escQ.zero(ctx->stream));
+    CU(g.nuTouched.alloc(ctx->cfg.nbins + 1)); CU(g.nuTouched.zero(ctx->stream));
     CU(g.esc.alloc(es));   CU(g.esc.zero(ctx->stream));
     if (ctx->cfg.lgDebug) {
         CU(g.JdifQ.alloc(ts)); CU(g.JdifQ.zero(ctx->stream));
@@ -270,22 +273,61 @@ int ensure_estimators(mcb200_ctx *ctx, GridState &g)
     return MCB200_OK;
 }
 
+// contiguous runs [first,last] of touched frequency bins (gaps of <= 2 bins are bridged)
+std::vector<std::pair<int, int>> touched_ranges(const std::vector<int> &flag)
+{
+    std::vector<std::pair<int, int>> r;
+    int n = (int)flag.size();
+    for (int i = 0; i < n; ++i) {
+        if (!flag[i]) continue;
+        if (!r.empty() && i - r.back().second <= 3) r.back().second = i;
+        else r.emplace_back(i, i);
+    }
+    return r;
+}
+
 int fold_pending(mcb200_ctx *ctx)
 {
     if (!ctx->pending) return MCB200_OK;
     int blocks = ctx->numSMs * 8;
+    const int nb = ctx->cfg.nbins;
+    int launches = 0;
     for (auto &g : ctx->grids) {
-        size_t ts = tsize(ctx, g), es = esize(ctx, g);
+        size_t nR = (size_t)g.nCells + 1;
         double lenUnit = std::ldexp(1.0, g.lenExp);
-        CU(launch_fold_j(g.JsteQ.p, g.Jste.p, g.dV.p, g.nCells + 1, ts, lenUnit, ctx->pendingDeltaE, blocks, ctx->stream));
-        CU(launch_fold_count(g.escQ.p, g.esc.p, es, ctx->pendingDeltaE, blocks, ctx->stream));
-        if (ctx->cfg.lgDebug) {
-            CU(launch_fold_j(g.JdifQ.p, g.Jdif.p, g.dV.p, g.nCells + 1, ts, lenUnit, ctx->pendingDeltaE, blocks, ctx->stream));
-            if (g.lineQ.n) CU(launch_fold_count(g.lineQ.p, g.linePk.p, g.lineQ.n, ctx->pendingDeltaE, blocks, ctx->stream));
+        // only nu-planes in which a packet was emitted can hold tallies
+        std::vector<int> flag(nb + 1, 1);
+        if (g.nuTouched.p) {
+            CU(cudaMemcpyAsync(flag.data(), g.nuTouched.p, sizeof(int) * (nb + 1), cudaMemcpyDeviceToHost, ctx->stream));
+            CU(cudaStreamSynchronize(ctx->stream));
         }
+        for (auto &rg : touched_ranges(flag)) {
+            int p0 = rg.first < 1 ? 1 : rg.first, p1 = rg.second;
+            if (p1 >= p0) {
+                size_t off = (size_t)(p0 - 1) * nR, len = (size_t)(p1 - p0 + 1) * nR;
+                CU(launch_fold_j(g.JsteQ.p + off, g.Jste.p + off, g.dV.p, (int)nR, len, lenUnit, ctx->pendingDeltaE, blocks, ctx->stream));
+                ++launches;
+                if (ctx->cfg.lgDebug) {
+                    CU(launch_fold_j(g.JdifQ.p + off, g.Jdif.p + off, g.dV.p, (int)nR, len, lenUnit, ctx->pendingDeltaE, blocks, ctx->stream));
+                    ++launches;
+                }
+            }
+            for (int ang = 0; ang <= ctx->cfg.nAngleBins; ++ang) {
+                size_t off = nR * ((size_t)rg.first + (size_t)(nb + 1) * (size_t)ang);
+                size_t len = (size_t)(rg.second - rg.first + 1) * nR;
+                CU(launch_fold_count(g.escQ.p + off, g.esc.p + off, len, ctx->pendingDeltaE, blocks, ctx->stream));
+                ++launches;
+            }
+        }
+        if (ctx->cfg.lgDebug && g.lineQ.n) {
+            CU(launch_fold_count(g.lineQ.p, g.linePk.p, g.lineQ.n, ctx->pendingDeltaE, blocks, ctx->stream));
+            ++launches;
+        }
+        if (g.nuTouched.p) CU(g.nuTouched.zero(ctx->stream));
     }
     CU(cudaStreamSynchronize(ctx->stream));
     ctx->pending = false;
+    ctx->lastFoldLaunches = launches;
     return MCB200_OK;
 }
 
@@ -502,7 +544,7 @@ int run_transport(mcb200_ctx *ctx, int iStar, int difGrid, const int32_t *cellLo
         CU(cudaEventSynchronize(ctx->ev2));
         float ms2 = 0.f;
         CU(cudaEventElapsedTime(&ms2, ctx->ev0, ctx->ev2));
-        if (out) { out->total_ms = ms2; out->nLaunches += 2 * (int64_t)ctx->grids.size() * (ctx->cfg.lgDebug ? 2 : 1); }
+        if (out) { out->total_ms = ms2; out->nLaunches += ctx->lastFoldLaunches; }
     }
     return MCB200_OK;
 }
@@ -845,6 +887,7 @@ int mcb200_zero_estimators(mcb200_ctx *ctx)
         CU(g.escQ.zero(ctx->stream));  CU(g.esc.zero(ctx->stream));
         CU(g.JdifQ.zero(ctx->stream)); CU(g.Jdif.zero(ctx->stream));
         CU(g.lineQ.zero(ctx->stream)); CU(g.linePk.zero(ctx->stream));
+        CU(g.nuTouched.zero(ctx->stream));
     }
     CU(cudaStreamSynchronize(ctx->stream));
     ctx->pending = false;
@@ -879,6 +922,8 @@ int mcb200_tally_buffer(mcb200_ctx *ctx, int32_t iG, int32_t which, void **devPt
     } else if (which == 1 || which == 3) {
         DevBuf<unsigned int> *b = which == 1 ? &g->escQ : &g->lineQ;
         *devPtr = b->p; *count = (int64_t)b->n;
+    } else if (which == 4) {
+        *devPtr = g->nuTouched.p; *count = (int64_t)g->nuTouched.n;
     } else {
         return fail(ctx, MCB200_EINVAL, "bad tally selector %d", which);
     }

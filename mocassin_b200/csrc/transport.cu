@@ -188,7 +188,7 @@ cudaError_t launch_order(const TransportArgs &a, unsigned short *key, unsigned i
 
 cudaError_t launch_transport(const TransportArgs &a, bool multi, int gridBlocks, cudaStream_t stream, const WfArgs *resume)
 {
-    size_t smem = (size_t)(C_COUNT * kThreads + a.P.nbins) * sizeof(unsigned int);
+    size_t smem = (size_t)scratch_words(a.P.nbins) * sizeof(unsigned int);
     if (multi) {
         cudaFuncSetAttribute(transport_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         transport_kernel<true><<<gridBlocks, kThreads, smem, stream>>>(a, resume);
@@ -202,7 +202,7 @@ cudaError_t launch_transport(const TransportArgs &a, bool multi, int gridBlocks,
 int transport_blocks_per_sm(bool multi)
 {
     int nb = 0;
-    size_t smem = (size_t)(C_COUNT * kThreads + 1024) * sizeof(unsigned int);
+    size_t smem = (size_t)scratch_words(1024) * sizeof(unsigned int);
     if (multi) cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, transport_kernel<true>, kThreads, smem);
     else       cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, transport_kernel<false>, kThreads, smem);
     return nb;

@@ -362,6 +362,7 @@ struct Transport {
         L.orgG = L.gP; L.orgC = cell;
         L.nuP = nuP;
         L.planeG = 0;
+        atomicOr(&qph[a.P.nbins + (nuP >> 5)], 1u << (nuP & 31));   // nu-plane touched (flushed per CTA)
         float nu = __ldg(&P.nuArray[nuP - 1]);
         if (stellar && nu > 1.f) atomicAdd(&qph[nuP - 1], 1u);     // Qphot, :859-861
         if (!P.lgDust && nu < P.ionEdge1) {                         // :370-465
@@ -741,9 +742,11 @@ struct Transport {
 
 
 // per-CTA shared-memory scratch: [C_COUNT][kThreads] event counters + [nbins] Qphot histogram
+// + [(nbins+32)/32] bitmap of the frequency bins packets were emitted in
+__host__ __device__ __forceinline__ int scratch_words(int nbins) { return C_COUNT * kThreads + nbins + (nbins + 32) / 32; }
 __device__ __forceinline__ void scratch_init(unsigned int *smem, int nbins)
 {
-    for (int i = threadIdx.x; i < C_COUNT * kThreads + nbins; i += kThreads) smem[i] = 0u;
+    for (int i = threadIdx.x; i < scratch_words(nbins); i += kThreads) smem[i] = 0u;
     __syncthreads();
 }
 __device__ __forceinline__ void scratch_flush(const TransportArgs &a, unsigned int *smem)
@@ -759,6 +762,14 @@ __device__ __forceinline__ void scratch_flush(const TransportArgs &a, unsigned i
     }
     for (int i = threadIdx.x; i < a.P.nbins; i += kThreads)
         if (qph[i]) atomicAdd(&a.qphotCounts[i], (unsigned long long)qph[i]);
+    // a packet tallies in whatever grid it flies through: flag the bin in every grid
+    const unsigned int *bits = qph + a.P.nbins;
+    for (int i = threadIdx.x; i <= a.P.nbins; i += kThreads) {
+        if (bits[i >> 5] & (1u << (i & 31))) {
+            if (a.P.nGrids == 1) a.g1.nuTouched[i] = 1;
+            else for (int g = 0; g < a.P.nGrids; ++g) a.grids[g].nuTouched[i] = 1;
+        }
+    }
 }
 
 }  // namespace mcb

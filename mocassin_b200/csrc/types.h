@@ -34,6 +34,8 @@ struct DevGrid {
     const unsigned char *canScatter; // per cell: an unsublimated species exists (photon_mod.f90:1722-1748)
     unsigned long long *JsteQ, *JdifQ;
     unsigned int *escQ, *lineQ;      // packet counts: < 2^32 per rank and call
+    int *nuTouched;                  // [nbins+1] 1 = some packet was emitted in this bin since the last fold:
+                                     // only those nu-planes of JsteQ/escQ can be non-zero (exchange + fold skip the rest)
 };
 
 struct DevParams {

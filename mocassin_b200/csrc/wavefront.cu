@@ -106,7 +106,7 @@ __global__ void __launch_bounds__(kThreads, 4) wf_fly_kernel(const __grid_consta
     extern __shared__ unsigned int smem[];
     scratch_init(smem, w.t.P.nbins);
     Transport<MULTI, DENSE> T(w.t, smem, smem + C_COUNT * kThreads);
-    unsigned int *stage = smem + C_COUNT * kThreads + w.t.P.nbins + (threadIdx.x >> 5) * (EV_COUNT * kStage);
+    unsigned int *stage = smem + scratch_words(w.t.P.nbins) + (threadIdx.x >> 5) * (EV_COUNT * kStage);
     const unsigned int FULL = 0xffffffffu;
     const unsigned int lane = threadIdx.x & 31u;
     const unsigned int total = *w.flyCount;
@@ -287,7 +287,7 @@ __global__ void wf_scatter_kernel(const WfArgs w, int nb)
 }
 
 // ---- host-side launchers -------------------------------------------------------------------
-static size_t scratch_bytes(int nbins) { return (size_t)(C_COUNT * kThreads + nbins) * sizeof(unsigned int); }
+static size_t scratch_bytes(int nbins) { return (size_t)scratch_words(nbins) * sizeof(unsigned int); }
 
 template <bool MULTI, int EV>
 static cudaError_t launch_event_t(const WfArgs &w, int blocks, cudaStream_t s)
