@@ -160,7 +160,10 @@ int mcb200_get_opacity(mcb200_ctx *ctx, int32_t iG, float *opacity, float *scaOp
 /* Re-emission tables of grid iG built by emissionDriver (iteration_mod.f90:279-424):
  * recPDF or dustPDF (0:nCells,nbins), totalLines(0:nCells) (NULL for dust-only),
  * linePDF (0:nCells,nLines) (debug only, else NULL).  Tables must be non-decreasing
- * along nu (they are cumulative sums); MCB200_ETABLE otherwise. */
+ * along nu (they are cumulative sums); MCB200_ETABLE otherwise.  With option
+ * "async_pdfs"=1 the call only enqueues upload+transpose on a copy stream (the buffers must
+ * stay valid, ideally pinned, until the next transport call returns): the upload then
+ * overlaps the stellar wave and MCB200_ETABLE is reported by that transport call. */
 int mcb200_set_pdfs(mcb200_ctx *ctx, int32_t iG, const float *recPDF, const float *dustPDF,
                     const float *totalLines, const float *linePDF);
 

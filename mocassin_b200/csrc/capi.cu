@@ -108,6 +108,10 @@ struct mcb200_ctx {
     int device = 0, rank = 0, nranks = 1;
     uint64_t seed = 0;
     cudaStream_t stream = nullptr;
+    cudaStream_t copyStream = nullptr;    // async PDF upload (option async_pdfs): overlaps wave 0
+    cudaEvent_t pdfReady = nullptr;
+    bool asyncPdfs = false, pdfPending = false;
+    DevBuf<int> pdfBad;                   // deferred monotonicity verdicts, one per grid
     int numSMs = 0;
     bool haveCfg = false;
     mcb200_config cfg{};
@@ -379,6 +383,7 @@ int run_wavefront(mcb200_ctx *ctx, const TransportArgs &a, bool multi, int64_t m
         uint64_t alive = (uint64_t)hc[1] + hc[2] + hc[3] + hc[4];
         if (alive == 0) break;
         if ((int64_t)alive <= ctx->tailThreshold) {
+            if (ctx->pdfPending) CU(cudaStreamWaitEvent(s, ctx->pdfReady, 0));
             // thin tail: one persistent kernel carries the remaining packets to completion
             CU(ctx->wfArgsDev.alloc(sizeof(WfArgs)));
             CU(cudaMemcpyAsync(ctx->wfArgsDev.p, &w, sizeof(WfArgs), cudaMemcpyHostToDevice, s));
@@ -392,6 +397,7 @@ int run_wavefront(mcb200_ctx *ctx, const TransportArgs &a, bool multi, int64_t m
             break;
         }
         CU(cudaMemsetAsync(w.flyCount, 0, sizeof(unsigned int), s));
+        if (ctx->pdfPending) CU(cudaStreamWaitEvent(s, ctx->pdfReady, 0));   // re-emission needs the PDFs now
         for (int ev = 3; ev >= 0; --ev) {
             if (!hc[1 + ev]) continue;
             w.inList = w.evList[ev]; w.inCount = &w.evCount[ev];
@@ -506,6 +512,7 @@ int run_transport(mcb200_ctx *ctx, int iStar, int difGrid, const int32_t *cellLo
         int rcw = run_wavefront(ctx, a, multi, mine);
         if (rcw) return rcw;
     } else if (mine > 0) {
+        if (ctx->pdfPending) CU(cudaStreamWaitEvent(ctx->stream, ctx->pdfReady, 0));
         CU(launch_transport(a, multi, blocks, ctx->stream, nullptr));
     }
     CU(cudaEventRecord(ctx->ev1, ctx->stream));
@@ -513,6 +520,14 @@ int run_transport(mcb200_ctx *ctx, int iStar, int difGrid, const int32_t *cellLo
     float ms = 0.f;
     CU(cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev1));
 
+    if (ctx->pdfPending) {                                // deferred verdict of the async PDF upload
+        CU(cudaStreamSynchronize(ctx->copyStream));
+        std::vector<int> bad(cfg.nGrids, 0);
+        CU(cudaMemcpy(bad.data(), ctx->pdfBad.p, sizeof(int) * cfg.nGrids, cudaMemcpyDeviceToHost));
+        ctx->pdfPending = false;
+        for (int i = 0; i < cfg.nGrids; ++i)
+            if (bad[i]) { ctx->grids[i].havePdf = false; return fail(ctx, MCB200_ETABLE, "grid %d: re-emission PDF is not non-decreasing along nu", i + 1); }
+    }
     unsigned long long hc[C_COUNT];
     int herr = 0;
     CU(cudaMemcpy(hc, ctx->counters.p, sizeof(hc), cudaMemcpyDeviceToHost));
@@ -593,6 +608,8 @@ int mcb200_create(mcb200_ctx **pctx, int32_t device, int32_t rank, int32_t nrank
     cudaEventCreate(&ctx->ev0);
     cudaEventCreate(&ctx->ev1);
     cudaEventCreate(&ctx->ev2);
+    cudaStreamCreateWithFlags(&ctx->copyStream, cudaStreamNonBlocking);
+    cudaEventCreateWithFlags(&ctx->pdfReady, cudaEventDisableTiming);
     *pctx = ctx;
     return MCB200_OK;
 }
@@ -605,6 +622,8 @@ int mcb200_destroy(mcb200_ctx *ctx)
     if (ctx->ev0) cudaEventDestroy(ctx->ev0);
     if (ctx->ev1) cudaEventDestroy(ctx->ev1);
     if (ctx->ev2) cudaEventDestroy(ctx->ev2);
+    if (ctx->pdfReady) cudaEventDestroy(ctx->pdfReady);
+    if (ctx->copyStream) { cudaStreamSynchronize(ctx->copyStream); cudaStreamDestroy(ctx->copyStream); }
     ctx->grids.clear();
     cudaStream_t s = ctx->stream;
     delete ctx;
@@ -822,6 +841,35 @@ int mcb200_set_pdfs(mcb200_ctx *ctx, int32_t iG, const float *recPDF, const floa
     size_t ts = tsize(ctx, *g);
     int nRows = g->nCells + 1;
     bool re = (g->pdfT.n != ts);
+    if (ctx->asyncPdfs) {
+        // Enqueue upload + transpose + check on the copy stream and return: the tables are
+        // first needed by the re-emissions of wave 1, so the (PCIe-bound) upload overlaps the
+        // stellar wave.  The caller's buffer must stay valid (and should be pinned) until the
+        // next transport call returns; the monotonicity verdict is reported by that call.
+        cudaStream_t cs = ctx->copyStream;
+        // small (possibly pageable -> synchronous) tables first, on the main stream
+        if (c.lgGas) {
+            if (g->totalLines.n != (size_t)nRows) re = true;
+            CU(g->totalLines.upload(totalLines, nRows, ctx->stream));
+        }
+        if (c.lgDebug && c.lgGas) {
+            if (g->linePDF.n != lsize(ctx, *g)) re = true;
+            CU(g->linePDF.upload(linePDF, lsize(ctx, *g), ctx->stream));
+        }
+        CU(cudaStreamSynchronize(ctx->stream));          // earlier users of pdfT are done
+        CU(ctx->pdfBad.alloc(c.nGrids));
+        if (!ctx->pdfPending) CU(ctx->pdfBad.zero(cs));
+        CU(g->stage.alloc(ts));
+        CU(g->pdfT.alloc(ts));
+        CU(cudaMemcpyAsync(g->stage.p, src, ts * sizeof(float), cudaMemcpyHostToDevice, cs));
+        CU(launch_transpose_pdf(g->stage.p, g->pdfT.p, nRows, c.nbins, cs));
+        CU(launch_check_monotone(g->pdfT.p, nRows, c.nbins, ctx->pdfBad.p + (iG - 1), cs));
+        CU(cudaEventRecord(ctx->pdfReady, cs));
+        ctx->pdfPending = true;
+        g->havePdf = true;
+        if (re) ctx->gridsDirty = true;
+        return MCB200_OK;
+    }
     CU(g->stage.upload(src, ts, ctx->stream));
     CU(g->pdfT.alloc(ts));
     CU(launch_transpose_pdf(g->stage.p, g->pdfT.p, nRows, c.nbins, ctx->stream));
@@ -1015,6 +1063,7 @@ int mcb200_set_option(mcb200_ctx *ctx, const char *name, int64_t value)
     if (!strcmp(name, "wavefront")) { ctx->waveMode = (int)value; return MCB200_OK; }
     if (!strcmp(name, "step_budget")) { ctx->stepBudget = (int)value; return MCB200_OK; }
     if (!strcmp(name, "tail")) { ctx->tailThreshold = value; return MCB200_OK; }
+    if (!strcmp(name, "async_pdfs")) { ctx->asyncPdfs = value != 0; return MCB200_OK; }
     if (!strcmp(name, "agg_steps")) { ctx->aggSteps = (int)value; return MCB200_OK; }
     if (!strcmp(name, "batch")) { ctx->batch = (int)value; return MCB200_OK; }
     return fail(ctx, MCB200_EINVAL, "unknown option %s", name);

@@ -231,3 +231,31 @@ def test_packet_reaching_a_reference_stop_is_reported():
     with pytest.raises(RuntimeError):
         o.transport(1, 0, 100, seed=SEED)
     e.close()
+
+
+def test_async_pdf_upload_gives_same_answer_and_reports_bad_tables():
+    """option async_pdfs: set_pdfs only enqueues upload+transpose on a copy stream (overlapping
+    the stellar wave); results are unchanged and a non-monotone table is reported by the
+    next transport call."""
+    m, n = make("cube_clumpy_gasdust")
+    n = 200000                                   # wave-front path
+    ref = _engine(m)
+    ref.zero_estimators(); ref.energyPacketDriver(1, n)
+    want = ref.fetch(1); ref.close()
+    e = PacketEngine(m, seed=SEED)
+    e.set_option("async_pdfs", 1)
+    e.set_opacity(); e.set_dust_state(); e.set_pdfs()
+    e.zero_estimators(); e.energyPacketDriver(1, n)
+    got = e.fetch(1)
+    assert np.array_equal(got["Jste"], want["Jste"]) and np.array_equal(got["escapedPackets"], want["escapedPackets"])
+    good = m.grids[0].recPDF
+    bad = good.copy(order="F"); bad[7, 50] = 3.0
+    m.grids[0].recPDF = bad
+    e.set_pdfs()                                 # accepted: verdict is deferred
+    with pytest.raises(MocassinError) as ei:
+        e.energyPacketDriver(1, n)
+    assert ei.value.code == -7
+    m.grids[0].recPDF = good
+    e.set_pdfs(); e.zero_estimators(); e.energyPacketDriver(1, n)
+    assert np.array_equal(e.fetch(1)["Jste"], want["Jste"])
+    e.close()
