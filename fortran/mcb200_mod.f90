@@ -87,6 +87,13 @@ module mcb200_mod
          integer(c_int64_t), value :: nPacketsGlobal; real(c_float), value :: deltaE
          type(mcb200_counters), intent(out) :: counters
        end function
+       integer(c_int) function mcb200_set_res_line_packets(ctx, iG, resLinePackets) bind(C, name="mcb200_set_res_line_packets")
+         import; type(c_ptr), value :: ctx, resLinePackets; integer(c_int32_t), value :: iG
+       end function
+       integer(c_int) function mcb200_transport_reslines(ctx, iStar, deltaE, counters) bind(C, name="mcb200_transport_reslines")
+         import; type(c_ptr), value :: ctx; integer(c_int32_t), value :: iStar; real(c_float), value :: deltaE
+         type(mcb200_counters), intent(out) :: counters
+       end function
        integer(c_int) function mcb200_tally_buffer(ctx, iG, which, devPtr, count) bind(C, name="mcb200_tally_buffer")
          import; type(c_ptr), value :: ctx; integer(c_int32_t), value :: iG, which
          type(c_ptr), intent(out) :: devPtr; integer(c_int64_t), intent(out) :: count

@@ -195,6 +195,16 @@ int mcb200_transport(mcb200_ctx *ctx, int32_t iStar, int64_t nPacketsGlobal, flo
 int mcb200_transport_diffuse(mcb200_ctx *ctx, int32_t gpLoc, const int32_t *cellLoc,
                              int64_t nPacketsGlobal, float deltaE, mcb200_counters *counters);
 
+/* Resonance-line packet transfer, the second half of energyPacketDriver
+ * (photon_mod.f90:180-266; the host decides when it runs: lgDust, convPercent >=
+ * resLinesTransfer, not the first iteration).  resLinePackets(0:nCells) of grid iG is the
+ * table emission_mod fills (emission_mod.f90:244); mcb200_transport_reslines then starts
+ * that many "diffuse" packets at the centre of every cell this rank owns under the
+ * reference's round-robin rule mod(iCell-(taskid+1),numtasks)==0, tallying with
+ * deltaE(iStar) exactly like the loop it replaces. */
+int mcb200_set_res_line_packets(mcb200_ctx *ctx, int32_t iG, const int32_t *resLinePackets);
+int mcb200_transport_reslines(mcb200_ctx *ctx, int32_t iStar, float deltaE, mcb200_counters *counters);
+
 /* Device pointers and element counts of the pending integer tallies of grid iG so
  * the caller's communicator can sum them across ranks in place (NCCL allreduce, sum)
  * -- replaces MPI_ALLREDUCE at iteration_mod.f90:627,649,653,659.  which: 0 JsteQ,

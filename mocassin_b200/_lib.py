@@ -51,6 +51,8 @@ _SIGS = {
     "mcb200_zero_estimators": [C.c_void_p],
     "mcb200_transport": [C.c_void_p, C.c_int32, C.c_int64, C.c_float, C.POINTER(Counters)],
     "mcb200_transport_diffuse": [C.c_void_p, C.c_int32, c_int32_p, C.c_int64, C.c_float, C.POINTER(Counters)],
+    "mcb200_set_res_line_packets": [C.c_void_p, C.c_int32, c_int32_p],
+    "mcb200_transport_reslines": [C.c_void_p, C.c_int32, C.c_float, C.POINTER(Counters)],
     "mcb200_tally_buffer": [C.c_void_p, C.c_int32, C.c_int32, C.POINTER(C.c_void_p), c_int64_p],
     "mcb200_reduce": [C.c_void_p],
     "mcb200_fetch_estimators": [C.c_void_p, C.c_int32, c_float_p, c_float_p, c_float_p, c_float_p],

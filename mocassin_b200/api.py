@@ -233,6 +233,18 @@ class PacketEngine:
         self._check(rc)
         return cnt.as_dict()
 
+    def resLinePacketsTransfer(self, iStar: int, deltaE: Optional[float] = None) -> dict:
+        """The resonance-line packet loop of energyPacketDriver (photon_mod.f90:180-266):
+        `grid.resLinePackets(cell)` diffuse packets from the centre of every cell of this rank."""
+        for i, g in enumerate(self.model.grids, start=1):
+            r = getattr(g, "resLinePackets", None)
+            self._check(self.lib.mcb200_set_res_line_packets(self.h, i, _ip(_f(r, I32)) if r is not None else None))
+        cnt = _lib.Counters()
+        if deltaE is None:
+            deltaE = float(self.model.deltaE[iStar])
+        self._check(self.lib.mcb200_transport_reslines(self.h, iStar, C.c_float(deltaE), C.byref(cnt)))
+        return cnt.as_dict()
+
     def tally_buffer(self, iG: int, which: int) -> tuple[int, int]:
         p = C.c_void_p()
         n = C.c_int64()

@@ -91,6 +91,7 @@ struct GridState {
     int lenExp = 0;                       // path-length unit = 2^lenExp cm
     std::vector<float> hx, hy, hz;        // host copies of the axes
     std::vector<int> hactive;
+    std::vector<int> resLinePackets;      // (0:nCells) extra packets of the resonance-line transfer
     DevBuf<float> xAxis, yAxis, zAxis, xWall, yWall, zWall;
     DevBuf<int> active;
     DevBuf<float> opacity, scaOpac, absOpac, pdfT, totalLines, linePDF, dV, stage;
@@ -140,6 +141,8 @@ struct mcb200_ctx {
     int stepBudget = 96;
     int64_t tailThreshold = 32768;        // alive packets below which the persistent kernel finishes the batch
     DevBuf<unsigned char> wfArgsDev;
+    DevBuf<ResCell> resCells;
+    DevBuf<unsigned int> resPrefix;
     DevBuf<unsigned short> wfFlyKey;
     DevBuf<unsigned long long> wfNext;
     int lastWaves = 0, lastLaunches = 0, lastFoldLaunches = 0;
@@ -409,8 +412,63 @@ int run_wavefront(mcb200_ctx *ctx, const TransportArgs &a, bool multi, int64_t m
     return MCB200_OK;
 }
 
+// interpolation_mod.f90:48-81 on the host (ascending axis)
+int host_locate(const std::vector<float> &xa, float x)
+{
+    int n = (int)xa.size();
+    if (x > xa[n - 1]) return n;
+    if (x < xa[0]) return 0;
+    int first = n;                       // first 0-based index with xa > x
+    for (int i = 0; i < n; ++i) if (xa[i] > x) { first = i; break; }
+    if (first >= n) return 1;
+    return first > 1 ? first : 1;
+}
+
+// source cells of the resonance-line transfer owned by this rank (photon_mod.f90:187-262)
+int build_res_cells(mcb200_ctx *ctx, std::vector<ResCell> &cells, std::vector<unsigned int> &prefix)
+{
+    long long iCell = 0;
+    unsigned long long gid = 0, local = 0;
+    cells.clear(); prefix.clear();
+    for (int ig = 0; ig < ctx->cfg.nGrids; ++ig) {
+        GridState &g = ctx->grids[ig];
+        for (int ix = 1; ix <= g.nx; ++ix)
+            for (int iy = 1; iy <= g.ny; ++iy)
+                for (int iz = 1; iz <= g.nz; ++iz) {
+                    ++iCell;
+                    int cell = g.hactive[(size_t)(ix - 1) + (size_t)g.nx * ((size_t)(iy - 1) + (size_t)g.ny * (size_t)(iz - 1))];
+                    int cnt = (cell > 0 && !g.resLinePackets.empty()) ? g.resLinePackets[cell] : 0;
+                    if (cnt <= 0) continue;
+                    if (((iCell - (ctx->rank + 1)) % ctx->nranks) == 0) {
+                        ResCell rc{};
+                        rc.grid = ig + 1; rc.x = (short)ix; rc.y = (short)iy; rc.z = (short)iz;
+                        rc.px = g.hx[ix - 1]; rc.py = g.hy[iy - 1]; rc.pz = g.hz[iz - 1];
+                        rc.mx = rc.my = rc.mz = -1;
+                        if (ig > 0) {
+                            GridState &m = ctx->grids[g.motherP - 1];
+                            int a = host_locate(m.hx, rc.px);
+                            if (a >= 1 && a < m.nx && rc.px > (m.hx[a - 1] + m.hx[a]) / 2.f) a = a + 1;
+                            int b = host_locate(m.hy, rc.py);
+                            if (b >= 1 && b < m.ny && rc.py > (m.hy[b - 1] + m.hy[b]) / 2.f) b = b + 1;
+                            int c = host_locate(m.hz, rc.pz);
+                            if (c >= 1 && c < m.nz && rc.pz > (m.hz[c - 1] + m.hz[c]) / 2.f) c = c + 1;
+                            rc.mx = (short)a; rc.my = (short)b; rc.mz = (short)c;
+                        }
+                        rc.gid = gid;
+                        cells.push_back(rc);
+                        prefix.push_back((unsigned int)local);
+                        local += (unsigned long long)cnt;
+                    }
+                    gid += (unsigned long long)cnt;
+                }
+    }
+    if (local >= (1ull << 31)) return fail(ctx, MCB200_EINVAL, "too many resonance-line packets on one rank");
+    prefix.push_back((unsigned int)local);
+    return MCB200_OK;
+}
+
 int run_transport(mcb200_ctx *ctx, int iStar, int difGrid, const int32_t *cellLoc, int64_t nGlobal,
-                  float deltaE, mcb200_counters *out)
+                  float deltaE, mcb200_counters *out, bool resLines = false)
 {
     const mcb200_config &cfg = ctx->cfg;
     if (!ctx->haveCfg) return fail(ctx, MCB200_ESTATE, "mcb200_set_config not called");
@@ -466,6 +524,21 @@ int run_transport(mcb200_ctx *ctx, int iStar, int difGrid, const int32_t *cellLo
         a.difGrid = difGrid; a.difX = cellLoc[0]; a.difY = cellLoc[1]; a.difZ = cellLoc[2];
     }
     a.firstId = first; a.n = mine; a.seed = ctx->seed;
+    a.resCells = nullptr; a.resPrefix = nullptr; a.nResCells = 0;
+    if (resLines) {
+        if (!cfg.lgGas || !cfg.lgDust) return fail(ctx, MCB200_ESTATE, "resonance-line transfer needs gas and dust (photon_mod.f90:180,910)");
+        std::vector<ResCell> cells;
+        std::vector<unsigned int> prefix;
+        int rcb = build_res_cells(ctx, cells, prefix);
+        if (rcb) return rcb;
+        mine = (int64_t)prefix.back();
+        a.n = mine; a.firstId = 0;
+        if (mine > 0) {
+            CU(ctx->resCells.upload(cells.data(), cells.size(), ctx->stream));
+            CU(ctx->resPrefix.upload(prefix.data(), prefix.size(), ctx->stream));
+            a.resCells = ctx->resCells.p; a.resPrefix = ctx->resPrefix.p; a.nResCells = (int)cells.size();
+        }
+    }
     CU(ctx->nextPacket.alloc(1)); CU(ctx->nextPacket.zero(ctx->stream));
     CU(ctx->counters.alloc(C_COUNT)); CU(ctx->counters.zero(ctx->stream));
     CU(ctx->qphot.alloc(cfg.nbins)); CU(ctx->qphot.zero(ctx->stream));
@@ -490,7 +563,7 @@ int run_transport(mcb200_ctx *ctx, int iStar, int difGrid, const int32_t *cellLo
     // frequency-ordered processing pays when the nu-planes do not all fit in L2 anyway
     size_t tableBytes = 0;
     for (auto &g : ctx->grids) tableBytes += tsize(ctx, g) * 12;       // opacity 4 B + JsteQ 8 B
-    bool ordered = ctx->orderMode == 1 || (ctx->orderMode < 0 && tableBytes > (size_t)48 << 20 && mine >= (1 << 16));
+    bool ordered = !resLines && (ctx->orderMode == 1 || (ctx->orderMode < 0 && tableBytes > (size_t)48 << 20 && mine >= (1 << 16)));
     if (mine >= ((int64_t)1 << 32)) return fail(ctx, MCB200_EINVAL, "more than 2^32 packets per rank in one call: split the call");
     CU(cudaEventRecord(ctx->ev0, ctx->stream));
     a.order = nullptr;
@@ -954,6 +1027,24 @@ int mcb200_transport_diffuse(mcb200_ctx *ctx, int32_t gpLoc, const int32_t *cell
 {
     NEED_CTX();
     return run_transport(ctx, 0, gpLoc, cellLoc, nPacketsGlobal, deltaE, counters);
+}
+
+int mcb200_set_res_line_packets(mcb200_ctx *ctx, int32_t iG, const int32_t *resLinePackets)
+{
+    NEED_CTX();
+    GridState *g = grid_of(ctx, iG);
+    if (!g || !g->set) return fail(ctx, MCB200_ESTATE, "grid %d not set", iG);
+    if (!resLinePackets) { g->resLinePackets.clear(); return MCB200_OK; }
+    g->resLinePackets.assign(resLinePackets, resLinePackets + g->nCells + 1);
+    for (int v : g->resLinePackets) if (v < 0) return fail(ctx, MCB200_EINVAL, "negative resLinePackets");
+    return MCB200_OK;
+}
+
+int mcb200_transport_reslines(mcb200_ctx *ctx, int32_t iStar, float deltaE, mcb200_counters *counters)
+{
+    NEED_CTX();
+    if (iStar < 1) return fail(ctx, MCB200_EINVAL, "iStar must be >= 1");
+    return run_transport(ctx, iStar, 0, nullptr, 0, deltaE, counters, true);
 }
 
 int mcb200_tally_buffer(mcb200_ctx *ctx, int32_t iG, int32_t which, void **devPtr, int64_t *count)

@@ -167,6 +167,25 @@ __device__ __forceinline__ int hg(const DevParams &P, Lane &L)
     return 1;
 }
 
+// Philox stream id of packet k of this call.  Stellar / diffuse-source packets: global packet
+// index.  Resonance-line packets: 2^40 + global enumeration index (cell looked up in the
+// rank-local prefix table).
+__device__ __forceinline__ int res_cell_of(const TransportArgs &a, long long k)
+{
+    int lo = 0, hi = a.nResCells;        // last c with resPrefix[c] <= k
+    while (hi - lo > 1) {
+        int mid = (lo + hi) >> 1;
+        if ((long long)__ldg(&a.resPrefix[mid]) <= k) lo = mid; else hi = mid;
+    }
+    return lo;
+}
+__device__ __forceinline__ unsigned long long packet_pid(const TransportArgs &a, long long k)
+{
+    if (!a.resCells) return (unsigned long long)(a.firstId + k);
+    int c = res_cell_of(a, k);
+    return (1ull << 40) + a.resCells[c].gid + (unsigned long long)(k - (long long)a.resPrefix[c]);
+}
+
 template <bool MULTI, bool DENSE = false>
 struct Transport {
     const TransportArgs &a;
@@ -286,10 +305,22 @@ struct Transport {
     {
         const DevParams &P = a.P;
         L.k = k;
-        L.rng.init(a.seed, (unsigned long long)(a.firstId + k), (uint32_t)a.iStar);
         L.segs = 0; L.gen = 0; L.fate = 0; L.lastNuP = 0; L.planeG = 0;
         L.mx = L.my = L.mz = -1;
         L.sx = L.sy = L.sz = -1;
+        if (a.resCells) {                // resonance-line packet: "diffuse" from a cell centre
+            int c = res_cell_of(a, k);
+            const ResCell rc = a.resCells[c];
+            L.rng.init(a.seed, (1ull << 40) + rc.gid + (unsigned long long)(k - (long long)a.resPrefix[c]), (uint32_t)a.iStar);
+            L.chType = CH_DIFFUSE;
+            L.gP = rc.grid;
+            L.rx = rc.px; L.ry = rc.py; L.rz = rc.pz;
+            if (L.gP == 1) { L.mx = rc.x; L.my = rc.y; L.mz = rc.z; }
+            else { L.sx = rc.x; L.sy = rc.y; L.sz = rc.z; L.mx = rc.mx; L.my = rc.my; L.mz = rc.mz; }
+            L.phase = PH_EMIT;
+            return;
+        }
+        L.rng.init(a.seed, (unsigned long long)(a.firstId + k), (uint32_t)a.iStar);
         if (a.iStar >= 1) {
             const int *si = &P.starIdx[4 * (a.iStar - 1)];
             L.chType = CH_STELLAR;

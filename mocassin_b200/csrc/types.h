@@ -56,6 +56,15 @@ enum Counter {
     C_COUNT
 };
 
+// one source cell of the resonance-line packet transfer (photon_mod.f90:180-266)
+struct ResCell {
+    int grid;                        // 1-based grid
+    short x, y, z;                   // cell indices in that grid
+    short mx, my, mz;                // mother-grid slot (sub-grids: nearest mother point, :222-239)
+    float px, py, pz;                // cell centre
+    unsigned long long gid;          // global index of the cell's first packet (all ranks, loop order)
+};
+
 struct TransportArgs {
     DevParams P;
     DevGrid g1;                      // copy of grids[0] (constant-bank access for the mother grid)
@@ -72,6 +81,9 @@ struct TransportArgs {
     unsigned long long *qphotCounts; // [nbins]
     int *errFlag;
     int *fates;                      // optional [4*n]
+    const ResCell *resCells;         // resonance-line transfer: this rank's source cells, or NULL
+    const unsigned int *resPrefix;   // [nResCells+1] packets before each source cell (this rank)
+    int nResCells;
     unsigned int *segsArr;           // wave-front + trace: segments of earlier flights per packet
 };
 

@@ -51,6 +51,7 @@ class Grid:
     dustAbunIndex: Optional[np.ndarray] = None  # (nCells+1,) int32
     Ndust: Optional[np.ndarray] = None        # (nCells+1,)
     Hden: Optional[np.ndarray] = None         # (nCells+1,)
+    resLinePackets: Optional[np.ndarray] = None   # (nCells+1,) int32, resonance-line transfer
 
     @property
     def nx(self):

@@ -1084,6 +1084,60 @@ int oracle_transport(const OrParams *P, OrGrid *grids, int32_t iStar, int64_t fi
     return 0;
 }
 
+/* photon_mod.f90:180-266 */
+int oracle_transport_reslines(const OrParams *P, OrGrid *grids, int32_t iStar, uint64_t seed,
+                              int32_t rank, int32_t nranks, OrCounters *C, int64_t *nRun)
+{
+    Ctx c;
+    memset(&c, 0, sizeof(c));
+    c.P = P; c.grids = grids; c.iStar = iStar; c.C = C; c.qphotCounts = NULL;
+    c.deltaE = P->deltaE[iStar];
+    int64_t iCell = 0, gid = 0, run = 0;
+    for (int igrid = 1; igrid <= P->nGrids; ++igrid) {
+        OrGrid *g = &grids[igrid - 1];
+        int igp = igrid == 1 ? 0 : 1;
+        for (int ix = 1; ix <= g->nx; ++ix)
+            for (int iy = 1; iy <= g->ny; ++iy)
+                for (int iz = 1; iz <= g->nz; ++iz) {
+                    iCell = iCell + 1;
+                    int32_t cell = ACTIVE(g, ix, iy, iz);
+                    int32_t cnt = (cell > 0 && g->resLinePackets) ? g->resLinePackets[cell] : 0;
+                    int mine = ((iCell - (rank + 1)) % nranks) == 0;
+                    for (int iPhot = 1; iPhot <= cnt; ++iPhot, ++gid) {
+                        if (!mine) continue;
+                        int32_t inX[2] = { -1, -1 }, inY[2] = { -1, -1 }, inZ[2] = { -1, -1 };
+                        vec3 pos = { g->xAxis[ix - 1], g->yAxis[iy - 1], g->zAxis[iz - 1] };
+                        inX[igp] = ix; inY[igp] = iy; inZ[igp] = iz;
+                        if (igrid > 1) {          /* location on the mother grid, :222-239 */
+                            const OrGrid *m = &grids[g->motherP - 1];
+                            inX[0] = locate(m->xAxis, m->nx, pos.x);
+                            if (inX[0] >= 1 && inX[0] < m->nx && pos.x > (m->xAxis[inX[0] - 1] + m->xAxis[inX[0]]) / 2.f) inX[0] = inX[0] + 1;
+                            inY[0] = locate(m->yAxis, m->ny, pos.y);
+                            if (inY[0] >= 1 && inY[0] < m->ny && pos.y > (m->yAxis[inY[0] - 1] + m->yAxis[inY[0]]) / 2.f) inY[0] = inY[0] + 1;
+                            inZ[0] = locate(m->zAxis, m->nz, pos.z);
+                            if (inZ[0] >= 1 && inZ[0] < m->nz && pos.z > (m->zAxis[inZ[0] - 1] + m->zAxis[inZ[0]]) / 2.f) inZ[0] = inZ[0] + 1;
+                        }
+                        rng_init(&c.rng, seed, ((uint64_t)1 << 40) + (uint64_t)gid, (uint32_t)iStar);
+                        c.segs = 0; c.fateCode = 0;
+                        int chTypeIn = CH_DIFFUSE, reRun = 0, i, rc;
+                        int32_t gPIn = igrid, lastNuP = 0;
+                        vec3 positionIn = pos;
+                        for (i = 1; i <= 5000; ++i) {
+                            rc = energy_packet_run(&c, &chTypeIn, &positionIn, inX, inY, inZ, &gPIn, &reRun, &lastNuP);
+                            if (rc) return rc;
+                            if (reRun == 0) break;
+                        }
+                        if (i >= 5000) C->trapped++;
+                        if (c.fateCode == 3) C->nDropped++;
+                        C->nSegments += c.segs;
+                        run++;
+                    }
+                }
+    }
+    if (nRun) *nRun = run;
+    return 0;
+}
+
 /* ------------------------------------------------------------------------- */
 typedef struct MtArg {
     const OrParams *P; OrGrid *grids; int32_t iStar; int64_t first, n; uint64_t seed;

@@ -40,6 +40,8 @@ typedef struct OrGrid {
      *   JsteQ/JdifQ: sum of llrintf(pathlength * invLenUnit)
      *   escapedQ/linePacketsQ: packet counts */
     int64_t *JsteQ, *JdifQ, *escapedQ, *linePacketsQ;
+    /* extra packets per cell of the resonance-line transfer (0:nCells), may be NULL */
+    const int32_t *resLinePackets;
 } OrGrid;
 
 typedef struct OrParams {
@@ -100,6 +102,14 @@ int oracle_transport(const OrParams *P, OrGrid *grids, int32_t iStar,
 int oracle_transport_mt(const OrParams *P, OrGrid *grids, int32_t iStar,
                         int64_t firstId, int64_t n, uint64_t seed,
                         int32_t nThreads, OrCounters *C, int64_t *qphotCounts);
+
+/* Resonance-line packet transfer (photon_mod.f90:180-266): for every cell owned by `rank`
+ * (mod(iCell-(rank+1),nranks)==0, iCell counting all cells of all grids in loop order)
+ * resLinePackets(cell) "diffuse" packets start at the cell centre.  The Philox stream of
+ * packet j (global enumeration order over grids/cells/iPhot) is keyed by 2^40+j, so the
+ * result does not depend on nranks.  Returns the number of packets run via *nRun. */
+int oracle_transport_reslines(const OrParams *P, OrGrid *grids, int32_t iStar, uint64_t seed,
+                              int32_t rank, int32_t nranks, OrCounters *C, int64_t *nRun);
 
 /* Opacity assembly for every active cell of one grid: restatement of ionizationDriver's
  * density computation (ionization_mod.f90:65-80), addOpacity/putOpacity/inOpacity

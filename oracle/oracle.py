@@ -28,7 +28,7 @@ class OrGrid(C.Structure):
                 ("opacity", fp), ("scaOpac", fp), ("recPDF", fp), ("dustPDF", fp), ("linePDF", fp),
                 ("totalLines", fp), ("Tdust", fp), ("dustAbunIndex", ip),
                 ("Jste", fp), ("Jdif", fp), ("escapedPackets", fp), ("linePackets", fp),
-                ("JsteQ", lp), ("JdifQ", lp), ("escapedQ", lp), ("linePacketsQ", lp)]
+                ("JsteQ", lp), ("JdifQ", lp), ("escapedQ", lp), ("linePacketsQ", lp), ("resLinePackets", ip)]
 
 
 class OrParams(C.Structure):
@@ -217,6 +217,7 @@ class Oracle:
                 self._keep.append(a)
                 setattr(og, name, _p(a, fp))
             dai = _F(g.dustAbunIndex, np.int32); self._keep.append(dai); og.dustAbunIndex = _p(dai, ip)
+            rlp = _F(getattr(g, 'resLinePackets', None), np.int32); self._keep.append(rlp); og.resLinePackets = _p(rlp, ip)
             tshape = (g.nCells + 1, m.nbins)
             eshape = (g.nCells + 1, m.nbins + 1, m.nAngleBins + 1)
             lshape = (g.nCells + 1, max(m.nLines, 1))
@@ -253,6 +254,18 @@ class Oracle:
         if rc != 0:
             raise RuntimeError(f"oracle stop condition {rc}")
         return cnt.as_dict(), fates
+
+    def transport_reslines(self, iStar: int, seed: int = 12345, rank: int = 0, nranks: int = 1):
+        cnt = OrCounters()
+        n = C.c_int64()
+        self.lib.oracle_transport_reslines.restype = C.c_int
+        self.lib.oracle_transport_reslines.argtypes = [C.POINTER(OrParams), C.POINTER(OrGrid), C.c_int32, C.c_uint64,
+                                                       C.c_int32, C.c_int32, C.POINTER(OrCounters), lp]
+        rc = self.lib.oracle_transport_reslines(C.byref(self.P), self.G, iStar, C.c_uint64(seed), rank, nranks,
+                                                C.byref(cnt), C.byref(n))
+        if rc != 0:
+            raise RuntimeError(f"oracle stop condition {rc}")
+        return cnt.as_dict(), int(n.value)
 
     def transport_mt(self, iStar: int, first: int, n: int, seed: int = 12345, threads: int = 1):
         cnt = OrCounters()

@@ -259,3 +259,41 @@ def test_async_pdf_upload_gives_same_answer_and_reports_bad_tables():
     e.set_pdfs(); e.zero_estimators(); e.energyPacketDriver(1, n)
     assert np.array_equal(e.fetch(1)["Jste"], want["Jste"])
     e.close()
+
+
+@pytest.mark.parametrize("wavefront", [0, 1])
+def test_resonance_line_packet_transfer(wavefront):
+    """Second half of energyPacketDriver (photon_mod.f90:180-266): resLinePackets(cell) diffuse
+    packets from every cell centre, cells dealt round-robin to ranks."""
+    m, _ = make("multigrid_sym")
+    rng = np.random.default_rng(4)
+    for g in m.grids:
+        r = rng.integers(0, 5, g.nCells + 1).astype(np.int32)
+        r[0] = 0
+        g.resLinePackets = r
+    o = Oracle(m)
+    co, nrun = o.transport_reslines(1, seed=SEED)
+    e = _engine(m)
+    e.set_option("wavefront", wavefront)
+    e.zero_estimators()
+    cg = e.resLinePacketsTransfer(1)
+    assert cg["nPackets"] == nrun == sum(int(g.resLinePackets.sum()) for g in m.grids)
+    for k in ("nAbs", "nSca", "nSegments", "nEscaped", "nLinePackets", "nFlights"):
+        assert cg[k] == co[k], k
+    for iG in (1, 2):
+        got, want = e.fetch(iG), o.folded(iG, float(m.deltaE[1]))
+        assert np.array_equal(got["Jste"][1:], want["Jste"][1:])
+        assert np.array_equal(got["escapedPackets"], want["escapedPackets"])
+    e.close()
+    # two ranks, one after the other on this GPU: integer tallies add up to the oracle's
+    parts = []
+    for r in range(2):
+        e = _engine(m, rank=r, nranks=2)
+        e.set_option("wavefront", wavefront)
+        e.zero_estimators()
+        e.resLinePacketsTransfer(1)
+        parts.append([e.fetch_tallies(iG) for iG in (1, 2)])
+        e.close()
+    for iG in (0, 1):
+        assert np.array_equal((parts[0][iG]["JsteQ"] + parts[1][iG]["JsteQ"])[1:], o.out[iG]["JsteQ"][1:])
+        assert np.array_equal(parts[0][iG]["escapedQ"] + parts[1][iG]["escapedQ"], o.out[iG]["escapedQ"])
