@@ -94,6 +94,10 @@ module mcb200_mod
          import; type(c_ptr), value :: ctx; integer(c_int32_t), value :: iStar; real(c_float), value :: deltaE
          type(mcb200_counters), intent(out) :: counters
        end function
+       integer(c_int) function mcb200_fetch_plane_distribution(ctx, planeIonDistribution) &
+            & bind(C, name="mcb200_fetch_plane_distribution")
+         import; type(c_ptr), value :: ctx, planeIonDistribution
+       end function
        integer(c_int) function mcb200_tally_buffer(ctx, iG, which, devPtr, count) bind(C, name="mcb200_tally_buffer")
          import; type(c_ptr), value :: ctx; integer(c_int32_t), value :: iG, which
          type(c_ptr), intent(out) :: devPtr; integer(c_int64_t), intent(out) :: count

@@ -36,7 +36,7 @@ extern "C" {
 #define MCB200_ESTATE       -3   /* call sequence error (e.g. transport before set) */
 #define MCB200_ENOMEM       -4   /* device allocation failed                        */
 #define MCB200_EPACKET      -5   /* a packet hit one of the reference's `stop`s     */
-#define MCB200_EUNSUPPORTED -6   /* lgPlaneIonization / lg1D                        */
+#define MCB200_EUNSUPPORTED -6   /* nested sub-grids / lg1D                          */
 #define MCB200_ETABLE       -7   /* CDF table not monotone / bad range              */
 
 typedef struct mcb200_ctx mcb200_ctx;   /* opaque */
@@ -235,6 +235,11 @@ int mcb200_fetch_estimators(mcb200_ctx *ctx, int32_t iG, float *Jste, float *esc
 int mcb200_fetch_tallies(mcb200_ctx *ctx, int32_t iG, int64_t *JsteQ, int64_t *escapedQ,
                          int64_t *JdifQ, int64_t *linePacketsQ);
 int mcb200_len_unit(mcb200_ctx *ctx, int32_t iG, double *lenUnit);
+/* planeIonDistribution(grid(1)%nx, grid(1)%nz) of plane-parallel runs (packets emitted per
+ * (x,z) of the y=0 face, photon_mod.f90:643-646; written to planeIonDistribution.out by
+ * iteration_mod.f90:553-581); accumulated since the last mcb200_zero_estimators.  For
+ * nranks>1 sum it across ranks (mcb200_tally_buffer which=5, int32). */
+int mcb200_fetch_plane_distribution(mcb200_ctx *ctx, int32_t *planeIonDistribution);
 /* Number of stellar emissions per frequency bin with nu>1 Ryd of the last transport
  * call (Qphot = sum counts*deltaE/(2.1799153e-11*nu)). */
 int mcb200_fetch_qphot_counts(mcb200_ctx *ctx, int64_t *counts);

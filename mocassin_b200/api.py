@@ -333,6 +333,12 @@ class PacketEngine:
         self._check(self.lib.mcb200_len_unit(self.h, iG, C.byref(v)))
         return float(v.value)
 
+    def plane_distribution(self) -> np.ndarray:
+        g = self.model.grids[0]
+        d = np.zeros((g.nx, g.nz), dtype=I32, order="F")
+        self._check(self.lib.mcb200_fetch_plane_distribution(self.h, _ip(d)))
+        return d
+
     def qphot_counts(self) -> np.ndarray:
         q = np.zeros(self.model.nbins, dtype=np.int64)
         self._check(self.lib.mcb200_fetch_qphot_counts(self.h, _lp(q)))

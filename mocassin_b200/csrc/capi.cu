@@ -141,6 +141,7 @@ struct mcb200_ctx {
     int stepBudget = 96;
     int64_t tailThreshold = 32768;        // alive packets below which the persistent kernel finishes the batch
     DevBuf<unsigned char> wfArgsDev;
+    DevBuf<int> planeDist;                // planeIonDistribution(grid(1)%nx, grid(1)%nz)
     DevBuf<ResCell> resCells;
     DevBuf<unsigned int> resPrefix;
     DevBuf<unsigned short> wfFlyKey;
@@ -472,7 +473,6 @@ int run_transport(mcb200_ctx *ctx, int iStar, int difGrid, const int32_t *cellLo
 {
     const mcb200_config &cfg = ctx->cfg;
     if (!ctx->haveCfg) return fail(ctx, MCB200_ESTATE, "mcb200_set_config not called");
-    if (cfg.lgPlaneIonization) return fail(ctx, MCB200_EUNSUPPORTED, "lgPlaneIonization is not supported");
     if (!ctx->haveSpectra || !ctx->haveStars) return fail(ctx, MCB200_ESTATE, "spectra/stars not set");
     if (cfg.nAngleBins > 0 && !ctx->haveView) return fail(ctx, MCB200_ESTATE, "viewpoints not set");
     if (nGlobal < 0) return fail(ctx, MCB200_EINVAL, "negative packet count");
@@ -508,7 +508,14 @@ int run_transport(mcb200_ctx *ctx, int iStar, int difGrid, const int32_t *cellLo
     P.nGrids = cfg.nGrids; P.nbins = cfg.nbins; P.nStars = cfg.nStars; P.nAngleBins = cfg.nAngleBins;
     P.totT = cfg.totAngleBinsTheta; P.totP = cfg.totAngleBinsPhi; P.nLines = cfg.nLines;
     P.lgDust = cfg.lgDust; P.lgGas = cfg.lgGas; P.lgSym = cfg.lgSymmetricXYZ; P.lgIso = cfg.lgIsotropic;
-    P.lgDebug = cfg.lgDebug; P.lgMultistars = cfg.lgMultistars;
+    P.lgDebug = cfg.lgDebug; P.lgMultistars = cfg.lgMultistars; P.lgPlane = cfg.lgPlaneIonization;
+    P.safeLimit = cfg.lgPlaneIonization ? 5000 : 500000;
+    P.planeDist = nullptr;
+    if (cfg.lgPlaneIonization) {
+        size_t np = (size_t)ctx->grids[0].nx * ctx->grids[0].nz;
+        if (ctx->planeDist.n != np) { CU(ctx->planeDist.alloc(np)); CU(ctx->planeDist.zero(ctx->stream)); }
+        P.planeDist = ctx->planeDist.p;
+    }
     P.dTheta = cfg.dTheta; P.dPhi = cfg.dPhi; P.R_out = cfg.R_out; P.ionEdge1 = cfg.ionEdge1;
     P.nuArray = ctx->nuArray.p; P.gSca = ctx->gSca.p; P.starCdf = ctx->starCdf.p;
     P.starPos = ctx->starPos.p; P.starIdx = ctx->starIdx.p; P.starCell = ctx->starCell.p;
@@ -712,7 +719,8 @@ int mcb200_set_config(mcb200_ctx *ctx, const mcb200_config *cfg)
     if (!cfg) return fail(ctx, MCB200_EINVAL, "null config");
     if (cfg->nGrids < 1 || cfg->nbins < 3 || cfg->nStars < 0 || cfg->nAngleBins < 0)
         return fail(ctx, MCB200_EINVAL, "bad sizes in config");
-    if (cfg->lgPlaneIonization) return fail(ctx, MCB200_EUNSUPPORTED, "lgPlaneIonization is not supported");
+    if (cfg->lgPlaneIonization && cfg->lgSymmetricXYZ)
+        return fail(ctx, MCB200_EINVAL, "lgSymmetricXYZ and lgPlaneIonization flags both raised (photon_mod.f90:2675-2678)");
     if (cfg->totAngleBinsTheta < 1 || cfg->totAngleBinsPhi < 1 || !(cfg->dTheta > 0.f) || !(cfg->dPhi > 0.f))
         return fail(ctx, MCB200_EINVAL, "bad angle bins in config");
     ctx->cfg = *cfg;
@@ -1010,6 +1018,7 @@ int mcb200_zero_estimators(mcb200_ctx *ctx)
         CU(g.lineQ.zero(ctx->stream)); CU(g.linePk.zero(ctx->stream));
         CU(g.nuTouched.zero(ctx->stream));
     }
+    CU(ctx->planeDist.zero(ctx->stream));
     CU(cudaStreamSynchronize(ctx->stream));
     ctx->pending = false;
     return MCB200_OK;
@@ -1063,6 +1072,8 @@ int mcb200_tally_buffer(mcb200_ctx *ctx, int32_t iG, int32_t which, void **devPt
         *devPtr = b->p; *count = (int64_t)b->n;
     } else if (which == 4) {
         *devPtr = g->nuTouched.p; *count = (int64_t)g->nuTouched.n;
+    } else if (which == 5) {
+        *devPtr = ctx->planeDist.p; *count = (int64_t)ctx->planeDist.n;
     } else {
         return fail(ctx, MCB200_EINVAL, "bad tally selector %d", which);
     }
@@ -1124,6 +1135,15 @@ int mcb200_len_unit(mcb200_ctx *ctx, int32_t iG, double *lenUnit)
     GridState *g = grid_of(ctx, iG);
     if (!g || !g->set || !lenUnit) return fail(ctx, MCB200_EINVAL, "bad len_unit arguments");
     *lenUnit = std::ldexp(1.0, g->lenExp);
+    return MCB200_OK;
+}
+
+int mcb200_fetch_plane_distribution(mcb200_ctx *ctx, int32_t *planeIonDistribution)
+{
+    NEED_CTX();
+    if (!planeIonDistribution || !ctx->planeDist.p) return fail(ctx, MCB200_ESTATE, "no plane-ionisation run yet");
+    CU(cudaStreamSynchronize(ctx->stream));
+    CU(cudaMemcpy(planeIonDistribution, ctx->planeDist.p, ctx->planeDist.n * sizeof(int), cudaMemcpyDeviceToHost));
     return MCB200_OK;
 }
 

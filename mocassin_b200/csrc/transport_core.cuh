@@ -15,7 +15,6 @@ enum { PH_NEED = 0, PH_EMIT = 1, PH_FLY = 2, PH_SCATTER = 3, PH_ESCAPE = 4, PH_D
 enum { FATE_ESCAPED = 1, FATE_LINE = 2, FATE_DROPPED = 3, FATE_TRAPPED = 4, FATE_EARLY = 5 };
 
 constexpr int kThreads = 256;
-constexpr int kSafeLimit = 500000;       // photon_mod.f90:1190
 constexpr int kRecursionLimit = 5000;    // constants_mod.f90:56
 constexpr int kBatch = 8;                // lanes that must wait for a rare phase before it runs
 constexpr int kAggSteps = 6;             // first steps of a flight whose tallies are warp-aggregated
@@ -389,7 +388,38 @@ struct Transport {
         L.lastNuP = nuP;
         if (nuP >= P.nbins) { fail(L, 33); return; }   // fatal in the reference (:826,868,962,1018)
         L.lgStellar = stellar ? 1 : 0;
-        new_direction(P, L, stellar);
+        if (stellar && P.lgPlane) {
+            // plane-parallel ionisation: enter through the y=0 face along +y (:561-646)
+            const DevGrid &g = G(L.gP);
+            const float *xa = g.xAxis, *za = g.zAxis;
+            float random = 1.f - L.rng.uniform();
+            float x1 = __ldg(&xa[0]), x2 = __ldg(&xa[1]), xm = __ldg(&xa[g.nx - 2]), xn = __ldg(&xa[g.nx - 1]);
+            L.rx = -(x2 - x1) / 2.f + random * ((x2 - x1) / 2.f + (xn - xm) / 2.f + xn);
+            if (L.rx < x1) L.rx = x1;
+            if (L.rx > xn) L.rx = xn;
+            ex = locate_axis(xa, g.nx, L.rx);
+            if (ex < g.nx) { if (ex >= 1 && L.rx >= (__ldg(&xa[ex - 1]) + __ldg(&xa[ex])) / 2.f) ex = ex + 1; }
+            L.ry = 0.f;
+            ey = 1;
+            random = 1.f - L.rng.uniform();
+            float z1 = __ldg(&za[0]), z2 = __ldg(&za[1]), zm = __ldg(&za[g.nz - 2]), zn = __ldg(&za[g.nz - 1]);
+            L.rz = -(z2 - z1) / 2.f + random * ((z2 - z1) / 2.f + (zn - zm) / 2.f + zn);
+            if (L.rz < z1) L.rz = z1;
+            if (L.rz > zn) L.rz = zn;
+            ez = locate_axis(za, g.nz, L.rz);
+            if (ez < g.nz) {             // sic: xAxis(zP) in the z test (:612)
+                if (ez >= 1 && ez <= g.nx && L.rz >= (__ldg(&xa[ez - 1]) + __ldg(&za[ez])) / 2.f) ez = ez + 1;
+            }
+            if (ex < 1) ex = 1;
+            if (ez < 1) ez = 1;
+            L.dx = 0.f; L.dy = 1.f; L.dz = 0.f;
+            if (igp) { L.sx = ex; L.sy = ey; L.sz = ez; } else { L.mx = ex; L.my = ey; L.mz = ez; }
+            if (P.planeDist) atomicAdd(&P.planeDist[(ex - 1) + G(1).nx * (ez - 1)], 1);
+            if (ex > g.nx || ez > g.nz) { fail(L, 24); return; }
+            cell = active_at(g, ex, ey, ez);
+        } else {
+            new_direction(P, L, stellar);
+        }
         L.orgG = L.gP; L.orgC = cell;
         L.nuP = nuP;
         L.planeG = 0;
@@ -448,7 +478,7 @@ struct Transport {
     // tally -> `drop`.  The zero numerator is kept away from the divider (it would take the
     // IEEE slow path and, like any rare branch here, split one lane off the warp for the
     // rest of the step: ncu showed 58 % of the warp trips running a 1-lane straggler).
-    __device__ __forceinline__ void wall(const float *W, int n, float v, float &r, int &iP, int gP, float &dS,
+    __device__ __forceinline__ void wall(const float *W, int n, float v, float &r, int &iP, bool outer, float &dS,
                                          bool &drop, bool &pos)
     {
         pos = v > 1.e-10f;
@@ -465,7 +495,7 @@ struct Transport {
         dS = moving ? d : 1.e35f;
         if (moving && fabsf(d) < 1.e-10f) {          // sitting on the wall: snap and step over (rare,
             r = w;                                   // tiny body: reconverges immediately)
-            if (pos) { if (iP < n) iP = iP + 1; else drop = drop || (gP == 1); }
+            if (pos) { if (iP < n) iP = iP + 1; else drop = drop || outer; }
             else     { if (iP > 1) iP = iP - 1; }
         }
     }
@@ -474,7 +504,7 @@ struct Transport {
     __device__ __forceinline__ void absorb(Lane &L, int packetType)
     {
         count(C_ABS);
-        if (L.istep >= kSafeLimit) { finish(L, FATE_DROPPED); return; }   // :2838-2846
+        if (L.istep >= a.P.safeLimit) { finish(L, FATE_DROPPED); return; }   // :2838-2846
         L.igpp = (L.gP == 1) ? 0 : 1;
         if (L.igpp) { L.sx = L.xP; L.sy = L.yP; L.sz = L.zP; } else { L.mx = L.xP; L.my = L.yP; L.mz = L.zP; }
         L.chType = packetType;
@@ -523,14 +553,16 @@ struct Transport {
             // the reference returns at the first axis found on the outer wall, i.e. before
             // the later axes are looked at; nothing after a `return` is observable
             bool drop = false;
-            wall(g.xWall, g.nx, L.vx, L.rx, L.xP, L.gP, dSx, drop, posx);
-            wall(g.yWall, g.ny, L.vy, L.ry, L.yP, L.gP, dSy, drop, posy);
-            wall(g.zWall, g.nz, L.vz, L.rz, L.zP, L.gP, dSz, drop, posz);
+            // outermost wall of the mother grid: `return` (x,z not in plane mode, :1276,1315,1354)
+            const bool outerY = L.gP == 1, outerXZ = outerY && !P.lgPlane;
+            wall(g.xWall, g.nx, L.vx, L.rx, L.xP, outerXZ, dSx, drop, posx);
+            wall(g.yWall, g.ny, L.vy, L.ry, L.yP, outerY, dSy, drop, posy);
+            wall(g.zWall, g.nz, L.vz, L.rz, L.zP, outerXZ, dSz, drop, posz);
             if (drop) { finish(L, FATE_DROPPED); return; }
             if ((dSx != dSx) | (dSy != dSy) | (dSz != dSz)) { fail(L, 60); return; }
             cell = active_at<DENSE>(g, L.xP, L.yP, L.zP);
             if (!MULTI || cell >= 0) break;
-            if (j >= kSafeLimit) { fail(L, 63); return; }
+            if (j >= a.P.safeLimit) { fail(L, 63); return; }
         }
         const DevGrid &g = G(L.gP);
         // index of (cell, nuP) in the (0:nCells, nbins) tables: the nu-plane offset is constant
@@ -591,7 +623,7 @@ struct Transport {
                 }
                 count(C_SCA);
                 if (!__ldg(&g.canScatter[cell])) { fail(L, 69); return; }
-                if (L.istep >= kSafeLimit) { finish(L, FATE_DROPPED); return; }   // loop ends: :2838
+                if (L.istep >= a.P.safeLimit) { finish(L, FATE_DROPPED); return; }   // loop ends: :2838
                 L.phase = PH_SCATTER;
                 return;
             }
@@ -627,7 +659,9 @@ struct Transport {
             else if (dS == dSz && L.vz < 0.f) L.zP = L.zP - 1;
         }
 
-        if (!MULTI) {
+        if (P.lgPlane) {
+            if (!step_tail_plane(L)) return;
+        } else if (!MULTI) {
             // single grid: every test of :1986-2194, :2417-2540 and :2733-2834 that is true
             // ends in the same escape tally, so they collapse into one predicate
             bool out = (L.rx >= g.xHi) | (L.ry >= g.yHi) | (L.rz >= g.zHi) |
@@ -644,7 +678,59 @@ struct Transport {
         } else {
             if (!step_tail_multi(L)) return;
         }
-        if (L.istep >= kSafeLimit) finish(L, FATE_DROPPED);   // :2838-2846
+        if (L.istep >= a.P.safeLimit) finish(L, FATE_DROPPED);   // :2838-2846
+    }
+
+    // plane-parallel tail of a non-interacting step (:2199-2414, then :2703-2726): mirror at
+    // the x and z faces, escape through the y faces; false = packet left FLY
+    __device__ __forceinline__ bool step_tail_plane(Lane &L)
+    {
+        bool lgReturn = false;
+        const DevGrid &m = G(1);
+        {
+            const DevGrid &c = G(L.gP);
+            if (L.ry <= c.yLo || L.yP < 1) {
+                if (L.gP == 1) { L.yP = 1; lgReturn = true; }
+                else to_mother(L);
+            }
+        }
+        {
+            const DevGrid &c = G(L.gP);
+            if (L.ry > c.yHi || L.yP > c.ny) {
+                if (L.gP == 1) { L.yP = c.ny; lgReturn = true; }
+                else to_mother(L);
+            }
+        }
+        if (L.rx <= m.x1 || L.xP < 1) { L.xP = 1; L.rx = G(L.gP).x1; L.vx = -L.vx; }
+        { const DevGrid &c = G(L.gP); if ((L.rx <= c.xLo || L.xP < 1) && L.gP > 1) to_mother(L); }
+        {
+            const DevGrid &c = G(L.gP);
+            int im = c.nx <= m.nx ? c.nx : m.nx;                 // grid(1)%xAxis(grid(gP)%nx)
+            if (L.rx >= __ldg(&m.xAxis[im - 1]) || L.xP > c.nx) { L.xP = c.nx; L.rx = c.xN; L.vx = -L.vx; }
+        }
+        { const DevGrid &c = G(L.gP); if ((L.rx >= c.xHi || L.xP > c.nx) && L.gP > 1) to_mother(L); }
+        if (L.rz <= m.z1 || L.zP < 1) { L.zP = 1; L.rz = G(L.gP).y1; L.vz = -L.vz; }   // sic: yAxis(1), :2278
+        { const DevGrid &c = G(L.gP); if ((L.rz <= c.zLo || L.zP < 1) && L.gP > 1) to_mother(L); }
+        {
+            const DevGrid &c = G(L.gP);
+            int im = c.nz <= m.nz ? c.nz : m.nz;
+            if (L.rz >= __ldg(&m.zAxis[im - 1]) || L.zP > c.nz) { L.zP = c.nz; L.rz = c.zN; L.vz = -L.vz; }
+        }
+        { const DevGrid &c = G(L.gP); if ((L.rz >= c.zHi || L.zP > c.nz) && L.gP > 1) to_mother(L); }
+        if (lgReturn) { escape(L, FATE_ESCAPED); return false; }
+        if (MULTI && L.gP > 1) {         // leaving the sub-grid (:2703-2726)
+            const DevGrid &s = G(L.gP);
+            if (((L.rx <= s.x1 || L.xP < 1) && L.vx <= 0.f) || ((L.ry <= s.y1 || L.yP < 1) && L.vy <= 0.f) ||
+                ((L.rz <= s.z1 || L.zP < 1) && L.vz <= 0.f) || ((L.rx >= s.xN || L.xP > s.nx) && L.vx >= 0.f) ||
+                ((L.ry >= s.yN || L.yP > s.ny) && L.vy >= 0.f) || ((L.rz >= s.zN || L.zP > s.nz) && L.vz >= 0.f)) to_mother(L);
+        }
+        return true;
+    }
+    __device__ __forceinline__ void to_mother(Lane &L)
+    {
+        L.xP = L.mx; L.yP = L.my; L.zP = L.mz;
+        L.gP = 1;
+        L.igpp = 0;
     }
 
     // multi-grid tail of a non-interacting step (:1986-2834); false = packet left FLY

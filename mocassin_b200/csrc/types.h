@@ -40,7 +40,9 @@ struct DevGrid {
 
 struct DevParams {
     int nGrids, nbins, nStars, nAngleBins, totT, totP, nLines;
-    int lgDust, lgGas, lgSym, lgIso, lgDebug, lgMultistars;
+    int lgDust, lgGas, lgSym, lgIso, lgDebug, lgMultistars, lgPlane;
+    int safeLimit;                   // photon_mod.f90:1187-1192: 500000, or 5000 in plane-parallel mode
+    int *planeDist;                  // planeIonDistribution(grid(1)%nx, grid(1)%nz), plane mode only
     float dTheta, dPhi, R_out, ionEdge1;
     const float *nuArray, *gSca;
     const float *starCdf;            // [(s)*nbins + nu-1], s = 0..nStars

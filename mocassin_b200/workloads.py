@@ -348,3 +348,28 @@ def viewing_angles(n: int = 9, nbins: int = 64, nPhotons: int = 100_000, seed: i
     Nd = np.where(mask, 2.0 / ((cabs[iV] + csca[iV]) * edge), 0.0)
     _dust_tables(model, g, Nd, nu, wid, rng, Tdust3d=np.where(mask, 300.0, 0.0))
     return model
+
+
+def plane_slab(nx: int = 9, ny: int = 17, nz: int = 9, nbins: int = 120, dust: bool = True, Tstar: float = 35000.0,
+               Hden: float = 300.0, nPhotons: int = 100_000, seed: int = 21) -> Model:
+    """Plane-parallel ionisation (`planeIonization` keyword): packets enter through the y=0
+    face along +y, are mirrored at the x and z faces and leave through the y faces
+    (photon_mod.f90:561-646, 2199-2414)."""
+    rng = np.random.default_rng(seed)
+    nu, wid = nu_mesh(nbins)
+    ax = auto_axis(nx, 1.0e17, False)
+    ay = (np.arange(ny, dtype=F32) / F32(ny - 1) * F32(4.0e17)).astype(F32)
+    az = auto_axis(nz, 1.0e17, False)
+    mask = np.ones((nx, ny, nz), dtype=bool)
+    active, nCells = number_active(mask)
+    g = Grid(xAxis=ax, yAxis=ay, zAxis=az, active=active, nCells=nCells)
+    kw = _dust_model_kw() if dust else {}
+    model = _finish_model([g], nu, np.stack([np.zeros(nbins, F32), blackbody_cdf(Tstar, nu, wid)]),
+                          [0.0, 1.0 / nPhotons], [[0.0, 0.0, 0.0]], [star_indices(g, [0.0, 0.0, 0.0]) + [1]],
+                          lgDust=dust, lgGas=True, lgSymmetricXYZ=False, lgPlaneIonization=True, R_out=0.0, **kw)
+    y = np.broadcast_to(ay.astype(np.float64)[None, :, None], (nx, ny, nz))
+    xH0 = np.clip(1.0e-3 * np.exp(y / 6.0e16), 1.0e-3, 1.0)
+    _gas_tables(model, g, np.full((nx, ny, nz), Hden), xH0, nu, wid, rng)
+    if dust:
+        _dust_tables(model, g, np.full((nx, ny, nz), 3.0e-10 * Hden), nu, wid, rng)
+    return model

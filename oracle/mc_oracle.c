@@ -29,8 +29,7 @@
  *      (photon_mod.f90:781,841-843); here it is -1 (the value energyPacketDriver gives
  *      the unused slot of inX/inY/inZ, :107-113), which makes the mother-index
  *      tracker re-locate the packet (:1844-1871) instead of using garbage.
- *  (4) lgPlaneIonization, lg1D (dead: set_input_mod.f90:291-297 aborts) and the
- *      resonance-line packet loop (:180-266) are not restated; they return an error.
+ *  (4) lg1D (dead: set_input_mod.f90:291-297 aborts) is not restated.
  *  (5) Besides the faithful float32 tallies the oracle also keeps order-independent
  *      integer tallies (path length in fixed point, packet counts); these are what the
  *      CUDA path is compared with bit for bit.
@@ -257,12 +256,46 @@ static int init_photon_packet(Ctx *c, Packet *pk, int32_t nuP, vec3 position, ve
     for (int k = 0; k < 2; ++k) { pk->xP[k] = xP[k]; pk->yP[k] = yP[k]; pk->zP[k] = zP[k]; }
 
     if (!lgHG || P->lgIsotropic || pk->lgStellar) {
-        if (pk->lgStellar && P->lgPlaneIonization) ERR_STOP(22); /* not restated */
-        int irepeat;
-        for (irepeat = 1; irepeat <= 1000000; ++irepeat) {
-            pk->direction = random_unit_vector(&c->rng);
-            if (!(pk->direction.x >= 0.f || pk->direction.x < 0.f)) ERR_STOP(23);
-            if (pk->direction.x != 0.f && pk->direction.y != 0.f && pk->direction.z != 0.f) break;
+        if (pk->lgStellar && P->lgPlaneIonization) {
+            /* plane-parallel ionisation: emission from the y=0 face, :561-646 */
+            const OrGrid *g = &c->grids[gP - 1];
+            const float *xa = g->xAxis - 1, *za = g->zAxis - 1;
+            float random = rng_uniform(&c->rng);
+            random = 1.f - random;
+            pk->position.x = -(xa[2] - xa[1]) / 2.f + random * ((xa[2] - xa[1]) / 2.f + (xa[g->nx] - xa[g->nx - 1]) / 2.f + xa[g->nx]);
+            if (pk->position.x < xa[1]) pk->position.x = xa[1];
+            if (pk->position.x > xa[g->nx]) pk->position.x = xa[g->nx];
+            pk->xP[igpi] = locate(g->xAxis, g->nx, pk->position.x);
+            if (pk->xP[igpi] < g->nx) {
+                if (pk->xP[igpi] >= 1 && pk->position.x >= (xa[pk->xP[igpi]] + xa[pk->xP[igpi] + 1]) / 2.f) pk->xP[igpi] = pk->xP[igpi] + 1;
+            }
+            pk->position.y = 0.f;
+            pk->yP[igpi] = 1;
+            random = rng_uniform(&c->rng);
+            random = 1.f - random;
+            pk->position.z = -(za[2] - za[1]) / 2.f + random * ((za[2] - za[1]) / 2.f + (za[g->nz] - za[g->nz - 1]) / 2.f + za[g->nz]);
+            if (pk->position.z < za[1]) pk->position.z = za[1];
+            if (pk->position.z > za[g->nz]) pk->position.z = za[g->nz];
+            pk->zP[igpi] = locate(g->zAxis, g->nz, pk->position.z);
+            if (pk->zP[igpi] < g->nz) {
+                /* sic: xAxis(zP) in the z test, :612 (guarded against indexing outside xAxis) */
+                int zi = pk->zP[igpi];
+                if (zi >= 1 && zi <= g->nx && pk->position.z >= (xa[zi] + za[zi + 1]) / 2.f) pk->zP[igpi] = zi + 1;
+            }
+            if (pk->xP[igpi] < 1) pk->xP[igpi] = 1;
+            if (pk->zP[igpi] < 1) pk->zP[igpi] = 1;
+            pk->direction.x = 0.f; pk->direction.y = 1.f; pk->direction.z = 0.f;
+            if (P->planeIonDistribution) {
+                int32_t *d = &P->planeIonDistribution[(pk->xP[igpi] - 1) + (size_t)c->grids[0].nx * (pk->zP[igpi] - 1)];
+                if (c->atomicMode) __atomic_fetch_add(d, 1, __ATOMIC_RELAXED); else *d += 1;
+            }
+        } else {
+            int irepeat;
+            for (irepeat = 1; irepeat <= 1000000; ++irepeat) {
+                pk->direction = random_unit_vector(&c->rng);
+                if (!(pk->direction.x >= 0.f || pk->direction.x < 0.f)) ERR_STOP(23);
+                if (pk->direction.x != 0.f && pk->direction.y != 0.f && pk->direction.z != 0.f) break;
+            }
         }
         if (P->lgSymmetricXYZ && pk->lgStellar && !P->lgMultistars) {
             if (pk->direction.x < 0.f) pk->direction.x = -pk->direction.x;
@@ -502,8 +535,7 @@ static int path_segment(Ctx *c, Packet *enPacket, int *chTypeIn, vec3 *positionI
     random = rng_uniform(&c->rng);
     passProb = -dm_logf(1.f - random);
 
-    if (P->lgPlaneIonization) ERR_STOP(57);   /* not restated */
-    safeLimit = 500000;
+    if (P->lgPlaneIonization) safeLimit = 5000; else safeLimit = 500000;   /* :1187-1192 */
 
     for (i = 1; i <= safeLimit; ++i) {
         c->segs++;
@@ -548,7 +580,7 @@ static int path_segment(Ctx *c, Packet *enPacket, int *chTypeIn, vec3 *positionI
                     if (fabsf(dSx) < 1.e-10f) { rVec.x = (xa[xP + 1] + xa[xP]) / 2.f; xP = xP + 1; }
                 } else {
                     dSx = (xa[g->nx] - rVec.x) / vHat.x;
-                    if (fabsf(dSx) < 1.e-10f) { rVec.x = xa[g->nx]; if (gP == 1) { c->fateCode = 3; return PS_RETURN; } }
+                    if (fabsf(dSx) < 1.e-10f) { rVec.x = xa[g->nx]; if (!P->lgPlaneIonization && gP == 1) { c->fateCode = 3; return PS_RETURN; } }
                 }
             } else if (vHat.x < -1.e-10f) {
                 if (xP > 1) {
@@ -592,7 +624,7 @@ static int path_segment(Ctx *c, Packet *enPacket, int *chTypeIn, vec3 *positionI
                     if (fabsf(dSz) < 1.e-10f) { rVec.z = (za[zP + 1] + za[zP]) / 2.f; zP = zP + 1; }
                 } else {
                     dSz = (za[g->nz] - rVec.z) / vHat.z;
-                    if (fabsf(dSz) < 1.e-10f) { rVec.z = za[g->nz]; if (gP == 1) { c->fateCode = 3; return PS_RETURN; } }
+                    if (fabsf(dSz) < 1.e-10f) { rVec.z = za[g->nz]; if (!P->lgPlaneIonization && gP == 1) { c->fateCode = 3; return PS_RETURN; } }
                 }
             } else if (vHat.z < -1.e-10f) {
                 if (zP > 1) {
@@ -841,6 +873,58 @@ static int path_segment(Ctx *c, Packet *enPacket, int *chTypeIn, vec3 *positionI
                     xP = enPacket->xP[mp]; yP = enPacket->yP[mp]; zP = enPacket->zP[mp];
                     gP = grid[gP].motherP;
                 }
+                if (lgReturn) {
+                    rc = escape_tally(c, enPacket);
+                    if (rc) return rc;
+                    c->fateCode = 1;
+                    return PS_RETURN;
+                }
+            }
+
+            if (P->lgPlaneIonization) {        /* :2199-2414 */
+                lgReturn = 0;
+#define TO_MOTHER_PLANE() do { xP = enPacket->xP[0]; yP = enPacket->yP[0]; zP = enPacket->zP[0]; gP = 1; igpp = 0; } while (0)
+                if (rVec.y <= grid[gP].yAxis[0] - grid[gP].geoCorrY || yP < 1) {
+                    if (gP == 1) { yP = 1; lgReturn = 1; }
+                    else if (gP > 1) TO_MOTHER_PLANE();
+                    else ERR_STOP(77);
+                }
+                if (rVec.y > grid[gP].yAxis[grid[gP].ny - 1] + grid[gP].geoCorrY || yP > grid[gP].ny) {
+                    if (gP == 1) { yP = grid[gP].ny; lgReturn = 1; }
+                    else if (gP > 1) TO_MOTHER_PLANE();
+                    else ERR_STOP(78);
+                }
+                if (rVec.x <= grid[1].xAxis[0] || xP < 1) {
+                    xP = 1;
+                    rVec.x = grid[gP].xAxis[0];
+                    vHat.x = -vHat.x;
+                }
+                if ((rVec.x <= grid[gP].xAxis[0] - grid[gP].geoCorrX || xP < 1) && gP > 1) TO_MOTHER_PLANE();
+                {
+                    int nxg = grid[gP].nx, im = nxg <= grid[1].nx ? nxg : grid[1].nx;   /* grid(1)%xAxis(grid(gP)%nx) */
+                    if (rVec.x >= grid[1].xAxis[im - 1] || xP > nxg) {
+                        xP = nxg;
+                        rVec.x = grid[gP].xAxis[nxg - 1];
+                        vHat.x = -vHat.x;
+                    }
+                }
+                if ((rVec.x >= grid[gP].xAxis[grid[gP].nx - 1] + grid[gP].geoCorrX || xP > grid[gP].nx) && gP > 1) TO_MOTHER_PLANE();
+                if (rVec.z <= grid[1].zAxis[0] || zP < 1) {
+                    zP = 1;
+                    rVec.z = grid[gP].yAxis[0];            /* sic: yAxis(1), :2278 */
+                    vHat.z = -vHat.z;
+                }
+                if ((rVec.z <= grid[gP].zAxis[0] - grid[gP].geoCorrZ || zP < 1) && gP > 1) TO_MOTHER_PLANE();
+                {
+                    int nzg = grid[gP].nz, im = nzg <= grid[1].nz ? nzg : grid[1].nz;
+                    if (rVec.z >= grid[1].zAxis[im - 1] || zP > nzg) {
+                        zP = nzg;
+                        rVec.z = grid[gP].zAxis[nzg - 1];
+                        vHat.z = -vHat.z;
+                    }
+                }
+                if ((rVec.z >= grid[gP].zAxis[grid[gP].nz - 1] + grid[gP].geoCorrZ || zP > grid[gP].nz) && gP > 1) TO_MOTHER_PLANE();
+#undef TO_MOTHER_PLANE
                 if (lgReturn) {
                     rc = escape_tally(c, enPacket);
                     if (rc) return rc;

@@ -64,6 +64,8 @@ typedef struct OrParams {
     const float *grainAbun;        /* (nDustComp,nSpeciesMax) column major */
     const int32_t *dustComPoint;   /* 1:nDustComp */
     const float *TdustSublime;     /* 1:nSpecies */
+    int32_t *planeIonDistribution; /* (grid(1)%nx, grid(1)%nz) packets emitted per (x,z) of the y=0 face
+                                      in plane-parallel mode (photon_mod.f90:643-646), may be NULL */
 } OrParams;
 
 typedef struct OrCounters {

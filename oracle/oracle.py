@@ -40,7 +40,7 @@ class OrParams(C.Structure):
         ("nuArray", fp), ("gSca", fp), ("viewPointPtheta", ip), ("viewPointPphi", ip),
         ("viewPointTheta", fp), ("viewPointPhi", fp), ("starPosition", fp), ("starIndeces", ip),
         ("deltaE", fp), ("inSpectrumProbDen", fp), ("nSpeciesPart", ip), ("grainAbun", fp),
-        ("dustComPoint", ip), ("TdustSublime", fp)]
+        ("dustComPoint", ip), ("TdustSublime", fp), ("planeIonDistribution", ip)]
 
 
 class OrCounters(C.Structure):
@@ -198,6 +198,8 @@ class Oracle:
         self._ga = _F(m.grainAbun, np.float32); P.grainAbun = _p(self._ga, fp)
         P.dustComPoint = _p(keep(m.dustComPoint, np.int32), ip)
         P.TdustSublime = _p(keep(m.TdustSublime, np.float32), fp)
+        self.planeIonDistribution = np.zeros((m.grids[0].nx, m.grids[0].nz), np.int32, order="F")
+        P.planeIonDistribution = _p(self.planeIonDistribution, ip)
         self.P = P
 
         G = (OrGrid * m.nGrids)()

@@ -13,6 +13,8 @@ CASES = {
     "cube_clumpy_gasdust": (W.synthetic_cube, dict(n=24, nbins=150, clumpy=True, dust=True, nPhotons=10**6), 8000),
     "viewing_angles": (W.viewing_angles, dict(), 20000),
     "viewing_angles_phifree": (W.viewing_angles, dict(phi_free=True), 10000),
+    "plane_slab_gasdust": (W.plane_slab, dict(Hden=30.0), 12000),
+    "plane_slab_gas": (W.plane_slab, dict(dust=False, Hden=30.0), 12000),
 }
 
 

@@ -64,6 +64,9 @@ def _compare(m, n, e, o, iStar=1):
         assert cg[k] == co[k], k
     assert cg["nPackets"] == n
     assert np.array_equal(e.qphot_counts(), o.qphotCounts)
+    if m.lgPlaneIonization:
+        assert np.array_equal(e.plane_distribution(), o.planeIonDistribution)
+        assert o.planeIonDistribution.sum() == n
     dE = float(m.deltaE[iStar])
     want = ["Jste", "escapedPackets"] + (["Jdif", "linePackets"] if m.lgDebug else [])
     for iG in range(1, m.nGrids + 1):
@@ -211,10 +214,10 @@ def test_error_behaviour():
     assert e.energyPacketDriver(1, 1)["nPackets"] == 1  # ragged: fewer packets than a warp
     e.close()
     m2 = W.hii_region()
-    m2.lgPlaneIonization = True
+    m2.lgPlaneIonization = True                       # symmetricXYZ + planeIonization: the reference stops
     with pytest.raises(MocassinError) as ei:
         PacketEngine(m2)
-    assert ei.value.code == -6
+    assert ei.value.code == -2
 
 
 def test_packet_reaching_a_reference_stop_is_reported():
