@@ -300,7 +300,13 @@ def run_b200(args):
     nGlobal = P * world
     dE = float(model.deltaE[1])
 
+    # measured on 2 GPUs: splitting the batch in halves costs more (smaller waves, NCCL sharing
+    # the SMs) than hiding half of the exchange gains -> off by default
+    overlap = world > 1 and os.environ.get("MCB_OVERLAP", "0") == "1"
+
     def step():
+        if overlap:      # exchange of the first half hidden behind the transport of the second
+            return eng.energyPacketDriverOverlapped(1, nGlobal, deltaE=dE)
         c = eng.energyPacketDriver(1, nGlobal, deltaE=dE)
         if world > 1:
             eng.reduce()

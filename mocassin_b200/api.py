@@ -251,45 +251,95 @@ class PacketEngine:
         self._check(self.lib.mcb200_tally_buffer(self.h, iG, which, C.byref(p), C.byref(n)))
         return int(p.value or 0), int(n.value)
 
+    def _exchange(self, tset: int = 0, group=None, async_op: bool = False) -> list:
+        """All-reduce the pending integer tallies of tally set `tset` over ranks (NCCL over
+        NVLink, replacing MPI_ALLREDUCE at iteration_mod.f90:627-659): first the touched-bin
+        flags (tiny max-reduce), then only the flagged nu-planes -- int64 path lengths, uint32
+        packet counts (summed as int32 bit patterns).  Returns the NCCL work handles when
+        async_op (the transfers then overlap whatever the library stream does next)."""
+        import torch
+        import torch.distributed as dist
+
+        m = self.model
+        dev = self._device_index()
+        base = 16 * tset
+        works = []
+        for iG in range(1, m.nGrids + 1):
+            nR = m.grids[iG - 1].nCells + 1
+            fptr, fn = self.tally_buffer(iG, base + 4)
+            flags = _as_cuda_tensor(fptr, fn, "<i4", dev)
+            dist.all_reduce(flags, op=dist.ReduceOp.MAX, group=group)
+            ranges = _touched_ranges(flags.cpu().numpy())
+            self.last_exchange_planes = (sum(b - a + 1 for a, b in ranges), m.nbins + 1, len(ranges))
+            whichs = [0, 1] + ([2] if (m.lgDebug and tset == 0) else [])
+            for w in whichs:
+                ptr, n = self.tally_buffer(iG, base + w)
+                if n == 0:
+                    continue
+                t = _as_cuda_tensor(ptr, n, "<i8" if w in (0, 2) else "<i4", dev)
+                for p0, p1 in ranges:
+                    if w == 1:
+                        for ang in range(m.nAngleBins + 1):
+                            off = nR * (p0 + (m.nbins + 1) * ang)
+                            works.append(dist.all_reduce(t[off:off + (p1 - p0 + 1) * nR], op=dist.ReduceOp.SUM,
+                                                         group=group, async_op=async_op))
+                    elif p1 >= max(p0, 1):
+                        q0 = max(p0, 1)
+                        works.append(dist.all_reduce(t[(q0 - 1) * nR:p1 * nR], op=dist.ReduceOp.SUM, group=group,
+                                                     async_op=async_op))
+            if m.lgDebug and tset == 0:
+                ptr, n = self.tally_buffer(iG, 3)
+                if n:
+                    works.append(dist.all_reduce(_as_cuda_tensor(ptr, n, "<i4", dev), op=dist.ReduceOp.SUM,
+                                                 group=group, async_op=async_op))
+            if m.lgPlaneIonization and tset == 0 and iG == 1:
+                ptr, n = self.tally_buffer(1, 5)
+                if n:
+                    works.append(dist.all_reduce(_as_cuda_tensor(ptr, n, "<i4", dev), op=dist.ReduceOp.SUM,
+                                                 group=group, async_op=async_op))
+        return [w for w in works if w is not None] if async_op else []
+
     def reduce(self, group=None):
-        """Sum the pending integer tallies over ranks (NCCL allreduce over NVLink,
-        replacing MPI_ALLREDUCE at iteration_mod.f90:627-659) and fold them into the
-        float32 estimators.  Exact integer sums -> identical bits on every rank and for
-        every rank count."""
+        """Sum the pending integer tallies over ranks and fold them into the float32
+        estimators.  Exact integer sums -> identical bits on every rank and for every rank
+        count."""
         if self.nranks > 1:
             import torch
-            import torch.distributed as dist
 
-            m = self.model
-            dev = self._device_index()
-            for iG in range(1, m.nGrids + 1):
-                nR = m.grids[iG - 1].nCells + 1
-                # 1) which frequency bins were touched on any rank (tiny max-reduce)
-                fptr, fn = self.tally_buffer(iG, 4)
-                flags = _as_cuda_tensor(fptr, fn, "<i4", dev)
-                dist.all_reduce(flags, op=dist.ReduceOp.MAX, group=group)
-                ranges = _touched_ranges(flags.cpu().numpy())
-                self.last_exchange_planes = (sum(b - a + 1 for a, b in ranges), m.nbins + 1, len(ranges))
-                # 2) sum only those nu-planes: int64 path lengths, uint32 counts (as int32 bits)
-                for w in [0, 1] + ([2] if m.lgDebug else []):
-                    ptr, n = self.tally_buffer(iG, w)
-                    if n == 0:
-                        continue
-                    t = _as_cuda_tensor(ptr, n, "<i8" if w in (0, 2) else "<i4", dev)
-                    for p0, p1 in ranges:
-                        if w == 1:
-                            for ang in range(m.nAngleBins + 1):
-                                off = nR * (p0 + (m.nbins + 1) * ang)
-                                dist.all_reduce(t[off:off + (p1 - p0 + 1) * nR], op=dist.ReduceOp.SUM, group=group)
-                        elif p1 >= max(p0, 1):
-                            q0 = max(p0, 1)
-                            dist.all_reduce(t[(q0 - 1) * nR:p1 * nR], op=dist.ReduceOp.SUM, group=group)
-                if m.lgDebug:
-                    ptr, n = self.tally_buffer(iG, 3)
-                    if n:
-                        dist.all_reduce(_as_cuda_tensor(ptr, n, "<i4", dev), op=dist.ReduceOp.SUM, group=group)
+            self._exchange(0, group)
             torch.cuda.synchronize()
         self._check(self.lib.mcb200_reduce(self.h))
+
+    def energyPacketDriverOverlapped(self, iStar: int, n: int, deltaE: Optional[float] = None, group=None) -> dict:
+        """energyPacketDriver + exchange + fold for nranks > 1 with the exchange hidden behind
+        the transport: this rank's packets are run in two halves into two tally sets; while
+        the second half is transported the first half's tallies are all-reduced on NCCL's
+        stream.  The sets are merged as integers before the single fold, so the result is
+        bit-identical to the plain path."""
+        import torch
+
+        if self.nranks == 1 or self.model.lgDebug:
+            c = self.energyPacketDriver(iStar, n, deltaE=deltaE)
+            self.reduce(group)
+            return c
+        self.set_option("parts", 2)
+        try:
+            self.set_option("part", 0); self.set_option("tally_set", 0)
+            c0 = self.energyPacketDriver(iStar, n, deltaE=deltaE)
+            works = self._exchange(0, group, async_op=True)
+            self.set_option("part", 1); self.set_option("tally_set", 1)
+            c1 = self.energyPacketDriver(iStar, n, deltaE=deltaE)
+            for w in works:
+                w.wait()
+            self._exchange(1, group)
+            torch.cuda.synchronize()
+        finally:
+            self.set_option("parts", 1); self.set_option("tally_set", 0)
+        self._check(self.lib.mcb200_reduce(self.h))
+        out = dict(c0)
+        for k, v in c1.items():
+            out[k] = out[k] + v
+        return out
 
     def _device_index(self):
         import torch

@@ -25,6 +25,8 @@ cudaError_t launch_fold_j(unsigned long long *Q, float *J, const float *dV, int 
                           double lenUnit, float deltaE, int blocks, cudaStream_t s);
 cudaError_t launch_fold_count(unsigned int *Q, float *E, size_t total, float deltaE, int blocks,
                               cudaStream_t s);
+cudaError_t launch_merge_sets(unsigned long long *J0, unsigned long long *J1, size_t nJ, unsigned int *E0,
+                              unsigned int *E1, size_t nE, int *f0, int *f1, int nf, int blocks, cudaStream_t s);
 cudaError_t wf_launch_event(const WfArgs &w, bool multi, int ev, int blocks, cudaStream_t s);
 cudaError_t wf_launch_fly(const WfArgs &w, bool multi, int blocks, cudaStream_t s);
 cudaError_t wf_launch_sort(const WfArgs &w, bool multi, int numSMs, cudaStream_t s);
@@ -99,6 +101,11 @@ struct GridState {
     DevBuf<unsigned long long> JsteQ, JdifQ;
     DevBuf<unsigned int> escQ, lineQ;
     DevBuf<int> nuTouched;
+    // second tally set (option "tally_set"=1): lets the caller all-reduce one half of a call's
+    // tallies while the other half is still being transported (overlap of the exchange)
+    DevBuf<unsigned long long> JsteQ2;
+    DevBuf<unsigned int> escQ2;
+    DevBuf<int> nuTouched2;
     DevBuf<float> Jste, Jdif, esc, linePk;
     bool haveOpacity = false, havePdf = false;
 };
@@ -112,6 +119,9 @@ struct mcb200_ctx {
     cudaStream_t copyStream = nullptr;    // async PDF upload (option async_pdfs): overlaps wave 0
     cudaEvent_t pdfReady = nullptr;
     bool asyncPdfs = false, pdfPending = false;
+    int tallySet = 0;                     // tally set new transport calls write to
+    bool pending2 = false;                // set 1 holds tallies not yet merged into set 0
+    int partIndex = 0, partCount = 1;     // sub-range of this rank's share (option part / parts)
     DevBuf<int> pdfBad;                   // deferred monotonicity verdicts, one per grid
     int numSMs = 0;
     bool haveCfg = false;
@@ -253,6 +263,7 @@ int sync_grids(mcb200_ctx *ctx)
         d.canScatter = g.canScatter.p;
         d.JsteQ = g.JsteQ.p; d.JdifQ = g.JdifQ.p; d.escQ = g.escQ.p; d.lineQ = g.lineQ.p;
         d.nuTouched = g.nuTouched.p;
+        if (ctx->tallySet == 1) { d.JsteQ = g.JsteQ2.p; d.escQ = g.escQ2.p; d.nuTouched = g.nuTouched2.p; }
     }
     CU(ctx->dGrids.upload(ctx->hGrids.data(), nG, ctx->stream));
     CU(cudaStreamSynchronize(ctx->stream));
@@ -281,6 +292,17 @@ int ensure_estimators(mcb200_ctx *ctx, GridState &g)
     return MCB200_OK;
 }
 
+int ensure_second_set(mcb200_ctx *ctx, GridState &g)
+{
+    size_t ts = tsize(ctx, g), es = esize(ctx, g);
+    if (g.JsteQ2.n == ts) return MCB200_OK;
+    CU(g.JsteQ2.alloc(ts)); CU(g.JsteQ2.zero(ctx->stream));
+    CU(g.escQ2.alloc(es)); CU(g.escQ2.zero(ctx->stream));
+    CU(g.nuTouched2.alloc(ctx->cfg.nbins + 1)); CU(g.nuTouched2.zero(ctx->stream));
+    ctx->gridsDirty = true;
+    return MCB200_OK;
+}
+
 // contiguous runs [first,last] of touched frequency bins (gaps of <= 2 bins are bridged)
 std::vector<std::pair<int, int>> touched_ranges(const std::vector<int> &flag)
 {
@@ -300,6 +322,16 @@ int fold_pending(mcb200_ctx *ctx)
     int blocks = ctx->numSMs * 8;
     const int nb = ctx->cfg.nbins;
     int launches = 0;
+    if (ctx->pending2) {
+        // integer merge first (exact), then ONE fold: fold(Q0)+fold(Q1) would round differently
+        for (auto &g : ctx->grids) {
+            if (!g.JsteQ2.p) continue;
+            CU(launch_merge_sets(g.JsteQ.p, g.JsteQ2.p, g.JsteQ.n, g.escQ.p, g.escQ2.p, g.escQ.n,
+                                 g.nuTouched.p, g.nuTouched2.p, nb + 1, blocks, ctx->stream));
+            ++launches;
+        }
+        ctx->pending2 = false;
+    }
     for (auto &g : ctx->grids) {
         size_t nR = (size_t)g.nCells + 1;
         double lenUnit = std::ldexp(1.0, g.lenExp);
@@ -487,7 +519,10 @@ int run_transport(mcb200_ctx *ctx, int iStar, int difGrid, const int32_t *cellLo
         if (!g.havePdf) return fail(ctx, MCB200_ESTATE, "re-emission PDFs of grid %d not set", i + 1);
         int rc = ensure_estimators(ctx, g);
         if (rc) return rc;
+        if (ctx->tallySet == 1) { rc = ensure_second_set(ctx, g); if (rc) return rc; }
     }
+    if (ctx->tallySet == 1 && (cfg.lgDebug || ctx->nranks == 1))
+        return fail(ctx, MCB200_ESTATE, "tally_set=1 is for multi-rank, non-debug runs");
     // a previous call with a different deltaE must be folded first (single rank), or
     // reduced by the caller (multi rank)
     if (ctx->pending) {
@@ -502,6 +537,11 @@ int run_transport(mcb200_ctx *ctx, int iStar, int difGrid, const int32_t *cellLo
     int64_t load = nGlobal / ctx->nranks, rest = nGlobal % ctx->nranks;
     int64_t mine = load + (ctx->rank < rest ? 1 : 0);
     int64_t first = (int64_t)ctx->rank * load + (ctx->rank < rest ? ctx->rank : rest);
+    if (ctx->partCount > 1) {            // contiguous sub-range of this rank's share
+        int64_t pl = mine / ctx->partCount, pr = mine % ctx->partCount, pi = ctx->partIndex;
+        first += pi * pl + (pi < pr ? pi : pr);
+        mine = pl + (pi < pr ? 1 : 0);
+    }
 
     TransportArgs a{};
     DevParams &P = a.P;
@@ -630,6 +670,7 @@ int run_transport(mcb200_ctx *ctx, int iStar, int difGrid, const int32_t *cellLo
         out->nWaves = ctx->lastWaves;
     }
     ctx->pending = true;
+    if (ctx->tallySet == 1) ctx->pending2 = true;
     ctx->pendingDeltaE = deltaE;
     if (herr) return fail(ctx, MCB200_EPACKET, "a packet hit reference stop condition %d (see oracle/mc_oracle.c ERR_STOP codes)", herr);
     if (ctx->nranks == 1) {
@@ -1017,7 +1058,9 @@ int mcb200_zero_estimators(mcb200_ctx *ctx)
         CU(g.JdifQ.zero(ctx->stream)); CU(g.Jdif.zero(ctx->stream));
         CU(g.lineQ.zero(ctx->stream)); CU(g.linePk.zero(ctx->stream));
         CU(g.nuTouched.zero(ctx->stream));
+        CU(g.JsteQ2.zero(ctx->stream)); CU(g.escQ2.zero(ctx->stream)); CU(g.nuTouched2.zero(ctx->stream));
     }
+    ctx->pending2 = false;
     CU(ctx->planeDist.zero(ctx->stream));
     CU(cudaStreamSynchronize(ctx->stream));
     ctx->pending = false;
@@ -1064,6 +1107,16 @@ int mcb200_tally_buffer(mcb200_ctx *ctx, int32_t iG, int32_t which, void **devPt
     int rc = ensure_estimators(ctx, *g);
     if (rc) return rc;
     CU(cudaStreamSynchronize(ctx->stream));
+    if (which >= 16) {                   // second tally set
+        rc = ensure_second_set(ctx, *g);
+        if (rc) return rc;
+        CU(cudaStreamSynchronize(ctx->stream));
+        if (which == 16) { *devPtr = g->JsteQ2.p; *count = (int64_t)g->JsteQ2.n; }
+        else if (which == 17) { *devPtr = g->escQ2.p; *count = (int64_t)g->escQ2.n; }
+        else if (which == 20) { *devPtr = g->nuTouched2.p; *count = (int64_t)g->nuTouched2.n; }
+        else return fail(ctx, MCB200_EINVAL, "bad tally selector %d", which);
+        return MCB200_OK;
+    }
     if (which == 0 || which == 2) {
         DevBuf<unsigned long long> *b = which == 0 ? &g->JsteQ : &g->JdifQ;
         *devPtr = b->p; *count = (int64_t)b->n;
@@ -1175,6 +1228,16 @@ int mcb200_set_option(mcb200_ctx *ctx, const char *name, int64_t value)
     if (!strcmp(name, "step_budget")) { ctx->stepBudget = (int)value; return MCB200_OK; }
     if (!strcmp(name, "tail")) { ctx->tailThreshold = value; return MCB200_OK; }
     if (!strcmp(name, "async_pdfs")) { ctx->asyncPdfs = value != 0; return MCB200_OK; }
+    if (!strcmp(name, "tally_set")) {
+        if (value != 0 && value != 1) return fail(ctx, MCB200_EINVAL, "tally_set must be 0 or 1");
+        if (ctx->tallySet != (int)value) { ctx->tallySet = (int)value; ctx->gridsDirty = true; }
+        return MCB200_OK;
+    }
+    if (!strcmp(name, "parts")) { ctx->partCount = value < 1 ? 1 : (int)value; ctx->partIndex = 0; return MCB200_OK; }
+    if (!strcmp(name, "part")) {
+        if (value < 0 || value >= ctx->partCount) return fail(ctx, MCB200_EINVAL, "part out of range");
+        ctx->partIndex = (int)value; return MCB200_OK;
+    }
     if (!strcmp(name, "agg_steps")) { ctx->aggSteps = (int)value; return MCB200_OK; }
     if (!strcmp(name, "batch")) { ctx->batch = (int)value; return MCB200_OK; }
     return fail(ctx, MCB200_EINVAL, "unknown option %s", name);

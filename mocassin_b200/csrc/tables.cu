@@ -94,6 +94,24 @@ __global__ void fold_count_kernel(unsigned int *__restrict__ Q, float *__restric
     }
 }
 
+// merge the second tally set into the first (exact integer adds) and clear it
+__global__ void merge_sets_kernel(unsigned long long *__restrict__ J0, unsigned long long *__restrict__ J1, size_t nJ,
+                                  unsigned int *__restrict__ E0, unsigned int *__restrict__ E1, size_t nE,
+                                  int *__restrict__ f0, int *__restrict__ f1, int nf)
+{
+    size_t i0 = (size_t)blockIdx.x * blockDim.x + threadIdx.x, stride = (size_t)gridDim.x * blockDim.x;
+    for (size_t i = i0; i < nJ; i += stride) { unsigned long long v = J1[i]; if (v) { J0[i] += v; J1[i] = 0ull; } }
+    for (size_t i = i0; i < nE; i += stride) { unsigned int v = E1[i]; if (v) { E0[i] += v; E1[i] = 0u; } }
+    for (size_t i = i0; i < (size_t)nf; i += stride) { if (f1[i]) { f0[i] = 1; f1[i] = 0; } }
+}
+
+cudaError_t launch_merge_sets(unsigned long long *J0, unsigned long long *J1, size_t nJ, unsigned int *E0,
+                              unsigned int *E1, size_t nE, int *f0, int *f1, int nf, int blocks, cudaStream_t s)
+{
+    merge_sets_kernel<<<blocks, 256, 0, s>>>(J0, J1, nJ, E0, E1, nE, f0, f1, nf);
+    return cudaGetLastError();
+}
+
 cudaError_t launch_fold_j(unsigned long long *Q, float *J, const float *dV, int nRows, size_t total,
                           double lenUnit, float deltaE, int blocks, cudaStream_t s)
 {

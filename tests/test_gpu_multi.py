@@ -21,7 +21,7 @@ def _free_port():
     return p
 
 
-def _worker(rank, world, port, name, n, q):
+def _worker(rank, world, port, name, n, q, overlap=False):
     sys.path.insert(0, ROOT)
     sys.path.insert(0, os.path.join(ROOT, "tests"))
     import torch
@@ -37,7 +37,11 @@ def _worker(rank, world, port, name, n, q):
     m, _ = make(name)
     e = PacketEngine(m, device=rank, rank=rank, nranks=world, seed=12345)
     e.upload_iteration_inputs()
-    e.lucy_transport([n])
+    if overlap:
+        e.zero_estimators()
+        e.energyPacketDriverOverlapped(1, n)
+    else:
+        e.lucy_transport([n])
     out = [e.fetch(iG) for iG in range(1, m.nGrids + 1)]
     q.put((rank, out))
     dist.barrier()
@@ -45,8 +49,9 @@ def _worker(rank, world, port, name, n, q):
     dist.destroy_process_group()
 
 
+@pytest.mark.parametrize("overlap", [False, True])
 @pytest.mark.parametrize("name", ["multigrid_sym", "cube_clumpy_gasdust"])
-def test_nccl_allreduce_matches_single_gpu(name):
+def test_nccl_allreduce_matches_single_gpu(name, overlap):
     import torch
     import torch.multiprocessing as mp
 
@@ -60,7 +65,7 @@ def test_nccl_allreduce_matches_single_gpu(name):
     ctx = mp.get_context("spawn")
     q = ctx.Queue()
     port = _free_port()
-    procs = [ctx.Process(target=_worker, args=(r, 2, port, name, n, q)) for r in range(2)]
+    procs = [ctx.Process(target=_worker, args=(r, 2, port, name, n, q, overlap)) for r in range(2)]
     for p in procs:
         p.start()
     got = dict(q.get(timeout=600) for _ in range(2))
