@@ -172,6 +172,38 @@ int mcb200_set_pdfs(mcb200_ctx *ctx, int32_t iG, const float *recPDF, const floa
 int mcb200_set_dust_state(mcb200_ctx *ctx, int32_t iG, const float *Tdust,
                           const int32_t *dustAbunIndex);
 
+/* ---- dust-only closure of the iteration ("next" rows) ------------------
+ * With these three calls a dust-only model (lgDust and not lgGas) iterates without the
+ * estimators or the emission PDFs leaving the device:
+ *     transport -> [reduce] -> mcb200_dust_update -> mcb200_dust_pdf -> transport ...
+ *
+ * mcb200_set_dust_tables: once, after set_dust_species and set_xsec and BEFORE
+ *   set_dust_state (which then keeps a device copy of Tdust).  widFlx(nbins),
+ *   grainWeight(nSizes), dustAbsXsecP(nSpecies,nSizes) (1-based offsets into xSecArray),
+ *   dustEmIntegral(nSpecies,nSizes,nTemps) (dust_mod / xSec_mod; grid_mod.f90 tables).
+ *
+ * mcb200_dust_update: replaces the dust-only branch of updateCell (update_mod.f90:308-334)
+ *   and getDustT (:1836-1945) for all cells of grid iG.  Reads the device-resident Jste
+ *   (Jdif in debug mode) with the host scaling of iteration_mod.f90:705-724 applied on the
+ *   fly (*1e-9, /8 for symmetricXYZ), updates the device Tdust and the sublimation flags of
+ *   the next transport.  Optional outputs: Tdust(0:nSpeciesMax,0:nSizes,0:nCells),
+ *   lgConverged(0:nCells), and the number of converged cells.  A grain whose absorption
+ *   integral is below dustEmIntegral(.,.,1) gets 1 K (the reference's lgTalk branch; without
+ *   lgTalk the reference reads dustEmIntegral(.,.,0), out of bounds).  In multi-rank runs every
+ *   rank holds the reduced Jste and updates all cells itself: no exchange (the reference
+ *   splits cells over ranks and all-reduces TdustTemp, iteration_mod.f90:797-870).
+ *
+ * mcb200_dust_pdf: replaces setDustPDF (emission_mod.f90:1313-1387; quantum heating
+ *   excluded) for all cells: builds the re-emission CDF rows of grid iG from the device
+ *   Tdust, in place of mcb200_set_pdfs.  dustPDF (0:nCells,nbins), if not NULL, receives a
+ *   copy in the reference's layout. */
+int mcb200_set_dust_tables(mcb200_ctx *ctx, const float *widFlx, const float *grainWeight,
+                           const int32_t *dustAbsXsecP, int32_t nSpecies,
+                           const float *dustEmIntegral, int32_t nTemps);
+int mcb200_dust_update(mcb200_ctx *ctx, int32_t iG, float XHILimit, float *Tdust,
+                       int32_t *lgConverged, int64_t *nConverged);
+int mcb200_dust_pdf(mcb200_ctx *ctx, int32_t iG, float *dustPDF);
+
 /* ---- the hot path ------------------------------------------------------------------ */
 
 /* Zero Jste, Jdif, linePackets, escapedPackets of all grids

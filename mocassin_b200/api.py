@@ -176,6 +176,38 @@ class PacketEngine:
                 self.h, i, _fp(_f(g.Tdust)),
                 _ip(_f(g.dustAbunIndex, I32)) if g.dustAbunIndex is not None else None))
 
+    # -- dust-only closure (update_mod.f90 getDustT, emission_mod.f90 setDustPDF) --------
+    def set_dust_tables(self, widFlx, grainWeight, dustAbsXsecP, dustEmIntegral):
+        """Tables of the dust closure; call after set_xsec and before set_dust_state.
+        ``dustAbsXsecP`` (nSpecies, nSizes) 1-based offsets into xSecArray,
+        ``dustEmIntegral`` (nSpecies, nSizes, nTemps), both in Fortran order."""
+        ap = _f(dustAbsXsecP, I32)
+        em = _f(dustEmIntegral)
+        self._check(self.lib.mcb200_set_dust_tables(
+            self.h, _fp(_f(widFlx)), _fp(_f(grainWeight)), _ip(ap), int(ap.shape[0]), _fp(em), int(em.shape[2])))
+
+    def getDustT(self, iG: int, XHILimit: float):
+        """Dust-only updateCell over every cell of grid iG (update_mod.f90:308-334,
+        :1836-1945) from the device-resident Jste.  Returns (Tdust, lgConverged, nConverged);
+        also stored on the host grid as the reference does."""
+        g = self.model.grids[iG - 1]
+        T = np.zeros_like(_f(g.Tdust), order="F")
+        conv = np.zeros(g.nCells + 1, dtype=I32)
+        n = C.c_int64(0)
+        self._check(self.lib.mcb200_dust_update(self.h, iG, float(XHILimit), _fp(T), _ip(conv), C.byref(n)))
+        g.Tdust = T
+        g.lgConverged = conv
+        return T, conv, int(n.value)
+
+    def setDustPDF(self, iG: int, fetch: bool = False):
+        """emissionDriver's dust-only work for every cell of grid iG (emission_mod.f90:1313-1387),
+        from the device Tdust into the device re-emission tables.  ``fetch`` returns dustPDF
+        (0:nCells, nbins)."""
+        g = self.model.grids[iG - 1]
+        out = np.zeros((g.nCells + 1, self.model.nbins), dtype=F32, order="F") if fetch else None
+        self._check(self.lib.mcb200_dust_pdf(self.h, iG, _fp(out) if fetch else None))
+        return out
+
     def upload_iteration_inputs(self):
         self.set_opacity()
         self.set_pdfs()

@@ -14,8 +14,8 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libmocassin_b200.so")
-SOURCES = ["capi.cu", "transport.cu", "wavefront.cu", "tables.cu"]
-HEADERS = ["types.h", "detmath.cuh", "philox.cuh", "transport_core.cuh", "wf_rec.cuh", os.path.join("..", "..", "include", "mcb200.h")]
+SOURCES = ["capi.cu", "transport.cu", "wavefront.cu", "tables.cu", "dust.cu"]
+HEADERS = ["types.h", "detmath.cuh", "philox.cuh", "transport_core.cuh", "wf_rec.cuh", "locate.cuh", "dust.h", os.path.join("..", "..", "include", "mcb200.h")]
 
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",

@@ -4,6 +4,7 @@
 #include "types.h"
 #include "detmath.cuh"
 #include "philox.cuh"
+#include "dust.h"
 
 #include <cuda_runtime.h>
 
@@ -107,6 +108,9 @@ struct GridState {
     DevBuf<unsigned int> escQ2;
     DevBuf<int> nuTouched2;
     DevBuf<float> Jste, Jdif, esc, linePk;
+    // dust closure (mcb200_dust_update / mcb200_dust_pdf): device copy of the dust state
+    DevBuf<float> Tdust;
+    DevBuf<int> dustAbun, lgConverged;
     bool haveOpacity = false, havePdf = false;
 };
 
@@ -139,6 +143,12 @@ struct mcb200_ctx {
     std::vector<int> nSpeciesPart, dustComPoint;
     std::vector<float> grainAbun, TdustSublime;
     bool haveDustSpecies = false;
+    // dust closure tables (mcb200_set_dust_tables)
+    DevBuf<float> widFlx, grainWeight, emT, dGrainAbun, dSublime;
+    DevBuf<int> absP, dSpeciesPart, dComPoint;
+    DevBuf<unsigned long long> nConv;
+    int nSpeciesTot = 0, nTemps = 0;
+    bool haveDustTables = false;
     // work buffers
     DevBuf<unsigned long long> nextPacket, counters, qphot;
     DevBuf<int> errFlag, fates, flag;
@@ -696,6 +706,7 @@ __global__ void detmath_kernel(int which, const float *in, float *out, long long
     case 2: dm_sincosf(in[i], s, c); out[i] = c; break;
     case 3: out[i] = dm_acosf(in[i]); break;
     case 4: out[i] = dm_atanf(in[i]); break;
+    case 5: out[i] = dm_expf(in[i]); break;
     default: out[i] = 0.f;
     }
 }
@@ -1040,7 +1051,129 @@ int mcb200_set_dust_state(mcb200_ctx *ctx, int32_t iG, const float *Tdust, const
     }
     bool re = (g->canScatter.n != can.size());
     CU(g->canScatter.upload(can.data(), can.size(), ctx->stream));
+    if (ctx->haveDustTables) {
+        // the dust closure updates this state in place on the device
+        CU(g->Tdust.upload(Tdust, s0 * s1 * ((size_t)g->nCells + 1), ctx->stream));
+        if (c.lgMultiDustChemistry) CU(g->dustAbun.upload(dustAbunIndex, (size_t)g->nCells + 1, ctx->stream));
+    }
     CU(cudaStreamSynchronize(ctx->stream));
+    if (re) ctx->gridsDirty = true;
+    return MCB200_OK;
+}
+
+int mcb200_set_dust_tables(mcb200_ctx *ctx, const float *widFlx, const float *grainWeight,
+                           const int32_t *dustAbsXsecP, int32_t nSpeciesTot, const float *dustEmIntegral,
+                           int32_t nTemps)
+{
+    NEED_CTX();
+    if (!ctx->haveCfg || !ctx->haveSpectra) return fail(ctx, MCB200_ESTATE, "set_config and set_spectra first");
+    if (!ctx->haveDustSpecies) return fail(ctx, MCB200_ESTATE, "set_dust_species first");
+    if (!ctx->xSec.p) return fail(ctx, MCB200_ESTATE, "mcb200_set_xsec first");
+    const mcb200_config &c = ctx->cfg;
+    if (!widFlx || !grainWeight || !dustAbsXsecP || !dustEmIntegral || nSpeciesTot < 1 || nTemps < 2)
+        return fail(ctx, MCB200_EINVAL, "bad dust tables");
+    if (nSpeciesTot < c.nSpeciesMax) return fail(ctx, MCB200_EINVAL, "nSpecies %d < nSpeciesMax %d", nSpeciesTot, c.nSpeciesMax);
+    if ((size_t)nSpeciesTot != ctx->TdustSublime.size())
+        return fail(ctx, MCB200_EINVAL, "nSpecies %d differs from set_dust_species (%d)", nSpeciesTot, (int)ctx->TdustSublime.size());
+    size_t nP = (size_t)nSpeciesTot * c.nSizes;
+    for (size_t k = 0; k < nP; ++k)
+        if (dustAbsXsecP[k] < 1 || (int64_t)dustAbsXsecP[k] + c.nbins - 1 > (int64_t)ctx->xSec.n)
+            return fail(ctx, MCB200_EINVAL, "dustAbsXsecP entry %d out of xSecArray", (int)k + 1);
+    // dustEmIntegral(nSpecies, nSizes, nTemps) -> contiguous temperature rows; must ascend for locate
+    std::vector<float> emT(nP * (size_t)nTemps);
+    for (size_t k = 0; k < nP; ++k)
+        for (int t = 0; t < nTemps; ++t) {
+            float v = dustEmIntegral[k + nP * (size_t)t];
+            emT[k * (size_t)nTemps + t] = v;
+            if (t > 0 && !(v >= emT[k * (size_t)nTemps + t - 1]))
+                return fail(ctx, MCB200_ETABLE, "dustEmIntegral(%d,%d,:) is not non-decreasing", (int)(k % nSpeciesTot) + 1, (int)(k / nSpeciesTot) + 1);
+        }
+    CU(ctx->widFlx.upload(widFlx, c.nbins, ctx->stream));
+    CU(ctx->grainWeight.upload(grainWeight, c.nSizes, ctx->stream));
+    CU(ctx->absP.upload(dustAbsXsecP, nP, ctx->stream));
+    CU(ctx->emT.upload(emT.data(), emT.size(), ctx->stream));
+    CU(ctx->dGrainAbun.upload(ctx->grainAbun.data(), ctx->grainAbun.size(), ctx->stream));
+    CU(ctx->dSublime.upload(ctx->TdustSublime.data(), ctx->TdustSublime.size(), ctx->stream));
+    CU(ctx->dSpeciesPart.upload(ctx->nSpeciesPart.data(), ctx->nSpeciesPart.size(), ctx->stream));
+    CU(ctx->dComPoint.upload(ctx->dustComPoint.data(), ctx->dustComPoint.size(), ctx->stream));
+    CU(ctx->nConv.alloc(1));
+    CU(cudaStreamSynchronize(ctx->stream));
+    ctx->nSpeciesTot = nSpeciesTot;
+    ctx->nTemps = nTemps;
+    ctx->haveDustTables = true;
+    return MCB200_OK;
+}
+
+namespace {
+int dust_args(mcb200_ctx *ctx, GridState *g, DustArgs &A)
+{
+    const mcb200_config &c = ctx->cfg;
+    if (!ctx->haveDustTables) return fail(ctx, MCB200_ESTATE, "mcb200_set_dust_tables first");
+    if (c.lgGas || !c.lgDust) return fail(ctx, MCB200_EUNSUPPORTED, "the dust closure is the dust-only branch (lgDust and not lgGas)");
+    if (!g->Tdust.p) return fail(ctx, MCB200_ESTATE, "mcb200_set_dust_state (after set_dust_tables) first");
+    A = DustArgs{};
+    A.nCells = g->nCells; A.nb = c.nbins; A.nSpeciesMax = c.nSpeciesMax; A.nSizes = c.nSizes;
+    A.nDustComp = c.nDustComp; A.nSpeciesTot = ctx->nSpeciesTot; A.nTemps = ctx->nTemps;
+    A.multiChem = c.lgMultiDustChemistry; A.lgDebug = c.lgDebug; A.sym = c.lgSymmetricXYZ;
+    A.nuArray = ctx->nuArray.p; A.widFlx = ctx->widFlx.p; A.xSec = ctx->xSec.p; A.absP = ctx->absP.p;
+    A.nSpeciesPart = ctx->dSpeciesPart.p; A.dustComPoint = ctx->dComPoint.p; A.dustAbunIndex = g->dustAbun.p;
+    A.grainAbun = ctx->dGrainAbun.p; A.grainWeight = ctx->grainWeight.p; A.TdustSublime = ctx->dSublime.p;
+    A.emT = ctx->emT.p; A.Tdust = g->Tdust.p; A.canScatter = g->canScatter.p; A.nConv = ctx->nConv.p;
+    return MCB200_OK;
+}
+}  // namespace
+
+int mcb200_dust_update(mcb200_ctx *ctx, int32_t iG, float XHILimit, float *Tdust, int32_t *lgConverged,
+                       int64_t *nConverged)
+{
+    NEED_CTX();
+    GridState *g = grid_of(ctx, iG);
+    if (!g || !g->set) return fail(ctx, MCB200_ESTATE, "grid %d not set", iG);
+    DustArgs A;
+    int rc = dust_args(ctx, g, A);
+    if (rc) return rc;
+    if (ctx->pending) return fail(ctx, MCB200_ESTATE, "tallies pending: call mcb200_reduce first");
+    rc = ensure_estimators(ctx, *g);
+    if (rc) return rc;
+    CU(g->lgConverged.alloc((size_t)g->nCells + 1));
+    CU(g->lgConverged.zero(ctx->stream));
+    CU(ctx->nConv.zero(ctx->stream));
+    A.Jste = g->Jste.p; A.Jdif = g->Jdif.p; A.lgConverged = g->lgConverged.p; A.XHILimit = XHILimit;
+    if (A.lgDebug && !A.Jdif) return fail(ctx, MCB200_ESTATE, "Jdif missing in debug mode");
+    CU(launch_dust_update(A, ctx->stream));
+    unsigned long long n = 0;
+    CU(cudaMemcpyAsync(&n, ctx->nConv.p, 8, cudaMemcpyDeviceToHost, ctx->stream));
+    if (Tdust) CU(cudaMemcpyAsync(Tdust, g->Tdust.p, g->Tdust.n * sizeof(float), cudaMemcpyDeviceToHost, ctx->stream));
+    if (lgConverged) CU(cudaMemcpyAsync(lgConverged, g->lgConverged.p, g->lgConverged.n * sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+    CU(cudaStreamSynchronize(ctx->stream));
+    if (nConverged) *nConverged = (int64_t)n;
+    return MCB200_OK;
+}
+
+int mcb200_dust_pdf(mcb200_ctx *ctx, int32_t iG, float *dustPDF)
+{
+    NEED_CTX();
+    GridState *g = grid_of(ctx, iG);
+    if (!g || !g->set) return fail(ctx, MCB200_ESTATE, "grid %d not set", iG);
+    DustArgs A;
+    int rc = dust_args(ctx, g, A);
+    if (rc) return rc;
+    size_t ts = tsize(ctx, *g);
+    bool re = (g->pdfT.n != ts);
+    if (ctx->pdfPending) { CU(cudaStreamSynchronize(ctx->copyStream)); ctx->pdfPending = false; }
+    CU(g->pdfT.alloc(ts));
+    A.pdfT = g->pdfT.p;
+    CU(launch_dust_pdf(A, ctx->numSMs, ctx->stream));
+    if (dustPDF) {
+        // back to the reference layout (0:nCells, nbins), cell index fastest
+        CU(g->stage.alloc(ts));
+        CU(launch_transpose_pdf(g->pdfT.p, g->stage.p, ctx->cfg.nbins, g->nCells + 1, ctx->stream));
+        CU(cudaMemcpyAsync(dustPDF, g->stage.p, ts * sizeof(float), cudaMemcpyDeviceToHost, ctx->stream));
+        CU(cudaStreamSynchronize(ctx->stream));
+        g->stage.release();
+    }
+    CU(cudaStreamSynchronize(ctx->stream));
+    g->havePdf = true;
     if (re) ctx->gridsDirty = true;
     return MCB200_OK;
 }

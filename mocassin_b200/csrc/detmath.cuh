@@ -14,6 +14,7 @@
 //           r^16 (Horner in r^2); quadrant q mod 4
 //   atan  : |t|>1 -> 1/t;  t>tan(pi/8) -> (t-1)/(t+1);  odd Taylor series to u^27
 //   acos  : 2*atan(sqrt((1-x)/(1+x))), acos(x<=-1)=pi, acos(x>=1)=0
+//   exp   : x = k*ln2 + r; Taylor to r^13; scale by 2^k
 #pragma once
 #include <cstdint>
 
@@ -119,5 +120,36 @@ __device__ __forceinline__ float dm_acosf(float xf)
     if (x <= -1.0) return (float)MCB_PI;
     return (float)(2.0 * dm_atan_d(sqrt((1.0 - x) / (1.0 + x))));
 }
+
+// exp: x = k*ln2 + r, |r| <= ln2/2; Taylor series of exp(r) to r^13; 2^k by exponent
+// arithmetic in two exact steps.  x < -708 -> 0, x > 709 -> inf.
+__device__ __forceinline__ double dm_exp_d(double x)
+{
+    if (x < -708.0) return 0.0;
+    if (x > 709.0) return __longlong_as_double(0x7ff0000000000000ll);
+    double t = x * 1.4426950408889634074;
+    int k = (int)(t >= 0.0 ? t + 0.5 : t - 0.5);
+    double r = x - (double)k * MCB_LN2;
+    double p = 1.0 / 6227020800.0;
+    p = p * r + 1.0 / 479001600.0;
+    p = p * r + 1.0 / 39916800.0;
+    p = p * r + 1.0 / 3628800.0;
+    p = p * r + 1.0 / 362880.0;
+    p = p * r + 1.0 / 40320.0;
+    p = p * r + 1.0 / 5040.0;
+    p = p * r + 1.0 / 720.0;
+    p = p * r + 1.0 / 120.0;
+    p = p * r + 1.0 / 24.0;
+    p = p * r + 1.0 / 6.0;
+    p = p * r + 0.5;
+    p = p * r + 1.0;
+    p = p * r + 1.0;
+    int k1 = k / 2, k2 = k - k1;
+    double s1 = __longlong_as_double((long long)(k1 + 1023) << 52);
+    double s2 = __longlong_as_double((long long)(k2 + 1023) << 52);
+    return p * s1 * s2;
+}
+
+__device__ __forceinline__ float dm_expf(float x) { return (float)dm_exp_d((double)x); }
 
 }  // namespace mcb

@@ -4,6 +4,7 @@
 #pragma once
 #include "types.h"
 #include "detmath.cuh"
+#include "locate.cuh"
 #include "philox.cuh"
 
 #include <cuda_runtime.h>
@@ -47,21 +48,6 @@ __device__ __forceinline__ int active_at(const DevGrid &g, int x, int y, int z)
     if (DENSE || g.dense) return 1 + (z - 1) + g.nz * ((y - 1) + g.ny * (x - 1));
     // nx*ny*nz < 2^31 (checked at upload): 32-bit index arithmetic
     return __ldg(&g.active[(x - 1) + g.nx * ((y - 1) + g.ny * (z - 1))]);
-}
-
-// interpolation_mod.f90:48-81 for an ascending axis
-__device__ __forceinline__ int locate_axis(const float *xa, int n, float x)
-{
-    if (x > __ldg(&xa[n - 1])) return n;
-    if (x < __ldg(&xa[0])) return 0;
-    int lo = 0, hi = n;                  // first 0-based index with xa > x
-    while (lo < hi) {
-        int mid = (lo + hi) >> 1;
-        if (__ldg(&xa[mid]) > x) hi = mid; else lo = mid + 1;
-    }
-    // no element > x  <=>  x == xa(n): minloc over an empty mask is 0 -> max(-1,1) = 1
-    if (lo >= n) return 1;
-    return lo > 1 ? lo : 1;              // (1-based first) - 1 = lo
 }
 
 // getNu2 (photon_mod.f90:720-764) on a contiguous non-decreasing CDF row

@@ -241,6 +241,98 @@ def dust_shell(n: int = 16, nbins: int = 215, Tstar: float = 2500.0, Rout: float
     return model
 
 
+def wid_flx(nu: np.ndarray) -> np.ndarray:
+    """widFlx of initCartesianGrid (grid_mod.f90:333-338)."""
+    w = np.empty_like(nu, dtype=F32)
+    w[0] = nu[1] - nu[0]
+    w[1:-1] = (nu[2:] - nu[:-2]) / F32(2.0)
+    w[-1] = nu[-1] - nu[-2]
+    return w
+
+
+def dust_closure(n: int = 9, nbins: int = 120, nPhotons: int = 200_000, Lstar: float = 38.26, Tstar: float = 2500.0,
+                 Rout: float = 2.18e17, Rin: float = 2.18e16, tauV: float = 1.0, multiChem: bool = True,
+                 T0: float = 100.0, nTemps: int = 3000, seed: int = 23):
+    """Dust-only shell with a full dust description, for the device closure of the iteration
+    (getDustT + setDustPDF): 3 grain species in 2 chemistry components ([sp1,sp2] and [sp3]),
+    3 grain sizes.  Returns (model, tables) where tables holds xSecArray, dustAbsXsecP,
+    dustScaXsecP, grainWeight, widFlx and dustEmIntegral (dust_mod.f90:155-181)."""
+    nu, wid = nu_mesh(nbins, nuMin=1.0e-4, nuMax=15.0, edges=())
+    widFlx = wid_flx(nu)
+    ax = auto_axis(n, Rout, True)
+    r = _radius(ax, ax, ax)
+    mask = (r >= Rin) & (r <= Rout)
+    active, nCells = number_active(mask)
+    g = Grid(xAxis=ax, yAxis=ax.copy(), zAxis=ax.copy(), active=active, nCells=nCells)
+    sizes = np.array([0.05, 0.16, 0.5])
+    nSizes, nSpecies = 3, 3
+    w = sizes ** -2.5
+    grainWeight = (w / w.sum()).astype(F32)
+    qscale = np.array([1.0, 0.55, 1.6])               # per-species absorption efficiency factor
+    xs = [np.zeros(1, F32)]                           # entry 1 unused: offsets are 1-based
+    absP = np.zeros((nSpecies, nSizes), dtype=I32, order="F")
+    scaP = np.zeros((nSpecies, nSizes), dtype=I32, order="F")
+    pos = 2
+    gs = None
+    for nS in range(nSpecies):
+        for ai in range(nSizes):
+            cabs, csca, gsc = dust_optics(nu, float(sizes[ai]))
+            gs = gsc if ai == 1 else gs
+            absP[nS, ai] = pos; xs.append((cabs * qscale[nS]).astype(F32)); pos += nbins
+            scaP[nS, ai] = pos; xs.append(csca.astype(F32)); pos += nbins
+    xSecArray = np.concatenate(xs).astype(F32)
+    nSpeciesPart = np.array([2, 1], dtype=I32)
+    dustComPoint = np.array([1, 3], dtype=I32)
+    grainAbun = np.array([[0.6, 0.4], [1.0, 0.0]], dtype=F32, order="F")
+    TdustSublime = np.array([1400.0, 1200.0, 900.0], dtype=F32)
+    # dustEmIntegral(nS,ai,T) = 4 h fr1Ryd sum_i Cabs(i) (B_nu(T)/h) widFlx(i), T = 1..nTemps K
+    T = np.arange(1, nTemps + 1, dtype=np.float64)
+    x = HC_RYD_K * nu.astype(np.float64)[None, :] / T[:, None]
+    bb = (0.5250229 / 6.6262e-27) * nu.astype(np.float64)[None, :] ** 3 / np.expm1(np.minimum(x, 700.0))
+    em = np.zeros((nSpecies, nSizes, nTemps), dtype=F32, order="F")
+    for nS in range(nSpecies):
+        for ai in range(nSizes):
+            cabs = xSecArray[absP[nS, ai] - 1: absP[nS, ai] - 1 + nbins].astype(np.float64)
+            em[nS, ai, :] = ((bb * (cabs * 3.28984e15 * widFlx.astype(np.float64))[None, :]).sum(axis=1)
+                             * 6.6262e-27 * 4.0).astype(F32)
+    comp3d = np.where(r < 0.55 * Rout, 1, 2) if multiChem else np.ones_like(r, dtype=np.int64)
+    # mean cross-sections per component for the opacity
+    def mean_xs(P, comp):
+        out = np.zeros(nbins, dtype=np.float64)
+        dcp = dustComPoint[comp - 1]
+        for k in range(nSpeciesPart[comp - 1]):
+            for ai in range(nSizes):
+                o = P[dcp - 1 + k, ai] - 1
+                out += grainAbun[comp - 1, k] * grainWeight[ai] * xSecArray[o:o + nbins].astype(np.float64)
+        return out
+    iV = int(np.argmin(np.abs(nu - 0.1657)))
+    ext1 = mean_xs(absP, 1) + mean_xs(scaP, 1)
+    n0 = tauV / (ext1[iV] * Rin * (1.0 - Rin / Rout))
+    Nd3 = np.where(mask, n0 * (Rin / np.maximum(r, Rin)) ** 2, 0.0)
+    nd = _per_cell(active, Nd3, nCells)
+    comp = _per_cell(active, comp3d, nCells, dtype=I32)
+    comp[0] = 1
+    g.Ndust = nd
+    g.dustAbunIndex = comp
+    g.absOpac = np.zeros((nCells + 1, nbins), dtype=F32, order="F")
+    g.scaOpac = np.zeros((nCells + 1, nbins), dtype=F32, order="F")
+    for c in (1, 2):
+        sel = comp == c
+        g.absOpac[sel, :] = (nd[sel, None] * mean_xs(absP, c)[None, :]).astype(F32)
+        g.scaOpac[sel, :] = (nd[sel, None] * mean_xs(scaP, c)[None, :]).astype(F32)
+    g.opacity = (g.absOpac + g.scaOpac).astype(F32, order="F")
+    g.Tdust = np.zeros((2 + 1, nSizes + 1, nCells + 1), dtype=F32, order="F")
+    g.Tdust[:, :, 1:] = F32(T0)
+    model = _finish_model([g], nu, np.stack([np.zeros(nbins, F32), blackbody_cdf(Tstar, nu, wid)]),
+                          [0.0, Lstar / nPhotons], [[0.0, 0.0, 0.0]], [[1, 1, 1, 1]],
+                          lgDust=True, lgGas=False, lgSymmetricXYZ=True, R_out=Rout, gSca=gs,
+                          lgMultiDustChemistry=multiChem, nSpeciesMax=2, nSizes=nSizes, nSpeciesPart=nSpeciesPart,
+                          grainAbun=grainAbun, dustComPoint=dustComPoint, TdustSublime=TdustSublime)
+    tables = dict(xSecArray=xSecArray, dustAbsXsecP=absP, dustScaXsecP=scaP, grainWeight=grainWeight,
+                  widFlx=widFlx, dustEmIntegral=em)
+    return model, tables
+
+
 def multigrid(n: int = 16, nsub: int = 11, nbins: int = 600, Tstar: float = 80000.0, Rin: float = 1.0e15,
               Rout: float = 1.0e18, sub_hi: float = 2.0e17, nPhotons: int = 1_000_000, Lstar: float = 1.0,
               symmetric: bool = True, seed: int = 13) -> Model:

@@ -142,4 +142,38 @@ static inline float dm_acosf(float xf)
     return (float)a;
 }
 
+/* exp: x = k*ln2 + r, |r| <= ln2/2, k = nearest integer to x/ln2; exp(r) by its Taylor
+ * series to r^13 (Horner); 2^k applied by exponent arithmetic.  x < -708 -> 0, x > 709 -> inf. */
+static inline double dm_exp_d(double x)
+{
+    if (x < -708.0) return 0.0;
+    if (x > 709.0) return INFINITY;
+    double t = x * 1.4426950408889634074;             /* 1/ln2 */
+    int k = (int)(t >= 0.0 ? t + 0.5 : t - 0.5);
+    double r = x - (double)k * DM_LN2;
+    double p = 1.0 / 6227020800.0;                    /* 1/13! */
+    p = p * r + 1.0 / 479001600.0;
+    p = p * r + 1.0 / 39916800.0;
+    p = p * r + 1.0 / 3628800.0;
+    p = p * r + 1.0 / 362880.0;
+    p = p * r + 1.0 / 40320.0;
+    p = p * r + 1.0 / 5040.0;
+    p = p * r + 1.0 / 720.0;
+    p = p * r + 1.0 / 120.0;
+    p = p * r + 1.0 / 24.0;
+    p = p * r + 1.0 / 6.0;
+    p = p * r + 0.5;
+    p = p * r + 1.0;
+    p = p * r + 1.0;
+    /* scale by 2^k in two exact steps (k in [-1022, 1024)) */
+    int k1 = k / 2, k2 = k - k1;
+    uint64_t b1 = (uint64_t)(k1 + 1023) << 52, b2 = (uint64_t)(k2 + 1023) << 52;
+    double s1, s2;
+    memcpy(&s1, &b1, 8);
+    memcpy(&s2, &b2, 8);
+    return p * s1 * s2;
+}
+
+static inline float dm_expf(float x) { return (float)dm_exp_d((double)x); }
+
 #endif /* ORACLE_DETMATH_H */

@@ -1362,6 +1362,105 @@ void oracle_opacity(const OrOpacityIn *in, float *opacityOut, float *scaOut, flo
 }
 
 /* ------------------------------------------------------------------------- */
+/* dust-only closure: getFlux, setDustPDF, getDustT                            */
+/* ------------------------------------------------------------------------- */
+/* continuum_mod.f90:359-416, cShape 'blackbody' */
+static float get_flux(float energy, float temperature)
+{
+    const float hPlanck = 6.6262e-27f, hcRyd_k = 157893.94f;
+    float constant = 0.5250229f / hPlanck;
+    if (hcRyd_k * energy / temperature > 86.f) {
+        /* Wien: real*real*real*real * exp(dble(..)) -> double product, rounded on assignment */
+        float pre = constant * energy * energy * energy;
+        return (float)((double)pre * dm_exp_d((double)(-hcRyd_k * energy / temperature)));
+    }
+    float denominator = dm_expf(hcRyd_k * energy / temperature) - 1.f;
+    if (denominator <= 0.f) return 3.32154e-6f * energy * energy * temperature / hPlanck;
+    return constant * energy * energy * energy / denominator;
+}
+float oracle_get_flux(float energy, float temperature) { return get_flux(energy, temperature); }
+
+#define TDUST(in, T, nS, ai, cell) (T)[(size_t)(nS) + (size_t)((in)->nSpeciesMax + 1) * ((size_t)(ai) + (size_t)((in)->nSizes + 1) * (size_t)(cell))]
+
+void oracle_dust_pdf(const OrDustIn *in, const float *Tdust, float *dustPDF)
+{
+    const int nR = in->nCells + 1, nb = in->nbins;
+    const float *xs = in->xSecArray - 1;
+    for (size_t i = 0; i < (size_t)nR * nb; ++i) dustPDF[i] = 0.f;
+    for (int cell = 1; cell <= in->nCells; ++cell) {
+        int nspE = in->lgMultiDustChemistry ? in->dustAbunIndex[cell] : 1;
+        if (nspE < 1 || nspE > in->nDustComp) continue;
+        int dcp = in->dustComPoint[nspE - 1];
+        for (int n = 1; n <= in->nSpeciesPart[nspE - 1]; ++n)
+            for (int ai = 1; ai <= in->nSizes; ++ai) {
+                float treal = TDUST(in, Tdust, n, ai, cell);
+                if (treal > 0.f && treal < in->TdustSublime[dcp - 1 + n - 1]) {
+                    int ap = in->dustAbsXsecP[(size_t)(n + dcp - 1 - 1) + (size_t)in->nSpeciesTot * (size_t)(ai - 1)];
+                    float ga = in->grainAbun[(size_t)(nspE - 1) + (size_t)in->nDustComp * (size_t)(n - 1)];
+                    for (int i = 1; i <= nb; ++i) {
+                        float bb = get_flux(in->nuArray[i - 1], treal);
+                        size_t o = (size_t)(i - 1) * nR + cell;
+                        dustPDF[o] = dustPDF[o] + xs[ap + i - 1] * bb * in->widFlx[i - 1] * in->grainWeight[ai - 1] * ga;
+                    }
+                }
+            }
+        for (int i = 2; i <= nb; ++i) {
+            size_t o = (size_t)(i - 1) * nR + cell;
+            dustPDF[o] = dustPDF[o - nR] + dustPDF[o];
+        }
+        float last = dustPDF[(size_t)(nb - 1) * nR + cell];
+        for (int i = 1; i <= nb; ++i) {
+            size_t o = (size_t)(i - 1) * nR + cell;
+            dustPDF[o] = dustPDF[o] / last;
+        }
+        dustPDF[(size_t)(nb - 1) * nR + cell] = 1.f;
+    }
+}
+
+void oracle_dust_update(const OrDustIn *in, const float *Jste, const float *Jdif, float XHILimit,
+                        float *Tdust, int32_t *lgConverged)
+{
+    const int nR = in->nCells + 1, nb = in->nbins, nT = in->nTemps;
+    const float *xs = in->xSecArray - 1;
+    const float Pi = 3.141592654f;
+    float *radField = (float *)malloc(sizeof(float) * nb);
+    float *row = (float *)malloc(sizeof(float) * nT);
+    for (int cell = 1; cell <= in->nCells; ++cell) {
+        int nspU = in->lgMultiDustChemistry ? in->dustAbunIndex[cell] : 1;
+        float XOldHI = TDUST(in, Tdust, 0, 0, cell);
+        for (int i = 0; i < nb; ++i) {
+            size_t o = (size_t)i * nR + cell;
+            radField[i] = (in->lgDebug && Jdif) ? (Jste[o] + Jdif[o]) / Pi : Jste[o] / Pi;
+        }
+        for (int nS = 0; nS <= in->nSpeciesMax; ++nS)
+            for (int ai = 0; ai <= in->nSizes; ++ai) TDUST(in, Tdust, nS, ai, cell) = 0.f;
+        if (nspU >= 1 && nspU <= in->nDustComp) {
+            for (int nS = 1; nS <= in->nSpeciesPart[nspU - 1]; ++nS) {
+                for (int ai = 1; ai <= in->nSizes; ++ai) {
+                    float dustAbsIntegral = 0.f;
+                    int ap = in->dustAbsXsecP[(size_t)(nS - 1) + (size_t)in->nSpeciesTot * (size_t)(ai - 1)];   /* sic: local nS */
+                    for (int i = 1; i <= nb; ++i) dustAbsIntegral = dustAbsIntegral + xs[ap + i - 1] * radField[i - 1];
+                    for (int t = 0; t < nT; ++t)
+                        row[t] = in->dustEmIntegral[(size_t)(nS - 1) + (size_t)in->nSpeciesTot * ((size_t)(ai - 1) + (size_t)in->nSizes * (size_t)t)];
+                    int iT = locate(row, nT, dustAbsIntegral);
+                    float T;
+                    if (iT <= 0) T = 1.f;
+                    else if (iT >= nT) T = (float)nT;
+                    else T = (float)iT + (dustAbsIntegral - row[iT - 1]) * ((float)(iT + 1) - (float)iT) / (row[iT] - row[iT - 1]);
+                    TDUST(in, Tdust, nS, ai, cell) = T;
+                    TDUST(in, Tdust, nS, 0, cell) = TDUST(in, Tdust, nS, 0, cell) + T * in->grainWeight[ai - 1];
+                }
+                float ga = in->grainAbun[(size_t)(nspU - 1) + (size_t)in->nDustComp * (size_t)(nS - 1)];
+                TDUST(in, Tdust, 0, 0, cell) = TDUST(in, Tdust, 0, 0, cell) + TDUST(in, Tdust, nS, 0, cell) * ga;
+            }
+        }
+        float deltaXHI = (TDUST(in, Tdust, 0, 0, cell) - XOldHI) / XOldHI;
+        lgConverged[cell] = (fabsf(deltaXHI) <= XHILimit) ? 1 : 0;
+    }
+    free(radField); free(row);
+}
+
+/* ------------------------------------------------------------------------- */
 /* unit-test hooks                                                            */
 /* ------------------------------------------------------------------------- */
 void oracle_philox(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3, uint32_t k0, uint32_t k1, uint32_t *out4)
@@ -1418,6 +1517,7 @@ void oracle_detmath(int32_t which, const float *in, float *out, int64_t n)
         case 2: dm_sincosf(in[i], &s, &c); out[i] = c; break;
         case 3: out[i] = dm_acosf(in[i]); break;
         case 4: out[i] = dm_atanf(in[i]); break;
+        case 5: out[i] = dm_expf(in[i]); break;
         default: out[i] = 0.f;
         }
     }

@@ -136,6 +136,34 @@ typedef struct OrOpacityIn {
 } OrOpacityIn;
 void oracle_opacity(const OrOpacityIn *in, float *opacity, float *scaOpac, float *absOpac);
 
+/* Dust-only closure of the Lucy iteration ("next" rows of SURVEY.md 8f):
+ *  oracle_dust_pdf:    setDustPDF (emission_mod.f90:1313-1387, non-quantum-heating branch)
+ *                      for every active cell: dustPDF(cell,:) = normalised running sum of
+ *                      Cabs * B_nu(Tdust) * widFlx * grainWeight * grainAbun
+ *  oracle_dust_update: the dust-only branch of updateCell (update_mod.f90:308-334) with
+ *                      getDustT (:1836-1945): Tdust from sum_nu Cabs*J/pi by inverse lookup in
+ *                      dustEmIntegral, weighted means, lgConverged from |dT/T| <= XHILimit.
+ *                      Jste is the array the host holds at that point, i.e. after the scaling
+ *                      of iteration_mod.f90:705-724.  getDustT indexes dustAbsXsecP and
+ *                      dustEmIntegral with the component-local species number (sic).  A cell
+ *                      whose absorption integral lies below dustEmIntegral(.,.,1) makes the
+ *                      reference read dustEmIntegral(.,.,0) (out of bounds, :1915-1919) unless
+ *                      lgTalk is set; here it gets the lgTalk value, 1 K.
+ * getFlux is continuum_mod.f90:359-416 ('blackbody') with detmath's exp. */
+typedef struct OrDustIn {
+    int32_t nCells, nbins, nSpeciesMax, nSizes, nDustComp, nSpeciesTot, nTemps;
+    int32_t lgMultiDustChemistry, lgDebug;
+    const float *nuArray, *widFlx, *xSecArray;
+    const int32_t *dustAbsXsecP;      /* (nSpeciesTot, nSizes) */
+    const int32_t *nSpeciesPart, *dustComPoint, *dustAbunIndex;
+    const float *grainAbun, *grainWeight, *TdustSublime;
+    const float *dustEmIntegral;      /* (nSpeciesTot, nSizes, nTemps) */
+} OrDustIn;
+void oracle_dust_pdf(const OrDustIn *in, const float *Tdust, float *dustPDF);
+void oracle_dust_update(const OrDustIn *in, const float *Jste, const float *Jdif, float XHILimit,
+                        float *Tdust, int32_t *lgConverged);
+float oracle_get_flux(float energy, float temperature);
+
 /* unit-test hooks */
 void oracle_philox(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3,
                    uint32_t k0, uint32_t k1, uint32_t *out4);

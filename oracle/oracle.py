@@ -299,3 +299,69 @@ class Oracle:
         if "linePacketsQ" in o:
             res["linePackets"] = np.asfortranarray((o["linePacketsQ"].astype(np.float32) * np.float32(deltaE)).astype(np.float32))
         return res
+
+
+class OrDustIn(C.Structure):
+    _fields_ = [(n, C.c_int32) for n in (
+        "nCells", "nbins", "nSpeciesMax", "nSizes", "nDustComp", "nSpeciesTot", "nTemps",
+        "lgMultiDustChemistry", "lgDebug")] + [
+        ("nuArray", fp), ("widFlx", fp), ("xSecArray", fp), ("dustAbsXsecP", ip),
+        ("nSpeciesPart", ip), ("dustComPoint", ip), ("dustAbunIndex", ip),
+        ("grainAbun", fp), ("grainWeight", fp), ("TdustSublime", fp), ("dustEmIntegral", fp)]
+
+
+def _dust_in(model, nCells, tables, dustAbunIndex, keep):
+    def A(a, dt):
+        a = np.asfortranarray(a, dtype=dt)
+        keep.append(a)
+        return a
+
+    I = OrDustIn()
+    ap = A(tables["dustAbsXsecP"], np.int32)
+    em = A(tables["dustEmIntegral"], np.float32)
+    I.nCells, I.nbins, I.nSpeciesMax, I.nSizes = nCells, model.nbins, model.nSpeciesMax, model.nSizes
+    I.nDustComp, I.nSpeciesTot, I.nTemps = int(model.nSpeciesPart.shape[0]), int(ap.shape[0]), int(em.shape[2])
+    I.lgMultiDustChemistry, I.lgDebug = int(model.lgMultiDustChemistry), int(model.lgDebug)
+    I.nuArray = _p(A(model.nuArray, np.float32), fp); I.widFlx = _p(A(tables["widFlx"], np.float32), fp)
+    I.xSecArray = _p(A(tables["xSecArray"], np.float32), fp); I.dustAbsXsecP = _p(ap, ip)
+    I.nSpeciesPart = _p(A(model.nSpeciesPart, np.int32), ip); I.dustComPoint = _p(A(model.dustComPoint, np.int32), ip)
+    I.dustAbunIndex = _p(A(dustAbunIndex, np.int32), ip) if dustAbunIndex is not None else ip()
+    I.grainAbun = _p(A(model.grainAbun, np.float32), fp); I.grainWeight = _p(A(tables["grainWeight"], np.float32), fp)
+    I.TdustSublime = _p(A(model.TdustSublime, np.float32), fp); I.dustEmIntegral = _p(em, fp)
+    return I
+
+
+def dust_pdf(model, grid, tables):
+    """oracle_dust_pdf (setDustPDF over all cells) -> dustPDF (0:nCells, nbins)."""
+    lib = load()
+    keep = []
+    I = _dust_in(model, grid.nCells, tables, grid.dustAbunIndex, keep)
+    T = np.asfortranarray(grid.Tdust, dtype=np.float32)
+    out = np.zeros((grid.nCells + 1, model.nbins), np.float32, order="F")
+    lib.oracle_dust_pdf.argtypes = [C.POINTER(OrDustIn), fp, fp]
+    lib.oracle_dust_pdf.restype = None
+    lib.oracle_dust_pdf(C.byref(I), _p(T, fp), _p(out, fp))
+    return out
+
+
+def dust_update(model, grid, tables, Jste, XHILimit, Jdif=None):
+    """oracle_dust_update (dust-only updateCell + getDustT over all cells); Jste is the
+    host-scaled estimator.  Returns (Tdust, lgConverged); the grid is not modified."""
+    lib = load()
+    keep = []
+    I = _dust_in(model, grid.nCells, tables, grid.dustAbunIndex, keep)
+    T = np.array(grid.Tdust, dtype=np.float32, order="F", copy=True)
+    conv = np.zeros(grid.nCells + 1, np.int32)
+    J = np.asfortranarray(Jste, dtype=np.float32)
+    Jd = np.asfortranarray(Jdif, dtype=np.float32) if Jdif is not None else None
+    lib.oracle_dust_update.argtypes = [C.POINTER(OrDustIn), fp, fp, C.c_float, fp, ip]
+    lib.oracle_dust_update.restype = None
+    lib.oracle_dust_update(C.byref(I), _p(J, fp), _p(Jd, fp) if Jd is not None else fp(), float(XHILimit), _p(T, fp), _p(conv, ip))
+    return T, conv
+
+
+def get_flux(energy, temperature):
+    lib = load()
+    lib.oracle_get_flux.argtypes = [C.c_float, C.c_float]
+    lib.oracle_get_flux.restype = C.c_float
+    return float(lib.oracle_get_flux(float(energy), float(temperature)))

@@ -31,7 +31,8 @@ def ctx(cuda_lib):
     cuda_lib.mcb200_destroy(h)
 
 
-@pytest.mark.parametrize("which,lo,hi", [(0, 2.0 ** -24, 1.0), (1, -7.0, 7.0), (2, -7.0, 7.0), (3, -1.0, 1.0), (4, -1e4, 1e4)])
+@pytest.mark.parametrize("which,lo,hi", [(0, 2.0 ** -24, 1.0), (1, -7.0, 7.0), (2, -7.0, 7.0), (3, -1.0, 1.0), (4, -1e4, 1e4),
+                                         (5, -100.0, 88.0)])
 def test_device_detmath_is_bit_identical_to_oracle(cuda_lib, oracle_lib, ctx, which, lo, hi):
     rng = np.random.default_rng(which + 10)
     x = rng.uniform(lo, hi, 1 << 20).astype(np.float32)

@@ -44,7 +44,7 @@ def test_uniforms_are_24bit_in_unit_interval(oracle_lib):
 
 @pytest.mark.parametrize("which,fn,lo,hi", [
     (0, np.log, 2.0 ** -24, 1.0), (1, np.sin, -7.0, 7.0), (2, np.cos, -7.0, 7.0),
-    (3, np.arccos, -1.0, 1.0), (4, np.arctan, -1.0e6, 1.0e6)])
+    (3, np.arccos, -1.0, 1.0), (4, np.arctan, -1.0e6, 1.0e6), (5, np.exp, -87.0, 88.0)])
 def test_detmath_within_one_ulp_of_libm(oracle_lib, which, fn, lo, hi):
     rng = np.random.default_rng(which)
     x = rng.uniform(lo, hi, 200000).astype(np.float32)
