@@ -246,11 +246,27 @@ int mcb200_transport_reslines(mcb200_ctx *ctx, int32_t iStar, float deltaE, mcb2
  * only those nu-planes of the tallies can be non-zero, so an exchange may max-reduce the
  * flags first and then sum only the flagged planes -- plane nu of JsteQ is the contiguous
  * run [(nu-1)*(nCells+1), nu*(nCells+1)), plane (nu,ang) of escapedQ starts at
- * (nCells+1)*(nu + (nbins+1)*ang)). */
+ * (nCells+1)*(nu + (nbins+1)*ang)); 5 planeIonDistribution (int32); 6 sedQ (uint64
+ * (nbins+1)*(nAngleBins+1), iG ignored; see mcb200_fetch_sed, option "sed_local");
+ * 16, 17, 20 = buffers 0, 1, 4 of the second tally set (option "tally_set"). */
 int mcb200_tally_buffer(mcb200_ctx *ctx, int32_t iG, int32_t which, void **devPtr, int64_t *count);
 /* After the allreduce: fold the (now global) integer tallies of the last transport
  * call into the float32 estimators. No-op when nothing is pending. */
 int mcb200_reduce(mcb200_ctx *ctx);
+
+/* SED(1:nbins, 0:nAngleBins) = sum over grids and cells of escapedPackets(i, freq, imu):
+ * the reduction at the head of writeSED (output_mod.f90:2561-2568), done on the device so the
+ * (cell, nu, angle) array never has to leave the GPU for the SED.  Raw sums in the same sense
+ * as mcb200_fetch_estimators (before the host's /8 of iteration_mod.f90:719 and writeSED's own
+ * *8, *4 and Jy conversion, which stay on the host).  Each transport call contributes
+ * float(packets escaped in (freq, imu)) * deltaE -- the integer count is exact and independent
+ * of order and rank count; the reference adds deltaE packet by packet in float32.
+ * counts (nullable) receives the cumulative integer counts.  Zeroed by mcb200_zero_estimators.
+ * Multi-rank: with option "sed_local"=1 the per-call counts are taken from this rank's own
+ * escapes at the end of mcb200_transport and exposed as tally buffer 6 (uint64,
+ * (nbins+1)*(nAngleBins+1)); the caller all-reduces that instead of buffer 1, and
+ * escapedPackets then stays rank-local (only its sum over cells, the SED, is global). */
+int mcb200_fetch_sed(mcb200_ctx *ctx, float *SED, int64_t *counts);
 
 /* Copy the raw estimator sums of grid iG into the caller's arrays, laid out as
  * Jste(0:nCells,nbins), escapedPackets(0:nCells,0:nbins,0:nAngleBins),

@@ -93,6 +93,7 @@ class PacketEngine:
             raise MocassinError(rc, "mcb200_create failed (no CUDA device? this library has no CPU fallback)")
         self.h = h
         self._keep = []
+        self.sed_local = False
         self._upload_static()
 
     # -- plumbing ---------------------------------------------------------------------
@@ -283,7 +284,7 @@ class PacketEngine:
         self._check(self.lib.mcb200_tally_buffer(self.h, iG, which, C.byref(p), C.byref(n)))
         return int(p.value or 0), int(n.value)
 
-    def _exchange(self, tset: int = 0, group=None, async_op: bool = False) -> list:
+    def _exchange(self, tset: int = 0, group=None, async_op: bool = False, sed: bool = True) -> list:
         """All-reduce the pending integer tallies of tally set `tset` over ranks (NCCL over
         NVLink, replacing MPI_ALLREDUCE at iteration_mod.f90:627-659): first the touched-bin
         flags (tiny max-reduce), then only the flagged nu-planes -- int64 path lengths, uint32
@@ -303,7 +304,7 @@ class PacketEngine:
             dist.all_reduce(flags, op=dist.ReduceOp.MAX, group=group)
             ranges = _touched_ranges(flags.cpu().numpy())
             self.last_exchange_planes = (sum(b - a + 1 for a, b in ranges), m.nbins + 1, len(ranges))
-            whichs = [0, 1] + ([2] if (m.lgDebug and tset == 0) else [])
+            whichs = [0] + ([] if self.sed_local else [1]) + ([2] if (m.lgDebug and tset == 0) else [])
             for w in whichs:
                 ptr, n = self.tally_buffer(iG, base + w)
                 if n == 0:
@@ -329,7 +330,27 @@ class PacketEngine:
                 if n:
                     works.append(dist.all_reduce(_as_cuda_tensor(ptr, n, "<i4", dev), op=dist.ReduceOp.SUM,
                                                  group=group, async_op=async_op))
+        if self.sed_local and sed:
+            ptr, n = self.tally_buffer(1, 6)
+            works.append(dist.all_reduce(_as_cuda_tensor(ptr, n, "<i8", dev), op=dist.ReduceOp.SUM, group=group,
+                                         async_op=async_op))
         return [w for w in works if w is not None] if async_op else []
+
+    def set_sed_local(self, on: bool = True):
+        """Exchange the per-(nu, angle) escape counts (a few KB) instead of the per-cell
+        escapedPackets tallies (5 GB at 128^3 x 600): the SED stays exact and global,
+        escapedPackets becomes rank-local."""
+        self.set_option("sed_local", 1 if on else 0)
+        self.sed_local = bool(on)
+
+    def fetch_sed(self):
+        """(SED, counts), each (nbins, nAngleBins+1): raw sums over cells and grids of
+        escapedPackets (head of writeSED, output_mod.f90:2561-2568) and the integer packet counts."""
+        m = self.model
+        sed = np.zeros((m.nbins, m.nAngleBins + 1), dtype=F32, order="F")
+        cnt = np.zeros((m.nbins, m.nAngleBins + 1), dtype=np.int64, order="F")
+        self._check(self.lib.mcb200_fetch_sed(self.h, _fp(sed), cnt.ctypes.data_as(C.POINTER(C.c_int64))))
+        return sed, cnt
 
     def reduce(self, group=None):
         """Sum the pending integer tallies over ranks and fold them into the float32
@@ -358,7 +379,7 @@ class PacketEngine:
         try:
             self.set_option("part", 0); self.set_option("tally_set", 0)
             c0 = self.energyPacketDriver(iStar, n, deltaE=deltaE)
-            works = self._exchange(0, group, async_op=True)
+            works = self._exchange(0, group, async_op=True, sed=False)
             self.set_option("part", 1); self.set_option("tally_set", 1)
             c1 = self.energyPacketDriver(iStar, n, deltaE=deltaE)
             for w in works:

@@ -53,6 +53,8 @@ struct OpacityArgs {
     float *opacity, *scaOpac, *absOpac;
 };
 cudaError_t launch_opacity(const OpacityArgs &A, cudaStream_t s);
+cudaError_t launch_sed_sum(const unsigned int *escQ, size_t nR, int firstPlane, int nPlanes,
+                           unsigned long long *sedQ, cudaStream_t s);
 }  // namespace mcb
 
 using namespace mcb;
@@ -170,6 +172,14 @@ struct mcb200_ctx {
     int aggSteps = 0, batch = 12;
     bool trace = false;
     int blocksPerSM = 0;                  // 0 = occupancy default
+    // SED(nu, angle) = sum over cells and grids of escapedPackets (writeSED): integer counts of
+    // the pending call on the device, raw float sums and cumulative counts on the host
+    DevBuf<unsigned long long> sedQ;
+    std::vector<float> sed;
+    std::vector<long long> sedCount;
+    bool sedLocal = false;                // option sed_local: sedQ is taken from this rank's escQ at
+                                          // the end of the transport call and exchanged instead of escQ
+    bool sedReady = false;                // sedQ already holds the pending call's counts
     // pending fold
     bool pending = false;
     float pendingDeltaE = 0.f;
@@ -326,6 +336,44 @@ std::vector<std::pair<int, int>> touched_ranges(const std::vector<int> &flag)
     return r;
 }
 
+size_t sed_size(const mcb200_ctx *ctx) { return (size_t)(ctx->cfg.nbins + 1) * (size_t)(ctx->cfg.nAngleBins + 1); }
+
+int ensure_sed(mcb200_ctx *ctx)
+{
+    size_t n = sed_size(ctx);
+    if (ctx->sedQ.n != n) {
+        CU(ctx->sedQ.alloc(n)); CU(ctx->sedQ.zero(ctx->stream));
+        ctx->sed.assign(n, 0.f); ctx->sedCount.assign(n, 0);
+    }
+    return MCB200_OK;
+}
+
+// sedQ += per-plane sums of the escape counts of every grid (tally set `set`)
+int sed_tally(mcb200_ctx *ctx, int set, int *launches)
+{
+    int rc = ensure_sed(ctx);
+    if (rc) return rc;
+    const int nb = ctx->cfg.nbins;
+    for (auto &g : ctx->grids) {
+        const unsigned int *q = set == 1 ? g.escQ2.p : g.escQ.p;
+        const int *touched = set == 1 ? g.nuTouched2.p : g.nuTouched.p;
+        if (!q) continue;
+        size_t nR = (size_t)g.nCells + 1;
+        std::vector<int> flag(nb + 1, 1);
+        if (touched) {
+            CU(cudaMemcpyAsync(flag.data(), touched, sizeof(int) * (nb + 1), cudaMemcpyDeviceToHost, ctx->stream));
+            CU(cudaStreamSynchronize(ctx->stream));
+        }
+        for (auto &rg : touched_ranges(flag))
+            for (int ang = 0; ang <= ctx->cfg.nAngleBins; ++ang)
+            {
+                CU(launch_sed_sum(q, nR, rg.first + (nb + 1) * ang, rg.second - rg.first + 1, ctx->sedQ.p, ctx->stream));
+                if (launches) ++*launches;
+            }
+    }
+    return MCB200_OK;
+}
+
 int fold_pending(mcb200_ctx *ctx)
 {
     if (!ctx->pending) return MCB200_OK;
@@ -341,6 +389,24 @@ int fold_pending(mcb200_ctx *ctx)
             ++launches;
         }
         ctx->pending2 = false;
+    }
+    {
+        // SED: counts of this call per (nu, angle) over all cells and grids, folded like
+        // escapedPackets: SED += float(count) * deltaE
+        if (!ctx->sedReady) { int rc = sed_tally(ctx, 0, &launches); if (rc) return rc; }
+        size_t n = sed_size(ctx);
+        std::vector<unsigned long long> q(n);
+        CU(cudaMemcpyAsync(q.data(), ctx->sedQ.p, n * 8, cudaMemcpyDeviceToHost, ctx->stream));
+        CU(cudaStreamSynchronize(ctx->stream));
+        CU(ctx->sedQ.zero(ctx->stream));
+        for (size_t k = 0; k < n; ++k)
+            if (q[k]) {
+                volatile float add = (float)q[k] * ctx->pendingDeltaE;
+                volatile float sum = ctx->sed[k] + add;
+                ctx->sed[k] = sum;
+                ctx->sedCount[k] += (long long)q[k];
+            }
+        ctx->sedReady = false;
     }
     for (auto &g : ctx->grids) {
         size_t nR = (size_t)g.nCells + 1;
@@ -682,6 +748,14 @@ int run_transport(mcb200_ctx *ctx, int iStar, int difGrid, const int32_t *cellLo
     ctx->pending = true;
     if (ctx->tallySet == 1) ctx->pending2 = true;
     ctx->pendingDeltaE = deltaE;
+    if (ctx->sedLocal && ctx->nranks > 1 && !herr) {
+        // the caller exchanges sedQ (a few KB) instead of the escape counts (5 GB at 128^3 x 600)
+        int nl = 0;
+        int rcs = sed_tally(ctx, ctx->tallySet, &nl);
+        if (rcs) return rcs;
+        ctx->sedReady = true;
+        if (out) out->nLaunches += nl;
+    }
     if (herr) return fail(ctx, MCB200_EPACKET, "a packet hit reference stop condition %d (see oracle/mc_oracle.c ERR_STOP codes)", herr);
     if (ctx->nranks == 1) {
         int rcf = fold_pending(ctx);
@@ -1182,6 +1256,14 @@ int mcb200_zero_estimators(mcb200_ctx *ctx)
 {
     NEED_CTX();
     if (!ctx->haveCfg) return fail(ctx, MCB200_ESTATE, "set_config first");
+    {
+        int rc = ensure_sed(ctx);
+        if (rc) return rc;
+        CU(ctx->sedQ.zero(ctx->stream));
+        std::fill(ctx->sed.begin(), ctx->sed.end(), 0.f);
+        std::fill(ctx->sedCount.begin(), ctx->sedCount.end(), 0ll);
+        ctx->sedReady = false;
+    }
     for (auto &g : ctx->grids) {
         if (!g.set) continue;
         int rc = ensure_estimators(ctx, g);
@@ -1260,6 +1342,11 @@ int mcb200_tally_buffer(mcb200_ctx *ctx, int32_t iG, int32_t which, void **devPt
         *devPtr = g->nuTouched.p; *count = (int64_t)g->nuTouched.n;
     } else if (which == 5) {
         *devPtr = ctx->planeDist.p; *count = (int64_t)ctx->planeDist.n;
+    } else if (which == 6) {
+        rc = ensure_sed(ctx);
+        if (rc) return rc;
+        CU(cudaStreamSynchronize(ctx->stream));
+        *devPtr = ctx->sedQ.p; *count = (int64_t)ctx->sedQ.n;
     } else {
         return fail(ctx, MCB200_EINVAL, "bad tally selector %d", which);
     }
@@ -1270,6 +1357,25 @@ int mcb200_reduce(mcb200_ctx *ctx)
 {
     NEED_CTX();
     return fold_pending(ctx);
+}
+
+int mcb200_fetch_sed(mcb200_ctx *ctx, float *SED, int64_t *counts)
+{
+    NEED_CTX();
+    if (!ctx->haveCfg) return fail(ctx, MCB200_ESTATE, "set_config first");
+    if (ctx->pending) return fail(ctx, MCB200_ESTATE, "tallies pending: call mcb200_reduce first");
+    int rc = ensure_sed(ctx);
+    if (rc) return rc;
+    // internal rows are nu = 0..nbins (row 0 = packets that escaped before getting a frequency
+    // bin is never written); the reference's SED(1:nbins, 0:nAngleBins) drops row 0
+    const int nb = ctx->cfg.nbins, nA = ctx->cfg.nAngleBins;
+    for (int a = 0; a <= nA; ++a)
+        for (int f = 1; f <= nb; ++f) {
+            size_t src = (size_t)f + (size_t)(nb + 1) * a, dst = (size_t)(f - 1) + (size_t)nb * a;
+            if (SED) SED[dst] = ctx->sed[src];
+            if (counts) counts[dst] = ctx->sedCount[src];
+        }
+    return MCB200_OK;
 }
 
 int mcb200_fetch_estimators(mcb200_ctx *ctx, int32_t iG, float *Jste, float *escapedPackets, float *Jdif, float *linePackets)
@@ -1361,6 +1467,11 @@ int mcb200_set_option(mcb200_ctx *ctx, const char *name, int64_t value)
     if (!strcmp(name, "step_budget")) { ctx->stepBudget = (int)value; return MCB200_OK; }
     if (!strcmp(name, "tail")) { ctx->tailThreshold = value; return MCB200_OK; }
     if (!strcmp(name, "async_pdfs")) { ctx->asyncPdfs = value != 0; return MCB200_OK; }
+    if (!strcmp(name, "sed_local")) {
+        if (ctx->pending) return fail(ctx, MCB200_ESTATE, "sed_local cannot change while tallies are pending");
+        ctx->sedLocal = value != 0;
+        return MCB200_OK;
+    }
     if (!strcmp(name, "tally_set")) {
         if (value != 0 && value != 1) return fail(ctx, MCB200_EINVAL, "tally_set must be 0 or 1");
         if (ctx->tallySet != (int)value) { ctx->tallySet = (int)value; ctx->gridsDirty = true; }

@@ -105,6 +105,45 @@ __global__ void merge_sets_kernel(unsigned long long *__restrict__ J0, unsigned 
     for (size_t i = i0; i < (size_t)nf; i += stride) { if (f1[i]) { f0[i] = 1; f1[i] = 0; } }
 }
 
+// ---------------------------------------------------------------------------------------
+// K7 SED reduction (writeSED, output_mod.f90:2561-2568): per (nu, viewing angle) plane, the
+// number of packets that escaped, summed over the cells of origin.  Exact integer sum, so the
+// 5 GB escapedPackets array never has to be exchanged or downloaded for the SED.
+// grid = (slices of a plane, planes).  HBM-bound: 4 B per (cell, nu, angle) element.
+// ---------------------------------------------------------------------------------------
+constexpr int kSedPerThread = 16;
+
+__global__ void __launch_bounds__(256) sed_sum_kernel(const unsigned int *__restrict__ escQ, size_t nR,
+                                                      unsigned long long *__restrict__ sedQ)
+{
+    const unsigned int *plane = escQ + nR * (size_t)blockIdx.y;
+    size_t base = (size_t)blockIdx.x * (256 * kSedPerThread);
+    unsigned long long s = 0;
+#pragma unroll
+    for (int k = 0; k < kSedPerThread; ++k) {
+        size_t i = base + (size_t)k * 256 + threadIdx.x;
+        if (i < nR) s += plane[i];
+    }
+    for (int o = 16; o > 0; o >>= 1) s += __shfl_down_sync(0xffffffffu, s, o);
+    __shared__ unsigned long long part[8];
+    if ((threadIdx.x & 31) == 0) part[threadIdx.x >> 5] = s;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        unsigned long long t = 0;
+        for (int w = 0; w < 8; ++w) t += part[w];
+        if (t) atomicAdd(&sedQ[blockIdx.y], t);
+    }
+}
+
+cudaError_t launch_sed_sum(const unsigned int *escQ, size_t nR, int firstPlane, int nPlanes,
+                           unsigned long long *sedQ, cudaStream_t s)
+{
+    if (nPlanes <= 0) return cudaSuccess;
+    dim3 grid((unsigned)((nR + 256 * kSedPerThread - 1) / (256 * kSedPerThread)), (unsigned)nPlanes);
+    sed_sum_kernel<<<grid, 256, 0, s>>>(escQ + nR * (size_t)firstPlane, nR, sedQ + firstPlane);
+    return cudaGetLastError();
+}
+
 cudaError_t launch_merge_sets(unsigned long long *J0, unsigned long long *J1, size_t nJ, unsigned int *E0,
                               unsigned int *E1, size_t nE, int *f0, int *f1, int nf, int blocks, cudaStream_t s)
 {

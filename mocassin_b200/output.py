@@ -1,0 +1,63 @@
+"""Host-side output of the escaped-packet spectrum: the part of ``writeSED``
+(output_mod.f90:2508-2719) that follows the reduction over cells.  The reduction itself,
+``SED(freq, imu) = sum_cells escapedPackets(i, freq, imu)``, is ``mcb200_fetch_sed`` (device);
+everything here is O(nbins) float32 arithmetic in the reference's order."""
+from __future__ import annotations
+
+import numpy as np
+
+from .model import F32, Model
+
+C_LIGHT = F32(2.9979250e10)      # constants_mod.f90: c [cm/s]
+FR1RYD = F32(3.28984e15)         # constants_mod.f90:13
+PI = F32(3.141592654)
+
+
+def sed_from_raw(model: Model, widFlx: np.ndarray, raw: np.ndarray):
+    """raw: (nbins, nAngleBins+1) sums of escapedPackets as fetched from the library (before the
+    host's /8).  Applies iteration_mod.f90:719 (/8 for symmetricXYZ) and writeSED's scaling
+    (:2626-2660).  Returns (SED [Jy pc^2], totalE [1e36 erg/s])."""
+    at = model.angle_tables()
+    sed = np.array(raw, dtype=F32, order="F", copy=True)
+    if model.lgSymmetricXYZ:
+        sed = (sed / F32(8.0)).astype(F32)                       # iteration_mod.f90:719
+        sed[:, 0] = sed[:, 0] * F32(8.0)                         # output_mod.f90:2629
+        sed[:, 1:] = sed[:, 1:] * F32(4.0)                       # :2631
+    totalE = F32(0.0)
+    for f in range(model.nbins):
+        totalE = F32(totalE + sed[f, 0])                         # :2635
+    wid = np.asarray(widFlx, dtype=F32)
+    sed[:, 0] = sed[:, 0] / F32(F32(F32(F32(4.0) * PI) * F32(3.08)) * F32(3.08))       # :2639
+    sed[:, 0] = F32(1.0e23) * sed[:, 0] / (F32(3.2898e15) * wid)                       # :2642
+    dTheta, dPhi = F32(at["dTheta"]), F32(at["dPhi"])
+    for imu in range(1, model.nAngleBins + 1):
+        theta1 = F32(int(F32(model.viewPointTheta[imu]) / dTheta)) * dTheta            # :2649
+        theta2 = F32(theta1 + dTheta)
+        solid = F32(F32(F32(dPhi * F32(3.08)) * F32(3.08)) * F32(abs(F32(np.cos(theta1)) - F32(np.cos(theta2)))))
+        sed[:, imu] = sed[:, imu] / solid                                              # :2656
+        sed[:, imu] = F32(1.0e23) * sed[:, imu] / (F32(3.2898e15) * wid)               # :2658
+    return sed, float(totalE)
+
+
+def write_sed(path: str, model: Model, widFlx: np.ndarray, raw: np.ndarray) -> float:
+    """output/SED.out in the reference's layout (:2551-2554, :2660, :2692-2708); list-directed
+    number formatting is the compiler's in the reference, here %.7E."""
+    at = model.angle_tables()
+    sed, totalE = sed_from_raw(model, widFlx, raw)
+    nu = np.asarray(model.nuArray, dtype=F32)
+    with open(path, "w") as fh:
+        fh.write(" Spectral energy distribution at the surface of the nebula: \n")
+        vp = "".join(f" {float(model.viewPointTheta[i]):.7E} {float(model.viewPointPhi[i]):.7E}  , "
+                     for i in range(1, model.nAngleBins + 1))
+        fh.write("   viewPoints = " + vp + "\n")
+        fh.write("    nu [Ryd]        lambda [um]         F(nu)*D^2            \n")
+        fh.write("                                        [Jy * pc^2]              \n")
+        for f in range(model.nbins):
+            lam_um = F32(C_LIGHT / F32(nu[f] * FR1RYD)) * F32(1.0e4)
+            cols = " ".join(f"{float(sed[f, a]):.7E}" for a in range(model.nAngleBins + 1))
+            fh.write(f" {float(nu[f]):.7E} {float(lam_um):.7E} {cols}\n")
+        fh.write(" \n")
+        fh.write(f" Total energy radiated out of the nebula [e36 erg/s]: {totalE:.7E}\n")
+        fh.write(f" dTheta:  {float(at['dTheta']):.7E}\n")
+        fh.write(f" dPhi:  {float(at['dPhi']):.7E}\n")
+    return totalE

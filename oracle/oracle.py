@@ -301,6 +301,21 @@ class Oracle:
         return res
 
 
+def _sed(self, deltaE: float):
+    """Head of writeSED (output_mod.f90:2561-2568): escaped packets per (nu, viewing angle)
+    summed over cells and grids -> (counts int64, raw SED float32 = float(count) * deltaE),
+    both (nbins, nAngleBins+1)."""
+    cnt = None
+    for o in self.out:
+        c = o["escapedQ"].sum(axis=0)[1:, :]
+        cnt = c if cnt is None else cnt + c
+    cnt = np.asfortranarray(cnt.astype(np.int64))
+    return cnt, np.asfortranarray((cnt.astype(np.float32) * np.float32(deltaE)).astype(np.float32))
+
+
+Oracle.sed = _sed
+
+
 class OrDustIn(C.Structure):
     _fields_ = [(n, C.c_int32) for n in (
         "nCells", "nbins", "nSpeciesMax", "nSizes", "nDustComp", "nSpeciesTot", "nTemps",

@@ -21,7 +21,7 @@ def _free_port():
     return p
 
 
-def _worker(rank, world, port, name, n, q, overlap=False):
+def _worker(rank, world, port, name, n, q, overlap=False, sed_local=False):
     sys.path.insert(0, ROOT)
     sys.path.insert(0, os.path.join(ROOT, "tests"))
     import torch
@@ -37,12 +37,16 @@ def _worker(rank, world, port, name, n, q, overlap=False):
     m, _ = make(name)
     e = PacketEngine(m, device=rank, rank=rank, nranks=world, seed=12345)
     e.upload_iteration_inputs()
+    if sed_local:
+        e.set_sed_local(True)
     if overlap:
         e.zero_estimators()
         e.energyPacketDriverOverlapped(1, n)
     else:
         e.lucy_transport([n])
     out = [e.fetch(iG) for iG in range(1, m.nGrids + 1)]
+    if sed_local:
+        out.append(e.fetch_sed())
     q.put((rank, out))
     dist.barrier()
     e.close()
@@ -81,4 +85,45 @@ def test_nccl_allreduce_matches_single_gpu(name, overlap):
         for r in (0, 1):
             assert np.array_equal(got[r][iG - 1]["Jste"], ref["Jste"])
             assert np.array_equal(got[r][iG - 1]["escapedPackets"], ref["escapedPackets"])
+    e.close()
+
+
+@pytest.mark.parametrize("overlap", [False, True])
+def test_nccl_sed_exchange_replaces_escaped_packets(overlap):
+    """sed_local: the ranks all-reduce the (nu, angle) escape counts instead of the per-cell
+    escapedPackets tallies.  Jste and the SED equal the single-GPU run bit for bit; the per-cell
+    escapedPackets are rank-local and add up to the global array."""
+    import torch
+    import torch.multiprocessing as mp
+
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    from cases import make
+    from mocassin_b200.api import PacketEngine
+
+    name, n = "viewing_angles", 20001
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_worker, args=(r, 2, port, name, n, q, overlap, True)) for r in range(2)]
+    for p in procs:
+        p.start()
+    got = dict(q.get(timeout=600) for _ in range(2))
+    for p in procs:
+        p.join(timeout=120)
+        assert p.exitcode == 0
+    m, _ = make(name)
+    e = PacketEngine(m, seed=12345)
+    e.upload_iteration_inputs()
+    e.lucy_transport([n])
+    ref = e.fetch(1)
+    sed, cnt = e.fetch_sed()
+    for r in (0, 1):
+        assert np.array_equal(got[r][0]["Jste"], ref["Jste"])
+        assert np.array_equal(got[r][-1][0].view(np.uint32), sed.view(np.uint32))
+        assert np.array_equal(got[r][-1][1], cnt)
+    both = got[0][0]["escapedPackets"].astype(np.float64) + got[1][0]["escapedPackets"].astype(np.float64)
+    assert np.allclose(both, ref["escapedPackets"], rtol=1e-6)
+    assert not np.array_equal(got[0][0]["escapedPackets"], ref["escapedPackets"])
     e.close()
