@@ -109,6 +109,27 @@ module mcb200_mod
             & bind(C, name="mcb200_fetch_estimators")
          import; type(c_ptr), value :: ctx, Jste, escapedPackets, Jdif, linePackets; integer(c_int32_t), value :: iG
        end function
+       integer(c_int) function mcb200_set_xsec(ctx, xSecArray, nXsec) bind(C, name="mcb200_set_xsec")
+         import; type(c_ptr), value :: ctx, xSecArray; integer(c_int64_t), value :: nXsec
+       end function
+       ! dust-only closure: getDustT / updateCell (update_mod.f90:308-334,1836-1945), setDustPDF (emission_mod.f90:1313-1387)
+       integer(c_int) function mcb200_set_dust_tables(ctx, widFlx, grainWeight, dustAbsXsecP, nSpecies, dustEmIntegral, nTemps) &
+            & bind(C, name="mcb200_set_dust_tables")
+         import; type(c_ptr), value :: ctx, widFlx, grainWeight, dustAbsXsecP, dustEmIntegral
+         integer(c_int32_t), value :: nSpecies, nTemps
+       end function
+       integer(c_int) function mcb200_dust_update(ctx, iG, XHILimit, Tdust, lgConverged, nConverged) &
+            & bind(C, name="mcb200_dust_update")
+         import; type(c_ptr), value :: ctx, Tdust, lgConverged; integer(c_int32_t), value :: iG
+         real(c_float), value :: XHILimit; integer(c_int64_t), intent(out) :: nConverged
+       end function
+       integer(c_int) function mcb200_dust_pdf(ctx, iG, dustPDF) bind(C, name="mcb200_dust_pdf")
+         import; type(c_ptr), value :: ctx, dustPDF; integer(c_int32_t), value :: iG
+       end function
+       ! head of writeSED (output_mod.f90:2561-2568): SED(1:nbins,0:nAngleBins) raw sums over cells and grids
+       integer(c_int) function mcb200_fetch_sed(ctx, SED, counts) bind(C, name="mcb200_fetch_sed")
+         import; type(c_ptr), value :: ctx, SED, counts
+       end function
     end interface
 
 contains
