@@ -268,6 +268,21 @@ int mcb200_reduce(mcb200_ctx *ctx);
  * escapedPackets then stays rank-local (only its sum over cells, the SED, is global). */
 int mcb200_fetch_sed(mcb200_ctx *ctx, float *SED, int64_t *counts);
 
+/* Photo-rate pre-integration for updateCell: instead of shipping Jste
+ * (5 GB at 128^3 x 600) to the host solver, integrate it on the device against each ion's
+ * outer-shell cross-section.  Band b = (bandOff: 1-based index in xSecArray of the
+ * cross-section at bin bandLow; bandLow = IPnuP; bandHigh = highNuP, clipped to nbins) -- the
+ * (elem, ion) loop of update_mod.f90:170-213 flattened by the host.  Outputs
+ * (0:nCells, nBands), cell index fastest, any may be NULL:
+ *   nPhotoSte(cell,b) = 1e-20 + sum_{j, Jste>0} Jste*phXSec/(hcRyd*nuArray(j))   (:240-245)
+ *   heatSte(cell,b)   = sum_{j until phXSec<1e-35, Jste>0} phXSec*Jste*(nu(j)-nu(IP))/nu(j)
+ *                       (thermBalance :1196-1201, before the ionDen*elemAbun factor)
+ * and the same from Jdif in debug mode.  Jste is the device-resident estimator with the host
+ * scaling of iteration_mod.f90:705-724 applied on the fly.  Needs mcb200_set_xsec. */
+int mcb200_photo_integrals(mcb200_ctx *ctx, int32_t iG, int32_t nBands, const int32_t *bandOff,
+                           const int32_t *bandLow, const int32_t *bandHigh, float *nPhotoSte,
+                           float *heatSte, float *nPhotoDif, float *heatDif);
+
 /* Copy the raw estimator sums of grid iG into the caller's arrays, laid out as
  * Jste(0:nCells,nbins), escapedPackets(0:nCells,0:nbins,0:nAngleBins),
  * Jdif(0:nCells,nbins), linePackets(0:nCells,nLines) (NULL = skip).  These are the

@@ -209,6 +209,23 @@ class PacketEngine:
         self._check(self.lib.mcb200_dust_pdf(self.h, iG, _fp(out) if fetch else None))
         return out
 
+    def photo_integrals(self, iG: int, off, low, high, dif: bool = False) -> dict:
+        """Photo-ionisation and heating integrals of updateCell / thermBalance
+        (update_mod.f90:170-262, :1160-1214) per (cell, band) from the device-resident Jste.
+        Bands are 1-based (xSecArray offset, first bin, last bin).  Returns arrays
+        (nCells+1, nBands): nPhotoSte, heatSte (and nPhotoDif, heatDif with ``dif``)."""
+        g = self.model.grids[iG - 1]
+        off, low, high = (_f(a, I32) for a in (off, low, high))
+        nb = int(off.shape[0])
+        mk = lambda: np.zeros((g.nCells + 1, nb), dtype=F32, order="F")
+        out = dict(nPhotoSte=mk(), heatSte=mk())
+        if dif:
+            out.update(nPhotoDif=mk(), heatDif=mk())
+        self._check(self.lib.mcb200_photo_integrals(
+            self.h, iG, nb, _ip(off), _ip(low), _ip(high), _fp(out["nPhotoSte"]), _fp(out["heatSte"]),
+            _fp(out.get("nPhotoDif")), _fp(out.get("heatDif"))))
+        return out
+
     def upload_iteration_inputs(self):
         self.set_opacity()
         self.set_pdfs()

@@ -138,7 +138,7 @@ struct mcb200_ctx {
     bool gridsDirty = true;
     DevBuf<float> nuArray, gSca, starCdf, starPos, vpTheta, vpPhi, xSec;
     DevBuf<int> starIdx, starCell, vpPtheta, vpPphi;
-    std::vector<float> hNu, hStarPos;
+    std::vector<float> hNu, hStarPos, hXsec;
     std::vector<int> hStarIdx;
     bool haveSpectra = false, haveStars = false, haveView = false;
     // dust species tables (host)
@@ -1519,6 +1519,68 @@ int mcb200_set_xsec(mcb200_ctx *ctx, const float *xSecArray, int64_t nXsec)
     if (!xSecArray || nXsec < 1) return fail(ctx, MCB200_EINVAL, "bad xSecArray");
     CU(ctx->xSec.upload(xSecArray, (size_t)nXsec, ctx->stream));
     CU(cudaStreamSynchronize(ctx->stream));
+    ctx->hXsec.assign(xSecArray, xSecArray + nXsec);
+    return MCB200_OK;
+}
+
+int mcb200_photo_integrals(mcb200_ctx *ctx, int32_t iG, int32_t nBands, const int32_t *bandOff,
+                           const int32_t *bandLow, const int32_t *bandHigh, float *nPhotoSte, float *heatSte,
+                           float *nPhotoDif, float *heatDif)
+{
+    NEED_CTX();
+    GridState *g = grid_of(ctx, iG);
+    if (!g || !g->set) return fail(ctx, MCB200_ESTATE, "grid %d not set", iG);
+    if (!ctx->xSec.p || !ctx->haveSpectra) return fail(ctx, MCB200_ESTATE, "mcb200_set_xsec and set_spectra first");
+    if (ctx->pending) return fail(ctx, MCB200_ESTATE, "tallies pending: call mcb200_reduce first");
+    if (nBands < 1 || !bandOff || !bandLow || !bandHigh) return fail(ctx, MCB200_EINVAL, "bad band list");
+    if ((nPhotoDif || heatDif) && !ctx->cfg.lgDebug) return fail(ctx, MCB200_ESTATE, "Jdif only exists in debug mode");
+    int rc = ensure_estimators(ctx, *g);
+    if (rc) return rc;
+    const int nb = ctx->cfg.nbins;
+    const int64_t nXs = (int64_t)ctx->hXsec.size();
+    std::vector<int> hi(nBands), heatHigh(nBands), nuStart(nb + 1, 0), nuBand;
+    for (int b = 0; b < nBands; ++b) {
+        int lo = bandLow[b];
+        hi[b] = bandHigh[b] < nb ? bandHigh[b] : nb;
+        if (lo < 1 || lo > nb) return fail(ctx, MCB200_EINVAL, "band %d: first bin %d out of range", b + 1, lo);
+        if (hi[b] >= lo && (bandOff[b] < 1 || (int64_t)bandOff[b] + (hi[b] - lo) > nXs))
+            return fail(ctx, MCB200_EINVAL, "band %d: xSecArray index out of range", b + 1);
+        // thermBalance leaves the frequency loop at the first cross-section below 1e-35 (:1186)
+        heatHigh[b] = hi[b];
+        for (int j = lo; j <= hi[b]; ++j)
+            if (ctx->hXsec[(size_t)bandOff[b] - 1 + (j - lo)] < 1.e-35f) { heatHigh[b] = j - 1; break; }
+    }
+    for (int nu = 1; nu <= nb; ++nu) {
+        for (int b = 0; b < nBands; ++b)
+            if (nu >= bandLow[b] && nu <= hi[b]) nuBand.push_back(b);
+        nuStart[nu] = (int)nuBand.size();
+    }
+    if (nuBand.empty()) nuBand.push_back(0);
+    cudaStream_t s = ctx->stream;
+    DevBuf<int> dStart, dBand, dOff, dLow, dHeat;
+    DevBuf<float> dRate, dHeatOut;
+    size_t nR = (size_t)g->nCells + 1, outN = nR * (size_t)nBands;
+    CU(dStart.upload(nuStart.data(), nuStart.size(), s)); CU(dBand.upload(nuBand.data(), nuBand.size(), s));
+    CU(dOff.upload(bandOff, nBands, s)); CU(dLow.upload(bandLow, nBands, s)); CU(dHeat.upload(heatHigh.data(), nBands, s));
+    CU(dRate.alloc(outN)); CU(dHeatOut.alloc(outN));
+    PhotoArgs A{};
+    A.nCells = g->nCells; A.nb = nb; A.sym = ctx->cfg.lgSymmetricXYZ;
+    A.nuStart = dStart.p; A.nuBand = dBand.p; A.off = dOff.p; A.low = dLow.p; A.heatHigh = dHeat.p;
+    A.xSec = ctx->xSec.p; A.nuArray = ctx->nuArray.p; A.nPhoto = dRate.p; A.heat = dHeatOut.p;
+    const int perLaunch = 96;                 // 2 * 96 * 128 * 4 B = 96 KB of shared memory
+    for (int pass = 0; pass < 2; ++pass) {
+        float *outR = pass ? nPhotoDif : nPhotoSte, *outH = pass ? heatDif : heatSte;
+        if (!outR && !outH) continue;
+        A.J = pass ? g->Jdif.p : g->Jste.p;
+        if (!A.J) return fail(ctx, MCB200_ESTATE, "estimator missing");
+        for (int b0 = 0; b0 < nBands; b0 += perLaunch) {
+            A.b0 = b0; A.nB = nBands - b0 < perLaunch ? nBands - b0 : perLaunch;
+            CU(launch_photo(A, s));
+        }
+        if (outR) CU(cudaMemcpyAsync(outR, dRate.p, outN * sizeof(float), cudaMemcpyDeviceToHost, s));
+        if (outH) CU(cudaMemcpyAsync(outH, dHeatOut.p, outN * sizeof(float), cudaMemcpyDeviceToHost, s));
+        CU(cudaStreamSynchronize(s));
+    }
     return MCB200_OK;
 }
 

@@ -3,6 +3,8 @@
 //  K5 dust_update_kernel : getDustT (update_mod.f90:1836-1945) + the dust-only branch of
 //                          updateCell (:308-334) for every cell, reading the folded Jste that
 //                          is already resident after mcb200_transport / mcb200_reduce.
+//  K8 photo_kernel       : photo-ionisation and heating integrals of updateCell / thermBalance
+//                          (update_mod.f90:170-262, :1160-1214) per (cell, ion band).
 //  K6 dust_pdf_kernel    : setDustPDF (emission_mod.f90:1313-1387, non-quantum-heating branch)
 //                          written straight into the nu-contiguous PDF rows the transport samples.
 //
@@ -173,6 +175,66 @@ __global__ void __launch_bounds__(256) dust_pdf_kernel(const DustArgs A)
         for (int i = lane; i < A.nb; i += 32) out[i] = (i == A.nb - 1) ? 1.f : row[i] / last;
         __syncwarp();
     }
+}
+
+// ---------------------------------------------------------------------------------------
+// K8: nPhoto(cell,b) = 1e-20 + sum_j J x /(hcRyd nu_j);  heat(cell,b) = sum_j x J (nu_j - nu_IP)/nu_j.
+// One CTA = 128 cells; nu is the outer loop so every Jste element is read once (coalesced
+// over cells); the bands covering a bin come from a CSR in band order, each band's running
+// sums live in shared memory, so each sum is formed in the reference's frequency order.
+// HBM-bound: 4 B per (cell, nu) read + 8 B per (cell, band) written.
+// ---------------------------------------------------------------------------------------
+constexpr int kPhotoTile = 128;
+
+__global__ void __launch_bounds__(kPhotoTile) photo_kernel(const PhotoArgs A)
+{
+    extern __shared__ float acc[];               // [2][nB][kPhotoTile]
+    const float hcRyd = 2.1799153e-11f;
+    const int t = threadIdx.x;
+    const int cell = blockIdx.x * kPhotoTile + t;        // 0..nCells
+    const bool live = cell <= A.nCells;
+    const size_t nR = (size_t)A.nCells + 1;
+    float *accR = acc, *accH = acc + (size_t)A.nB * kPhotoTile;
+    for (int b = 0; b < A.nB; ++b) { accR[b * kPhotoTile + t] = 1.e-20f; accH[b * kPhotoTile + t] = 0.f; }
+    for (int j = 1; j <= A.nb; ++j) {
+        int k0 = __ldg(&A.nuStart[j - 1]), k1 = __ldg(&A.nuStart[j]);
+        if (k0 == k1) continue;
+        float J = 0.f;
+        if (live) {
+            J = A.J[(size_t)(j - 1) * nR + cell] * 1.e-9f;     // iteration_mod.f90:706
+            if (A.sym) J = J / 8.f;                              // :718
+        }
+        if (!(J > 0.f)) continue;
+        float nu = __ldg(&A.nuArray[j - 1]);
+        for (int k = k0; k < k1; ++k) {
+            int b = __ldg(&A.nuBand[k]);
+            if (b < A.b0 || b >= A.b0 + A.nB) continue;
+            int lo = __ldg(&A.low[b]);
+            float x = __ldg(&A.xSec[__ldg(&A.off[b]) + (j - lo) - 1]);
+            if (x < 1.e-35f) x = 0.f;
+            int lb = b - A.b0;
+            accR[lb * kPhotoTile + t] = accR[lb * kPhotoTile + t] + J * x / (hcRyd * nu);
+            if (j <= __ldg(&A.heatHigh[b]))
+                accH[lb * kPhotoTile + t] = accH[lb * kPhotoTile + t] + x * J * (nu - __ldg(&A.nuArray[lo - 1])) / nu;
+        }
+    }
+    if (live)
+        for (int b = 0; b < A.nB; ++b) {
+            if (A.nPhoto) A.nPhoto[(size_t)(A.b0 + b) * nR + cell] = accR[b * kPhotoTile + t];
+            if (A.heat) A.heat[(size_t)(A.b0 + b) * nR + cell] = accH[b * kPhotoTile + t];
+        }
+}
+
+cudaError_t launch_photo(const PhotoArgs &A, cudaStream_t s)
+{
+    size_t smem = (size_t)2 * A.nB * kPhotoTile * sizeof(float);
+    if (smem > 48 * 1024) {
+        cudaError_t e = cudaFuncSetAttribute(photo_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return e;
+    }
+    unsigned blocks = (unsigned)((A.nCells + 1 + kPhotoTile - 1) / kPhotoTile);
+    photo_kernel<<<blocks, kPhotoTile, smem, s>>>(A);
+    return cudaGetLastError();
 }
 
 cudaError_t launch_dust_update(const DustArgs &A, cudaStream_t s)

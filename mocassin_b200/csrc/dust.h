@@ -21,6 +21,18 @@ struct DustArgs {
     unsigned long long *nConv;
 };
 
+// photo-rate pre-integration (K8, dust.cu): bands [b0, b0+nB) of a CSR over nu
+struct PhotoArgs {
+    int nCells, nb, sym;
+    int b0, nB;                      // bands handled by this launch
+    const int *nuStart, *nuBand;     // CSR: bands covering bin nu are nuBand[nuStart[nu-1] .. nuStart[nu])
+    const int *off, *low, *heatHigh; // per band: 1-based xSecArray offset, first bin, last bin of the heating sum
+    const float *xSec, *nuArray;
+    const float *J;                  // folded raw sums (0:nCells, nbins)
+    float *nPhoto, *heat;            // (0:nCells, nBands)
+};
+cudaError_t launch_photo(const PhotoArgs &A, cudaStream_t s);
+
 cudaError_t launch_dust_update(const DustArgs &A, cudaStream_t s);
 cudaError_t launch_dust_pdf(const DustArgs &A, int numSMs, cudaStream_t s);
 

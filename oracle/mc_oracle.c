@@ -1461,6 +1461,36 @@ void oracle_dust_update(const OrDustIn *in, const float *Jste, const float *Jdif
 }
 
 /* ------------------------------------------------------------------------- */
+/* photo-rate pre-integration, update_mod.f90:170-262 and :1160-1214           */
+/* ------------------------------------------------------------------------- */
+void oracle_photo_integrals(int32_t nCells, int32_t nbins, int32_t nBands, const int32_t *off,
+                            const int32_t *low, const int32_t *high, const float *xSecArray,
+                            const float *nuArray, const float *J, float *nPhoto, float *heat)
+{
+    const float hcRyd = 2.1799153e-11f;
+    const size_t nR = (size_t)nCells + 1;
+    const float *xs = xSecArray - 1, *nu = nuArray - 1;
+    for (int b = 0; b < nBands; ++b) {
+        int hi = high[b] < nbins ? high[b] : nbins;
+        for (int cell = 0; cell <= nCells; ++cell) {
+            float np = 1.e-20f, ht = 0.f;
+            int heatOn = 1;
+            for (int j = low[b]; j <= hi; ++j) {
+                float phXSec = xs[off[b] + (j - low[b])];
+                float Jc = J[(size_t)(j - 1) * nR + cell];
+                if (phXSec < 1.e-35f) { heatOn = 0; phXSec = 0.f; }
+                if (Jc > 0.f) {
+                    np = np + Jc * phXSec / (hcRyd * nu[j]);
+                    if (heatOn) ht = ht + phXSec * Jc * (nu[j] - nu[low[b]]) / nu[j];
+                }
+            }
+            if (nPhoto) nPhoto[(size_t)b * nR + cell] = np;
+            if (heat) heat[(size_t)b * nR + cell] = ht;
+        }
+    }
+}
+
+/* ------------------------------------------------------------------------- */
 /* unit-test hooks                                                            */
 /* ------------------------------------------------------------------------- */
 void oracle_philox(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3, uint32_t k0, uint32_t k1, uint32_t *out4)

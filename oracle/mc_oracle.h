@@ -164,6 +164,17 @@ void oracle_dust_update(const OrDustIn *in, const float *Jste, const float *Jdif
                         float *Tdust, int32_t *lgConverged);
 float oracle_get_flux(float energy, float temperature);
 
+/* Photo-rate pre-integration for updateCell: per band b (one ion's outer
+ * shell: 1-based offset off into xSecArray, frequency range low..high) and per cell
+ *   nPhoto(cell,b) = 1e-20 + sum_{j=low..high, J(cell,j)>0} J*x/(hcRyd*nu(j)), x<1e-35 -> 0
+ *                                                     (update_mod.f90:170-262)
+ *   heat(cell,b)   = sum_{j=low.., stop at the first x<1e-35, J>0} x*J*(nu(j)-nu(low))/nu(j)
+ *                                                     (thermBalance, update_mod.f90:1160-1214)
+ * J is the host-scaled Jste (or Jdif).  Outputs (0:nCells, nBands), cell index fastest. */
+void oracle_photo_integrals(int32_t nCells, int32_t nbins, int32_t nBands, const int32_t *off,
+                            const int32_t *low, const int32_t *high, const float *xSecArray,
+                            const float *nuArray, const float *J, float *nPhoto, float *heat);
+
 /* unit-test hooks */
 void oracle_philox(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3,
                    uint32_t k0, uint32_t k1, uint32_t *out4);

@@ -380,3 +380,21 @@ def get_flux(energy, temperature):
     lib.oracle_get_flux.argtypes = [C.c_float, C.c_float]
     lib.oracle_get_flux.restype = C.c_float
     return float(lib.oracle_get_flux(float(energy), float(temperature)))
+
+
+def photo_integrals(nbins, off, low, high, xSecArray, nuArray, J):
+    """oracle_photo_integrals -> (nPhoto, heat), each (nCells+1, nBands) F-order."""
+    lib = load()
+    J = np.asfortranarray(J, dtype=np.float32)
+    nR = J.shape[0]
+    off, low, high = (np.ascontiguousarray(a, dtype=np.int32) for a in (off, low, high))
+    xs = np.ascontiguousarray(xSecArray, dtype=np.float32)
+    nu = np.ascontiguousarray(nuArray, dtype=np.float32)
+    nb = int(off.shape[0])
+    nPhoto = np.zeros((nR, nb), np.float32, order="F")
+    heat = np.zeros((nR, nb), np.float32, order="F")
+    lib.oracle_photo_integrals.argtypes = [C.c_int32, C.c_int32, C.c_int32, ip, ip, ip, fp, fp, fp, fp, fp]
+    lib.oracle_photo_integrals.restype = None
+    lib.oracle_photo_integrals(nR - 1, nbins, nb, _p(off, ip), _p(low, ip), _p(high, ip), _p(xs, fp), _p(nu, fp),
+                               _p(J, fp), _p(nPhoto, fp), _p(heat, fp))
+    return nPhoto, heat
