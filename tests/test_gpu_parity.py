@@ -44,6 +44,32 @@ def test_device_detmath_is_bit_identical_to_oracle(cuda_lib, oracle_lib, ctx, wh
     assert np.array_equal(a.view(np.uint32), b.view(np.uint32))
 
 
+def test_device_division_is_ieee(cuda_lib, ctx):
+    """The transport divides wall distances by direction cosines with a reciprocal-multiply
+    plus one FMA correction (div_rn, transport_core.cuh).  It must equal IEEE division -- what
+    the oracle and the reference do -- for every operand pair."""
+    rng = np.random.default_rng(99)
+    n = 1 << 22
+    fp = _lib.c_float_p
+    for trial in range(3):
+        x = np.empty(n, np.float32)
+        # even slots: numerators over 2^-40..2^69 (both signs, some zeros); odd: cosines 1e-10..1
+        x[0::2] = (np.exp2(rng.uniform(-40, 69, n // 2)) * rng.choice([-1.0, 1.0], n // 2)).astype(np.float32)
+        x[0::2][rng.integers(0, n // 2, 1000)] = 0.0
+        v = (np.exp2(rng.uniform(-33.2, 0, n // 2)) * rng.choice([-1.0, 1.0], n // 2)).astype(np.float32)
+        edge = rng.integers(0, n // 2, 4000)
+        v[edge] = (np.float32(1.0) - np.float32(2.0 ** -24) * rng.integers(0, 4, 4000)).astype(np.float32) * np.exp2(rng.integers(-30, 1, 4000)).astype(np.float32)
+        x[1::2] = v
+        a, b = np.zeros_like(x), np.zeros_like(x)
+        assert cuda_lib.mcb200_test_detmath(ctx, 6, x.ctypes.data_as(fp), a.ctypes.data_as(fp), n) == 0
+        assert cuda_lib.mcb200_test_detmath(ctx, 7, x.ctypes.data_as(fp), b.ctypes.data_as(fp), n) == 0
+        ev = slice(0, n, 2)                      # numerator / cosine pairs
+        assert np.array_equal(a[ev].view(np.uint32), b[ev].view(np.uint32))
+        with np.errstate(over="ignore"):
+            want = (x[0::2] / x[1::2]).astype(np.float32)
+        assert np.array_equal(b[ev].view(np.uint32), want.view(np.uint32))
+
+
 def test_device_philox_stream_is_identical_to_oracle(cuda_lib, oracle_lib, ctx):
     fp = _lib.c_float_p
     for seed, pid, stream in [(12345, 0, 1), (2 ** 40 + 3, 2 ** 33 + 17, 0), (0, 999999937, 7)]:
@@ -89,8 +115,8 @@ SCHEDULES = {
     "persistent": dict(wavefront=0, order=0),          # one thread carries a packet through all phases
     "persistent_ordered": dict(wavefront=0, order=1, agg_steps=6),   # + packets sorted by first nu, aggregated tallies
     "wavefront": dict(wavefront=1, tail=64),           # per-wave event kernels + nu-sorted FLY kernel
-    "wavefront_budget3": dict(wavefront=1, step_budget=3, tail=0),   # flights continue across many waves
-    "wavefront_tail": dict(wavefront=1, step_budget=5, tail=10 ** 9),    # wave 0, then the persistent kernel resumes all
+    "wavefront_budget3": dict(wavefront=1, step_budget=3, tail=0, fly_batch=1),   # flights continue across many waves; no batching
+    "wavefront_tail": dict(wavefront=1, step_budget=5, tail=10 ** 9, fly_batch=32),    # wave 0, then the persistent kernel resumes all
 }
 
 
