@@ -194,8 +194,13 @@ __device__ __forceinline__ unsigned long long packet_pid(const TransportArgs &a,
     return (1ull << 40) + a.resCells[c].gid + (unsigned long long)(k - (long long)a.resPrefix[c]);
 }
 
-template <bool MULTI, bool DENSE = false>
+// PLAIN: the call has neither debug tallies nor plane-parallel illumination (compile-time
+// false for both flags; chosen by the launcher), so their tests leave the crossing loop.
+template <bool MULTI, bool DENSE = false, bool PLAIN = false>
 struct Transport {
+    // single dense grid: the table index of the packet's cell is carried along and advanced with
+    // the cell indices instead of being rebuilt from (x,y,z) on every crossing
+    static constexpr bool kInc = DENSE && !MULTI;
     const TransportArgs &a;
     unsigned int *cnt;                   // per-thread event counters in shared memory
     unsigned int *qph;                   // per-CTA Qphot histogram in shared memory
@@ -208,6 +213,8 @@ struct Transport {
         if (MULTI) return a.grids[gP - 1];
         return a.g1;
     }
+    __device__ __forceinline__ bool debug() const { return PLAIN ? false : (bool)a.P.lgDebug; }
+    __device__ __forceinline__ bool plane() const { return PLAIN ? false : (bool)a.P.lgPlane; }
     __device__ __forceinline__ void count(int which) { cnt[which * kThreads + threadIdx.x]++; }
     __device__ __forceinline__ void fail(Lane &L, int code)
     {
@@ -285,9 +292,9 @@ struct Transport {
     __device__ __forceinline__ void j_add(const DevGrid &g, const Lane &L, int cell, size_t tix, float len, bool aggregate)
     {
         long long q = __float2ll_rn(len * g.invLenUnit);
-        unsigned long long *Q = (!L.lgStellar && a.P.lgDebug) ? g.JdifQ : g.JsteQ;
+        unsigned long long *Q = (debug() && !L.lgStellar) ? g.JdifQ : g.JsteQ;
         unsigned long long *addr = &Q[tix];
-        bool live = cell > 0;            // sink row 0: never read by the reference
+        bool live = kInc || cell > 0;    // sink row 0: never read by the reference
         if (aggregate) {
             // one round: the lanes that share the address of the first live lane are summed
             // (REDUX) and added once; everybody else falls through to a plain reduction
@@ -490,7 +497,7 @@ struct Transport {
     // IEEE slow path and, like any rare branch here, split one lane off the warp for the
     // rest of the step: ncu showed 58 % of the warp trips running a 1-lane straggler).
     __device__ __forceinline__ void wall(const float *W, int n, float v, float ia, float &r, int &iP, bool outer, float &dS,
-                                         bool &drop, bool &pos)
+                                         bool &drop, bool &pos, bool &snapped)
     {
         pos = v > 1.e-10f;
         bool neg = v < -1.e-10f;
@@ -501,6 +508,7 @@ struct Transport {
         dS = moving ? d : 1.e35f;
         if (moving && fabsf(d) < 1.e-10f) {          // sitting on the wall: snap and step over (rare,
             r = w;                                   // tiny body: reconverges immediately)
+            snapped = true;
             if (pos) { if (iP < n) iP = iP + 1; else drop = drop || outer; }
             else     { if (iP > 1) iP = iP - 1; }
         }
@@ -527,6 +535,12 @@ struct Transport {
         float dSx = 0.f, dSy = 0.f, dSz = 0.f;
         bool posx = false, posy = false, posz = false;
         int cell;
+        // carried table index: the opacity of the cell is requested before the wall arithmetic
+        // so that its L2 latency overlaps it
+        const bool early = kInc && L.planeG == L.gP;
+        float opacEarly = 0.f;
+        if (early) opacEarly = __ldg(&a.g1.opacity[L.planeBase]);
+        bool snapped = false;
         for (int j = 1;; ++j) {
             if (MULTI) {
                 const DevGrid &g0 = G(L.gP);
@@ -560,12 +574,17 @@ struct Transport {
             // the later axes are looked at; nothing after a `return` is observable
             bool drop = false;
             // outermost wall of the mother grid: `return` (x,z not in plane mode, :1276,1315,1354)
-            const bool outerY = L.gP == 1, outerXZ = outerY && !P.lgPlane;
-            wall(g.xWall, g.nx, L.vx, L.iax, L.rx, L.xP, outerXZ, dSx, drop, posx);
-            wall(g.yWall, g.ny, L.vy, L.iay, L.ry, L.yP, outerY, dSy, drop, posy);
-            wall(g.zWall, g.nz, L.vz, L.iaz, L.rz, L.zP, outerXZ, dSz, drop, posz);
+            const bool outerY = L.gP == 1, outerXZ = outerY && !plane();
+            wall(g.xWall, g.nx, L.vx, L.iax, L.rx, L.xP, outerXZ, dSx, drop, posx, snapped);
+            wall(g.yWall, g.ny, L.vy, L.iay, L.ry, L.yP, outerY, dSy, drop, posy, snapped);
+            wall(g.zWall, g.nz, L.vz, L.iaz, L.rz, L.zP, outerXZ, dSz, drop, posz, snapped);
             if (drop) { finish(L, FATE_DROPPED); return; }
             if ((dSx != dSx) | (dSy != dSy) | (dSz != dSz)) { fail(L, 60); return; }
+            if (kInc) {
+                if (snapped) L.planeG = 0;           // indices moved: rebuild the carried table index
+                cell = 1;                            // every cell of a dense grid is active; the id is
+                break;                               // recomputed where it is needed (scattering)
+            }
             cell = active_at<DENSE>(g, L.xP, L.yP, L.zP);
             if (!MULTI || cell >= 0) break;
             if (j >= a.P.safeLimit) { fail(L, 63); return; }
@@ -575,10 +594,11 @@ struct Transport {
         // during a flight inside one grid and cached in the lane
         if (L.planeG != L.gP) {
             L.planeBase = (unsigned long long)(unsigned int)(L.nuP - 1) * (unsigned int)(g.nCells + 1);
+            if (kInc) L.planeBase += (unsigned int)active_at<DENSE>(g, L.xP, L.yP, L.zP);
             L.planeG = L.gP;
         }
-        size_t tix = (size_t)L.planeBase + (size_t)(unsigned int)cell;
-        float opac = __ldg(&g.opacity[tix]);
+        size_t tix = kInc ? (size_t)L.planeBase : (size_t)L.planeBase + (size_t)(unsigned int)cell;
+        float opac = (early && !snapped) ? opacEarly : __ldg(&g.opacity[tix]);
 
         // cells on a wall (:1395-1397): the axis end coordinate replaces a zero distance
         if (fabsf(dSx) < 1.e-10f) dSx = g.xN;
@@ -628,6 +648,7 @@ struct Transport {
                     return;
                 }
                 count(C_SCA);
+                if (kInc) cell = active_at<DENSE>(g, L.xP, L.yP, L.zP);
                 if (!__ldg(&g.canScatter[cell])) { fail(L, 69); return; }
                 if (L.istep >= a.P.safeLimit) { finish(L, FATE_DROPPED); return; }   // loop ends: :2838
                 L.phase = PH_SCATTER;
@@ -653,10 +674,11 @@ struct Transport {
         // needs the literal chain.
         if (dS < 1.e35f) {
             bool ex = dS == dSx, ey = (dS == dSy) & !ex, ez = (dS == dSz) & !ex & !ey;
-            L.xP += ex ? (posx ? 1 : -1) : 0;
-            L.yP += ey ? (posy ? 1 : -1) : 0;
-            L.zP += ez ? (posz ? 1 : -1) : 0;
+            int ix = ex ? (posx ? 1 : -1) : 0, iy = ey ? (posy ? 1 : -1) : 0, iz = ez ? (posz ? 1 : -1) : 0;
+            L.xP += ix; L.yP += iy; L.zP += iz;
+            if (kInc) L.planeBase += (unsigned long long)(long long)(ix * (g.ny * g.nz) + iy * g.nz + iz);
         } else {
+            if (kInc) L.planeG = 0;
             if (dS == dSx && L.vx > 0.f) L.xP = L.xP + 1;
             else if (dS == dSx && L.vx < 0.f) L.xP = L.xP - 1;
             else if (dS == dSy && L.vy > 0.f) L.yP = L.yP + 1;
@@ -665,7 +687,8 @@ struct Transport {
             else if (dS == dSz && L.vz < 0.f) L.zP = L.zP - 1;
         }
 
-        if (P.lgPlane) {
+        if (plane()) {
+            if (kInc) L.planeG = 0;
             if (!step_tail_plane(L)) return;
         } else if (!MULTI) {
             // single grid: every test of :1986-2194, :2417-2540 and :2733-2834 that is true
@@ -677,9 +700,9 @@ struct Transport {
             out = out | (low & !P.lgSym);
             if (out) { escape(L, FATE_ESCAPED); return; }
             if (P.lgSym) {               // :2674-2699
-                if (L.rx <= g.x1 || L.xP < 1) { L.vx = fabsf(L.vx); L.xP = 1; L.rx = g.x1; }
-                if (L.ry <= g.y1 || L.yP < 1) { L.vy = fabsf(L.vy); L.yP = 1; L.ry = g.y1; }
-                if (L.rz <= g.z1 || L.zP < 1) { L.vz = fabsf(L.vz); L.zP = 1; L.rz = g.z1; }
+                if (L.rx <= g.x1 || L.xP < 1) { L.vx = fabsf(L.vx); L.xP = 1; L.rx = g.x1; if (kInc) L.planeG = 0; }
+                if (L.ry <= g.y1 || L.yP < 1) { L.vy = fabsf(L.vy); L.yP = 1; L.ry = g.y1; if (kInc) L.planeG = 0; }
+                if (L.rz <= g.z1 || L.zP < 1) { L.vz = fabsf(L.vz); L.zP = 1; L.rz = g.z1; if (kInc) L.planeG = 0; }
             }
         } else {
             if (!step_tail_multi(L)) return;

@@ -100,12 +100,12 @@ __global__ void __launch_bounds__(kThreads) wf_event_kernel(const __grid_constan
 // atomic per chunk, records of the chunk prefetched into L2) and cross cells until the next
 // event; ended flights are written back in place and their positions staged per warp in
 // shared memory, flushed 32 at a time (one global atomic per 32 events, coalesced stores).
-template <bool MULTI, bool DENSE>
+template <bool MULTI, bool DENSE, bool PLAIN>
 __global__ void __launch_bounds__(kThreads, 4) wf_fly_kernel(const __grid_constant__ WfArgs w)
 {
     extern __shared__ unsigned int smem[];
     scratch_init(smem, w.t.P.nbins);
-    Transport<MULTI, DENSE> T(w.t, smem, smem + C_COUNT * kThreads);
+    Transport<MULTI, DENSE, PLAIN> T(w.t, smem, smem + C_COUNT * kThreads);
     unsigned int *stage = smem + scratch_words(w.t.P.nbins) + (threadIdx.x >> 5) * (EV_COUNT * kStage);
     const unsigned int FULL = 0xffffffffu;
     const unsigned int lane = threadIdx.x & 31u;
@@ -123,11 +123,12 @@ __global__ void __launch_bounds__(kThreads, 4) wf_fly_kernel(const __grid_consta
     // crossing loop (41 % of the trips end a flight in some lane) cost more warp instructions
     // than the crossings themselves.
     const unsigned int batch = (unsigned int)(w.flyBatch < 1 ? 1 : w.flyBatch);
+    unsigned int doneM = 0u;                         // lanes that found the work list empty
     for (;;) {
-        const bool ended = L.phase == PH_EMIT || L.phase == PH_SCATTER || L.phase == PH_ESCAPE || L.phase == PH_CONT;
-        const unsigned int waitM = __ballot_sync(FULL, ended || L.phase == PH_NEED);
         unsigned int flyM = __ballot_sync(FULL, L.phase == PH_FLY);
+        const unsigned int waitM = ~(flyM | doneM);
         if (waitM && ((unsigned int)__popc(waitM) >= batch || flyM == 0u)) {
+            const bool ended = L.phase == PH_EMIT || L.phase == PH_SCATTER || L.phase == PH_ESCAPE || L.phase == PH_CONT;
             // flights that ended: write the record back and stage its position
             if (__ballot_sync(FULL, ended)) {
                 if (ended) {
@@ -187,7 +188,8 @@ __global__ void __launch_bounds__(kThreads, 4) wf_fly_kernel(const __grid_consta
                 need = __ballot_sync(FULL, L.phase == PH_NEED);
             }
             if (exhausted && L.phase == PH_NEED) L.phase = PH_DONE;
-            flyM = __ballot_sync(FULL, L.phase == PH_FLY);
+            doneM = __ballot_sync(FULL, L.phase == PH_DONE);
+            flyM = ~doneM;                           // every other lane holds a flight now
         }
         if (flyM == 0u) break;
         if (L.phase == PH_FLY) {
@@ -324,28 +326,29 @@ cudaError_t wf_launch_event(const WfArgs &w, bool multi, int ev, int blocks, cud
 
 static size_t fly_smem(int nbins) { return scratch_bytes(nbins) + (size_t)(kThreads / 32) * EV_COUNT * kStage * sizeof(unsigned int); }
 
-template <bool MULTI, bool DENSE>
+template <bool MULTI, bool DENSE, bool PLAIN>
 static cudaError_t launch_fly_t(const WfArgs &w, int blocks, cudaStream_t s)
 {
     size_t smem = fly_smem(w.t.P.nbins);
-    cudaFuncSetAttribute(wf_fly_kernel<MULTI, DENSE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    wf_fly_kernel<MULTI, DENSE><<<blocks, kThreads, smem, s>>>(w);
+    cudaFuncSetAttribute(wf_fly_kernel<MULTI, DENSE, PLAIN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    wf_fly_kernel<MULTI, DENSE, PLAIN><<<blocks, kThreads, smem, s>>>(w);
     return cudaGetLastError();
 }
 
 cudaError_t wf_launch_fly(const WfArgs &w, bool multi, int blocks, cudaStream_t s)
 {
-    if (multi) return launch_fly_t<true, false>(w, blocks, s);
-    if (w.t.g1.dense) return launch_fly_t<false, true>(w, blocks, s);
-    return launch_fly_t<false, false>(w, blocks, s);
+    if (multi) return launch_fly_t<true, false, false>(w, blocks, s);
+    const bool plain = !w.t.P.lgDebug && !w.t.P.lgPlane;
+    if (w.t.g1.dense) return plain ? launch_fly_t<false, true, true>(w, blocks, s) : launch_fly_t<false, true, false>(w, blocks, s);
+    return plain ? launch_fly_t<false, false, true>(w, blocks, s) : launch_fly_t<false, false, false>(w, blocks, s);
 }
 
 int wf_fly_blocks_per_sm(bool multi)
 {
     int nb = 0;
     size_t smem = fly_smem(1024);
-    if (multi) cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, wf_fly_kernel<true, false>, kThreads, smem);
-    else       cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, wf_fly_kernel<false, false>, kThreads, smem);
+    if (multi) cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, wf_fly_kernel<true, false, false>, kThreads, smem);
+    else       cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, wf_fly_kernel<false, false, false>, kThreads, smem);
     return nb;
 }
 
