@@ -287,7 +287,7 @@ def run_b200(args):
 
     eng = PacketEngine(model, device=local, rank=rank, nranks=world, seed=SEED)
     eng.set_xsec(xsec)
-    for opt in ("order", "agg_steps", "batch", "blocks_per_sm", "wavefront", "step_budget", "tail", "fly_batch"):
+    for opt in ("order", "agg_steps", "batch", "blocks_per_sm", "wavefront", "step_budget", "tail", "fly_batch", "wave0_order", "wave0_blocks"):
         if os.environ.get("MCB_" + opt.upper()):
             eng.set_option(opt, int(os.environ["MCB_" + opt.upper()]))
 

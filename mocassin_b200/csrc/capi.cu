@@ -162,6 +162,8 @@ struct mcb200_ctx {
     DevBuf<unsigned char> wfRecA, wfRecB, wfRecXA, wfRecXB;
     DevBuf<unsigned int> wfEv0, wfEv1, wfEv2, wfEv3, wfCounts, wfHist, wfCursor, wfSegs;
     int stepBudget = 96;
+    int wave0Order = 1;                   // wave 0 of the wave-front pipeline emits in first-frequency order: 0 off, 1 for >= 2^17 packets, 2 always
+    int wave0Blocks = 4;                  // CTAs per SM of the pre-ordered wave-0 emission
     int flyBatch = 8;                     // FLY kernel: lanes of a warp that must be idle before records are stored / claimed
     int64_t tailThreshold = 32768;        // alive packets below which the persistent kernel finishes the batch
     DevBuf<unsigned char> wfArgsDev;
@@ -480,13 +482,34 @@ int run_wavefront(mcb200_ctx *ctx, const TransportArgs &a, bool multi, int64_t m
         uint64_t b = (cnt + 255) / 256, cap = (uint64_t)ctx->numSMs * 16;
         return (int)(b < 1 ? 1 : (b > cap ? cap : b));
     };
-    // wave 0: every packet is emitted
+    // wave 0: every packet is emitted.  With option wave0_order the packets are emitted in the
+    // order of their first frequency bin (first_nu_kernel replays that draw) straight into recA:
+    // 4 B of index per packet are sorted instead of 64 B of record.
     CU(ctx->wfCounts.zero(s));
     w.inList = nullptr; w.inCount = nullptr;
-    CU(wf_launch_event(w, multi, 0, evBlocks((uint64_t)mine), s));
+    w.directA = 0;
+    if (!a.resCells && mine > 0 && (ctx->wave0Order == 2 || (ctx->wave0Order == 1 && mine >= (1 << 17)))) {
+        CU(ctx->sortKey.alloc(n)); CU(ctx->sortOrder.alloc(n));
+        CU(ctx->sortHist.alloc(nb + 1)); CU(ctx->sortCursor.alloc(nb + 1));
+        CU(launch_order(a, ctx->sortKey.p, ctx->sortHist.p, ctx->sortCursor.p, ctx->sortOrder.p, ctx->numSMs, s));
+        w.t.order = ctx->sortOrder.p;
+        w.directA = 1;
+        ctx->lastLaunches += 3;
+    }
+    {
+        // pre-ordered: a small grid keeps the grid-stride window (= how far arrival order can
+        // deviate from frequency order) below one frequency bin's worth of packets
+        int eb = evBlocks((uint64_t)mine), capOrdered = ctx->numSMs * ctx->wave0Blocks;
+        if (w.directA && eb > capOrdered) eb = capOrdered;
+        CU(wf_launch_event(w, multi, 0, eb, s));
+    }
     ctx->lastLaunches++;
+    w.t.order = nullptr;
+    bool sorted = w.directA != 0;
+    w.directA = 0;
     for (;;) {
-        CU(wf_launch_sort(w, multi, ctx->numSMs, s));
+        if (!sorted) CU(wf_launch_sort(w, multi, ctx->numSMs, s));
+        sorted = false;
         CU(cudaMemsetAsync(w.evCount, 0, 4 * sizeof(unsigned int), s));
         CU(ctx->wfNext.zero(s));
         CU(wf_launch_fly(w, multi, flyBlocks, s));
@@ -1472,6 +1495,8 @@ int mcb200_set_option(mcb200_ctx *ctx, const char *name, int64_t value)
     if (!strcmp(name, "wavefront")) { ctx->waveMode = (int)value; return MCB200_OK; }
     if (!strcmp(name, "step_budget")) { ctx->stepBudget = (int)value; return MCB200_OK; }
     if (!strcmp(name, "tail")) { ctx->tailThreshold = value; return MCB200_OK; }
+    if (!strcmp(name, "wave0_order")) { ctx->wave0Order = value < 0 ? 0 : (value > 2 ? 2 : (int)value); return MCB200_OK; }
+    if (!strcmp(name, "wave0_blocks")) { ctx->wave0Blocks = value < 1 ? 1 : (int)value; return MCB200_OK; }
     if (!strcmp(name, "fly_batch")) { ctx->flyBatch = value < 1 ? 1 : (value > 32 ? 32 : (int)value); return MCB200_OK; }
     if (!strcmp(name, "async_pdfs")) { ctx->asyncPdfs = value != 0; return MCB200_OK; }
     if (!strcmp(name, "sed_local")) {

@@ -129,6 +129,7 @@ struct WfArgs {
     unsigned int *flyCount;              // entries in recB / recA
     unsigned int *evList[EV_COUNT];      // positions in recA of flights that ended, per event
     unsigned int *evCount;               // [EV_COUNT]
+    int directA;                         // wave 0 with pre-ordered packets: EMIT writes recA directly, no sort
     int flyBatch;                        // idle lanes of a warp that trigger the store/claim pass of the FLY kernel
     int stepBudget;                      // cell crossings per flight per wave (longer flights continue
                                          // in the next wave, so one straggler cannot hold a wave open)

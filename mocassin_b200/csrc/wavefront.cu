@@ -71,7 +71,8 @@ __global__ void __launch_bounds__(kThreads) wf_event_kernel(const __grid_constan
         }
         if (valid) {
             if (EV == EV_EMIT && !w.inList) {
-                T.start_packet(L, (long long)i);
+                // wave 0: packet i, or the i-th packet in order of its first frequency bin
+                T.start_packet(L, w.t.order ? (long long)__ldg(&w.t.order[i]) : (long long)i);
             } else {
                 rec_load<MULTI>(w.t, w.recA, w.recxA, L, w.inList[i]);
             }
@@ -88,8 +89,15 @@ __global__ void __launch_bounds__(kThreads) wf_event_kernel(const __grid_constan
         unsigned int pos = warp_append(toFly, w.flyCount);
         if (toFly) {
             L.vx = L.dx; L.vy = L.dy; L.vz = L.dz; L.absTau = 0.f;     // fresh flight
-            rec_store<MULTI>(w.recB, w.recxB, L, pos);
-            w.flyKey[pos] = (unsigned short)L.nuP;
+            if (EV == EV_EMIT && w.directA) {
+                // pre-ordered wave 0: arrival order already follows the frequency bins closely
+                // enough (within one grid-stride window), so the record goes straight to the
+                // FLY kernel's array and the counting sort is skipped
+                rec_store<MULTI>(w.recA, w.recxA, L, pos);
+            } else {
+                rec_store<MULTI>(w.recB, w.recxB, L, pos);
+                w.flyKey[pos] = (unsigned short)L.nuP;
+            }
         }
     }
     scratch_flush(w.t, smem);

@@ -114,8 +114,8 @@ def _compare(m, n, e, o, iStar=1):
 SCHEDULES = {
     "persistent": dict(wavefront=0, order=0),          # one thread carries a packet through all phases
     "persistent_ordered": dict(wavefront=0, order=1, agg_steps=6),   # + packets sorted by first nu, aggregated tallies
-    "wavefront": dict(wavefront=1, tail=64),           # per-wave event kernels + nu-sorted FLY kernel
-    "wavefront_budget3": dict(wavefront=1, step_budget=3, tail=0, fly_batch=1),   # flights continue across many waves; no batching
+    "wavefront": dict(wavefront=1, tail=64, wave0_order=2),   # per-wave event kernels + nu-sorted FLY kernel; wave 0 pre-ordered
+    "wavefront_budget3": dict(wavefront=1, step_budget=3, tail=0, fly_batch=1, wave0_order=0),   # flights continue across many waves; no batching
     "wavefront_tail": dict(wavefront=1, step_budget=5, tail=10 ** 9, fly_batch=32),    # wave 0, then the persistent kernel resumes all
 }
 
