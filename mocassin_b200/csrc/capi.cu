@@ -9,6 +9,7 @@
 
 #include <cuda_runtime.h>
 
+#include <chrono>
 #include <cmath>
 #include <cstdarg>
 #include <cstdio>
@@ -150,6 +151,10 @@ struct mcb200_ctx {
     DevBuf<float> widFlx, grainWeight, emT, dGrainAbun, dSublime;
     DevBuf<int> absP, dSpeciesPart, dComPoint;
     DevBuf<unsigned long long> nConv;
+    // temporaries of mcb200_assemble_opacity
+    DevBuf<float> opDen, opFf, opNd, opCoef;
+    DevBuf<int> opStart, opSpec, opXs, opComp, opTermOn, opScaP, opAbsP;
+    DevBuf<unsigned char> opOn;
     int nSpeciesTot = 0, nTemps = 0;
     bool haveDustTables = false;
     // work buffers
@@ -1650,10 +1655,18 @@ int mcb200_assemble_opacity(mcb200_ctx *ctx, int32_t iG, int32_t nBands, const i
     }
     size_t ts = tsize(ctx, *g);
     bool re = (g->opacity.n != ts);
-    DevBuf<float> dDen, dFf, dNd, dCoef;
-    DevBuf<int> dStart, dSpec, dXs, dComp, dTermOn, dScaP, dAbsP;
-    DevBuf<unsigned char> dOn;
+    // device temporaries live in the context: cudaMalloc / cudaFree per call cost more than K1
+    DevBuf<float> &dDen = ctx->opDen, &dFf = ctx->opFf, &dNd = ctx->opNd, &dCoef = ctx->opCoef;
+    DevBuf<int> &dStart = ctx->opStart, &dSpec = ctx->opSpec, &dXs = ctx->opXs, &dComp = ctx->opComp,
+                &dTermOn = ctx->opTermOn, &dScaP = ctx->opScaP, &dAbsP = ctx->opAbsP;
+    DevBuf<unsigned char> &dOn = ctx->opOn;
     cudaStream_t s = ctx->stream;
+    const bool tr = ctx->trace;
+    auto now = [] { return std::chrono::steady_clock::now(); };
+    auto ms = [](std::chrono::steady_clock::time_point a, std::chrono::steady_clock::time_point b) {
+        return std::chrono::duration<double, std::milli>(b - a).count();
+    };
+    auto t0 = now();
     OpacityArgs A{};
     A.nRows = nRows; A.nb = nb; A.nSpeciesDen = nSpeciesDen;
     if (nSpeciesDen > 0) CU(dDen.upload(den, (size_t)nRows * nSpeciesDen, s));
@@ -1706,6 +1719,8 @@ int mcb200_assemble_opacity(mcb200_ctx *ctx, int32_t iG, int32_t nBands, const i
                     on[(size_t)t * nRows + cell] = Td < ctx->TdustSublime[sg - 1] ? 1 : 0;
                 }
         }
+        auto t1 = now();
+        if (tr) fprintf(stderr, "[mcb200] assemble_opacity: gas uploads + dust host mask %.1f ms\n", ms(t0, t1));
         CU(dNd.upload(Ndust, nRows, s)); CU(dOn.upload(on.data(), on.size(), s));
         CU(dCoef.upload(coef.data(), coef.size(), s)); CU(dTermOn.upload(termOn.data(), termOn.size(), s));
         CU(dScaP.upload(scaP.data(), nT, s)); CU(dAbsP.upload(absP.data(), nT, s));
@@ -1721,8 +1736,10 @@ int mcb200_assemble_opacity(mcb200_ctx *ctx, int32_t iG, int32_t nBands, const i
         CU(g->scaOpac.alloc(ts)); CU(g->absOpac.alloc(ts));
         CU(g->scaOpac.zero(s)); CU(g->absOpac.zero(s));
     }
+    auto t2 = now();
     CU(launch_opacity(A, s));
     CU(cudaStreamSynchronize(s));
+    if (tr) fprintf(stderr, "[mcb200] assemble_opacity: total host prep %.1f ms, kernel + pending copies %.1f ms\n", ms(t0, t2), ms(t2, now()));
     g->haveOpacity = true;
     if (re) ctx->gridsDirty = true;
     return MCB200_OK;
