@@ -303,6 +303,11 @@ def run_b200(args):
     # measured on 2 GPUs: splitting the batch in halves costs more (smaller waves, NCCL sharing
     # the SMs) than hiding half of the exchange gains -> off by default
     overlap = world > 1 and os.environ.get("MCB_OVERLAP", "0") == "1"
+    if world > 1 and os.environ.get("MCB_SED_LOCAL", "0") == "1":
+        # exchange the (nu, angle) escape counts instead of the per-cell escapedPackets tallies;
+        # escapedPackets then stays rank-local (see mcb200_fetch_sed).  Off by default: the
+        # reference all-reduces escapedPackets (iteration_mod.f90:649-659).
+        eng.set_sed_local(True)
 
     def step():
         if overlap:      # exchange of the first half hidden behind the transport of the second
