@@ -36,7 +36,7 @@ ALG_BYTES_PER_SEGMENT = 16       # active 4 + opacity 4 + Jste 4 read + 4 write 
 def parse():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--grid", type=int, default=128)
@@ -138,11 +138,16 @@ class ClockSampler(threading.Thread):
         self.rows = []
         self.stop_flag = False
         self.proc = None
+        self.first = 0
+
+    def mark(self):
+        """Start of the timed region: only rows sampled from here on are reported."""
+        self.first = len(self.rows)
 
     def run(self):
         try:
             self.proc = subprocess.Popen(
-                ["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "200"],
+                ["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100"],
                 stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             for line in self.proc.stdout:
                 self.rows.append([c.strip() for c in line.split(",")])
@@ -156,7 +161,7 @@ class ClockSampler(threading.Thread):
         if self.proc:
             self.proc.terminate()
         sm, mx, reasons = [], [], set()
-        for r in self.rows:
+        for r in self.rows[self.first:]:
             try:
                 sm.append(float(r[0])); mx.append(float(r[1]))
                 for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[3:7]):
@@ -287,7 +292,7 @@ def run_b200(args):
 
     eng = PacketEngine(model, device=local, rank=rank, nranks=world, seed=SEED)
     eng.set_xsec(xsec)
-    for opt in ("order", "agg_steps", "batch", "blocks_per_sm", "wavefront", "step_budget", "tail", "fly_batch", "wave0_order", "wave0_blocks"):
+    for opt in ("order", "agg_steps", "batch", "blocks_per_sm", "wavefront", "step_budget", "tail", "fly_batch", "wave0_order", "wave0_blocks", "wave0_exact"):
         if os.environ.get("MCB_" + opt.upper()):
             eng.set_option(opt, int(os.environ["MCB_" + opt.upper()]))
 
@@ -318,14 +323,18 @@ def run_b200(args):
         return c
 
     eng.zero_estimators()
-    for _ in range(args.warmup):
-        step()
+    # the sampler process is started before the warm-up so that it is already delivering rows
+    # when the timed region begins; rows before mark() are discarded
     sampler = ClockSampler(local) if rank == 0 else None
     if sampler:
         sampler.start()
+    for _ in range(args.warmup):
+        step()
     if world > 1:
         dist.barrier()
     torch.cuda.synchronize()
+    if sampler:
+        sampler.mark()
     t0 = time.perf_counter()
     kms, tms, segs, flights, launches, waves = 0.0, 0.0, 0, 0, 0, 0
     for _ in range(args.steps):

@@ -168,6 +168,8 @@ struct mcb200_ctx {
     DevBuf<unsigned int> wfEv0, wfEv1, wfEv2, wfEv3, wfCounts, wfHist, wfCursor, wfSegs;
     int stepBudget = 96;
     int wave0Order = 1;                   // wave 0 of the wave-front pipeline emits in first-frequency order: 0 off, 1 for >= 2^17 packets, 2 always
+    unsigned int wave0Count = 0;
+    bool wave0Exact = false;              // exact slots instead of appended records (measured slower)
     int wave0Blocks = 4;                  // CTAs per SM of the pre-ordered wave-0 emission
     int flyBatch = 8;                     // FLY kernel: lanes of a warp that must be idle before records are stored / claimed
     int64_t tailThreshold = 32768;        // alive packets below which the persistent kernel finishes the batch
@@ -498,15 +500,19 @@ int run_wavefront(mcb200_ctx *ctx, const TransportArgs &a, bool multi, int64_t m
         CU(ctx->sortHist.alloc(nb + 1)); CU(ctx->sortCursor.alloc(nb + 1));
         CU(launch_order(a, ctx->sortKey.p, ctx->sortHist.p, ctx->sortCursor.p, ctx->sortOrder.p, ctx->numSMs, s));
         w.t.order = ctx->sortOrder.p;
-        w.directA = 1;
+        w.directA = ctx->wave0Exact ? 2 : 1;
         ctx->lastLaunches += 3;
     }
     {
         // pre-ordered: a small grid keeps the grid-stride window (= how far arrival order can
         // deviate from frequency order) below one frequency bin's worth of packets
         int eb = evBlocks((uint64_t)mine), capOrdered = ctx->numSMs * ctx->wave0Blocks;
-        if (w.directA && eb > capOrdered) eb = capOrdered;
+        if (w.directA && ctx->wave0Blocks > 0 && eb > capOrdered) eb = capOrdered;
         CU(wf_launch_event(w, multi, 0, eb, s));
+        if (w.directA == 2) {            // slot i holds packet order[i] (or a hole)
+            ctx->wave0Count = (unsigned int)mine;
+            CU(cudaMemcpyAsync(w.flyCount, &ctx->wave0Count, sizeof(unsigned int), cudaMemcpyHostToDevice, s));
+        }
     }
     ctx->lastLaunches++;
     w.t.order = nullptr;
@@ -1501,7 +1507,8 @@ int mcb200_set_option(mcb200_ctx *ctx, const char *name, int64_t value)
     if (!strcmp(name, "step_budget")) { ctx->stepBudget = (int)value; return MCB200_OK; }
     if (!strcmp(name, "tail")) { ctx->tailThreshold = value; return MCB200_OK; }
     if (!strcmp(name, "wave0_order")) { ctx->wave0Order = value < 0 ? 0 : (value > 2 ? 2 : (int)value); return MCB200_OK; }
-    if (!strcmp(name, "wave0_blocks")) { ctx->wave0Blocks = value < 1 ? 1 : (int)value; return MCB200_OK; }
+    if (!strcmp(name, "wave0_exact")) { ctx->wave0Exact = value != 0; return MCB200_OK; }
+    if (!strcmp(name, "wave0_blocks")) { ctx->wave0Blocks = value < 0 ? 0 : (int)value; return MCB200_OK; }   // 0 = full grid
     if (!strcmp(name, "fly_batch")) { ctx->flyBatch = value < 1 ? 1 : (value > 32 ? 32 : (int)value); return MCB200_OK; }
     if (!strcmp(name, "async_pdfs")) { ctx->asyncPdfs = value != 0; return MCB200_OK; }
     if (!strcmp(name, "sed_local")) {

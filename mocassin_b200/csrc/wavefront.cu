@@ -86,13 +86,30 @@ __global__ void __launch_bounds__(kThreads) wf_event_kernel(const __grid_constan
             }
         }
         bool toFly = valid && L.phase == PH_FLY;
+        if (EV == EV_EMIT && w.directA == 2) {
+            // pre-ordered wave 0, exact variant: packet i of the frequency order goes to slot i of
+            // the FLY array.  A packet that does not fly (escaped at emission, line packet, stop
+            // condition) leaves a hole (nuP = 0) that the FLY kernel skips; the host sets
+            // flyCount = n.  Measured slower than the appended variant below: with an exactly
+            // sorted array every resident flight starts in the same frequency plane at the star
+            // and the first crossings' reductions collide on a handful of addresses.
+            if (valid) {
+                if (toFly) {
+                    L.vx = L.dx; L.vy = L.dy; L.vz = L.dz; L.absTau = 0.f;
+                    rec_store<MULTI>(w.recA, w.recxA, L, i);
+                } else {
+                    reinterpret_cast<uint4 *>(&w.recA[i])[3] = make_uint4(0u, 0u, 0u, 0u);
+                }
+            }
+            continue;
+        }
         unsigned int pos = warp_append(toFly, w.flyCount);
         if (toFly) {
             L.vx = L.dx; L.vy = L.dy; L.vz = L.dz; L.absTau = 0.f;     // fresh flight
             if (EV == EV_EMIT && w.directA) {
-                // pre-ordered wave 0: arrival order already follows the frequency bins closely
-                // enough (within one grid-stride window), so the record goes straight to the
-                // FLY kernel's array and the counting sort is skipped
+                // pre-ordered wave 0: arrival order follows the frequency order to within one
+                // grid-stride window (the launcher keeps the grid small: < 1 bin), so the record
+                // goes straight to the FLY array and the counting sort is skipped
                 rec_store<MULTI>(w.recA, w.recxA, L, pos);
             } else {
                 rec_store<MULTI>(w.recB, w.recxB, L, pos);
@@ -188,7 +205,7 @@ __global__ void __launch_bounds__(kThreads, 4) wf_fly_kernel(const __grid_consta
                 if (take) {
                     pos = cur + rank;
                     rec_load<MULTI>(w.t, w.recA, w.recxA, L, pos);
-                    L.phase = PH_FLY;
+                    L.phase = L.nuP ? PH_FLY : PH_NEED;      // nuP = 0: hole left by the pre-ordered wave 0
                     budget = w.stepBudget;
                 }
                 unsigned int took = (unsigned int)__popc(need) < avail ? (unsigned int)__popc(need) : avail;
@@ -201,7 +218,7 @@ __global__ void __launch_bounds__(kThreads, 4) wf_fly_kernel(const __grid_consta
         }
         if (flyM == 0u) break;
         if (L.phase == PH_FLY) {
-            T.step(L, false);
+            T.step(L, false);                        // warp-aggregated tallies measured slower here too
             if (L.phase == PH_FLY && --budget <= 0) L.phase = PH_CONT;   // out of budget: continue next wave
         }
     }
