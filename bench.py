@@ -220,7 +220,9 @@ def run_reference(args):
     # size the per-step sample for ~cpu-seconds of work
     t = time.time(); c = o.transport_mt(1, 0, 400000, seed=SEED, threads=cores); dt = time.time() - t
     rate = 400000 / max(dt, 1e-6)
-    sample = int(max(400000, min(rate * args.cpu_seconds, 200_000_000)))
+    # bounded sample per step: the whole --steps/--warmup run stays within ~2.5 minutes of CPU time
+    per_step_s = min(args.cpu_seconds, 150.0 / max(args.steps + args.warmup, 1))
+    sample = int(max(400000, min(rate * per_step_s, 200_000_000)))
     first = 400000
     for _ in range(args.warmup):
         o.transport_mt(1, first, sample, seed=SEED, threads=cores); first += sample
