@@ -913,6 +913,14 @@ int mcb200_set_grid(mcb200_ctx *ctx, int32_t iG, int32_t nx, int32_t ny, int32_t
     for (auto *ax : {&g->hx, &g->hy, &g->hz})
         for (size_t i = 1; i < ax->size(); ++i)
             if (!((*ax)[i] > (*ax)[i - 1])) return fail(ctx, MCB200_EINVAL, "grid %d: axes must be strictly ascending", iG);
+    // operand range of the transport's division (div_rn, transport_core.cuh): coordinates in cm,
+    // zero or 1e-10 <= |x| <= 1e27, spacings >= 1e-10
+    for (auto *ax : {&g->hx, &g->hy, &g->hz})
+        for (size_t i = 0; i < ax->size(); ++i) {
+            float v = std::fabs((*ax)[i]);
+            if (!(v == 0.f || (v >= 1.e-10f && v <= 1.e27f)) || (i > 0 && !((*ax)[i] - (*ax)[i - 1] >= 1.e-10f)))
+                return fail(ctx, MCB200_EUNSUPPORTED, "grid %d: axis coordinates must be 0 or within 1e-10..1e27 cm, spacings >= 1e-10 cm", iG);
+        }
     size_t nTot = (size_t)nx * ny * nz;
     if (nTot >= ((size_t)1 << 31) || nx > 32000 || ny > 32000 || nz > 32000) return fail(ctx, MCB200_EINVAL, "grid %d too large for 32-bit cell indexing", iG);
     g->hactive.assign(active, active + nTot);

@@ -70,6 +70,23 @@ def test_device_division_is_ieee(cuda_lib, ctx):
         assert np.array_equal(b[ev].view(np.uint32), want.view(np.uint32))
 
 
+def test_set_grid_rejects_axes_outside_the_division_range(cuda_lib, ctx):
+    m, _ = make("hii_sym_gas")
+    e = _engine(m)
+    g = m.grids[0]
+    for bad in (1.0e28, 1.0e-12):
+        ax = g.xAxis.copy()
+        ax[-1 if bad > 1 else 1] = np.float32(bad)
+        if bad < 1:
+            ax[0] = 0.0
+        fp, ip = _lib.c_float_p, _lib.c_int32_p
+        act = np.asfortranarray(g.active, dtype=np.int32)
+        rc = cuda_lib.mcb200_set_grid(e.h, 1, g.nx, g.ny, g.nz, g.nCells, g.motherP, np.sort(ax).ctypes.data_as(fp),
+                                      g.yAxis.ctypes.data_as(fp), g.zAxis.ctypes.data_as(fp), act.ctypes.data_as(ip))
+        assert rc == -6, rc            # MCB200_EUNSUPPORTED
+    e.close()
+
+
 def test_device_philox_stream_is_identical_to_oracle(cuda_lib, oracle_lib, ctx):
     fp = _lib.c_float_p
     for seed, pid, stream in [(12345, 0, 1), (2 ** 40 + 3, 2 ** 33 + 17, 0), (0, 999999937, 7)]:
