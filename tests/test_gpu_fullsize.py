@@ -56,6 +56,11 @@ def test_conservation_and_schedule_independence_at_full_size(big):
         # every escaped packet carries deltaE: sum of the angle-0 plane == nEscaped * deltaE
         esc = out["escapedPackets"][:, :, 0].astype(np.float64).sum()
         assert abs(esc / (c["nEscaped"] * float(dE)) - 1) < 1e-6
+        # K7 at full size: the device SED is the exact cell sum of the escape counts
+        sed, cnt = e.fetch_sed()
+        assert int(cnt[:, 0].sum()) == c["nEscaped"]
+        per_nu = np.rint(out["escapedPackets"][:, 1:, 0].astype(np.float64).sum(axis=0) / float(dE)).astype(np.int64)
+        assert np.array_equal(cnt[:, 0], per_nu)
         sums.append((c["nSegments"], c["nAbs"], c["nSca"], c["nEscaped"], c["nLinePackets"]))
         if ref is None:
             ref = out
@@ -121,3 +126,32 @@ def test_oracle_subsample_at_full_size(big):
     assert np.array_equal(got["escapedPackets"], want["escapedPackets"])
     e.close()
     g.opacity = g.scaOpac = None
+
+
+def test_photo_integrals_at_full_size(big):
+    """K8 on the full table against the oracle restatement run on a sample of cells."""
+    from mocassin_b200.api import scale_estimators
+    from oracle import oracle as O
+
+    m, engine = big
+    e = engine()
+    e.zero_estimators()
+    e.energyPacketDriver(1, 2_000_000)
+    rng = np.random.default_rng(11)
+    nb = m.nbins
+    nBands = 24
+    low = rng.integers(1, nb - 10, nBands).astype(np.int32)
+    high = np.minimum(low + rng.integers(5, nb, nBands), nb).astype(np.int32)
+    xs = (1e-18 * rng.lognormal(0.0, 1.0, 4 + nBands * nb)).astype(np.float32)
+    off = (4 + np.arange(nBands) * nb).astype(np.int32)
+    e.set_xsec(xs)
+    got = e.photo_integrals(1, off, low, high)
+    J = e.fetch(1, want=["Jste"])["Jste"]
+    g = m.grids[0]
+    cells = np.concatenate([[0, 1, g.nCells], rng.integers(1, g.nCells, 400)])
+    Js, _ = scale_estimators(m, np.asfortranarray(J[cells, :]), np.zeros((1, 1, 1), np.float32))
+    wP, wH = O.photo_integrals(nb, off, low, high, xs, m.nuArray, Js)
+    assert np.array_equal(got["nPhotoSte"][cells].view(np.uint32), wP.view(np.uint32))
+    assert np.array_equal(got["heatSte"][cells].view(np.uint32), wH.view(np.uint32))
+    assert (wP > 1e-20).any()
+    e.close()
