@@ -309,6 +309,24 @@ int mcb200_fetch_qphot_counts(mcb200_ctx *ctx, int64_t *counts);
 /* Per-packet fate records of the last call (4 int32 each: segments, generations,
  * last nuP, fate); enable with mcb200_set_option("trace",1) before transport. */
 int mcb200_fetch_fates(mcb200_ctx *ctx, int32_t *fates, int64_t nPackets);
+/* Tuning and diagnostic options; none of them changes a result bit (tallies are order-independent
+ * integers, every packet owns its random stream).
+ *   "seed"          Philox seed (also the `seed` of mcb200_create)
+ *   "trace"         1: keep per-packet fate records (mcb200_fetch_fates), print phase timings
+ *   "wavefront"     -1 auto (wave-front pipeline for >= 2^17 packets per call), 0 persistent kernel, 1 wave front
+ *   "order"         persistent kernel: -1 auto / 0 / 1 process packets in order of their first frequency bin
+ *   "batch"         persistent kernel: lanes that must wait for a rare phase before it runs (12)
+ *   "agg_steps"     persistent kernel: warp-aggregate the tallies of the first n crossings (0 = off)
+ *   "blocks_per_sm" CTAs per SM of the transport kernels (0 = occupancy default)
+ *   "step_budget"   wave front: cell crossings per flight per wave (96)
+ *   "fly_batch"     wave front: idle lanes of a warp that trigger its store/claim pass (8)
+ *   "tail"          wave front: alive packets below which the persistent kernel finishes the call (32768)
+ *   "wave0_order"   wave front: 0 off, 1 auto, 2 always: emit wave 0 in first-frequency order into the FLY array
+ *   "wave0_blocks"  CTAs per SM of that emission (4; 0 = full grid); "wave0_exact" 1: exact slots (slower)
+ *   "async_pdfs"    1: mcb200_set_pdfs only enqueues the upload (see there)
+ *   "sed_local"     1: per-rank SED counts, see mcb200_fetch_sed
+ *   "tally_set", "parts", "part"   second tally set / sub-ranges of a rank's share, for overlapping the
+ *                   exchange of one half with the transport of the other (PacketEngine.energyPacketDriverOverlapped) */
 int mcb200_set_option(mcb200_ctx *ctx, const char *name, int64_t value);
 
 /* unit-test hooks: run device primitives on n inputs (host arrays in/out). */
