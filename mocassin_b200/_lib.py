@@ -82,11 +82,12 @@ def load() -> C.CDLL:
     global _lib
     if _lib is not None:
         return _lib
-    if not os.path.exists(LIB_PATH):
+    path = os.environ.get("MCB200_LIB", LIB_PATH)       # A/B builds of the same library (scripts/)
+    if not os.path.exists(path):
         raise ImportError(
-            f"{LIB_PATH} is missing: build it with `python -m mocassin_b200.build` "
+            f"{path} is missing: build it with `python -m mocassin_b200.build` "
             "(nvcc, sm_100a). mocassin_b200 has no CPU fallback.")
-    lib = C.CDLL(LIB_PATH)
+    lib = C.CDLL(path)
     for name, args in _SIGS.items():
         fn = getattr(lib, name)
         fn.argtypes = args

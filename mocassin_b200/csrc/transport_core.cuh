@@ -506,7 +506,7 @@ struct Transport {
         float num = w - r;
         float d = div_rn(num, v, ia);                // == num / v, bit for bit
         dS = moving ? d : 1.e35f;
-        if (moving && fabsf(d) < 1.e-10f) {          // sitting on the wall: snap and step over (rare,
+        if (__builtin_expect(moving && fabsf(d) < 1.e-10f, 0)) {   // sitting on the wall: snap and step over (rare,
             r = w;                                   // tiny body: reconverges immediately)
             snapped = true;
             if (pos) { if (iP < n) iP = iP + 1; else drop = drop || outer; }
@@ -578,8 +578,8 @@ struct Transport {
             wall(g.xWall, g.nx, L.vx, L.iax, L.rx, L.xP, outerXZ, dSx, drop, posx, snapped);
             wall(g.yWall, g.ny, L.vy, L.iay, L.ry, L.yP, outerY, dSy, drop, posy, snapped);
             wall(g.zWall, g.nz, L.vz, L.iaz, L.rz, L.zP, outerXZ, dSz, drop, posz, snapped);
-            if (drop) { finish(L, FATE_DROPPED); return; }
-            if ((dSx != dSx) | (dSy != dSy) | (dSz != dSz)) { fail(L, 60); return; }
+            if (__builtin_expect(drop, 0)) { finish(L, FATE_DROPPED); return; }
+            if (__builtin_expect((dSx != dSx) | (dSy != dSy) | (dSz != dSz), 0)) { fail(L, 60); return; }
             if (kInc) {
                 if (snapped) L.planeG = 0;           // indices moved: rebuild the carried table index
                 cell = 1;                            // every cell of a dense grid is active; the id is
@@ -606,7 +606,7 @@ struct Transport {
         if (fabsf(dSz) < 1.e-10f) dSz = g.zN;
         dSx = fabsf(dSx); dSy = fabsf(dSy); dSz = fabsf(dSz);
         float dS = fminf(fminf(dSx, dSy), dSz);
-        if (dS <= 0.f) {                             // :1404-1432, only if an axis end coordinate is <= 0
+        if (__builtin_expect(dS <= 0.f, 0)) {        // :1404-1432, only if an axis end coordinate is <= 0
             if (dSx <= 0.f)      dS = fminf(dSy, dSz);
             else if (dSy <= 0.f) dS = fminf(dSx, dSz);
             else                 dS = fminf(dSx, dSy);
@@ -707,7 +707,7 @@ struct Transport {
         } else {
             if (!step_tail_multi(L)) return;
         }
-        if (L.istep >= a.P.safeLimit) finish(L, FATE_DROPPED);   // :2838-2846
+        if (__builtin_expect(L.istep >= a.P.safeLimit, 0)) finish(L, FATE_DROPPED);   // :2838-2846
     }
 
     // plane-parallel tail of a non-interacting step (:2199-2414, then :2703-2726): mirror at
