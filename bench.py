@@ -310,6 +310,8 @@ def run_b200(args):
     # measured on 2 GPUs: splitting the batch in halves costs more (smaller waves, NCCL sharing
     # the SMs) than hiding half of the exchange gains -> off by default
     overlap = world > 1 and os.environ.get("MCB_OVERLAP", "0") == "1"
+    if os.environ.get("MCB_SPARSE_ESCAPED"):
+        eng.sparse_escaped = os.environ["MCB_SPARSE_ESCAPED"] == "1"
     if world > 1 and os.environ.get("MCB_SED_LOCAL", "0") == "1":
         # exchange the (nu, angle) escape counts instead of the per-cell escapedPackets tallies;
         # escapedPackets then stays rank-local (see mcb200_fetch_sed).  Off by default: the
@@ -421,6 +423,7 @@ def run_b200(args):
         "flights_per_packet": flights / (P * args.steps),
         "kernel_ms_per_step": kms_max / args.steps, "wall_ms_per_step": 1e3 * wall_max / args.steps,
         "exchange_planes": getattr(eng, "last_exchange_planes", None),
+        "escaped_exchange": getattr(eng, "last_escaped_exchange", None),
     }
     print(json.dumps(line), flush=True)
     if world > 1:

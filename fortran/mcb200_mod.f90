@@ -126,6 +126,15 @@ module mcb200_mod
        integer(c_int) function mcb200_dust_pdf(ctx, iG, dustPDF) bind(C, name="mcb200_dust_pdf")
          import; type(c_ptr), value :: ctx, dustPDF; integer(c_int32_t), value :: iG
        end function
+       ! sparse exchange of the escape counts: compact -> all-gather -> scatter (see include/mcb200.h)
+       integer(c_int) function mcb200_escaped_compact(ctx, iG, set, devList, nEntries) bind(C, name="mcb200_escaped_compact")
+         import; type(c_ptr), value :: ctx; integer(c_int32_t), value :: iG, set
+         type(c_ptr), intent(out) :: devList; integer(c_int64_t), intent(out) :: nEntries
+       end function
+       integer(c_int) function mcb200_escaped_scatter(ctx, iG, set, devList, nEntries) bind(C, name="mcb200_escaped_scatter")
+         import; type(c_ptr), value :: ctx, devList; integer(c_int32_t), value :: iG, set
+         integer(c_int64_t), value :: nEntries
+       end function
        ! head of writeSED (output_mod.f90:2561-2568): SED(1:nbins,0:nAngleBins) raw sums over cells and grids
        integer(c_int) function mcb200_fetch_sed(ctx, SED, counts) bind(C, name="mcb200_fetch_sed")
          import; type(c_ptr), value :: ctx, SED, counts

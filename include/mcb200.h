@@ -250,6 +250,17 @@ int mcb200_transport_reslines(mcb200_ctx *ctx, int32_t iStar, float deltaE, mcb2
  * (nbins+1)*(nAngleBins+1), iG ignored; see mcb200_fetch_sed, option "sed_local");
  * 16, 17, 20 = buffers 0, 1, 4 of the second tally set (option "tally_set"). */
 int mcb200_tally_buffer(mcb200_ctx *ctx, int32_t iG, int32_t which, void **devPtr, int64_t *count);
+/* Sparse form of the escapedQ exchange.  escapedPackets is indexed by the cell a packet was
+ * last emitted or scattered in, so only a few per cent of its entries are non-zero after a
+ * call: instead of all-reducing the dense array (5 GB at 128^3 x 600) each rank
+ *   1. mcb200_escaped_compact: moves its non-zero (index, count) pairs of grid iG into a device
+ *      list (uint64 index, uint64 count per entry; the array itself is cleared),
+ *   2. all-gathers the lists (NCCL all_gather, or MPI_Allgatherv on a CUDA-aware MPI),
+ *   3. mcb200_escaped_scatter: adds every rank's list (its own included) back into the array.
+ * Integer adds: the result equals the dense all-reduce bit for bit.  set = 0, or 1 for the
+ * second tally set. */
+int mcb200_escaped_compact(mcb200_ctx *ctx, int32_t iG, int32_t set, void **devList, int64_t *nEntries);
+int mcb200_escaped_scatter(mcb200_ctx *ctx, int32_t iG, int32_t set, const void *devList, int64_t nEntries);
 /* After the allreduce: fold the (now global) integer tallies of the last transport
  * call into the float32 estimators. No-op when nothing is pending. */
 int mcb200_reduce(mcb200_ctx *ctx);

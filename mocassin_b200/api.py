@@ -94,6 +94,8 @@ class PacketEngine:
         self.h = h
         self._keep = []
         self.sed_local = False
+        self.sparse_escaped = True       # N>1: exchange the escape counts as (index, count) lists
+        self.last_escaped_exchange = None
         self._upload_static()
 
     # -- plumbing ---------------------------------------------------------------------
@@ -323,6 +325,8 @@ class PacketEngine:
             self.last_exchange_planes = (sum(b - a + 1 for a, b in ranges), m.nbins + 1, len(ranges))
             whichs = [0] + ([] if self.sed_local else [1]) + ([2] if (m.lgDebug and tset == 0) else [])
             for w in whichs:
+                if w == 1 and self.sparse_escaped and not async_op and self._exchange_escaped_sparse(iG, tset, ranges, group):
+                    continue
                 ptr, n = self.tally_buffer(iG, base + w)
                 if n == 0:
                     continue
@@ -352,6 +356,43 @@ class PacketEngine:
             works.append(dist.all_reduce(_as_cuda_tensor(ptr, n, "<i8", dev), op=dist.ReduceOp.SUM, group=group,
                                          async_op=async_op))
         return [w for w in works if w is not None] if async_op else []
+
+    def _exchange_escaped_sparse(self, iG: int, tset: int, ranges, group=None) -> bool:
+        """All-gather the non-zero (index, count) pairs of the escape counts instead of
+        all-reducing the dense array (mcb200_escaped_compact / _scatter).  Returns False, with
+        the array restored, when the lists would move more bytes than the dense exchange."""
+        import torch
+        import torch.distributed as dist
+
+        m = self.model
+        dev = self._device_index()
+        world = self.nranks
+        p = C.c_void_p()
+        n = C.c_int64()
+        self._check(self.lib.mcb200_escaped_compact(self.h, iG, tset, C.byref(p), C.byref(n)))
+        n = int(n.value)
+        sizes = torch.tensor([n], dtype=torch.int64, device=f"cuda:{dev}")
+        allsz = torch.empty(world, dtype=torch.int64, device=f"cuda:{dev}")
+        dist.all_gather_into_tensor(allsz, sizes, group=group)
+        maxn = int(allsz.max().item())
+        nR = m.grids[iG - 1].nCells + 1
+        dense = 2 * 4 * nR * (m.nAngleBins + 1) * sum(b - a + 1 for a, b in ranges)
+        mine = _as_cuda_tensor(int(p.value or 0), 2 * n, "<i8", dev) if n else None
+        self.last_escaped_exchange = dict(entries=n, max_entries=maxn, sparse_bytes=16 * maxn * world, dense_bytes=dense)
+        if 16 * maxn * world >= dense:
+            if n:
+                self._check(self.lib.mcb200_escaped_scatter(self.h, iG, tset, C.c_void_p(mine.data_ptr()), n))
+            return False
+        if maxn == 0:
+            return True
+        pad = torch.zeros(2 * maxn, dtype=torch.int64, device=f"cuda:{dev}")
+        if n:
+            pad[:2 * n] = mine
+        gathered = torch.empty(2 * maxn * world, dtype=torch.int64, device=f"cuda:{dev}")
+        dist.all_gather_into_tensor(gathered, pad, group=group)
+        torch.cuda.synchronize()
+        self._check(self.lib.mcb200_escaped_scatter(self.h, iG, tset, C.c_void_p(gathered.data_ptr()), maxn * world))
+        return True
 
     def set_sed_local(self, on: bool = True):
         """Exchange the per-(nu, angle) escape counts (a few KB) instead of the per-cell

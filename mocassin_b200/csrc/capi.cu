@@ -55,6 +55,11 @@ struct OpacityArgs {
     float *opacity, *scaOpac, *absOpac;
 };
 cudaError_t launch_opacity(const OpacityArgs &A, cudaStream_t s);
+cudaError_t launch_esc_compact(unsigned int *Q, size_t off, size_t len, unsigned long long *list,
+                               unsigned long long *count, unsigned long long capacity, int clear, int blocks,
+                               cudaStream_t s);
+cudaError_t launch_esc_scatter(unsigned int *Q, size_t total, const unsigned long long *list, unsigned long long n,
+                               int blocks, cudaStream_t s);
 cudaError_t launch_sed_sum(const unsigned int *escQ, size_t nR, int firstPlane, int nPlanes,
                            unsigned long long *sedQ, cudaStream_t s);
 }  // namespace mcb
@@ -185,6 +190,7 @@ struct mcb200_ctx {
     int blocksPerSM = 0;                  // 0 = occupancy default
     // SED(nu, angle) = sum over cells and grids of escapedPackets (writeSED): integer counts of
     // the pending call on the device, raw float sums and cumulative counts on the host
+    DevBuf<unsigned long long> escList, escCount;   // sparse escape-count exchange (mcb200_escaped_compact)
     DevBuf<unsigned long long> sedQ;
     std::vector<float> sed;
     std::vector<long long> sedCount;
@@ -1405,6 +1411,63 @@ int mcb200_reduce(mcb200_ctx *ctx)
 {
     NEED_CTX();
     return fold_pending(ctx);
+}
+
+int mcb200_escaped_compact(mcb200_ctx *ctx, int32_t iG, int32_t set, void **devList, int64_t *nEntries)
+{
+    NEED_CTX();
+    GridState *g = grid_of(ctx, iG);
+    if (!g || !g->set || !devList || !nEntries) return fail(ctx, MCB200_EINVAL, "bad escaped_compact arguments");
+    if (!ctx->pending) return fail(ctx, MCB200_ESTATE, "no pending tallies");
+    unsigned int *Q = set == 1 ? g->escQ2.p : g->escQ.p;
+    const int *touched = set == 1 ? g->nuTouched2.p : g->nuTouched.p;
+    if (!Q) return fail(ctx, MCB200_ESTATE, "tally set %d not allocated", set);
+    const int nb = ctx->cfg.nbins;
+    const size_t nR = (size_t)g->nCells + 1;
+    cudaStream_t s = ctx->stream;
+    std::vector<int> flag(nb + 1, 1);
+    if (touched) {
+        CU(cudaMemcpyAsync(flag.data(), touched, sizeof(int) * (nb + 1), cudaMemcpyDeviceToHost, s));
+        CU(cudaStreamSynchronize(s));
+    }
+    auto ranges = touched_ranges(flag);
+    const int blocks = ctx->numSMs * 8;
+    CU(ctx->escCount.alloc(1));
+    // pass 1: count; pass 2: fill and clear (the scatter of every rank's list rebuilds the sum)
+    for (int pass = 0; pass < 2; ++pass) {
+        CU(ctx->escCount.zero(s));
+        unsigned long long cap = pass ? ctx->escList.n / 2 : 0;
+        for (auto &rg : ranges)
+            for (int ang = 0; ang <= ctx->cfg.nAngleBins; ++ang) {
+                size_t off = nR * ((size_t)rg.first + (size_t)(nb + 1) * (size_t)ang);
+                size_t len = (size_t)(rg.second - rg.first + 1) * nR;
+                CU(launch_esc_compact(Q, off, len, pass ? ctx->escList.p : nullptr, ctx->escCount.p, cap, pass, blocks, s));
+            }
+        unsigned long long n = 0;
+        CU(cudaMemcpyAsync(&n, ctx->escCount.p, 8, cudaMemcpyDeviceToHost, s));
+        CU(cudaStreamSynchronize(s));
+        if (!pass) {
+            if (ctx->escList.n < 2 * n || ctx->escList.n > 8 * n + 1024) CU(ctx->escList.alloc((size_t)(2 * n > 2 ? 2 * n : 2)));
+        } else {
+            *nEntries = (int64_t)n;
+        }
+    }
+    *devList = ctx->escList.p;
+    return MCB200_OK;
+}
+
+int mcb200_escaped_scatter(mcb200_ctx *ctx, int32_t iG, int32_t set, const void *devList, int64_t nEntries)
+{
+    NEED_CTX();
+    GridState *g = grid_of(ctx, iG);
+    if (!g || !g->set || (nEntries > 0 && !devList) || nEntries < 0) return fail(ctx, MCB200_EINVAL, "bad escaped_scatter arguments");
+    unsigned int *Q = set == 1 ? g->escQ2.p : g->escQ.p;
+    if (!Q) return fail(ctx, MCB200_ESTATE, "tally set %d not allocated", set);
+    size_t total = set == 1 ? g->escQ2.n : g->escQ.n;
+    CU(launch_esc_scatter(Q, total, reinterpret_cast<const unsigned long long *>(devList), (unsigned long long)nEntries,
+                          ctx->numSMs * 8, ctx->stream));
+    CU(cudaStreamSynchronize(ctx->stream));
+    return MCB200_OK;
 }
 
 int mcb200_fetch_sed(mcb200_ctx *ctx, float *SED, int64_t *counts)

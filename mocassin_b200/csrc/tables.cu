@@ -94,6 +94,63 @@ __global__ void fold_count_kernel(unsigned int *__restrict__ Q, float *__restric
     }
 }
 
+// ---------------------------------------------------------------------------------------
+// Sparse exchange of the escape counts (multi-rank): escapedQ is indexed by the cell a packet
+// was last emitted or scattered in, so only a few per cent of its 1.26e9 entries are non-zero.
+// compact: (index, count) pairs of the non-zero entries of a range, appended with one atomic
+// per warp; scatter: add a list of pairs into the array (exact integer adds, any order).
+// ---------------------------------------------------------------------------------------
+__global__ void esc_compact_kernel(unsigned int *__restrict__ Q, size_t off, size_t len,
+                                   unsigned long long *__restrict__ list, unsigned long long *count,
+                                   unsigned long long capacity, int clear)
+{
+    size_t i0 = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    size_t stride = (size_t)gridDim.x * blockDim.x;
+    const unsigned int lane = threadIdx.x & 31u;
+    for (size_t base = i0 - lane; base < len; base += stride) {
+        size_t i = base + lane;
+        unsigned int q = i < len ? Q[off + i] : 0u;
+        unsigned int m = __ballot_sync(0xffffffffu, q != 0u);
+        if (!m) continue;
+        unsigned long long p = 0;
+        if (lane == 0) p = atomicAdd(count, (unsigned long long)__popc(m));
+        p = __shfl_sync(0xffffffffu, p, 0) + __popc(m & ((1u << lane) - 1u));
+        if (q != 0u) {
+            if (list && p < capacity) { list[2 * p] = (unsigned long long)(off + i); list[2 * p + 1] = q; }
+            if (clear) Q[off + i] = 0u;
+        }
+    }
+}
+
+__global__ void esc_scatter_kernel(unsigned int *__restrict__ Q, size_t total, const unsigned long long *__restrict__ list,
+                                   unsigned long long n)
+{
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    size_t stride = (size_t)gridDim.x * blockDim.x;
+    for (; i < n; i += stride) {
+        unsigned long long idx = list[2 * i];
+        unsigned int q = (unsigned int)list[2 * i + 1];
+        if (q && idx < total) atomicAdd(&Q[idx], q);
+    }
+}
+
+cudaError_t launch_esc_compact(unsigned int *Q, size_t off, size_t len, unsigned long long *list,
+                               unsigned long long *count, unsigned long long capacity, int clear, int blocks,
+                               cudaStream_t s)
+{
+    if (len == 0) return cudaSuccess;
+    esc_compact_kernel<<<blocks, 256, 0, s>>>(Q, off, len, list, count, capacity, clear);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_esc_scatter(unsigned int *Q, size_t total, const unsigned long long *list, unsigned long long n,
+                               int blocks, cudaStream_t s)
+{
+    if (n == 0) return cudaSuccess;
+    esc_scatter_kernel<<<blocks, 256, 0, s>>>(Q, total, list, n);
+    return cudaGetLastError();
+}
+
 // merge the second tally set into the first (exact integer adds) and clear it
 __global__ void merge_sets_kernel(unsigned long long *__restrict__ J0, unsigned long long *__restrict__ J1, size_t nJ,
                                   unsigned int *__restrict__ E0, unsigned int *__restrict__ E1, size_t nE,

@@ -21,7 +21,7 @@ def _free_port():
     return p
 
 
-def _worker(rank, world, port, name, n, q, overlap=False, sed_local=False):
+def _worker(rank, world, port, name, n, q, overlap=False, sed_local=False, sparse=True):
     sys.path.insert(0, ROOT)
     sys.path.insert(0, os.path.join(ROOT, "tests"))
     import torch
@@ -39,12 +39,15 @@ def _worker(rank, world, port, name, n, q, overlap=False, sed_local=False):
     e.upload_iteration_inputs()
     if sed_local:
         e.set_sed_local(True)
+    e.sparse_escaped = sparse
     if overlap:
         e.zero_estimators()
         e.energyPacketDriverOverlapped(1, n)
     else:
         e.lucy_transport([n])
     out = [e.fetch(iG) for iG in range(1, m.nGrids + 1)]
+    if sparse and not overlap and not sed_local:
+        assert e.last_escaped_exchange is not None
     if sed_local:
         out.append(e.fetch_sed())
     q.put((rank, out))
@@ -53,9 +56,10 @@ def _worker(rank, world, port, name, n, q, overlap=False, sed_local=False):
     dist.destroy_process_group()
 
 
-@pytest.mark.parametrize("overlap", [False, True])
-@pytest.mark.parametrize("name", ["multigrid_sym", "cube_clumpy_gasdust"])
-def test_nccl_allreduce_matches_single_gpu(name, overlap):
+@pytest.mark.parametrize("name,overlap,sparse", [("multigrid_sym", False, True), ("multigrid_sym", True, True),
+                                                 ("cube_clumpy_gasdust", False, True), ("cube_clumpy_gasdust", True, True),
+                                                 ("viewing_angles", False, True), ("multigrid_sym", False, False)])
+def test_nccl_allreduce_matches_single_gpu(name, overlap, sparse):
     import torch
     import torch.multiprocessing as mp
 
@@ -69,7 +73,7 @@ def test_nccl_allreduce_matches_single_gpu(name, overlap):
     ctx = mp.get_context("spawn")
     q = ctx.Queue()
     port = _free_port()
-    procs = [ctx.Process(target=_worker, args=(r, 2, port, name, n, q, overlap)) for r in range(2)]
+    procs = [ctx.Process(target=_worker, args=(r, 2, port, name, n, q, overlap, False, sparse)) for r in range(2)]
     for p in procs:
         p.start()
     got = dict(q.get(timeout=600) for _ in range(2))
