@@ -310,6 +310,10 @@ def run_b200(args):
     # measured on 2 GPUs: splitting the batch in halves costs more (smaller waves, NCCL sharing
     # the SMs) than hiding half of the exchange gains -> off by default
     overlap = world > 1 and os.environ.get("MCB_OVERLAP", "0") == "1"
+    if os.environ.get("MCB_PIPELINED_FOLD"):
+        eng.pipelined_fold = os.environ["MCB_PIPELINED_FOLD"] == "1"
+    if os.environ.get("MCB_CHUNK_PLANES"):
+        eng.exchange_chunk_planes = int(os.environ["MCB_CHUNK_PLANES"])
     if os.environ.get("MCB_SPARSE_ESCAPED"):
         eng.sparse_escaped = os.environ["MCB_SPARSE_ESCAPED"] == "1"
     if world > 1 and os.environ.get("MCB_SED_LOCAL", "0") == "1":

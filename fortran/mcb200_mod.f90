@@ -126,6 +126,9 @@ module mcb200_mod
        integer(c_int) function mcb200_dust_pdf(ctx, iG, dustPDF) bind(C, name="mcb200_dust_pdf")
          import; type(c_ptr), value :: ctx, dustPDF; integer(c_int32_t), value :: iG
        end function
+       integer(c_int) function mcb200_reduce_range(ctx, iG, nu0, nu1) bind(C, name="mcb200_reduce_range")
+         import; type(c_ptr), value :: ctx; integer(c_int32_t), value :: iG, nu0, nu1
+       end function
        ! sparse exchange of the escape counts: compact -> all-gather -> scatter (see include/mcb200.h)
        integer(c_int) function mcb200_escaped_compact(ctx, iG, set, devList, nEntries) bind(C, name="mcb200_escaped_compact")
          import; type(c_ptr), value :: ctx; integer(c_int32_t), value :: iG, set

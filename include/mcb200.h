@@ -250,6 +250,12 @@ int mcb200_transport_reslines(mcb200_ctx *ctx, int32_t iStar, float deltaE, mcb2
  * (nbins+1)*(nAngleBins+1), iG ignored; see mcb200_fetch_sed, option "sed_local");
  * 16, 17, 20 = buffers 0, 1, 4 of the second tally set (option "tally_set"). */
 int mcb200_tally_buffer(mcb200_ctx *ctx, int32_t iG, int32_t which, void **devPtr, int64_t *count);
+/* Fold only the nu-planes [nu0, nu1] of grid iG (J planes nu >= 1, escape-count planes nu0..nu1 of
+ * every angle) and return without waiting: lets the caller fold the planes whose all-reduce has
+ * finished while later planes are still being exchanged.  mcb200_reduce afterwards folds whatever
+ * is left and closes the call.  Not available while a second tally set is pending. */
+int mcb200_reduce_range(mcb200_ctx *ctx, int32_t iG, int32_t nu0, int32_t nu1);
+
 /* Sparse form of the escapedQ exchange.  escapedPackets is indexed by the cell a packet was
  * last emitted or scattered in, so only a few per cent of its entries are non-zero after a
  * call: instead of all-reducing the dense array (5 GB at 128^3 x 600) each rank

@@ -53,6 +53,7 @@ _SIGS = {
     "mcb200_dust_pdf": [C.c_void_p, C.c_int32, c_float_p],
     "mcb200_photo_integrals": [C.c_void_p, C.c_int32, C.c_int32, c_int32_p, c_int32_p, c_int32_p,
                                c_float_p, c_float_p, c_float_p, c_float_p],
+    "mcb200_reduce_range": [C.c_void_p, C.c_int32, C.c_int32, C.c_int32],
     "mcb200_escaped_compact": [C.c_void_p, C.c_int32, C.c_int32, C.POINTER(C.c_void_p), C.POINTER(C.c_int64)],
     "mcb200_escaped_scatter": [C.c_void_p, C.c_int32, C.c_int32, C.c_void_p, C.c_int64],
     "mcb200_fetch_sed": [C.c_void_p, c_float_p, C.POINTER(C.c_int64)],

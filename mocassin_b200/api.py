@@ -95,6 +95,8 @@ class PacketEngine:
         self._keep = []
         self.sed_local = False
         self.sparse_escaped = True       # N>1: exchange the escape counts as (index, count) lists
+        self.pipelined_fold = False      # N>1: fold plane chunks while later chunks are exchanged (measured: no gain)
+        self.exchange_chunk_planes = 64
         self.last_escaped_exchange = None
         self._upload_static()
 
@@ -410,6 +412,56 @@ class PacketEngine:
         self._check(self.lib.mcb200_fetch_sed(self.h, _fp(sed), cnt.ctypes.data_as(C.POINTER(C.c_int64))))
         return sed, cnt
 
+    def _exchange_pipelined(self, group=None) -> bool:
+        """Exchange with the fold hidden behind it: the escape counts go first (sparse), then
+        the touched JsteQ planes are all-reduced in chunks on NCCL's stream and every chunk is
+        folded (mcb200_reduce_range, library stream) as soon as it has arrived, while the next
+        chunk is in flight.  Returns False if the plain path has to be used."""
+        import torch
+        import torch.distributed as dist
+
+        m = self.model
+        if m.lgDebug or self.sed_local or not self.sparse_escaped:
+            return False
+        dev = self._device_index()
+        plan = []
+        for iG in range(1, m.nGrids + 1):
+            nR = m.grids[iG - 1].nCells + 1
+            fptr, fn = self.tally_buffer(iG, 4)
+            flags = _as_cuda_tensor(fptr, fn, "<i4", dev)
+            dist.all_reduce(flags, op=dist.ReduceOp.MAX, group=group)
+            ranges = _touched_ranges(flags.cpu().numpy())
+            self.last_exchange_planes = (sum(b - a + 1 for a, b in ranges), m.nbins + 1, len(ranges))
+            if not self._exchange_escaped_sparse(iG, 0, ranges, group):
+                # dense fallback for the escape counts, then the plain fold
+                ptr, n = self.tally_buffer(iG, 1)
+                t = _as_cuda_tensor(ptr, n, "<i4", dev)
+                for p0, p1 in ranges:
+                    for ang in range(m.nAngleBins + 1):
+                        off = nR * (p0 + (m.nbins + 1) * ang)
+                        dist.all_reduce(t[off:off + (p1 - p0 + 1) * nR], op=dist.ReduceOp.SUM, group=group)
+            ptr, n = self.tally_buffer(iG, 0)
+            t = _as_cuda_tensor(ptr, n, "<i8", dev)
+            step = max(1, self.exchange_chunk_planes)
+            for p0, p1 in ranges:
+                a = p0
+                while a <= p1:
+                    b = min(a + step - 1, p1)
+                    q0 = max(a, 1)
+                    w = dist.all_reduce(t[(q0 - 1) * nR:b * nR], op=dist.ReduceOp.SUM, group=group, async_op=True) if b >= q0 else None
+                    plan.append((iG, a, b, w))
+                    a = b + 1
+            if m.lgPlaneIonization and iG == 1:
+                ptr, n = self.tally_buffer(1, 5)
+                if n:
+                    dist.all_reduce(_as_cuda_tensor(ptr, n, "<i4", dev), op=dist.ReduceOp.SUM, group=group)
+        for iG, a, b, w in plan:
+            if w is not None:
+                w.wait()
+            torch.cuda.current_stream().synchronize()
+            self._check(self.lib.mcb200_reduce_range(self.h, iG, a, b))
+        return True
+
     def reduce(self, group=None):
         """Sum the pending integer tallies over ranks and fold them into the float32
         estimators.  Exact integer sums -> identical bits on every rank and for every rank
@@ -417,7 +469,8 @@ class PacketEngine:
         if self.nranks > 1:
             import torch
 
-            self._exchange(0, group)
+            if not (self.pipelined_fold and self._exchange_pipelined(group)):
+                self._exchange(0, group)
             torch.cuda.synchronize()
         self._check(self.lib.mcb200_reduce(self.h))
 

@@ -117,6 +117,7 @@ struct GridState {
     DevBuf<unsigned int> escQ2;
     DevBuf<int> nuTouched2;
     DevBuf<float> Jste, Jdif, esc, linePk;
+    std::vector<char> folded;             // nu-planes of the pending call already folded by mcb200_reduce_range
     // dust closure (mcb200_dust_update / mcb200_dust_pdf): device copy of the dust state
     DevBuf<float> Tdust;
     DevBuf<int> dustAbun, lgConverged;
@@ -184,7 +185,7 @@ struct mcb200_ctx {
     DevBuf<unsigned int> resPrefix;
     DevBuf<unsigned short> wfFlyKey;
     DevBuf<unsigned long long> wfNext;
-    int lastWaves = 0, lastLaunches = 0, lastFoldLaunches = 0;
+    int lastWaves = 0, lastLaunches = 0, lastFoldLaunches = 0, rangeFoldLaunches = 0;
     int aggSteps = 0, batch = 12;
     bool trace = false;
     int blocksPerSM = 0;                  // 0 = occupancy default
@@ -341,13 +342,13 @@ int ensure_second_set(mcb200_ctx *ctx, GridState &g)
 }
 
 // contiguous runs [first,last] of touched frequency bins (gaps of <= 2 bins are bridged)
-std::vector<std::pair<int, int>> touched_ranges(const std::vector<int> &flag)
+std::vector<std::pair<int, int>> touched_ranges(const std::vector<int> &flag, int bridge = 3)
 {
     std::vector<std::pair<int, int>> r;
     int n = (int)flag.size();
     for (int i = 0; i < n; ++i) {
         if (!flag[i]) continue;
-        if (!r.empty() && i - r.back().second <= 3) r.back().second = i;
+        if (!r.empty() && i - r.back().second <= bridge) r.back().second = i;
         else r.emplace_back(i, i);
     }
     return r;
@@ -381,12 +382,40 @@ int sed_tally(mcb200_ctx *ctx, int set, int *launches)
             CU(cudaMemcpyAsync(flag.data(), touched, sizeof(int) * (nb + 1), cudaMemcpyDeviceToHost, ctx->stream));
             CU(cudaStreamSynchronize(ctx->stream));
         }
-        for (auto &rg : touched_ranges(flag))
+        if (set == 0 && !g.folded.empty())           // planes a ranged fold has already tallied and cleared
+            for (int nu = 0; nu <= nb; ++nu) if (g.folded[nu]) flag[nu] = 0;
+        for (auto &rg : touched_ranges(flag, g.folded.empty() ? 3 : 1))
             for (int ang = 0; ang <= ctx->cfg.nAngleBins; ++ang)
             {
                 CU(launch_sed_sum(q, nR, rg.first + (nb + 1) * ang, rg.second - rg.first + 1, ctx->sedQ.p, ctx->stream));
                 if (launches) ++*launches;
             }
+    }
+    return MCB200_OK;
+}
+
+// fold the tallies of the nu-planes [nu0, nu1] of one grid: J planes nu >= 1, escape-count planes
+// nu0..nu1 of every viewing angle.  Asynchronous on the library stream.
+int fold_planes(mcb200_ctx *ctx, GridState &g, int nu0, int nu1, int *launches)
+{
+    const int nb = ctx->cfg.nbins, blocks = ctx->numSMs * 8;
+    const size_t nR = (size_t)g.nCells + 1;
+    const double lenUnit = std::ldexp(1.0, g.lenExp);
+    int p0 = nu0 < 1 ? 1 : nu0, p1 = nu1;
+    if (p1 >= p0) {
+        size_t off = (size_t)(p0 - 1) * nR, len = (size_t)(p1 - p0 + 1) * nR;
+        CU(launch_fold_j(g.JsteQ.p + off, g.Jste.p + off, g.dV.p, (int)nR, len, lenUnit, ctx->pendingDeltaE, blocks, ctx->stream));
+        if (launches) ++*launches;
+        if (ctx->cfg.lgDebug) {
+            CU(launch_fold_j(g.JdifQ.p + off, g.Jdif.p + off, g.dV.p, (int)nR, len, lenUnit, ctx->pendingDeltaE, blocks, ctx->stream));
+            if (launches) ++*launches;
+        }
+    }
+    for (int ang = 0; ang <= ctx->cfg.nAngleBins; ++ang) {
+        size_t off = nR * ((size_t)nu0 + (size_t)(nb + 1) * (size_t)ang);
+        size_t len = (size_t)(nu1 - nu0 + 1) * nR;
+        CU(launch_fold_count(g.escQ.p + off, g.esc.p + off, len, ctx->pendingDeltaE, blocks, ctx->stream));
+        if (launches) ++*launches;
     }
     return MCB200_OK;
 }
@@ -426,32 +455,20 @@ int fold_pending(mcb200_ctx *ctx)
         ctx->sedReady = false;
     }
     for (auto &g : ctx->grids) {
-        size_t nR = (size_t)g.nCells + 1;
-        double lenUnit = std::ldexp(1.0, g.lenExp);
         // only nu-planes in which a packet was emitted can hold tallies
         std::vector<int> flag(nb + 1, 1);
         if (g.nuTouched.p) {
             CU(cudaMemcpyAsync(flag.data(), g.nuTouched.p, sizeof(int) * (nb + 1), cudaMemcpyDeviceToHost, ctx->stream));
             CU(cudaStreamSynchronize(ctx->stream));
         }
-        for (auto &rg : touched_ranges(flag)) {
-            int p0 = rg.first < 1 ? 1 : rg.first, p1 = rg.second;
-            if (p1 >= p0) {
-                size_t off = (size_t)(p0 - 1) * nR, len = (size_t)(p1 - p0 + 1) * nR;
-                CU(launch_fold_j(g.JsteQ.p + off, g.Jste.p + off, g.dV.p, (int)nR, len, lenUnit, ctx->pendingDeltaE, blocks, ctx->stream));
-                ++launches;
-                if (ctx->cfg.lgDebug) {
-                    CU(launch_fold_j(g.JdifQ.p + off, g.Jdif.p + off, g.dV.p, (int)nR, len, lenUnit, ctx->pendingDeltaE, blocks, ctx->stream));
-                    ++launches;
-                }
-            }
-            for (int ang = 0; ang <= ctx->cfg.nAngleBins; ++ang) {
-                size_t off = nR * ((size_t)rg.first + (size_t)(nb + 1) * (size_t)ang);
-                size_t len = (size_t)(rg.second - rg.first + 1) * nR;
-                CU(launch_fold_count(g.escQ.p + off, g.esc.p + off, len, ctx->pendingDeltaE, blocks, ctx->stream));
-                ++launches;
-            }
+        // planes a ranged fold (mcb200_reduce_range) has already taken are skipped
+        if (!g.folded.empty())
+            for (int nu = 0; nu <= nb; ++nu) if (g.folded[nu]) flag[nu] = 0;
+        for (auto &rg : touched_ranges(flag, g.folded.empty() ? 3 : 1)) {
+            int rc = fold_planes(ctx, g, rg.first, rg.second, &launches);
+            if (rc) return rc;
         }
+        g.folded.clear();
         if (ctx->cfg.lgDebug && g.lineQ.n) {
             CU(launch_fold_count(g.lineQ.p, g.linePk.p, g.lineQ.n, ctx->pendingDeltaE, blocks, ctx->stream));
             ++launches;
@@ -1411,6 +1428,31 @@ int mcb200_reduce(mcb200_ctx *ctx)
 {
     NEED_CTX();
     return fold_pending(ctx);
+}
+
+int mcb200_reduce_range(mcb200_ctx *ctx, int32_t iG, int32_t nu0, int32_t nu1)
+{
+    NEED_CTX();
+    GridState *g = grid_of(ctx, iG);
+    if (!g || !g->set) return fail(ctx, MCB200_ESTATE, "grid %d not set", iG);
+    const int nb = ctx->cfg.nbins;
+    if (nu0 < 0 || nu1 > nb || nu1 < nu0) return fail(ctx, MCB200_EINVAL, "bad plane range %d..%d", nu0, nu1);
+    if (!ctx->pending) return MCB200_OK;
+    if (ctx->pending2) return fail(ctx, MCB200_ESTATE, "second tally set pending: use mcb200_reduce");
+    int rc = ensure_sed(ctx);
+    if (rc) return rc;
+    int launches = 0;
+    if (!ctx->sedReady)                  // the SED counts of these planes, before the fold clears them
+        for (int ang = 0; ang <= ctx->cfg.nAngleBins; ++ang) {
+            CU(launch_sed_sum(g->escQ.p, (size_t)g->nCells + 1, nu0 + (nb + 1) * ang, nu1 - nu0 + 1, ctx->sedQ.p, ctx->stream));
+            ++launches;
+        }
+    rc = fold_planes(ctx, *g, nu0, nu1, &launches);
+    if (rc) return rc;
+    if (g->folded.empty()) g->folded.assign(nb + 1, 0);
+    for (int nu = nu0; nu <= nu1; ++nu) g->folded[nu] = 1;
+    ctx->rangeFoldLaunches += launches;
+    return MCB200_OK;
 }
 
 int mcb200_escaped_compact(mcb200_ctx *ctx, int32_t iG, int32_t set, void **devList, int64_t *nEntries)

@@ -21,7 +21,7 @@ def _free_port():
     return p
 
 
-def _worker(rank, world, port, name, n, q, overlap=False, sed_local=False, sparse=True):
+def _worker(rank, world, port, name, n, q, overlap=False, sed_local=False, sparse=True, pipelined=False):
     sys.path.insert(0, ROOT)
     sys.path.insert(0, os.path.join(ROOT, "tests"))
     import torch
@@ -40,6 +40,7 @@ def _worker(rank, world, port, name, n, q, overlap=False, sed_local=False, spars
     if sed_local:
         e.set_sed_local(True)
     e.sparse_escaped = sparse
+    e.pipelined_fold = pipelined
     if overlap:
         e.zero_estimators()
         e.energyPacketDriverOverlapped(1, n)
@@ -58,8 +59,11 @@ def _worker(rank, world, port, name, n, q, overlap=False, sed_local=False, spars
 
 @pytest.mark.parametrize("name,overlap,sparse", [("multigrid_sym", False, True), ("multigrid_sym", True, True),
                                                  ("cube_clumpy_gasdust", False, True), ("cube_clumpy_gasdust", True, True),
-                                                 ("viewing_angles", False, True), ("multigrid_sym", False, False)])
+                                                 ("viewing_angles", False, True), ("multigrid_sym", False, False),
+                                                 ("multigrid_sym", "pipelined", True)])
 def test_nccl_allreduce_matches_single_gpu(name, overlap, sparse):
+    pipelined = overlap == "pipelined"
+    overlap = overlap is True
     import torch
     import torch.multiprocessing as mp
 
@@ -73,7 +77,7 @@ def test_nccl_allreduce_matches_single_gpu(name, overlap, sparse):
     ctx = mp.get_context("spawn")
     q = ctx.Queue()
     port = _free_port()
-    procs = [ctx.Process(target=_worker, args=(r, 2, port, name, n, q, overlap, False, sparse)) for r in range(2)]
+    procs = [ctx.Process(target=_worker, args=(r, 2, port, name, n, q, overlap, False, sparse, pipelined)) for r in range(2)]
     for p in procs:
         p.start()
     got = dict(q.get(timeout=600) for _ in range(2))
