@@ -46,7 +46,8 @@ def _worker(rank, world, port, name, n, q, overlap=False, sed_local=False, spars
         e.energyPacketDriverOverlapped(1, n)
     else:
         e.lucy_transport([n])
-    out = [e.fetch(iG) for iG in range(1, m.nGrids + 1)]
+    want = ["Jste", "escapedPackets"] + (["Jdif", "linePackets"] if m.lgDebug else [])
+    out = [e.fetch(iG, want=want) for iG in range(1, m.nGrids + 1)]
     if sparse and not overlap and not sed_local:
         assert e.last_escaped_exchange is not None
     if sed_local:
@@ -60,7 +61,7 @@ def _worker(rank, world, port, name, n, q, overlap=False, sed_local=False, spars
 @pytest.mark.parametrize("name,overlap,sparse", [("multigrid_sym", False, True), ("multigrid_sym", True, True),
                                                  ("cube_clumpy_gasdust", False, True), ("cube_clumpy_gasdust", True, True),
                                                  ("viewing_angles", False, True), ("multigrid_sym", False, False),
-                                                 ("multigrid_sym", "pipelined", True)])
+                                                 ("multigrid_sym", "pipelined", True), ("hii_sym_gas_debug", False, True)])
 def test_nccl_allreduce_matches_single_gpu(name, overlap, sparse):
     pipelined = overlap == "pipelined"
     overlap = overlap is True
@@ -88,11 +89,12 @@ def test_nccl_allreduce_matches_single_gpu(name, overlap, sparse):
     e = PacketEngine(m, seed=12345)
     e.upload_iteration_inputs()
     e.lucy_transport([n])
+    want = ["Jste", "escapedPackets"] + (["Jdif", "linePackets"] if m.lgDebug else [])
     for iG in range(1, m.nGrids + 1):
-        ref = e.fetch(iG)
+        ref = e.fetch(iG, want=want)
         for r in (0, 1):
-            assert np.array_equal(got[r][iG - 1]["Jste"], ref["Jste"])
-            assert np.array_equal(got[r][iG - 1]["escapedPackets"], ref["escapedPackets"])
+            for k in want:
+                assert np.array_equal(got[r][iG - 1][k], ref[k]), (iG, r, k)
     e.close()
 
 
