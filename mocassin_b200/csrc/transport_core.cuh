@@ -194,9 +194,11 @@ __device__ __forceinline__ unsigned long long packet_pid(const TransportArgs &a,
     return (1ull << 40) + a.resCells[c].gid + (unsigned long long)(k - (long long)a.resPrefix[c]);
 }
 
-// PLAIN: the call has neither debug tallies nor plane-parallel illumination (compile-time
-// false for both flags; chosen by the launcher), so their tests leave the crossing loop.
-template <bool MULTI, bool DENSE = false, bool PLAIN = false>
+// MODE (chosen by the launcher from the call's flags, so their tests leave the crossing loop):
+// 0 generic; 1 neither debug tallies nor plane-parallel illumination; 2 = 1 and not symmetricXYZ.
+// LIMIT = false: the caller (FLY kernel) folds the iteration limit of :2838-2846 into its own
+// per-flight step budget instead of testing it on every crossing.
+template <bool MULTI, bool DENSE = false, int MODE = 0, bool LIMIT = true>
 struct Transport {
     // single dense grid: the table index of the packet's cell is carried along and advanced with
     // the cell indices instead of being rebuilt from (x,y,z) on every crossing
@@ -213,8 +215,9 @@ struct Transport {
         if (MULTI) return a.grids[gP - 1];
         return a.g1;
     }
-    __device__ __forceinline__ bool debug() const { return PLAIN ? false : (bool)a.P.lgDebug; }
-    __device__ __forceinline__ bool plane() const { return PLAIN ? false : (bool)a.P.lgPlane; }
+    __device__ __forceinline__ bool debug() const { return MODE >= 1 ? false : (bool)a.P.lgDebug; }
+    __device__ __forceinline__ bool plane() const { return MODE >= 1 ? false : (bool)a.P.lgPlane; }
+    __device__ __forceinline__ bool sym() const { return MODE == 2 ? false : (bool)a.P.lgSym; }
     __device__ __forceinline__ void count(int which) { cnt[which * kThreads + threadIdx.x]++; }
     __device__ __forceinline__ void fail(Lane &L, int code)
     {
@@ -564,7 +567,7 @@ struct Transport {
                 }
             }
             const DevGrid &g = G(L.gP);
-            if (P.lgSym) {               // :1248-1261 (always against the mother grid's first point)
+            if (sym()) {                 // :1248-1261 (always against the mother grid's first point)
                 const DevGrid &m = G(1);
                 if (L.rx <= m.x1) { L.vx = fabsf(L.vx); L.rx = m.x1; }
                 if (L.ry <= m.y1) { L.vy = fabsf(L.vy); L.ry = m.y1; }
@@ -626,7 +629,7 @@ struct Transport {
             L.ry = L.ry + dlLoc * L.vy;
             L.rz = L.rz + dlLoc * L.vz;
             if (!(L.rx >= 0.f || L.rx < 0.f) || !(L.ry >= 0.f || L.ry < 0.f) || !(L.rz >= 0.f || L.rz < 0.f)) { fail(L, 65); return; }
-            if (P.lgSym && L.gP == 1) {
+            if (sym() && L.gP == 1) {
                 if (L.rx <= g.x1) { L.vx = fabsf(L.vx); L.rx = g.x1; }
                 if (L.ry <= g.y1) { L.vy = fabsf(L.vy); L.ry = g.y1; }
                 if (L.rz <= g.z1) { L.vz = fabsf(L.vz); L.rz = g.z1; }
@@ -697,9 +700,9 @@ struct Transport {
                        (L.xP > g.nx) | (L.yP > g.ny) | (L.zP > g.nz);
             bool low = (L.rx <= g.xLo) | (L.ry <= g.yLo) | (L.rz <= g.zLo) |
                        (L.xP < 1) | (L.yP < 1) | (L.zP < 1);
-            out = out | (low & !P.lgSym);
+            out = out | (low & !sym());
             if (out) { escape(L, FATE_ESCAPED); return; }
-            if (P.lgSym) {               // :2674-2699
+            if (sym()) {                 // :2674-2699
                 if (L.rx <= g.x1 || L.xP < 1) { L.vx = fabsf(L.vx); L.xP = 1; L.rx = g.x1; if (kInc) L.planeG = 0; }
                 if (L.ry <= g.y1 || L.yP < 1) { L.vy = fabsf(L.vy); L.yP = 1; L.ry = g.y1; if (kInc) L.planeG = 0; }
                 if (L.rz <= g.z1 || L.zP < 1) { L.vz = fabsf(L.vz); L.zP = 1; L.rz = g.z1; if (kInc) L.planeG = 0; }
@@ -707,7 +710,7 @@ struct Transport {
         } else {
             if (!step_tail_multi(L)) return;
         }
-        if (__builtin_expect(L.istep >= a.P.safeLimit, 0)) finish(L, FATE_DROPPED);   // :2838-2846
+        if (LIMIT && __builtin_expect(L.istep >= a.P.safeLimit, 0)) finish(L, FATE_DROPPED);   // :2838-2846
     }
 
     // plane-parallel tail of a non-interacting step (:2199-2414, then :2703-2726): mirror at

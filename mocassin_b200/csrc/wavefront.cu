@@ -125,12 +125,13 @@ __global__ void __launch_bounds__(kThreads) wf_event_kernel(const __grid_constan
 // atomic per chunk, records of the chunk prefetched into L2) and cross cells until the next
 // event; ended flights are written back in place and their positions staged per warp in
 // shared memory, flushed 32 at a time (one global atomic per 32 events, coalesced stores).
-template <bool MULTI, bool DENSE, bool PLAIN>
+template <bool MULTI, bool DENSE, int MODE>
 __global__ void __launch_bounds__(kThreads, 4) wf_fly_kernel(const __grid_constant__ WfArgs w)
 {
     extern __shared__ unsigned int smem[];
     scratch_init(smem, w.t.P.nbins);
-    Transport<MULTI, DENSE, PLAIN> T(w.t, smem, smem + C_COUNT * kThreads);
+    // single grid: the per-crossing iteration-limit test is folded into the step budget below
+    Transport<MULTI, DENSE, MODE, MULTI> T(w.t, smem, smem + C_COUNT * kThreads);
     unsigned int *stage = smem + scratch_words(w.t.P.nbins) + (threadIdx.x >> 5) * (EV_COUNT * kStage);
     const unsigned int FULL = 0xffffffffu;
     const unsigned int lane = threadIdx.x & 31u;
@@ -207,6 +208,10 @@ __global__ void __launch_bounds__(kThreads, 4) wf_fly_kernel(const __grid_consta
                     rec_load<MULTI>(w.t, w.recA, w.recxA, L, pos);
                     L.phase = L.nuP ? PH_FLY : PH_NEED;      // nuP = 0: hole left by the pre-ordered wave 0
                     budget = w.stepBudget;
+                    if (!MULTI) {                            // never run past the iteration limit (:2838-2846)
+                        int left = w.t.P.safeLimit - L.istep;
+                        budget = left < budget ? (left < 1 ? 1 : left) : budget;
+                    }
                 }
                 unsigned int took = (unsigned int)__popc(need) < avail ? (unsigned int)__popc(need) : avail;
                 cur += took;
@@ -219,7 +224,12 @@ __global__ void __launch_bounds__(kThreads, 4) wf_fly_kernel(const __grid_consta
         if (flyM == 0u) break;
         if (L.phase == PH_FLY) {
             T.step(L, false);                        // warp-aggregated tallies measured slower here too
-            if (L.phase == PH_FLY && --budget <= 0) L.phase = PH_CONT;   // out of budget: continue next wave
+            if (L.phase == PH_FLY && --budget <= 0) {
+                // out of budget: continue in the next wave -- unless the budget was the iteration
+                // limit itself, where the reference drops the packet
+                if (!MULTI && L.istep >= w.t.P.safeLimit) T.finish(L, FATE_DROPPED);
+                else L.phase = PH_CONT;
+            }
         }
     }
 #pragma unroll
@@ -351,29 +361,33 @@ cudaError_t wf_launch_event(const WfArgs &w, bool multi, int ev, int blocks, cud
 
 static size_t fly_smem(int nbins) { return scratch_bytes(nbins) + (size_t)(kThreads / 32) * EV_COUNT * kStage * sizeof(unsigned int); }
 
-template <bool MULTI, bool DENSE, bool PLAIN>
+template <bool MULTI, bool DENSE, int MODE>
 static cudaError_t launch_fly_t(const WfArgs &w, int blocks, cudaStream_t s)
 {
     size_t smem = fly_smem(w.t.P.nbins);
-    cudaFuncSetAttribute(wf_fly_kernel<MULTI, DENSE, PLAIN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    wf_fly_kernel<MULTI, DENSE, PLAIN><<<blocks, kThreads, smem, s>>>(w);
+    cudaFuncSetAttribute(wf_fly_kernel<MULTI, DENSE, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    wf_fly_kernel<MULTI, DENSE, MODE><<<blocks, kThreads, smem, s>>>(w);
     return cudaGetLastError();
 }
 
 cudaError_t wf_launch_fly(const WfArgs &w, bool multi, int blocks, cudaStream_t s)
 {
-    if (multi) return launch_fly_t<true, false, false>(w, blocks, s);
-    const bool plain = !w.t.P.lgDebug && !w.t.P.lgPlane;
-    if (w.t.g1.dense) return plain ? launch_fly_t<false, true, true>(w, blocks, s) : launch_fly_t<false, true, false>(w, blocks, s);
-    return plain ? launch_fly_t<false, false, true>(w, blocks, s) : launch_fly_t<false, false, false>(w, blocks, s);
+    if (multi) return launch_fly_t<true, false, 0>(w, blocks, s);
+    const int mode = (w.t.P.lgDebug || w.t.P.lgPlane) ? 0 : (w.t.P.lgSym ? 1 : 2);
+    if (w.t.g1.dense) {
+        if (mode == 2) return launch_fly_t<false, true, 2>(w, blocks, s);
+        return mode == 1 ? launch_fly_t<false, true, 1>(w, blocks, s) : launch_fly_t<false, true, 0>(w, blocks, s);
+    }
+    if (mode == 2) return launch_fly_t<false, false, 2>(w, blocks, s);
+    return mode == 1 ? launch_fly_t<false, false, 1>(w, blocks, s) : launch_fly_t<false, false, 0>(w, blocks, s);
 }
 
 int wf_fly_blocks_per_sm(bool multi)
 {
     int nb = 0;
     size_t smem = fly_smem(1024);
-    if (multi) cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, wf_fly_kernel<true, false, false>, kThreads, smem);
-    else       cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, wf_fly_kernel<false, false, false>, kThreads, smem);
+    if (multi) cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, wf_fly_kernel<true, false, 0>, kThreads, smem);
+    else       cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, wf_fly_kernel<false, false, 0>, kThreads, smem);
     return nb;
 }
 
