@@ -90,18 +90,21 @@ __device__ __forceinline__ int sample_cdf(Rng &rng, const float *cdf, int nb)
     return nuP;
 }
 
-// getNu2 on a strided row (linePDF, debug only): faithful linear scan
-__device__ __forceinline__ int sample_cdf_strided(Rng &rng, const float *cdf, size_t stride, int nb)
+// getNu2 on a strided row (linePDF, debug only): faithful linear scan.  getNu2 takes the scan
+// bound and the "+1" rule from the module variable nbins whatever the length of the row
+// (photon_mod.f90:747-757): nscan = entries that exist (nLines), nb = nbins.
+__device__ __forceinline__ int sample_cdf_strided(Rng &rng, const float *cdf, size_t stride, int nscan, int nb)
 {
     float u = rng.uniform();
     for (int i = 1; i <= 10000; ++i) {
         if (u == 0.f || u == 1.f || u == 0.9999999f) u = rng.uniform(); else break;
     }
     int nuP = 1;
-    for (int is = 1; is <= nb; ++is) {
+    for (int is = 1; is <= nscan && is <= nb; ++is) {
         if (u >= __ldg(&cdf[(size_t)(is - 1) * stride])) nuP = is; else break;
     }
     if (nuP < nb - 1) nuP = nuP + 1;
+    if (nuP > nscan) nuP = nscan;        // the reference would index past the row here
     return nuP;
 }
 
@@ -392,7 +395,7 @@ struct Transport {
                     // non-ionising line packet: leaves silently (:923-957, :475-485)
                     int nuL = 0;
                     if (P.lgDebug) {
-                        nuL = sample_cdf_strided(L.rng, g.linePDF + cell, (size_t)(g.nCells + 1), P.nLines);
+                        nuL = sample_cdf_strided(L.rng, g.linePDF + cell, (size_t)(g.nCells + 1), P.nLines, P.nbins);
                         atomicAdd(&g.lineQ[(size_t)(nuL - 1) * (size_t)(g.nCells + 1) + (size_t)cell], 1u);
                     }
                     L.lastNuP = nuL;

@@ -163,7 +163,29 @@ static vec3 random_unit_vector(Rng *r)
     return v;
 }
 
-/* photon_mod.f90:720-764 */
+/* photon_mod.f90:720-764.  getNu2 takes the scan bound and the "+1" rule from the MODULE
+ * variable nbins whatever the length of the row it is given; for linePDF(cell,:) (nLines
+ * entries, :931) the scan can only stop inside the row because the row ends with 1 > random,
+ * but the rule stays "nuP < nbins-1" (pinned against the translated reference,
+ * tests/test_reference_pin.py).  nscan = entries that exist, nbins = the module's nbins. */
+static int32_t get_nu2_row(Rng *r, const float *probDen, size_t stride, int32_t nscan, int32_t nbins)
+{
+    float random = rng_uniform(r);
+    int i;
+    for (i = 1; i <= 10000; ++i) {
+        if (random == 0.f || random == 1.f || random == 0.9999999f) random = rng_uniform(r);
+        else break;
+    }
+    int32_t nuP = 1;
+    for (int32_t is = 1; is <= nscan && is <= nbins; ++is) {
+        if (random >= probDen[(size_t)(is - 1) * stride]) nuP = is;
+        else break;
+    }
+    if (nuP < nbins - 1) nuP = nuP + 1;
+    if (nuP > nscan) nuP = nscan;      /* the reference would index past the row here */
+    return nuP;
+}
+
 static int32_t get_nu2(Rng *r, const float *probDen, size_t stride, int32_t nbins)
 {
     float random = rng_uniform(r);
@@ -374,10 +396,9 @@ static int new_photon_packet(Ctx *c, Packet *pk, int chType, vec3 position, cons
         random = 1.f - random;
         if (random <= g->totalLines[cell]) {
             if (P->lgDebug) {
-                nuP = get_nu2(&c->rng, &g->linePDF[cell], (size_t)(g->nCells + 1), P->nLines);
-                /* NOTE: the reference passes linePDF(cell,:) to getNu2, which scans 1..nbins
-                 * (photon_mod.f90:747); with nLines < nbins that reads past the row.  The
-                 * restatement scans nLines entries. */
+                /* the reference passes linePDF(cell,:) to getNu2, which scans 1..nbins and
+                 * applies "nuP<nbins-1 -> nuP+1" with the module's nbins (photon_mod.f90:747-757) */
+                nuP = get_nu2_row(&c->rng, &g->linePDF[cell], (size_t)(g->nCells + 1), P->nLines, P->nbins);
                 if (nuP < 1) ERR_STOP(41);
             } else {
                 nuP = 0;
