@@ -1,0 +1,39 @@
+"""Generate tests/golden/ref_<case>.npz from the reference's own code.
+
+    python tests/golden/make_golden.py [case ...]
+
+Runs in the build container only (needs /root/reference): oracle/f90ref translates
+photon_mod.f90 & co. into oracle/_ref/mocassin_ref.py, tests/ref_cases.run_reference
+executes the reference's energyPacketDriver on each seeded case with the oracle's Philox
+stream bound to RANDOM_NUMBER and detmath bound to LOG/SIN/COS/ACOS/ATAN, and the
+reference's own output arrays are stored here.  The fixtures travel to the GPU box; the
+reference does not.
+
+Per case: fates (n,2) int32 = cell crossings and energyPacketRun calls per packet; draws (n,)
+= uniforms consumed per packet; Jste_g<i>, escapedPackets_g<i> (+ Jdif, linePackets in
+debug mode) = grid(i)%... float32 exactly as the Fortran accumulates them; Qphot, absInt,
+scaInt; plane = planeIonDistribution.
+"""
+import os
+import sys
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(os.path.dirname(HERE))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+
+import ref_cases  # noqa: E402
+
+
+def main(names):
+    for name in names or list(ref_cases.REF_CASES):
+        res = ref_cases.run_reference(name)
+        path = os.path.join(HERE, f"ref_{name}.npz")
+        np.savez_compressed(path, **res)
+        print(f"{name}: {os.path.getsize(path)} bytes, {res['draws'].shape[0]} packets, {int(res['nSegments'])} crossings")
+
+
+if __name__ == "__main__":
+    main(sys.argv[1:])

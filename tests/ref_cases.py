@@ -1,0 +1,100 @@
+"""Small seeded cases on which the CPU oracle is pinned against the reference's own code
+(the f90py translation of photon_mod.f90, oracle/f90ref) and against the golden vectors
+generated from it (tests/golden/make_golden.py -> tests/golden/ref_*.npz).
+
+Sizes are chosen so that the translated reference (numpy.float32 scalar arithmetic in
+Python, ~10^4 cell crossings per second) finishes each case in a few seconds."""
+import numpy as np
+
+from mocassin_b200 import workloads as W
+
+SEED = 12345
+
+# name: (builder, kwargs, packets, mode)   mode: "stellar" | ("diffext", gpLoc, cellLoc) | "reslines"
+REF_CASES = {
+    "hii_sym_gas": (W.hii_region, dict(n=9, nbins=80), 3000, "stellar"),
+    "hii_sym_gas_debug": (W.hii_region, dict(n=7, nbins=60, debug=True, seed=9), 2000, "stellar"),
+    "dust_shell_hg": (W.dust_shell, dict(n=8, nbins=40, tauV=3.0), 600, "stellar"),
+    "dust_shell_iso": (W.dust_shell, dict(tauV=10.0, isotropic=True, n=7, nbins=40), 300, "stellar"),
+    "multigrid_sym": (W.multigrid, dict(n=8, nsub=5, nbins=60), 1000, "stellar"),
+    "multigrid_nonsym": (W.multigrid, dict(symmetric=False, n=9, nsub=5, nbins=60), 1000, "stellar"),
+    "cube_uniform_gas": (W.synthetic_cube, dict(n=10, nbins=60, clumpy=False, dust=False, nPhotons=10**6), 2000, "stellar"),
+    "cube_clumpy_gasdust": (W.synthetic_cube, dict(n=10, nbins=60, clumpy=True, dust=True, nPhotons=10**6), 800, "stellar"),
+    "viewing_angles": (W.viewing_angles, dict(n=7, nbins=40), 2000, "stellar"),
+    "viewing_angles_phifree": (W.viewing_angles, dict(n=7, nbins=40, phi_free=True), 1000, "stellar"),
+    "plane_slab_gasdust": (W.plane_slab, dict(nx=5, ny=9, nz=5, nbins=60, Hden=30.0), 1000, "stellar"),
+    "plane_slab_gas": (W.plane_slab, dict(nx=5, ny=9, nz=5, nbins=60, dust=False, Hden=30.0), 1000, "stellar"),
+    "diffext_mother": (W.multigrid, dict(n=8, nsub=5, nbins=60), 500, ("diffext", 1, (3, 2, 5))),
+    "diffext_subgrid": (W.multigrid, dict(n=8, nsub=5, nbins=60), 500, ("diffext", 2, (3, 2, 4))),
+    "reslines_multigrid": (W.multigrid, dict(n=8, nsub=5, nbins=60), 0, "reslines"),
+}
+DIFFEXT_DELTAE = 1.0e-3
+
+
+def make(name):
+    fn, kw, n, mode = REF_CASES[name]
+    m = fn(**kw)
+    if isinstance(mode, tuple):
+        m.inSpectrumProbDen[0, :] = W.blackbody_cdf(20000.0, m.nuArray, np.gradient(m.nuArray).astype(np.float32))
+        m.deltaE[0] = DIFFEXT_DELTAE
+    if mode == "reslines":
+        rs = np.random.default_rng(3)
+        for g in m.grids:
+            g.resLinePackets = np.zeros(g.nCells + 1, np.int32)
+            g.resLinePackets[1:] = rs.integers(0, 3, g.nCells)
+    return m, n, mode
+
+
+def _collect(out, counters, fates, plane):
+    res = {"Qphot": np.float32(counters["Qphot"]), "absInt": np.float32(counters["absInt"]),
+           "scaInt": np.float32(counters["scaInt"]), "plane": np.asarray(plane, np.int64)}
+    if fates is not None:
+        res["fates"] = np.asarray(fates)[:, :2].astype(np.int32)      # segments, energyPacketRun calls
+    for i, o in enumerate(out):
+        for k in ("Jste", "escapedPackets", "Jdif", "linePackets"):
+            if k in o:
+                res[f"{k}_g{i + 1}"] = np.asarray(o[k], np.float32)
+    return res
+
+
+def run_oracle(name):
+    """the C oracle's faithful float32 tallies and per-packet records"""
+    from oracle.oracle import Oracle
+
+    m, n, mode = make(name)
+    o = Oracle(m)
+    if mode == "stellar":
+        c, f = o.transport(1, 0, n, seed=SEED, want_fates=True)
+    elif mode == "reslines":
+        c, nrun = o.transport_reslines(1, seed=SEED)
+        f = None
+        c = dict(c, nRun=nrun)
+    else:
+        _, gp, cell = mode
+        c, f = o.transport(0, 0, n, seed=SEED, gpLoc=gp, cellLoc=cell, want_fates=True)
+    res = _collect(o.out, c, f, o.planeIonDistribution)
+    res["nSegments"] = np.int64(c["nSegments"])
+    return res
+
+
+def run_reference(name, math="detmath", uninit_int=0):
+    """the reference's own energyPacketDriver (translated), same Philox streams"""
+    from oracle import oracle as orc
+    from oracle.f90ref.harness import Reference
+
+    m, n, mode = make(name)
+    r = Reference(m, orc.load(), math=math, uninit_int=uninit_int)
+    if mode == "stellar":
+        c, f = r.transport(1, 0, n, seed=SEED)
+    elif mode == "reslines":
+        c, f = r.transport_reslines(1, seed=SEED)
+    else:
+        _, gp, cell = mode
+        g = m.grids[gp - 1]
+        # the reference derives deltaE(0) = LdiffuseLoc(cell)/NphotonsDiffuseLoc (photon_mod.f90:64-66)
+        r.grid[gp].ldiffuseloc[int(g.active[cell[0] - 1, cell[1] - 1, cell[2] - 1])] = np.float32(DIFFEXT_DELTAE)
+        c, f = r.transport(0, 0, n, seed=SEED, gpLoc=gp, cellLoc=cell)
+    res = _collect(r.out, c, f, r.G.planeiondistribution.a)
+    res["draws"] = f[:, 2].astype(np.int32)
+    res["nSegments"] = np.int64(c["nSegments"])
+    return res
