@@ -1280,6 +1280,8 @@ int mcb200_dust_update(mcb200_ctx *ctx, int32_t iG, float XHILimit, float *Tdust
     if (ctx->pending) return fail(ctx, MCB200_ESTATE, "tallies pending: call mcb200_reduce first");
     rc = ensure_estimators(ctx, *g);
     if (rc) return rc;
+    // iterateMC zeroes grid%lgConverged at the start of every iteration (iteration_mod.f90:87);
+    // a cell no packet crossed is skipped by updateCell (update_mod.f90:104-149) and stays 0
     CU(g->lgConverged.alloc((size_t)g->nCells + 1));
     CU(g->lgConverged.zero(ctx->stream));
     CU(ctx->nConv.zero(ctx->stream));

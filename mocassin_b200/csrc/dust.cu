@@ -51,6 +51,28 @@ __global__ void __launch_bounds__(128) dust_update_kernel(const DustArgs A)
     int conv = 0;
     if (live) {
         const size_t nR = (size_t)A.nCells + 1;
+        // updateCell returns first thing for a cell no packet crossed (update_mod.f90:104-149):
+        // Tdust and the sublimation flag keep their previous values, lgConverged the 0 that
+        // iterateMC gave it at the start of the iteration (iteration_mod.f90:87)
+        bool hit = false;
+        for (int i = 1; i <= A.nb && !hit; ++i) {
+            size_t o = (size_t)(i - 1) * nR + cell;
+            float J = A.Jste[o] * 1.e-9f;
+            if (A.sym) J = J / 8.f;
+            hit = J > 0.f;
+            if (A.lgDebug && !hit) {
+                float Jd = A.Jdif[o] * 1.e-9f;
+                if (A.sym) Jd = Jd / 8.f;
+                hit = Jd > 0.f;
+            }
+        }
+        if (!hit) {
+            conv = A.lgConverged[cell];
+            live = false;
+        }
+    }
+    if (live) {
+        const size_t nR = (size_t)A.nCells + 1;
         const float Pi = 3.141592654f;
         int nspU = A.multiChem ? __ldg(&A.dustAbunIndex[cell]) : 1;
         bool comp = nspU >= 1 && nspU <= A.nDustComp;

@@ -1,5 +1,6 @@
 """Recipe: translate the reference's hot-path Fortran, where it lies under
-/root/reference/source, into oracle/_ref/mocassin_ref.py (TEST INFRASTRUCTURE).
+/root/reference/source, into oracle/_ref/mocassin_ref.py and mocassin_ref_aux.py
+(TEST INFRASTRUCTURE).
 
     python -m oracle.f90ref.build_ref [--force]
 
@@ -15,6 +16,19 @@ What is translated (executable code):
     constants_mod.f90     parameters
 What is only read for its declarations (module variables and derived types):
     common_mod.f90, continuum_mod.f90, grid_mod.f90, pathIntegration_mod.f90
+
+Second target, mocassin_ref_aux.py -- the callers either side of the transport
+(SURVEY.md 8a K1 and 8f.1), translated leniently: statements outside the pinned procedures
+that the translator does not cover become calls that raise if they are ever reached.
+    ionization_mod.f90    ionizationDriver, eDenSum, addOpacity (+ putOpacity, inOpacity)   strict
+    continuum_mod.f90     getFlux                                         strict
+    emission_mod.f90      emissionDriver with its internal setDustPDF     setDustPDF strict
+    update_mod.f90        updateCell with its internal getDustT           getDustT strict
+    iteration_mod.f90     lines 106-230 of iterateMC (the opacity block: ionizationDriver over the
+                          cells + the dust contribution to scaOpac/absOpac/opacity) as a
+                          synthetic subroutine with iterateMC's declarations                strict
+(the one untranslated statement inside each of setDustPDF / getDustT is the call of the
+quantum-heating / resonance-line-heating routine, in a branch the dust-only path never takes)
 """
 from __future__ import annotations
 
@@ -26,6 +40,7 @@ from . import f90py
 HERE = os.path.dirname(os.path.abspath(__file__))
 OUT_DIR = os.path.join(os.path.dirname(HERE), '_ref')
 OUT = os.path.join(OUT_DIR, 'mocassin_ref.py')
+OUT_AUX = os.path.join(OUT_DIR, 'mocassin_ref_aux.py')
 REF_ROOT = os.environ.get('MOCASSIN_REFERENCE', '/root/reference')
 
 # (file, declarations only?, procedures to keep or None for all)
@@ -45,6 +60,39 @@ LOOP_HOOKS = {'energypacketdriver.iphot',    # one trip per energy packet (photo
 PROC_HOOKS = {'energypacketrun'}             # one call per packet generation
 
 
+# (file, declarations only?, procedures to keep, internal procedures to keep)
+AUX_SOURCES = [
+    ('constants_mod.f90', False, None, None),
+    ('vector_mod.f90', False, set(), None),
+    ('interpolation_mod.f90', False, {'locate'}, None),
+    ('common_mod.f90', True, None, None),
+    ('ph_mod.f90', True, None, None),            # module xSec_mod
+    ('hydro_mod.f90', True, None, None),         # module elements_mod
+    ('grid_mod.f90', True, None, None),
+    ('composition_mod.f90', True, None, None),
+    ('continuum_mod.f90', False, {'getflux'}, None),
+    ('ionization_mod.f90', False, {'ionizationdriver', 'edensum', 'addopacity'}, None),
+    ('emission_mod.f90', False, {'emissiondriver'}, {'setdustpdf'}),
+    ('update_mod.f90', False, {'updatecell'}, {'getdustt'}),
+]
+# A statement range of a procedure that cannot be run as a whole (iterateMC is the entire Lucy
+# iteration, MPI included): the opacity block of iterateMC -- ionizationDriver over all cells and
+# the dust contribution to scaOpac/absOpac/opacity -- wrapped, with iterateMC's own declarations,
+# into a synthetic subroutine.  (file, name, declaration line ranges, body line range, guards)
+AUX_SLICES = [
+    ('iteration_mod.f90', 'opacity_block', [(20, 20), (24, 24), (37, 77)], (106, 230),
+     {106: 'icell = 0', 108: 'do ig = 1, ngrids', 230: 'end do'}),
+]
+# supplied by the harness: BoltGaunt (ionization_mod.f90:134-174) fills contBoltz/gauntFF from Gaunt
+# factor tables; its only trace in the opacity is the free-free term of bin 1, which the
+# oracle takes as an input (ff1), so the harness sets those arrays directly
+AUX_EXTERNS = {'boltgaunt'}
+# procedures that must translate completely, and the untranslated statements tolerated in them
+AUX_STRICT = {'opacity_block': 0, 'ionizationdriver': 0, 'edensum': 0, 'addopacity': 0, 'putopacity': 0, 'inopacity': 0, 'getflux': 0, 'locate': 0,
+              'setdustpdf': 1,      # call qHeat (lgQHeat branch)
+              'getdustt': 1}        # resLineHeating (gas + resonance-line transfer branch)
+
+
 class ReferenceUnavailable(RuntimeError):
     pass
 
@@ -55,17 +103,6 @@ def source_dir():
 
 def available() -> bool:
     return os.path.exists(OUT) or os.path.isdir(source_dir())
-
-
-def _stale() -> bool:
-    if not os.path.exists(OUT):
-        return True
-    if not os.path.isdir(source_dir()):
-        return False            # the box without the reference uses the prebuilt file
-    t = os.path.getmtime(OUT)
-    deps = [os.path.join(source_dir(), f) for f, _, _ in SOURCES]
-    deps += [os.path.join(HERE, f) for f in ('f90py.py', 'build_ref.py')]
-    return any(os.path.getmtime(d) > t for d in deps)
 
 
 def translate() -> str:
@@ -93,20 +130,74 @@ def gen_warnings(gen):
     return list(gen.warnings)
 
 
-def build(force: bool = False) -> str:
-    if not force and not _stale():
-        return OUT
-    if not os.path.isdir(source_dir()):
-        raise ReferenceUnavailable(f'{source_dir()} not present and {OUT} not built')
-    code = translate()
+def translate_aux() -> str:
+    mods = []
+    for fn, spec_only, keep, keep_internal in AUX_SOURCES:
+        with open(os.path.join(source_dir(), fn), errors='replace') as fh:
+            unit = f90py.Unit(fh.read(), fn, spec_only=spec_only, lenient=True)
+        for m in unit.modules:
+            if keep is not None:
+                m.procs = {k: v for k, v in m.procs.items() if k in keep}
+            if keep_internal is not None:
+                for p in m.procs.values():
+                    p.contains = {k: v for k, v in p.contains.items() if k in keep_internal}
+            mods.append(m)
+    for fn, name, decl_ranges, (b0, b1), guards in AUX_SLICES:
+        with open(os.path.join(source_dir(), fn), errors='replace') as fh:
+            lines = fh.read().split('\n')
+        for ln, want in guards.items():
+            got = ' '.join(lines[ln - 1].split('!')[0].lower().split())
+            if not got.startswith(want):
+                raise f90py.TranslateError(f'{fn}:{ln}: expected {want!r}, found {got!r} (reference changed?)')
+        text = ['module slice_' + name, 'contains', f'subroutine {name}(grid)']
+        for a, b in decl_ranges:
+            text += lines[a - 1:b]
+        text += lines[b0 - 1:b1] + [f'end subroutine {name}', 'end module slice_' + name]
+        unit = f90py.Unit('\n'.join(text), f'{fn}[{b0}-{b1}]', lenient=True)
+        mods.extend(unit.modules)
+    gen = f90py.Gen(mods, lenient=True, externs=AUX_EXTERNS)
+    code = gen.generate('@@HEADER@@')
+    for name, allowed in AUX_STRICT.items():
+        bad = gen.untranslated.get(name, [])
+        if len(bad) > allowed:
+            raise f90py.TranslateError(f'{name}: untranslated statements in a pinned procedure: {bad}')
+    notes = [f'{k}: {x}' for k, v in gen.untranslated.items() for x in v]
+    header = ('# GENERATED by oracle/f90ref/build_ref.py from the Fortran sources under\n'
+              f'# {source_dir()} -- a build artefact, do not edit, do not commit.\n'
+              '# statements that raise if reached (lenient translation):\n' + ''.join(f'#   {w}\n' for w in notes))
+    return code.replace('@@HEADER@@', header, 1)
+
+
+def _write(path, code):
     os.makedirs(OUT_DIR, exist_ok=True)
-    compile(code, OUT, 'exec')
-    tmp = OUT + '.tmp'
+    compile(code, path, 'exec')
+    tmp = path + '.tmp'
     with open(tmp, 'w') as fh:
         fh.write(code)
-    os.replace(tmp, OUT)
-    return OUT
+    os.replace(tmp, path)
+
+
+def _stale_path(path, sources) -> bool:
+    if not os.path.exists(path):
+        return True
+    if not os.path.isdir(source_dir()):
+        return False            # the box without the reference uses the prebuilt file
+    t = os.path.getmtime(path)
+    deps = [os.path.join(source_dir(), f[0]) for f in sources]
+    deps += [os.path.join(HERE, f) for f in ('f90py.py', 'build_ref.py')]
+    return any(os.path.getmtime(d) > t for d in deps)
+
+
+def build(force: bool = False, target: str = 'photon') -> str:
+    path, sources, fn = (OUT, SOURCES, translate) if target == 'photon' else (OUT_AUX, AUX_SOURCES, translate_aux)
+    if not force and not _stale_path(path, sources):
+        return path
+    if not os.path.isdir(source_dir()):
+        raise ReferenceUnavailable(f'{source_dir()} not present and {path} not built')
+    _write(path, fn())
+    return path
 
 
 if __name__ == '__main__':
-    print(build(force='--force' in sys.argv))
+    for tgt in ('photon', 'aux'):
+        print(build(force='--force' in sys.argv, target=tgt))

@@ -484,6 +484,7 @@ class Module:
     procs: Dict[str, Proc] = field(default_factory=dict)
     operators: Dict[str, List[str]] = field(default_factory=dict)
     generics: Dict[str, List[str]] = field(default_factory=dict)
+    failed: Dict[str, str] = field(default_factory=dict)      # procedures skipped by a lenient parse
 
 
 TYPE_START = re.compile(r'^(integer|real|double\s*precision|logical|character|complex|type\s*\()')
@@ -704,11 +705,15 @@ def parse_decl(stmt: str, line: int) -> List[Decl]:
 class Unit:
     """Parser of one source file into Module objects."""
 
-    def __init__(self, text: str, fname: str = '', spec_only: bool = False):
+    def __init__(self, text: str, fname: str = '', spec_only: bool = False, lenient: bool = False):
+        """lenient: a statement the parser does not know becomes an ('untranslated', ...) node
+        that raises if it is ever *reached* at run time, and a procedure whose block structure
+        cannot be parsed is skipped (recorded in Module.failed); strict: both are errors."""
         self.lines = logical_lines(text)
         self.k = 0
         self.fname = fname
         self.spec_only = spec_only
+        self.lenient = lenient
         self.modules: List[Module] = []
         while self.k < len(self.lines):
             ln, s = self.lines[self.k]
@@ -743,9 +748,9 @@ class Unit:
                 if pr is None:
                     self.err(f'expected a procedure, got {s!r}', ln)
                 self.k += 1
-                self.parse_proc(pr, mod)
-                pr.module = mod.name
-                mod.procs[pr.name] = pr
+                if self.parse_proc_or_skip(pr, mod):
+                    pr.module = mod.name
+                    mod.procs[pr.name] = pr
                 continue
             self.k += 1
             self.spec_stmt(s, ln, mod.decls, mod, mod.order)
@@ -853,12 +858,33 @@ class Unit:
                     self.err(f'expected internal procedure, got {s!r}', ln)
                 self.k += 1
                 sub.parent = pr
-                self.parse_proc(sub, mod)
-                pr.contains[sub.name] = sub
+                if self.parse_proc_or_skip(sub, mod):
+                    pr.contains[sub.name] = sub
             ln, s = self.lines[self.k]
         if not re.match(r'^end(\s*(subroutine|function)(\s+\w+)?)?$', s):
             self.err(f'expected end of {pr.name}, got {s!r}', ln)
         self.k += 1
+
+    def parse_proc_or_skip(self, pr: Proc, mod: Optional[Module]) -> bool:
+        start = self.k
+        if not self.lenient:
+            self.parse_proc(pr, mod)
+            return True
+        try:
+            self.parse_proc(pr, mod)
+            return True
+        except TranslateError as ex:
+            # skip to "end subroutine|function <name>"
+            self.k = start
+            pat = re.compile(r'^end\s*(subroutine|function)\s+' + re.escape(pr.name) + r'$')
+            while self.k < len(self.lines) and not pat.match(self.lines[self.k][1]):
+                self.k += 1
+            if self.k >= len(self.lines):
+                raise
+            self.k += 1
+            if mod is not None:
+                mod.failed[pr.name] = str(ex)
+            return False
 
     def spec_stmt_in_proc(self, s, ln, pr: Proc) -> bool:
         save = self.k
@@ -1009,17 +1035,24 @@ class Unit:
             args = q.args(')')
             return ('deallocate', ln, args)
         if first in ('goto', 'go', 'where', 'forall', 'nullify', 'format', 'data', 'entry'):
+            if self.lenient:
+                return ('untranslated', ln, s)
             self.err('unsupported statement: ' + s, ln)
         # assignment
-        q = P(toks, s)
-        lhs = q.primary()
-        if q.at('='):
-            q.eat()
-            rhs = q.expr()
-            if not q.done():
-                self.err('trailing tokens in assignment: ' + s, ln)
-            return ('assign', ln, lhs, rhs)
-        self.err('unsupported statement: ' + s, ln)
+        try:
+            q = P(toks, s)
+            lhs = q.primary()
+            if q.at('='):
+                q.eat()
+                rhs = q.expr()
+                if not q.done():
+                    self.err('trailing tokens in assignment: ' + s, ln)
+                return ('assign', ln, lhs, rhs)
+            self.err('unsupported statement: ' + s, ln)
+        except TranslateError:
+            if self.lenient:
+                return ('untranslated', ln, s)
+            raise
 
 
 def _match_paren(toks, i):
@@ -1085,8 +1118,17 @@ class Scope:
 
 
 class Gen:
-    def __init__(self, modules: List[Module], loop_hooks=(), proc_hooks=(), skip_procs=()):
+    def __init__(self, modules: List[Module], loop_hooks=(), proc_hooks=(), skip_procs=(), lenient=False,
+                 externs=()):
+        """lenient: a statement that cannot be translated becomes a call that raises when it is
+        reached (never a silent skip); self.untranslated maps each procedure to those
+        statements so that a recipe can insist that the procedures it pins are complete."""
         self.modules = modules
+        self.lenient = lenient
+        self.untranslated: Dict[str, List[str]] = {}
+        # argument-less subroutines the harness supplies (rt.externs[name]); used for a routine
+        # whose *result* is an input of the pinned code (BoltGaunt -> contBoltz, gauntFF)
+        self.externs = set(externs)
         self.globals: Dict[str, Decl] = {}
         self.types: Dict[str, TypeDef] = {}
         self.procs: Dict[str, Proc] = {}
@@ -1563,11 +1605,22 @@ class Gen:
     def stmt(self, s, sc: Scope, ind: int, out: List[str], ctx):
         k, ln = s[0], s[1]
         pre: List[str] = []
+        pname = sc.proc.name if sc.proc else ''
+        if k == 'untranslated':
+            self.untranslated.setdefault(pname, []).append(f'line {ln}: {s[2]}')
+            self.emit(out, ind, [f'_rt.unsupported({s[2]!r}, {ln})'])
+            return
+        tmp: List[str] = []
         try:
-            self._stmt(s, sc, ind, out, ctx, pre)
+            self._stmt(s, sc, ind, tmp, ctx, pre)
+            out.extend(tmp)
         except TranslateError as ex:
+            if self.lenient:
+                self.untranslated.setdefault(pname, []).append(f'line {ln}: {ex}')
+                self.emit(out, ind, [f'_rt.unsupported({str(ex)!r}, {ln})'])
+                return
             if 'line ' not in str(ex):
-                raise TranslateError(f'line {ln} ({sc.proc.name if sc.proc else ""}): {ex}') from None
+                raise TranslateError(f'line {ln} ({pname}): {ex}') from None
             raise
 
     def _stmt(self, s, sc, ind, out, ctx, pre):
@@ -1761,6 +1814,18 @@ class Gen:
         pr = sc.lookup_proc(name)
         if pr is None and name in self.generics:
             pr = self.resolve_generic(name, args, sc, pre)
+        if pr is None and name in self.externs and not args:
+            self.emit(out, ind, pre + [f'_rt.call_extern({name!r})'])
+            return
+        if pr is None and name == 'mpi_allreduce' and len(args) >= 2:
+            # one rank: the sum over ranks of the send buffer is the send buffer
+            a, _ = self.expr(args[0], sc, pre)
+            b, _ = self.expr(args[1], sc, pre)
+            self.emit(out, ind, pre + [f'_rt.mpi_allreduce_single({a}, {b})'])
+            return
+        if pr is None and name == 'mpi_barrier':
+            self.emit(out, ind, ['pass'])
+            return
         if pr is None:
             if name.startswith('mpi_'):
                 self.emit(out, ind, [f'_rt.unsupported({name!r}, {s[1]})'])
@@ -1800,6 +1865,19 @@ class Gen:
         raise TranslateError(f'cannot initialise {d.name}')
 
     def proc_code(self, pr: Proc, ind: int, out: List[str]):
+        tmp: List[str] = []
+        saved = getattr(self, 'nonlocals', set())
+        try:
+            self._proc_code(pr, ind, tmp)
+            out.extend(tmp)
+        except TranslateError as ex:
+            if not self.lenient:
+                raise
+            self.nonlocals = saved
+            self.untranslated.setdefault(pr.name, []).append(f'whole procedure: {ex}')
+            self.emit(out, ind, [f'def p_{pr.name}(*a):', f'    _rt.unsupported({("procedure " + pr.name + ": " + str(ex))!r}, {pr.line})', ''])
+
+    def _proc_code(self, pr: Proc, ind: int, out: List[str]):
         sc = Scope(self, pr)
         params = []
         for a in pr.args:
@@ -1835,6 +1913,7 @@ class Gen:
                 chk = f'if {pyname(a)} is not None: ' if 'optional' in d.attrs else ''
                 pre.append(f'{chk}{pyname(a)} = _rt.rebase({pyname(a)}, ({", ".join(lbs)},))')
         # locals
+        saved_vars: List[tuple] = []
         for n, d in pr.decls.items():
             if n in pr.args:
                 continue
@@ -1845,21 +1924,38 @@ class Gen:
             z = self.zero_code(d, sc, pre)
             if z is None:
                 raise TranslateError(f'{pr.name}: local {n} has assumed shape')
+            if d.init is not None or 'save' in d.attrs:
+                # SAVE (explicit, or implied by the initialiser): the value survives the call
+                key = f'{pr.name}.{n}'
+                saved_vars.append((key, pyname(n)))
+                pre.append(f'if {key!r} in _SAVE:')
+                pre.append(f'    {pyname(n)} = _SAVE[{key!r}]')
+                pre.append('else:')
+                pre.append(f'    {pyname(n)} = {z}')
+                if d.init is not None:
+                    ipre: List[str] = []
+                    c, t = self.expr(d.init, sc, ipre)
+                    if ipre:
+                        raise TranslateError(f'{pr.name}: initialiser of {n} needs a call')
+                    if d.ty.rank:
+                        pre.append(f'    {pyname(n)}.setall({c})')
+                    else:
+                        pre.append(f'    {pyname(n)} = {self.conv(c, t, d.ty)}')
+                continue
             pre.append(f'{pyname(n)} = {z}')
-            if d.init is not None:
-                self.warnings.append(f'{pr.name}: local {n} has an initialiser (implicit SAVE); re-initialised on every call')
-                c, t = self.expr(d.init, sc, pre)
-                if d.ty.rank:
-                    pre.append(f'{pyname(n)}.setall({c})')
-                else:
-                    pre.append(f'{pyname(n)} = {self.conv(c, t, d.ty)}')
         self.emit(body, ind + 1, pre)
         inner: List[str] = []
         for sub in pr.contains.values():
             self.proc_code(sub, ind + 1, inner)
         stmts: List[str] = []
-        self.block(pr.body, sc, ind + 1, stmts, ctx)
-        self.emit(stmts, ind + 1, [ret])
+        if saved_vars:
+            self.emit(stmts, ind + 1, ['try:'])
+            self.block(pr.body, sc, ind + 2, stmts, ctx)
+            self.emit(stmts, ind + 2, [ret])
+            self.emit(stmts, ind + 1, ['finally:'] + [f'    _SAVE[{k!r}] = {v}' for k, v in saved_vars])
+        else:
+            self.block(pr.body, sc, ind + 1, stmts, ctx)
+            self.emit(stmts, ind + 1, [ret])
         nl = sorted(self.nonlocals)
         if nl:
             if pr.parent is None:
@@ -1941,6 +2037,7 @@ class Gen:
         # module variables
         sc = Scope(self, None)
         body.append('def init_globals():')
+        body.append('    _SAVE.clear()')
         body.append('    """module variables: PARAMETERs and initialised variables get their values, the')
         body.append('    rest the zero of their type (allocatables None)."""')
         for m in self.modules:
@@ -1980,6 +2077,7 @@ class Gen:
         out.append('class _Globals:')
         out.append('    pass')
         out.append('_G = _Globals()')
+        out.append('_SAVE = {}      # SAVEd local variables, "procedure.variable" -> value')
         out.append('')
         for (text, kind), name in self.consts.items():
             if kind == 'r':

@@ -1,0 +1,209 @@
+"""Run the reference's own routines either side of the transport (oracle/_ref/mocassin_ref_aux.py,
+the f90py translation) -- TEST INFRASTRUCTURE:
+
+* `gas_opacity`  : `ionizationDriver(grid, ix, iy, iz)` for every cell (ionization_mod.f90:26-129:
+                   density loop, eDenSum, addOpacity/putOpacity/inOpacity).  BoltGaunt, whose only
+                   trace in the result is the free-free term of bin 1, is supplied by the harness.
+* `dust_pdf`     : `emissionDriver(grids, ix, iy, iz, iG)` on a dust-only model = setDustPDF
+                   (emission_mod.f90:1313-1387) with getFlux (continuum_mod.f90:359-416).
+* `dust_update`  : `updateCell(grid, xP, yP, zP)` on a dust-only model = the no-gas branch
+                   (update_mod.f90:308-334) with getDustT (:1836-1945).
+"""
+from __future__ import annotations
+
+import importlib
+import os
+import sys
+
+import numpy as np
+
+from . import build_ref, rt
+
+
+def load_aux():
+    path = build_ref.build(target='aux')
+    d = os.path.dirname(path)
+    if d not in sys.path:
+        sys.path.insert(0, d)
+    name = os.path.splitext(os.path.basename(path))[0]
+    if name in sys.modules:
+        return sys.modules[name]
+    return importlib.import_module(name)
+
+
+def _F(a, dt):
+    return np.array(a, dtype=dt, order='F', copy=True)
+
+
+def _cells(active):
+    """(x, y, z) 1-based of every active cell in the reference's loop order"""
+    nx, ny, nz = active.shape
+    for i in range(1, nx + 1):
+        for j in range(1, ny + 1):
+            for k in range(1, nz + 1):
+                if active[i - 1, j - 1, k - 1] > 0:
+                    yield i, j, k
+
+
+class AuxReference:
+    def __init__(self, oracle_lib, math: str = 'detmath'):
+        self.ref = load_aux()
+        self.lib = oracle_lib
+        if math == 'detmath':
+            rt.use_detmath(oracle_lib)
+        else:
+            rt.use_libm()
+        rt.UNINIT_INT = 0
+        self.G = self.ref.init_globals()
+        G = self.G
+        G.taskid, G.numtasks, G.lgtalk, G.lgecho = 0, 1, False, False
+        G.lgforcetdust, G.lgtraceheating, G.lgqheat, G.lgphotoelectric = False, False, False, False
+
+    # ------------------------------------------------------------------------------------------
+    def _gas_setup(self, t, nbins, ionDen, elemAbun, abIndex, Hden, active, contBoltz1, gauntFF1, Ne, Te,
+                   bremsXSecP):
+        G, ref = self.G, self.ref
+        nR = Hden.shape[0]
+        G.lggas = True
+        G.nbins, G.nstages = int(nbins), int(t.nstages)
+        G.lgelementon = rt.wrap(np.asarray(t.lgElementOn) != 0)
+        G.elementxref = rt.wrap(_F(t.elementXref, np.int64))
+        G.xsecarray = rt.wrap(_F(t.xSecArray, np.float32))
+        G.bremsxsecp = int(bremsXSecP)
+        for name, v in (('hlevxsecp', t.HlevXSecP1), ('hlevnup', t.HlevNuP1), ('heisingxsecp', t.HeISingXSecP1),
+                        ('heilevnup', t.HeIlevNuP1), ('heiixsecp', t.HeIIXSecP1), ('heiilevnup', t.HeIIlevNuP1)):
+            arr = getattr(G, name)
+            if arr is None:
+                arr = rt.alloc('i', [(1, 10)])
+                setattr(G, name, arr)
+            arr[1] = int(v)
+        G.elementp = rt.wrap(_F(t.elementP, np.int64))
+        G.nshells = rt.wrap(_F(t.nShells, np.int64))
+        G.nuarray = rt.wrap(np.linspace(0.1, 10.0, nbins).astype(np.float32))
+        G.iondenused = rt.alloc('r', [(1, ionDen.shape[1]), (1, t.nstages)])
+        g = ref.T_grid_type()
+        g.nx, g.ny, g.nz = active.shape
+        g.ncells = nR - 1
+        g.active = rt.wrap(_F(active, np.int64))
+        ab3 = np.zeros(active.shape, np.int64, order='F')
+        ab3[active > 0] = abIndex[active[active > 0]]
+        g.abfileindex = rt.wrap(ab3)
+        g.ionden = rt.wrap(_F(ionDen, np.float32), (0, 1, 1))
+        g.elemabun = rt.wrap(_F(elemAbun, np.float32))
+        g.hden = rt.wrap(_F(Hden, np.float32), (0,))
+        g.ne = rt.wrap(_F(Ne, np.float32), (0,))
+        g.te = rt.wrap(_F(Te, np.float32), (0,))
+        op = np.zeros((nR, nbins), np.float32, order='F')
+        g.opacity = rt.wrap(op, (0, 1))
+
+        def boltgaunt():                      # stand-in for BoltGaunt: bin 1 only matters
+            G.contboltz[1] = np.float32(contBoltz1)
+            G.gauntff[1] = np.float32(gauntFF1)
+        rt.externs['boltgaunt'] = boltgaunt
+        return g, op
+
+    def gas_opacity(self, t, nbins, ionDen, elemAbun, abIndex, Hden, active, contBoltz1, gauntFF1, Ne, Te,
+                    bremsXSecP):
+        """opacity(0:nCells, nbins) from ionizationDriver called cell by cell; also returns
+        FFOpacity(1) per cell (the value the oracle takes as its ff1 input).  abIndex is per
+        cell (0:nCells); the reference indexes abFileIndex(ix,iy,iz), built here from `active`."""
+        g, op = self._gas_setup(t, nbins, ionDen, elemAbun, abIndex, Hden, active, contBoltz1, gauntFF1, Ne, Te,
+                                bremsXSecP)
+        ff1 = np.zeros(Hden.shape[0], np.float32)
+        with np.errstate(all='ignore'):
+            for (i, j, k) in _cells(active):
+                self.ref.p_ionizationdriver(g, i, j, k)
+                ff1[active[i - 1, j - 1, k - 1]] = self.G.ffopacity[1]
+        return op, ff1
+
+    def opacity_block(self, t, nbins, ionDen, elemAbun, abIndex, Hden, active, contBoltz1, gauntFF1, Ne, Te,
+                      bremsXSecP, dust=None, dust_model=None):
+        """the opacity block of iterateMC (iteration_mod.f90:106-230) on one grid: ionizationDriver
+        over all cells, the single-rank all-reduce, and the dust contribution.  Returns
+        (opacity, scaOpac, absOpac), each (0:nCells, nbins); the last two None without dust."""
+        G = self.G
+        g, op = self._gas_setup(t, nbins, ionDen, elemAbun, abIndex, Hden, active, contBoltz1, gauntFF1, Ne, Te,
+                                bremsXSecP)
+        G.ngrids, G.lg2d, G.lgequivalenttau, G.niteratemc = 1, False, False, 1
+        G.lgdust = dust is not None
+        sca = ab = None
+        if dust is not None:
+            nR = Hden.shape[0]
+            G.lgmultidustchemistry = bool(dust_model.lgMultiDustChemistry)
+            G.nsizes = int(dust_model.nSizes)
+            G.nspeciespart = rt.wrap(_F(dust_model.nSpeciesPart, np.int64))
+            G.dustcompoint = rt.wrap(_F(dust_model.dustComPoint, np.int64))
+            G.grainabun = rt.wrap(_F(dust_model.grainAbun, np.float32))
+            G.tdustsublime = rt.wrap(_F(dust_model.TdustSublime, np.float32))
+            G.grainweight = rt.wrap(_F(dust['grainWeight'], np.float32))
+            G.dustscaxsecp = rt.wrap(_F(dust['dustScaXsecP'], np.int64))
+            G.dustabsxsecp = rt.wrap(_F(dust['dustAbsXsecP'], np.int64))
+            g.ndust = rt.wrap(_F(dust['Ndust'], np.float32), (0,))
+            g.tdust = rt.wrap(_F(dust['Tdust'], np.float32), (0, 0, 0))
+            if dust.get('dustAbunIndex') is not None:
+                g.dustabunindex = rt.wrap(_F(dust['dustAbunIndex'], np.int64), (0,))
+            sca = np.zeros((nR, nbins), np.float32, order='F')
+            ab = np.zeros((nR, nbins), np.float32, order='F')
+            g.scaopac, g.absopac = rt.wrap(sca, (0, 1)), rt.wrap(ab, (0, 1))
+        grids = np.empty(1, dtype=object)
+        grids[0] = g
+        with np.errstate(all='ignore'):
+            self.ref.p_opacity_block(rt.wrap(grids))
+        return op, sca, ab
+
+    # ------------------------------------------------------------------------------------------
+    def _dust_globals(self, model, tables, lgDebug=False):
+        G = self.G
+        G.lgdust, G.lggas, G.lgdebug = True, False, bool(lgDebug)
+        G.lgmultidustchemistry = bool(model.lgMultiDustChemistry)
+        G.nbins, G.nsizes, G.nspeciesmax = int(model.nbins), int(model.nSizes), int(model.nSpeciesMax)
+        G.nuarray = rt.wrap(_F(model.nuArray, np.float32))
+        G.widflx = rt.wrap(_F(tables['widFlx'], np.float32))
+        G.xsecarray = rt.wrap(_F(tables['xSecArray'], np.float32))
+        G.dustabsxsecp = rt.wrap(_F(tables['dustAbsXsecP'], np.int64))
+        G.grainweight = rt.wrap(_F(tables['grainWeight'], np.float32))
+        G.grainabun = rt.wrap(_F(model.grainAbun, np.float32))
+        G.nspeciespart = rt.wrap(_F(model.nSpeciesPart, np.int64))
+        G.dustcompoint = rt.wrap(_F(model.dustComPoint, np.int64))
+        G.tdustsublime = rt.wrap(_F(model.TdustSublime, np.float32))
+        G.dustemintegral = rt.wrap(_F(tables['dustEmIntegral'], np.float32))
+        G.convpercent, G.niteratemc = np.float32(0.0), 1
+
+    def _grid(self, model, g):
+        t = self.ref.T_grid_type()
+        t.nx, t.ny, t.nz, t.ncells = g.nx, g.ny, g.nz, int(g.nCells)
+        t.active = rt.wrap(_F(g.active, np.int64))
+        t.dustabunindex = rt.wrap(_F(g.dustAbunIndex, np.int64), (0,)) if g.dustAbunIndex is not None else None
+        t.tdust = rt.wrap(_F(g.Tdust, np.float32), (0, 0, 0))
+        return t
+
+    def dust_pdf(self, model, g, tables):
+        """dustPDF(0:nCells, nbins): emissionDriver on every cell of a dust-only model"""
+        self._dust_globals(model, tables)
+        t = self._grid(model, g)
+        pdf = np.zeros((g.nCells + 1, model.nbins), np.float32, order='F')
+        t.dustpdf = rt.wrap(pdf, (0, 1))
+        grids = np.empty(1, dtype=object)
+        grids[0] = t
+        grids = rt.wrap(grids)
+        with np.errstate(all='ignore'):
+            for (i, j, k) in _cells(g.active):
+                self.ref.p_emissiondriver(grids, i, j, k, 1)
+        return pdf
+
+    def dust_update(self, model, g, tables, Jste, XHILimit, Jdif=None):
+        """(Tdust, lgConverged) after updateCell on every cell of a dust-only model; Jste is the
+        host-scaled estimator the reference holds at that point"""
+        self._dust_globals(model, tables, lgDebug=Jdif is not None)
+        G = self.G
+        G.xhilimit = np.float32(XHILimit)
+        t = self._grid(model, g)
+        t.jste = rt.wrap(_F(Jste, np.float32), (0, 1))
+        t.jdif = rt.wrap(_F(Jdif, np.float32), (0, 1)) if Jdif is not None else None
+        t.lgblack = rt.alloc('i', [(0, g.nCells)])
+        t.lgconverged = rt.alloc('i', [(0, g.nCells)])
+        G.tdusttemp = rt.alloc('r', [(0, model.nSpeciesMax), (0, model.nSizes), (0, g.nCells)])
+        with np.errstate(all='ignore'):
+            for (i, j, k) in _cells(g.active):
+                self.ref.p_updatecell(t, i, j, k)
+        return t.tdust.a, t.lgconverged.a.astype(np.int32)

@@ -216,6 +216,20 @@ def fprint(line, *items):
         print(f'[ref:{line}]', *items, file=sys.stderr)
 
 
+externs = {}      # name -> callable, supplied by the harness (see f90py.Gen externs)
+
+
+def call_extern(name):
+    if name not in externs:
+        raise NotImplementedError(f'external routine {name} was not supplied by the harness')
+    return externs[name]()
+
+
+def mpi_allreduce_single(send, recv):
+    """MPI_ALLREDUCE(sum) on one rank"""
+    recv.setall(send)
+
+
 def unsupported(what, line):
     raise NotImplementedError(f'untranslated statement reached at line {line}: {what}')
 
@@ -410,6 +424,7 @@ class _Math:
 
 
 math32 = _Math()
+math64 = _Math()      # double-precision overrides (only what detmath defines), else numpy
 
 
 def use_libm():
@@ -418,6 +433,7 @@ def use_libm():
         setattr(math32, n, getattr(np, n))
     math32.acos, math32.asin, math32.atan = np.arccos, np.arcsin, np.arctan
     math32.name = 'libm'
+    math64.__dict__.clear()
 
 
 def use_detmath(lib):
@@ -442,6 +458,16 @@ def use_detmath(lib):
     math32.log, math32.sin, math32.cos = make(0), make(1), make(2)
     math32.acos, math32.atan, math32.exp = make(3), make(4), make(5)
     math32.name = 'detmath'
+    fd = lib.oracle_detmath_d
+    fd.argtypes = [C.c_int32, C.POINTER(C.c_double), C.POINTER(C.c_double), C.c_int64]
+    fd.restype = None
+    din, dout = (C.c_double * 1)(), (C.c_double * 1)()
+
+    def exp64(x):
+        din[0] = x
+        fd(0, din, dout, 1)
+        return np.float64(dout[0])
+    math64.exp = exp64
 
 
 use_libm()
@@ -460,7 +486,7 @@ def _m(name):
                                      np.float32).reshape(x.a.shape, order='F'))
             return FArr(npf(x.a))
         with np.errstate(all='ignore'):
-            return npf(np.float64(x))
+            return getattr(math64, name, npf)(np.float64(x))
     return f
 
 

@@ -1448,6 +1448,14 @@ void oracle_dust_update(const OrDustIn *in, const float *Jste, const float *Jdif
     float *row = (float *)malloc(sizeof(float) * nT);
     for (int cell = 1; cell <= in->nCells; ++cell) {
         int nspU = in->lgMultiDustChemistry ? in->dustAbunIndex[cell] : 1;
+        /* updateCell returns before anything else for a cell no packet crossed
+         * (update_mod.f90:104-149): Tdust and lgConverged keep their previous values */
+        int lgHit = 0;
+        for (int i = 0; i < nb && !lgHit; ++i) {
+            size_t o = (size_t)i * nR + cell;
+            lgHit = Jste[o] > 0.f || (in->lgDebug && Jdif && Jdif[o] > 0.f);
+        }
+        if (!lgHit) continue;
         float XOldHI = TDUST(in, Tdust, 0, 0, cell);
         for (int i = 0; i < nb; ++i) {
             size_t o = (size_t)i * nR + cell;
@@ -1572,6 +1580,12 @@ void oracle_detmath(int32_t which, const float *in, float *out, int64_t n)
         default: out[i] = 0.f;
         }
     }
+}
+
+/* double-precision detmath (which: 0 = dm_exp_d, the Wien branch of getFlux) */
+void oracle_detmath_d(int32_t which, const double *in, double *out, int64_t n)
+{
+    for (int64_t i = 0; i < n; ++i) out[i] = which == 0 ? dm_exp_d(in[i]) : 0.0;
 }
 
 int32_t oracle_escape_bins(const OrParams *P, const float *dir, int32_t *idirT, int32_t *idirP)

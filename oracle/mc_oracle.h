@@ -143,6 +143,9 @@ void oracle_opacity(const OrOpacityIn *in, float *opacity, float *scaOpac, float
  *  oracle_dust_update: the dust-only branch of updateCell (update_mod.f90:308-334) with
  *                      getDustT (:1836-1945): Tdust from sum_nu Cabs*J/pi by inverse lookup in
  *                      dustEmIntegral, weighted means, lgConverged from |dT/T| <= XHILimit.
+ *                      A cell with no Jste(cell,:) > 0 (no Jdif > 0 either in debug mode) is
+ *                      left untouched (updateCell's lgHit test, :104-149): its Tdust and its
+ *                      lgConverged entry keep the values they came in with.
  *                      Jste is the array the host holds at that point, i.e. after the scaling
  *                      of iteration_mod.f90:705-724.  getDustT indexes dustAbsXsecP and
  *                      dustEmIntegral with the component-local species number (sic).  A cell
@@ -186,6 +189,7 @@ void oracle_random_unit_vector(uint64_t seed, uint64_t pid, uint32_t stream, flo
 int32_t oracle_hg(float g, const float *vin, uint64_t seed, uint64_t pid, uint32_t stream,
                   float *vout);
 void oracle_detmath(int32_t which, const float *in, float *out, int64_t n);
+void oracle_detmath_d(int32_t which, const double *in, double *out, int64_t n);
 int32_t oracle_escape_bins(const OrParams *P, const float *dir, int32_t *idirT, int32_t *idirP);
 float oracle_cell_volume(const OrParams *P, const OrGrid *g, int32_t xP, int32_t yP, int32_t zP);
 

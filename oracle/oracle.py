@@ -359,14 +359,15 @@ def dust_pdf(model, grid, tables):
     return out
 
 
-def dust_update(model, grid, tables, Jste, XHILimit, Jdif=None):
+def dust_update(model, grid, tables, Jste, XHILimit, Jdif=None, lgConverged=None):
     """oracle_dust_update (dust-only updateCell + getDustT over all cells); Jste is the
-    host-scaled estimator.  Returns (Tdust, lgConverged); the grid is not modified."""
+    host-scaled estimator.  Returns (Tdust, lgConverged); the grid is not modified.
+    lgConverged: the flags before the call (kept by cells no packet crossed), default 0."""
     lib = load()
     keep = []
     I = _dust_in(model, grid.nCells, tables, grid.dustAbunIndex, keep)
     T = np.array(grid.Tdust, dtype=np.float32, order="F", copy=True)
-    conv = np.zeros(grid.nCells + 1, np.int32)
+    conv = np.zeros(grid.nCells + 1, np.int32) if lgConverged is None else np.array(lgConverged, np.int32)
     J = np.asfortranarray(Jste, dtype=np.float32)
     Jd = np.asfortranarray(Jdif, dtype=np.float32) if Jdif is not None else None
     lib.oracle_dust_update.argtypes = [C.POINTER(OrDustIn), fp, fp, C.c_float, fp, ip]

@@ -13,6 +13,11 @@ Per case: fates (n,2) int32 = cell crossings and energyPacketRun calls per packe
 = uniforms consumed per packet; Jste_g<i>, escapedPackets_g<i> (+ Jdif, linePackets in
 debug mode) = grid(i)%... float32 exactly as the Fortran accumulates them; Qphot, absInt,
 scaInt; plane = planeIonDistribution.
+
+ref_aux_<case>.npz hold the outputs of the reference routines either side of the transport
+(oracle/f90ref/harness_aux.py): the opacity block of iterateMC (opacity, scaOpac, absOpac and the
+free-free term ff1 = FFOpacity(1) per cell), emissionDriver -> setDustPDF (dustPDF) and
+updateCell -> getDustT (Tdust, lgConverged) on seeded inputs built by tests/ref_cases.py.
 """
 import os
 import sys
@@ -28,7 +33,13 @@ import ref_cases  # noqa: E402
 
 
 def main(names):
-    for name in names or list(ref_cases.REF_CASES):
+    for name in names or list(ref_cases.REF_CASES) + list(ref_cases.AUX_CASES):
+        if name in ref_cases.AUX_CASES:
+            res = ref_cases.run_reference_aux(name)
+            path = os.path.join(HERE, f"ref_aux_{name}.npz")
+            np.savez_compressed(path, **res)
+            print(f"{name}: {os.path.getsize(path)} bytes, " + ", ".join(f"{k}{tuple(v.shape)}" for k, v in res.items()))
+            continue
         res = ref_cases.run_reference(name)
         path = os.path.join(HERE, f"ref_{name}.npz")
         np.savez_compressed(path, **res)

@@ -98,3 +98,96 @@ def run_reference(name, math="detmath", uninit_int=0):
     res["draws"] = f[:, 2].astype(np.int32)
     res["nSegments"] = np.int64(c["nSegments"])
     return res
+
+
+# ---------------------------------------------------------------------------------------------
+# the callers either side of the transport: opacity block of iterateMC (K1), dust closure (K5, K6)
+# ---------------------------------------------------------------------------------------------
+AUX_CASES = ["opacity_multichem", "opacity_singlechem", "dust_closure", "dust_closure_debug"]
+CONTBOLTZ1, GAUNTFF1, BREMS_P = 0.5, 1.1, 7      # what the harness's BoltGaunt stand-in sets for bin 1
+
+
+def _opacity_inputs(multi):
+    import types
+
+    import opacity_case
+    from mocassin_b200.model import number_active
+
+    c = opacity_case.make(nCells=60, nbins=140, seed=5, multi_chem=multi)
+    n = c["nCells"]
+    mask = np.zeros((4, 4, 4), bool)
+    mask.reshape(-1)[:n] = True
+    active, nc = number_active(mask)
+    assert nc == n and c["t"].band_list(c["nbins"])["low"].min() >= 2
+    rng = np.random.default_rng(1)
+    c["Ne"] = (rng.random(n + 1) * 1e12 + 1).astype(np.float32)
+    c["Te"] = (rng.random(n + 1) * 1e4 + 5e3).astype(np.float32)
+    c["active"] = active
+    c["dm"] = types.SimpleNamespace(**c["dust_model"])
+    return c
+
+
+def _dust_inputs(debug):
+    model, t = W.dust_closure(n=6, nbins=60, nPhotons=20000)
+    g = model.grids[0]
+    rng = np.random.default_rng(3)
+    g.Tdust[1:, 1:, 1:] = rng.uniform(20.0, 1300.0, size=g.Tdust[1:, 1:, 1:].shape).astype(np.float32)
+    g.Tdust[1, 1, 1:] = np.float32(300.0)
+    g.Tdust[:, :, 5] = np.float32(2000.0)                 # one cell with every grain sublimed (0/0 row)
+    g.Tdust[0, 0, 1:] = rng.uniform(50.0, 900.0, g.nCells).astype(np.float32)
+    # radiation field: black-body baths of various temperatures (some close to the old mean
+    # temperature -> converged), a few cells no packet crossed, a few far above the table
+    nu = model.nuArray.astype(np.float64)
+    J = np.zeros((g.nCells + 1, model.nbins), np.float32, order="F")
+    for c in range(1, g.nCells + 1):
+        Tb = float(g.Tdust[0, 0, c]) * (1.0 + 0.04 * rng.standard_normal()) if c % 3 else rng.uniform(30, 2500)
+        x = np.minimum(157893.94 * nu / Tb, 80.0)
+        J[c, :] = (4.0 * np.pi * 0.5250229 * nu ** 3 / np.expm1(x) * 3.28984e15 * np.asarray(t["widFlx"], np.float64)).astype(np.float32)
+    J[rng.random(g.nCells + 1) < 0.12, :] = 0.0
+    J[7, :] *= np.float32(1.0e6)
+    Jd = None
+    if debug:
+        Jd = (J * np.float32(0.25)).astype(np.float32)
+        Jd[9, :] = J[11, :]
+        J[9, :] = 0.0                                     # hit only through Jdif
+    return model, g, t, J, Jd
+
+
+def run_oracle_aux(name):
+    from oracle import oracle as O
+
+    if name.startswith("opacity"):
+        c = _opacity_inputs(name == "opacity_multichem")
+        ff1 = dict(np.load(_gold(name)))["ff1"]          # FFOpacity(1) is an input of the oracle (BoltGaunt stays on the host)
+        op, sca, ab = O.opacity(c["t"], c["nbins"], c["ionDen"], c["elemAbun"], c["abIndex"], c["Hden"], ff1=ff1,
+                                dust=c["dust"], model=c["dm"])
+        return dict(opacity=op, scaOpac=sca, absOpac=ab)
+    model, g, t, J, Jd = _dust_inputs(name.endswith("debug"))
+    model.lgDebug = Jd is not None
+    pdf = O.dust_pdf(model, g, t)
+    T, conv = O.dust_update(model, g, t, J, 0.05, Jdif=Jd)
+    return dict(dustPDF=pdf, Tdust=T, lgConverged=conv)
+
+
+def run_reference_aux(name):
+    from oracle import oracle as O
+    from oracle.f90ref.harness_aux import AuxReference
+
+    a = AuxReference(O.load())
+    if name.startswith("opacity"):
+        c = _opacity_inputs(name == "opacity_multichem")
+        args = (c["t"], c["nbins"], c["ionDen"], c["elemAbun"], c["abIndex"], c["Hden"], c["active"], CONTBOLTZ1, GAUNTFF1,
+                c["Ne"], c["Te"], BREMS_P)
+        op, sca, ab = a.opacity_block(*args, dust=c["dust"], dust_model=c["dm"])
+        _, ff1 = AuxReference(O.load()).gas_opacity(*args)
+        return dict(opacity=op, scaOpac=sca, absOpac=ab, ff1=ff1)
+    model, g, t, J, Jd = _dust_inputs(name.endswith("debug"))
+    pdf = a.dust_pdf(model, g, t)
+    T, conv = a.dust_update(model, g, t, J, 0.05, Jdif=Jd)
+    return dict(dustPDF=pdf, Tdust=np.array(T), lgConverged=conv)
+
+
+def _gold(name):
+    import os
+
+    return os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", f"ref_aux_{name}.npz")

@@ -134,9 +134,17 @@ def test_dust_update_table_ends(case):
     model, t = case
     g = model.grids[0]
     g.Tdust[:, :, 1:] = F32(100.0)
-    zero = np.zeros((g.nCells + 1, model.nbins), dtype=F32, order="F")
-    T, conv = O.dust_update(model, g, t, zero, 0.05)
+    faint = np.full((g.nCells + 1, model.nbins), 1.0e-30, dtype=F32, order="F")
+    T, conv = O.dust_update(model, g, t, faint, 0.05)
     assert np.all(T[1, 1:, 1:] == 1.0)                       # below the table: 1 K (lgTalk branch)
+    # a cell no packet crossed is not updated at all (updateCell's lgHit test,
+    # update_mod.f90:104-149): Tdust and lgConverged keep the values they came in with
+    faint[3, :] = 0.0
+    was = np.zeros(g.nCells + 1, np.int32)
+    was[3] = 1
+    T, conv = O.dust_update(model, g, t, faint, 0.05, lgConverged=was)
+    assert np.all(T[:, :, 3] == 100.0) and conv[3] == 1
+    assert np.all(T[1, 1:, 4] == 1.0) and conv[4] == 0
     hot = _bath(model, g, t, 2900.0) * F32(10.0)
     T, conv = O.dust_update(model, g, t, hot, 0.05)
     assert np.all(T[1, 1:, 1:] == 3000.0)                    # above the table: nTemps

@@ -85,12 +85,25 @@ def test_dust_update_table_ends_and_unlit_cells():
     model, t = W.dust_closure(n=7, nbins=90)
     g = model.grids[0]
     eng = _engine(model, t)
-    eng.zero_estimators()                       # J = 0 everywhere: every grain below the table
-    zero = np.zeros((g.nCells + 1, model.nbins), F32, order="F")
+    T0 = g.Tdust.copy()
+    eng.zero_estimators()                       # J = 0 everywhere: no cell was crossed by a packet,
+    zero = np.zeros((g.nCells + 1, model.nbins), F32, order="F")       # updateCell leaves them all alone
     wantT, wantC = O.dust_update(model, g, t, zero, 0.05)
     T, conv, nconv = eng.getDustT(1, 0.05)
     assert _same(T, wantT) and np.array_equal(conv, wantC) and nconv == 0
-    assert np.all(T[1, 1:, 1:] == 1.0)
+    assert _same(T, T0)
+    # a very faint field: crossed cells fall below the table (1 K), the others keep their T
+    eng.setDustPDF(1)
+    eng.zero_estimators()
+    eng.energyPacketDriver(1, 40, deltaE=1.0e-25)
+    eng.reduce()
+    Js, _ = scale_estimators(model, eng.fetch(1)["Jste"], np.zeros((1, 1, 1), F32))
+    lit = (Js > 0).any(axis=1)
+    assert lit[1:].any() and not lit[1:].all()
+    wantT, wantC = O.dust_update(model, g, t, Js, 0.05)
+    T, conv, nconv = eng.getDustT(1, 0.05)
+    assert _same(T, wantT) and np.array_equal(conv, wantC)
+    assert np.all(T[1, 1:, lit] == 1.0) and _same(T[:, :, ~lit], T0[:, :, ~lit])
 
 
 def test_device_lucy_loop_matches_oracle_loop():
@@ -116,6 +129,7 @@ def test_device_lucy_loop_matches_oracle_loop():
         Jr = orc.folded(1, float(ref_model.deltaE[1]))["Jste"]
         assert _same(eng.fetch(1)["Jste"][1:], Jr[1:]), f"iteration {it}"
         Js, _ = scale_estimators(ref_model, Jr, np.zeros((1, 1, 1), F32))
+        # iterateMC zeroes grid%lgConverged before every iteration (iteration_mod.f90:87)
         wantT, wantC = O.dust_update(ref_model, rg, t, Js, 0.05)
         rg.Tdust = wantT
         assert _same(T, wantT), f"iteration {it}"

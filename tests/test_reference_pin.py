@@ -93,6 +93,52 @@ def test_platform_libm_changes_few_histories(oracle_lib):
 
 
 # ---------------------------------------------------------------------------------------------
+# the callers either side of the transport: K1 (opacity block of iterateMC), K5/K6 (dust closure)
+# ---------------------------------------------------------------------------------------------
+def _assert_same_nan(got, want):
+    """bit equality, except that two NaNs count as equal whatever their payload (a fully
+    sublimed cell makes setDustPDF divide 0 by 0 on both sides)"""
+    for k, w in want.items():
+        if k == "ff1":
+            continue
+        g = np.asarray(got[k])
+        assert g.shape == w.shape, (k, g.shape, w.shape)
+        if g.dtype == np.float32:
+            nan = np.isnan(w)
+            assert np.array_equal(np.isnan(g), nan), k
+            assert np.array_equal(_bits(g)[~nan], _bits(w)[~nan]), k
+        else:
+            assert np.array_equal(g, w), k
+
+
+@pytest.mark.parametrize("name", ref_cases.AUX_CASES)
+def test_oracle_aux_matches_reference_golden(name, oracle_lib):
+    """oracle_opacity / oracle_dust_pdf / oracle_dust_update against the outputs of the
+    reference's own iterateMC opacity block (iteration_mod.f90:106-230 incl. ionizationDriver,
+    addOpacity), emissionDriver -> setDustPDF and updateCell -> getDustT."""
+    want = dict(np.load(os.path.join(GOLD, f"ref_aux_{name}.npz")))
+    got = ref_cases.run_oracle_aux(name)
+    _assert_same_nan(got, want)
+    if name.startswith("dust"):
+        c = want["lgConverged"]
+        assert 0 < c[1:].sum() < c.shape[0] - 1              # converged and unconverged cells both occur
+        assert np.isnan(want["dustPDF"][5, :-1]).all() and want["dustPDF"][5, -1] == 1.0   # the fully sublimed cell: 0/0, last bin forced to 1
+        assert (want["Tdust"][1, 1, 1:] == 300.0).any()      # cells no packet crossed keep their Tdust
+    else:
+        assert want["ff1"][1:].min() > 1e-35 and want["scaOpac"][1:].any()
+
+
+@pytest.mark.skipif(not HAVE_REF, reason="reference sources not present")
+@pytest.mark.parametrize("name", ["opacity_multichem", "dust_closure_debug"])
+def test_translated_reference_reproduces_aux_golden(name, oracle_lib):
+    want = dict(np.load(os.path.join(GOLD, f"ref_aux_{name}.npz")))
+    got = ref_cases.run_reference_aux(name)
+    _assert_same_nan(got, want)
+    if "ff1" in want:
+        assert np.array_equal(_bits(got["ff1"]), _bits(want["ff1"]))
+
+
+# ---------------------------------------------------------------------------------------------
 # the translator itself
 # ---------------------------------------------------------------------------------------------
 SNIPPET = """
