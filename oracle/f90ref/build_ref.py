@@ -24,6 +24,10 @@ that the translator does not cover become calls that raise if they are ever reac
     continuum_mod.f90     getFlux                                         strict
     emission_mod.f90      emissionDriver with its internal setDustPDF     setDustPDF strict
     update_mod.f90        updateCell with its internal getDustT           getDustT strict
+    hydro_mod.f90         getOuterShell                                                     strict
+    update_mod.f90        lines 168-269 of updateCell (photo-ionisation rates nPhotoSte/nPhotoDif) and
+                          lines 1123-1234 of thermBalance (photo-ionisation heating), each as a
+                          synthetic subroutine with the host's declarations                 strict
     iteration_mod.f90     lines 106-230 of iterateMC (the opacity block: ionizationDriver over the
                           cells + the dust contribution to scaOpac/absOpac/opacity) as a
                           synthetic subroutine with iterateMC's declarations                strict
@@ -67,7 +71,7 @@ AUX_SOURCES = [
     ('interpolation_mod.f90', False, {'locate'}, None),
     ('common_mod.f90', True, None, None),
     ('ph_mod.f90', True, None, None),            # module xSec_mod
-    ('hydro_mod.f90', True, None, None),         # module elements_mod
+    ('hydro_mod.f90', False, {'getoutershell'}, None),   # module elements_mod
     ('grid_mod.f90', True, None, None),
     ('composition_mod.f90', True, None, None),
     ('continuum_mod.f90', False, {'getflux'}, None),
@@ -75,20 +79,37 @@ AUX_SOURCES = [
     ('emission_mod.f90', False, {'emissiondriver'}, {'setdustpdf'}),
     ('update_mod.f90', False, {'updatecell'}, {'getdustt'}),
 ]
-# A statement range of a procedure that cannot be run as a whole (iterateMC is the entire Lucy
-# iteration, MPI included): the opacity block of iterateMC -- ionizationDriver over all cells and
-# the dust contribution to scaOpac/absOpac/opacity -- wrapped, with iterateMC's own declarations,
-# into a synthetic subroutine.  (file, name, declaration line ranges, body line range, guards)
+# Statement ranges of procedures that cannot be run as a whole (iterateMC is the entire Lucy
+# iteration, MPI included; updateCell's gas branch is the whole ionisation/thermal solver),
+# wrapped -- with the host procedure's own declarations -- into synthetic subroutines.
+# dict(file, name, args, decls = line ranges of declarations, body = line ranges of statements,
+#      glue_decls / glue_end = the only lines that are ours: the dummies of the wrapper and the
+#      copy of a local result into them, guards = {line: expected start} against a changed file)
 AUX_SLICES = [
-    ('iteration_mod.f90', 'opacity_block', [(20, 20), (24, 24), (37, 77)], (106, 230),
-     {106: 'icell = 0', 108: 'do ig = 1, ngrids', 230: 'end do'}),
+    # the opacity block of iterateMC: ionizationDriver over all cells, the all-reduce, and the dust
+    # contribution to scaOpac/absOpac/opacity
+    dict(file='iteration_mod.f90', name='opacity_block', args='grid',
+         decls=[(20, 20), (24, 24), (37, 77)], body=[(106, 230)], glue_decls=[], glue_end=[],
+         guards={106: 'icell = 0', 108: 'do ig = 1, ngrids', 230: 'end do'}),
+    # updateCell: number of stellar/diffuse photo-ionisations per (element, ion)
+    dict(file='update_mod.f90', name='photo_rates', args='grid, xp, yp, zp, outste, outdif',
+         decls=[(18, 86)], body=[(90, 98), (168, 269)],
+         glue_decls=['real, intent(out) :: outste(nelements, nstages), outdif(nelements, nstages)'],
+         glue_end=['outste = nphotoste', 'outdif = nphotodif'],
+         guards={92: 'cellp = grid%active', 168: 'nphotoste = 1.e-20', 269: 'end do'}),
+    # thermBalance: heating by photo-ionisation, heatSte/heatDif
+    dict(file='update_mod.f90', name='photo_heat', args='grid, xp, yp, zp, outste, outdif',
+         decls=[(18, 86), (936, 959)], body=[(90, 98), (1123, 1234)],
+         glue_decls=['real, intent(out) :: outste, outdif'],
+         glue_end=['outste = heatste', 'outdif = heatdif'],
+         guards={936: 'real, intent(out) :: heatint', 1123: 'heatste = 0.', 1234: 'end do'}),
 ]
 # supplied by the harness: BoltGaunt (ionization_mod.f90:134-174) fills contBoltz/gauntFF from Gaunt
 # factor tables; its only trace in the opacity is the free-free term of bin 1, which the
 # oracle takes as an input (ff1), so the harness sets those arrays directly
 AUX_EXTERNS = {'boltgaunt'}
 # procedures that must translate completely, and the untranslated statements tolerated in them
-AUX_STRICT = {'opacity_block': 0, 'ionizationdriver': 0, 'edensum': 0, 'addopacity': 0, 'putopacity': 0, 'inopacity': 0, 'getflux': 0, 'locate': 0,
+AUX_STRICT = {'opacity_block': 0, 'photo_rates': 0, 'photo_heat': 0, 'getoutershell': 0, 'ionizationdriver': 0, 'edensum': 0, 'addopacity': 0, 'putopacity': 0, 'inopacity': 0, 'getflux': 0, 'locate': 0,
               'setdustpdf': 1,      # call qHeat (lgQHeat branch)
               'getdustt': 1}        # resLineHeating (gas + resonance-line transfer branch)
 
@@ -142,18 +163,22 @@ def translate_aux() -> str:
                 for p in m.procs.values():
                     p.contains = {k: v for k, v in p.contains.items() if k in keep_internal}
             mods.append(m)
-    for fn, name, decl_ranges, (b0, b1), guards in AUX_SLICES:
+    for sl in AUX_SLICES:
+        fn, name = sl['file'], sl['name']
         with open(os.path.join(source_dir(), fn), errors='replace') as fh:
             lines = fh.read().split('\n')
-        for ln, want in guards.items():
+        for ln, want in sl['guards'].items():
             got = ' '.join(lines[ln - 1].split('!')[0].lower().split())
             if not got.startswith(want):
                 raise f90py.TranslateError(f'{fn}:{ln}: expected {want!r}, found {got!r} (reference changed?)')
-        text = ['module slice_' + name, 'contains', f'subroutine {name}(grid)']
-        for a, b in decl_ranges:
+        text = ['module slice_' + name, 'contains', f'subroutine {name}({sl["args"]})']
+        for a, b in sl['decls']:
             text += lines[a - 1:b]
-        text += lines[b0 - 1:b1] + [f'end subroutine {name}', 'end module slice_' + name]
-        unit = f90py.Unit('\n'.join(text), f'{fn}[{b0}-{b1}]', lenient=True)
+        text += sl['glue_decls']
+        for a, b in sl['body']:
+            text += lines[a - 1:b]
+        text += sl['glue_end'] + [f'end subroutine {name}', 'end module slice_' + name]
+        unit = f90py.Unit('\n'.join(text), f'{fn}[{sl["body"]}]', lenient=True)
         mods.extend(unit.modules)
     gen = f90py.Gen(mods, lenient=True, externs=AUX_EXTERNS)
     code = gen.generate('@@HEADER@@')

@@ -4,6 +4,8 @@ the f90py translation) -- TEST INFRASTRUCTURE:
 * `gas_opacity`  : `ionizationDriver(grid, ix, iy, iz)` for every cell (ionization_mod.f90:26-129:
                    density loop, eDenSum, addOpacity/putOpacity/inOpacity).  BoltGaunt, whose only
                    trace in the result is the free-free term of bin 1, is supplied by the harness.
+* `photo`        : lines 168-269 of updateCell (nPhotoSte/nPhotoDif per element and ion) and lines
+                   1123-1234 of thermBalance (heatSte/heatDif), with getOuterShell (hydro_mod.f90).
 * `dust_pdf`     : `emissionDriver(grids, ix, iy, iz, iG)` on a dust-only model = setDustPDF
                    (emission_mod.f90:1313-1387) with getFlux (continuum_mod.f90:359-416).
 * `dust_update`  : `updateCell(grid, xP, yP, zP)` on a dust-only model = the no-gas branch
@@ -150,6 +152,58 @@ class AuxReference:
         with np.errstate(all='ignore'):
             self.ref.p_opacity_block(rt.wrap(grids))
         return op, sca, ab
+
+    # ------------------------------------------------------------------------------------------
+    def photo(self, t, nbins, nuArray, active, J, Jdif, ionDen, elemAbun, abIndex):
+        """per cell: nPhotoSte/nPhotoDif(30, nstages) of updateCell and heatSte/heatDif of
+        thermBalance.  J/Jdif are the host-scaled estimators (0:nCells, nbins); Jdif None = not
+        debug mode.  Also returns outShell(30, nstages) from getOuterShell for the band list."""
+        G, ref = self.G, self.ref
+        nR = J.shape[0]
+        G.lggas, G.lgdebug = True, Jdif is not None
+        G.nbins, G.nstages = int(nbins), int(t.nstages)
+        G.lgelementon = rt.wrap(np.asarray(t.lgElementOn) != 0)
+        G.elementxref = rt.wrap(_F(t.elementXref, np.int64))
+        G.xsecarray = rt.wrap(_F(t.xSecArray, np.float32))
+        G.nuarray = rt.wrap(_F(nuArray, np.float32))
+        for name, v in (('hlevxsecp', t.HlevXSecP1), ('hlevnup', t.HlevNuP1), ('heisingxsecp', t.HeISingXSecP1),
+                        ('heilevnup', t.HeIlevNuP1), ('heiixsecp', t.HeIIXSecP1), ('heiilevnup', t.HeIIlevNuP1)):
+            arr = getattr(G, name)
+            if arr is None:
+                arr = rt.alloc('i', [(1, 10)])
+                setattr(G, name, arr)
+            arr[1] = int(v)
+        G.elementp = rt.wrap(_F(t.elementP, np.int64))
+        G.iondenused = rt.alloc('r', [(1, ionDen.shape[1]), (1, t.nstages)])
+        g = ref.T_grid_type()
+        g.nx, g.ny, g.nz = active.shape
+        g.ncells = nR - 1
+        g.active = rt.wrap(_F(active, np.int64))
+        ab3 = np.zeros(active.shape, np.int64, order='F')
+        ab3[active > 0] = abIndex[active[active > 0]]
+        g.abfileindex = rt.wrap(ab3)
+        g.elemabun = rt.wrap(_F(elemAbun, np.float32))
+        g.jste = rt.wrap(_F(J, np.float32), (0, 1))
+        g.jdif = rt.wrap(_F(Jdif, np.float32), (0, 1)) if Jdif is not None else None
+        ns = int(t.nstages)
+        res = dict(nPhotoSte=np.zeros((nR, 30, ns), np.float32), nPhotoDif=np.zeros((nR, 30, ns), np.float32),
+                   heatSte=np.zeros(nR, np.float32), heatDif=np.zeros(nR, np.float32))
+        oste, odif = rt.alloc('r', [(1, 30), (1, ns)]), rt.alloc('r', [(1, 30), (1, ns)])
+        with np.errstate(all='ignore'):
+            for (i, j, k) in _cells(active):
+                c = int(active[i - 1, j - 1, k - 1])
+                G.iondenused.setall(rt.wrap(_F(ionDen[c], np.float32)))
+                ref.p_photo_rates(g, i, j, k, oste, odif)
+                res['nPhotoSte'][c], res['nPhotoDif'][c] = oste.a, odif.a
+                hs, hd = ref.p_photo_heat(g, i, j, k, rt.ZERO32, rt.ZERO32)
+                res['heatSte'][c], res['heatDif'][c] = hs, hd
+            shell = np.zeros((30, ns), np.int64)
+            for el in range(3, 31):
+                if t.lgElementOn[el - 1]:
+                    for ion in range(1, min(el, ns - 1) + 1):
+                        shell[el - 1, ion - 1] = ref.p_getoutershell(el, el - ion + 1, 0, 0, 0)[0]
+        res['outShell'] = shell
+        return res
 
     # ------------------------------------------------------------------------------------------
     def _dust_globals(self, model, tables, lgDebug=False):

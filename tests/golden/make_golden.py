@@ -17,7 +17,9 @@ scaInt; plane = planeIonDistribution.
 ref_aux_<case>.npz hold the outputs of the reference routines either side of the transport
 (oracle/f90ref/harness_aux.py): the opacity block of iterateMC (opacity, scaOpac, absOpac and the
 free-free term ff1 = FFOpacity(1) per cell), emissionDriver -> setDustPDF (dustPDF) and
-updateCell -> getDustT (Tdust, lgConverged) on seeded inputs built by tests/ref_cases.py.
+updateCell -> getDustT (Tdust, lgConverged), and the photo-ionisation rate / heating loops of
+updateCell / thermBalance (nPhotoSte, nPhotoDif per element and ion, heatSte, heatDif per cell, and
+getOuterShell's shell numbers) on seeded inputs built by tests/ref_cases.py.
 """
 import os
 import sys
@@ -33,9 +35,9 @@ import ref_cases  # noqa: E402
 
 
 def main(names):
-    for name in names or list(ref_cases.REF_CASES) + list(ref_cases.AUX_CASES):
-        if name in ref_cases.AUX_CASES:
-            res = ref_cases.run_reference_aux(name)
+    for name in names or list(ref_cases.REF_CASES) + list(ref_cases.AUX_CASES) + list(ref_cases.PHOTO_CASES):
+        if name in ref_cases.AUX_CASES or name in ref_cases.PHOTO_CASES:
+            res = ref_cases.run_reference_aux(name) if name in ref_cases.AUX_CASES else ref_cases.run_reference_photo(name)
             path = os.path.join(HERE, f"ref_aux_{name}.npz")
             np.savez_compressed(path, **res)
             print(f"{name}: {os.path.getsize(path)} bytes, " + ", ".join(f"{k}{tuple(v.shape)}" for k, v in res.items()))

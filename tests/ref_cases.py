@@ -191,3 +191,119 @@ def _gold(name):
     import os
 
     return os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", f"ref_aux_{name}.npz")
+
+
+# ---------------------------------------------------------------------------------------------
+# photo-rate pre-integration (K8): updateCell's nPhotoSte/nPhotoDif and thermBalance's heatSte
+# ---------------------------------------------------------------------------------------------
+PHOTO_CASES = ["photo", "photo_debug"]
+
+
+def _photo_inputs(debug):
+    from mocassin_b200.model import number_active
+    from mocassin_b200.opacity import XSecTables
+
+    rng = np.random.default_rng(41)
+    nbins, nstages, n = 70, 5, 20
+    on = np.zeros(30, np.int32)
+    for el in (1, 2, 6, 8, 20, 26):
+        on[el - 1] = 1
+    xref = np.zeros(30, np.int32)
+    xref[on > 0] = np.arange(1, int(on.sum()) + 1)
+    xs = [0.0, 0.0, 0.0]
+
+    def push(k, holes=True):
+        start = len(xs) + 1
+        v = (1e-18 * rng.lognormal(0.0, 2.0, k) * (np.arange(1, k + 1) ** -3.0) * 50).astype(np.float32)
+        if holes and k > 6:
+            v[k // 2] = np.float32(1e-37)          # thermBalance leaves its loop here, updateCell treats it as 0
+        xs.extend(v.tolist())
+        return start
+
+    tabs = dict(HlevNuP1=12, HeIlevNuP1=25, HeIIlevNuP1=40)
+    tabs["HlevXSecP1"] = push(nbins - 12 + 1, holes=False)
+    tabs["HeISingXSecP1"] = push(nbins - 25 + 1)
+    tabs["HeIIXSecP1"] = push(nbins - 40 + 1, holes=False)
+    elementP = np.zeros((30, 30, 7, 3), np.int32, order="F")
+    for el in range(3, 31):
+        if on[el - 1]:
+            for ion in range(1, min(el, nstages) + 1):
+                for sh in range(1, 8):
+                    lo = int(rng.integers(2, nbins - 8))
+                    hi = int(rng.integers(lo + 1, nbins + 1))
+                    elementP[el - 1, ion - 1, sh - 1, :] = (lo, hi, push(hi - lo + 1, holes=bool(rng.integers(0, 2))))
+    t = XSecTables(xSecArray=np.array(xs, np.float32), nstages=nstages, lgElementOn=on, elementXref=xref,
+                   elementP=elementP, nShells=np.full((30, 30), 7, np.int32, order="F"), **tabs)
+    mask = np.zeros((3, 3, 3), bool)
+    mask.reshape(-1)[:n] = True
+    active, nc = number_active(mask)
+    nu = np.geomspace(0.05, 40.0, nbins).astype(np.float32)
+    J = (rng.lognormal(-8.0, 2.0, (n + 1, nbins))).astype(np.float32, order="F")
+    J[rng.random(J.shape) < 0.2] = 0.0
+    J[0] = 0.0
+    Jd = (J * np.float32(0.3)).astype(np.float32, order="F")[::-1].copy(order="F") if debug else None
+    if Jd is not None:
+        Jd[0] = 0.0
+    ionDen = np.asfortranarray(rng.random((n + 1, int(on.sum()), nstages)).astype(np.float32))
+    elemAbun = np.asfortranarray((rng.random((2, 30)) * 1e-3).astype(np.float32))
+    abIndex = rng.integers(1, 3, n + 1).astype(np.int32)
+    return dict(t=t, nbins=nbins, nu=nu, active=active, J=J, Jd=Jd, ionDen=ionDen, elemAbun=elemAbun, abIndex=abIndex)
+
+
+def run_reference_photo(name):
+    from oracle import oracle as O
+    from oracle.f90ref.harness_aux import AuxReference
+
+    c = _photo_inputs(name.endswith("debug"))
+    return AuxReference(O.load()).photo(c["t"], c["nbins"], c["nu"], c["active"], c["J"], c["Jd"], c["ionDen"],
+                                        c["elemAbun"], c["abIndex"])
+
+
+def run_oracle_photo(name, outShell):
+    """oracle_photo_integrals on the band list a host builds from the reference's pointer tables
+    (one band per element and ion: outer shell from getOuterShell; update_mod.f90:175-204 for the
+    rates, :1125-1157 for the heating, whose upper limit is one bin higher), then thermBalance's
+    last step, heatSte = sum over ions of heat*ionDen*elemAbun (:1222-1231), in float32."""
+    from oracle import oracle as O
+
+    c = _photo_inputs(name.endswith("debug"))
+    t, nb = c["t"], c["nbins"]
+    ions, off, low, hiR, hiH = [], [], [], [], []
+    for el in range(1, 31):
+        if not t.lgElementOn[el - 1]:
+            continue
+        for ion in range(1, min(el, t.nstages - 1) + 1):
+            if el == 1:
+                o, l, h1, h2 = t.HlevXSecP1, t.HlevNuP1, nb, nb
+            elif el == 2 and ion == 1:
+                o, l, h1, h2 = t.HeISingXSecP1, t.HeIlevNuP1, nb, nb
+            elif el == 2:
+                o, l, h1, h2 = t.HeIIXSecP1, t.HeIIlevNuP1, nb, nb
+            else:
+                sh = int(outShell[el - 1, ion - 1])
+                l, h, o = (int(v) for v in t.elementP[el - 1, ion - 1, sh - 1, :])
+                h1, h2 = h - 1, h
+            ions.append((el, ion)); off.append(o); low.append(l); hiR.append(h1); hiH.append(h2)
+    nR = c["J"].shape[0]
+    res = dict(nPhotoSte=np.zeros((nR, 30, t.nstages), np.float32), nPhotoDif=np.zeros((nR, 30, t.nstages), np.float32),
+               heatSte=np.zeros(nR, np.float32), heatDif=np.zeros(nR, np.float32))
+    for key, hkey, J in (("nPhotoSte", "heatSte", c["J"]), ("nPhotoDif", "heatDif", c["Jd"])):
+        if J is None:
+            res[key][1:] = np.float32(0.0)
+            continue
+        nP, _ = O.photo_integrals(nb, off, low, hiR, t.xSecArray, c["nu"], J)
+        _, ht = O.photo_integrals(nb, off, low, hiH, t.xSecArray, c["nu"], J)
+        res[key][:] = np.float32(1.0e-20)
+        for b, (el, ion) in enumerate(ions):
+            res[key][:, el - 1, ion - 1] = nP[:, b]
+        ab = c["elemAbun"][np.maximum(c["abIndex"], 1) - 1]
+        tot = np.zeros(nR, np.float32)
+        for b, (el, ion) in enumerate(ions):
+            h = (ht[:, b] * c["ionDen"][:, int(t.elementXref[el - 1]) - 1, ion - 1]).astype(np.float32)
+            tot = (tot + (h * ab[:, el - 1]).astype(np.float32)).astype(np.float32)
+        res[hkey][:] = tot
+    res["nPhotoSte"][0] = 0
+    res["nPhotoDif"][0] = 0
+    res["heatSte"][0] = 0
+    res["heatDif"][0] = 0
+    return res

@@ -128,6 +128,27 @@ def test_oracle_aux_matches_reference_golden(name, oracle_lib):
         assert want["ff1"][1:].min() > 1e-35 and want["scaOpac"][1:].any()
 
 
+@pytest.mark.parametrize("name", ref_cases.PHOTO_CASES)
+def test_oracle_photo_integrals_match_reference_golden(name, oracle_lib):
+    """oracle_photo_integrals (K8) against the reference's own loops: update_mod.f90:168-269
+    (nPhotoSte/nPhotoDif of updateCell) and :1123-1234 (heatSte/heatDif of thermBalance), run per
+    cell; the band list is built from the pointer tables with getOuterShell's shell numbers."""
+    want = dict(np.load(os.path.join(GOLD, f"ref_aux_{name}.npz")))
+    got = ref_cases.run_oracle_photo(name, want["outShell"])
+    for k in ("nPhotoSte", "nPhotoDif", "heatSte", "heatDif"):
+        assert np.array_equal(_bits(got[k]), _bits(want[k])), k
+    assert (want["nPhotoSte"][1:] > 1e-20).any() and (want["heatSte"][1:] > 0).all()
+    assert (want["heatDif"][1:] > 0).any() == name.endswith("debug")
+
+
+@pytest.mark.skipif(not HAVE_REF, reason="reference sources not present")
+def test_translated_reference_reproduces_photo_golden(oracle_lib):
+    want = dict(np.load(os.path.join(GOLD, "ref_aux_photo_debug.npz")))
+    got = ref_cases.run_reference_photo("photo_debug")
+    for k, w in want.items():
+        assert np.array_equal(_bits(np.asarray(got[k])), _bits(w)), k
+
+
 @pytest.mark.skipif(not HAVE_REF, reason="reference sources not present")
 @pytest.mark.parametrize("name", ["opacity_multichem", "dust_closure_debug"])
 def test_translated_reference_reproduces_aux_golden(name, oracle_lib):
