@@ -24,6 +24,7 @@ that the translator does not cover become calls that raise if they are ever reac
     continuum_mod.f90     getFlux                                         strict
     emission_mod.f90      emissionDriver with its internal setDustPDF     setDustPDF strict
     update_mod.f90        updateCell with its internal getDustT           getDustT strict
+    output_mod.f90        writeSED (list-directed WRITEs are recorded, OPEN/CLOSE do nothing)  strict
     hydro_mod.f90         getOuterShell                                                     strict
     update_mod.f90        lines 168-269 of updateCell (photo-ionisation rates nPhotoSte/nPhotoDif) and
                           lines 1123-1234 of thermBalance (photo-ionisation heating), each as a
@@ -78,6 +79,7 @@ AUX_SOURCES = [
     ('ionization_mod.f90', False, {'ionizationdriver', 'edensum', 'addopacity'}, None),
     ('emission_mod.f90', False, {'emissiondriver'}, {'setdustpdf'}),
     ('update_mod.f90', False, {'updatecell'}, {'getdustt'}),
+    ('output_mod.f90', False, {'writesed'}, None),
 ]
 # Statement ranges of procedures that cannot be run as a whole (iterateMC is the entire Lucy
 # iteration, MPI included; updateCell's gas branch is the whole ionisation/thermal solver),
@@ -109,7 +111,7 @@ AUX_SLICES = [
 # oracle takes as an input (ff1), so the harness sets those arrays directly
 AUX_EXTERNS = {'boltgaunt'}
 # procedures that must translate completely, and the untranslated statements tolerated in them
-AUX_STRICT = {'opacity_block': 0, 'photo_rates': 0, 'photo_heat': 0, 'getoutershell': 0, 'ionizationdriver': 0, 'edensum': 0, 'addopacity': 0, 'putopacity': 0, 'inopacity': 0, 'getflux': 0, 'locate': 0,
+AUX_STRICT = {'writesed': 0, 'opacity_block': 0, 'photo_rates': 0, 'photo_heat': 0, 'getoutershell': 0, 'ionizationdriver': 0, 'edensum': 0, 'addopacity': 0, 'putopacity': 0, 'inopacity': 0, 'getflux': 0, 'locate': 0,
               'setdustpdf': 1,      # call qHeat (lgQHeat branch)
               'getdustt': 1}        # resLineHeating (gas + resonance-line transfer branch)
 

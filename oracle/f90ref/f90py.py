@@ -1022,6 +1022,23 @@ class Unit:
                 if it:
                     exprs.append(_expr_from(it, s))
             return ('print', ln, exprs)
+        if first in ('open', 'close') and len(toks) > 1 and toks[1].text == '(':
+            return ('ionoop', ln, s)
+        if first == 'write' and len(toks) > 1 and toks[1].text == '(':
+            # list-directed WRITE(unit,*) only; items may be implied-DO lists (expr, ..., v=lo,hi)
+            try:
+                close = _match_paren(toks, 1)
+                ctl = _split_top(toks[2:close])
+                if len(ctl) == 2 and len(ctl[1]) == 1 and ctl[1][0].text == '*':
+                    unit = _expr_from(ctl[0], s)
+                    items = []
+                    for it in _split_top(toks[close + 1:]):
+                        if it:
+                            items.append(_io_item(it, s))
+                    return ('write', ln, unit, items)
+            except TranslateError:
+                pass
+            return ('io', ln, s)
         if first in ('write', 'read', 'open', 'close', 'rewind', 'backspace', 'inquire') and len(toks) > 1 and toks[1].text == '(':
             return ('io', ln, s)
         if first == 'allocate' and toks[1].text == '(':
@@ -1053,6 +1070,20 @@ class Unit:
             if self.lenient:
                 return ('untranslated', ln, s)
             raise
+
+
+def _io_item(toks, src):
+    """an output item: an expression, or an implied-DO list ( item, item, ..., v = lo, hi [, st] )"""
+    if toks[0].text == '(' and _match_paren(toks, 0) == len(toks) - 1:
+        parts = _split_top(toks[1:-1])
+        for k, pt in enumerate(parts):
+            if len(pt) >= 3 and pt[0].kind == 'name' and pt[1].text == '=' and k >= 1 and len(parts) - k in (2, 3):
+                var = pt[0].text
+                lo = _expr_from(pt[2:], src)
+                hi = _expr_from(parts[k + 1], src)
+                st = _expr_from(parts[k + 2], src) if len(parts) - k == 3 else None
+                return ('implied', [_io_item(x, src) for x in parts[:k]], var, lo, hi, st)
+    return ('item', _expr_from(toks, src))
 
 
 def _match_paren(toks, i):
@@ -1735,6 +1766,12 @@ class Gen:
             self.emit(out, ind, pre + [f'_rt.fprint({ln}, {", ".join(items)})'])
         elif k == 'io':
             self.emit(out, ind, [f'_rt.unsupported({s[2]!r}, {ln})'])
+        elif k == 'ionoop':
+            self.emit(out, ind, [f'_rt.fio({s[2]!r})'])
+        elif k == 'write':
+            uc, _ = self.expr(s[2], sc, pre)
+            items = [self.io_item(it, sc, pre) for it in s[3]]
+            self.emit(out, ind, pre + [f'_rt.fwrite({uc}, [{", ".join(items)}])'])
         elif k == 'allocate':
             lines = []
             for a in s[2]:
@@ -1775,6 +1812,20 @@ class Gen:
             self.emit(out, ind, pre + lines)
         else:
             raise TranslateError(f'statement kind {k}')
+
+    def io_item(self, it, sc: Scope, pre) -> str:
+        if it[0] == 'item':
+            return self.expr(it[1], sc, pre)[0]
+        _, inner, var, lo, hi, st = it
+        r = sc.lookup_var(var)
+        if r is None or r[0] != 'local':
+            raise TranslateError(f'implied-DO variable {var} must be a local')
+        vname = r[2]
+        parts = ', '.join(self.io_item(x, sc, pre) for x in inner)
+        loc, hic = self.expr(lo, sc, pre)[0], self.expr(hi, sc, pre)[0]
+        stc = self.expr(st, sc, pre)[0] if st is not None else '1'
+        # the comprehension binds the loop variable in its own scope, like the implied DO
+        return f'*[_x for {vname} in _rt.frange({loc}, {hic}, {stc}) for _x in ({parts},)]'
 
     def alloc_code(self, ty: Ty, dims: List[str]) -> str:
         if ty.base == 't':

@@ -6,6 +6,8 @@ the f90py translation) -- TEST INFRASTRUCTURE:
                    trace in the result is the free-free term of bin 1, is supplied by the harness.
 * `photo`        : lines 168-269 of updateCell (nPhotoSte/nPhotoDif per element and ion) and lines
                    1123-1234 of thermBalance (heatSte/heatDif), with getOuterShell (hydro_mod.f90).
+* `write_sed`    : `writeSED(grid)` (output_mod.f90:2508-2719); the records it writes to unit 16
+                   are captured instead of going to output/SED.out.
 * `dust_pdf`     : `emissionDriver(grids, ix, iy, iz, iG)` on a dust-only model = setDustPDF
                    (emission_mod.f90:1313-1387) with getFlux (continuum_mod.f90:359-416).
 * `dust_update`  : `updateCell(grid, xP, yP, zP)` on a dust-only model = the no-gas branch
@@ -204,6 +206,39 @@ class AuxReference:
                         shell[el - 1, ion - 1] = ref.p_getoutershell(el, el - ion + 1, 0, 0, 0)[0]
         res['outShell'] = shell
         return res
+
+    # ------------------------------------------------------------------------------------------
+    def write_sed(self, model, widFlx, escaped):
+        """writeSED on host-scaled escapedPackets arrays (one (0:nCells,0:nbins,0:nAngleBins)
+        float32 array per grid).  Returns (SED (nbins, nAngleBins+1) as written, totalE)."""
+        G, ref = self.G, self.ref
+        at = model.angle_tables()
+        G.nbins, G.ngrids, G.nanglebins = int(model.nbins), int(model.nGrids), int(model.nAngleBins)
+        G.lgecho, G.lgnosource, G.lgequivalenttau, G.niteratemc = False, False, False, 1
+        G.lgsymmetricxyz = bool(model.lgSymmetricXYZ)
+        G.dtheta, G.dphi = np.float32(at['dTheta']), np.float32(at['dPhi'])
+        G.viewpointtheta = rt.wrap(_F(at['viewPointTheta'], np.float32), (0,))
+        G.viewpointphi = rt.wrap(_F(at['viewPointPhi'], np.float32), (0,))
+        G.nuarray = rt.wrap(_F(model.nuArray, np.float32))
+        G.widflx = rt.wrap(_F(widFlx, np.float32))
+        G.radio4p9ghzp = 1
+        G.lstar = rt.wrap(np.zeros(1, np.float32))
+        G.nphotons = rt.wrap(np.zeros(1, np.int64))
+        grids = np.empty(model.nGrids, dtype=object)
+        for i, (g, e) in enumerate(zip(model.grids, escaped)):
+            t = ref.T_grid_type()
+            t.nx, t.ny, t.nz, t.ncells = g.nx, g.ny, g.nz, int(g.nCells)
+            t.escapedpackets = rt.wrap(_F(e, np.float32), (0, 0, 0))
+            grids[i] = t
+        rt.io_log.clear()
+        with np.errstate(all='ignore'):
+            ref.p_writesed(rt.wrap(grids))
+        recs = rt.io_log.get(16, [])
+        rows = [r for r in recs if len(r) == model.nAngleBins + 3 and not isinstance(r[0], str)]
+        assert len(rows) == model.nbins, (len(rows), model.nbins)
+        sed = np.array([[r[2 + a] for a in range(model.nAngleBins + 1)] for r in rows], np.float32)
+        tot = [r for r in recs if isinstance(r[0], str) and r[0].startswith('Total energy')][0][1]
+        return sed, np.float32(tot), rows
 
     # ------------------------------------------------------------------------------------------
     def _dust_globals(self, model, tables, lgDebug=False):

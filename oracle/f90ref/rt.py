@@ -230,6 +230,18 @@ def mpi_allreduce_single(send, recv):
     recv.setall(send)
 
 
+io_log = {}       # unit -> list of records (tuples of the values of a list-directed WRITE)
+
+
+def fwrite(unit, items):
+    io_log.setdefault(int(unit), []).append(tuple(items))
+
+
+def fio(what):
+    """OPEN / CLOSE: nothing to do, WRITE records are kept in io_log"""
+    return None
+
+
 def unsupported(what, line):
     raise NotImplementedError(f'untranslated statement reached at line {line}: {what}')
 

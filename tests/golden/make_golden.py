@@ -19,7 +19,9 @@ ref_aux_<case>.npz hold the outputs of the reference routines either side of the
 free-free term ff1 = FFOpacity(1) per cell), emissionDriver -> setDustPDF (dustPDF) and
 updateCell -> getDustT (Tdust, lgConverged), and the photo-ionisation rate / heating loops of
 updateCell / thermBalance (nPhotoSte, nPhotoDif per element and ion, heatSte, heatDif per cell, and
-getOuterShell's shell numbers) on seeded inputs built by tests/ref_cases.py.
+getOuterShell's shell numbers) on seeded inputs built by tests/ref_cases.py.  ref_aux_sed_<case>.npz:
+what writeSED writes to output/SED.out (nu, lambda, SED per viewing angle, total energy) for the
+escapedPackets of the transport case of the same name.
 """
 import os
 import sys
@@ -35,7 +37,14 @@ import ref_cases  # noqa: E402
 
 
 def main(names):
-    for name in names or list(ref_cases.REF_CASES) + list(ref_cases.AUX_CASES) + list(ref_cases.PHOTO_CASES):
+    for name in names or list(ref_cases.REF_CASES) + list(ref_cases.AUX_CASES) + list(ref_cases.PHOTO_CASES) + \
+            ["sed:" + c for c in ref_cases.SED_CASES]:
+        if name.startswith("sed:"):          # after the transport cases: reads their golden files
+            res = ref_cases.run_reference_sed(name[4:])
+            path = os.path.join(HERE, f"ref_aux_sed_{name[4:]}.npz")
+            np.savez_compressed(path, **res)
+            print(f"{name}: {os.path.getsize(path)} bytes, totalE {float(res['totalE'])}")
+            continue
         if name in ref_cases.AUX_CASES or name in ref_cases.PHOTO_CASES:
             res = ref_cases.run_reference_aux(name) if name in ref_cases.AUX_CASES else ref_cases.run_reference_photo(name)
             path = os.path.join(HERE, f"ref_aux_{name}.npz")

@@ -307,3 +307,37 @@ def run_oracle_photo(name, outShell):
     res["heatSte"][0] = 0
     res["heatDif"][0] = 0
     return res
+
+
+# ---------------------------------------------------------------------------------------------
+# writeSED (K7 + the host scaling of mocassin_b200/output.py)
+# ---------------------------------------------------------------------------------------------
+SED_CASES = ["viewing_angles", "viewing_angles_phifree", "multigrid_sym", "hii_sym_gas"]
+
+
+def sed_inputs(name):
+    """model, widFlx, the reference's escapedPackets of the transport golden file, and `raw` = its
+    sequential float32 sum over cells (the order writeSED adds in: grids, then cells)"""
+    import os
+
+    m, n, mode = make(name)
+    gold = dict(np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", f"ref_{name}.npz")))
+    esc = [gold[f"escapedPackets_g{i + 1}"] for i in range(m.nGrids)]
+    raw = np.zeros((m.nbins, m.nAngleBins + 1), np.float32)
+    for e in esc:
+        for i in range(e.shape[0]):
+            raw = (raw + e[i, 1:, :]).astype(np.float32)
+    return m, W.wid_flx(m.nuArray), esc, raw
+
+
+def run_reference_sed(name):
+    from oracle import oracle as O
+    from oracle.f90ref.harness_aux import AuxReference
+
+    m, wid, esc, raw = sed_inputs(name)
+    # the host divides escapedPackets by 8 for symmetricXYZ before writeSED (iteration_mod.f90:719);
+    # writeSED is host code: COS is the platform's (numpy's), not detmath
+    scaled = [(e / np.float32(8.0)).astype(np.float32) if m.lgSymmetricXYZ else e for e in esc]
+    sed, tot, rows = AuxReference(O.load(), math="libm").write_sed(m, wid, scaled)
+    return dict(SED=sed, totalE=np.float32(tot), nu=np.array([r[0] for r in rows], np.float32),
+                lambda_um=np.array([r[1] for r in rows], np.float32))

@@ -159,6 +159,39 @@ def test_translated_reference_reproduces_aux_golden(name, oracle_lib):
         assert np.array_equal(_bits(got["ff1"]), _bits(want["ff1"]))
 
 
+@pytest.mark.parametrize("name", ref_cases.SED_CASES)
+def test_sed_scaling_matches_reference_writesed(name, oracle_lib):
+    """mocassin_b200/output.py (the host part of writeSED that follows the device reduction K7)
+    against what the reference's own writeSED writes (output_mod.f90:2508-2719, unit 16 records
+    captured): bit exact when fed the reference's float32 cell sum; and the device's exact count
+    sum (K7: count * deltaE) agrees with that float32 sum to its accumulation error."""
+    from mocassin_b200 import output
+    from oracle.oracle import Oracle
+
+    want = dict(np.load(os.path.join(GOLD, f"ref_aux_sed_{name}.npz")))
+    m, wid, esc, raw = ref_cases.sed_inputs(name)
+    sed, totalE = output.sed_from_raw(m, wid, raw)
+    assert np.array_equal(_bits(sed), _bits(want["SED"]))
+    assert np.float32(totalE) == want["totalE"]
+    lam = (output.C_LIGHT / (m.nuArray.astype(np.float32) * output.FR1RYD)).astype(np.float32) * np.float32(1.0e4)
+    assert np.array_equal(lam, want["lambda_um"]) and np.array_equal(m.nuArray.astype(np.float32), want["nu"])
+    o = Oracle(m)
+    o.transport(1, 0, ref_cases.REF_CASES[name][2], seed=ref_cases.SEED)
+    cnt, rawq = o.sed(float(m.deltaE[1]))
+    assert np.array_equal(cnt, np.rint(raw.astype(np.float64) / float(m.deltaE[1])).astype(np.int64))
+    assert np.allclose(rawq, raw, rtol=1e-5, atol=0)
+    sedq, totq = output.sed_from_raw(m, wid, rawq)
+    assert np.allclose(sedq, want["SED"], rtol=2e-5, atol=0) and abs(totq / float(want["totalE"]) - 1) < 1e-5
+
+
+@pytest.mark.skipif(not HAVE_REF, reason="reference sources not present")
+def test_translated_writesed_reproduces_golden(oracle_lib):
+    want = dict(np.load(os.path.join(GOLD, "ref_aux_sed_viewing_angles_phifree.npz")))
+    got = ref_cases.run_reference_sed("viewing_angles_phifree")
+    for k, w in want.items():
+        assert np.array_equal(_bits(np.asarray(got[k])), _bits(w)), k
+
+
 # ---------------------------------------------------------------------------------------------
 # the translator itself
 # ---------------------------------------------------------------------------------------------
