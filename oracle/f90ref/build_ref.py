@@ -137,20 +137,12 @@ def translate() -> str:
             if keep is not None:
                 m.procs = {k: v for k, v in m.procs.items() if k in keep}
             mods.append(m)
-    gen = f90py.Gen(mods, loop_hooks=LOOP_HOOKS, proc_hooks=PROC_HOOKS)
+    gen = f90py.Gen(mods, loop_hooks=LOOP_HOOKS, proc_hooks=PROC_HOOKS)      # strict: every statement
+    code = gen.generate('@@HEADER@@')
     header = ('# GENERATED by oracle/f90ref/build_ref.py from the Fortran sources under\n'
               f'# {source_dir()} -- a build artefact, do not edit, do not commit.\n'
-              '# translator notes:\n' + ''.join(f'#   {w}\n' for w in gen_warnings(gen)))
-    code = gen.generate(header)
-    # generate() may add warnings; put the final list in the header
-    header2 = ('# GENERATED by oracle/f90ref/build_ref.py from the Fortran sources under\n'
-               f'# {source_dir()} -- a build artefact, do not edit, do not commit.\n'
-               '# translator notes:\n' + ''.join(f'#   {w}\n' for w in gen.warnings))
-    return code.replace(header, header2, 1)
-
-
-def gen_warnings(gen):
-    return list(gen.warnings)
+              '# translator notes:\n' + ''.join(f'#   {w}\n' for w in gen.warnings))
+    return code.replace('@@HEADER@@', header, 1)
 
 
 def translate_aux() -> str:

@@ -3,7 +3,8 @@
  *
  * Plain-C restatement of the reference's energy-packet transport.  Only tests/,
  * __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference legs may
- * load this.  PARITY UNPINNED (see mc_oracle.h).
+ * load this.  Pinned against the reference's own code run through oracle/f90ref (see
+ * mc_oracle.h, tests/test_reference_pin.py).
  *
  * Follows, routine by routine (all citations into /root/reference/source/):
  *   energyPacketDriver   photon_mod.f90:26-286    -> run_packet / oracle_transport

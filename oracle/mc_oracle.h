@@ -5,10 +5,18 @@
  * transport of the reference (source/photon_mod.f90:26-2974) and of the per-cell
  * opacity assembly (source/ionization_mod.f90:349-484, iteration_mod.f90:166-227).
  *
- * PARITY UNPINNED: the reference ships no golden vectors / tests for this path
- *  and cannot be compiled here (no Fortran compiler), so
- * this oracle is pinned only by its own unit tests (geometry, locate, getNu2, hg,
- * conservation, analytic limits) -- see DESIGN.md.
+ * PIN: the reference ships no golden vectors / tests for this path
+ * and cannot be compiled here (no Fortran compiler).  It is *run* all the same: oracle/f90ref
+ * translates photon_mod.f90 (and ionization_mod/emission_mod/update_mod/output_mod routines
+ * either side of it) statement by statement into an executable module under oracle/_ref/, and
+ * this oracle is checked against that -- bit for bit, every float32 tally element and every
+ * packet history -- in tests/test_reference_pin.py, live where /root/reference exists and
+ * through the golden vectors tests/golden/ref_*.npz everywhere.  Two restatement errors were
+ * found and fixed that way (getNu2's "+1" rule on linePDF rows; updateCell's no-hit return).
+ * Bound from outside, because the Fortran standard leaves them to the processor:
+ * RANDOM_NUMBER (Philox here) and LOG/SIN/COS/ACOS/ATAN/EXP (detmath here); with the
+ * platform's libm instead of detmath a few per cent of the packet histories differ by a
+ * branch flipped at the last ulp (test_platform_libm_changes_few_histories).
  *
  * Array layouts follow the Fortran reference (column major, 1-based unless noted):
  *   active(nx,ny,nz)               -> active[(x-1) + nx*((y-1) + ny*(z-1))]

@@ -2,7 +2,8 @@
 
 TEST INFRASTRUCTURE: only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline /
 --impl reference legs may import this module.  The product package (mocassin_b200)
-never does.  PARITY UNPINNED (see oracle/mc_oracle.h).
+never does.  Pinned against the reference's own code run through oracle/f90ref (see
+oracle/mc_oracle.h).
 """
 from __future__ import annotations
 
