@@ -187,7 +187,10 @@ int mcb200_set_dust_state(mcb200_ctx *ctx, int32_t iG, const float *Tdust,
  *   (Jdif in debug mode) with the host scaling of iteration_mod.f90:705-724 applied on the
  *   fly (*1e-9, /8 for symmetricXYZ), updates the device Tdust and the sublimation flags of
  *   the next transport.  Optional outputs: Tdust(0:nSpeciesMax,0:nSizes,0:nCells),
- *   lgConverged(0:nCells), and the number of converged cells.  A grain whose absorption
+ *   lgConverged(0:nCells), and the number of converged cells.  A cell no packet crossed (no
+ *   Jste(cell,:) > 0, nor Jdif in debug mode) is left alone, as updateCell returns first thing
+ *   for it (update_mod.f90:104-149): its Tdust stays, its lgConverged is the 0 iterateMC gives
+ *   every cell at the start of an iteration (iteration_mod.f90:87).  A grain whose absorption
  *   integral is below dustEmIntegral(.,.,1) gets 1 K (the reference's lgTalk branch; without
  *   lgTalk the reference reads dustEmIntegral(.,.,0), out of bounds).  In multi-rank runs every
  *   rank holds the reduced Jste and updates all cells itself: no exchange (the reference
