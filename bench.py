@@ -412,6 +412,7 @@ def run_b200(args):
                 "kernel": "mcb::wf_fly_kernel<false> (+ event/sort kernels of the wave-front pipeline)", "algorithmic_bytes_per_segment": ALG_BYTES_PER_SEGMENT,
                 "segments_per_launch": segs / args.steps, "kernel_ms_per_launch": kms / args.steps,
                 "segments_per_s": segs / (kms / 1e3)}
+    access = access_roofline(eng, g, nb, segs / (kms / 1e3)) if world == 1 else None
     cpu = None
     if not args.no_cpu and world == 1:
         cpu = cpu_baseline(args, eng, model, g)
@@ -422,7 +423,7 @@ def run_b200(args):
         "config": workload_config(args, P), "clocks": clocks, "e2e": e2e,
         "gpu_launches": int(launches),            # counted by the library: wave-front kernels + fold kernels
         "waves_per_step": waves / args.steps,
-        "roofline": roofline, "cpu_baseline": cpu,
+        "roofline": roofline, "access_roofline": access, "cpu_baseline": cpu,
         "segments_per_packet": segs_all / (nGlobal * args.steps),
         "flights_per_packet": flights / (P * args.steps),
         "kernel_ms_per_step": kms_max / args.steps, "wall_ms_per_step": 1e3 * wall_max / args.steps,
@@ -432,6 +433,34 @@ def run_b200(args):
     print(json.dumps(line), flush=True)
     if world > 1:
         dist.barrier(); dist.destroy_process_group()
+
+
+def access_roofline(eng, g, nb, segs_per_s):
+    """The second roofline SURVEY.md 8d asks for: cell crossings per second against the measured
+    rate at which this GPU serves the crossing's access pattern and nothing else -- one 4-byte
+    opacity read plus one 64-bit Jste reduction at addresses the lanes of a warp do not share
+    (mcb200_test_access_peak).  `peak`: both windows the size of one nu-plane (what the
+    frequency-ordered FLY kernel keeps in L2); `peak_dram`: windows the size of the whole tables."""
+    import ctypes as C
+
+    plane_q, plane_f = 8 * (g.nCells + 1), 4 * (g.nCells + 1)
+
+    def peak(mode, qbytes, fbytes, ops):
+        v = C.c_double()
+        eng._check(eng.lib.mcb200_test_access_peak(eng.h, mode, int(qbytes), int(fbytes), int(ops), C.byref(v)))
+        return float(v.value)
+
+    try:
+        mixed_l2 = peak(3, plane_q, plane_f, 1 << 29)
+        red_l2 = peak(1, plane_q, plane_f, 1 << 29)
+        mixed_dram = peak(3, plane_q * nb, plane_f * nb, 1 << 27)
+    except Exception as ex:          # a measurement aid must not take the bench line down
+        return {"error": str(ex)}
+    return {"bound": "memory-system request rate: 1 LDG.32 + 1 RED.64 per cell crossing at scattered addresses",
+            "achieved": segs_per_s, "peak": mixed_l2, "unit": "crossings/s", "frac": segs_per_s / mixed_l2,
+            "peak_kind": "measured here: access_peak_kernel, windows = one nu-plane of opacity / JsteQ (L2 resident)",
+            "peak_red64_only": red_l2, "peak_dram": mixed_dram,
+            "frac_of_dram_regime": segs_per_s / mixed_dram}
 
 
 def cpu_baseline(args, eng, model, g):

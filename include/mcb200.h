@@ -354,6 +354,14 @@ int mcb200_test_detmath(mcb200_ctx *ctx, int32_t which, const float *in, float *
 int mcb200_test_uniforms(mcb200_ctx *ctx, uint64_t seed, uint64_t pid, uint32_t stream,
                          int32_t n, float *out);
 
+/* measurement hook (bench.py, SURVEY.md 8d "atomic roofline"): rate at which the device serves
+ * the transport's per-crossing access pattern and nothing else -- mode bit 0: one 64-bit
+ * reduction, bit 1: one 4-byte read, per iteration, at uniformly random addresses inside windows
+ * of the given sizes (a nu-plane of JsteQ / opacity at 128^3 is 16.8 / 8.4 MB: L2 resident; use
+ * GBs for the DRAM regime).  Returns iterations per second (best of 3 timed launches). */
+int mcb200_test_access_peak(mcb200_ctx *ctx, int32_t mode, int64_t redWindowBytes, int64_t loadWindowBytes,
+                            int64_t opsTotal, double *opsPerSecond);
+
 #ifdef __cplusplus
 }
 #endif

@@ -1659,6 +1659,66 @@ int mcb200_test_detmath(mcb200_ctx *ctx, int32_t which, const float *in, float *
     return MCB200_OK;
 }
 
+// Speed of light of the transport's access pattern ("atomic roofline"): every cell
+// crossing is one 4-byte read of opacity(cell, nu) and one 64-bit reduction into JsteQ(cell, nu)
+// at an address the lanes of a warp do not share.  This kernel issues exactly those two requests
+// per iteration at uniformly random addresses inside two windows and nothing else, so its rate
+// is what the memory system can give that pattern; bench.py reports the FLY kernel against it.
+__global__ void __launch_bounds__(256) access_peak_kernel(unsigned long long *q, const float *tab, unsigned long long nq,
+                                                          unsigned long long nt, int iters, int mode, float *sink)
+{
+    unsigned int s = (blockIdx.x * blockDim.x + threadIdx.x) * 2654435761u + 12345u;
+    float acc = 0.f;
+#pragma unroll 4
+    for (int i = 0; i < iters; ++i) {
+        s = s * 1664525u + 1013904223u;
+        unsigned int h = s ^ (s >> 15);
+        if (mode & 1) atomicAdd(&q[((unsigned long long)h * nq) >> 32], 1ull);                 // RED.E.ADD.64
+        if (mode & 2) acc += __ldg(&tab[((unsigned long long)(h * 2246822519u) * nt) >> 32]);  // LDG.32
+    }
+    if (acc == 123.456f) *sink = acc;
+}
+
+int mcb200_test_access_peak(mcb200_ctx *ctx, int32_t mode, int64_t redWindowBytes, int64_t loadWindowBytes,
+                            int64_t opsTotal, double *opsPerSecond)
+{
+    NEED_CTX();
+    if (!(mode >= 1 && mode <= 3) || redWindowBytes < 8 || loadWindowBytes < 4 || opsTotal < 1 || !opsPerSecond)
+        return fail(ctx, MCB200_EINVAL, "bad access-peak arguments");
+    DevBuf<unsigned long long> q;
+    DevBuf<float> t, sink;
+    const unsigned long long nq = (unsigned long long)redWindowBytes / 8, nt = (unsigned long long)loadWindowBytes / 4;
+    CU(q.alloc((size_t)nq));
+    CU(t.alloc((size_t)nt));
+    CU(sink.alloc(1));
+    CU(q.zero(ctx->stream));
+    CU(t.zero(ctx->stream));
+    int dev = 0, sms = 0;
+    CU(cudaGetDevice(&dev));
+    CU(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+    const int blocks = sms * 8, threads = 256;                 // 2048 threads per SM: full occupancy
+    int iters = (int)((opsTotal + (int64_t)blocks * threads - 1) / ((int64_t)blocks * threads));
+    if (iters < 1) iters = 1;
+    cudaEvent_t e0, e1;
+    CU(cudaEventCreate(&e0));
+    CU(cudaEventCreate(&e1));
+    float best = 0.f;
+    for (int rep = 0; rep < 4; ++rep) {                        // first repetition warms up; best of the rest
+        CU(cudaEventRecord(e0, ctx->stream));
+        access_peak_kernel<<<blocks, threads, 0, ctx->stream>>>(q.p, t.p, nq, nt, iters, mode, sink.p);
+        CU(cudaGetLastError());
+        CU(cudaEventRecord(e1, ctx->stream));
+        CU(cudaEventSynchronize(e1));
+        float ms = 0.f;
+        CU(cudaEventElapsedTime(&ms, e0, e1));
+        if (rep > 0 && (best == 0.f || ms < best)) best = ms;
+    }
+    cudaEventDestroy(e0);
+    cudaEventDestroy(e1);
+    *opsPerSecond = (double)blocks * threads * iters / ((double)best * 1e-3);
+    return MCB200_OK;
+}
+
 int mcb200_test_uniforms(mcb200_ctx *ctx, uint64_t seed, uint64_t pid, uint32_t stream, int32_t n, float *out)
 {
     NEED_CTX();
