@@ -25,6 +25,7 @@ that the translator does not cover become calls that raise if they are ever reac
     emission_mod.f90      emissionDriver with its internal setDustPDF     setDustPDF strict
     update_mod.f90        updateCell with its internal getDustT           getDustT strict
     output_mod.f90        writeSED (list-directed WRITEs are recorded, OPEN/CLOSE do nothing)  strict
+    grid_mod.f90          writeGrid (grid0-3.out, dustGrid.out, photoSource.out records)        strict
     hydro_mod.f90         getOuterShell                                                     strict
     update_mod.f90        lines 168-269 of updateCell (photo-ionisation rates nPhotoSte/nPhotoDif) and
                           lines 1123-1234 of thermBalance (photo-ionisation heating), each as a
@@ -73,8 +74,9 @@ AUX_SOURCES = [
     ('common_mod.f90', True, None, None),
     ('ph_mod.f90', True, None, None),            # module xSec_mod
     ('hydro_mod.f90', False, {'getoutershell'}, None),   # module elements_mod
-    ('grid_mod.f90', True, None, None),
+    ('grid_mod.f90', False, {'writegrid'}, None),
     ('composition_mod.f90', True, None, None),
+    ('set_input_mod.f90', True, None, None),
     ('continuum_mod.f90', False, {'getflux'}, None),
     ('ionization_mod.f90', False, {'ionizationdriver', 'edensum', 'addopacity'}, None),
     ('emission_mod.f90', False, {'emissiondriver'}, {'setdustpdf'}),
@@ -111,7 +113,7 @@ AUX_SLICES = [
 # oracle takes as an input (ff1), so the harness sets those arrays directly
 AUX_EXTERNS = {'boltgaunt'}
 # procedures that must translate completely, and the untranslated statements tolerated in them
-AUX_STRICT = {'writesed': 0, 'opacity_block': 0, 'photo_rates': 0, 'photo_heat': 0, 'getoutershell': 0, 'ionizationdriver': 0, 'edensum': 0, 'addopacity': 0, 'putopacity': 0, 'inopacity': 0, 'getflux': 0, 'locate': 0,
+AUX_STRICT = {'writegrid': 0, 'writesed': 0, 'opacity_block': 0, 'photo_rates': 0, 'photo_heat': 0, 'getoutershell': 0, 'ionizationdriver': 0, 'edensum': 0, 'addopacity': 0, 'putopacity': 0, 'inopacity': 0, 'getflux': 0, 'locate': 0,
               'setdustpdf': 1,      # call qHeat (lgQHeat branch)
               'getdustt': 1}        # resLineHeating (gas + resonance-line transfer branch)
 

@@ -8,6 +8,8 @@ the f90py translation) -- TEST INFRASTRUCTURE:
                    1123-1234 of thermBalance (heatSte/heatDif), with getOuterShell (hydro_mod.f90).
 * `write_sed`    : `writeSED(grid)` (output_mod.f90:2508-2719); the records it writes to unit 16
                    are captured instead of going to output/SED.out.
+* `write_grid`   : `writeGrid(grid)` (grid_mod.f90:2646-2870): the records of grid0-3.out, dustGrid.out
+                   and photoSource.out, captured per unit.
 * `dust_pdf`     : `emissionDriver(grids, ix, iy, iz, iG)` on a dust-only model = setDustPDF
                    (emission_mod.f90:1313-1387) with getFlux (continuum_mod.f90:359-416).
 * `dust_update`  : `updateCell(grid, xP, yP, zP)` on a dust-only model = the no-gas branch
@@ -239,6 +241,95 @@ class AuxReference:
         sed = np.array([[r[2 + a] for a in range(model.nAngleBins + 1)] for r in rows], np.float32)
         tot = [r for r in recs if isinstance(r[0], str) and r[0].startswith('Total energy')][0][1]
         return sed, np.float32(tot), rows
+
+    # ------------------------------------------------------------------------------------------
+    def write_grid(self, model, rp, state):
+        """writeGrid on a Model + checkpoint.RunParams + per-grid state arrays (dict with lists
+        lgConverged, lgBlack, and for gas Te, Ne, ionDen, abFileIndex plus lgElementOn/elementXref;
+        star: contShape, TStellar, LStar, nPhotons, spID, tStep; lgMultiChemistry, totalDustMass).
+        Returns {unit: [record tuples]} (21 grid0, 20 grid1, 30 grid2, 50 dustGrid, 42 photoSource,
+        40 grid3)."""
+        G, ref = self.G, self.ref
+        m = model
+        G.ngrids, G.nbins, G.nstars = int(m.nGrids), int(m.nbins), int(m.nStars)
+        G.lggas, G.lgdust, G.lg2d = bool(m.lgGas), bool(m.lgDust), bool(rp.lg2D)
+        G.lgmultichemistry = bool(state.get('lgMultiChemistry', False))
+        G.r_out = np.float32(m.R_out)
+        G.nsizes, G.nspeciesmax, G.nspecies = int(m.nSizes), int(m.nSpeciesMax), int(rp.nSpecies)
+        G.totaldustmass = np.float32(state.get('totalDustMass', 0.0))
+        G.nstages = int(rp.nstages)
+        if m.lgGas:
+            G.lgelementon = rt.wrap(np.asarray(state['lgElementOn']) != 0)
+            G.elementxref = rt.wrap(_F(state['elementXref'], np.int64))
+        # photoSource.out
+        n = m.nStars
+        strs = lambda v, w: rt.wrap(np.array([str(x).ljust(w) for x in v], dtype=object))
+        G.contshapein = strs(state['contShape'], 50)
+        G.spid = strs(state['spID'], 50)
+        G.tstellar = rt.wrap(_F(state['TStellar'], np.float32))
+        G.lstar = rt.wrap(_F(state['LStar'], np.float32))
+        G.nphotons = rt.wrap(_F(state['nPhotons'], np.int64))
+        G.tstep = rt.wrap(_F(state['tStep'], np.float32))
+        sp = np.empty(n, dtype=object)
+        for i in range(n):
+            sp[i] = ref.T_vector(*[np.float32(v) for v in m.starPosition[i]])
+        G.starposition = rt.wrap(sp)
+        G.pwlindex = np.float32(0.0)
+        # grid3.out
+        G.convwritegrid = np.float32(rp.convWriteGrid)
+        G.lgautopackets, G.convincpercent = bool(rp.lgAutoPackets), np.float32(rp.convIncPercent)
+        G.nphotincrease, G.maxphotons = np.float32(rp.nPhotIncrease), int(rp.maxPhotons)
+        G.lgsymmetricxyz, G.lgtalk, G.lg1d = bool(m.lgSymmetricXYZ), bool(rp.lgTalk), bool(rp.lg1D)
+        G.nustepsize, G.numax, G.numin = np.float32(rp.nuStepSize), np.float32(rp.nuMax), np.float32(rp.nuMin)
+        G.r_in, G.xhilimit = np.float32(rp.R_in), np.float32(rp.XHIlimit)
+        G.maxiteratemc, G.minconvergence = int(rp.maxIterateMC), np.float32(rp.minConvergence)
+        G.lgdebug, G.lgplaneionization = bool(m.lgDebug), bool(m.lgPlaneIonization)
+        G.nabcomponents = int(rp.nAbComponents)
+        G.abundancefile = strs(rp.abundanceFile, 50)
+        G.lgoutput, G.dxslit, G.dyslit = bool(rp.lgOutput), np.float32(rp.dxSlit), np.float32(rp.dySlit)
+        G.lgdustconstant = bool(rp.lgDustConstant)
+        G.lgmultidustchemistry, G.ndustcomponents = bool(m.lgMultiDustChemistry), int(rp.nDustComponents)
+        G.dustspeciesfile = strs(rp.dustSpeciesFile, 50)
+        G.dustfile = strs(['', rp.dustFile2], 50)
+        G.lgrecombination = bool(rp.lgRecombination)
+        G.nspeciespart = rt.wrap(_F(m.nSpeciesPart, np.int64))
+        G.reslinestransfer, G.lgdustscattering = np.float32(rp.resLinesTransfer), bool(rp.lgDustScattering)
+        G.nanglebins = int(m.nAngleBins)
+        if m.nAngleBins > 0:
+            G.viewpointtheta = rt.wrap(_F(m.viewPointTheta, np.float32), (0,))
+            G.viewpointphi = rt.wrap(_F(m.viewPointPhi, np.float32), (0,))
+        G.contcube = rt.wrap(_F(rp.contCube, np.float32))
+        G.lgphotoelectric, G.lgtraceheating = bool(rp.lgPhotoelectric), bool(rp.lgTraceHeating)
+        G.ldiffuse, G.tdiffuse = np.float32(rp.Ldiffuse), np.float32(rp.Tdiffuse)
+        G.shapediffuse = str(rp.shapeDiffuse).ljust(50)
+        G.nphotonsdiffuse, G.emittinggrid = int(rp.nPhotonsDiffuse), int(rp.emittingGrid)
+        G.lgmultistars, G.lgecho = bool(m.lgMultistars), bool(rp.lgEcho)
+        G.echot1, G.echot2, G.echotemp = np.float32(rp.echot1), np.float32(rp.echot2), np.float32(rp.echoTemp)
+        G.lgnosource = bool(rp.lgNosource)
+        grids = np.empty(m.nGrids, dtype=object)
+        for i, g in enumerate(m.grids):
+            t = ref.T_grid_type()
+            t.nx, t.ny, t.nz, t.ncells, t.motherp = g.nx, g.ny, g.nz, int(g.nCells), int(g.motherP)
+            t.xaxis, t.yaxis, t.zaxis = (rt.wrap(_F(a, np.float32)) for a in (g.xAxis, g.yAxis, g.zAxis))
+            t.active = rt.wrap(_F(g.active, np.int64))
+            t.lgconverged = rt.wrap(_F(state['lgConverged'][i], np.int64), (0,))
+            t.lgblack = rt.wrap(_F(state['lgBlack'][i], np.int64), (0,))
+            if m.lgGas:
+                t.te = rt.wrap(_F(state['Te'][i], np.float32), (0,))
+                t.ne = rt.wrap(_F(state['Ne'][i], np.float32), (0,))
+                t.hden = rt.wrap(_F(g.Hden, np.float32), (0,))
+                t.ionden = rt.wrap(_F(state['ionDen'][i], np.float32), (0, 1, 1))
+                t.abfileindex = rt.wrap(_F(state['abFileIndex'][i], np.int64))
+            if m.lgDust:
+                t.ndust = rt.wrap(_F(g.Ndust, np.float32), (0,))
+                t.tdust = rt.wrap(_F(g.Tdust, np.float32), (0, 0, 0))
+                if g.dustAbunIndex is not None:
+                    t.dustabunindex = rt.wrap(_F(g.dustAbunIndex, np.int64), (0,))
+            grids[i] = t
+        rt.io_log.clear()
+        with np.errstate(all='ignore'):
+            ref.p_writegrid(rt.wrap(grids))
+        return {u: list(v) for u, v in rt.io_log.items()}
 
     # ------------------------------------------------------------------------------------------
     def _dust_globals(self, model, tables, lgDebug=False):

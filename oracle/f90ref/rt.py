@@ -234,7 +234,13 @@ io_log = {}       # unit -> list of records (tuples of the values of a list-dire
 
 
 def fwrite(unit, items):
-    io_log.setdefault(int(unit), []).append(tuple(items))
+    flat = []
+    for it in items:             # a whole array is written element by element, in array element order
+        if type(it) is FArr:
+            flat.extend(int(v) if it.isint else v for v in it.a.ravel(order='F'))
+        else:
+            flat.append(it)
+    io_log.setdefault(int(unit), []).append(tuple(flat))
 
 
 def fio(what):

@@ -21,7 +21,9 @@ updateCell -> getDustT (Tdust, lgConverged), and the photo-ionisation rate / hea
 updateCell / thermBalance (nPhotoSte, nPhotoDif per element and ion, heatSte, heatDif per cell, and
 getOuterShell's shell numbers) on seeded inputs built by tests/ref_cases.py.  ref_aux_sed_<case>.npz:
 what writeSED writes to output/SED.out (nu, lambda, SED per viewing angle, total energy) for the
-escapedPackets of the transport case of the same name.
+escapedPackets of the transport case of the same name.  ref_aux_writegrid.json: the records
+writeGrid writes to grid0-3.out, dustGrid.out and photoSource.out (numbers rendered with
+checkpoint.py's format; list-directed formatting is the compiler's business).
 """
 import os
 import sys
@@ -38,7 +40,15 @@ import ref_cases  # noqa: E402
 
 def main(names):
     for name in names or list(ref_cases.REF_CASES) + list(ref_cases.AUX_CASES) + list(ref_cases.PHOTO_CASES) + \
-            ["sed:" + c for c in ref_cases.SED_CASES]:
+            ["sed:" + c for c in ref_cases.SED_CASES] + ["writegrid"]:
+        if name == "writegrid":
+            import json
+            res = ref_cases.run_reference_writegrid()
+            path = os.path.join(HERE, "ref_aux_writegrid.json")
+            with open(path, "w") as fh:
+                json.dump(res, fh, indent=0)
+            print(f"{name}: {os.path.getsize(path)} bytes, " + ", ".join(f"{k}: {len(v)} records" for k, v in res.items()))
+            continue
         if name.startswith("sed:"):          # after the transport cases: reads their golden files
             res = ref_cases.run_reference_sed(name[4:])
             path = os.path.join(HERE, f"ref_aux_sed_{name[4:]}.npz")

@@ -341,3 +341,77 @@ def run_reference_sed(name):
     sed, tot, rows = AuxReference(O.load(), math="libm").write_sed(m, wid, scaled)
     return dict(SED=sed, totalE=np.float32(tot), nu=np.array([r[0] for r in rows], np.float32),
                 lambda_um=np.array([r[1] for r in rows], np.float32))
+
+
+# ---------------------------------------------------------------------------------------------
+# writeGrid: the checkpoint files grid0-3.out, dustGrid.out, photoSource.out
+# ---------------------------------------------------------------------------------------------
+GRID_FILES = {21: "grid0.out", 20: "grid1.out", 30: "grid2.out", 40: "grid3.out", 50: "dustGrid.out", 42: "photoSource.out"}
+
+
+def writegrid_inputs():
+    from mocassin_b200 import checkpoint as ck
+
+    F32 = np.float32
+    m = W.multigrid(n=6, nsub=4, nbins=20)
+    m.nAngleBins = 2
+    m.viewPointTheta = np.array([0, 0.5, 1.9], F32)
+    m.viewPointPhi = np.array([0, 0.7, 3.4], F32)
+    rng = np.random.default_rng(2)
+    on = np.zeros(30, np.int32)
+    for e in (1, 2, 6, 8):
+        on[e - 1] = 1
+    xref = np.zeros(30, np.int32)
+    xref[on > 0] = np.arange(1, 5)
+    rp = ck.RunParams(abundanceFile=("abun/solar.dat",), dustSpeciesFile=("dust/sil.dat",), dustFile2="sizes.dat", nstages=5,
+                      maxPhotons=10 ** 7, lgAutoPackets=True, convIncPercent=40.0, nPhotIncrease=2.0)
+    state = dict(lgConverged=[rng.integers(0, 2, g.nCells + 1) for g in m.grids],
+                 lgBlack=[rng.integers(0, 2, g.nCells + 1) for g in m.grids],
+                 Te=[(rng.random(g.nCells + 1) * 1e4).astype(F32) for g in m.grids],
+                 Ne=[(rng.random(g.nCells + 1) * 1e3).astype(F32) for g in m.grids],
+                 ionDen=[np.asfortranarray(rng.random((g.nCells + 1, 4, 5)).astype(F32)) for g in m.grids],
+                 abFileIndex=[np.asfortranarray(rng.integers(1, 3, g.active.shape)) for g in m.grids],
+                 lgElementOn=on, elementXref=xref, contShape=["blackbody"], TStellar=[80000.0], LStar=[1.0],
+                 nPhotons=[1000000], spID=["mocassin"], tStep=[0.0], lgMultiChemistry=True, totalDustMass=1.5)
+    for g in m.grids:
+        g.Hden = (rng.random(g.nCells + 1) * 100).astype(F32)
+        g.Ndust = (rng.random(g.nCells + 1) * 1e-9).astype(F32)
+        g.dustAbunIndex = np.ones(g.nCells + 1, np.int32)
+    return m, rp, state
+
+
+def _norm(s):
+    return " ".join(s.split())
+
+
+def run_reference_writegrid():
+    """{file name: [normalised record lines]} from the reference's own writeGrid; values are
+    rendered with checkpoint.py's number format (list-directed formatting is the compiler's)"""
+    from mocassin_b200 import checkpoint as ck
+    from oracle import oracle as O
+    from oracle.f90ref.harness_aux import AuxReference
+
+    m, rp, state = writegrid_inputs()
+    recs = AuxReference(O.load()).write_grid(m, rp, state)
+    out = {}
+    for unit, fn in GRID_FILES.items():
+        lines = []
+        for r in recs[unit]:
+            items = [(v.rstrip() if isinstance(v, str) and v.strip() else v) for v in r]
+            lines.append(_norm(ck._join(items)))
+        out[fn] = lines
+    return out
+
+
+def run_writers(outdir):
+    from mocassin_b200 import checkpoint as ck
+
+    m, rp, s = writegrid_inputs()
+    p = lambda f: f"{outdir}/{f}"
+    ck.write_grid0(p("grid0.out"), m, lgConverged=s["lgConverged"], lgBlack=s["lgBlack"])
+    ck.write_grid1(p("grid1.out"), m, s["Te"], s["Ne"], abFileIndex=s["abFileIndex"])
+    ck.write_grid2(p("grid2.out"), m, s["ionDen"], s["lgElementOn"], s["elementXref"], rp.nstages)
+    ck.write_grid3(p("grid3.out"), m, rp)
+    ck.write_dust_grid(p("dustGrid.out"), m, lgMultiChemistry=True, totalDustMass=s["totalDustMass"])
+    ck.write_photo_source(p("photoSource.out"), m, s["contShape"], s["TStellar"], s["LStar"], s["nPhotons"], s["spID"], s["tStep"])
+    return {fn: [_norm(l) for l in open(p(fn)).read().splitlines()] for fn in GRID_FILES.values()}

@@ -76,3 +76,29 @@ def test_checkpoint_feeds_a_second_engine_state(tmp_path):
     assert np.array_equal(grids[0].active, b.grids[0].active)
     ck.read_dust_grid(os.path.join(tmp_path, "dustGrid.out"), b, lgMultiChemistry=True)
     assert np.array_equal(b.grids[0].Tdust[:, :, 1:], a.grids[0].Tdust[:, :, 1:])
+
+
+def test_grid1_grid2_grid3_round_trip(tmp_path):
+    """grid1.out (Te, Ne, Hden, abFileIndex), grid2.out (ionDen) and grid3.out (run parameters):
+    what write_* writes, read_* reads back (the order resetGrid reads in, grid_mod.f90:3038-3111,
+    :3423-3465)."""
+    import ref_cases
+
+    m, rp, s = ref_cases.writegrid_inputs()
+    ref_cases.run_writers(str(tmp_path))
+    Te, Ne, Hden, ab = ck.read_grid1(os.path.join(tmp_path, "grid1.out"), m.grids, multi_chemistry=True)
+    for iG, g in enumerate(m.grids):
+        assert np.array_equal(Te[iG][1:], s["Te"][iG][1:]) and np.array_equal(Ne[iG][1:], s["Ne"][iG][1:])
+        assert np.array_equal(Hden[iG][1:], g.Hden[1:]) and np.array_equal(ab[iG], s["abFileIndex"][iG])
+    ion = ck.read_grid2(os.path.join(tmp_path, "grid2.out"), m.grids, s["lgElementOn"], s["elementXref"], rp.nstages)
+    for iG in range(m.nGrids):
+        want = s["ionDen"][iG].copy()
+        for e in (1, 2, 6, 8):                       # stages beyond min(elem+1, nstages) are not stored
+            want[:, int(s["elementXref"][e - 1]) - 1, min(e + 1, rp.nstages):] = 0
+        assert np.array_equal(ion[iG][1:], want[1:])
+    d = ck.read_grid3(os.path.join(tmp_path, "grid3.out"))
+    assert d["nGrids"] == 2 and d["nbins"] == m.nbins and d["lgSymmetricXYZ"] == m.lgSymmetricXYZ
+    assert d["abundanceFile"] == ["abun/solar.dat"] and d["dustSpeciesFile"] == ["dust/sil.dat"] and d["dustFile2"] == "sizes.dat"
+    assert d["lgAutoPackets"] and d["maxPhotons"] == 10 ** 7 and d["nstages"] == 5 and d["lgDust"] and d["lgGas"]
+    assert d["nAngleBins"] == 2 and np.allclose(d["viewPointTheta"], [0, 0.5, 1.9]) and d["nSpeciesPart"] == [1]
+    assert (d["nSpeciesMax"], d["nSizes"]) == (m.nSpeciesMax, m.nSizes) and d["lgNosource"] is False

@@ -192,6 +192,26 @@ def test_translated_writesed_reproduces_golden(oracle_lib):
         assert np.array_equal(_bits(np.asarray(got[k])), _bits(w)), k
 
 
+def test_checkpoint_writers_match_reference_writegrid(tmp_path):
+    """mocassin_b200/checkpoint.py against the records the reference's own writeGrid writes
+    (grid_mod.f90:2646-2870): same records, same order, same values, in all six files."""
+    import json
+
+    want = json.load(open(os.path.join(GOLD, "ref_aux_writegrid.json")))
+    got = ref_cases.run_writers(str(tmp_path))
+    for fn, lines in want.items():
+        assert got[fn] == lines, fn
+    assert len(want["grid3.out"]) == 45 and len(want["grid2.out"]) > 1000
+
+
+@pytest.mark.skipif(not HAVE_REF, reason="reference sources not present")
+def test_translated_writegrid_reproduces_golden(oracle_lib):
+    import json
+
+    want = json.load(open(os.path.join(GOLD, "ref_aux_writegrid.json")))
+    assert ref_cases.run_reference_writegrid() == want
+
+
 # ---------------------------------------------------------------------------------------------
 # the translator itself
 # ---------------------------------------------------------------------------------------------
