@@ -378,26 +378,50 @@ def run_b200(args):
         torch.cuda.synchronize()
         te = time.perf_counter()
         eng.set_option("async_pdfs", 1)                       # PDF upload overlaps the stellar wave
-        for _ in range(nE):
+
+        def e2e_step(sparse):
             eng.assemble_opacity(1, bands, den, None, dust)   # H2D: den, Ndust, Tdust + K1
             eng.set_dust_state()
             eng.set_pdfs()                                    # H2D (async, 5 GB): recPDF, totalLines
             eng.zero_estimators()
             step()
-            eng.fetch(1, out={"Jste": Jh, "escapedPackets": Eh})   # D2H
+            if not sparse:
+                eng.fetch(1, out={"Jste": Jh, "escapedPackets": Eh})   # D2H, both arrays dense
+                return Eh.nbytes
+            eng.fetch(1, want=("Jste",), out={"Jste": Jh})    # D2H: Jste dense
+            # escapedPackets: only its non-zero entries cross PCIe; the entries of the previous
+            # step are zeroed first (clear_previous), so Eh ends up exactly as the dense fetch leaves it
+            _, nnz = eng.fetch_escaped_sparse(1, out=Eh, clear_previous=True)
+            return 8 * nnz + 8 if nnz >= 0 else Eh.nbytes
+
+        Eh[...] = 0.0
+        e2e_step(True)                                        # untimed: sizes the staging buffers
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        te = time.perf_counter()
+        for _ in range(nE):
+            esc_bytes = e2e_step(True)
         torch.cuda.synchronize()
         if world > 1:
             dist.barrier()
         dte = time.perf_counter() - te
+        td = time.perf_counter()
+        e2e_step(False)                                       # the dense fetch of both arrays, for comparison
+        torch.cuda.synchronize()
+        dte_dense = time.perf_counter() - td
         if world > 1:
             tmax = torch.tensor([dte], dtype=torch.float64, device="cuda"); dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
             dte = float(tmax[0])
         h2d = recPDF.nbytes + tl.nbytes + den.nbytes + dust["Ndust"].nbytes + dust["Tdust"].nbytes + 4 * (g.nCells + 1)
-        d2h = Jh.nbytes + Eh.nbytes
+        d2h = Jh.nbytes + esc_bytes
         e2e = {"value": nGlobal * nE / dte, "unit": "packets/s", "h2d_bytes_per_step": int(h2d),
                "d2h_bytes_per_step": int(d2h), "steps": nE,
                "path": "assemble_opacity + set_dust_state + set_pdfs (async H2D from pinned host, overlaps wave 0) -> "
-                       "zero_estimators -> energyPacketDriver -> fetch Jste+escapedPackets (D2H to pinned host)"}
+                       "zero_estimators -> energyPacketDriver -> fetch Jste (dense D2H to pinned host) + "
+                       "fetch_escaped_sparse (non-zero escapedPackets entries only, written into the host array)",
+               "dense_fetch": {"value": nGlobal / dte_dense, "d2h_bytes_per_step": int(Jh.nbytes + Eh.nbytes),
+                               "note": "same step with mcb200_fetch_estimators for both arrays (one step)"}}
 
     if rank != 0:
         if world > 1:

@@ -313,6 +313,19 @@ int mcb200_photo_integrals(mcb200_ctx *ctx, int32_t iG, int32_t nBands, const in
 int mcb200_fetch_estimators(mcb200_ctx *ctx, int32_t iG, float *Jste, float *escapedPackets,
                             float *Jdif, float *linePackets);
 
+/* escapedPackets of grid iG, sparsely.  escapedPackets(cell, nu, angle) is indexed by the cell a
+ * packet was last emitted or scattered in, so in a large grid almost all of it is zero (0.5 % of
+ * the 1.26e9 entries at 128^3 x 600): the library compacts the non-zero entries on the device,
+ * moves only those over PCIe (48 MB instead of 5 GB) and writes them into the caller's array.
+ * Contract: the array is zero where this call does not write -- iterateMC zeroes
+ * grid%escapedPackets before the packet loop (iteration_mod.f90:466-470), so a Fortran host gets
+ * exactly what mcb200_fetch_estimators would give.  clearPrevious != 0: entries written by the
+ * previous call into the same array are zeroed first (for a caller that reuses the array without
+ * zeroing it).  Falls back to the dense copy when more than 1/64 of the entries are non-zero.
+ * nNonZero (optional): entries written, -1 after a dense fallback. */
+int mcb200_fetch_escaped_sparse(mcb200_ctx *ctx, int32_t iG, float *escapedPackets, int32_t clearPrevious,
+                                int64_t *nNonZero);
+
 /* Diagnostics: raw integer tallies (same shapes as above, int64) and the
  * path-length unit [cm] of grid iG's fixed-point J tally. */
 int mcb200_fetch_tallies(mcb200_ctx *ctx, int32_t iG, int64_t *JsteQ, int64_t *escapedQ,

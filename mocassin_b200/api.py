@@ -532,6 +532,20 @@ class PacketEngine:
                 out[k] = v
         return out
 
+    def fetch_escaped_sparse(self, iG: int = 1, out: Optional[np.ndarray] = None, clear_previous: bool = True):
+        """escapedPackets of grid iG through the sparse path (mcb200_fetch_escaped_sparse): only
+        the non-zero entries cross PCIe and are written into `out`, which must be zero elsewhere
+        (as iterateMC leaves it, iteration_mod.f90:466-470); with `clear_previous` the entries the
+        previous call wrote into the same array are zeroed first.  Returns (array, entries written;
+        -1 = dense fallback)."""
+        m = self.model
+        g = m.grids[iG - 1]
+        if out is None:
+            out = np.zeros((g.nCells + 1, m.nbins + 1, m.nAngleBins + 1), dtype=F32, order="F")
+        n = C.c_int64()
+        self._check(self.lib.mcb200_fetch_escaped_sparse(self.h, iG, _fp(out), int(bool(clear_previous)), C.byref(n)))
+        return out, int(n.value)
+
     def fetch_tallies(self, iG: int = 1) -> dict:
         m = self.model
         g = m.grids[iG - 1]

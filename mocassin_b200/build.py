@@ -21,7 +21,7 @@ NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",
     "-lineinfo", "-O3", "-std=c++17",
     "-fmad=false",
-    "-Xcompiler", "-fPIC,-ffp-contract=off",
+    "-Xcompiler", "-fPIC,-ffp-contract=off,-pthread",
     "-shared",
 ]
 

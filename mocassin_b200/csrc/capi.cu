@@ -10,6 +10,7 @@
 #include <cuda_runtime.h>
 
 #include <chrono>
+#include <thread>
 #include <cmath>
 #include <cstdarg>
 #include <cstdio>
@@ -117,6 +118,10 @@ struct GridState {
     DevBuf<unsigned int> escQ2;
     DevBuf<int> nuTouched2;
     DevBuf<float> Jste, Jdif, esc, linePk;
+    // mcb200_fetch_escaped_sparse: the entries written by the previous call and where
+    std::vector<unsigned int> sparsePrev;
+    const float *sparsePrevPtr = nullptr;
+    bool sparsePrevDense = false;         // the previous call fell back to the dense copy
     std::vector<char> folded;             // nu-planes of the pending call already folded by mcb200_reduce_range
     // dust closure (mcb200_dust_update / mcb200_dust_pdf): device copy of the dust state
     DevBuf<float> Tdust;
@@ -157,6 +162,9 @@ struct mcb200_ctx {
     DevBuf<float> widFlx, grainWeight, emT, dGrainAbun, dSublime;
     DevBuf<int> absP, dSpeciesPart, dComPoint;
     DevBuf<unsigned long long> nConv;
+    DevBuf<unsigned long long> sparseList, sparseCount;   // mcb200_fetch_escaped_sparse
+    unsigned long long *sparseHost = nullptr;             // pinned staging of the (index, value) list
+    size_t sparseHostCap = 0;
     // temporaries of mcb200_assemble_opacity
     DevBuf<float> opDen, opFf, opNd, opCoef;
     DevBuf<int> opStart, opSpec, opXs, opComp, opTermOn, opScaP, opAbsP;
@@ -893,6 +901,7 @@ int mcb200_destroy(mcb200_ctx *ctx)
     if (ctx->ev2) cudaEventDestroy(ctx->ev2);
     if (ctx->pdfReady) cudaEventDestroy(ctx->pdfReady);
     if (ctx->copyStream) { cudaStreamSynchronize(ctx->copyStream); cudaStreamDestroy(ctx->copyStream); }
+    if (ctx->sparseHost) cudaFreeHost(ctx->sparseHost);
     ctx->grids.clear();
     cudaStream_t s = ctx->stream;
     delete ctx;
@@ -1552,6 +1561,153 @@ int mcb200_fetch_estimators(mcb200_ctx *ctx, int32_t iG, float *Jste, float *esc
         if (!g->linePk.p) return fail(ctx, MCB200_ESTATE, "linePackets only exists in debug mode");
         CU(cudaMemcpy(linePackets, g->linePk.p, g->linePk.n * sizeof(float), cudaMemcpyDeviceToHost));
     }
+    return MCB200_OK;
+}
+
+// Non-zero entries of a float array as (index << 32 | value bits), tile by tile: a block takes a
+// tile of 4096 consecutive elements (16 per thread, so the tile's entries come out in index
+// order), counts its non-zeros with a block scan and reserves its slice of the list with one
+// atomic.  Tiles land in the list in any order, entries inside a tile ascend: the host writes
+// that follow touch one 16 KB window at a time.  HBM-bound: the array is read once.
+constexpr int kSparsePerThread = 16;
+__global__ void __launch_bounds__(256) sparse_f32_kernel(const float *__restrict__ E, unsigned long long len,
+                                                         unsigned long long *__restrict__ list,
+                                                         unsigned long long *__restrict__ count, unsigned long long capacity)
+{
+    __shared__ unsigned int warpTot[8];
+    __shared__ unsigned long long tileBase;
+    const unsigned int lane = threadIdx.x & 31u, w = threadIdx.x >> 5;
+    const unsigned long long tile = 256ull * kSparsePerThread;
+    for (unsigned long long t0 = (unsigned long long)blockIdx.x * tile; t0 < len; t0 += (unsigned long long)gridDim.x * tile) {
+        const unsigned long long i0 = t0 + (unsigned long long)threadIdx.x * kSparsePerThread;
+        unsigned int bits[kSparsePerThread];
+        unsigned int nz = 0;
+        if (i0 + kSparsePerThread <= len) {
+            const uint4 *p = reinterpret_cast<const uint4 *>(E + i0);      // i0 is a multiple of 16: aligned
+#pragma unroll
+            for (int k = 0; k < kSparsePerThread / 4; ++k) {
+                uint4 v = p[k];
+                bits[4 * k] = v.x; bits[4 * k + 1] = v.y; bits[4 * k + 2] = v.z; bits[4 * k + 3] = v.w;
+            }
+        } else {
+#pragma unroll
+            for (int k = 0; k < kSparsePerThread; ++k) bits[k] = i0 + k < len ? __float_as_uint(E[i0 + k]) : 0u;
+        }
+#pragma unroll
+        for (int k = 0; k < kSparsePerThread; ++k) nz += bits[k] != 0u;
+        // exclusive scan of nz over the block
+        unsigned int incl = nz;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            unsigned int t = __shfl_up_sync(0xffffffffu, incl, d);
+            if (lane >= (unsigned int)d) incl += t;
+        }
+        if (lane == 31) warpTot[w] = incl;
+        __syncthreads();
+        unsigned int before = 0, total = 0;
+#pragma unroll
+        for (int k = 0; k < 8; ++k) { unsigned int t = warpTot[k]; if ((unsigned int)k < w) before += t; total += t; }
+        if (threadIdx.x == 0) tileBase = total ? atomicAdd(count, (unsigned long long)total) : 0ull;
+        __syncthreads();
+        if (nz) {
+            unsigned long long pos = tileBase + before + (incl - nz);
+#pragma unroll
+            for (int k = 0; k < kSparsePerThread; ++k) {
+                if (bits[k] != 0u) {
+                    if (pos < capacity) list[pos] = ((i0 + k) << 32) | (unsigned long long)bits[k];
+                    ++pos;
+                }
+            }
+        }
+        __syncthreads();                       // warpTot / tileBase are reused by the next tile
+    }
+}
+
+int mcb200_fetch_escaped_sparse(mcb200_ctx *ctx, int32_t iG, float *escapedPackets, int32_t clearPrevious,
+                                int64_t *nNonZero)
+{
+    NEED_CTX();
+    GridState *g = grid_of(ctx, iG);
+    if (!g || !g->set) return fail(ctx, MCB200_ESTATE, "grid %d not set", iG);
+    if (!escapedPackets) return fail(ctx, MCB200_EINVAL, "escapedPackets is NULL");
+    if (ctx->pending) return fail(ctx, MCB200_ESTATE, "tallies pending: call mcb200_reduce first");
+    int rc = ensure_estimators(ctx, *g);
+    if (rc) return rc;
+    const size_t len = g->esc.n;
+    // The host side is a scatter of ~10^6-10^7 single floats into a multi-GB array: every store
+    // misses the cache, so it is spread over a few host threads (disjoint entries, no sharing).
+    auto parallel_for = [](size_t n, auto &&body) {
+        unsigned int hw = std::thread::hardware_concurrency();
+        size_t nt = n < (1u << 16) ? 1 : (hw >= 16 ? 8 : hw >= 4 ? hw / 2 : 1);
+        if (nt <= 1) { body((size_t)0, n); return; }
+        std::vector<std::thread> th;
+        size_t chunk = (n + nt - 1) / nt;
+        for (size_t t = 0; t < nt; ++t) {
+            size_t a = t * chunk, b = a + chunk < n ? a + chunk : n;
+            if (a < b) th.emplace_back([&body, a, b] { body(a, b); });
+        }
+        for (auto &x : th) x.join();
+    };
+    if (clearPrevious && g->sparsePrevPtr == escapedPackets) {
+        if (g->sparsePrevDense) {
+            parallel_for(len, [&](size_t a, size_t b) { memset(escapedPackets + a, 0, (b - a) * sizeof(float)); });
+        } else {
+            const unsigned int *prev = g->sparsePrev.data();
+            parallel_for(g->sparsePrev.size(), [&](size_t a, size_t b) { for (size_t k = a; k < b; ++k) escapedPackets[prev[k]] = 0.f; });
+        }
+    }
+    g->sparsePrev.clear();
+    g->sparsePrevPtr = escapedPackets;
+    g->sparsePrevDense = false;
+    const size_t cap = len / 64 + 4096;         // 1.6 % of the entries; beyond that the dense copy is as good
+    unsigned long long n = ~0ull;
+    if (len < (1ull << 32)) {
+        CU(ctx->sparseList.alloc(cap));
+        CU(ctx->sparseCount.alloc(1));
+        CU(ctx->sparseCount.zero(ctx->stream));
+        int dev = 0, sms = 0;
+        CU(cudaGetDevice(&dev));
+        CU(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+        sparse_f32_kernel<<<sms * 8, 256, 0, ctx->stream>>>(g->esc.p, (unsigned long long)len, ctx->sparseList.p,
+                                                            ctx->sparseCount.p, (unsigned long long)cap);
+        CU(cudaGetLastError());
+        CU(cudaMemcpyAsync(&n, ctx->sparseCount.p, 8, cudaMemcpyDeviceToHost, ctx->stream));
+        CU(cudaStreamSynchronize(ctx->stream));
+    }
+    if (n > cap) {
+        // too dense (or an index would not fit 32 bits): the plain copy; every entry is written
+        CU(cudaStreamSynchronize(ctx->stream));
+        CU(cudaMemcpy(escapedPackets, g->esc.p, len * sizeof(float), cudaMemcpyDeviceToHost));
+        g->sparsePrevDense = true;
+        if (nNonZero) *nNonZero = -1;
+        return MCB200_OK;
+    }
+    if (n > ctx->sparseHostCap) {
+        if (ctx->sparseHost) cudaFreeHost(ctx->sparseHost);
+        ctx->sparseHost = nullptr;
+        ctx->sparseHostCap = 0;
+        size_t want = (size_t)n + (size_t)n / 4 + 4096;
+        if (want > cap) want = cap;
+        CU(cudaHostAlloc((void **)&ctx->sparseHost, want * 8, cudaHostAllocDefault));
+        ctx->sparseHostCap = want;
+    }
+    if (n) CU(cudaMemcpy(ctx->sparseHost, ctx->sparseList.p, (size_t)n * 8, cudaMemcpyDeviceToHost));
+    g->sparsePrev.resize((size_t)n);
+    {
+        const unsigned long long *src = ctx->sparseHost;
+        unsigned int *prev = g->sparsePrev.data();
+        parallel_for((size_t)n, [&](size_t a, size_t b) {
+            for (size_t k = a; k < b; ++k) {
+                unsigned long long e = src[k];
+                unsigned int idx = (unsigned int)(e >> 32), bits = (unsigned int)e;
+                float v;
+                memcpy(&v, &bits, 4);
+                escapedPackets[idx] = v;
+                prev[k] = idx;
+            }
+        });
+    }
+    if (nNonZero) *nNonZero = (int64_t)n;
     return MCB200_OK;
 }
 

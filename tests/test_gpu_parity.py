@@ -344,3 +344,32 @@ def test_resonance_line_packet_transfer(wavefront):
     for iG in (0, 1):
         assert np.array_equal((parts[0][iG]["JsteQ"] + parts[1][iG]["JsteQ"])[1:], o.out[iG]["JsteQ"][1:])
         assert np.array_equal(parts[0][iG]["escapedQ"] + parts[1][iG]["escapedQ"], o.out[iG]["escapedQ"])
+
+
+@pytest.mark.parametrize("name", ["viewing_angles", "multigrid_sym", "hii_sym_gas", "dust_shell_hg"])
+def test_sparse_escaped_fetch_equals_dense_fetch(name):
+    """mcb200_fetch_escaped_sparse writes exactly the non-zero entries of escapedPackets: the
+    array it fills equals the dense fetch, also when the same array is reused for a second,
+    different call (clear_previous), and without clear_previous into a zeroed array."""
+    m, n = make(name)
+    e = _engine(m)
+    e.zero_estimators()
+    e.energyPacketDriver(1, n)
+    bufs = {}
+    for iG in range(1, m.nGrids + 1):
+        dense = e.fetch(iG)["escapedPackets"]
+        sparse, k = e.fetch_escaped_sparse(iG)
+        bufs[iG] = sparse
+        assert k == int(np.count_nonzero(dense)) or k == -1
+        assert np.array_equal(sparse.view(np.uint32), dense.view(np.uint32)), iG
+    assert any(np.count_nonzero(b) for b in bufs.values())
+    # a second, different call into the same arrays
+    e.zero_estimators()
+    e.energyPacketDriver(1, max(n // 7, 50), deltaE=float(m.deltaE[1]) * 3.0)
+    for iG in range(1, m.nGrids + 1):
+        dense = e.fetch(iG)["escapedPackets"]
+        again, k = e.fetch_escaped_sparse(iG, out=bufs[iG], clear_previous=True)
+        assert again is bufs[iG] and np.array_equal(again.view(np.uint32), dense.view(np.uint32)), iG
+        fresh, _ = e.fetch_escaped_sparse(iG, clear_previous=False)
+        assert np.array_equal(fresh.view(np.uint32), dense.view(np.uint32))
+    e.close()
