@@ -388,10 +388,10 @@ def run_b200(args):
             if not sparse:
                 eng.fetch(1, out={"Jste": Jh, "escapedPackets": Eh})   # D2H, both arrays dense
                 return Eh.nbytes
-            eng.fetch(1, want=("Jste",), out={"Jste": Jh})    # D2H: Jste dense
-            # escapedPackets: only its non-zero entries cross PCIe; the entries of the previous
-            # step are zeroed first (clear_previous), so Eh ends up exactly as the dense fetch leaves it
-            _, nnz = eng.fetch_escaped_sparse(1, out=Eh, clear_previous=True)
+            # D2H: Jste dense; escapedPackets: only its non-zero entries cross PCIe and are written
+            # into Eh by host threads while Jste is still copying; the entries of the previous step
+            # are zeroed first (clear_previous), so Eh ends up exactly as the dense fetch leaves it
+            _, nnz = eng.fetch_sparse(1, out={"Jste": Jh, "escapedPackets": Eh}, clear_previous=True)
             return 8 * nnz + 8 if nnz >= 0 else Eh.nbytes
 
         Eh[...] = 0.0
@@ -418,8 +418,8 @@ def run_b200(args):
         e2e = {"value": nGlobal * nE / dte, "unit": "packets/s", "h2d_bytes_per_step": int(h2d),
                "d2h_bytes_per_step": int(d2h), "steps": nE,
                "path": "assemble_opacity + set_dust_state + set_pdfs (async H2D from pinned host, overlaps wave 0) -> "
-                       "zero_estimators -> energyPacketDriver -> fetch Jste (dense D2H to pinned host) + "
-                       "fetch_escaped_sparse (non-zero escapedPackets entries only, written into the host array)",
+                       "zero_estimators -> energyPacketDriver -> mcb200_fetch_estimators_sparse: Jste dense D2H to "
+                       "pinned host, overlapped with the non-zero escapedPackets entries being written into the host array",
                "dense_fetch": {"value": nGlobal / dte_dense, "d2h_bytes_per_step": int(Jh.nbytes + Eh.nbytes),
                                "note": "same step with mcb200_fetch_estimators for both arrays (one step)"}}
 

@@ -109,6 +109,18 @@ module mcb200_mod
             & bind(C, name="mcb200_fetch_estimators")
          import; type(c_ptr), value :: ctx, Jste, escapedPackets, Jdif, linePackets; integer(c_int32_t), value :: iG
        end function
+       ! escapedPackets sparsely (only its non-zero entries cross PCIe; the array must be zero elsewhere,
+       ! as iterateMC leaves it at iteration_mod.f90:466-470), alone or together with the dense Jste
+       integer(c_int) function mcb200_fetch_escaped_sparse(ctx, iG, escapedPackets, clearPrevious, nNonZero) &
+            & bind(C, name="mcb200_fetch_escaped_sparse")
+         import; type(c_ptr), value :: ctx, escapedPackets; integer(c_int32_t), value :: iG, clearPrevious
+         integer(c_int64_t), intent(out) :: nNonZero
+       end function
+       integer(c_int) function mcb200_fetch_estimators_sparse(ctx, iG, Jste, escapedPackets, clearPrevious, nNonZero) &
+            & bind(C, name="mcb200_fetch_estimators_sparse")
+         import; type(c_ptr), value :: ctx, Jste, escapedPackets; integer(c_int32_t), value :: iG, clearPrevious
+         integer(c_int64_t), intent(out) :: nNonZero
+       end function
        integer(c_int) function mcb200_set_xsec(ctx, xSecArray, nXsec) bind(C, name="mcb200_set_xsec")
          import; type(c_ptr), value :: ctx, xSecArray; integer(c_int64_t), value :: nXsec
        end function

@@ -325,6 +325,11 @@ int mcb200_fetch_estimators(mcb200_ctx *ctx, int32_t iG, float *Jste, float *esc
  * nNonZero (optional): entries written, -1 after a dense fallback. */
 int mcb200_fetch_escaped_sparse(mcb200_ctx *ctx, int32_t iG, float *escapedPackets, int32_t clearPrevious,
                                 int64_t *nNonZero);
+/* Jste (dense, as mcb200_fetch_estimators) and escapedPackets (sparse, as above) in one call: the
+ * Jste copy crosses PCIe while the host threads write the escapedPackets entries.  Jste should be
+ * page-locked (cudaHostRegister / pinned) for the two to overlap; pageable memory works, serially. */
+int mcb200_fetch_estimators_sparse(mcb200_ctx *ctx, int32_t iG, float *Jste, float *escapedPackets,
+                                   int32_t clearPrevious, int64_t *nNonZero);
 
 /* Diagnostics: raw integer tallies (same shapes as above, int64) and the
  * path-length unit [cm] of grid iG's fixed-point J tally. */

@@ -66,6 +66,7 @@ _SIGS = {
     "mcb200_reduce": [C.c_void_p],
     "mcb200_fetch_estimators": [C.c_void_p, C.c_int32, c_float_p, c_float_p, c_float_p, c_float_p],
     "mcb200_fetch_escaped_sparse": [C.c_void_p, C.c_int32, c_float_p, C.c_int32, c_int64_p],
+    "mcb200_fetch_estimators_sparse": [C.c_void_p, C.c_int32, c_float_p, c_float_p, C.c_int32, c_int64_p],
     "mcb200_fetch_tallies": [C.c_void_p, C.c_int32, c_int64_p, c_int64_p, c_int64_p, c_int64_p],
     "mcb200_len_unit": [C.c_void_p, C.c_int32, C.POINTER(C.c_double)],
     "mcb200_fetch_plane_distribution": [C.c_void_p, c_int32_p],

@@ -532,6 +532,23 @@ class PacketEngine:
                 out[k] = v
         return out
 
+    def fetch_sparse(self, iG: int = 1, out: Optional[dict] = None, clear_previous: bool = True):
+        """Jste (dense) and escapedPackets (sparse, see fetch_escaped_sparse) in one call
+        (mcb200_fetch_estimators_sparse): the Jste copy overlaps the host-side scatter.  `out` may
+        hold preallocated "Jste" / "escapedPackets" arrays.  Returns (dict, entries written)."""
+        m = self.model
+        g = m.grids[iG - 1]
+        pre = out or {}
+        J = pre.get("Jste")
+        E = pre.get("escapedPackets")
+        if J is None:
+            J = np.zeros((g.nCells + 1, m.nbins), dtype=F32, order="F")
+        if E is None:
+            E = np.zeros((g.nCells + 1, m.nbins + 1, m.nAngleBins + 1), dtype=F32, order="F")
+        n = C.c_int64()
+        self._check(self.lib.mcb200_fetch_estimators_sparse(self.h, iG, _fp(J), _fp(E), int(bool(clear_previous)), C.byref(n)))
+        return {"Jste": J, "escapedPackets": E}, int(n.value)
+
     def fetch_escaped_sparse(self, iG: int = 1, out: Optional[np.ndarray] = None, clear_previous: bool = True):
         """escapedPackets of grid iG through the sparse path (mcb200_fetch_escaped_sparse): only
         the non-zero entries cross PCIe and are written into `out`, which must be zero elsewhere

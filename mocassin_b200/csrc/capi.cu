@@ -1623,8 +1623,11 @@ __global__ void __launch_bounds__(256) sparse_f32_kernel(const float *__restrict
     }
 }
 
-int mcb200_fetch_escaped_sparse(mcb200_ctx *ctx, int32_t iG, float *escapedPackets, int32_t clearPrevious,
-                                int64_t *nNonZero)
+namespace {
+// Jste (optional): its dense copy is started once the device part of the sparse path is done, so
+// that it crosses PCIe while the host threads scatter the escapedPackets entries
+int fetch_sparse_impl(mcb200_ctx *ctx, int32_t iG, float *Jste, float *escapedPackets, int32_t clearPrevious,
+                      int64_t *nNonZero)
 {
     NEED_CTX();
     GridState *g = grid_of(ctx, iG);
@@ -1648,17 +1651,6 @@ int mcb200_fetch_escaped_sparse(mcb200_ctx *ctx, int32_t iG, float *escapedPacke
         }
         for (auto &x : th) x.join();
     };
-    if (clearPrevious && g->sparsePrevPtr == escapedPackets) {
-        if (g->sparsePrevDense) {
-            parallel_for(len, [&](size_t a, size_t b) { memset(escapedPackets + a, 0, (b - a) * sizeof(float)); });
-        } else {
-            const unsigned int *prev = g->sparsePrev.data();
-            parallel_for(g->sparsePrev.size(), [&](size_t a, size_t b) { for (size_t k = a; k < b; ++k) escapedPackets[prev[k]] = 0.f; });
-        }
-    }
-    g->sparsePrev.clear();
-    g->sparsePrevPtr = escapedPackets;
-    g->sparsePrevDense = false;
     const size_t cap = len / 64 + 4096;         // 1.6 % of the entries; beyond that the dense copy is as good
     unsigned long long n = ~0ull;
     if (len < (1ull << 32)) {
@@ -1674,10 +1666,15 @@ int mcb200_fetch_escaped_sparse(mcb200_ctx *ctx, int32_t iG, float *escapedPacke
         CU(cudaMemcpyAsync(&n, ctx->sparseCount.p, 8, cudaMemcpyDeviceToHost, ctx->stream));
         CU(cudaStreamSynchronize(ctx->stream));
     }
+    const bool withJ = Jste != nullptr && ctx->copyStream != nullptr;
+    if (Jste && !withJ) CU(cudaMemcpy(Jste, g->Jste.p, g->Jste.n * sizeof(float), cudaMemcpyDeviceToHost));
     if (n > cap) {
         // too dense (or an index would not fit 32 bits): the plain copy; every entry is written
         CU(cudaStreamSynchronize(ctx->stream));
+        if (withJ) CU(cudaMemcpy(Jste, g->Jste.p, g->Jste.n * sizeof(float), cudaMemcpyDeviceToHost));
         CU(cudaMemcpy(escapedPackets, g->esc.p, len * sizeof(float), cudaMemcpyDeviceToHost));
+        g->sparsePrev.clear();
+        g->sparsePrevPtr = escapedPackets;
         g->sparsePrevDense = true;
         if (nNonZero) *nNonZero = -1;
         return MCB200_OK;
@@ -1692,6 +1689,19 @@ int mcb200_fetch_escaped_sparse(mcb200_ctx *ctx, int32_t iG, float *escapedPacke
         ctx->sparseHostCap = want;
     }
     if (n) CU(cudaMemcpy(ctx->sparseHost, ctx->sparseList.p, (size_t)n * 8, cudaMemcpyDeviceToHost));
+    if (withJ) CU(cudaMemcpyAsync(Jste, g->Jste.p, g->Jste.n * sizeof(float), cudaMemcpyDeviceToHost, ctx->copyStream));
+    // from here on the host works while Jste crosses PCIe
+    if (clearPrevious && g->sparsePrevPtr == escapedPackets) {
+        if (g->sparsePrevDense) {
+            parallel_for(len, [&](size_t a, size_t b) { memset(escapedPackets + a, 0, (b - a) * sizeof(float)); });
+        } else {
+            const unsigned int *prev = g->sparsePrev.data();
+            parallel_for(g->sparsePrev.size(), [&](size_t a, size_t b) { for (size_t k = a; k < b; ++k) escapedPackets[prev[k]] = 0.f; });
+        }
+    }
+    g->sparsePrev.clear();
+    g->sparsePrevPtr = escapedPackets;
+    g->sparsePrevDense = false;
     g->sparsePrev.resize((size_t)n);
     {
         const unsigned long long *src = ctx->sparseHost;
@@ -1707,8 +1717,23 @@ int mcb200_fetch_escaped_sparse(mcb200_ctx *ctx, int32_t iG, float *escapedPacke
             }
         });
     }
+    if (withJ) CU(cudaStreamSynchronize(ctx->copyStream));
     if (nNonZero) *nNonZero = (int64_t)n;
     return MCB200_OK;
+}
+}  // namespace
+
+int mcb200_fetch_escaped_sparse(mcb200_ctx *ctx, int32_t iG, float *escapedPackets, int32_t clearPrevious,
+                                int64_t *nNonZero)
+{
+    return fetch_sparse_impl(ctx, iG, nullptr, escapedPackets, clearPrevious, nNonZero);
+}
+
+int mcb200_fetch_estimators_sparse(mcb200_ctx *ctx, int32_t iG, float *Jste, float *escapedPackets,
+                                   int32_t clearPrevious, int64_t *nNonZero)
+{
+    if (ctx && !Jste) return fail(ctx, MCB200_EINVAL, "Jste is NULL");
+    return fetch_sparse_impl(ctx, iG, Jste, escapedPackets, clearPrevious, nNonZero);
 }
 
 int mcb200_fetch_tallies(mcb200_ctx *ctx, int32_t iG, int64_t *JsteQ, int64_t *escapedQ, int64_t *JdifQ, int64_t *linePacketsQ)

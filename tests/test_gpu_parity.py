@@ -372,4 +372,7 @@ def test_sparse_escaped_fetch_equals_dense_fetch(name):
         assert again is bufs[iG] and np.array_equal(again.view(np.uint32), dense.view(np.uint32)), iG
         fresh, _ = e.fetch_escaped_sparse(iG, clear_previous=False)
         assert np.array_equal(fresh.view(np.uint32), dense.view(np.uint32))
+        both, _ = e.fetch_sparse(iG)                      # Jste dense + escapedPackets sparse in one call
+        assert np.array_equal(both["escapedPackets"].view(np.uint32), dense.view(np.uint32))
+        assert np.array_equal(both["Jste"].view(np.uint32), e.fetch(iG)["Jste"].view(np.uint32))
     e.close()
