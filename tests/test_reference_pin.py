@@ -92,6 +92,27 @@ def test_platform_libm_changes_few_histories(oracle_lib):
         float(want["escapedPackets_g1"].sum() + want["escapedPackets_g2"].sum()), rel=1e-3)
 
 
+@pytest.mark.skipif(not HAVE_REF, reason="reference sources not present")
+def test_fuzz_oracle_against_reference(oracle_lib):
+    """A short run of scripts/fuzz_reference.py: random models (non-uniform axes, opacity scatter
+    with zeros, random CDFs, albedo, sublimed grains, R_out inside the grid, off-centre star)
+    through the oracle and the translated reference.  (2000 trials were run once, 0 mismatches.)"""
+    import importlib.util
+    import sys
+
+    spec = importlib.util.spec_from_file_location("fuzz_reference", os.path.join(os.path.dirname(GOLD), "..", "scripts", "fuzz_reference.py"))
+    fz = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(fz)
+    bad = []
+    for t in range(12):
+        rng = np.random.default_rng([2024, t])
+        m, desc = fz.build(rng)
+        msg, ok = fz.compare(m, 120, 500 + t, oracle_lib)
+        if not ok:
+            bad.append((t, desc, msg))
+    assert not bad, bad
+
+
 # ---------------------------------------------------------------------------------------------
 # the callers either side of the transport: K1 (opacity block of iterateMC), K5/K6 (dust closure)
 # ---------------------------------------------------------------------------------------------
