@@ -7,7 +7,8 @@ Each trial builds one of the seeded workloads with random parameters, then pertu
 builders keep regular: non-uniform axes, per-(cell, nu) opacity scatter over several decades
 (including exact zeros), random scattering albedo, random re-emission CDFs and line fractions,
 random asymmetry parameters, sublimed grain species, R_out inside the grid, viewing angles, an
-off-centre star.  Both sides then transport the same packets (same Philox streams, detmath) and
+off-centre star; and picks the stellar packets, the extra diffuse source (iStar = 0) in a random
+cell, or the resonance-line packet loop.  Both sides then transport the same packets (same Philox streams, detmath) and
 every float32 tally element, Qphot/absInt/scaInt and the per-packet histories must be equal.
 A trial in which both sides hit a `print; stop` condition counts as equal; one in which the
 reference itself indexes an array out of bounds (undefined behaviour) is skipped.
@@ -125,16 +126,53 @@ def build(rng):
     return m, desc
 
 
-def compare(m, n, seed, lib):
+def pick_mode(rng, m):
+    """stellar packets (mostly), the extra diffuse source in a random active cell, or the
+    resonance-line packet loop"""
+    u = rng.random()
+    if u < 0.15 and m.lgGas:
+        gp = int(rng.integers(1, m.nGrids + 1))
+        g = m.grids[gp - 1]
+        cells = np.argwhere(np.asarray(g.active) > 0)
+        c = cells[int(rng.integers(0, len(cells)))]
+        nb = m.nbins
+        m.inSpectrumProbDen[0, :] = random_cdf_rows(rng, 1, nb)[0]
+        m.deltaE[0] = F32(1.0e-3)
+        return ("diffext", gp, tuple(int(v) + 1 for v in c))
+    if u < 0.25 and m.lgDust and m.lgGas:
+        for g in m.grids:
+            r = rng.integers(0, 3, g.nCells + 1).astype(np.int32)
+            r[0] = 0
+            g.resLinePackets = r
+        return ("reslines",)
+    return ("stellar",)
+
+
+def compare(m, n, seed, lib, mode=("stellar",)):
     o = Oracle(m)
     err_o = err_r = None
+    fo = None
     try:
-        co, fo = o.transport(1, 0, n, seed=seed, want_fates=True)
+        if mode[0] == "stellar":
+            co, fo = o.transport(1, 0, n, seed=seed, want_fates=True)
+        elif mode[0] == "diffext":
+            co, fo = o.transport(0, 0, n, seed=seed, gpLoc=mode[1], cellLoc=mode[2], want_fates=True)
+        else:
+            co, n = o.transport_reslines(1, seed=seed)
+            n = max(n, 1)
     except RuntimeError as ex:
         err_o = str(ex)
     r = Reference(m, lib)
     try:
-        cr, fr = r.transport(1, 0, n, seed=seed)
+        if mode[0] == "stellar":
+            cr, fr = r.transport(1, 0, n, seed=seed)
+        elif mode[0] == "diffext":
+            g = m.grids[mode[1] - 1]
+            x, y, z = mode[2]
+            r.grid[mode[1]].ldiffuseloc[int(g.active[x - 1, y - 1, z - 1])] = F32(m.deltaE[0])
+            cr, fr = r.transport(0, 0, n, seed=seed, gpLoc=mode[1], cellLoc=mode[2])
+        else:
+            cr, fr = r.transport_reslines(1, seed=seed)
     except rt.FortranStop as ex:
         err_r = str(ex)
     except rt.FortranBoundsError as ex:
@@ -144,7 +182,10 @@ def compare(m, n, seed, lib):
     if err_o or err_r:
         return ("both stop" if (err_o and err_r) else f"STOP MISMATCH oracle={err_o} reference={err_r}"), bool(err_o and err_r)
     bad = []
-    if not (np.array_equal(fo[:, 0], fr[:, 0]) and np.array_equal(fo[:, 1], fr[:, 1])):
+    if fo is None:
+        if co["nSegments"] != cr["nSegments"]:
+            bad.append(f"nSegments {co['nSegments']} vs {cr['nSegments']}")
+    elif not (np.array_equal(fo[:, 0], fr[:, 0]) and np.array_equal(fo[:, 1], fr[:, 1])):
         k = np.flatnonzero((fo[:, 0] != fr[:, 0]) | (fo[:, 1] != fr[:, 1]))
         bad.append(f"{k.size} packet histories differ, first {k[:3]} oracle {fo[k[:3], :2].tolist()} reference {fr[k[:3], :2].tolist()}")
     for i in range(m.nGrids):
@@ -177,7 +218,9 @@ def main():
         except Exception as ex:          # a builder rejecting random parameters is not a finding
             print(f"trial {t}: builder failed: {ex!r}")
             continue
-        msg, ok = compare(m, a.packets, 1000 + t, lib)
+        mode = pick_mode(rng, m)
+        desc["mode"] = mode[0]
+        msg, ok = compare(m, a.packets, 1000 + t, lib, mode)
         nbad += not ok
         print(f"trial {t} {'ok ' if ok else 'BAD'} {desc} :: {msg}", flush=True)
     print(f"{a.trials} trials, {nbad} mismatches, {time.time() - t0:.0f} s")

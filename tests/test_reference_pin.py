@@ -362,3 +362,64 @@ def test_translator_float32_arithmetic_and_bounds():
     assert toks == ["x", "<", "0", ".or.", "y", ">=", "1.e-3", ".and.", "z", "/=", "2.d0"]
     lines = f90py.logical_lines("a = 'it''s ! not a comment' ! comment\nb = 1 + &\n   & 2\nprint*, \"split&\n  &string\"")
     assert [" ".join(s.split()) for _, s in lines] == ["a = 'it''s ! not a comment'", "b = 1 + 2", 'print*, "splitstring"']
+
+
+SNIPPET2 = """
+module m2
+  implicit none
+  integer :: total = 0
+contains
+  subroutine counter(k)
+    integer, intent(out) :: k
+    integer, save :: calls = 0
+    logical :: first = .true.          ! initialiser = implicit SAVE
+    calls = calls + 1
+    if (first) then
+       total = total + 100
+       first = .false.
+    end if
+    k = calls
+  end subroutine counter
+
+  subroutine report(a, n)
+    real, intent(in) :: a(0:n)
+    integer, intent(in) :: n
+    integer :: i
+    open(unit=9, file='out.txt', status='unknown')
+    write(9, *) 'n = ', n, ' values: ', (a(i), ' ', i = 0, n)
+    write(9, *) a
+    close(9)
+  end subroutine report
+
+  subroutine partly(x)
+    real, intent(inout) :: x
+    x = x + 1.
+    if (x > 100.) then
+       where (x > 0.) x = 0.             ! not in the subset
+    end if
+  end subroutine partly
+end module m2
+"""
+
+
+def test_translator_save_write_capture_and_leniency():
+    # strict translation refuses what it does not cover ...
+    with pytest.raises(f90py.TranslateError):
+        f90py.Gen(f90py.Unit(SNIPPET2, "snippet2").modules).generate("#")
+    # ... lenient translation turns it into a statement that raises only if it is reached
+    gen = f90py.Gen(f90py.Unit(SNIPPET2, "snippet2", lenient=True).modules, lenient=True)
+    ns = {}
+    exec(compile(gen.generate("# snippet2"), "snippet2_ref", "exec"), ns)
+    assert list(gen.untranslated) == ["partly"] and len(gen.untranslated["partly"]) == 1
+    G = ns["init_globals"]()
+    assert [ns["p_counter"](0)[0] for _ in range(3)] == [1, 2, 3] and G.total == 100       # SAVE
+    ns["init_globals"]()
+    assert ns["p_counter"](0)[0] == 1                                                       # fresh program
+    rt.io_log.clear()
+    ns["p_report"](rt.wrap(np.float32([1.5, 2.5, 3.5]), (0,)), 2)
+    rec = rt.io_log[9]
+    assert rec[0] == ("n = ", 2, " values: ", np.float32(1.5), " ", np.float32(2.5), " ", np.float32(3.5), " ")
+    assert rec[1] == (np.float32(1.5), np.float32(2.5), np.float32(3.5))                   # whole array, element order
+    assert ns["p_partly"](np.float32(1.0))[0] == np.float32(2.0)
+    with pytest.raises(NotImplementedError):
+        ns["p_partly"](np.float32(500.0))
