@@ -27,13 +27,35 @@ REF_CASES = {
     "diffext_mother": (W.multigrid, dict(n=8, nsub=5, nbins=60), 500, ("diffext", 1, (3, 2, 5))),
     "diffext_subgrid": (W.multigrid, dict(n=8, nsub=5, nbins=60), 500, ("diffext", 2, (3, 2, 4))),
     "reslines_multigrid": (W.multigrid, dict(n=8, nsub=5, nbins=60), 0, "reslines"),
+    "two_stars": (None, dict(), 500, ("stars", (1, 2))),
 }
 DIFFEXT_DELTAE = 1.0e-3
 
 
+def two_stars():
+    """lgMultistars: a second, off-centre source with its own spectrum and packet energy in the
+    clumpy gas+dust cube; the two sources are transported one after the other (iteration_mod.f90:474-496)"""
+    from mocassin_b200.model import star_indices
+
+    F32 = np.float32
+    m = W.synthetic_cube(n=9, nbins=40, clumpy=True, dust=True, nPhotons=10 ** 6)
+    g = m.grids[0]
+    pos = [float(g.xAxis[5]) * 0.9, float(g.yAxis[2]) * 1.1 + 1e15, float(g.zAxis[6])]
+    idx = star_indices(g, pos)
+    assert g.active[idx[0] - 1, idx[1] - 1, idx[2] - 1] > 0
+    m.starPosition = np.vstack([m.starPosition, np.asarray(pos, F32)[None, :]]).astype(F32)
+    m.starIndeces = np.vstack([m.starIndeces, np.asarray(idx + [1], np.int32)[None, :]]).astype(np.int32)
+    m.deltaE = np.concatenate([m.deltaE, [F32(2e-6)]]).astype(F32)
+    row = (m.inSpectrumProbDen[1:2] ** 2).astype(F32)
+    row[0, -1] = 1.0
+    m.inSpectrumProbDen = np.vstack([m.inSpectrumProbDen, row]).astype(F32)
+    m.lgMultistars = True
+    return m
+
+
 def make(name):
     fn, kw, n, mode = REF_CASES[name]
-    m = fn(**kw)
+    m = fn(**kw) if fn is not None else two_stars()
     if isinstance(mode, tuple):
         m.inSpectrumProbDen[0, :] = W.blackbody_cdf(20000.0, m.nuArray, np.gradient(m.nuArray).astype(np.float32))
         m.deltaE[0] = DIFFEXT_DELTAE
@@ -57,6 +79,20 @@ def _collect(out, counters, fates, plane):
     return res
 
 
+def _stars(run, stars):
+    """one energyPacketDriver call per source into the same tallies; per-packet records concatenated,
+    Qphot (reset by every call, photon_mod.f90:89) of the last source, absInt/scaInt/nSegments summed"""
+    cs, fs = [], []
+    for i in stars:
+        c, f = run(i)
+        cs.append(c); fs.append(np.asarray(f))
+    c = dict(cs[-1])
+    for k in ("absInt", "scaInt"):
+        c[k] = np.float32(sum(np.float32(x[k]) for x in cs))
+    c["nSegments"] = sum(int(x["nSegments"]) for x in cs)
+    return c, np.concatenate(fs, axis=0)
+
+
 def run_oracle(name):
     """the C oracle's faithful float32 tallies and per-packet records"""
     from oracle.oracle import Oracle
@@ -65,6 +101,8 @@ def run_oracle(name):
     o = Oracle(m)
     if mode == "stellar":
         c, f = o.transport(1, 0, n, seed=SEED, want_fates=True)
+    elif mode[0] == "stars":
+        c, f = _stars(lambda i: o.transport(i, 0, n, seed=SEED, want_fates=True), mode[1])
     elif mode == "reslines":
         c, nrun = o.transport_reslines(1, seed=SEED)
         f = None
@@ -86,6 +124,8 @@ def run_reference(name, math="detmath", uninit_int=0):
     r = Reference(m, orc.load(), math=math, uninit_int=uninit_int)
     if mode == "stellar":
         c, f = r.transport(1, 0, n, seed=SEED)
+    elif mode[0] == "stars":
+        c, f = _stars(lambda i: r.transport(i, 0, n, seed=SEED), mode[1])
     elif mode == "reslines":
         c, f = r.transport_reslines(1, seed=SEED)
     else:

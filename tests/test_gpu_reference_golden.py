@@ -43,6 +43,27 @@ def test_cuda_matches_reference_golden(name, wavefront):
     if mode == "stellar":
         iStar = 1
         cg = e.energyPacketDriver(1, n)
+    elif mode[0] == "stars":                 # one call per source, different packet energies
+        nseg, k0 = 0, 0
+        for iStar in mode[1]:
+            c = e.energyPacketDriver(iStar, n)
+            nseg += c["nSegments"]
+            assert np.array_equal(e.fates(n)[:, :2], want["fates"][k0:k0 + n]), f"star {iStar}"
+            k0 += n
+        assert nseg == int(want["nSegments"])
+        got = e.fetch(1)
+        for k in ("Jste", "escapedPackets"):
+            g, w = got[k][1:].astype(np.float64), want[f"{k}_g1"][1:].astype(np.float64)
+            assert np.array_equal(g > 0, w > 0), k
+            sel = w > 0
+            rel = np.abs(g[sel] - w[sel]) / w[sel]
+            if k == "escapedPackets":        # count * deltaE per source, summed: float32 rounding only
+                assert rel.max() < 2e-6, rel.max()
+            else:
+                big = w[sel] >= np.percentile(w[sel], 50)
+                assert np.median(rel) < 1e-6 and rel[big].max() < 1e-5, (np.median(rel), rel[big].max())
+        e.close()
+        return
     elif mode == "reslines":
         iStar = 1
         cg = e.resLinePacketsTransfer(1)
