@@ -109,6 +109,36 @@ module mcb200_mod
             & bind(C, name="mcb200_fetch_estimators")
          import; type(c_ptr), value :: ctx, Jste, escapedPackets, Jdif, linePackets; integer(c_int32_t), value :: iG
        end function
+       ! K1: opacity, scaOpac, absOpac of grid iG on the device from the band list of addOpacity's
+       ! inOpacity calls (ionization_mod.f90:349-484) and the dust loop (iteration_mod.f90:166-227);
+       ! den(0:nCells, nSpeciesDen) = ionDen*elemAbun*Hden per species column, ff1 = FFOpacity(1) per cell
+       integer(c_int) function mcb200_assemble_opacity(ctx, iG, nBands, bandSpecies, bandOff, bandLow, bandHigh, &
+            & nSpeciesDen, den, ff1, Ndust, Tdust, dustAbunIndex, grainWeight, dustScaXsecP, dustAbsXsecP, nSpeciesTot) &
+            & bind(C, name="mcb200_assemble_opacity")
+         import; type(c_ptr), value :: ctx, bandSpecies, bandOff, bandLow, bandHigh, den, ff1
+         type(c_ptr), value :: Ndust, Tdust, dustAbunIndex, grainWeight, dustScaXsecP, dustAbsXsecP
+         integer(c_int32_t), value :: iG, nBands, nSpeciesDen, nSpeciesTot
+       end function
+       integer(c_int) function mcb200_get_opacity(ctx, iG, opacity, scaOpac, absOpac) bind(C, name="mcb200_get_opacity")
+         import; type(c_ptr), value :: ctx, opacity, scaOpac, absOpac; integer(c_int32_t), value :: iG
+       end function
+       ! K8: nPhotoSte/heatSte (and Dif) per (cell, band) for updateCell / thermBalance (update_mod.f90:170-262, 1160-1214)
+       integer(c_int) function mcb200_photo_integrals(ctx, iG, nBands, bandOff, bandLow, bandHigh, nPhotoSte, heatSte, &
+            & nPhotoDif, heatDif) bind(C, name="mcb200_photo_integrals")
+         import; type(c_ptr), value :: ctx, bandOff, bandLow, bandHigh, nPhotoSte, heatSte, nPhotoDif, heatDif
+         integer(c_int32_t), value :: iG, nBands
+       end function
+       integer(c_int) function mcb200_fetch_qphot_counts(ctx, counts) bind(C, name="mcb200_fetch_qphot_counts")
+         import; type(c_ptr), value :: ctx, counts
+       end function
+       integer(c_int) function mcb200_len_unit(ctx, iG, lenUnit) bind(C, name="mcb200_len_unit")
+         import; type(c_ptr), value :: ctx; integer(c_int32_t), value :: iG; real(c_double), intent(out) :: lenUnit
+       end function
+       ! name is a C string: pass e.g. "wavefront"//c_null_char
+       integer(c_int) function mcb200_set_option(ctx, name, value) bind(C, name="mcb200_set_option")
+         import; type(c_ptr), value :: ctx; character(kind=c_char), dimension(*), intent(in) :: name
+         integer(c_int64_t), value :: value
+       end function
        ! escapedPackets sparsely (only its non-zero entries cross PCIe; the array must be zero elsewhere,
        ! as iterateMC leaves it at iteration_mod.f90:466-470), alone or together with the dense Jste
        integer(c_int) function mcb200_fetch_escaped_sparse(ctx, iG, escapedPackets, clearPrevious, nNonZero) &

@@ -56,3 +56,16 @@ def test_product_package_never_imports_oracle():
                 text = open(os.path.join(dirpath, f)).read()
                 assert "import oracle" not in text and "from oracle" not in text and "oracle/" not in text.replace(
                     "oracle/mc_oracle.c ERR_STOP", ""), f
+
+
+def test_fortran_binding_covers_the_header():
+    """fortran/mcb200_mod.f90 (the ISO_C_BINDING shim a maintainer of the reference adds) declares
+    every entry point of include/mcb200.h except the diagnostic / unit-test hooks."""
+    hdr = open(os.path.join(ROOT, "include", "mcb200.h")).read()
+    f90 = open(os.path.join(ROOT, "fortran", "mcb200_mod.f90")).read()
+    exported = set(re.findall(r"^(?:int|const char \*)\s*(mcb200_\w+)\s*\(", hdr, flags=re.M))
+    bound = set(re.findall(r'name="(mcb200_\w+)"', f90))
+    diagnostic = {"mcb200_fetch_fates", "mcb200_fetch_tallies", "mcb200_test_access_peak", "mcb200_test_detmath",
+                  "mcb200_test_uniforms"}
+    assert exported - bound == diagnostic, sorted(exported - bound - diagnostic)
+    assert bound <= exported, sorted(bound - exported)
