@@ -102,3 +102,53 @@ def test_cuda_matches_reference_golden(name, wavefront):
             assert rel[big].max() < 1e-5, (iG, k, rel[big].max())
             assert abs(g.sum() - w.sum()) / w.sum() < 1e-5, (iG, k)
     e.close()
+
+
+def _same_nan(a, b):
+    a, b = np.asarray(a), np.asarray(b)
+    both = np.isnan(a) & np.isnan(b)
+    return a.shape == b.shape and bool(np.all((a.view(np.uint32) == b.view(np.uint32)) | both))
+
+
+def test_device_dust_pdf_matches_reference_setdustpdf():
+    """K6 (dust_pdf_kernel) against what the reference's own emissionDriver -> setDustPDF produced
+    (tests/golden/ref_aux_dust_closure.npz)."""
+    want = dict(np.load(os.path.join(GOLD, "ref_aux_dust_closure.npz")))
+    model, g, t, J, Jd = ref_cases._dust_inputs(False)
+    eng = PacketEngine(model)
+    eng.set_xsec(t["xSecArray"])
+    eng.set_dust_tables(t["widFlx"], t["grainWeight"], t["dustAbsXsecP"], t["dustEmIntegral"])
+    eng.set_opacity()
+    eng.set_dust_state()
+    got = eng.setDustPDF(1, fetch=True)
+    assert _same_nan(got[1:], want["dustPDF"][1:])
+    eng.close()
+
+
+@pytest.mark.parametrize("name", ["opacity_multichem", "opacity_singlechem"])
+def test_device_opacity_matches_reference_opacity_block(name):
+    """K1 (opacity_kernel + the host band flattening) against the output of the reference's own
+    opacity block of iterateMC (ionizationDriver/addOpacity + dust loop; ref_aux_opacity_*.npz)."""
+    from mocassin_b200 import workloads as W
+    from mocassin_b200.model import Grid
+
+    want = dict(np.load(os.path.join(GOLD, f"ref_aux_{name}.npz")))
+    c = ref_cases._opacity_inputs(name == "opacity_multichem")
+    t, nb, dm = c["t"], c["nbins"], c["dm"]
+    m = W.dust_shell(n=8, nbins=nb)
+    ax = np.arange(4, dtype=np.float32) * np.float32(1e15)
+    m.grids[0] = Grid(xAxis=ax, yAxis=ax.copy(), zAxis=ax.copy(), active=c["active"], nCells=c["nCells"])
+    m.lgGas = True
+    m.lgMultiDustChemistry = bool(dm.lgMultiDustChemistry)
+    m.nSpeciesMax, m.nSizes = dm.nSpeciesMax, dm.nSizes
+    m.nSpeciesPart, m.dustComPoint = dm.nSpeciesPart, dm.dustComPoint
+    m.grainAbun, m.TdustSublime = dm.grainAbun, dm.TdustSublime
+    m.starIndeces[0, :3] = 1
+    e = PacketEngine(m)
+    e.set_xsec(t.xSecArray)
+    den = t.species_densities(c["ionDen"], c["elemAbun"], c["abIndex"], c["Hden"])
+    e.assemble_opacity(1, t.band_list(nb), den, want["ff1"], c["dust"])
+    op, sca, ab = e.get_opacity(1, want_abs=True)
+    for got, key in ((sca, "scaOpac"), (ab, "absOpac"), (op, "opacity")):
+        assert np.array_equal(got[1:].view(np.uint32), want[key][1:].view(np.uint32)), key
+    e.close()
