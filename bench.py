@@ -322,6 +322,12 @@ def run_b200(args):
         # reference all-reduces escapedPackets (iteration_mod.f90:649-659).
         eng.set_sed_local(True)
 
+    if world > 1 and os.environ.get("MCB_NATIVE_COMM", "0") == "1":
+        # the library's own NCCL communicator (mcb200_comm_init / mcb200_exchange: what a Fortran/MPI
+        # host calls) instead of torch.distributed collectives on the tally buffers.  Off by
+        # default until it has been timed at N > 1.
+        eng.comm_init_from_group()
+
     def step():
         if overlap:      # exchange of the first half hidden behind the transport of the second
             return eng.energyPacketDriverOverlapped(1, nGlobal, deltaE=dE)

@@ -105,6 +105,26 @@ module mcb200_mod
        integer(c_int) function mcb200_reduce(ctx) bind(C, name="mcb200_reduce")
          import; type(c_ptr), value :: ctx
        end function
+       ! the library's own NCCL communicator: rank 0 makes the 128-byte id, the host broadcasts it
+       ! (MPI_BCAST(id, 128, MPI_BYTE, 0, ...)), every rank joins; mcb200_exchange then replaces the
+       ! MPI_ALLREDUCE block iteration_mod.f90:564,627,649,653,659
+       integer(c_int) function mcb200_comm_unique_id(ctx, id128) bind(C, name="mcb200_comm_unique_id")
+         import; type(c_ptr), value :: ctx, id128
+       end function
+       integer(c_int) function mcb200_comm_init(ctx, id128) bind(C, name="mcb200_comm_init")
+         import; type(c_ptr), value :: ctx, id128
+       end function
+       integer(c_int) function mcb200_comm_destroy(ctx) bind(C, name="mcb200_comm_destroy")
+         import; type(c_ptr), value :: ctx
+       end function
+       integer(c_int) function mcb200_exchange(ctx) bind(C, name="mcb200_exchange")
+         import; type(c_ptr), value :: ctx
+       end function
+       integer(c_int) function mcb200_exchange_info(ctx, bytesSent, sparseGrids, ncclVersion) &
+            & bind(C, name="mcb200_exchange_info")
+         import; type(c_ptr), value :: ctx
+         integer(c_int64_t), intent(out) :: bytesSent; integer(c_int32_t), intent(out) :: sparseGrids, ncclVersion
+       end function
        integer(c_int) function mcb200_fetch_estimators(ctx, iG, Jste, escapedPackets, Jdif, linePackets) &
             & bind(C, name="mcb200_fetch_estimators")
          import; type(c_ptr), value :: ctx, Jste, escapedPackets, Jdif, linePackets; integer(c_int32_t), value :: iG

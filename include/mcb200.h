@@ -38,6 +38,7 @@ extern "C" {
 #define MCB200_EPACKET      -5   /* a packet hit one of the reference's `stop`s     */
 #define MCB200_EUNSUPPORTED -6   /* nested sub-grids / lg1D                          */
 #define MCB200_ETABLE       -7   /* CDF table not monotone / bad range              */
+#define MCB200_ECOMM        -8   /* NCCL unavailable or a collective failed         */
 
 typedef struct mcb200_ctx mcb200_ctx;   /* opaque */
 
@@ -270,6 +271,37 @@ int mcb200_reduce_range(mcb200_ctx *ctx, int32_t iG, int32_t nu0, int32_t nu1);
  * second tally set. */
 int mcb200_escaped_compact(mcb200_ctx *ctx, int32_t iG, int32_t set, void **devList, int64_t *nEntries);
 int mcb200_escaped_scatter(mcb200_ctx *ctx, int32_t iG, int32_t set, const void *devList, int64_t nEntries);
+/* The exchange done by the library itself: a NCCL communicator owned by the context, for a
+ * host (the Fortran/MPI reference) that has no device-aware collective of its own.  Replaces
+ * the MPI_ALLREDUCE block iteration_mod.f90:564,627,649,653,659 together with mcb200_reduce.
+ *   rank 0:     mcb200_comm_unique_id(ctx, id)         128-byte ncclUniqueId
+ *   host:       MPI_BCAST(id, 128, MPI_BYTE, 0, ...)   the only host-side message
+ *   every rank: mcb200_comm_init(ctx, id)              rank / nranks as given to mcb200_create
+ *   per source: mcb200_transport(...); mcb200_exchange(ctx); mcb200_reduce(ctx);
+ * mcb200_exchange sums the pending integer tallies of every grid over the ranks, in place, on
+ * the library stream: max-reduce of the nuTouched flags, then only the flagged nu-planes of
+ * JsteQ (and JdifQ, linePacketsQ in debug mode), planeIonDistribution, and the escape counts
+ * as all-gathered sparse (index, count) lists when those are shorter than the dense planes
+ * (with option "sed_local": the (nu, angle) counts of buffer 6 instead).  Integer sums: the
+ * folded estimators are bit-identical on every rank and for every rank count.  A second tally
+ * set (option "tally_set") is merged first.  No-op for nranks = 1 or when nothing is pending.
+ * NCCL is bound at run time (dlopen, RTLD_LOCAL, of $MCB200_NCCL_LIB, libnccl.so.2, libnccl.so): the
+ * library has no link-time dependency on it; MCB200_ECOMM if it cannot be found.
+ * mcb200_exchange_info: bytes this rank handed to NCCL in the last exchange, the number of
+ * grids whose escape counts went sparse, and ncclGetVersion (0 if NCCL is not loaded); any
+ * pointer may be NULL. */
+int mcb200_comm_unique_id(mcb200_ctx *ctx, void *id128);
+int mcb200_comm_init(mcb200_ctx *ctx, const void *id128);
+int mcb200_comm_destroy(mcb200_ctx *ctx);
+int mcb200_exchange(mcb200_ctx *ctx);
+int mcb200_exchange_info(mcb200_ctx *ctx, int64_t *bytesSent, int32_t *sparseGrids, int32_t *ncclVersion);
+/* Which NCCL the library binds (needs no context and no device): ncclGetVersion and the file the
+ * symbols came from.  A process that also hosts another NCCL user (PyTorch) must bind the SAME
+ * copy: the dynamic loader keeps one object per SONAME, so whichever libnccl.so.2 is opened first
+ * serves both -- point $MCB200_NCCL_LIB at the newer one (mocassin_b200/_lib.py does, for torch's
+ * bundled copy).  MCB200_ECOMM if NCCL cannot be loaded. */
+int mcb200_nccl_info(int32_t *version, char *path, int64_t pathLen);
+
 /* After the allreduce: fold the (now global) integer tallies of the last transport
  * call into the float32 estimators. No-op when nothing is pending. */
 int mcb200_reduce(mcb200_ctx *ctx);
@@ -364,7 +396,10 @@ int mcb200_fetch_fates(mcb200_ctx *ctx, int32_t *fates, int64_t nPackets);
  *   "async_pdfs"    1: mcb200_set_pdfs only enqueues the upload (see there)
  *   "sed_local"     1: per-rank SED counts, see mcb200_fetch_sed
  *   "tally_set", "parts", "part"   second tally set / sub-ranges of a rank's share, for overlapping the
- *                   exchange of one half with the transport of the other (PacketEngine.energyPacketDriverOverlapped) */
+ *                   exchange of one half with the transport of the other (PacketEngine.energyPacketDriverOverlapped)
+ *   "exchange_dense" 1: mcb200_exchange all-reduces the escape counts densely whatever the list lengths
+ *   "defer_fold"    1: a single rank leaves its tallies pending after mcb200_transport, as a multi-rank run
+ *                   does, until mcb200_reduce (lets one GPU walk the mcb200_exchange path) */
 int mcb200_set_option(mcb200_ctx *ctx, const char *name, int64_t value);
 
 /* unit-test hooks: run device primitives on n inputs (host arrays in/out). */

@@ -64,6 +64,11 @@ _SIGS = {
     "mcb200_transport_reslines": [C.c_void_p, C.c_int32, C.c_float, C.POINTER(Counters)],
     "mcb200_tally_buffer": [C.c_void_p, C.c_int32, C.c_int32, C.POINTER(C.c_void_p), c_int64_p],
     "mcb200_reduce": [C.c_void_p],
+    "mcb200_comm_unique_id": [C.c_void_p, C.c_void_p],
+    "mcb200_comm_init": [C.c_void_p, C.c_void_p],
+    "mcb200_comm_destroy": [C.c_void_p],
+    "mcb200_exchange": [C.c_void_p],
+    "mcb200_exchange_info": [C.c_void_p, c_int64_p, c_int32_p, c_int32_p],
     "mcb200_fetch_estimators": [C.c_void_p, C.c_int32, c_float_p, c_float_p, c_float_p, c_float_p],
     "mcb200_fetch_escaped_sparse": [C.c_void_p, C.c_int32, c_float_p, C.c_int32, c_int64_p],
     "mcb200_fetch_estimators_sparse": [C.c_void_p, C.c_int32, c_float_p, c_float_p, C.c_int32, c_int64_p],
@@ -78,9 +83,29 @@ _SIGS = {
     "mcb200_test_access_peak": [C.c_void_p, C.c_int32, C.c_int64, C.c_int64, C.c_int64, C.POINTER(C.c_double)],
 }
 
-EXPORTS = sorted(list(_SIGS) + ["mcb200_last_error"])
+EXPORTS = sorted(list(_SIGS) + ["mcb200_last_error", "mcb200_nccl_info"])
 
 _lib = None
+
+
+def _prefer_bundled_nccl():
+    """The loader keeps ONE object per SONAME: if the library's dlopen("libnccl.so.2") found the
+    system copy first, a later `import torch` would be served that (older) copy and fail on a
+    missing symbol (seen on the GPU box: ncclDevCommCreate).  So, unless the user chose one,
+    point MCB200_NCCL_LIB at the copy torch itself loads (the nvidia-nccl wheel)."""
+    if os.environ.get("MCB200_NCCL_LIB"):
+        return
+    try:
+        import importlib.util
+
+        spec = importlib.util.find_spec("nvidia.nccl")
+        for d in (spec.submodule_search_locations if spec else []):
+            cand = os.path.join(d, "lib", "libnccl.so.2")
+            if os.path.exists(cand):
+                os.environ["MCB200_NCCL_LIB"] = cand
+                return
+    except Exception:
+        pass
 
 
 def load() -> C.CDLL:
@@ -93,6 +118,7 @@ def load() -> C.CDLL:
         raise ImportError(
             f"{path} is missing: build it with `python -m mocassin_b200.build` "
             "(nvcc, sm_100a). mocassin_b200 has no CPU fallback.")
+    _prefer_bundled_nccl()
     lib = C.CDLL(path)
     for name, args in _SIGS.items():
         fn = getattr(lib, name)
@@ -100,5 +126,18 @@ def load() -> C.CDLL:
         fn.restype = C.c_int
     lib.mcb200_last_error.argtypes = [C.c_void_p]
     lib.mcb200_last_error.restype = C.c_char_p
+    lib.mcb200_nccl_info.argtypes = [c_int32_p, C.c_char_p, C.c_int64]
+    lib.mcb200_nccl_info.restype = C.c_int
     _lib = lib
     return lib
+
+
+def nccl_info() -> tuple[int, str]:
+    """(ncclGetVersion, path of the libnccl the library bound); raises if NCCL cannot be loaded."""
+    lib = load()
+    v = C.c_int32()
+    buf = C.create_string_buffer(4096)
+    rc = lib.mcb200_nccl_info(C.byref(v), buf, 4096)
+    if rc != 0:
+        raise ImportError("libmocassin_b200.so could not bind NCCL (libnccl.so.2; set MCB200_NCCL_LIB)")
+    return v.value, buf.value.decode()

@@ -98,6 +98,7 @@ class PacketEngine:
         self.pipelined_fold = False      # N>1: fold plane chunks while later chunks are exchanged (measured: no gain)
         self.exchange_chunk_planes = 64
         self.last_escaped_exchange = None
+        self.native_comm = False         # N>1: the library's own NCCL communicator does the exchange
         self._upload_static()
 
     # -- plumbing ---------------------------------------------------------------------
@@ -462,11 +463,50 @@ class PacketEngine:
             self._check(self.lib.mcb200_reduce_range(self.h, iG, a, b))
         return True
 
+    # -- the library's own communicator (what a Fortran/MPI host uses) -------------------
+    def comm_unique_id(self) -> bytes:
+        """128-byte ncclUniqueId (rank 0 makes it, the host broadcasts it: MPI_BCAST in the
+        reference, any byte channel here)."""
+        buf = C.create_string_buffer(128)
+        self._check(self.lib.mcb200_comm_unique_id(self.h, buf))
+        return buf.raw
+
+    def comm_init(self, unique_id: bytes):
+        """mcb200_comm_init: join the NCCL communicator of `unique_id` as (rank, nranks) of
+        the constructor; reduce() then runs mcb200_exchange instead of torch.distributed."""
+        if len(unique_id) != 128:
+            raise ValueError("ncclUniqueId is 128 bytes")
+        self._check(self.lib.mcb200_comm_init(self.h, C.create_string_buffer(unique_id, 128)))
+        self.native_comm = True
+
+    def comm_init_from_group(self, group=None):
+        """Bootstrap the native communicator over an existing torch.distributed group (any
+        backend: only the 128 id bytes travel)."""
+        import torch.distributed as dist
+
+        box = [self.comm_unique_id() if self.rank == 0 else None]
+        dist.broadcast_object_list(box, src=0, group=group)
+        self.comm_init(box[0])
+
+    def comm_destroy(self):
+        self._check(self.lib.mcb200_comm_destroy(self.h))
+        self.native_comm = False
+
+    def exchange(self) -> dict:
+        """mcb200_exchange: sum the pending integer tallies over the ranks of the native
+        communicator (no fold).  Returns mcb200_exchange_info."""
+        self._check(self.lib.mcb200_exchange(self.h))
+        b, sp, v = C.c_int64(), C.c_int32(), C.c_int32()
+        self._check(self.lib.mcb200_exchange_info(self.h, C.byref(b), C.byref(sp), C.byref(v)))
+        return dict(bytes=b.value, sparse_grids=sp.value, nccl_version=v.value)
+
     def reduce(self, group=None):
         """Sum the pending integer tallies over ranks and fold them into the float32
         estimators.  Exact integer sums -> identical bits on every rank and for every rank
         count."""
-        if self.nranks > 1:
+        if self.native_comm:
+            self.last_exchange = self.exchange()
+        elif self.nranks > 1:
             import torch
 
             if not (self.pipelined_fold and self._exchange_pipelined(group)):
@@ -607,9 +647,9 @@ class PacketEngine:
         out = []
         for iStar in range(1, self.model.nStars + 1):
             out.append(self.energyPacketDriver(iStar, int(nPhotons[iStar - 1])))
-            if self.nranks > 1:
+            if self.nranks > 1 or self.native_comm:
                 self.reduce(group)
-        if self.nranks == 1:
+        if self.nranks == 1 and not self.native_comm:
             self.reduce()
         return out
 

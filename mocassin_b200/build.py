@@ -23,6 +23,7 @@ NVCC_FLAGS = [
     "-fmad=false",
     "-Xcompiler", "-fPIC,-ffp-contract=off,-pthread",
     "-shared",
+    "-ldl",
 ]
 
 

@@ -8,6 +8,7 @@
 #include "transport_core.cuh"
 
 #include <cuda_runtime.h>
+#include <dlfcn.h>
 
 #include <chrono>
 #include <thread>
@@ -206,6 +207,13 @@ struct mcb200_ctx {
     bool sedLocal = false;                // option sed_local: sedQ is taken from this rank's escQ at
                                           // the end of the transport call and exchanged instead of escQ
     bool sedReady = false;                // sedQ already holds the pending call's counts
+    // library-owned NCCL communicator (mcb200_comm_init) for hosts without a device-aware collective
+    void *comm = nullptr;
+    DevBuf<unsigned long long> commSizes, commPad, commGather;
+    int64_t lastExchangeBytes = 0;        // bytes this rank handed to NCCL in the last mcb200_exchange
+    int lastExchangeSparse = 0;           // grids whose escape counts went as sparse lists
+    bool exchangeDense = false;           // option exchange_dense: mcb200_exchange never takes the sparse path
+    bool deferFold = false;               // option defer_fold: a single rank keeps its tallies pending like a multi-rank run
     // pending fold
     bool pending = false;
     float pendingDeltaE = 0.f;
@@ -489,6 +497,46 @@ int fold_pending(mcb200_ctx *ctx)
     return MCB200_OK;
 }
 
+// non-zero (index, count) pairs of the escape counts of tally set `set` -> ctx->escList, entries
+// cleared (scattering every rank's list back rebuilds the sum); only the touched nu-planes are scanned
+int esc_compact(mcb200_ctx *ctx, GridState &g, int set, int64_t *nEntries)
+{
+    unsigned int *Q = set == 1 ? g.escQ2.p : g.escQ.p;
+    const int *touched = set == 1 ? g.nuTouched2.p : g.nuTouched.p;
+    if (!Q) return fail(ctx, MCB200_ESTATE, "tally set %d not allocated", set);
+    const int nb = ctx->cfg.nbins;
+    const size_t nR = (size_t)g.nCells + 1;
+    cudaStream_t s = ctx->stream;
+    std::vector<int> flag(nb + 1, 1);
+    if (touched) {
+        CU(cudaMemcpyAsync(flag.data(), touched, sizeof(int) * (nb + 1), cudaMemcpyDeviceToHost, s));
+        CU(cudaStreamSynchronize(s));
+    }
+    auto ranges = touched_ranges(flag);
+    const int blocks = ctx->numSMs * 8;
+    CU(ctx->escCount.alloc(1));
+    // pass 1: count; pass 2: fill and clear
+    for (int pass = 0; pass < 2; ++pass) {
+        CU(ctx->escCount.zero(s));
+        unsigned long long cap = pass ? ctx->escList.n / 2 : 0;
+        for (auto &rg : ranges)
+            for (int ang = 0; ang <= ctx->cfg.nAngleBins; ++ang) {
+                size_t off = nR * ((size_t)rg.first + (size_t)(nb + 1) * (size_t)ang);
+                size_t len = (size_t)(rg.second - rg.first + 1) * nR;
+                CU(launch_esc_compact(Q, off, len, pass ? ctx->escList.p : nullptr, ctx->escCount.p, cap, pass, blocks, s));
+            }
+        unsigned long long n = 0;
+        CU(cudaMemcpyAsync(&n, ctx->escCount.p, 8, cudaMemcpyDeviceToHost, s));
+        CU(cudaStreamSynchronize(s));
+        if (!pass) {
+            if (ctx->escList.n < 2 * n || ctx->escList.n > 8 * n + 1024) CU(ctx->escList.alloc((size_t)(2 * n > 2 ? 2 * n : 2)));
+        } else {
+            *nEntries = (int64_t)n;
+        }
+    }
+    return MCB200_OK;
+}
+
 // wave-front schedule (wavefront.cu): event kernels + frequency sort + FLY kernel per wave
 int run_wavefront(mcb200_ctx *ctx, const TransportArgs &a, bool multi, int64_t mine)
 {
@@ -670,7 +718,7 @@ int run_transport(mcb200_ctx *ctx, int iStar, int difGrid, const int32_t *cellLo
     // a previous call with a different deltaE must be folded first (single rank), or
     // reduced by the caller (multi rank)
     if (ctx->pending) {
-        if (ctx->nranks == 1) { int rc = fold_pending(ctx); if (rc) return rc; }
+        if (ctx->nranks == 1 && !ctx->deferFold) { int rc = fold_pending(ctx); if (rc) return rc; }
         else if (ctx->pendingDeltaE != deltaE)
             return fail(ctx, MCB200_ESTATE, "pending tallies with a different deltaE: call mcb200_reduce first");
     }
@@ -825,7 +873,7 @@ int run_transport(mcb200_ctx *ctx, int iStar, int difGrid, const int32_t *cellLo
         if (out) out->nLaunches += nl;
     }
     if (herr) return fail(ctx, MCB200_EPACKET, "a packet hit reference stop condition %d (see oracle/mc_oracle.c ERR_STOP codes)", herr);
-    if (ctx->nranks == 1) {
+    if (ctx->nranks == 1 && !ctx->deferFold) {
         int rcf = fold_pending(ctx);
         if (rcf) return rcf;
         CU(cudaEventRecord(ctx->ev2, ctx->stream));
@@ -862,6 +910,174 @@ __global__ void uniforms_kernel(unsigned long long seed, unsigned long long pid,
     Rng r;
     r.init(seed, pid, stream);
     for (int i = 0; i < n; ++i) out[i] = r.uniform();
+}
+
+
+// ---- NCCL, bound at run time -----------------------------------------------------------------
+// The library has no link-time dependency on NCCL: single-rank hosts never need it, and a
+// Python host has torch's copy in the process already (dlopen by SONAME returns that one).
+// Search order: $MCB200_NCCL_LIB, libnccl.so.2, libnccl.so.  Types restated from nccl.h (2.x ABI).
+struct NcclId { char internal[128]; };
+enum { kNcclInt32 = 2, kNcclUint32 = 3, kNcclUint64 = 5, kNcclSum = 0, kNcclMax = 2 };
+struct NcclApi {
+    void *handle = nullptr;
+    int (*GetUniqueId)(NcclId *) = nullptr;
+    int (*CommInitRank)(void **, int, NcclId, int) = nullptr;
+    int (*CommDestroy)(void *) = nullptr;
+    int (*AllReduce)(const void *, void *, size_t, int, int, void *, cudaStream_t) = nullptr;
+    int (*AllGather)(const void *, void *, size_t, int, void *, cudaStream_t) = nullptr;
+    int (*GroupStart)() = nullptr;
+    int (*GroupEnd)() = nullptr;
+    const char *(*GetErrorString)(int) = nullptr;
+    int (*GetVersion)(int *) = nullptr;
+    std::string why;
+};
+
+NcclApi &nccl_api()
+{
+    static NcclApi api;
+    if (api.handle || !api.why.empty()) return api;
+    const char *env = std::getenv("MCB200_NCCL_LIB");
+    const char *names[3] = {env, "libnccl.so.2", "libnccl.so"};
+    for (const char *nm : names) {
+        if (!nm || !*nm) continue;
+        api.handle = dlopen(nm, RTLD_NOW | RTLD_LOCAL);
+        if (api.handle) break;
+    }
+    if (!api.handle) { api.why = "libnccl.so.2 not found (set MCB200_NCCL_LIB)"; return api; }
+    bool ok = true;
+    auto sym = [&](const char *n) { void *p = dlsym(api.handle, n); if (!p) { ok = false; api.why = std::string("NCCL symbol missing: ") + n; } return p; };
+    api.GetUniqueId = reinterpret_cast<decltype(api.GetUniqueId)>(sym("ncclGetUniqueId"));
+    api.CommInitRank = reinterpret_cast<decltype(api.CommInitRank)>(sym("ncclCommInitRank"));
+    api.CommDestroy = reinterpret_cast<decltype(api.CommDestroy)>(sym("ncclCommDestroy"));
+    api.AllReduce = reinterpret_cast<decltype(api.AllReduce)>(sym("ncclAllReduce"));
+    api.AllGather = reinterpret_cast<decltype(api.AllGather)>(sym("ncclAllGather"));
+    api.GroupStart = reinterpret_cast<decltype(api.GroupStart)>(sym("ncclGroupStart"));
+    api.GroupEnd = reinterpret_cast<decltype(api.GroupEnd)>(sym("ncclGroupEnd"));
+    api.GetErrorString = reinterpret_cast<decltype(api.GetErrorString)>(sym("ncclGetErrorString"));
+    api.GetVersion = reinterpret_cast<decltype(api.GetVersion)>(sym("ncclGetVersion"));
+    if (!ok) { dlclose(api.handle); api.handle = nullptr; }
+    return api;
+}
+
+#define NC(call)                                                                                   \
+    do {                                                                                           \
+        int r__ = (call);                                                                          \
+        if (r__ != 0) return fail(ctx, MCB200_ECOMM, "%s: %s", #call, nccl_api().GetErrorString(r__)); \
+    } while (0)
+
+// in-place sum / max over ranks of `count` elements on the library stream
+int comm_allreduce(mcb200_ctx *ctx, void *buf, size_t count, int dtype, int op)
+{
+    if (!count) return MCB200_OK;
+    NC(nccl_api().AllReduce(buf, buf, count, dtype, op, ctx->comm, ctx->stream));
+    ctx->lastExchangeBytes += (int64_t)count * (dtype == kNcclUint64 ? 8 : 4);
+    return MCB200_OK;
+}
+
+// escape counts of one grid: all-gather of every rank's non-zero (index, count) pairs when that
+// moves fewer bytes than the dense all-reduce of the touched planes (PacketEngine._exchange_escaped_sparse)
+int comm_exchange_escaped(mcb200_ctx *ctx, GridState &g, const std::vector<std::pair<int, int>> &ranges)
+{
+    NcclApi &N = nccl_api();
+    const int nb = ctx->cfg.nbins, world = ctx->nranks;
+    const size_t nR = (size_t)g.nCells + 1;
+    cudaStream_t s = ctx->stream;
+    size_t planes = 0;
+    for (auto &rg : ranges) planes += (size_t)(rg.second - rg.first + 1);
+    const unsigned long long dense = 2ull * 4ull * nR * (unsigned long long)(ctx->cfg.nAngleBins + 1) * planes;
+    int64_t n = 0;
+    int rc = esc_compact(ctx, g, 0, &n);
+    if (rc) return rc;
+    CU(ctx->commSizes.alloc((size_t)world + 1));
+    unsigned long long mine = (unsigned long long)n;
+    CU(cudaMemcpyAsync(ctx->commSizes.p + world, &mine, 8, cudaMemcpyHostToDevice, s));
+    NC(N.AllGather(ctx->commSizes.p + world, ctx->commSizes.p, 1, kNcclUint64, ctx->comm, s));
+    std::vector<unsigned long long> all(world);
+    CU(cudaMemcpyAsync(all.data(), ctx->commSizes.p, 8 * (size_t)world, cudaMemcpyDeviceToHost, s));
+    CU(cudaStreamSynchronize(s));
+    unsigned long long maxn = 0;
+    for (auto v : all) maxn = v > maxn ? v : maxn;
+    if (ctx->exchangeDense || 16ull * maxn * (unsigned long long)world >= dense) {
+        // lists too long: put this rank's entries back and all-reduce the touched planes
+        CU(launch_esc_scatter(g.escQ.p, g.escQ.n, ctx->escList.p, (unsigned long long)n, ctx->numSMs * 8, s));
+        for (auto &rg : ranges)
+            for (int ang = 0; ang <= ctx->cfg.nAngleBins; ++ang) {
+                size_t off = nR * ((size_t)rg.first + (size_t)(nb + 1) * (size_t)ang);
+                rc = comm_allreduce(ctx, g.escQ.p + off, (size_t)(rg.second - rg.first + 1) * nR, kNcclUint32, kNcclSum);
+                if (rc) return rc;
+            }
+        return MCB200_OK;
+    }
+    ctx->lastExchangeSparse++;
+    if (maxn == 0) return MCB200_OK;
+    // equal-sized slots, zero padded: a (0, 0) pair adds nothing
+    if (ctx->commPad.n < 2 * maxn) CU(ctx->commPad.alloc((size_t)(2 * maxn)));
+    if (ctx->commGather.n < 2 * maxn * (unsigned long long)world) CU(ctx->commGather.alloc((size_t)(2 * maxn * world)));
+    CU(cudaMemsetAsync(ctx->commPad.p, 0, 16 * (size_t)maxn, s));
+    if (n) CU(cudaMemcpyAsync(ctx->commPad.p, ctx->escList.p, 16 * (size_t)n, cudaMemcpyDeviceToDevice, s));
+    NC(N.AllGather(ctx->commPad.p, ctx->commGather.p, (size_t)(2 * maxn), kNcclUint64, ctx->comm, s));
+    ctx->lastExchangeBytes += (int64_t)(16 * maxn);
+    CU(launch_esc_scatter(g.escQ.p, g.escQ.n, ctx->commGather.p, maxn * (unsigned long long)world, ctx->numSMs * 8, s));
+    return MCB200_OK;
+}
+
+int comm_exchange(mcb200_ctx *ctx)
+{
+    const int nb = ctx->cfg.nbins, blocks = ctx->numSMs * 8;
+    cudaStream_t s = ctx->stream;
+    ctx->lastExchangeBytes = 0;
+    ctx->lastExchangeSparse = 0;
+    if (ctx->pending2) {                  // two tally sets: merge as integers first, exchange the sum
+        for (auto &g : ctx->grids) {
+            if (!g.JsteQ2.p) continue;
+            CU(launch_merge_sets(g.JsteQ.p, g.JsteQ2.p, g.JsteQ.n, g.escQ.p, g.escQ2.p, g.escQ.n,
+                                 g.nuTouched.p, g.nuTouched2.p, nb + 1, blocks, s));
+        }
+        ctx->pending2 = false;
+    }
+    if (ctx->sedLocal) {                  // per-(nu, angle) escape counts instead of the per-cell array
+        if (!ctx->sedReady) { int rc = sed_tally(ctx, 0, nullptr); if (rc) return rc; ctx->sedReady = true; }
+        int rc = comm_allreduce(ctx, ctx->sedQ.p, ctx->sedQ.n, kNcclUint64, kNcclSum);
+        if (rc) return rc;
+    }
+    for (size_t ig = 0; ig < ctx->grids.size(); ++ig) {
+        GridState &g = ctx->grids[ig];
+        if (!g.set || !g.JsteQ.p) continue;
+        const size_t nR = (size_t)g.nCells + 1;
+        // which nu-planes did any rank touch
+        int rc = comm_allreduce(ctx, g.nuTouched.p, g.nuTouched.n, kNcclInt32, kNcclMax);
+        if (rc) return rc;
+        std::vector<int> flag(nb + 1, 0);
+        CU(cudaMemcpyAsync(flag.data(), g.nuTouched.p, sizeof(int) * (nb + 1), cudaMemcpyDeviceToHost, s));
+        CU(cudaStreamSynchronize(s));
+        auto ranges = touched_ranges(flag);
+        for (auto &rg : ranges) {
+            int p0 = rg.first < 1 ? 1 : rg.first, p1 = rg.second;
+            if (p1 < p0) continue;
+            size_t off = (size_t)(p0 - 1) * nR, len = (size_t)(p1 - p0 + 1) * nR;
+            rc = comm_allreduce(ctx, g.JsteQ.p + off, len, kNcclUint64, kNcclSum);
+            if (rc) return rc;
+            if (ctx->cfg.lgDebug && g.JdifQ.p) {
+                rc = comm_allreduce(ctx, g.JdifQ.p + off, len, kNcclUint64, kNcclSum);
+                if (rc) return rc;
+            }
+        }
+        if (ctx->cfg.lgDebug && g.lineQ.n) {
+            rc = comm_allreduce(ctx, g.lineQ.p, g.lineQ.n, kNcclUint32, kNcclSum);
+            if (rc) return rc;
+        }
+        if (!ctx->sedLocal) {
+            rc = comm_exchange_escaped(ctx, g, ranges);
+            if (rc) return rc;
+        }
+        if (ig == 0 && ctx->cfg.lgPlaneIonization && ctx->planeDist.n) {
+            rc = comm_allreduce(ctx, ctx->planeDist.p, ctx->planeDist.n, kNcclInt32, kNcclSum);
+            if (rc) return rc;
+        }
+    }
+    CU(cudaStreamSynchronize(s));
+    return MCB200_OK;
 }
 
 }  // namespace
@@ -902,6 +1118,7 @@ int mcb200_destroy(mcb200_ctx *ctx)
     if (ctx->pdfReady) cudaEventDestroy(ctx->pdfReady);
     if (ctx->copyStream) { cudaStreamSynchronize(ctx->copyStream); cudaStreamDestroy(ctx->copyStream); }
     if (ctx->sparseHost) cudaFreeHost(ctx->sparseHost);
+    if (ctx->comm) { nccl_api().CommDestroy(ctx->comm); ctx->comm = nullptr; }
     ctx->grids.clear();
     cudaStream_t s = ctx->stream;
     delete ctx;
@@ -1466,45 +1683,88 @@ int mcb200_reduce_range(mcb200_ctx *ctx, int32_t iG, int32_t nu0, int32_t nu1)
     return MCB200_OK;
 }
 
+int mcb200_comm_unique_id(mcb200_ctx *ctx, void *id128)
+{
+    NEED_CTX();
+    if (!id128) return fail(ctx, MCB200_EINVAL, "null id buffer");
+    NcclApi &N = nccl_api();
+    if (!N.handle) return fail(ctx, MCB200_ECOMM, "NCCL unavailable: %s", N.why.c_str());
+    NcclId id;
+    NC(N.GetUniqueId(&id));
+    std::memcpy(id128, id.internal, sizeof(id.internal));
+    return MCB200_OK;
+}
+
+int mcb200_comm_init(mcb200_ctx *ctx, const void *id128)
+{
+    NEED_CTX();
+    if (!id128) return fail(ctx, MCB200_EINVAL, "null id buffer");
+    if (ctx->comm) return fail(ctx, MCB200_ESTATE, "communicator already initialised");
+    NcclApi &N = nccl_api();
+    if (!N.handle) return fail(ctx, MCB200_ECOMM, "NCCL unavailable: %s", N.why.c_str());
+    NcclId id;
+    std::memcpy(id.internal, id128, sizeof(id.internal));
+    NC(N.CommInitRank(&ctx->comm, ctx->nranks, id, ctx->rank));
+    return MCB200_OK;
+}
+
+int mcb200_comm_destroy(mcb200_ctx *ctx)
+{
+    NEED_CTX();
+    if (!ctx->comm) return MCB200_OK;
+    CU(cudaStreamSynchronize(ctx->stream));
+    NC(nccl_api().CommDestroy(ctx->comm));
+    ctx->comm = nullptr;
+    return MCB200_OK;
+}
+
+int mcb200_exchange(mcb200_ctx *ctx)
+{
+    NEED_CTX();
+    if (!ctx->haveCfg) return fail(ctx, MCB200_ESTATE, "set_config first");
+    if (!ctx->pending || (ctx->nranks == 1 && !ctx->comm)) return MCB200_OK;
+    if (!ctx->comm) return fail(ctx, MCB200_ESTATE, "no communicator: call mcb200_comm_init (or all-reduce the buffers of mcb200_tally_buffer yourself)");
+    return comm_exchange(ctx);
+}
+
+int mcb200_nccl_info(int32_t *version, char *path, int64_t pathLen)
+{
+    NcclApi &N = nccl_api();
+    if (version) *version = 0;
+    if (path && pathLen > 0) path[0] = 0;
+    if (!N.handle) return MCB200_ECOMM;
+    int v = 0;
+    if (N.GetVersion(&v) != 0) return MCB200_ECOMM;
+    if (version) *version = v;
+    Dl_info di;
+    if (path && pathLen > 0 && dladdr(reinterpret_cast<void *>(N.GetVersion), &di) && di.dli_fname) {
+        std::strncpy(path, di.dli_fname, (size_t)pathLen - 1);
+        path[pathLen - 1] = 0;
+    }
+    return MCB200_OK;
+}
+
+int mcb200_exchange_info(mcb200_ctx *ctx, int64_t *bytesSent, int32_t *sparseGrids, int32_t *ncclVersion)
+{
+    NEED_CTX();
+    if (bytesSent) *bytesSent = ctx->lastExchangeBytes;
+    if (sparseGrids) *sparseGrids = ctx->lastExchangeSparse;
+    if (ncclVersion) {
+        *ncclVersion = 0;
+        NcclApi &N = nccl_api();
+        if (N.handle && N.GetVersion) { int v = 0; if (N.GetVersion(&v) == 0) *ncclVersion = v; }
+    }
+    return MCB200_OK;
+}
+
 int mcb200_escaped_compact(mcb200_ctx *ctx, int32_t iG, int32_t set, void **devList, int64_t *nEntries)
 {
     NEED_CTX();
     GridState *g = grid_of(ctx, iG);
     if (!g || !g->set || !devList || !nEntries) return fail(ctx, MCB200_EINVAL, "bad escaped_compact arguments");
     if (!ctx->pending) return fail(ctx, MCB200_ESTATE, "no pending tallies");
-    unsigned int *Q = set == 1 ? g->escQ2.p : g->escQ.p;
-    const int *touched = set == 1 ? g->nuTouched2.p : g->nuTouched.p;
-    if (!Q) return fail(ctx, MCB200_ESTATE, "tally set %d not allocated", set);
-    const int nb = ctx->cfg.nbins;
-    const size_t nR = (size_t)g->nCells + 1;
-    cudaStream_t s = ctx->stream;
-    std::vector<int> flag(nb + 1, 1);
-    if (touched) {
-        CU(cudaMemcpyAsync(flag.data(), touched, sizeof(int) * (nb + 1), cudaMemcpyDeviceToHost, s));
-        CU(cudaStreamSynchronize(s));
-    }
-    auto ranges = touched_ranges(flag);
-    const int blocks = ctx->numSMs * 8;
-    CU(ctx->escCount.alloc(1));
-    // pass 1: count; pass 2: fill and clear (the scatter of every rank's list rebuilds the sum)
-    for (int pass = 0; pass < 2; ++pass) {
-        CU(ctx->escCount.zero(s));
-        unsigned long long cap = pass ? ctx->escList.n / 2 : 0;
-        for (auto &rg : ranges)
-            for (int ang = 0; ang <= ctx->cfg.nAngleBins; ++ang) {
-                size_t off = nR * ((size_t)rg.first + (size_t)(nb + 1) * (size_t)ang);
-                size_t len = (size_t)(rg.second - rg.first + 1) * nR;
-                CU(launch_esc_compact(Q, off, len, pass ? ctx->escList.p : nullptr, ctx->escCount.p, cap, pass, blocks, s));
-            }
-        unsigned long long n = 0;
-        CU(cudaMemcpyAsync(&n, ctx->escCount.p, 8, cudaMemcpyDeviceToHost, s));
-        CU(cudaStreamSynchronize(s));
-        if (!pass) {
-            if (ctx->escList.n < 2 * n || ctx->escList.n > 8 * n + 1024) CU(ctx->escList.alloc((size_t)(2 * n > 2 ? 2 * n : 2)));
-        } else {
-            *nEntries = (int64_t)n;
-        }
-    }
+    int rc = esc_compact(ctx, *g, set, nEntries);
+    if (rc) return rc;
     *devList = ctx->escList.p;
     return MCB200_OK;
 }
@@ -1822,6 +2082,8 @@ int mcb200_set_option(mcb200_ctx *ctx, const char *name, int64_t value)
         if (value < 0 || value >= ctx->partCount) return fail(ctx, MCB200_EINVAL, "part out of range");
         ctx->partIndex = (int)value; return MCB200_OK;
     }
+    if (!strcmp(name, "exchange_dense")) { ctx->exchangeDense = value != 0; return MCB200_OK; }
+    if (!strcmp(name, "defer_fold")) { ctx->deferFold = value != 0; return MCB200_OK; }
     if (!strcmp(name, "agg_steps")) { ctx->aggSteps = (int)value; return MCB200_OK; }
     if (!strcmp(name, "batch")) { ctx->batch = (int)value; return MCB200_OK; }
     return fail(ctx, MCB200_EINVAL, "unknown option %s", name);

@@ -66,6 +66,27 @@ def test_fortran_binding_covers_the_header():
     exported = set(re.findall(r"^(?:int|const char \*)\s*(mcb200_\w+)\s*\(", hdr, flags=re.M))
     bound = set(re.findall(r'name="(mcb200_\w+)"', f90))
     diagnostic = {"mcb200_fetch_fates", "mcb200_fetch_tallies", "mcb200_test_access_peak", "mcb200_test_detmath",
-                  "mcb200_test_uniforms"}
+                  "mcb200_test_uniforms", "mcb200_nccl_info"}
     assert exported - bound == diagnostic, sorted(exported - bound - diagnostic)
     assert bound <= exported, sorted(bound - exported)
+
+
+def test_nccl_is_bound_at_run_time_not_link_time(cuda_lib):
+    """No DT_NEEDED on NCCL (single-rank hosts never load it); mcb200_nccl_info binds it on demand."""
+    from mocassin_b200 import _lib
+
+    out = subprocess.run(["readelf", "-d", _lib.LIB_PATH], capture_output=True, text=True).stdout
+    assert "nccl" not in out.lower()
+    version, path = _lib.nccl_info()
+    assert version >= 22000 and os.path.exists(path), (version, path)
+
+
+def test_bound_nccl_is_the_one_torch_loads():
+    """One object per SONAME and process: the library must bind the copy torch brings, or a later
+    `import torch` is served an older system libnccl and dies on a missing symbol (seen on the GPU
+    box).  Fresh interpreter: library first, torch second."""
+    code = ("from mocassin_b200 import _lib; v, p = _lib.nccl_info(); import torch; "
+            "t = torch.cuda.nccl.version(); assert v == t[0] * 10000 + t[1] * 100 + t[2], (v, t); print('ok', p)")
+    env = {k: v for k, v in os.environ.items() if k != "MCB200_NCCL_LIB"}
+    res = subprocess.run([os.sys.executable, "-c", code], capture_output=True, text=True, cwd=ROOT, env=env)
+    assert res.returncode == 0 and "ok" in res.stdout, res.stderr[-600:]

@@ -1,0 +1,154 @@
+"""The library's own NCCL exchange (mcb200_comm_init / mcb200_exchange): what a Fortran/MPI
+host calls in place of the MPI_ALLREDUCE block iteration_mod.f90:564,627,649,653,659.
+
+One GPU: a one-rank communicator with option defer_fold walks the whole exchange path
+(dlopen of NCCL, flag max-reduce, plane all-reduces, compact -> all-gather -> scatter of the
+escape counts, dense variant, sed_local) and must leave every estimator bit-identical to the
+run that folded immediately.  Two GPUs (skipped otherwise): two processes bootstrap the
+communicator from the 128 id bytes alone (a file stands in for MPI_BCAST; no torch.distributed)
+and must reproduce the single-GPU result bit for bit on both ranks."""
+import os
+import sys
+import tempfile
+import time
+
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+
+
+def _want(m):
+    return ["Jste", "escapedPackets"] + (["Jdif", "linePackets"] if m.lgDebug else [])
+
+
+def _run(name, n, native, dense=False, sed_local=False):
+    from cases import make
+    from mocassin_b200.api import PacketEngine
+
+    m, _ = make(name)
+    e = PacketEngine(m, seed=12345)
+    e.upload_iteration_inputs()
+    if native:
+        e.set_option("defer_fold", 1)
+        e.set_option("exchange_dense", 1 if dense else 0)
+        e.comm_init(e.comm_unique_id())
+    if sed_local:
+        e.set_sed_local(True)
+    cnt = e.lucy_transport([n] * m.nStars)
+    out = [e.fetch(iG, want=_want(m)) for iG in range(1, m.nGrids + 1)]
+    sed = e.fetch_sed()
+    plane = e.plane_distribution() if m.lgPlaneIonization else None
+    info = getattr(e, "last_exchange", None)
+    e.close()
+    return out, sed, plane, info, cnt
+
+
+@pytest.mark.parametrize("name,dense", [("multigrid_sym", False), ("multigrid_sym", True), ("cube_clumpy_gasdust", False),
+                                        ("hii_sym_gas_debug", False), ("viewing_angles", False),
+                                        ("plane_slab_gasdust", False)])
+def test_one_rank_exchange_is_the_identity(cuda_lib, name, dense):
+    from cases import make
+
+    m, _ = make(name)
+    n = 20001
+    ref, sed0, plane0, _, c0 = _run(name, n, native=False)
+    got, sed1, plane1, info, c1 = _run(name, n, native=True, dense=dense)
+    assert info["nccl_version"] >= 20000, info
+    assert info["bytes"] > 0
+    assert info["sparse_grids"] == (0 if dense else m.nGrids)
+    for iG in range(m.nGrids):
+        for k in _want(m):
+            assert np.array_equal(got[iG][k].view(np.uint32), ref[iG][k].view(np.uint32)), (iG, k)
+    assert np.array_equal(sed1[0].view(np.uint32), sed0[0].view(np.uint32))
+    assert np.array_equal(sed1[1], sed0[1])
+    if plane0 is not None:
+        assert np.array_equal(plane0, plane1)
+    assert [c["nSegments"] for c in c0] == [c["nSegments"] for c in c1]
+
+
+def test_one_rank_exchange_sed_local(cuda_lib):
+    ref, sed0, _, _, _ = _run("viewing_angles", 20001, native=False)
+    got, sed1, _, info, _ = _run("viewing_angles", 20001, native=True, sed_local=True)
+    assert info["sparse_grids"] == 0            # the (nu, angle) counts travelled instead of the per-cell array
+    assert np.array_equal(got[0]["Jste"], ref[0]["Jste"])
+    assert np.array_equal(got[0]["escapedPackets"], ref[0]["escapedPackets"])    # one rank: local = global
+    assert np.array_equal(sed1[0].view(np.uint32), sed0[0].view(np.uint32))
+    assert np.array_equal(sed1[1], sed0[1])
+
+
+def test_exchange_without_communicator_is_an_error(cuda_lib):
+    from cases import make
+    from mocassin_b200.api import MocassinError, PacketEngine
+
+    m, _ = make("hii_sym_gas")
+    e = PacketEngine(m, rank=0, nranks=2, seed=12345)     # rank 0 of 2: tallies stay pending
+    e.upload_iteration_inputs()
+    e.zero_estimators()
+    e.energyPacketDriver(1, 2000)
+    with pytest.raises(MocassinError) as ei:
+        e.exchange()
+    assert "mcb200_comm_init" in str(ei.value)
+    e.close()
+
+
+def _worker(rank, world, idfile, name, n, q):
+    sys.path.insert(0, ROOT)
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    from cases import make
+    from mocassin_b200.api import PacketEngine
+
+    m, _ = make(name)
+    e = PacketEngine(m, device=rank, rank=rank, nranks=world, seed=12345)
+    e.upload_iteration_inputs()
+    if rank == 0:                                          # the host's MPI_BCAST of 128 bytes
+        with open(idfile + ".tmp", "wb") as f:
+            f.write(e.comm_unique_id())
+        os.replace(idfile + ".tmp", idfile)
+    t0 = time.time()
+    while not os.path.exists(idfile):
+        if time.time() - t0 > 120:
+            raise TimeoutError("no unique id")
+        time.sleep(0.05)
+    with open(idfile, "rb") as f:
+        e.comm_init(f.read())
+    e.lucy_transport([n] * m.nStars)
+    out = [e.fetch(iG, want=_want(m)) for iG in range(1, m.nGrids + 1)]
+    q.put((rank, out, e.last_exchange))
+    e.comm_destroy()
+    e.close()
+
+
+@pytest.mark.parametrize("name", ["multigrid_sym", "cube_clumpy_gasdust", "hii_sym_gas_debug", "viewing_angles"])
+def test_two_ranks_native_exchange_matches_single_gpu(cuda_lib, name):
+    import torch
+    import torch.multiprocessing as mp
+
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    from cases import make
+
+    m, _ = make(name)
+    n = 20001
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    with tempfile.TemporaryDirectory() as d:
+        idfile = os.path.join(d, "nccl_id")
+        procs = [ctx.Process(target=_worker, args=(r, 2, idfile, name, n, q)) for r in range(2)]
+        for p in procs:
+            p.start()
+        got = {}
+        for _ in range(2):
+            r, out, info = q.get(timeout=600)
+            got[r] = out
+            assert info["bytes"] > 0
+        for p in procs:
+            p.join(timeout=120)
+            assert p.exitcode == 0
+    ref, _, _, _, _ = _run(name, n, native=False)
+    for iG in range(m.nGrids):
+        for r in (0, 1):
+            for k in _want(m):
+                assert np.array_equal(got[r][iG][k], ref[iG][k]), (iG, r, k)
