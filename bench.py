@@ -237,9 +237,11 @@ def run_reference(args):
         "impl": "reference", "metric": "energy packets/sec", "value": value, "unit": "packets/s",
         "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": workload_config(args, sample),
+        # the same config as the b200 arm; each step here is a bounded sample of it (cpu_baseline.sample)
+        "config": workload_config(args, default_packets(args)),
         "cpu_baseline": {"value": value, "unit": "packets/s", "cores": cores, "kind": "port",
-                         "sample": f"{sample} packets/step x {args.steps} steps of the same 128^3 workload, "
+                         "sample_packets_per_step": sample,
+                         "sample": f"{sample} packets/step x {args.steps} steps of the same {args.grid}^3 workload, "
                                    f"oracle port (-O2), {cores} threads; table build {build_s:.0f}s untimed"},
         "e2e": {"value": value, "unit": "packets/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "segments_per_packet": segs / (sample * args.steps),
@@ -248,10 +250,13 @@ def run_reference(args):
 
 
 def workload_config(args, packets):
+    table_gb = (args.grid ** 3 + 1) * args.nbins * 4 / 1e9
     return {"workload": f"S-{args.workload} {args.grid}^3 gas+dust nebula, nbins={args.nbins}, star at centre, "
                         f"Philox seed {SEED}", "grid": args.grid, "nbins": args.nbins,
             "packets_per_gpu_per_step": int(packets),
-            "cache": "inputs larger than L2 (opacity/scaOpac/recPDF/Jste tables 5-10 GB each)",
+            "cache": f"inputs larger than L2: opacity/scaOpac/recPDF/Jste tables {table_gb:.2f} GB each (float32; "
+                     f"JsteQ twice that), L2 126 MB" if table_gb > 0.126 else
+                     f"tables {table_gb * 1e3:.1f} MB each: L2-resident (reduced --grid/--nbins, not the headline workload)",
             "parallelism": f"packets sharded over {args.gpus} GPU(s), grid replicated"}
 
 
