@@ -1,0 +1,67 @@
+"""One Lucy iteration of a dust-only deck (setDustPDF -> energyPacketDriver -> host scaling ->
+getDustT -> dust opacities) on the CPU oracle and on the CUDA engine, as `step` callbacks for
+mocassin_b200.deck.iterate_dust.  Test infrastructure: the product never imports this."""
+import ctypes as C
+
+import numpy as np
+
+from mocassin_b200 import deck
+from mocassin_b200.api import PacketEngine, scale_estimators
+from mocassin_b200.model import F32
+
+
+def oracle_step(model, tables, d, seed=12345, threads=1):
+    from oracle import oracle as O
+
+    g = model.grids[0]
+    state = dict(it=0, counters=[])
+
+    def step(nPhotons, deltaE):
+        state["it"] += 1
+        model.deltaE[1] = F32(deltaE)
+        g.dustPDF = O.dust_pdf(model, g, tables)
+        orc = O.Oracle(model, fp32_tallies=False)
+        # a fresh packet stream per iteration (the reference reseeds from the clock, photon_mod.f90:68-87)
+        c = orc.transport_mt(1, 0, nPhotons, seed=seed + state["it"], threads=threads)
+        f = orc.folded(1, float(model.deltaE[1]))
+        Js, _ = scale_estimators(model, f["Jste"], np.zeros((1, 1, 1), F32))
+        # iterateMC zeroes grid%lgConverged before every iteration (iteration_mod.f90:85)
+        T, conv = O.dust_update(model, g, tables, Js, d.XHILimit)
+        g.Tdust = T
+        deck.dust_opacity(g, tables)
+        state["counters"].append(c)
+        state["escaped"] = f["escapedPackets"]
+        return int(conv[1:].sum()), g.nCells
+
+    return step, state
+
+
+def engine_step(model, tables, d, seed=12345):
+    """The same iteration through the C ABI.  Tdust and the convergence flags stay on the device
+    between K5 and K6; they come back once per iteration only because the host rebuilds the
+    dust opacities from them."""
+    g = model.grids[0]
+    eng = PacketEngine(model, seed=seed)
+    eng.set_xsec(tables["xSecArray"])
+    eng.set_dust_tables(tables["widFlx"], tables["grainWeight"], tables["dustAbsXsecP"], tables["dustEmIntegral"])
+    eng.set_opacity()
+    eng.set_dust_state()
+    state = dict(it=0, counters=[], eng=eng)
+
+    def step(nPhotons, deltaE):
+        state["it"] += 1
+        model.deltaE[1] = F32(deltaE)
+        eng.set_option("seed", seed + state["it"])
+        eng.setDustPDF(1)
+        eng.zero_estimators()
+        c = eng.energyPacketDriver(1, nPhotons, deltaE=float(F32(deltaE)))
+        eng.reduce()
+        T, conv, nconv = eng.getDustT(1, d.XHILimit)
+        g.Tdust = T
+        deck.dust_opacity(g, tables)
+        eng.set_opacity()
+        eng.set_dust_state()
+        state["counters"].append(c)
+        return int(nconv), g.nCells
+
+    return step, state
