@@ -106,6 +106,15 @@ def test_shipped_1d_decks_have_their_nominal_optical_depth_and_match_the_fixture
 
 
 @live
+def test_disk_fixture_is_what_the_loader_builds():
+    m, t, d = deck.load_dust_deck(os.path.join(REF, "benchmarks", "dust", "2D", "tau1.000"), REF)
+    want = dict(np.load(os.path.join(GOLD, "deck_tau1.000.npz")))
+    got = deck.deck_to_arrays(m, t, d)
+    for k in want:
+        assert np.array_equal(np.asarray(got[k]), want[k]), k
+
+
+@live
 @pytest.mark.parametrize("name", ["tau0.100", "tau1.000", "tau10.00", "tau100.0"])
 def test_shipped_2d_disk_decks_load(name):
     m, t, d = deck.load_dust_deck(os.path.join(REF, "benchmarks", "dust", "2D", name), REF)
@@ -135,6 +144,28 @@ def test_three_lucy_iterations_of_p0tau1_on_the_oracle(oracle_lib):
     T = g.Tdust[0, 0, cells]
     assert 650.0 < T[0] < 900.0                  # benchmark: 800 K at the inner edge of the shell
     assert np.all(np.diff(T[:9]) < 0) and np.all(T[9:] < 80.0)      # outer axis cells: few packets at 1e5, noisy
+
+
+def test_disk_deck_iteration_on_the_oracle_conserves_energy_and_fills_the_viewing_angles(oracle_lib):
+    """benchmarks/dust/2D/tau1.000 (40^3 disk, two phi-free inclinations) from its fixture: one
+    iteration on the oracle; writeSED's total equals LStar, both viewing-angle columns are filled."""
+    from deck_runner import oracle_step
+    from mocassin_b200 import output
+
+    m, t, d = deck.deck_from_arrays(dict(np.load(os.path.join(GOLD, "deck_tau1.000.npz"))))
+    assert m.nAngleBins == 2 and m.grids[0].nx == 40
+    d.maxIterateMC, d.nPhotons = 1, 60000
+    m.deltaE[1] = np.float32(d.LStar) / np.float32(d.nPhotons)
+    step, st = oracle_step(m, t, d, seed=9, threads=2)
+    deck.iterate_dust(d, m, step)
+    esc = st["escaped"]
+    raw = esc[:, 1:, :].astype(np.float64).sum(axis=0).astype(np.float32)
+    sed, totalE = output.sed_from_raw(m, t["widFlx"], raw)
+    assert abs(totalE - d.LStar) < 2e-4 * d.LStar
+    assert raw[:, 1].sum() > 0 and raw[:, 2].sum() > raw[:, 1].sum()      # 12.5 deg bin is smaller than the 77 deg one
+    assert np.all(sed >= 0)
+    T = m.grids[0].Tdust[0, 0, 1:]
+    assert T.max() > 200.0 and T.min() >= 1.0
 
 
 def test_iterate_dust_follows_the_autopackets_rule():

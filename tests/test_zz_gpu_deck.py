@@ -37,3 +37,35 @@ def test_deck_lucy_loop_on_device_matches_oracle(cuda_lib, oracle_lib, name, pac
         for k in ("nAbs", "nSca", "nSegments", "nEscaped", "nDropped"):
             assert a[k] == b[k], k
     assert np.array_equal(T0[:, :, 1:].view(np.uint32), T1[:, :, 1:].view(np.uint32))
+
+
+def test_disk_deck_iteration_on_device_matches_oracle(cuda_lib, oracle_lib):
+    """benchmarks/dust/2D/tau1.000: 40^3 disk with two phi-free viewing angles.  One iteration:
+    temperatures, escapedPackets (all three angle planes) and the device SED reduction equal the
+    oracle's."""
+    from deck_runner import engine_step, oracle_step
+    from mocassin_b200 import deck
+
+    packets = 80000
+    out = {}
+    for which in ("oracle", "cuda"):
+        m, t, d = deck.deck_from_arrays(dict(np.load(os.path.join(GOLD, "deck_tau1.000.npz"))))
+        d.maxIterateMC, d.nPhotons = 1, packets
+        m.deltaE[1] = np.float32(d.LStar) / np.float32(packets)
+        step, st = (oracle_step(m, t, d, seed=31, threads=4) if which == "oracle" else engine_step(m, t, d, seed=31))
+        deck.iterate_dust(d, m, step)
+        if which == "cuda":
+            esc = st["eng"].fetch(1, want=("escapedPackets",))["escapedPackets"]
+            _, cnt = st["eng"].fetch_sed()
+            st["eng"].close()
+        else:
+            esc, cnt = st["escaped"], None
+        out[which] = (m.grids[0].Tdust.copy(), esc, cnt, st["counters"][0])
+    (T0, e0, _, c0), (T1, e1, cnt, c1) = out["oracle"], out["cuda"]
+    for k in ("nAbs", "nSca", "nSegments", "nEscaped"):
+        assert c0[k] == c1[k], k
+    assert np.array_equal(T0[:, :, 1:].view(np.uint32), T1[:, :, 1:].view(np.uint32))
+    assert np.array_equal(e0.view(np.uint32), e1.view(np.uint32))
+    dE = np.float32(m.deltaE[1])
+    want_cnt = np.rint(e0.astype(np.float64).sum(axis=0)[1:, :] / float(dE)).astype(np.int64)
+    assert np.array_equal(cnt, want_cnt)
