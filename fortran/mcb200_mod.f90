@@ -102,6 +102,11 @@ module mcb200_mod
          import; type(c_ptr), value :: ctx; integer(c_int32_t), value :: iG, which
          type(c_ptr), intent(out) :: devPtr; integer(c_int64_t), intent(out) :: count
        end function
+       ! writeContCube's frequency sum per cell and viewing angle (output_mod.f90:2762-2772):
+       ! contI(0:nCells, 0:nAngleBins), raw sums
+       integer(c_int) function mcb200_fetch_contcube(ctx, iG, contI) bind(C, name="mcb200_fetch_contcube")
+         import; type(c_ptr), value :: ctx, contI; integer(c_int32_t), value :: iG
+       end function
        integer(c_int) function mcb200_reduce(ctx) bind(C, name="mcb200_reduce")
          import; type(c_ptr), value :: ctx
        end function

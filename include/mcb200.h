@@ -320,6 +320,15 @@ int mcb200_reduce(mcb200_ctx *ctx);
  * escapedPackets then stays rank-local (only its sum over cells, the SED, is global). */
 int mcb200_fetch_sed(mcb200_ctx *ctx, float *SED, int64_t *counts);
 
+/* contI(0:nCells, 0:nAngleBins) = sum over freq = 1..nbins of escapedPackets(cell, freq, imu): the
+ * reduction inside writeContCube (output_mod.f90:2762-2772), done on the device from the folded
+ * float32 estimator in the reference's order (running float32 sum, freq ascending), so it equals
+ * the reference's loop over the array mcb200_fetch_estimators returns bit for bit -- and that array
+ * (5 GB at 128^3 x 600) need not be downloaded for output/contCube.out.  Raw sums: the host's /8 of
+ * iteration_mod.f90:719 (exact in binary) and writeContCube's /dTheta, /dPhi, /(4 Pi) and file
+ * layout stay on the host (mocassin_b200/output.py: write_cont_cube). */
+int mcb200_fetch_contcube(mcb200_ctx *ctx, int32_t iG, float *contI);
+
 /* Photo-rate pre-integration for updateCell: instead of shipping Jste
  * (5 GB at 128^3 x 600) to the host solver, integrate it on the device against each ion's
  * outer-shell cross-section.  Band b = (bandOff: 1-based index in xSecArray of the

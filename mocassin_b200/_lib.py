@@ -57,6 +57,7 @@ _SIGS = {
     "mcb200_escaped_compact": [C.c_void_p, C.c_int32, C.c_int32, C.POINTER(C.c_void_p), C.POINTER(C.c_int64)],
     "mcb200_escaped_scatter": [C.c_void_p, C.c_int32, C.c_int32, C.c_void_p, C.c_int64],
     "mcb200_fetch_sed": [C.c_void_p, c_float_p, C.POINTER(C.c_int64)],
+    "mcb200_fetch_contcube": [C.c_void_p, C.c_int32, c_float_p],
     "mcb200_zero_estimators": [C.c_void_p],
     "mcb200_transport": [C.c_void_p, C.c_int32, C.c_int64, C.c_float, C.POINTER(Counters)],
     "mcb200_transport_diffuse": [C.c_void_p, C.c_int32, c_int32_p, C.c_int64, C.c_float, C.POINTER(Counters)],

@@ -413,6 +413,14 @@ class PacketEngine:
         self._check(self.lib.mcb200_fetch_sed(self.h, _fp(sed), cnt.ctypes.data_as(C.POINTER(C.c_int64))))
         return sed, cnt
 
+    def fetch_contcube(self, iG: int = 1) -> np.ndarray:
+        """(nCells+1, nAngleBins+1): sum over the frequency bins of escapedPackets per cell and
+        viewing angle (the reduction of writeContCube, output_mod.f90:2762-2772), raw sums."""
+        g = self.model.grids[iG - 1]
+        out = np.zeros((g.nCells + 1, self.model.nAngleBins + 1), dtype=F32, order="F")
+        self._check(self.lib.mcb200_fetch_contcube(self.h, iG, _fp(out)))
+        return out
+
     def _exchange_pipelined(self, group=None) -> bool:
         """Exchange with the fold hidden behind it: the escape counts go first (sparse), then
         the touched JsteQ planes are all-reduced in chunks on NCCL's stream and every chunk is

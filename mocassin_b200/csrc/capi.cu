@@ -64,6 +64,7 @@ cudaError_t launch_esc_scatter(unsigned int *Q, size_t total, const unsigned lon
                                int blocks, cudaStream_t s);
 cudaError_t launch_sed_sum(const unsigned int *escQ, size_t nR, int firstPlane, int nPlanes,
                            unsigned long long *sedQ, cudaStream_t s);
+cudaError_t launch_contcube(const float *esc, size_t nR, int nb, int nAngles, float *out, cudaStream_t s);
 }  // namespace mcb
 
 using namespace mcb;
@@ -109,6 +110,7 @@ struct GridState {
     DevBuf<float> xAxis, yAxis, zAxis, xWall, yWall, zWall;
     DevBuf<int> active;
     DevBuf<float> opacity, scaOpac, absOpac, pdfT, totalLines, linePDF, dV, stage;
+    DevBuf<float> contI;                  // mcb200_fetch_contcube: (0:nCells, 0:nAngleBins)
     DevBuf<unsigned char> canScatter;
     DevBuf<unsigned long long> JsteQ, JdifQ;
     DevBuf<unsigned int> escQ, lineQ;
@@ -1799,6 +1801,23 @@ int mcb200_fetch_sed(mcb200_ctx *ctx, float *SED, int64_t *counts)
             if (SED) SED[dst] = ctx->sed[src];
             if (counts) counts[dst] = ctx->sedCount[src];
         }
+    return MCB200_OK;
+}
+
+int mcb200_fetch_contcube(mcb200_ctx *ctx, int32_t iG, float *contI)
+{
+    NEED_CTX();
+    GridState *g = grid_of(ctx, iG);
+    if (!g || !g->set || !contI) return fail(ctx, MCB200_EINVAL, "bad fetch_contcube arguments");
+    if (ctx->pending) return fail(ctx, MCB200_ESTATE, "tallies pending: call mcb200_reduce first");
+    int rc = ensure_estimators(ctx, *g);
+    if (rc) return rc;
+    const size_t nR = (size_t)g->nCells + 1;
+    const int nA = ctx->cfg.nAngleBins + 1;
+    CU(g->contI.alloc(nR * (size_t)nA));
+    CU(launch_contcube(g->esc.p, nR, ctx->cfg.nbins, nA, g->contI.p, ctx->stream));
+    CU(cudaMemcpyAsync(contI, g->contI.p, nR * (size_t)nA * sizeof(float), cudaMemcpyDeviceToHost, ctx->stream));
+    CU(cudaStreamSynchronize(ctx->stream));
     return MCB200_OK;
 }
 

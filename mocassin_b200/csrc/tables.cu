@@ -201,6 +201,31 @@ cudaError_t launch_sed_sum(const unsigned int *escQ, size_t nR, int firstPlane, 
     return cudaGetLastError();
 }
 
+// ---------------------------------------------------------------------------------------
+// K9 continuum-cube reduction (writeContCube, output_mod.f90:2762-2772): per cell and viewing
+// angle, the folded escapedPackets summed over the frequency bins 1..nbins, in the reference's
+// order (freq ascending, float32 running sum) so the result equals its loop bit for bit.
+// One thread per cell (cell is the fast index of every (nu, angle) plane: coalesced), angle in
+// blockIdx.y.  HBM-bound: each element of escapedPackets is read once, 4 B per (cell, nu, angle).
+// ---------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) contcube_kernel(const float *__restrict__ esc, size_t nR, int nb,
+                                                       float *__restrict__ out)
+{
+    size_t cell = (size_t)blockIdx.x * 256 + threadIdx.x;
+    if (cell >= nR) return;
+    const float *p = esc + nR * (size_t)(nb + 1) * blockIdx.y + cell;     // plane nu = 0 of this angle
+    float s = 0.f;
+    for (int nu = 1; nu <= nb; ++nu) s = s + __ldg(p + nR * (size_t)nu);
+    out[nR * blockIdx.y + cell] = s;
+}
+
+cudaError_t launch_contcube(const float *esc, size_t nR, int nb, int nAngles, float *out, cudaStream_t s)
+{
+    dim3 grid((unsigned)((nR + 255) / 256), (unsigned)nAngles);
+    contcube_kernel<<<grid, 256, 0, s>>>(esc, nR, nb, out);
+    return cudaGetLastError();
+}
+
 cudaError_t launch_merge_sets(unsigned long long *J0, unsigned long long *J1, size_t nJ, unsigned int *E0,
                               unsigned int *E1, size_t nE, int *f0, int *f1, int nf, int blocks, cudaStream_t s)
 {

@@ -61,3 +61,52 @@ def write_sed(path: str, model: Model, widFlx: np.ndarray, raw: np.ndarray) -> f
         fh.write(f" dTheta:  {float(at['dTheta']):.7E}\n")
         fh.write(f" dPhi:  {float(at['dPhi']):.7E}\n")
     return totalE
+
+
+def cont_cube_from_raw(model: Model, contI_raw: np.ndarray) -> np.ndarray:
+    """contI_raw: (nCells+1, nAngleBins+1) frequency sums of escapedPackets of one grid as fetched
+    from the library (``mcb200_fetch_contcube``, before the host's /8).  Applies
+    iteration_mod.f90:719 (/8 for symmetricXYZ; exact, so it commutes with the sum) and
+    writeContCube's scaling (output_mod.f90:2774-2781)."""
+    at = model.angle_tables()
+    c = np.array(contI_raw, dtype=F32, order="F", copy=True)
+    if model.lgSymmetricXYZ:
+        c = (c / F32(8.0)).astype(F32)
+    for imu in range(1, model.nAngleBins + 1):
+        if F32(at["viewPointTheta"][imu]) > 0:
+            c[:, imu] = c[:, imu] / F32(at["dTheta"])
+        if F32(at["viewPointPhi"][imu]) > 0:
+            c[:, imu] = c[:, imu] / F32(at["dPhi"])
+    c[:, 0] = c[:, 0] / F32(F32(4.0) * PI)
+    return c
+
+
+def cont_cube_records(model: Model, contI_raw, origin=(1, 1, 1)) -> list:
+    """The records of output/contCube.out (output_mod.f90:2753-2794): for every grid point
+    ``iG ix iy iz contI(0:nAngleBins)``; zeros for inactive points except the mother-grid origin
+    cell (iOrigin, jOrigin, kOrigin), which reads row 0 of the array like the reference does."""
+    rows = []
+    for iG, (g, raw) in enumerate(zip(model.grids, contI_raw), start=1):
+        c = cont_cube_from_raw(model, raw)
+        act = np.asarray(g.active)
+        for ix in range(1, g.nx + 1):
+            for iy in range(1, g.ny + 1):
+                for iz in range(1, g.nz + 1):
+                    a = int(act[ix - 1, iy - 1, iz - 1])
+                    if a > 0 or (iG == 1 and (ix, iy, iz) == tuple(origin)):
+                        # an inactive origin cell has active = 0 (row 0); a sub-grid marker (< 0) there
+                        # would index out of bounds in the reference
+                        rows.append((iG, ix, iy, iz) + tuple(c[max(a, 0), :]))
+                    else:
+                        rows.append((iG, ix, iy, iz) + (F32(0.0),) * (model.nAngleBins + 1))
+    return rows
+
+
+def write_cont_cube(path: str, model: Model, contI_raw, origin=(1, 1, 1)) -> None:
+    """output/contCube.out; list-directed number formatting is the compiler's in the reference."""
+    with open(path, "w") as fh:
+        for r in cont_cube_records(model, contI_raw, origin):
+            fh.write(" " + " ".join(str(v) for v in r[:4]) + " " + " ".join(f"{float(v):.7E}" for v in r[4:]) + "\n")
+        fh.write("  \n")
+        fh.write(" All continuum intensities given per unit direction - must multiply column 3 by 4. Pi to obtain total "
+                 "emission over all directions.\n")

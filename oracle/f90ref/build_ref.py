@@ -81,7 +81,7 @@ AUX_SOURCES = [
     ('ionization_mod.f90', False, {'ionizationdriver', 'edensum', 'addopacity'}, None),
     ('emission_mod.f90', False, {'emissiondriver'}, {'setdustpdf'}),
     ('update_mod.f90', False, {'updatecell'}, {'getdustt'}),
-    ('output_mod.f90', False, {'writesed'}, None),
+    ('output_mod.f90', False, {'writesed', 'writecontcube'}, None),
 ]
 # Statement ranges of procedures that cannot be run as a whole (iterateMC is the entire Lucy
 # iteration, MPI included; updateCell's gas branch is the whole ionisation/thermal solver),
@@ -113,7 +113,7 @@ AUX_SLICES = [
 # oracle takes as an input (ff1), so the harness sets those arrays directly
 AUX_EXTERNS = {'boltgaunt'}
 # procedures that must translate completely, and the untranslated statements tolerated in them
-AUX_STRICT = {'writegrid': 0, 'writesed': 0, 'opacity_block': 0, 'photo_rates': 0, 'photo_heat': 0, 'getoutershell': 0, 'ionizationdriver': 0, 'edensum': 0, 'addopacity': 0, 'putopacity': 0, 'inopacity': 0, 'getflux': 0, 'locate': 0,
+AUX_STRICT = {'writegrid': 0, 'writesed': 0, 'writecontcube': 0, 'opacity_block': 0, 'photo_rates': 0, 'photo_heat': 0, 'getoutershell': 0, 'ionizationdriver': 0, 'edensum': 0, 'addopacity': 0, 'putopacity': 0, 'inopacity': 0, 'getflux': 0, 'locate': 0,
               'setdustpdf': 1,      # call qHeat (lgQHeat branch)
               'getdustt': 1}        # resLineHeating (gas + resonance-line transfer branch)
 

@@ -7,6 +7,7 @@ the f90py translation) -- TEST INFRASTRUCTURE:
 * `photo`        : lines 168-269 of updateCell (nPhotoSte/nPhotoDif per element and ion) and lines
                    1123-1234 of thermBalance (heatSte/heatDif), with getOuterShell (hydro_mod.f90).
 * `write_sed`    : `writeSED(grid)` (output_mod.f90:2508-2719); the records it writes to unit 16
+* `write_cont_cube`: `writeContCube(grid, freq1, freq2)` (output_mod.f90:2722-2806); unit 19 records
                    are captured instead of going to output/SED.out.
 * `write_grid`   : `writeGrid(grid)` (grid_mod.f90:2646-2870): the records of grid0-3.out, dustGrid.out
                    and photoSource.out, captured per unit.
@@ -241,6 +242,31 @@ class AuxReference:
         sed = np.array([[r[2 + a] for a in range(model.nAngleBins + 1)] for r in rows], np.float32)
         tot = [r for r in recs if isinstance(r[0], str) and r[0].startswith('Total energy')][0][1]
         return sed, np.float32(tot), rows
+
+    # ------------------------------------------------------------------------------------------
+    def write_cont_cube(self, model, escaped, freq1, freq2, origin=(1, 1, 1)):
+        """writeContCube(grid, freq1, freq2) (output_mod.f90:2722-2806) on host-scaled
+        escapedPackets arrays.  Returns the unit-19 records [(iG, ix, iy, iz, contI(0:nAngleBins))]."""
+        G, ref = self.G, self.ref
+        at = model.angle_tables()
+        G.nbins, G.ngrids, G.nanglebins = int(model.nbins), int(model.nGrids), int(model.nAngleBins)
+        G.dtheta, G.dphi = np.float32(at['dTheta']), np.float32(at['dPhi'])
+        G.viewpointtheta = rt.wrap(_F(at['viewPointTheta'], np.float32), (0,))
+        G.viewpointphi = rt.wrap(_F(at['viewPointPhi'], np.float32), (0,))
+        G.nuarray = rt.wrap(_F(model.nuArray, np.float32))
+        G.iorigin, G.jorigin, G.korigin = (int(v) for v in origin)
+        grids = np.empty(model.nGrids, dtype=object)
+        for i, (g, e) in enumerate(zip(model.grids, escaped)):
+            t = ref.T_grid_type()
+            t.nx, t.ny, t.nz, t.ncells = g.nx, g.ny, g.nz, int(g.nCells)
+            t.active = rt.wrap(_F(g.active, np.int32))
+            t.escapedpackets = rt.wrap(_F(e, np.float32), (0, 0, 0))
+            grids[i] = t
+        rt.io_log.clear()
+        with np.errstate(all='ignore'):
+            ref.p_writecontcube(rt.wrap(grids), np.float32(freq1), np.float32(freq2))
+        recs = rt.io_log.get(19, [])
+        return [r for r in recs if len(r) == model.nAngleBins + 5 and not isinstance(r[0], str)]
 
     # ------------------------------------------------------------------------------------------
     def write_grid(self, model, rp, state):

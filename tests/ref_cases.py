@@ -384,6 +384,37 @@ def run_reference_sed(name):
 
 
 # ---------------------------------------------------------------------------------------------
+# writeContCube (K9 + the host scaling of mocassin_b200/output.py)
+# ---------------------------------------------------------------------------------------------
+def contcube_inputs(name):
+    """model, the reference's escapedPackets per grid (transport golden file), `raws` = per grid the
+    sequential float32 sum over freq = 1..nbins (the order writeContCube adds in), and an origin
+    cell: an inactive mother-grid cell where there is one (the reference then reads row 0)"""
+    m, wid, esc, _ = sed_inputs(name)
+    raws = []
+    for e in esc:
+        c = np.zeros((e.shape[0], e.shape[2]), np.float32)
+        for f in range(1, m.nbins + 1):
+            c = (c + e[:, f, :]).astype(np.float32)
+        raws.append(c)
+    z = np.argwhere(np.asarray(m.grids[0].active) == 0)
+    origin = tuple(int(v) + 1 for v in z[0]) if len(z) else (1, 1, 1)
+    return m, esc, raws, origin
+
+
+def run_reference_contcube(name):
+    from oracle import oracle as O
+    from oracle.f90ref.harness_aux import AuxReference
+
+    m, esc, raws, origin = contcube_inputs(name)
+    scaled = [(e / np.float32(8.0)).astype(np.float32) if m.lgSymmetricXYZ else e for e in esc]
+    rows = AuxReference(O.load(), math="libm").write_cont_cube(m, scaled, 1.0, 10.0, origin=origin)
+    idx = np.array([[int(v) for v in r[:4]] for r in rows], np.int32)
+    val = np.array([np.asarray(r[4:], np.float32).ravel() for r in rows], np.float32)
+    return dict(index=idx, contI=val, origin=np.array(origin, np.int32))
+
+
+# ---------------------------------------------------------------------------------------------
 # writeGrid: the checkpoint files grid0-3.out, dustGrid.out, photoSource.out
 # ---------------------------------------------------------------------------------------------
 GRID_FILES = {21: "grid0.out", 20: "grid1.out", 30: "grid2.out", 40: "grid3.out", 50: "dustGrid.out", 42: "photoSource.out"}

@@ -213,6 +213,37 @@ def test_translated_writesed_reproduces_golden(oracle_lib):
         assert np.array_equal(_bits(np.asarray(got[k])), _bits(w)), k
 
 
+@pytest.mark.parametrize("name", ref_cases.SED_CASES)
+def test_contcube_matches_reference_writecontcube(name, tmp_path):
+    """mocassin_b200/output.py (the host part of writeContCube that follows the device reduction K9)
+    against the records the reference's own writeContCube writes (output_mod.f90:2722-2806, unit 19
+    captured): same records, same order, bit-equal values -- including the mother-grid origin cell,
+    which the reference reads from row 0 of escapedPackets when it is inactive."""
+    from mocassin_b200 import output
+
+    want = dict(np.load(os.path.join(GOLD, f"ref_aux_contcube_{name}.npz")))
+    m, esc, raws, origin = ref_cases.contcube_inputs(name)
+    assert tuple(want["origin"]) == origin
+    rows = output.cont_cube_records(m, raws, origin)
+    assert np.array_equal(np.array([r[:4] for r in rows], np.int32), want["index"])
+    got = np.array([r[4:] for r in rows], np.float32)
+    assert np.array_equal(_bits(got), _bits(want["contI"]))
+    assert np.count_nonzero(got[:, 0]) > 50
+    output.write_cont_cube(str(tmp_path / "contCube.out"), m, raws, origin)
+    lines = open(tmp_path / "contCube.out").read().splitlines()
+    assert len(lines) == len(rows) + 2 and lines[-1].startswith(" All continuum intensities")
+    back = np.array([[float(x) for x in ln.split()[4:]] for ln in lines[:len(rows)]], np.float32)
+    assert np.allclose(back, got, rtol=1e-6, atol=0)
+
+
+@pytest.mark.skipif(not HAVE_REF, reason="reference sources not present")
+def test_translated_writecontcube_reproduces_golden(oracle_lib):
+    want = dict(np.load(os.path.join(GOLD, "ref_aux_contcube_multigrid_sym.npz")))
+    got = ref_cases.run_reference_contcube("multigrid_sym")
+    for k, w in want.items():
+        assert np.array_equal(np.asarray(got[k]), w) if k != "contI" else np.array_equal(_bits(got[k]), _bits(w)), k
+
+
 def test_checkpoint_writers_match_reference_writegrid(tmp_path):
     """mocassin_b200/checkpoint.py against the records the reference's own writeGrid writes
     (grid_mod.f90:2646-2870): same records, same order, same values, in all six files."""

@@ -69,3 +69,27 @@ def test_disk_deck_iteration_on_device_matches_oracle(cuda_lib, oracle_lib):
     dE = np.float32(m.deltaE[1])
     want_cnt = np.rint(e0.astype(np.float64).sum(axis=0)[1:, :] / float(dE)).astype(np.int64)
     assert np.array_equal(cnt, want_cnt)
+
+
+@pytest.mark.parametrize("name", ["viewing_angles", "multigrid_sym", "hii_sym_gas"])
+def test_device_contcube_equals_frequency_sum_of_fetched_escaped_packets(cuda_lib, name):
+    """K9 (contcube_kernel): per cell and viewing angle the float32 running sum over freq = 1..nbins
+    of the folded escapedPackets -- the loop of writeContCube (output_mod.f90:2762-2772) -- equals
+    the same loop done on the host over the array mcb200_fetch_estimators returns, bit for bit."""
+    from cases import make
+    from mocassin_b200.api import PacketEngine
+
+    m, n = make(name)
+    e = PacketEngine(m, seed=12345)
+    e.upload_iteration_inputs()
+    e.lucy_transport([n] * m.nStars)
+    for iG in range(1, m.nGrids + 1):
+        esc = e.fetch(iG, want=("escapedPackets",))["escapedPackets"]
+        want = np.zeros((esc.shape[0], esc.shape[2]), np.float32)
+        for f in range(1, m.nbins + 1):
+            want = (want + esc[:, f, :]).astype(np.float32)
+        got = e.fetch_contcube(iG)
+        assert got.shape == want.shape
+        assert np.array_equal(got.view(np.uint32), want.view(np.uint32)), iG
+        assert np.count_nonzero(got) > 0
+    e.close()
