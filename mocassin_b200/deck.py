@@ -19,8 +19,9 @@ section 8d: "decks as shipped"), restated from
 
 The Fortran host keeps doing all of this itself in a drop-in build; this module exists so that
 the shipped decks can be run through the C ABI (and through the CPU oracle) without a Fortran
-compiler.  BHmie cannot be run through the Fortran translator (COMPLEX is outside its subset):
-it is checked against an independent Mie series instead (tests/test_deck.py).
+compiler.  BHmie, getQs, linearMap and the assembly tail of makeDustXsec are bit-equal to the
+reference's own code run through the Fortran translator (tests/test_reference_pin.py); BHmie is
+also checked against an independent Mie series (tests/test_deck.py).
 """
 from __future__ import annotations
 
@@ -385,15 +386,12 @@ def get_qs(Ere: np.ndarray, Eim: np.ndarray, radius: np.ndarray, nu: np.ndarray,
     return Qa, Qs, G
 
 
-def make_dust_xsec(species, radius, weight, nu, share_dir: str, scattering: bool = True):
-    """makeDustXsec for ONE dust component of `nk` species (ph_mod.f90:808-1544).  Returns the
-    dust part of xSecArray in the reference's layout -- [CTsca, CTabs, then Csca, Cabs per
-    (species, size)], cross-sections in cm^2 -- with the 1-based pointer tables
-    dustScaXsecP/dustAbsXsecP(0:nSpecies, nSizes), gSca, grainAbun, TdustSublime, labels."""
+def dust_efficiencies(species, radius, nu, share_dir: str, scattering: bool = True):
+    """n,k files -> Qsca, Qabs, <cos> (nSpecies, nSizes, nbins) on the frequency mesh, plus the
+    abundances, sublimation temperatures and labels (ph_mod.f90:1063-1201)."""
     nb, nSp, nSz = nu.shape[0], len(species), radius.shape[0]
-    PI = F32(3.141592654)
-    Csca = np.zeros((nSp, nSz, nb), dtype=F32)
-    Cabs = np.zeros((nSp, nSz, nb), dtype=F32)
+    Qsca = np.zeros((nSp, nSz, nb), dtype=F32)
+    Qabs = np.zeros((nSp, nSz, nb), dtype=F32)
     gCos = np.zeros((nSp, nSz, nb), dtype=F32)
     abun = np.zeros(nSp, dtype=F32)
     Tsub = np.zeros(nSp, dtype=F32)
@@ -406,12 +404,32 @@ def make_dust_xsec(species, radius, weight, nu, share_dir: str, scattering: bool
         e = (C_LIGHT / (wav * FR1RYD * F32(1.0e-4))).astype(F32)[::-1].copy()
         Ere = linear_map(n_re[::-1].copy(), e, nu)
         Eim = linear_map(k_im[::-1].copy(), e, nu)
-        Qa, Qs, G = get_qs(Ere, Eim, radius, nu, scattering)
+        Qabs[s], Qsca[s], gCos[s] = get_qs(Ere, Eim, radius, nu, scattering)
+    return Qsca, Qabs, gCos, abun, Tsub, labels
+
+
+def make_dust_xsec(species, radius, weight, nu, share_dir: str, scattering: bool = True):
+    """makeDustXsec for ONE dust component of `nk` species (ph_mod.f90:808-1544).  Returns the
+    dust part of xSecArray in the reference's layout -- [CTsca, CTabs, then Csca, Cabs per
+    (species, size)], cross-sections in cm^2 -- with the 1-based pointer tables
+    dustScaXsecP/dustAbsXsecP(0:nSpecies, nSizes), gSca, grainAbun, TdustSublime, labels."""
+    Qsca, Qabs, gCos, abun, Tsub, labels = dust_efficiencies(species, radius, nu, share_dir, scattering)
+    out = assemble_dust_xsec(Qsca, Qabs, gCos, radius, weight, abun)
+    out.update(grainAbun=abun, TdustSublime=Tsub, grainLabel=labels)
+    return out
+
+
+def assemble_dust_xsec(Qsca, Qabs, gCos, radius, weight, abun):
+    """The tail of makeDustXsec's component loop (ph_mod.f90:1456-1538), same operation order."""
+    nSp, nSz, nb = Qsca.shape
+    PI = F32(3.141592654)
+    Csca = np.zeros((nSp, nSz, nb), dtype=F32)
+    Cabs = np.zeros((nSp, nSz, nb), dtype=F32)
+    for s in range(nSp):
         for ai in range(nSz):
-            # ((Q*Pi)*a)*a*1e-8, left to right (:1452-1453)
-            Csca[s, ai] = (((Qs[ai] * PI).astype(F32) * radius[ai]).astype(F32) * radius[ai]).astype(F32) * F32(1.0e-8)
-            Cabs[s, ai] = (((Qa[ai] * PI).astype(F32) * radius[ai]).astype(F32) * radius[ai]).astype(F32) * F32(1.0e-8)
-        gCos[s] = G
+            # ((Q*Pi)*a)*a*1e-8, left to right (:1460-1461)
+            Csca[s, ai] = (((Qsca[s, ai] * PI).astype(F32) * radius[ai]).astype(F32) * radius[ai]).astype(F32) * F32(1.0e-8)
+            Cabs[s, ai] = (((Qabs[s, ai] * PI).astype(F32) * radius[ai]).astype(F32) * radius[ai]).astype(F32) * F32(1.0e-8)
     CTsca = np.zeros(nb, dtype=F32)
     CTabs = np.zeros(nb, dtype=F32)
     for s in range(nSp):
@@ -428,7 +446,12 @@ def make_dust_xsec(species, radius, weight, nu, share_dir: str, scattering: bool
         for ai in range(nSz):
             scaP[s + 1, ai] = 1 + nn * nb; blocks.append(Csca[s, ai]); nn += 1
             absP[s + 1, ai] = 1 + nn * nb; blocks.append(Cabs[s, ai]); nn += 1
-    xSec = np.concatenate(blocks).astype(F32)
+    # xSecTop advances by 2*nbins*(nSpecies+1)*nSizes (:1507), more than the 2+2*nSpecies*nSizes
+    # blocks written when nSizes > 1: the tail stays zero, the next component would start after it
+    xSecTop = 2 * nb * (nSp + 1) * nSz
+    xSec = np.zeros(xSecTop, dtype=F32)
+    flat = np.concatenate(blocks).astype(F32)
+    xSec[:flat.shape[0]] = flat
     gS = np.zeros(nb, dtype=F32)
     norm = np.zeros(nb, dtype=F32)
     for s in range(nSp):
@@ -438,8 +461,7 @@ def make_dust_xsec(species, radius, weight, nu, share_dir: str, scattering: bool
                   * abun[s]).astype(F32)
             norm = (norm + F32(F32(a2 * weight[ai]) * abun[s])).astype(F32)
     gS = (gS / norm).astype(F32)
-    return dict(xSecArray=xSec, dustScaXsecP=scaP, dustAbsXsecP=absP, gSca=gS, grainAbun=abun, TdustSublime=Tsub,
-                grainLabel=labels)
+    return dict(xSecArray=xSec, dustScaXsecP=scaP, dustAbsXsecP=absP, gSca=gS)
 
 
 def dust_em_integral(xSec, absP, nu, widFlx, nTemps: int = N_TEMPS) -> np.ndarray:

@@ -70,9 +70,9 @@ PROC_HOOKS = {'energypacketrun'}             # one call per packet generation
 AUX_SOURCES = [
     ('constants_mod.f90', False, None, None),
     ('vector_mod.f90', False, set(), None),
-    ('interpolation_mod.f90', False, {'locate'}, None),
+    ('interpolation_mod.f90', False, {'locate', 'linearmap'}, None),
     ('common_mod.f90', True, None, None),
-    ('ph_mod.f90', True, None, None),            # module xSec_mod
+    ('ph_mod.f90', False, {'bhmie', 'getqs'}, None),      # module xSec_mod; BHmie (COMPLEX arithmetic, statement functions)
     ('hydro_mod.f90', False, {'getoutershell'}, None),   # module elements_mod
     ('grid_mod.f90', False, {'writegrid'}, None),
     ('composition_mod.f90', True, None, None),
@@ -87,8 +87,9 @@ AUX_SOURCES = [
 # iteration, MPI included; updateCell's gas branch is the whole ionisation/thermal solver),
 # wrapped -- with the host procedure's own declarations -- into synthetic subroutines.
 # dict(file, name, args, decls = line ranges of declarations, body = line ranges of statements,
-#      glue_decls / glue_end = the only lines that are ours: the dummies of the wrapper and the
-#      copy of a local result into them, guards = {line: expected start} against a changed file)
+#      glue_decls / glue_start / glue_end = the only lines that are ours: the dummies of the wrapper,
+#      the copy of the dummies into the host's locals, and the copy of a local result into the
+#      dummies, guards = {line: expected start} against a changed file)
 AUX_SLICES = [
     # the opacity block of iterateMC: ionizationDriver over all cells, the all-reduce, and the dust
     # contribution to scaOpac/absOpac/opacity
@@ -107,13 +108,28 @@ AUX_SLICES = [
          glue_decls=['real, intent(out) :: outste, outdif'],
          glue_end=['outste = heatste', 'outdif = heatdif'],
          guards={936: 'real, intent(out) :: heatint', 1123: 'heatste = 0.', 1234: 'end do'}),
+    # makeDustXsec: from efficiencies to cross-sections, the dust part of xSecArray, its pointer
+    # tables and gSca, for one dust component (the tail of the icomp loop)
+    dict(file='ph_mod.f90', name='dust_xsec_assembly', args='in_icomp, in_csca, in_cabs, in_gcos',
+         decls=[(810, 835)], body=[(1456, 1538)],
+         glue_decls=['integer, intent(in) :: in_icomp',
+                     'real, intent(in) :: in_csca(nspecies, 0:nsizes, nbins), in_cabs(nspecies, 0:nsizes, nbins), '
+                     'in_gcos(nspecies, 0:nsizes, nbins)'],
+         glue_start=['icomp = in_icomp',
+                     'allocate(csca(1:nspecies, 0:nsizes, 1:nbins))', 'allocate(cabs(1:nspecies, 0:nsizes, 1:nbins))',
+                     'allocate(gcos(1:nspecies, 0:nsizes, 1:nbins))', 'allocate(ctsca(1:nbins))', 'allocate(ctabs(1:nbins))',
+                     'allocate(norm(nbins))',
+                     'csca = in_csca', 'cabs = in_cabs', 'gcos = in_gcos', 'ctsca = 0.', 'ctabs = 0.'],
+         glue_end=[],
+         guards={810: 'real :: normweight', 835: 'character(len=50) :: extinctionfile', 1456: 'do i = 1, nbins',
+                 1460: 'csca(nspec,ai,i) = csca(nspec,ai,i)*pi', 1538: 'enddo'}),
 ]
 # supplied by the harness: BoltGaunt (ionization_mod.f90:134-174) fills contBoltz/gauntFF from Gaunt
 # factor tables; its only trace in the opacity is the free-free term of bin 1, which the
 # oracle takes as an input (ff1), so the harness sets those arrays directly
 AUX_EXTERNS = {'boltgaunt'}
 # procedures that must translate completely, and the untranslated statements tolerated in them
-AUX_STRICT = {'writegrid': 0, 'writesed': 0, 'writecontcube': 0, 'opacity_block': 0, 'photo_rates': 0, 'photo_heat': 0, 'getoutershell': 0, 'ionizationdriver': 0, 'edensum': 0, 'addopacity': 0, 'putopacity': 0, 'inopacity': 0, 'getflux': 0, 'locate': 0,
+AUX_STRICT = {'writegrid': 0, 'writesed': 0, 'writecontcube': 0, 'bhmie': 0, 'getqs': 0, 'dust_xsec_assembly': 0, 'opacity_block': 0, 'photo_rates': 0, 'photo_heat': 0, 'getoutershell': 0, 'ionizationdriver': 0, 'edensum': 0, 'addopacity': 0, 'putopacity': 0, 'inopacity': 0, 'getflux': 0, 'locate': 0, 'linearmap': 0,
               'setdustpdf': 1,      # call qHeat (lgQHeat branch)
               'getdustt': 1}        # resLineHeating (gas + resonance-line transfer branch)
 
@@ -171,6 +187,7 @@ def translate_aux() -> str:
         for a, b in sl['decls']:
             text += lines[a - 1:b]
         text += sl['glue_decls']
+        text += sl.get('glue_start', [])
         for a, b in sl['body']:
             text += lines[a - 1:b]
         text += sl['glue_end'] + [f'end subroutine {name}', 'end module slice_' + name]

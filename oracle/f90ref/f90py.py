@@ -487,7 +487,7 @@ class Module:
     failed: Dict[str, str] = field(default_factory=dict)      # procedures skipped by a lenient parse
 
 
-TYPE_START = re.compile(r'^(integer|real|double\s*precision|logical|character|complex|type\s*\()')
+TYPE_START = re.compile(r'^((integer|real|double\s*precision|double\s*complex|logical|character|complex)\b|type\s*\()')
 
 
 def _split_top(toks: List[Tok], sep=','):
@@ -556,17 +556,23 @@ def parse_decl(stmt: str, line: int) -> List[Decl]:
     elif t0 == 'real':
         base = 'r'
     elif t0 == 'double':
-        p.eat('precision')
-        base = 'd'
+        if p.at('complex'):
+            p.eat()
+            base = 'Z'                   # double complex
+        else:
+            p.eat('precision')
+            base = 'd'
     elif t0 == 'doubleprecision':
         base = 'd'
+    elif t0 == 'doublecomplex':
+        base = 'Z'
     elif t0 == 'logical':
         base = 'l'
     elif t0 == 'character':
         base = 'c'
         clen = 1
     elif t0 == 'complex':
-        raise TranslateError('complex not supported: ' + stmt)
+        base = 'z'                       # default (single precision) complex
     elif t0 == 'type':
         p.eat('(')
         tname = p.eat().text
@@ -621,6 +627,13 @@ def parse_decl(stmt: str, line: int) -> List[Decl]:
                     base = 'd'
                 else:
                     raise TranslateError('unsupported real kind in ' + stmt)
+            elif base == 'z':
+                if val[0] == 'num' and val[1] == '8':
+                    base = 'Z'
+                elif val[0] == 'num' and val[1] == '4':
+                    pass
+                else:
+                    raise TranslateError('unsupported complex kind in ' + stmt)
             elif base == 'i':
                 pass
     attrs = set()
@@ -1376,6 +1389,11 @@ class Gen:
         base, args = e[1], e[2]
         if base[0] == 'name':
             name = base[1]
+            sf = getattr(self, 'stmt_funcs', {}).get((sc.proc.name if sc.proc else None, name))
+            if sf is not None:
+                rty, atys = sf
+                cs = [self.conv(*self.expr(a, sc, pre), to) for a, to in zip(args, atys)]
+                return f'sf_{pyname(name)}({", ".join(cs)})', rty
             r = sc.lookup_var(name)
             if r is not None:
                 code, ty = self.name_ref(name, sc)
@@ -1495,8 +1513,23 @@ class Gen:
             for x in t[1:]:
                 b = _promote(b, x.base)
             return b
+        if name in ('abs', 'cabs', 'cdabs') and t[0].base in 'zZ':
+            return f'abs({c[0]})', Ty('r' if t[0].base == 'z' else 'd', t[0].rank)
         if name == 'abs':
             return f'abs({c[0]})', t[0]
+        if name in ('cmplx', 'dcmplx'):
+            knd = c[2] if len(pos) > 2 else (kw['kind'][0] if 'kind' in kw else None)
+            wide = name == 'dcmplx' or (knd is not None and knd.strip() == '8')
+            im = c[1] if len(pos) > 1 else '0'
+            if wide:
+                return f'_rt.c128(complex(_rt.f64({c[0]}), _rt.f64({im})))', Ty('Z')
+            if t[0].base in 'zZ':
+                return f'_rt.c64({c[0]})', Ty('z')
+            return f'_rt.c64(complex(_rt.f32({c[0]}), _rt.f32({im})))', Ty('z')
+        if name in ('imag', 'aimag', 'dimag'):
+            return f'({c[0]}).imag', Ty('r' if t[0].base == 'z' else 'd', t[0].rank)
+        if name == 'conjg':
+            return f'({c[0]}).conjugate()', t[0]
         if name in ('sqrt', 'log', 'exp', 'sin', 'cos', 'tan', 'acos', 'asin', 'atan', 'log10', 'sinh', 'cosh', 'tanh'):
             if t[0].base not in 'rd':
                 raise TranslateError(f'{name} of non-real argument')
@@ -1515,6 +1548,10 @@ class Gen:
                 knd = c[1]
             if 'kind' in kw:
                 knd = kw['kind'][0]
+            if t[0].base in 'zZ':
+                # REAL of a complex: the real part, in the kind of the argument unless a kind is given
+                wide = (knd.strip() == '8') if knd is not None else t[0].base == 'Z'
+                return (f'_rt.f64(({c[0]}).real)', Ty('d', t[0].rank)) if wide else (f'_rt.f32(({c[0]}).real)', Ty('r', t[0].rank))
             if knd is not None and knd.strip() == '8':
                 return f'_rt.f64({c[0]})', Ty('d', t[0].rank)
             return f'_rt.f32({c[0]})', Ty('r', t[0].rank)
@@ -1573,6 +1610,33 @@ class Gen:
             return f'_rt.f_isnan({c[0]})', Ty('l')
         raise TranslateError(f'unknown function or array {name!r} in {sc.proc.name if sc.proc else "<module>"}')
 
+    # ---- statement functions:  f(a, b) = expr  with f a declared scalar ----
+    def statement_function(self, s, sc: Scope, ind, out) -> bool:
+        lhs = s[2]
+        if lhs[0] != 'call' or lhs[1][0] != 'name' or sc.proc is None:
+            return False
+        name = lhs[1][1]
+        d = sc.proc.decls.get(name)
+        if d is None or d.ty.rank != 0 or d.ty.base in 'ct' or name in sc.proc.args:
+            return False
+        if not all(a[0] == 'name' for a in lhs[2]):
+            return False
+        # dummy arguments are typed by the host's declarations; the nested def shadows those locals
+        params = []
+        for a in lhs[2]:
+            r = sc.lookup_var(a[1])
+            if r is None:
+                raise TranslateError(f'statement function {name}: dummy {a[1]} undeclared')
+            params.append(r[2])
+        spre: List[str] = []
+        c, t = self.expr(s[3], sc, spre)
+        if spre:
+            raise TranslateError(f'statement function {name} needs a hoisted call')
+        self.stmt_funcs = getattr(self, 'stmt_funcs', {})
+        self.stmt_funcs[(sc.proc.name, name)] = (d.ty, [sc.lookup_var(a[1])[1].ty for a in lhs[2]])
+        self.emit(out, ind, [f'def sf_{pyname(name)}({", ".join(params)}):', f'    return {self.conv(c, t, d.ty)}'])
+        return True
+
     # ---- assignment ----
     def lvalue_ty(self, lhs, sc, pre):
         return self.expr(lhs, sc, pre)
@@ -1605,6 +1669,8 @@ class Gen:
             if fr is not None and fr.base == 'i':
                 return code
             return f'_rt.f_int({code})'
+        if to.base in 'rd' and fr is not None and fr.base in 'zZ':
+            code = f'({code}).real'      # complex -> real assignment keeps the real part
         if to.base == 'r':
             if fr is not None and fr.base == 'r' and fr.rank == 0:
                 return code
@@ -1613,6 +1679,14 @@ class Gen:
             if fr is not None and fr.base == 'd' and fr.rank == 0:
                 return code
             return f'_rt.f64({code})'
+        if to.base == 'z':
+            if fr is not None and fr.base == 'z' and fr.rank == 0:
+                return code
+            return f'_rt.c64({code})'
+        if to.base == 'Z':
+            if fr is not None and fr.base == 'Z' and fr.rank == 0:
+                return code
+            return f'_rt.c128({code})'
         if to.base == 'c':
             if to.clen is None:
                 return code
@@ -1656,7 +1730,9 @@ class Gen:
 
     def _stmt(self, s, sc, ind, out, ctx, pre):
         k, ln = s[0], s[1]
-        if k == 'assign':
+        if k == 'assign' and self.statement_function(s, sc, ind, out):
+            pass
+        elif k == 'assign':
             rc, rt_ = self.expr(s[3], sc, pre)
             lines = self.assign_lines(s[2], rc, rt_, sc, pre)
             self.emit(out, ind, pre + lines)
@@ -1907,6 +1983,10 @@ class Gen:
             return '_rt.ZERO32'
         if ty.base == 'd':
             return '_rt.ZERO64'
+        if ty.base == 'z':
+            return '_rt.c64(0)'
+        if ty.base == 'Z':
+            return '_rt.c128(0)'
         if ty.base == 'l':
             return 'False'
         if ty.base == 'c':
@@ -2183,6 +2263,10 @@ def _walk_any(x):
 
 def _promote(a, b):
     order = {'l': 0, 'i': 1, 'r': 2, 'd': 3}
+    if a in 'zZ' or b in 'zZ':
+        # mixed-mode arithmetic with a complex operand: complex of the wider real kind
+        wide = 'Z' in (a, b) or 'd' in (a, b)
+        return 'Z' if wide else 'z'
     if a not in order or b not in order:
         return a if a in order else b
     return a if order[a] >= order[b] else b

@@ -7,6 +7,7 @@ the f90py translation) -- TEST INFRASTRUCTURE:
 * `photo`        : lines 168-269 of updateCell (nPhotoSte/nPhotoDif per element and ion) and lines
                    1123-1234 of thermBalance (heatSte/heatDif), with getOuterShell (hydro_mod.f90).
 * `write_sed`    : `writeSED(grid)` (output_mod.f90:2508-2719); the records it writes to unit 16
+* `bhmie`       : `BHmie` (ph_mod.f90:1600-1757), COMPLEX arithmetic and statement functions
 * `write_cont_cube`: `writeContCube(grid, freq1, freq2)` (output_mod.f90:2722-2806); unit 19 records
                    are captured instead of going to output/SED.out.
 * `write_grid`   : `writeGrid(grid)` (grid_mod.f90:2646-2870): the records of grid0-3.out, dustGrid.out
@@ -242,6 +243,65 @@ class AuxReference:
         sed = np.array([[r[2 + a] for a in range(model.nAngleBins + 1)] for r in rows], np.float32)
         tot = [r for r in recs if isinstance(r[0], str) and r[0].startswith('Total energy')][0][1]
         return sed, np.float32(tot), rows
+
+    # ------------------------------------------------------------------------------------------
+    def bhmie(self, x, refrel):
+        """BHmie(x, refrel, qext, qsca, ggsca) (ph_mod.f90:1600-1757): Mie efficiencies of a sphere,
+        REAL size parameter and COMPLEX refractive index in, three REALs out."""
+        with np.errstate(all='ignore'):
+            qext, qsca, gg = self.ref.p_bhmie(np.float32(x), np.complex64(refrel), np.float32(0), np.float32(0),
+                                              np.float32(0))
+        return np.float32(qext), np.float32(qsca), np.float32(gg)
+
+    def get_qs(self, Ere, Eim, radius, nu, scattering=True):
+        """getQs (ph_mod.f90:1548-1586): Qabs, Qsca, <cos> as (nSizes, nbins) for optical constants
+        already mapped on the frequency mesh."""
+        G, ref = self.G, self.ref
+        nS, nb = len(radius), len(nu)
+        G.nsizes, G.nbins = int(nS), int(nb)
+        G.grainradius = rt.wrap(_F(radius, np.float32))
+        G.nuarray = rt.wrap(_F(nu, np.float32))
+        G.lgdustscattering = bool(scattering)
+        out = [rt.wrap(np.zeros((nS, nb), np.float32, order='F')) for _ in range(3)]
+        with np.errstate(all='ignore'):
+            ref.p_getqs(rt.wrap(_F(Ere, np.float32)), rt.wrap(_F(Eim, np.float32)), *out)
+        return tuple(o.a.copy() for o in out)
+
+    def dust_xsec_assembly(self, Qsca, Qabs, gCos, radius, weight, abun, nbins):
+        """The tail of makeDustXsec's component loop (ph_mod.f90:1456-1538) for ONE dust component:
+        efficiencies (nSpecies, nSizes, nbins) -> the dust part of xSecArray, dustScaXsecP /
+        dustAbsXsecP (0:nSpecies, nSizes), gSca, absOpacSpecies."""
+        G, ref = self.G, self.ref
+        nSp, nSz = Qsca.shape[0], Qsca.shape[1]
+        G.nbins, G.nsizes, G.nspecies, G.ndustcomponents = int(nbins), int(nSz), int(nSp), 1
+        G.nspeciespart = rt.wrap(np.array([nSp], np.int64))
+        G.dustcompoint = rt.wrap(np.array([1], np.int64))
+        G.grainradius = rt.wrap(_F(radius, np.float32))
+        G.grainweight = rt.wrap(_F(weight, np.float32))
+        G.grainabun = rt.wrap(_F(np.asarray(abun, np.float32).reshape(1, nSp), np.float32))
+        G.xsecarraytemp = rt.wrap(np.zeros(2 * nbins * (nSp + 1) * nSz + 8, np.float32))
+        G.xsectop = 0
+        G.dustscaxsecp = rt.wrap(np.full((nSp + 1, nSz), -1, np.int64, order='F'), (0, 1))
+        G.dustabsxsecp = rt.wrap(np.full((nSp + 1, nSz), -1, np.int64, order='F'), (0, 1))
+        G.absopacspecies = rt.wrap(np.zeros((nSp, nbins), np.float32, order='F'))
+        G.gsca = rt.wrap(np.zeros(nbins, np.float32))
+
+        def pad(q):                      # the host arrays carry an unused size index 0
+            a = np.zeros((nSp, nSz + 1, nbins), np.float32, order='F')
+            a[:, 1:, :] = q
+            return rt.wrap(a, (1, 0, 1))
+        with np.errstate(all='ignore'):
+            ref.p_dust_xsec_assembly(1, pad(Qsca), pad(Qabs), pad(gCos))
+        return dict(xSecArray=G.xsecarraytemp.a[:int(G.xsectop)].copy(), xSecTop=int(G.xsectop),
+                    dustScaXsecP=G.dustscaxsecp.a.astype(np.int32), dustAbsXsecP=G.dustabsxsecp.a.astype(np.int32),
+                    gSca=G.gsca.a.copy(), absOpacSpecies=G.absopacspecies.a.copy())
+
+    def linear_map(self, y, x, x_new):
+        """linearMap (interpolation_mod.f90:86-106)."""
+        out = rt.wrap(np.zeros(len(x_new), np.float32))
+        self.ref.p_linearmap(rt.wrap(_F(y, np.float32)), rt.wrap(_F(x, np.float32)), int(len(x)), out,
+                             rt.wrap(_F(x_new, np.float32)), int(len(x_new)))
+        return out.a.copy()
 
     # ------------------------------------------------------------------------------------------
     def write_cont_cube(self, model, escaped, freq1, freq2, origin=(1, 1, 1)):

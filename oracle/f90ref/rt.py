@@ -22,11 +22,14 @@ import numpy as np
 
 f32 = np.float32
 f64 = np.float64
+c64 = np.complex64
+c128 = np.complex128
 ZERO32 = np.float32(0.0)
 ZERO64 = np.float64(0.0)
 UNINIT_INT = 0          # value of an uninitialised integer local (processor dependent)
 QUIET = True            # drop PRINT output
-_DT = {'i': np.int64, 'r': np.float32, 'd': np.float64, 'l': np.bool_, 'c': object, 't': object}
+_DT = {'i': np.int64, 'r': np.float32, 'd': np.float64, 'l': np.bool_, 'c': object, 't': object,
+       'z': np.complex64, 'Z': np.complex128}
 
 
 class FortranStop(Exception):

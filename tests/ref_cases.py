@@ -384,6 +384,43 @@ def run_reference_sed(name):
 
 
 # ---------------------------------------------------------------------------------------------
+# dust optics of the input side (mocassin_b200/deck.py): BHmie, getQs, linearMap, makeDustXsec's assembly
+# ---------------------------------------------------------------------------------------------
+def mie_inputs():
+    """seeded (x, m) pairs for BHmie; optical constants on a 40-bin mesh, radii, weights and
+    abundances for getQs and the assembly (2 species x 3 sizes)"""
+    rng = np.random.default_rng(20261017)
+    x = np.concatenate([10 ** rng.uniform(-2.5, 2.0, 150), [100.0, 0.5, 1.0e-3]]).astype(np.float32)
+    m = (rng.uniform(0.4, 3.2, x.shape[0]) + 1j * 10 ** rng.uniform(-4.5, 0.6, x.shape[0])).astype(np.complex64)
+    nu = (10 ** np.linspace(-4.0, 1.0, 40)).astype(np.float32)
+    Ere = rng.uniform(0.6, 3.0, (2, 40)).astype(np.float32)
+    Eim = (10 ** rng.uniform(-3.0, 0.4, (2, 40))).astype(np.float32)
+    radius = np.array([0.005, 0.12, 1.5], np.float32)
+    weight = np.array([0.7, 0.25, 0.05], np.float32)
+    abun = np.array([0.6, 0.4], np.float32)
+    # a table for linearMap: descending-wavelength optical constants onto the mesh, with points
+    # outside the table on both sides
+    xt = np.sort(10 ** rng.uniform(-3.0, 0.5, 25)).astype(np.float32)
+    yt = rng.uniform(0.5, 3.0, 25).astype(np.float32)
+    return dict(x=x, m=m, nu=nu, Ere=Ere, Eim=Eim, radius=radius, weight=weight, abun=abun, xt=xt, yt=yt)
+
+
+def run_reference_mie():
+    from oracle import oracle as O
+    from oracle.f90ref.harness_aux import AuxReference
+
+    I = mie_inputs()
+    A = AuxReference(O.load(), math="libm")
+    q = np.array([A.bhmie(x, m) for x, m in zip(I["x"], I["m"])], np.float32)
+    Qa, Qs, G = (np.zeros((2, 3, 40), np.float32) for _ in range(3))
+    for s in range(2):
+        Qa[s], Qs[s], G[s] = A.get_qs(I["Ere"][s], I["Eim"][s], I["radius"], I["nu"])
+    asm = A.dust_xsec_assembly(Qs, Qa, G, I["radius"], I["weight"], I["abun"], 40)
+    return dict(bhmie=q, Qabs=Qa, Qsca=Qs, gCos=G, mapped=A.linear_map(I["yt"], I["xt"], I["nu"]),
+                **{"asm_" + k: np.asarray(v) for k, v in asm.items()})
+
+
+# ---------------------------------------------------------------------------------------------
 # writeContCube (K9 + the host scaling of mocassin_b200/output.py)
 # ---------------------------------------------------------------------------------------------
 def contcube_inputs(name):

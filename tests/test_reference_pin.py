@@ -213,6 +213,40 @@ def test_translated_writesed_reproduces_golden(oracle_lib):
         assert np.array_equal(_bits(np.asarray(got[k])), _bits(w)), k
 
 
+def test_dust_optics_match_reference_bhmie_getqs_makedustxsec():
+    """mocassin_b200/deck.py against the reference's own code run through the translator (COMPLEX
+    arithmetic, statement functions): BHmie on 153 (x, m) pairs, getQs on 2 species x 3 sizes x 40
+    bins, linearMap, and the tail of makeDustXsec (cross-sections, xSecArray layout incl. its
+    over-advanced xSecTop, pointer tables, gSca) -- all bit-equal."""
+    from mocassin_b200 import deck
+
+    want = dict(np.load(os.path.join(GOLD, "ref_aux_mie.npz")))
+    I = ref_cases.mie_inputs()
+    got = np.array([deck.bhmie(x, m) for x, m in zip(I["x"], I["m"])], np.float32)
+    assert np.array_equal(_bits(got), _bits(want["bhmie"]))
+    assert np.array_equal(_bits(deck.linear_map(I["yt"], I["xt"], I["nu"])), _bits(want["mapped"]))
+    Qa, Qs, G = (np.zeros((2, 3, 40), np.float32) for _ in range(3))
+    for s in range(2):
+        Qa[s], Qs[s], G[s] = deck.get_qs(I["Ere"][s], I["Eim"][s], I["radius"], I["nu"])
+    for k, a in (("Qabs", Qa), ("Qsca", Qs), ("gCos", G)):
+        assert np.array_equal(_bits(a), _bits(want[k])), k
+    asm = deck.assemble_dust_xsec(Qs, Qa, G, I["radius"], I["weight"], I["abun"])
+    assert asm["xSecArray"].shape[0] == int(want["asm_xSecTop"]) == 2 * 40 * 3 * 3
+    assert np.array_equal(_bits(asm["xSecArray"]), _bits(want["asm_xSecArray"]))
+    assert np.array_equal(_bits(asm["gSca"]), _bits(want["asm_gSca"]))
+    assert np.array_equal(asm["dustScaXsecP"], want["asm_dustScaXsecP"])
+    assert np.array_equal(asm["dustAbsXsecP"], want["asm_dustAbsXsecP"])
+
+
+@pytest.mark.skipif(not HAVE_REF, reason="reference sources not present")
+def test_translated_mie_reproduces_golden(oracle_lib):
+    want = dict(np.load(os.path.join(GOLD, "ref_aux_mie.npz")))
+    got = ref_cases.run_reference_mie()
+    for k, w in want.items():
+        g = np.asarray(got[k])
+        assert np.array_equal(_bits(g) if g.dtype == np.float32 else g, _bits(w) if w.dtype == np.float32 else w), k
+
+
 @pytest.mark.parametrize("name", ref_cases.SED_CASES)
 def test_contcube_matches_reference_writecontcube(name, tmp_path):
     """mocassin_b200/output.py (the host part of writeContCube that follows the device reduction K9)
@@ -454,3 +488,55 @@ def test_translator_save_write_capture_and_leniency():
     assert ns["p_partly"](np.float32(1.0))[0] == np.float32(2.0)
     with pytest.raises(NotImplementedError):
         ns["p_partly"](np.float32(500.0))
+
+
+SNIPPET3 = """
+module m3
+  implicit none
+contains
+  subroutine cx(x, m, out)
+    real, intent(in) :: x
+    complex, intent(in) :: m
+    real, intent(out) :: out(6)
+    double complex :: y, d(3), acc
+    real(kind=8) :: re8, repart, impart
+    double complex :: zz
+    integer :: rn
+    repart(zz) = real(zz)
+    impart(zz) = imag(zz)
+    y = x*m                       ! single complex product, then widened
+    rn = 3
+    d(3) = cmplx(0.0, 0.0)
+    d(2) = (rn/y) - (1./(d(3) + rn/y))
+    acc = cmplx(repart(d(2)), -impart(d(2)), 8)
+    re8 = abs(y)
+    out(1) = real(y)              ! kind of the argument (8), then stored in a REAL
+    out(2) = impart(y)
+    out(3) = re8
+    out(4) = real((2.*rn + 1.)*(abs(acc)*abs(acc)))
+    out(5) = rn/x                 ! integer / real(4): single precision division
+    out(6) = repart(acc)*impart(acc)
+  end subroutine cx
+end module m3
+"""
+
+
+def test_translator_complex_arithmetic_and_statement_functions():
+    """COMPLEX / DOUBLE COMPLEX with Fortran's mixed-mode promotion, CMPLX with a kind, REAL/IMAG/ABS
+    of complex values, and statement functions (what BHmie, ph_mod.f90:1600-1757, needs)."""
+    unit = f90py.Unit(SNIPPET3, "snippet3")
+    ns = {}
+    exec(compile(f90py.Gen(unit.modules).generate("# snippet3"), "snippet3_ref", "exec"), ns)
+    ns["init_globals"]()
+    out = rt.wrap(np.zeros(6, np.float32))
+    x, m = np.float32(1.7), np.complex64(1.5 + 0.25j)
+    ns["p_cx"](x, m, out)
+    y = np.complex128(np.complex64(x * m))
+    d2 = (3 / y) - (1.0 / (0j + 3 / y))
+    acc = np.complex128(complex(d2.real, -d2.imag))
+    want = [np.float32(y.real), np.float32(y.imag), np.float32(abs(y)),
+            np.float32(np.float64(np.float32(7.0)) * (abs(acc) * abs(acc))), np.float32(3) / x,
+            np.float32(acc.real * acc.imag)]
+    assert np.array_equal(out.a.view(np.uint32), np.array(want, np.float32).view(np.uint32))
+    # a name that merely starts with a type keyword is not a declaration
+    assert not f90py.TYPE_START.match("realpart(dpcx)=real(dpcx)") and f90py.TYPE_START.match("real(kind=8) :: a")
