@@ -284,7 +284,9 @@ int mcb200_escaped_scatter(mcb200_ctx *ctx, int32_t iG, int32_t set, const void 
  * as all-gathered sparse (index, count) lists when those are shorter than the dense planes
  * (with option "sed_local": the (nu, angle) counts of buffer 6 instead).  Integer sums: the
  * folded estimators are bit-identical on every rank and for every rank count.  A second tally
- * set (option "tally_set") is merged first.  No-op for nranks = 1 or when nothing is pending.
+ * set (option "tally_set") is merged first.  No-op for nranks = 1 or when nothing is pending;
+ * MCB200_ESTATE if the pending tallies were exchanged already, or if a transport call follows an
+ * exchange without mcb200_reduce in between (either would count the other ranks' packets twice).
  * NCCL is bound at run time (dlopen, RTLD_LOCAL, of $MCB200_NCCL_LIB, libnccl.so.2, libnccl.so): the
  * library has no link-time dependency on it; MCB200_ECOMM if it cannot be found.
  * mcb200_exchange_info: bytes this rank handed to NCCL in the last exchange, the number of

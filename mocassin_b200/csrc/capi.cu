@@ -215,6 +215,7 @@ struct mcb200_ctx {
     int64_t lastExchangeBytes = 0;        // bytes this rank handed to NCCL in the last mcb200_exchange
     int lastExchangeSparse = 0;           // grids whose escape counts went as sparse lists
     bool exchangeDense = false;           // option exchange_dense: mcb200_exchange never takes the sparse path
+    bool exchanged = false;               // the pending tallies are already global (mcb200_exchange ran)
     bool deferFold = false;               // option defer_fold: a single rank keeps its tallies pending like a multi-rank run
     // pending fold
     bool pending = false;
@@ -495,6 +496,7 @@ int fold_pending(mcb200_ctx *ctx)
     }
     CU(cudaStreamSynchronize(ctx->stream));
     ctx->pending = false;
+    ctx->exchanged = false;
     ctx->lastFoldLaunches = launches;
     return MCB200_OK;
 }
@@ -721,6 +723,8 @@ int run_transport(mcb200_ctx *ctx, int iStar, int difGrid, const int32_t *cellLo
     // reduced by the caller (multi rank)
     if (ctx->pending) {
         if (ctx->nranks == 1 && !ctx->deferFold) { int rc = fold_pending(ctx); if (rc) return rc; }
+        else if (ctx->exchanged)
+            return fail(ctx, MCB200_ESTATE, "pending tallies already exchanged over the ranks: call mcb200_reduce before the next transport");
         else if (ctx->pendingDeltaE != deltaE)
             return fail(ctx, MCB200_ESTATE, "pending tallies with a different deltaE: call mcb200_reduce first");
     }
@@ -1146,6 +1150,7 @@ int mcb200_set_config(mcb200_ctx *ctx, const mcb200_config *cfg)
     ctx->haveCfg = true;
     ctx->gridsDirty = true;
     ctx->pending = false;
+    ctx->exchanged = false;
     return MCB200_OK;
 }
 
@@ -1580,6 +1585,7 @@ int mcb200_zero_estimators(mcb200_ctx *ctx)
     CU(ctx->planeDist.zero(ctx->stream));
     CU(cudaStreamSynchronize(ctx->stream));
     ctx->pending = false;
+    ctx->exchanged = false;
     return MCB200_OK;
 }
 
@@ -1726,7 +1732,10 @@ int mcb200_exchange(mcb200_ctx *ctx)
     if (!ctx->haveCfg) return fail(ctx, MCB200_ESTATE, "set_config first");
     if (!ctx->pending || (ctx->nranks == 1 && !ctx->comm)) return MCB200_OK;
     if (!ctx->comm) return fail(ctx, MCB200_ESTATE, "no communicator: call mcb200_comm_init (or all-reduce the buffers of mcb200_tally_buffer yourself)");
-    return comm_exchange(ctx);
+    if (ctx->exchanged) return fail(ctx, MCB200_ESTATE, "pending tallies already exchanged: call mcb200_reduce");
+    int rc = comm_exchange(ctx);
+    if (rc == MCB200_OK) ctx->exchanged = true;
+    return rc;
 }
 
 int mcb200_nccl_info(int32_t *version, char *path, int64_t pathLen)

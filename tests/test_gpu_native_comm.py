@@ -152,3 +152,25 @@ def test_two_ranks_native_exchange_matches_single_gpu(cuda_lib, name):
         for r in (0, 1):
             for k in _want(m):
                 assert np.array_equal(got[r][iG][k], ref[iG][k]), (iG, r, k)
+
+
+def test_exchange_twice_or_transport_after_exchange_is_refused(cuda_lib):
+    from cases import make
+    from mocassin_b200.api import MocassinError, PacketEngine
+
+    m, _ = make("hii_sym_gas")
+    e = PacketEngine(m, seed=12345)
+    e.upload_iteration_inputs()
+    e.set_option("defer_fold", 1)
+    e.comm_init(e.comm_unique_id())
+    e.zero_estimators()
+    e.energyPacketDriver(1, 3000)
+    e.exchange()
+    with pytest.raises(MocassinError):
+        e.exchange()                         # would sum the other ranks' tallies twice
+    with pytest.raises(MocassinError):
+        e.energyPacketDriver(1, 3000)        # new tallies on top of already-global ones
+    e._check(e.lib.mcb200_reduce(e.h))
+    e.energyPacketDriver(1, 3000)            # fine again after the fold
+    e.reduce()
+    e.close()
