@@ -65,3 +65,62 @@ def engine_step(model, tables, d, seed=12345):
         return int(nconv), g.nCells
 
     return step, state
+
+
+class OracleEngine:
+    """Stand-in for mocassin_b200.api.PacketEngine backed by the CPU oracle, with just the calls
+    scripts/run_dust_deck.py makes -- lets the script's own logic (iteration loop, output files)
+    be exercised without a GPU.  Test infrastructure only."""
+
+    def __init__(self, model, seed=12345, **kw):
+        self.model, self.seed, self.tables = model, seed, {}
+        self.sed_cnt = None
+
+    def set_xsec(self, x):
+        self.tables["xSecArray"] = x
+
+    def set_dust_tables(self, widFlx, grainWeight, dustAbsXsecP, dustEmIntegral):
+        self.tables.update(widFlx=widFlx, grainWeight=grainWeight, dustAbsXsecP=dustAbsXsecP, dustEmIntegral=dustEmIntegral)
+
+    def set_opacity(self, iG=0): pass
+    def set_dust_state(self, iG=0): pass
+    def close(self): pass
+
+    def set_option(self, name, value):
+        if name == "seed":
+            self.seed = int(value)
+
+    def setDustPDF(self, iG, fetch=False):
+        from oracle import oracle as O
+
+        g = self.model.grids[0]
+        g.dustPDF = O.dust_pdf(self.model, g, self.tables)
+
+    def zero_estimators(self):
+        self.sed_cnt = None
+
+    def energyPacketDriver(self, iStar, n, deltaE=None):
+        from oracle import oracle as O
+
+        self.orc = O.Oracle(self.model, fp32_tallies=False)
+        c = self.orc.transport_mt(iStar, 0, n, seed=self.seed, threads=2)
+        self.dE = float(deltaE)
+        c.update(total_ms=0.0, kernel_ms=0.0)
+        return c
+
+    def reduce(self):
+        self.f = self.orc.folded(1, self.dE)
+        cnt, raw = self.orc.sed(self.dE)
+        self.sed_cnt = (raw, cnt)
+
+    def getDustT(self, iG, XHILimit):
+        from oracle import oracle as O
+
+        g = self.model.grids[0]
+        Js, _ = scale_estimators(self.model, self.f["Jste"], np.zeros((1, 1, 1), F32))
+        T, conv = O.dust_update(self.model, g, self.tables, Js, XHILimit)
+        g.Tdust = T
+        return T, conv, int(conv[1:].sum())
+
+    def fetch_sed(self):
+        return self.sed_cnt
