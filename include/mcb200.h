@@ -145,7 +145,12 @@ int mcb200_set_opacity(mcb200_ctx *ctx, int32_t iG, const float *opacity, const 
  * ionization_mod.f90:65-80.  ff1 (0:nCells) is the bin-1 free-free opacity of
  * addOpacity :369-393 (the only bin the reference ever fills), computed by the host's
  * BoltGaunt so its cell-order-dependent Gaunt-factor cache is preserved. All band
- * indices are 1-based Fortran values; xSecArray is passed once with its length. */
+ * indices are 1-based Fortran values; xSecArray is passed once with its length.
+ * Tdust = NULL: the sublimation test reads the dust temperatures the library holds on the
+ * device (mcb200_set_dust_state, updated in place by mcb200_dust_update), so a dust-only Lucy
+ * iteration -- mcb200_dust_pdf, mcb200_transport, mcb200_dust_update, mcb200_assemble_opacity
+ * with nBands = 0 -- runs with nothing but counters crossing PCIe, sublimation included
+ * (needs mcb200_set_dust_tables; MCB200_ESTATE otherwise). */
 int mcb200_set_xsec(mcb200_ctx *ctx, const float *xSecArray, int64_t nXsec);
 int mcb200_assemble_opacity(mcb200_ctx *ctx, int32_t iG,
                             int32_t nBands, const int32_t *bandSpecies, const int32_t *bandOff,

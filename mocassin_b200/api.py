@@ -243,7 +243,9 @@ class PacketEngine:
     def assemble_opacity(self, iG: int, bands, den: np.ndarray, ff1: Optional[np.ndarray] = None, dust=None):
         """K1 on device.  `bands` = dict(species, off, low, high) int32 arrays (1-based
         Fortran values as in addOpacity); `den` (nCells+1, nSpeciesDen) F-order; `dust` =
-        dict(Ndust, Tdust, dustAbunIndex, grainWeight, dustScaXsecP, dustAbsXsecP) or None."""
+        dict(Ndust, Tdust, dustAbunIndex, grainWeight, dustScaXsecP, dustAbsXsecP) or None;
+        Tdust = None takes the sublimation mask from the device-resident dust state (after
+        set_dust_state / getDustT), so a dust-only Lucy iteration never brings Tdust to the host."""
         sp, off, lo, hi = (_f(bands[k], I32) for k in ("species", "off", "low", "high"))
         den = _f(den)
         nsd = int(den.shape[1]) if den.ndim == 2 else 0
@@ -252,7 +254,7 @@ class PacketEngine:
         self._check(self.lib.mcb200_assemble_opacity(
             self.h, iG, int(sp.shape[0]), _ip(sp), _ip(off), _ip(lo), _ip(hi), nsd, _fp(den),
             _fp(_f(ff1)) if ff1 is not None else None,
-            _fp(_f(d["Ndust"])) if dust else None, _fp(_f(d["Tdust"])) if dust else None,
+            _fp(_f(d["Ndust"])) if dust else None, _fp(_f(d["Tdust"])) if dust and d.get("Tdust") is not None else None,
             _ip(_f(d["dustAbunIndex"], I32)) if dust and d.get("dustAbunIndex") is not None else None,
             _fp(_f(d["grainWeight"])) if dust else None,
             _ip(_f(d["dustScaXsecP"], I32)) if dust else None,

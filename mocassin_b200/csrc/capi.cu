@@ -65,6 +65,9 @@ cudaError_t launch_esc_scatter(unsigned int *Q, size_t total, const unsigned lon
 cudaError_t launch_sed_sum(const unsigned int *escQ, size_t nR, int firstPlane, int nPlanes,
                            unsigned long long *sedQ, cudaStream_t s);
 cudaError_t launch_contcube(const float *esc, size_t nR, int nb, int nAngles, float *out, cudaStream_t s);
+cudaError_t launch_dust_mask(const float *Tdust, const int *compOfCell, const int *dustComPoint, const int *nSpeciesPart,
+                             const float *Tsub, int nRows, int nSpeciesTot, int nSizes, int s0, int s1, unsigned char *on,
+                             cudaStream_t s);
 }  // namespace mcb
 
 using namespace mcb;
@@ -2335,8 +2338,14 @@ int mcb200_assemble_opacity(mcb200_ctx *ctx, int32_t iG, int32_t nBands, const i
     std::vector<int> termOn, scaP, absP, comps;
     if (c.lgDust && Ndust) {
         if (!ctx->haveDustSpecies) return fail(ctx, MCB200_ESTATE, "set_dust_species first");
-        if (!Tdust || !grainWeight || !dustScaXsecP || !dustAbsXsecP || nSpeciesTot < 1 || c.nSizes < 1)
+        if (!grainWeight || !dustScaXsecP || !dustAbsXsecP || nSpeciesTot < 1 || c.nSizes < 1)
             return fail(ctx, MCB200_EINVAL, "bad dust arguments");
+        // Tdust = NULL: take the sublimation mask from the device-resident dust state
+        // (mcb200_set_dust_state / mcb200_dust_update), which then never leaves the device
+        const bool devT = Tdust == nullptr;
+        if (devT && (!ctx->haveDustTables || g->Tdust.n != ((size_t)c.nSpeciesMax + 1) * ((size_t)c.nSizes + 1) * (size_t)nRows ||
+                     nSpeciesTot != ctx->nSpeciesTot))
+            return fail(ctx, MCB200_ESTATE, "Tdust = NULL needs the device dust state: mcb200_set_dust_tables and mcb200_set_dust_state first");
         if (c.lgMultiDustChemistry && !dustAbunIndex) return fail(ctx, MCB200_EINVAL, "dustAbunIndex required");
         int nT = nSpeciesTot * c.nSizes, nC = c.nDustComp;
         coef.assign((size_t)nC * nT, 0.f); termOn.assign((size_t)nC * nT, 0);
@@ -2357,13 +2366,14 @@ int mcb200_assemble_opacity(mcb200_ctx *ctx, int32_t iG, int32_t nBands, const i
                 }
             }
         // sublimation mask Tdust(nS,ai,cell) < TdustSublime(dcp-1+nS), iteration_mod.f90:189
-        on.assign((size_t)nT * nRows, 0);
+        if (!devT) on.assign((size_t)nT * nRows, 0);
         comps.assign(nRows, 0);
         size_t s0 = (size_t)c.nSpeciesMax + 1, s1 = (size_t)c.nSizes + 1;
         for (int cell = 1; cell < nRows; ++cell) {
             int k = c.lgMultiDustChemistry ? dustAbunIndex[cell] : 1;
             if (k < 1 || k > nC) { comps[cell] = -1; continue; }
             comps[cell] = k - 1;
+            if (devT) continue;
             int dcp = ctx->dustComPoint[k - 1];
             for (int nS = 1; nS <= ctx->nSpeciesPart[k - 1]; ++nS)
                 for (int ai = 1; ai <= c.nSizes; ++ai) {
@@ -2374,10 +2384,17 @@ int mcb200_assemble_opacity(mcb200_ctx *ctx, int32_t iG, int32_t nBands, const i
         }
         auto t1 = now();
         if (tr) fprintf(stderr, "[mcb200] assemble_opacity: gas uploads + dust host mask %.1f ms\n", ms(t0, t1));
-        CU(dNd.upload(Ndust, nRows, s)); CU(dOn.upload(on.data(), on.size(), s));
+        CU(dNd.upload(Ndust, nRows, s));
         CU(dCoef.upload(coef.data(), coef.size(), s)); CU(dTermOn.upload(termOn.data(), termOn.size(), s));
         CU(dScaP.upload(scaP.data(), nT, s)); CU(dAbsP.upload(absP.data(), nT, s));
         CU(dComp.upload(comps.data(), nRows, s));
+        if (devT) {
+            CU(dOn.alloc((size_t)nT * nRows));
+            CU(launch_dust_mask(g->Tdust.p, dComp.p, ctx->dComPoint.p, ctx->dSpeciesPart.p, ctx->dSublime.p, nRows, nSpeciesTot,
+                                c.nSizes, c.nSpeciesMax + 1, c.nSizes + 1, dOn.p, s));
+        } else {
+            CU(dOn.upload(on.data(), on.size(), s));
+        }
         if (g->scaOpac.n != ts) re = true;
         CU(g->scaOpac.alloc(ts)); CU(g->absOpac.alloc(ts));
         A.nDustTerms = nT; A.Ndust = dNd.p; A.dustOn = dOn.p; A.dustCoef = dCoef.p;

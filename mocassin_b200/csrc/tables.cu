@@ -202,6 +202,45 @@ cudaError_t launch_sed_sum(const unsigned int *escQ, size_t nR, int firstPlane, 
 }
 
 // ---------------------------------------------------------------------------------------
+// Sublimation mask of the dust opacity terms from the device-resident dust state
+// (iteration_mod.f90:189: Tdust(nS,ai,cell) < TdustSublime(dcp-1+nS)), so that K1 can rebuild
+// scaOpac/absOpac/opacity after K5 (mcb200_dust_update) without Tdust leaving the device.
+// Term t = (sg-1)*nSizes + (ai-1), sg = global species; one thread per (cell, term).
+// ---------------------------------------------------------------------------------------
+__global__ void dust_mask_kernel(const float *__restrict__ Tdust, const int *__restrict__ compOfCell,
+                                 const int *__restrict__ dustComPoint, const int *__restrict__ nSpeciesPart,
+                                 const float *__restrict__ Tsub, int nRows, int nSpeciesTot, int nSizes, int s0, int s1,
+                                 unsigned char *__restrict__ on)
+{
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    size_t total = (size_t)nRows * (size_t)(nSpeciesTot * nSizes);
+    if (i >= total) return;
+    int cell = (int)(i % (size_t)nRows), t = (int)(i / (size_t)nRows);
+    int sg = t / nSizes + 1, ai = t % nSizes + 1;
+    unsigned char v = 0;
+    int k = cell > 0 ? compOfCell[cell] : -1;
+    if (k >= 0) {
+        int nS = sg - dustComPoint[k] + 1;
+        if (nS >= 1 && nS <= nSpeciesPart[k]) {
+            float Td = Tdust[(size_t)nS + (size_t)s0 * ((size_t)ai + (size_t)s1 * (size_t)cell)];
+            v = Td < Tsub[sg - 1] ? 1 : 0;
+        }
+    }
+    on[i] = v;
+}
+
+cudaError_t launch_dust_mask(const float *Tdust, const int *compOfCell, const int *dustComPoint, const int *nSpeciesPart,
+                             const float *Tsub, int nRows, int nSpeciesTot, int nSizes, int s0, int s1, unsigned char *on,
+                             cudaStream_t s)
+{
+    size_t total = (size_t)nRows * (size_t)(nSpeciesTot * nSizes);
+    if (!total) return cudaSuccess;
+    dust_mask_kernel<<<(unsigned)((total + 255) / 256), 256, 0, s>>>(Tdust, compOfCell, dustComPoint, nSpeciesPart, Tsub, nRows,
+                                                                     nSpeciesTot, nSizes, s0, s1, on);
+    return cudaGetLastError();
+}
+
+// ---------------------------------------------------------------------------------------
 // K9 continuum-cube reduction (writeContCube, output_mod.f90:2762-2772): per cell and viewing
 // angle, the folded escapedPackets summed over the frequency bins 1..nbins, in the reference's
 // order (freq ascending, float32 running sum) so the result equals its loop bit for bit.

@@ -36,10 +36,12 @@ def oracle_step(model, tables, d, seed=12345, threads=1):
     return step, state
 
 
-def engine_step(model, tables, d, seed=12345):
+def engine_step(model, tables, d, seed=12345, device_opacity=False):
     """The same iteration through the C ABI.  Tdust and the convergence flags stay on the device
-    between K5 and K6; they come back once per iteration only because the host rebuilds the
-    dust opacities from them."""
+    between K5 and K6.  device_opacity = False: the host rebuilds the dust opacities from the
+    fetched temperatures and uploads them; True: K1 rebuilds them on the device from the
+    device-resident dust state (mcb200_assemble_opacity with Tdust = NULL) and nothing is
+    uploaded between iterations."""
     g = model.grids[0]
     eng = PacketEngine(model, seed=seed)
     eng.set_xsec(tables["xSecArray"])
@@ -58,9 +60,15 @@ def engine_step(model, tables, d, seed=12345):
         eng.reduce()
         T, conv, nconv = eng.getDustT(1, d.XHILimit)
         g.Tdust = T
-        deck.dust_opacity(g, tables)
-        eng.set_opacity()
-        eng.set_dust_state()
+        if device_opacity:
+            eng.assemble_opacity(1, dict(species=[], off=[], low=[], high=[]), np.zeros((g.nCells + 1, 0), F32), None,
+                                 dict(Ndust=g.Ndust, Tdust=None, dustAbunIndex=g.dustAbunIndex,
+                                      grainWeight=tables["grainWeight"], dustScaXsecP=tables["dustScaXsecP"],
+                                      dustAbsXsecP=tables["dustAbsXsecP"]))
+        else:
+            deck.dust_opacity(g, tables)
+            eng.set_opacity()
+            eng.set_dust_state()
         state["counters"].append(c)
         return int(nconv), g.nCells
 

@@ -93,3 +93,67 @@ def test_device_contcube_equals_frequency_sum_of_fetched_escaped_packets(cuda_li
         assert np.array_equal(got.view(np.uint32), want.view(np.uint32)), iG
         assert np.count_nonzero(got) > 0
     e.close()
+
+
+def test_deck_loop_with_device_side_dust_opacity_matches_oracle(cuda_lib, oracle_lib):
+    """As the first test, but K1 rebuilds scaOpac/absOpac/opacity on the device from the
+    device-resident dust state after every K5 (mcb200_assemble_opacity with Tdust = NULL): the whole
+    iteration, sublimation test included, runs without Tdust or opacities crossing PCIe."""
+    from deck_runner import engine_step, oracle_step
+    from mocassin_b200 import deck
+
+    packets = 60000
+    runs = {}
+    for which in ("oracle", "cuda"):
+        m, t, d = deck.deck_from_arrays(dict(np.load(os.path.join(GOLD, "deck_p0tau1.npz"))))
+        d.maxIterateMC, d.nPhotons = 3, packets
+        m.deltaE[1] = np.float32(d.LStar) / np.float32(packets)
+        step, st = (oracle_step(m, t, d, seed=900, threads=4) if which == "oracle"
+                    else engine_step(m, t, d, seed=900, device_opacity=True))
+        hist = deck.iterate_dust(d, m, step)
+        g = m.grids[0]
+        if which == "cuda":
+            op, sca, ab = st["eng"].get_opacity(1, want_abs=True)
+            st["eng"].close()
+        else:
+            op, sca, ab = g.opacity, g.scaOpac, g.absOpac
+        runs[which] = (hist, g.Tdust.copy(), op, sca, ab)
+    (h0, T0, op0, sca0, ab0), (h1, T1, op1, sca1, ab1) = runs["oracle"], runs["cuda"]
+    assert [h["converged_pct"] for h in h0] == [h["converged_pct"] for h in h1]
+    assert np.array_equal(T0[:, :, 1:].view(np.uint32), T1[:, :, 1:].view(np.uint32))
+    for a, b in ((op0, op1), (sca0, sca1), (ab0, ab1)):
+        assert np.array_equal(a[1:].view(np.uint32), b[1:].view(np.uint32))
+
+
+def test_device_sublimation_mask_equals_host_mask(cuda_lib):
+    """K1 with Tdust = NULL (mask built by dust_mask_kernel from the device dust state) against K1
+    with the host's Tdust, on a 3-species, 2-component, 3-size model in which a third of the cells
+    hold grains above their sublimation temperature."""
+    from mocassin_b200 import workloads as W
+    from mocassin_b200.api import PacketEngine
+
+    model, t = W.dust_closure(n=9, nbins=60, nPhotons=1000, T0=100.0)
+    g = model.grids[0]
+    rng = np.random.default_rng(8)
+    hot = rng.random(g.nCells + 1) < 0.33
+    g.Tdust[1, 2, hot] = 1300.0          # species 1 of a component, size 2: above 1200 / 900 K, below 1400 K
+    g.Tdust[2, 1, hot] = 2000.0
+    e = PacketEngine(model)
+    e.set_xsec(t["xSecArray"])
+    e.set_dust_tables(t["widFlx"], t["grainWeight"], t["dustAbsXsecP"], t["dustEmIntegral"])
+    e.set_opacity()
+    e.set_dust_state()
+    none = dict(species=[], off=[], low=[], high=[])
+    den = np.zeros((g.nCells + 1, 0), np.float32)
+    dust = dict(Ndust=g.Ndust, Tdust=g.Tdust, dustAbunIndex=g.dustAbunIndex, grainWeight=t["grainWeight"],
+                dustScaXsecP=t["dustScaXsecP"], dustAbsXsecP=t["dustAbsXsecP"])
+    e.assemble_opacity(1, none, den, None, dust)
+    host = e.get_opacity(1, want_abs=True)
+    e.assemble_opacity(1, none, den, None, dict(dust, Tdust=None))
+    dev = e.get_opacity(1, want_abs=True)
+    for a, b in zip(host, dev):
+        assert np.array_equal(a.view(np.uint32), b.view(np.uint32))
+    cold = dict(dust, Tdust=np.full_like(g.Tdust, 50.0))
+    e.assemble_opacity(1, none, den, None, cold)
+    assert not np.array_equal(e.get_opacity(1)[0], host[0])      # the mask does matter in this model
+    e.close()
