@@ -29,6 +29,8 @@ def main():
     ap.add_argument("--out", default="output")
     ap.add_argument("--max-iter", type=int, default=0)
     ap.add_argument("--seed", type=int, default=12345)
+    ap.add_argument("--device-opacity", action="store_true",
+                    help="rebuild the dust opacities on the device (K1 from the device dust state) instead of on the host")
     a = ap.parse_args()
     if a.golden:
         model, tables, d = deck.deck_from_arrays(dict(np.load(a.golden)))
@@ -56,9 +58,15 @@ def main():
         c = eng.energyPacketDriver(1, nPhotons, deltaE=float(F32(deltaE)))
         eng.reduce()
         T, conv, nconv = eng.getDustT(1, d.XHILimit)
-        deck.dust_opacity(g, tables)                       # iteration_mod.f90:166-227 (sublimed grains drop out)
-        eng.set_opacity()
-        eng.set_dust_state()
+        if a.device_opacity:                               # iteration_mod.f90:166-227 on the device
+            eng.assemble_opacity(1, dict(species=[], off=[], low=[], high=[]), np.zeros((g.nCells + 1, 0), F32), None,
+                                 dict(Ndust=g.Ndust, Tdust=None, dustAbunIndex=g.dustAbunIndex,
+                                      grainWeight=tables["grainWeight"], dustScaXsecP=tables["dustScaXsecP"],
+                                      dustAbsXsecP=tables["dustAbsXsecP"]))
+        else:                                              # ... or on the host (sublimed grains drop out)
+            deck.dust_opacity(g, tables)
+            eng.set_opacity()
+            eng.set_dust_state()
         state.update(conv=conv, nPhotons=nPhotons, counters=c)
         return int(nconv), g.nCells
 
