@@ -110,3 +110,14 @@ def write_cont_cube(path: str, model: Model, contI_raw, origin=(1, 1, 1)) -> Non
         fh.write("  \n")
         fh.write(" All continuum intensities given per unit direction - must multiply column 3 by 4. Pi to obtain total "
                  "emission over all directions.\n")
+
+
+def write_plane_ion_distribution(path: str, planeIonDistribution: np.ndarray) -> None:
+    """output/planeIonDistribution.out (iteration_mod.f90:570-577): `i k count` for every (x, z)
+    column of the mother grid's illuminated face, x outermost; the array is what
+    ``mcb200_fetch_plane_distribution`` returns (already summed over ranks)."""
+    p = np.asarray(planeIonDistribution)
+    with open(path, "w") as fh:
+        for i in range(p.shape[0]):
+            for k in range(p.shape[1]):
+                fh.write(f" {i + 1:11d} {k + 1:11d} {int(p[i, k]):11d}\n")

@@ -154,3 +154,14 @@ def test_sed_local_on_two_ranks_of_one_gpu():
     assert np.allclose(loc[0] + loc[1], glob, rtol=1e-6)
     for e in engines:
         e.close()
+
+
+def test_plane_ion_distribution_file(tmp_path):
+    """planeIonDistribution.out: one `i k count` record per (x, z) column, x outermost
+    (iteration_mod.f90:570-577)."""
+    from mocassin_b200 import output
+
+    p = np.arange(12, dtype=np.int32).reshape(3, 4, order="F")
+    output.write_plane_ion_distribution(str(tmp_path / "p.out"), p)
+    rows = [[int(x) for x in ln.split()] for ln in open(tmp_path / "p.out")]
+    assert len(rows) == 12 and rows[0] == [1, 1, 0] and rows[1] == [1, 2, 3] and rows[-1] == [3, 4, 11]
