@@ -90,3 +90,33 @@ def test_bound_nccl_is_the_one_torch_loads():
     env = {k: v for k, v in os.environ.items() if k != "MCB200_NCCL_LIB"}
     res = subprocess.run([os.sys.executable, "-c", code], capture_output=True, text=True, cwd=ROOT, env=env)
     assert res.returncode == 0 and "ok" in res.stdout, res.stderr[-600:]
+
+
+def test_header_is_plain_c_and_a_c_program_links_against_the_library(cuda_lib, tmp_path):
+    """include/mcb200.h is the contract a Fortran/C host compiles against: it must be valid C99 (no
+    C++ or torch types), and a C program using it must link against the shared library and fail
+    cleanly where there is no device."""
+    from mocassin_b200 import _lib
+
+    hdr = os.path.join(ROOT, "include", "mcb200.h")
+    for cmd in (["gcc", "-std=c99", "-Wall", "-Wextra", "-pedantic", "-Werror", "-fsyntax-only", "-x", "c", hdr],
+                ["g++", "-std=c++17", "-fsyntax-only", "-x", "c++", hdr]):
+        r = subprocess.run(cmd, capture_output=True, text=True)
+        assert r.returncode == 0, r.stderr
+    src = tmp_path / "host.c"
+    src.write_text('#include "mcb200.h"\n#include <stdio.h>\n'
+                   'int main(void) { mcb200_ctx *c = 0; int rc = mcb200_create(&c, 0, 0, 1, 12345u);\n'
+                   '  int v = 0; char p[512]; int rn = mcb200_nccl_info(&v, p, 512);\n'
+                   '  printf("%d %d %d\\n", rc, rn, v); if (rc == 0) mcb200_destroy(c); return 0; }\n')
+    exe = tmp_path / "host"
+    r = subprocess.run(["gcc", "-std=c99", "-I", os.path.join(ROOT, "include"), str(src), "-o", str(exe),
+                        _lib.LIB_PATH, "-Wl,-rpath," + os.path.dirname(_lib.LIB_PATH)], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    out = subprocess.run([str(exe)], capture_output=True, text=True)
+    assert out.returncode == 0, out.stderr
+    rc, rn, v = (int(x) for x in out.stdout.split())
+    import torch
+
+    assert (rc == 0) == torch.cuda.is_available()        # MCB200_ENODEV without a device: no CPU fallback
+    assert rc in (0, -1)
+    assert (rn == 0 and v >= 20000) or rn == -8           # NCCL found through the default search, or MCB200_ECOMM
