@@ -120,3 +120,46 @@ def test_header_is_plain_c_and_a_c_program_links_against_the_library(cuda_lib, t
     assert (rc == 0) == torch.cuda.is_available()        # MCB200_ENODEV without a device: no CPU fallback
     assert rc in (0, -1)
     assert (rn == 0 and v >= 20000) or rn == -8           # NCCL found through the default search, or MCB200_ECOMM
+
+
+def test_fortran_binding_interfaces_are_well_formed():
+    """No Fortran compiler exists here, so lint the shim structurally: blocks balance, every dummy
+    of every bind(C) interface is declared exactly once inside its block, and the number of dummies
+    equals the number of parameters of the C prototype it binds."""
+    hdr = open(os.path.join(ROOT, "include", "mcb200.h")).read()
+    hdr = re.sub(r"/\*.*?\*/", "", hdr, flags=re.S)
+    protos = {m.group(1): [p for p in m.group(2).split(",") if p.strip() and p.strip() != "void"]
+              for m in re.finditer(r"\b(mcb200_\w+)\s*\(([^;{]*?)\)\s*;", hdr, flags=re.S)}
+    text = open(os.path.join(ROOT, "fortran", "mcb200_mod.f90")).read()
+    # join continuation lines, drop comments
+    logical, cur = [], ""
+    for raw in text.splitlines():
+        line = raw.split("!")[0].rstrip() if '"' not in raw.split("!")[0] or raw.count("!") == 0 else raw.rstrip()
+        if not line.strip():
+            continue
+        line = line.strip()
+        if line.startswith("&"):
+            line = line[1:].lstrip()
+        if line.endswith("&"):
+            cur += line[:-1] + " "
+            continue
+        logical.append(cur + line)
+        cur = ""
+    low = [s.lower() for s in logical]
+    starts = [i for i, s in enumerate(low) if re.search(r"\bfunction\s+mcb200_\w+\s*\(", s) and not s.startswith("end")]
+    ends = [i for i, s in enumerate(low) if s.startswith("end function")]
+    assert len(starts) == len(ends) >= 40
+    assert sum(s.startswith("interface") for s in low) == sum(s.startswith("end interface") for s in low)
+    for a, b in zip(starts, ends):
+        assert a < b
+        sig = logical[a]
+        name = re.search(r'name\s*=\s*"(mcb200_\w+)"', sig).group(1)
+        assert re.search(r"function\s+" + name + r"\s*\(", sig, flags=re.I), sig      # Fortran name = C name
+        dummies = [d.strip().lower() for d in re.search(r"function\s+\w+\s*\((.*?)\)", sig, flags=re.I).group(1).split(",") if d.strip()]
+        declared = []
+        for s in logical[a + 1:b]:
+            for part in s.split(";"):
+                if "::" in part:
+                    declared += [re.sub(r"\(.*?\)", "", v).strip().lower() for v in part.split("::", 1)[1].split(",") if v.strip()]
+        assert sorted(declared) == sorted(dummies), (name, sorted(set(dummies) ^ set(declared)))
+        assert len(dummies) == len(protos[name]), (name, len(dummies), len(protos[name]))
