@@ -652,20 +652,23 @@ def iterate_dust(deck: Deck, model: Model, step: Callable[[int, float], tuple], 
     by <= convIncPercent, with the reference's double count of star 1 in nPhotonsTot)."""
     nPhotons = int(deck.nPhotons)
     deltaE = F32(model.deltaE[1])
-    totOld = 0.0
+    totOld = F32(0.0)
     hist = []
     for it in range(1, deck.maxIterateMC + 1):
         nconv, ncells = step(nPhotons, float(deltaE))
-        tot = 100.0 * (100.0 * nconv / ncells) * ncells / 100.0 / ncells if ncells else 0.0
-        hist.append(dict(iteration=it, converged_pct=tot, nPhotons=nPhotons))
+        # float32 as in the reference (:982-1064): per grid 100*conv/totCells, weighted by nCells/100,
+        # then 100*sum/totCells
+        conv = F32(F32(100.0) * F32(nconv)) / F32(ncells) if ncells else F32(0.0)
+        tot = F32(F32(100.0) * F32(F32(conv * F32(ncells)) / F32(100.0))) / F32(ncells) if ncells else F32(0.0)
+        hist.append(dict(iteration=it, converged_pct=float(tot), nPhotons=nPhotons))
         if log:
             log(hist[-1])
         nTot = 2 * nPhotons               # nPhotonsTot = nPhotons(1) + sum over stars (:1106-1109)
-        if it > 1 and tot < 95.0 and deck.lgAutoPackets and nTot < deck.maxPhotons and totOld > 0.0:
-            if (tot - totOld) / totOld <= deck.convIncPercent:
-                nPhotons = int(round(nPhotons * deck.nPhotIncrease))
+        if it > 1 and tot < F32(95.0) and deck.lgAutoPackets and nTot < deck.maxPhotons and totOld > 0:
+            if F32(F32(tot - totOld) / totOld) <= F32(deck.convIncPercent):
+                nPhotons = int(np.rint(F32(nPhotons) * F32(deck.nPhotIncrease)))
                 deltaE = F32(deltaE / F32(deck.nPhotIncrease))
         totOld = tot
-        if tot >= deck.minConvergence:
+        if tot >= F32(deck.minConvergence):
             break
     return hist
