@@ -107,6 +107,10 @@ module mcb200_mod
        integer(c_int) function mcb200_fetch_contcube(ctx, iG, contI) bind(C, name="mcb200_fetch_contcube")
          import; type(c_ptr), value :: ctx, contI; integer(c_int32_t), value :: iG
        end function
+       ! opacity(cells(r), 1:nbins) for a short list of cells: the rows writeTauNu reads along its rays
+       integer(c_int) function mcb200_get_opacity_rows(ctx, iG, nWanted, cells, rows) bind(C, name="mcb200_get_opacity_rows")
+         import; type(c_ptr), value :: ctx, cells, rows; integer(c_int32_t), value :: iG, nWanted
+       end function
        integer(c_int) function mcb200_reduce(ctx) bind(C, name="mcb200_reduce")
          import; type(c_ptr), value :: ctx
        end function

@@ -160,6 +160,13 @@ int mcb200_assemble_opacity(mcb200_ctx *ctx, int32_t iG,
                             const float *Ndust, const float *Tdust, const int32_t *dustAbunIndex,
                             const float *grainWeight, const int32_t *dustScaXsecP,
                             const int32_t *dustAbsXsecP, int32_t nSpeciesTot);
+/* rows(1:nWanted, 1:nbins) = opacity(cells(r), :) of grid iG for a short list of cells (0..nCells):
+ * what writeTauNu / integratePathTauNu (output_mod.f90:2384-2505, pathIntegration_mod.f90:241-470)
+ * read along their rays from the origin every iteration.  With the opacities assembled on the
+ * device (mcb200_assemble_opacity) this replaces a download of the whole table (5 GB at 128^3 x
+ * 600) by a few hundred KB; mocassin_b200/output.py: tau_nu, write_tau_nu is the host part. */
+int mcb200_get_opacity_rows(mcb200_ctx *ctx, int32_t iG, int32_t nWanted, const int32_t *cells, float *rows);
+
 /* Read back opacity / scaOpac / absOpac (0:nCells,nbins) of grid iG (any may be NULL). */
 int mcb200_get_opacity(mcb200_ctx *ctx, int32_t iG, float *opacity, float *scaOpac, float *absOpac);
 

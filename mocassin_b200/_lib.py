@@ -46,6 +46,7 @@ _SIGS = {
                                 C.c_int32, c_float_p, c_float_p, c_float_p, c_float_p, c_int32_p, c_float_p,
                                 c_int32_p, c_int32_p, C.c_int32],
     "mcb200_get_opacity": [C.c_void_p, C.c_int32, c_float_p, c_float_p, c_float_p],
+    "mcb200_get_opacity_rows": [C.c_void_p, C.c_int32, C.c_int32, c_int32_p, c_float_p],
     "mcb200_set_pdfs": [C.c_void_p, C.c_int32, c_float_p, c_float_p, c_float_p, c_float_p],
     "mcb200_set_dust_state": [C.c_void_p, C.c_int32, c_float_p, c_int32_p],
     "mcb200_set_dust_tables": [C.c_void_p, c_float_p, c_float_p, c_int32_p, C.c_int32, c_float_p, C.c_int32],

@@ -260,6 +260,14 @@ class PacketEngine:
             _ip(_f(d["dustScaXsecP"], I32)) if dust else None,
             _ip(_f(d["dustAbsXsecP"], I32)) if dust else None, nTot))
 
+    def get_opacity_rows(self, iG: int, cells) -> np.ndarray:
+        """(len(cells), nbins) rows opacity(cell, :) gathered on the device (for writeTauNu:
+        mocassin_b200.output.tau_nu(model, lambda c: eng.get_opacity_rows(1, c)))."""
+        cells = np.ascontiguousarray(cells, dtype=I32)
+        out = np.zeros((cells.shape[0], self.model.nbins), dtype=F32, order="F")
+        self._check(self.lib.mcb200_get_opacity_rows(self.h, iG, int(cells.shape[0]), _ip(cells), _fp(out)))
+        return out
+
     def get_opacity(self, iG: int, want_abs: bool = False):
         g = self.model.grids[iG - 1]
         shape = (g.nCells + 1, self.model.nbins)

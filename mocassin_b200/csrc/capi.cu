@@ -65,6 +65,7 @@ cudaError_t launch_esc_scatter(unsigned int *Q, size_t total, const unsigned lon
 cudaError_t launch_sed_sum(const unsigned int *escQ, size_t nR, int firstPlane, int nPlanes,
                            unsigned long long *sedQ, cudaStream_t s);
 cudaError_t launch_contcube(const float *esc, size_t nR, int nb, int nAngles, float *out, cudaStream_t s);
+cudaError_t launch_gather_rows(const float *table, size_t nR, int nb, const int *cells, int nWanted, float *out, cudaStream_t s);
 cudaError_t launch_dust_mask(const float *Tdust, const int *compOfCell, const int *dustComPoint, const int *nSpeciesPart,
                              const float *Tsub, int nRows, int nSpeciesTot, int nSizes, int s0, int s1, unsigned char *on,
                              cudaStream_t s);
@@ -2412,6 +2413,27 @@ int mcb200_assemble_opacity(mcb200_ctx *ctx, int32_t iG, int32_t nBands, const i
     if (tr) fprintf(stderr, "[mcb200] assemble_opacity: total host prep %.1f ms, kernel + pending copies %.1f ms\n", ms(t0, t2), ms(t2, now()));
     g->haveOpacity = true;
     if (re) ctx->gridsDirty = true;
+    return MCB200_OK;
+}
+
+int mcb200_get_opacity_rows(mcb200_ctx *ctx, int32_t iG, int32_t nWanted, const int32_t *cells, float *rows)
+{
+    NEED_CTX();
+    GridState *g = grid_of(ctx, iG);
+    if (!g || !g->set) return fail(ctx, MCB200_ESTATE, "grid %d not set", iG);
+    if (!g->haveOpacity || !g->opacity.p) return fail(ctx, MCB200_ESTATE, "grid %d has no opacity yet", iG);
+    if (nWanted < 0 || (nWanted > 0 && (!cells || !rows))) return fail(ctx, MCB200_EINVAL, "bad get_opacity_rows arguments");
+    if (nWanted == 0) return MCB200_OK;
+    for (int r = 0; r < nWanted; ++r)
+        if (cells[r] < 0 || cells[r] > g->nCells) return fail(ctx, MCB200_EINVAL, "cell %d out of range 0..%d", cells[r], g->nCells);
+    const int nb = ctx->cfg.nbins;
+    DevBuf<int> dCells;
+    DevBuf<float> dOut;
+    CU(dCells.upload(cells, (size_t)nWanted, ctx->stream));
+    CU(dOut.alloc((size_t)nWanted * nb));
+    CU(launch_gather_rows(g->opacity.p, (size_t)g->nCells + 1, nb, dCells.p, nWanted, dOut.p, ctx->stream));
+    CU(cudaMemcpyAsync(rows, dOut.p, (size_t)nWanted * nb * sizeof(float), cudaMemcpyDeviceToHost, ctx->stream));
+    CU(cudaStreamSynchronize(ctx->stream));
     return MCB200_OK;
 }
 

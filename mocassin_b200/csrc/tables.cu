@@ -241,6 +241,27 @@ cudaError_t launch_dust_mask(const float *Tdust, const int *compOfCell, const in
 }
 
 // ---------------------------------------------------------------------------------------
+// Rows opacity(cell_r, 1:nbins) of a few cells out of the (0:nCells, nbins) table: what writeTauNu
+// (output_mod.f90:2384-2505) reads along its three rays, without downloading the table.
+// ---------------------------------------------------------------------------------------
+__global__ void gather_rows_kernel(const float *__restrict__ table, size_t nR, int nb, const int *__restrict__ cells,
+                                   int nWanted, float *__restrict__ out)
+{
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= (size_t)nWanted * (size_t)nb) return;
+    int r = (int)(i % (size_t)nWanted), nu = (int)(i / (size_t)nWanted);
+    out[i] = table[(size_t)cells[r] + nR * (size_t)nu];          // out(r, nu), r fastest
+}
+
+cudaError_t launch_gather_rows(const float *table, size_t nR, int nb, const int *cells, int nWanted, float *out, cudaStream_t s)
+{
+    size_t total = (size_t)nWanted * (size_t)nb;
+    if (!total) return cudaSuccess;
+    gather_rows_kernel<<<(unsigned)((total + 255) / 256), 256, 0, s>>>(table, nR, nb, cells, nWanted, out);
+    return cudaGetLastError();
+}
+
+// ---------------------------------------------------------------------------------------
 // K9 continuum-cube reduction (writeContCube, output_mod.f90:2762-2772): per cell and viewing
 // angle, the folded escapedPackets summed over the frequency bins 1..nbins, in the reference's
 // order (freq ascending, float32 running sum) so the result equals its loop bit for bit.

@@ -121,3 +121,130 @@ def write_plane_ion_distribution(path: str, planeIonDistribution: np.ndarray) ->
         for i in range(p.shape[0]):
             for k in range(p.shape[1]):
                 fh.write(f" {i + 1:11d} {k + 1:11d} {int(p[i, k]):11d}\n")
+
+
+# ---------------------------------------------------------------------------------------
+# output/tauNu.out: writeTauNu (output_mod.f90:2384-2505) over integratePathTauNu
+# (pathIntegration_mod.f90:241-470).  The march from the origin along +x, +z, +y visits the same
+# cells for every frequency, so it is done once per direction (`tau_path`) and the optical depth of
+# every bin is the float32 running sum of opacity(cell_k, nu)*dlSmall over its steps -- which needs
+# the opacity rows of a few dozen cells only (``mcb200_get_opacity_rows``), not the table.
+# ---------------------------------------------------------------------------------------
+MAX_TAU = 10_000_000             # constants_mod.f90:46
+
+
+def _axis_start(a: np.ndarray, v) -> int:
+    from .model import locate
+
+    p = locate(a, v)
+    if 1 <= p < a.shape[0]:      # p = 0 (below the axis) is rejected by the caller, as in the reference
+        if F32(v) >= F32(F32(a[p - 1] + a[p]) / F32(2.0)):
+            p += 1
+    return p
+
+
+def tau_path(model: Model, uHat, aVec=(0.0, 0.0, 0.0)):
+    """The cells integratePathTauNu steps through from aVec along uHat in the mother grid (single
+    grid only, like the reference).  Returns (cells int32[nsteps], dlSmall float32)."""
+    from .model import locate
+
+    if model.nGrids > 1:
+        return np.zeros(0, np.int32), F32(0.0)
+    g = model.grids[0]
+    ax = [np.asarray(g.xAxis, F32), np.asarray(g.yAxis, F32), np.asarray(g.zAxis, F32)]
+    n = [a.shape[0] for a in ax]
+    P = [_axis_start(ax[k], aVec[k]) for k in range(3)]
+    for k in range(3):
+        if P[k] <= 0 or P[k] > n[k]:
+            raise ValueError("integratePathTau: starting position is outside the grid")
+    dl = F32(0.0)
+    for k in range(3):           # half the smallest spacing of the axes the ray advances along (:283-318)
+        if uHat[k] > 0:
+            dmin = F32(np.abs(np.diff(ax[k])).astype(F32).min())
+            dl = dmin if dl <= 0 else F32(min(dl, dmin))
+    dl = F32(dl / F32(2.0))
+    v = [F32(uHat[0]), F32(uHat[1]), F32(uHat[2])]
+    r = [F32(F32(aVec[k]) + F32(dl * v[k])) for k in range(3)]
+    sym = bool(model.lgSymmetricXYZ)
+    Rout = F32(model.R_out)
+    cells = []
+    act = np.asarray(g.active)
+    for _ in range(MAX_TAU):
+        if r[0] > ax[0][-1] or r[1] > ax[1][-1] or r[2] > ax[2][-1]:
+            break
+        rad = F32(np.sqrt(F32(F32(F32(r[0] / F32(1e10)) ** 2 + F32(r[1] / F32(1e10)) ** 2) + F32(r[2] / F32(1e10)) ** 2))) * F32(1e10)
+        if Rout > 0 and rad >= Rout:
+            break
+        if sym:
+            for k in range(3):
+                if r[k] < ax[k][0]:
+                    v[k], r[k] = F32(-v[k]), F32(-r[k])
+                    P[k] = locate(ax[k], r[k])
+        stop = False
+        for k in range(3):
+            if P[k] < n[k]:
+                if r[k] > F32(F32(ax[k][P[k] - 1] + ax[k][P[k]]) / F32(2.0)):
+                    P[k] += 1
+            elif P[k] == n[k]:
+                if r[k] > ax[k][P[k] - 1]:
+                    stop = True
+                    break
+            if P[k] > 1:
+                if r[k] < F32(F32(ax[k][P[k] - 1] + ax[k][P[k] - 2]) / F32(2.0)):
+                    P[k] -= 1
+        if stop:
+            break
+        if not sym and (P[0] < 1 or P[1] < 1 or P[2] < 1):
+            break
+        if sym:
+            for k in range(3):
+                if P[k] < 1:
+                    v[k], r[k] = F32(-v[k]), F32(-r[k])
+                    P[k] = locate(ax[k], r[k])
+                    if P[k] < n[k]:
+                        if r[k] > F32(F32(ax[k][P[k] - 1] + ax[k][P[k]]) / F32(2.0)):
+                            P[k] += 1
+                    elif P[k] == n[k] and r[k] > ax[k][P[k] - 1]:
+                        stop = True
+                        break
+            if stop:
+                break
+        cells.append(int(act[P[0] - 1, P[1] - 1, P[2] - 1]))
+        r = [F32(r[k] + F32(dl * v[k])) for k in range(3)]
+    return np.asarray(cells, np.int32), dl
+
+
+TAU_DIRECTIONS = (((1.0, 0.0, 0.0), "1,0,0"), ((0.0, 0.0, 1.0), "0,0,1"), ((0.0, 1.0, 0.0), "0,1,0"))
+
+
+def tau_nu(model: Model, opacity_rows) -> list:
+    """outTau(1:nbins) for the three directions of writeTauNu.  `opacity_rows(cells)` returns the
+    (len(cells), nbins) float32 rows opacity(cell, :) -- from the host table or from the device
+    (``PacketEngine.get_opacity_rows``)."""
+    out = []
+    for uHat, _ in TAU_DIRECTIONS:
+        cells, dl = tau_path(model, uHat)
+        tau = np.zeros(model.nbins, dtype=F32)
+        if cells.size:
+            uniq, inv = np.unique(cells, return_inverse=True)
+            rows = np.asarray(opacity_rows(uniq.astype(np.int32)), dtype=F32)
+            for k in inv:
+                tau = (tau + (rows[k] * dl).astype(F32)).astype(F32)
+        out.append(tau)
+    return out
+
+
+def write_tau_nu(path: str, model: Model, opacity_rows) -> list:
+    """output/tauNu.out in the reference's layout."""
+    taus = tau_nu(model, opacity_rows)
+    nu = np.asarray(model.nuArray, dtype=F32)
+    lam = (F32(C_LIGHT) / (nu * FR1RYD)).astype(F32) * F32(1.0e4)
+    with open(path, "w") as fh:
+        for (uHat, label), tau in zip(TAU_DIRECTIONS, taus):
+            fh.write("  Optical depth from the centre to the edge of the nubula \n")
+            fh.write(f"  direction: {label}\n")
+            fh.write("  lambda [um]    tau(R_max) \n")
+            for f in range(model.nbins):
+                fh.write(f" {float(lam[f]):.7E} {float(tau[f]):.7E}\n")
+            fh.write("  \n")
+    return taus

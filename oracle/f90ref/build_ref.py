@@ -69,7 +69,7 @@ PROC_HOOKS = {'energypacketrun'}             # one call per packet generation
 # (file, declarations only?, procedures to keep, internal procedures to keep)
 AUX_SOURCES = [
     ('constants_mod.f90', False, None, None),
-    ('vector_mod.f90', False, set(), None),
+    ('vector_mod.f90', False, None, None),       # the vector operators (integratePathTauNu: rVec + dlSmall*vHat)
     ('interpolation_mod.f90', False, {'locate', 'linearmap'}, None),
     ('common_mod.f90', True, None, None),
     ('ph_mod.f90', False, {'bhmie', 'getqs'}, None),      # module xSec_mod; BHmie (COMPLEX arithmetic, statement functions)
@@ -81,7 +81,8 @@ AUX_SOURCES = [
     ('ionization_mod.f90', False, {'ionizationdriver', 'edensum', 'addopacity'}, None),
     ('emission_mod.f90', False, {'emissiondriver'}, {'setdustpdf'}),
     ('update_mod.f90', False, {'updatecell'}, {'getdustt'}),
-    ('output_mod.f90', False, {'writesed', 'writecontcube'}, None),
+    ('pathIntegration_mod.f90', False, {'integratepathtaunu'}, None),
+    ('output_mod.f90', False, {'writesed', 'writecontcube', 'writetaunu'}, None),
 ]
 # Statement ranges of procedures that cannot be run as a whole (iterateMC is the entire Lucy
 # iteration, MPI included; updateCell's gas branch is the whole ionisation/thermal solver),
@@ -129,7 +130,7 @@ AUX_SLICES = [
 # oracle takes as an input (ff1), so the harness sets those arrays directly
 AUX_EXTERNS = {'boltgaunt'}
 # procedures that must translate completely, and the untranslated statements tolerated in them
-AUX_STRICT = {'writegrid': 0, 'writesed': 0, 'writecontcube': 0, 'bhmie': 0, 'getqs': 0, 'dust_xsec_assembly': 0, 'opacity_block': 0, 'photo_rates': 0, 'photo_heat': 0, 'getoutershell': 0, 'ionizationdriver': 0, 'edensum': 0, 'addopacity': 0, 'putopacity': 0, 'inopacity': 0, 'getflux': 0, 'locate': 0, 'linearmap': 0,
+AUX_STRICT = {'writegrid': 0, 'writesed': 0, 'writecontcube': 0, 'writetaunu': 0, 'integratepathtaunu': 0, 'bhmie': 0, 'getqs': 0, 'dust_xsec_assembly': 0, 'opacity_block': 0, 'photo_rates': 0, 'photo_heat': 0, 'getoutershell': 0, 'ionizationdriver': 0, 'edensum': 0, 'addopacity': 0, 'putopacity': 0, 'inopacity': 0, 'getflux': 0, 'locate': 0, 'linearmap': 0,
               'setdustpdf': 1,      # call qHeat (lgQHeat branch)
               'getdustt': 1}        # resLineHeating (gas + resonance-line transfer branch)
 

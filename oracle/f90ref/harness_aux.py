@@ -8,6 +8,7 @@ the f90py translation) -- TEST INFRASTRUCTURE:
                    1123-1234 of thermBalance (heatSte/heatDif), with getOuterShell (hydro_mod.f90).
 * `write_sed`    : `writeSED(grid)` (output_mod.f90:2508-2719); the records it writes to unit 16
 * `bhmie`       : `BHmie` (ph_mod.f90:1600-1757), COMPLEX arithmetic and statement functions
+* `write_tau_nu`  : `writeTauNu(grid)` over `integratePathTauNu`; unit 73 records
 * `write_cont_cube`: `writeContCube(grid, freq1, freq2)` (output_mod.f90:2722-2806); unit 19 records
                    are captured instead of going to output/SED.out.
 * `write_grid`   : `writeGrid(grid)` (grid_mod.f90:2646-2870): the records of grid0-3.out, dustGrid.out
@@ -302,6 +303,32 @@ class AuxReference:
         self.ref.p_linearmap(rt.wrap(_F(y, np.float32)), rt.wrap(_F(x, np.float32)), int(len(x)), out,
                              rt.wrap(_F(x_new, np.float32)), int(len(x_new)))
         return out.a.copy()
+
+    # ------------------------------------------------------------------------------------------
+    def write_tau_nu(self, model):
+        """writeTauNu(grid) (output_mod.f90:2384-2505; integratePathTauNu, pathIntegration_mod.f90:
+        241-470) on a single-grid model with grid%opacity set.  Returns the three outTau(1:nbins)
+        arrays (directions 1,0,0 / 0,0,1 / 0,1,0) and the lambda column, as written to unit 73."""
+        G, ref = self.G, self.ref
+        g = model.grids[0]
+        G.nbins, G.ngrids = int(model.nbins), 1
+        G.lgsymmetricxyz = bool(model.lgSymmetricXYZ)
+        G.r_out = np.float32(model.R_out)
+        G.nuarray = rt.wrap(_F(model.nuArray, np.float32))
+        t = ref.T_grid_type()
+        t.nx, t.ny, t.nz, t.ncells = g.nx, g.ny, g.nz, int(g.nCells)
+        t.xaxis, t.yaxis, t.zaxis = (rt.wrap(_F(a, np.float32)) for a in (g.xAxis, g.yAxis, g.zAxis))
+        t.active = rt.wrap(_F(g.active, np.int32))
+        t.opacity = rt.wrap(_F(g.opacity, np.float32), (0, 1))
+        grids = np.empty(1, dtype=object)
+        grids[0] = t
+        rt.io_log.clear()
+        with np.errstate(all='ignore'):
+            ref.p_writetaunu(rt.wrap(grids))
+        rows = [r for r in rt.io_log.get(73, []) if len(r) == 2 and not isinstance(r[0], str)]
+        assert len(rows) == 3 * model.nbins, (len(rows), model.nbins)
+        a = np.array(rows, np.float32).reshape(3, model.nbins, 2)
+        return [a[k, :, 1].copy() for k in range(3)], a[0, :, 0].copy()
 
     # ------------------------------------------------------------------------------------------
     def write_cont_cube(self, model, escaped, freq1, freq2, origin=(1, 1, 1)):

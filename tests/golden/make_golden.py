@@ -20,7 +20,7 @@ free-free term ff1 = FFOpacity(1) per cell), emissionDriver -> setDustPDF (dustP
 updateCell -> getDustT (Tdust, lgConverged), and the photo-ionisation rate / heating loops of
 updateCell / thermBalance (nPhotoSte, nPhotoDif per element and ion, heatSte, heatDif per cell, and
 getOuterShell's shell numbers) on seeded inputs built by tests/ref_cases.py.  ref_aux_sed_<case>.npz:
-ref_aux_mie.npz: BHmie, getQs, linearMap and the assembly of makeDustXsec on seeded inputs.  ref_aux_contcube_<case>.npz: the records writeContCube writes to output/contCube.out.  ref_aux_sed: 
+ref_aux_taunu_<case>.npz: the three optical-depth columns writeTauNu writes to output/tauNu.out.  ref_aux_mie.npz: BHmie, getQs, linearMap and the assembly of makeDustXsec on seeded inputs.  ref_aux_contcube_<case>.npz: the records writeContCube writes to output/contCube.out.  ref_aux_sed: 
 what writeSED writes to output/SED.out (nu, lambda, SED per viewing angle, total energy) for the
 escapedPackets of the transport case of the same name.  ref_aux_writegrid.json: the records
 writeGrid writes to grid0-3.out, dustGrid.out and photoSource.out (numbers rendered with
@@ -41,7 +41,7 @@ import ref_cases  # noqa: E402
 
 def main(names):
     for name in names or list(ref_cases.REF_CASES) + list(ref_cases.AUX_CASES) + list(ref_cases.PHOTO_CASES) + \
-            ["sed:" + c for c in ref_cases.SED_CASES] + ["contcube:" + c for c in ref_cases.SED_CASES] + ["mie", "writegrid"]:
+            ["sed:" + c for c in ref_cases.SED_CASES] + ["contcube:" + c for c in ref_cases.SED_CASES] + ["taunu:" + c for c in ref_cases.TAUNU_CASES] + ["mie", "writegrid"]:
         if name == "writegrid":
             import json
             res = ref_cases.run_reference_writegrid()
@@ -49,6 +49,13 @@ def main(names):
             with open(path, "w") as fh:
                 json.dump(res, fh, indent=0)
             print(f"{name}: {os.path.getsize(path)} bytes, " + ", ".join(f"{k}: {len(v)} records" for k, v in res.items()))
+            continue
+        if name.startswith("taunu:"):
+            res = ref_cases.run_reference_taunu(name[6:])
+            path = os.path.join(HERE, f"ref_aux_taunu_{name[6:]}.npz")
+            np.savez_compressed(path, **res)
+            print(f"{name}: {os.path.getsize(path)} bytes, max tau {float(res['tau_x'].max()):.4g} {float(res['tau_z'].max()):.4g} "
+                  f"{float(res['tau_y'].max()):.4g}")
             continue
         if name == "mie":
             res = ref_cases.run_reference_mie()

@@ -421,6 +421,21 @@ def run_reference_mie():
 
 
 # ---------------------------------------------------------------------------------------------
+# writeTauNu / integratePathTauNu (mocassin_b200/output.py: tau_path, tau_nu)
+# ---------------------------------------------------------------------------------------------
+TAUNU_CASES = ["hii_sym_gas", "cube_clumpy_gasdust", "dust_shell_hg", "viewing_angles"]
+
+
+def run_reference_taunu(name):
+    from oracle import oracle as O
+    from oracle.f90ref.harness_aux import AuxReference
+
+    m, n, mode = make(name)
+    taus, lam = AuxReference(O.load(), math="libm").write_tau_nu(m)
+    return dict(tau_x=taus[0], tau_z=taus[1], tau_y=taus[2], lambda_um=lam)
+
+
+# ---------------------------------------------------------------------------------------------
 # writeContCube (K9 + the host scaling of mocassin_b200/output.py)
 # ---------------------------------------------------------------------------------------------
 def contcube_inputs(name):

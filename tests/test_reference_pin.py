@@ -247,6 +247,40 @@ def test_translated_mie_reproduces_golden(oracle_lib):
         assert np.array_equal(_bits(g) if g.dtype == np.float32 else g, _bits(w) if w.dtype == np.float32 else w), k
 
 
+@pytest.mark.parametrize("name", ref_cases.TAUNU_CASES)
+def test_tau_nu_matches_reference_writetaunu(name, tmp_path):
+    """mocassin_b200/output.py: tau_path / tau_nu (one march per direction, then a float32 running
+    sum per frequency over the opacity rows of the cells visited) against what the reference's own
+    writeTauNu -> integratePathTauNu writes to output/tauNu.out (one march per direction AND
+    frequency): bit-equal in all three directions."""
+    from mocassin_b200 import output
+
+    want = dict(np.load(os.path.join(GOLD, f"ref_aux_taunu_{name}.npz")))
+    m, n, mode = ref_cases.make(name)
+    g = m.grids[0]
+    asked = []
+
+    def rows(cells):
+        asked.append(len(cells))
+        return g.opacity[cells, :]
+    taus = output.write_tau_nu(str(tmp_path / "tauNu.out"), m, rows)
+    for got, key in zip(taus, ("tau_x", "tau_z", "tau_y")):
+        assert np.array_equal(_bits(got), _bits(want[key])), key
+    assert max(asked) <= g.nx + g.ny + g.nz            # a few dozen rows, not the table
+    lines = open(tmp_path / "tauNu.out").read().splitlines()
+    assert len(lines) == 3 * (m.nbins + 4) and lines[1].strip() == "direction: 1,0,0"
+    lam = np.array([float(ln.split()[0]) for ln in lines[3:3 + m.nbins]], np.float32)
+    assert np.allclose(lam, want["lambda_um"], rtol=1e-6)
+
+
+@pytest.mark.skipif(not HAVE_REF, reason="reference sources not present")
+def test_translated_writetaunu_reproduces_golden(oracle_lib):
+    want = dict(np.load(os.path.join(GOLD, "ref_aux_taunu_dust_shell_hg.npz")))
+    got = ref_cases.run_reference_taunu("dust_shell_hg")
+    for k, w in want.items():
+        assert np.array_equal(_bits(got[k]), _bits(w)), k
+
+
 @pytest.mark.parametrize("name", ref_cases.SED_CASES)
 def test_contcube_matches_reference_writecontcube(name, tmp_path):
     """mocassin_b200/output.py (the host part of writeContCube that follows the device reduction K9)

@@ -157,3 +157,28 @@ def test_device_sublimation_mask_equals_host_mask(cuda_lib):
     e.assemble_opacity(1, none, den, None, cold)
     assert not np.array_equal(e.get_opacity(1)[0], host[0])      # the mask does matter in this model
     e.close()
+
+
+@pytest.mark.parametrize("name", ["hii_sym_gas", "cube_clumpy_gasdust"])
+def test_device_opacity_rows_feed_tau_nu(cuda_lib, name):
+    """mcb200_get_opacity_rows: the gathered rows equal the rows of the full table, and tauNu.out's
+    three optical-depth columns computed from them equal those computed from the host table."""
+    from cases import make
+    from mocassin_b200 import output
+    from mocassin_b200.api import MocassinError, PacketEngine
+
+    m, _ = make(name)
+    g = m.grids[0]
+    e = PacketEngine(m, seed=1)
+    e.set_opacity()
+    full = e.get_opacity(1)[0]
+    cells = np.array([0, 1, g.nCells, 5, 5, g.nCells // 2], np.int32)
+    got = e.get_opacity_rows(1, cells)
+    assert np.array_equal(got.view(np.uint32), full[cells, :].view(np.uint32))
+    dev = output.tau_nu(m, lambda c: e.get_opacity_rows(1, c))
+    host = output.tau_nu(m, lambda c: g.opacity[c, :])
+    for a, b in zip(dev, host):
+        assert np.array_equal(a.view(np.uint32), b.view(np.uint32)) and a.max() > 0
+    with pytest.raises(MocassinError):
+        e.get_opacity_rows(1, np.array([g.nCells + 1], np.int32))
+    e.close()
