@@ -1,7 +1,7 @@
 """Run one of the reference's dust-only decks (e.g. benchmarks/dust/1D/p0tau1) through the CUDA
 library: the deck's own input.in, density, grain and n,k files -> Lucy iterations on the device
 (setDustPDF -> energyPacketDriver -> getDustT) with iterateMC's convergence and autoPackets
-rules -> output/SED.out, output/summary.out, output/dustGrid.out, output/grid0.out,
+rules -> output/SED.out, output/tauNu.out, output/summary.out, output/dustGrid.out, output/grid0.out,
 output/photoSource.out in the reference's layouts.
 
     python scripts/run_dust_deck.py <deck dir> <share dir with dustData/> [--out DIR] [--max-iter N]
@@ -84,6 +84,7 @@ def main():
     summary.close()
     raw, cnt = eng.fetch_sed()
     totalE = output.write_sed(os.path.join(a.out, "SED.out"), model, tables["widFlx"], raw)
+    output.write_tau_nu(os.path.join(a.out, "tauNu.out"), model, lambda cells: eng.get_opacity_rows(1, cells))
     checkpoint.write_checkpoint(a.out, model, lgConverged=[state["conv"]])
     checkpoint.write_photo_source(os.path.join(a.out, "photoSource.out"), model, ["blackbody"], [d.TStellar], [d.LStar],
                                   [state["nPhotons"]])

@@ -132,3 +132,6 @@ class OracleEngine:
 
     def fetch_sed(self):
         return self.sed_cnt
+
+    def get_opacity_rows(self, iG, cells):
+        return self.model.grids[iG - 1].opacity[np.asarray(cells), :]

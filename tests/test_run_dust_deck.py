@@ -28,12 +28,15 @@ def test_run_dust_deck_script_writes_the_reference_output_files(tmp_path, monkey
     assert abs(summary["total_energy_out_e36"] - 38.26) < 1e-3 * 38.26          # writeSED's total = LStar
     T = summary["Tdust_along_x"]
     assert 600 < T[0] < 900 and T[0] > T[3] > T[6]
-    for fn in ("SED.out", "summary.out", "dustGrid.out", "grid0.out", "photoSource.out"):
+    for fn in ("SED.out", "tauNu.out", "summary.out", "dustGrid.out", "grid0.out", "photoSource.out"):
         assert (out / fn).stat().st_size > 0, fn
     sed = (out / "SED.out").read_text().splitlines()
     assert sed[0].startswith(" Spectral energy distribution") and len([x for x in sed if x[:2] == " 1" or x[:2] == " 2"]) > 50
     assert "Total energy radiated out of the nebula" in sed[-3]
     assert "% converged cells in grid  1" in (out / "summary.out").read_text()
+    tau = np.array([[float(x) for x in ln.split()] for ln in (out / "tauNu.out").read_text().splitlines()[3:3 + 215]])
+    k = int(np.argmin(abs(tau[:, 0] - 1.0)))
+    assert abs(tau[k, 1] - 1.0) < 0.03                  # tau(1 um) = 1 along +x: the benchmark's definition
     # dustGrid.out reads back to the temperatures of the run
     m, t, d = deck.deck_from_arrays(dict(np.load(os.path.join(ROOT, "tests", "golden", "deck_p0tau1.npz"))))
     checkpoint.read_dust_grid(str(out / "dustGrid.out"), m)
