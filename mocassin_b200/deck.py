@@ -33,7 +33,7 @@ from typing import Callable, List, Optional
 import numpy as np
 
 from .model import F32, I32, Grid, Model, locate, number_active, star_indices
-from .workloads import blackbody_cdf, wid_flx
+from .workloads import wid_flx
 
 C_LIGHT = F32(2.9979250e10)       # constants_mod.f90
 FR1RYD = F32(3.28984e15)
@@ -465,22 +465,56 @@ def assemble_dust_xsec(Qsca, Qabs, gCos, radius, weight, abun):
 
 
 def dust_em_integral(xSec, absP, nu, widFlx, nTemps: int = N_TEMPS) -> np.ndarray:
-    """dustEmissionInt (dust_mod.f90:145-181): (nSpecies, nSizes, nTemps), T = 1..nTemps K.
-    Planck function as getFlux (continuum_mod.f90:359-416) in float64, rounded once."""
+    """dustEmissionInt (dust_mod.f90:145-181): (nSpecies, nSizes, nTemps), T = 1..nTemps K, in the
+    reference's float32: per temperature the running sum over the bins of
+    ((xSec*getFlux)*fr1Ryd)*widFlx, then *hPlanck*4."""
     nSp, nSz = absP.shape[0] - 1, absP.shape[1]
     nb = nu.shape[0]
-    T = np.arange(1, nTemps + 1, dtype=np.float64)
-    nu64 = nu.astype(np.float64)
-    x = 1.5789e5 * nu64[None, :] / T[:, None]          # hcRyd_k
-    bb = np.where(x > 86.0, 0.0, 0.5250229 * nu64[None, :] ** 3 / np.expm1(np.minimum(x, 86.0)) / 6.6262e-27)
+    T = np.arange(1, nTemps + 1, dtype=F32)
+    w = np.asarray(widFlx, dtype=F32)
+    bb = [get_flux_blackbody(nu[i], T) for i in range(nb)]     # (nbins)(nTemps)
     em = np.zeros((nSp, nSz, nTemps), dtype=F32, order="F")
     for s in range(nSp):
         for ai in range(nSz):
             o = int(absP[s + 1, ai]) - 1
-            cabs = xSec[o:o + nb].astype(np.float64)
-            em[s, ai, :] = ((bb * (cabs * 3.28984e15 * widFlx.astype(np.float64))[None, :]).sum(axis=1)
-                            * 6.6262e-27 * 4.0).astype(F32)
+            acc = np.zeros(nTemps, dtype=F32)
+            for i in range(nb):
+                acc = (acc + (((xSec[o + i] * bb[i]).astype(F32) * FR1RYD).astype(F32) * w[i]).astype(F32)).astype(F32)
+            em[s, ai, :] = ((acc * HPLANCK).astype(F32) * F32(4.0)).astype(F32)
     return em
+
+
+def get_flux_blackbody(nu: np.ndarray, T) -> np.ndarray:
+    """getFlux(nu, T, 'blackbody') (continuum_mod.f90:359-401) in the reference's float32: Planck
+    function / h, Wien form above h nu / k T = 86 (with its double-precision exp), Rayleigh-Jeans
+    where exp(x) - 1 rounds to zero."""
+    e = np.asarray(nu, dtype=F32)
+    T = np.asarray(T, dtype=F32)         # nu and T broadcast against each other
+    const = F32(F32(0.5250229) / HPLANCK)
+    x = (F32(157893.94) * e).astype(F32) / T
+    e3 = (((const * e).astype(F32) * e).astype(F32) * e).astype(F32)
+    with np.errstate(over="ignore", invalid="ignore", divide="ignore"):
+        wien = (e3.astype(np.float64) * np.exp((-x).astype(F32).astype(np.float64))).astype(F32)
+        den = (np.exp(x).astype(F32) - F32(1.0)).astype(F32)
+        rj = ((((F32(3.32154e-6) * e).astype(F32) * e).astype(F32) * T).astype(F32) / HPLANCK).astype(F32)
+        planck = (e3 / den).astype(F32)
+    return np.where(x > F32(86.0), wien, np.where(den <= 0, rj, planck)).astype(F32)
+
+
+def stellar_cdf(T, nu: np.ndarray, widFlx: np.ndarray) -> np.ndarray:
+    """inSpectrumProbDen of a blackbody source: setContinuum's inSpectrumErg = getFlux (:112) and
+    setProbDen (continuum_mod.f90:418-474) with its mix of REAL and DOUBLE PRECISION."""
+    f = get_flux_blackbody(nu, T).astype(np.float64)           # inSpSumErg = real(inSpectrumErg)
+    w = np.asarray(widFlx, dtype=F32)
+    norm = F32(0.0)
+    for i in range(f.shape[0]):
+        norm = F32(np.float64(norm) + f[i] * np.float64(w[i]))
+    cdf = np.zeros(f.shape[0], dtype=F32)
+    cdf[0] = F32(f[0] * np.float64(w[0]) / np.float64(norm))
+    for i in range(1, f.shape[0]):
+        cdf[i] = F32(np.float64(cdf[i - 1]) + f[i] * np.float64(w[i]) / np.float64(norm))
+    cdf[cdf >= cdf.max()] = F32(1.0)
+    return cdf
 
 
 def dust_opacity(g: Grid, tables: dict) -> None:
@@ -563,7 +597,7 @@ def load_dust_deck(run_dir: str, share_dir: str, input_file: str = "input.in"):
     dust_opacity(g, tables)
 
     wid = widFlx                                               # setProbDen uses widFlx
-    cdf = blackbody_cdf(d.TStellar, nu, wid)
+    cdf = stellar_cdf(d.TStellar, nu, wid)
     pos = [list(d.starPosition)]
     sidx = [star_indices(g, d.starPosition) + [1]]
     nPhot = int(d.nPhotons)

@@ -77,7 +77,7 @@ AUX_SOURCES = [
     ('grid_mod.f90', False, {'writegrid'}, None),
     ('composition_mod.f90', True, None, None),
     ('set_input_mod.f90', True, None, None),
-    ('continuum_mod.f90', False, {'getflux'}, None),
+    ('continuum_mod.f90', False, {'getflux', 'setprobden'}, None),
     ('ionization_mod.f90', False, {'ionizationdriver', 'edensum', 'addopacity'}, None),
     ('emission_mod.f90', False, {'emissiondriver'}, {'setdustpdf'}),
     ('update_mod.f90', False, {'updatecell'}, {'getdustt'}),
@@ -109,6 +109,11 @@ AUX_SLICES = [
          glue_decls=['real, intent(out) :: outste, outdif'],
          glue_end=['outste = heatste', 'outdif = heatdif'],
          guards={936: 'real, intent(out) :: heatint', 1123: 'heatste = 0.', 1234: 'end do'}),
+    # dustEmissionInt (internal to dustDriver): the emission integrals getDustT inverts
+    dict(file='dust_mod.f90', name='dust_emission_int', args='',
+         decls=[(148, 152)], body=[(155, 181)], glue_decls=['integer :: err'], glue_end=[],
+         guards={148: 'real :: bb', 155: 'allocate(dustemintegral(1:nspecies,1:nsizes,ntemps)', 170: 'bb = getflux(nuarray(i), real(nt), cshapeloc)',
+                 181: 'dustemintegral = dustemintegral*hplanck*4.'}),
     # makeDustXsec: from efficiencies to cross-sections, the dust part of xSecArray, its pointer
     # tables and gSca, for one dust component (the tail of the icomp loop)
     dict(file='ph_mod.f90', name='dust_xsec_assembly', args='in_icomp, in_csca, in_cabs, in_gcos',
@@ -130,7 +135,7 @@ AUX_SLICES = [
 # oracle takes as an input (ff1), so the harness sets those arrays directly
 AUX_EXTERNS = {'boltgaunt'}
 # procedures that must translate completely, and the untranslated statements tolerated in them
-AUX_STRICT = {'writegrid': 0, 'writesed': 0, 'writecontcube': 0, 'writetaunu': 0, 'integratepathtaunu': 0, 'bhmie': 0, 'getqs': 0, 'dust_xsec_assembly': 0, 'opacity_block': 0, 'photo_rates': 0, 'photo_heat': 0, 'getoutershell': 0, 'ionizationdriver': 0, 'edensum': 0, 'addopacity': 0, 'putopacity': 0, 'inopacity': 0, 'getflux': 0, 'locate': 0, 'linearmap': 0,
+AUX_STRICT = {'writegrid': 0, 'writesed': 0, 'writecontcube': 0, 'writetaunu': 0, 'integratepathtaunu': 0, 'bhmie': 0, 'getqs': 0, 'dust_xsec_assembly': 0, 'dust_emission_int': 0, 'opacity_block': 0, 'photo_rates': 0, 'photo_heat': 0, 'getoutershell': 0, 'ionizationdriver': 0, 'edensum': 0, 'addopacity': 0, 'putopacity': 0, 'inopacity': 0, 'getflux': 0, 'setprobden': 0, 'locate': 0, 'linearmap': 0,
               'setdustpdf': 1,      # call qHeat (lgQHeat branch)
               'getdustt': 1}        # resLineHeating (gas + resonance-line transfer branch)
 

@@ -297,6 +297,40 @@ class AuxReference:
                     dustScaXsecP=G.dustscaxsecp.a.astype(np.int32), dustAbsXsecP=G.dustabsxsecp.a.astype(np.int32),
                     gSca=G.gsca.a.copy(), absOpacSpecies=G.absopacspecies.a.copy())
 
+    def stellar_cdf(self, T, nu, widFlx):
+        """inSpectrumErg(i) = getFlux(nuArray(i), T, 'blackbody') (setContinuum, continuum_mod.f90:112)
+        followed by setProbDen(1) (:418-474).  Returns (getFlux values, inSpectrumProbDen(1, :))."""
+        G, ref = self.G, self.ref
+        nb = len(nu)
+        G.nbins = int(nb)
+        G.nuarray = rt.wrap(_F(nu, np.float32))
+        G.widflx = rt.wrap(_F(widFlx, np.float32))
+        G.lymanp = 1
+        shape = 'blackbody'.ljust(50)
+        flux = np.array([ref.p_getflux(np.float32(v), np.float32(T), shape) for v in nu], np.float32)
+        G.inspectrumerg = rt.wrap(flux.astype(np.float64))
+        G.inspectrumphot = rt.wrap(np.zeros(nb, np.float64))
+        G.inspectrumprobden = rt.wrap(np.zeros((2, nb), np.float32, order='F'), (0, 1))
+        G.contshape = rt.wrap(np.array([shape, shape], dtype=object), (0,))
+        with np.errstate(all='ignore'):
+            ref.p_setprobden(1)
+        return flux, G.inspectrumprobden.a[1, :].copy()
+
+    def dust_emission_int(self, xSec, absP, nu, widFlx, nTemps):
+        """dustEmissionInt (dust_mod.f90:145-181, statement-range slice): dustEmIntegral
+        (nSpecies, nSizes, nTemps) from xSecArray and the 1-based pointers absP(nSpecies, nSizes).
+        nTemps is a parameter of the reference (3000); the harness may shrink it (Python loops)."""
+        G, ref = self.G, self.ref
+        nSp, nSz = absP.shape
+        G.nspecies, G.nsizes, G.nbins, G.ntemps = int(nSp), int(nSz), int(len(nu)), int(nTemps)
+        G.nuarray = rt.wrap(_F(nu, np.float32))
+        G.widflx = rt.wrap(_F(widFlx, np.float32))
+        G.xsecarray = rt.wrap(_F(xSec, np.float32))
+        G.dustabsxsecp = rt.wrap(_F(np.vstack([np.zeros((1, nSz), np.int64), np.asarray(absP, np.int64)]), np.int64), (0, 1))
+        with np.errstate(all='ignore'):
+            ref.p_dust_emission_int()
+        return G.dustemintegral.a.copy()
+
     def linear_map(self, y, x, x_new):
         """linearMap (interpolation_mod.f90:86-106)."""
         out = rt.wrap(np.zeros(len(x_new), np.float32))

@@ -416,8 +416,19 @@ def run_reference_mie():
     for s in range(2):
         Qa[s], Qs[s], G[s] = A.get_qs(I["Ere"][s], I["Eim"][s], I["radius"], I["nu"])
     asm = A.dust_xsec_assembly(Qs, Qa, G, I["radius"], I["weight"], I["abun"], 40)
-    return dict(bhmie=q, Qabs=Qa, Qsca=Qs, gCos=G, mapped=A.linear_map(I["yt"], I["xt"], I["nu"]),
-                **{"asm_" + k: np.asarray(v) for k, v in asm.items()})
+    wid = W.wid_flx(I["nu"])
+    out = dict(bhmie=q, Qabs=Qa, Qsca=Qs, gCos=G, mapped=A.linear_map(I["yt"], I["xt"], I["nu"]),
+               **{"asm_" + k: np.asarray(v) for k, v in asm.items()})
+    # the stellar CDF (getFlux + setProbDen) at four temperatures, and dustEmissionInt for the first
+    # 80 K of the assembled cross-sections (nTemps is 3000 in the reference: Python loops)
+    for T in MIE_TSTAR:
+        out[f"flux_{int(T)}"], out[f"cdf_{int(T)}"] = A.stellar_cdf(T, I["nu"], wid)
+    out["emint"] = A.dust_emission_int(asm["xSecArray"], asm["dustAbsXsecP"][1:, :], I["nu"], wid, MIE_NTEMPS)
+    return out
+
+
+MIE_TSTAR = (2500.0, 5800.0, 40000.0, 150000.0)
+MIE_NTEMPS = 80
 
 
 # ---------------------------------------------------------------------------------------------

@@ -216,8 +216,9 @@ def test_translated_writesed_reproduces_golden(oracle_lib):
 def test_dust_optics_match_reference_bhmie_getqs_makedustxsec():
     """mocassin_b200/deck.py against the reference's own code run through the translator (COMPLEX
     arithmetic, statement functions): BHmie on 153 (x, m) pairs, getQs on 2 species x 3 sizes x 40
-    bins, linearMap, and the tail of makeDustXsec (cross-sections, xSecArray layout incl. its
-    over-advanced xSecTop, pointer tables, gSca) -- all bit-equal."""
+    bins, linearMap, the tail of makeDustXsec (cross-sections, xSecArray layout incl. its
+    over-advanced xSecTop, pointer tables, gSca), getFlux + setProbDen (the stellar CDF) and
+    dustEmissionInt -- all bit-equal."""
     from mocassin_b200 import deck
 
     want = dict(np.load(os.path.join(GOLD, "ref_aux_mie.npz")))
@@ -236,6 +237,15 @@ def test_dust_optics_match_reference_bhmie_getqs_makedustxsec():
     assert np.array_equal(_bits(asm["gSca"]), _bits(want["asm_gSca"]))
     assert np.array_equal(asm["dustScaXsecP"], want["asm_dustScaXsecP"])
     assert np.array_equal(asm["dustAbsXsecP"], want["asm_dustAbsXsecP"])
+    # stellar CDF: getFlux (Planck / Wien / Rayleigh-Jeans branches) + setProbDen; dustEmissionInt
+    from mocassin_b200 import workloads as W
+    wid = W.wid_flx(I["nu"])
+    for T in ref_cases.MIE_TSTAR:
+        assert np.array_equal(_bits(deck.get_flux_blackbody(I["nu"], T)), _bits(want[f"flux_{int(T)}"])), T
+        assert np.array_equal(_bits(deck.stellar_cdf(T, I["nu"], wid)), _bits(want[f"cdf_{int(T)}"])), T
+    em = deck.dust_em_integral(asm["xSecArray"], asm["dustAbsXsecP"], I["nu"], wid, nTemps=ref_cases.MIE_NTEMPS)
+    assert em.shape == want["emint"].shape == (2, 3, ref_cases.MIE_NTEMPS)
+    assert np.array_equal(_bits(em), _bits(want["emint"]))
 
 
 @pytest.mark.skipif(not HAVE_REF, reason="reference sources not present")
