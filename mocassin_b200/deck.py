@@ -229,29 +229,38 @@ def read_ndust(path: str, nx: int, ny: int, nz: int):
 # ---------------------------------------------------------------------------------------
 # grains: sizes, species, optical constants, Mie
 # ---------------------------------------------------------------------------------------
+def normalise_grain_weights(rad: np.ndarray, w: np.ndarray) -> np.ndarray:
+    """ph_mod.f90:986-1012: weights times the trapezoid widths da of the size grid, normalised to
+    sum 1 (float32, running sum); a single size gets weight 1."""
+    n = rad.shape[0]
+    rad, w = np.asarray(rad, F32), np.asarray(w, F32)
+    if n == 1:
+        return np.ones(1, dtype=F32)
+    da = np.zeros(n, dtype=F32)
+    da[0] = rad[1] - rad[0]
+    da[1:-1] = (rad[2:] - rad[:-2]) / F32(2.0)
+    da[-1] = rad[-1] - rad[-2]
+    norm = F32(0.0)
+    for i in range(n):
+        norm = F32(norm + F32(w[i] * da[i]))
+    out = ((w * da).astype(F32) / norm).astype(F32)
+    if not np.all(out >= 0):
+        raise ValueError("makeDustXSec : Invalid grain weight")
+    return out
+
+
 def read_grain_sizes(path: str):
-    """ph_mod.f90:958-1010: radii [um] and weights, normalised with the trapezoid widths da."""
+    """ph_mod.f90:958-1012: radii [um] and weights of the sizes file, weights normalised."""
     with open(path) as fh:
         n = int(fh.readline().split()[0])
+        if n < 1:
+            raise ValueError("makeDustXSec : Invalid nSizes")
         rad = np.zeros(n, dtype=F32)
         w = np.zeros(n, dtype=F32)
         for i in range(n):
             t = fh.readline().split()
             rad[i], w[i] = F32(_real(t[1])), F32(_real(t[2]))
-    if n > 1:
-        da = np.zeros(n, dtype=F32)
-        da[0] = rad[1] - rad[0]
-        da[1:-1] = (rad[2:] - rad[:-2]) / F32(2.0)
-        da[-1] = rad[-1] - rad[-2]
-        norm = F32(0.0)
-        for i in range(n):
-            norm = F32(norm + w[i] * da[i])
-        w = (w * da / norm).astype(F32)
-        if not np.all(w >= 0):
-            raise ValueError("makeDustXSec : Invalid grain weight")
-    else:
-        w[0] = F32(1.0)
-    return rad, w
+    return rad, normalise_grain_weights(rad, w)
 
 
 def read_grain_species(path: str):

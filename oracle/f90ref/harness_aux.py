@@ -331,6 +331,15 @@ class AuxReference:
             ref.p_dust_emission_int()
         return G.dustemintegral.a.copy()
 
+    def grain_weights(self, radius, weight):
+        """makeDustXsec's normalisation of the size distribution (ph_mod.f90:986-1012, slice)."""
+        G = self.G
+        G.nsizes = int(len(radius))
+        G.grainradius = rt.wrap(_F(radius, np.float32))
+        G.grainweight = rt.wrap(_F(weight, np.float32).copy())
+        self.ref.p_grain_weights()
+        return G.grainweight.a.copy()
+
     def linear_map(self, y, x, x_new):
         """linearMap (interpolation_mod.f90:86-106)."""
         out = rt.wrap(np.zeros(len(x_new), np.float32))

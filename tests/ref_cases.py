@@ -402,7 +402,10 @@ def mie_inputs():
     # outside the table on both sides
     xt = np.sort(10 ** rng.uniform(-3.0, 0.5, 25)).astype(np.float32)
     yt = rng.uniform(0.5, 3.0, 25).astype(np.float32)
-    return dict(x=x, m=m, nu=nu, Ere=Ere, Eim=Eim, radius=radius, weight=weight, abun=abun, xt=xt, yt=yt)
+    # an MRN-like size grid (10 sizes, weights ~ a^-3.5) for the weight normalisation
+    sizes = (0.04 * (0.4 / 0.04) ** (np.arange(10) / 9.0)).astype(np.float32)
+    return dict(x=x, m=m, nu=nu, Ere=Ere, Eim=Eim, radius=radius, weight=weight, abun=abun, xt=xt, yt=yt,
+                sizes=sizes, size_weights=(sizes.astype(np.float64) ** -3.5).astype(np.float32))
 
 
 def run_reference_mie():
@@ -423,6 +426,7 @@ def run_reference_mie():
     # 80 K of the assembled cross-sections (nTemps is 3000 in the reference: Python loops)
     for T in MIE_TSTAR:
         out[f"flux_{int(T)}"], out[f"cdf_{int(T)}"] = A.stellar_cdf(T, I["nu"], wid)
+    out["grain_weights"] = A.grain_weights(I["sizes"], I["size_weights"])
     out["emint"] = A.dust_emission_int(asm["xSecArray"], asm["dustAbsXsecP"][1:, :], I["nu"], wid, MIE_NTEMPS)
     return out
 

@@ -243,6 +243,8 @@ def test_dust_optics_match_reference_bhmie_getqs_makedustxsec():
     for T in ref_cases.MIE_TSTAR:
         assert np.array_equal(_bits(deck.get_flux_blackbody(I["nu"], T)), _bits(want[f"flux_{int(T)}"])), T
         assert np.array_equal(_bits(deck.stellar_cdf(T, I["nu"], wid)), _bits(want[f"cdf_{int(T)}"])), T
+    gw = deck.normalise_grain_weights(I["sizes"], I["size_weights"])
+    assert np.array_equal(_bits(gw), _bits(want["grain_weights"])) and abs(float(gw.sum()) - 1.0) < 1e-6
     em = deck.dust_em_integral(asm["xSecArray"], asm["dustAbsXsecP"], I["nu"], wid, nTemps=ref_cases.MIE_NTEMPS)
     assert em.shape == want["emint"].shape == (2, 3, ref_cases.MIE_NTEMPS)
     assert np.array_equal(_bits(em), _bits(want["emint"]))
