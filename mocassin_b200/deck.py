@@ -32,7 +32,7 @@ from typing import Callable, List, Optional
 
 import numpy as np
 
-from .model import F32, I32, Grid, Model, locate, number_active, star_indices
+from .model import F32, I32, Grid, Model, locate, number_active, set_star_position
 from .workloads import wid_flx
 
 C_LIGHT = F32(2.9979250e10)       # constants_mod.f90
@@ -607,8 +607,7 @@ def load_dust_deck(run_dir: str, share_dir: str, input_file: str = "input.in"):
 
     wid = widFlx                                               # setProbDen uses widFlx
     cdf = stellar_cdf(d.TStellar, nu, wid)
-    pos = [list(d.starPosition)]
-    sidx = [star_indices(g, d.starPosition) + [1]]
+    pos, sidx = set_star_position([g], [list(d.starPosition)])   # the keyword is in units of the axis ends
     nPhot = int(d.nPhotons)
     view = {}
     if d.nAngleBins > 0:
@@ -675,8 +674,8 @@ def deck_from_arrays(a: dict):
     model = Model(grids=[g], nbins=nbins, nuArray=nu,
                   inSpectrumProbDen=np.stack([np.zeros(nbins, F32), np.asarray(a["cdf"], F32)]).astype(F32),
                   deltaE=np.asarray([0.0, F32(d.LStar) / F32(int(d.nPhotons))], dtype=F32),
-                  starPosition=np.asarray([list(d.starPosition)], dtype=F32),
-                  starIndeces=np.asarray([star_indices(g, d.starPosition) + [1]], dtype=I32),
+                  starPosition=set_star_position([g], [list(d.starPosition)])[0],
+                  starIndeces=set_star_position([g], [list(d.starPosition)])[1],
                   lgDust=True, lgGas=False, lgSymmetricXYZ=d.lgSymmetricXYZ, lgIsotropic=d.lgIsotropic,
                   R_out=float(d.R_out), gSca=np.asarray(a["gSca"], F32), nSpeciesMax=nSp, nSizes=nSz,
                   nSpeciesPart=np.asarray([nSp], dtype=I32), grainAbun=grainAbun,

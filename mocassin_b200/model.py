@@ -218,3 +218,39 @@ def star_indices(grid: Grid, pos) -> list[int]:
                 ns += 1
         out.append(max(ns, 1))
     return out
+
+
+def set_star_position(grids, relative):
+    """setStarPosition (grid_mod.f90:3569-3648): the `starPosition` keyword gives coordinates in
+    units of the mother grid's last axis points; returns (positions [cm] float32 (nStars, 3),
+    starIndeces int32 (nStars, 4)).  A star whose mother cell points into a sub-grid
+    (active < 0) is located in that sub-grid -- with the reference's yAxis in the z mid-point test,
+    and with its other quirk: nxA/nyA/nzA are overwritten by the sub-grid's extents and not
+    restored, so every LATER star is scaled by, and searched up to, mother-axis point number
+    nx(sub-grid) instead of the last one (:3581-3583, :3607-3609)."""
+    g1 = grids[0]
+    pos = np.zeros((len(relative), 3), dtype=F32)
+    idx = np.zeros((len(relative), 4), dtype=I32)
+    nA = [g1.nx, g1.ny, g1.nz]
+
+    def find(a, v, n, mid=None):
+        mid = a if mid is None else mid
+        p = locate(a, v)
+        if p < n:
+            # p = 0 (below the axis) indexes xA(0) in the reference; only reachable off-grid
+            if p >= 1 and F32(v) > F32(F32(mid[p - 1] + mid[p]) / F32(2.0)):
+                p += 1
+        return p
+    for i, rel in enumerate(relative):
+        axes = (g1.xAxis, g1.yAxis, g1.zAxis)
+        pos[i] = [F32(F32(rel[k]) * axes[k][nA[k] - 1]) for k in range(3)]
+        x, y, z = (find(axes[k], pos[i, k], nA[k]) for k in range(3))
+        a = int(g1.active[x - 1, y - 1, z - 1])
+        if a >= 0:
+            idx[i] = [x, y, z, 1]
+        else:
+            s = grids[-a - 1]
+            nA = [s.nx, s.ny, s.nz]
+            idx[i] = [find(s.xAxis, pos[i, 0], nA[0]), find(s.yAxis, pos[i, 1], nA[1]),
+                      find(s.zAxis, pos[i, 2], nA[2], mid=s.yAxis), -a]
+    return pos, idx

@@ -340,6 +340,31 @@ class AuxReference:
         self.ref.p_grain_weights()
         return G.grainweight.a.copy()
 
+    def set_star_position(self, grids, relative):
+        """setStarPosition(xA, yA, zA, grid) (grid_mod.f90:3569-3648) for stars at `relative`
+        positions (units of the mother grid's last axis points).  Returns (positions, starIndeces)."""
+        G, ref = self.G, self.ref
+        G.nstars = len(relative)
+        sp = np.empty(len(relative), dtype=object)
+        for i, r in enumerate(relative):
+            v = ref.T_vector()
+            v.x, v.y, v.z = (np.float32(c) for c in r)
+            sp[i] = v
+        G.starposition = rt.wrap(sp)
+        G.starindeces = None
+        gs = np.empty(len(grids), dtype=object)
+        for i, g in enumerate(grids):
+            t = ref.T_grid_type()
+            t.nx, t.ny, t.nz, t.ncells = g.nx, g.ny, g.nz, int(g.nCells)
+            t.xaxis, t.yaxis, t.zaxis = (rt.wrap(_F(a, np.float32)) for a in (g.xAxis, g.yAxis, g.zAxis))
+            t.active = rt.wrap(_F(g.active, np.int32))
+            gs[i] = t
+        g1 = grids[0]
+        ref.p_setstarposition(rt.wrap(_F(g1.xAxis, np.float32)), rt.wrap(_F(g1.yAxis, np.float32)),
+                              rt.wrap(_F(g1.zAxis, np.float32)), rt.wrap(gs))
+        pos = np.array([[G.starposition.a[i].x, G.starposition.a[i].y, G.starposition.a[i].z] for i in range(len(relative))], np.float32)
+        return pos, np.asarray(G.starindeces.a, np.int32)
+
     def linear_map(self, y, x, x_new):
         """linearMap (interpolation_mod.f90:86-106)."""
         out = rt.wrap(np.zeros(len(x_new), np.float32))

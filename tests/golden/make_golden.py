@@ -41,7 +41,7 @@ import ref_cases  # noqa: E402
 
 def main(names):
     for name in names or list(ref_cases.REF_CASES) + list(ref_cases.AUX_CASES) + list(ref_cases.PHOTO_CASES) + \
-            ["sed:" + c for c in ref_cases.SED_CASES] + ["contcube:" + c for c in ref_cases.SED_CASES] + ["taunu:" + c for c in ref_cases.TAUNU_CASES] + ["mie", "writegrid"]:
+            ["sed:" + c for c in ref_cases.SED_CASES] + ["contcube:" + c for c in ref_cases.SED_CASES] + ["taunu:" + c for c in ref_cases.TAUNU_CASES] + ["mie", "starpos", "writegrid"]:
         if name == "writegrid":
             import json
             res = ref_cases.run_reference_writegrid()
@@ -56,6 +56,12 @@ def main(names):
             np.savez_compressed(path, **res)
             print(f"{name}: {os.path.getsize(path)} bytes, max tau {float(res['tau_x'].max()):.4g} {float(res['tau_z'].max()):.4g} "
                   f"{float(res['tau_y'].max()):.4g}")
+            continue
+        if name == "starpos":
+            res = ref_cases.run_reference_starpos()
+            path = os.path.join(HERE, "ref_aux_starpos.npz")
+            np.savez_compressed(path, **res)
+            print(f"{name}: {os.path.getsize(path)} bytes, " + ", ".join(f"{k}{tuple(v.shape)}" for k, v in res.items()))
             continue
         if name == "mie":
             res = ref_cases.run_reference_mie()

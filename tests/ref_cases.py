@@ -436,6 +436,34 @@ MIE_NTEMPS = 80
 
 
 # ---------------------------------------------------------------------------------------------
+# setStarPosition (mocassin_b200/model.py: set_star_position)
+# ---------------------------------------------------------------------------------------------
+def starpos_inputs():
+    """{case: (grids, relative positions)}: multi-grid symmetric / non-symmetric and a plain cube;
+    each list holds a star in the sub-grid followed by stars elsewhere (the order matters: the
+    reference keeps the sub-grid's extents for the stars that follow)."""
+    rng = np.random.default_rng(77)
+    out = {}
+    for name, m in (("multigrid_sym", W.multigrid()), ("multigrid_nonsym", W.multigrid(symmetric=False, n=15)),
+                    ("cube", W.synthetic_cube(n=12, nbins=40, nPhotons=10))):
+        lo = 0.0 if m.lgSymmetricXYZ else -0.9
+        rel = [list(rng.uniform(lo, 0.9, 3)) for _ in range(6)] + [[0.0, 0.0, 0.0]] + [list(rng.uniform(lo, 0.9, 3)) for _ in range(20)]
+        out[name] = (m.grids, np.array(rel, np.float32))
+    return out
+
+
+def run_reference_starpos():
+    from oracle import oracle as O
+    from oracle.f90ref.harness_aux import AuxReference
+
+    A = AuxReference(O.load(), math="libm")
+    res = {}
+    for name, (grids, rel) in starpos_inputs().items():
+        res[name + "_pos"], res[name + "_idx"] = A.set_star_position(grids, rel.tolist())
+    return res
+
+
+# ---------------------------------------------------------------------------------------------
 # writeTauNu / integratePathTauNu (mocassin_b200/output.py: tau_path, tau_nu)
 # ---------------------------------------------------------------------------------------------
 TAUNU_CASES = ["hii_sym_gas", "cube_clumpy_gasdust", "dust_shell_hg", "viewing_angles"]

@@ -259,6 +259,33 @@ def test_translated_mie_reproduces_golden(oracle_lib):
         assert np.array_equal(_bits(g) if g.dtype == np.float32 else g, _bits(w) if w.dtype == np.float32 else w), k
 
 
+def test_set_star_position_matches_reference():
+    """model.set_star_position against the reference's own setStarPosition (grid_mod.f90:3569-3648)
+    on 27 stars per case: positions and starIndeces equal, including the stars that follow one in a
+    sub-grid (the reference keeps the sub-grid's nx, ny, nz for them: they are scaled by and located
+    up to mother-axis point nx(sub-grid))."""
+    from mocassin_b200.model import set_star_position
+
+    want = dict(np.load(os.path.join(GOLD, "ref_aux_starpos.npz")))
+    quirk = False
+    for name, (grids, rel) in ref_cases.starpos_inputs().items():
+        pos, idx = set_star_position(grids, rel.tolist())
+        assert np.array_equal(_bits(pos), _bits(want[name + "_pos"])), name
+        assert np.array_equal(idx, want[name + "_idx"]), name
+        if len(grids) > 1:
+            later = pos[7:, 0] / (rel[7:, 0] * grids[0].xAxis[-1])
+            quirk = quirk or bool(np.all(later < 0.99))
+    assert quirk        # the later stars of the multi-grid cases are NOT where the keyword puts them
+
+
+@pytest.mark.skipif(not HAVE_REF, reason="reference sources not present")
+def test_translated_setstarposition_reproduces_golden(oracle_lib):
+    want = dict(np.load(os.path.join(GOLD, "ref_aux_starpos.npz")))
+    got = ref_cases.run_reference_starpos()
+    for k, w in want.items():
+        assert np.array_equal(_bits(np.asarray(got[k])), _bits(w)), k
+
+
 @pytest.mark.parametrize("name", ref_cases.TAUNU_CASES)
 def test_tau_nu_matches_reference_writetaunu(name, tmp_path):
     """mocassin_b200/output.py: tau_path / tau_nu (one march per direction, then a float32 running
