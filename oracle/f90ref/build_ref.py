@@ -74,7 +74,7 @@ AUX_SOURCES = [
     ('common_mod.f90', True, None, None),
     ('ph_mod.f90', False, {'bhmie', 'getqs'}, None),      # module xSec_mod; BHmie (COMPLEX arithmetic, statement functions)
     ('hydro_mod.f90', False, {'getoutershell'}, None),   # module elements_mod
-    ('grid_mod.f90', False, {'writegrid', 'setstarposition'}, None),
+    ('grid_mod.f90', False, {'writegrid', 'setstarposition', 'getvolume'}, None),
     ('composition_mod.f90', True, None, None),
     ('set_input_mod.f90', True, None, None),
     ('continuum_mod.f90', False, {'getflux', 'setprobden'}, None),
@@ -139,7 +139,7 @@ AUX_SLICES = [
 # oracle takes as an input (ff1), so the harness sets those arrays directly
 AUX_EXTERNS = {'boltgaunt'}
 # procedures that must translate completely, and the untranslated statements tolerated in them
-AUX_STRICT = {'writegrid': 0, 'setstarposition': 0, 'writesed': 0, 'writecontcube': 0, 'writetaunu': 0, 'integratepathtaunu': 0, 'bhmie': 0, 'getqs': 0, 'dust_xsec_assembly': 0, 'dust_emission_int': 0, 'grain_weights': 0, 'opacity_block': 0, 'photo_rates': 0, 'photo_heat': 0, 'getoutershell': 0, 'ionizationdriver': 0, 'edensum': 0, 'addopacity': 0, 'putopacity': 0, 'inopacity': 0, 'getflux': 0, 'setprobden': 0, 'locate': 0, 'linearmap': 0,
+AUX_STRICT = {'writegrid': 0, 'setstarposition': 0, 'getvolume': 0, 'writesed': 0, 'writecontcube': 0, 'writetaunu': 0, 'integratepathtaunu': 0, 'bhmie': 0, 'getqs': 0, 'dust_xsec_assembly': 0, 'dust_emission_int': 0, 'grain_weights': 0, 'opacity_block': 0, 'photo_rates': 0, 'photo_heat': 0, 'getoutershell': 0, 'ionizationdriver': 0, 'edensum': 0, 'addopacity': 0, 'putopacity': 0, 'inopacity': 0, 'getflux': 0, 'setprobden': 0, 'locate': 0, 'linearmap': 0,
               'setdustpdf': 1,      # call qHeat (lgQHeat branch)
               'getdustt': 1}        # resLineHeating (gas + resonance-line transfer branch)
 

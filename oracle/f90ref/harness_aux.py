@@ -365,6 +365,15 @@ class AuxReference:
         pos = np.array([[G.starposition.a[i].x, G.starposition.a[i].y, G.starposition.a[i].z] for i in range(len(relative))], np.float32)
         return pos, np.asarray(G.starindeces.a, np.int32)
 
+    def get_volume(self, g, symmetric, cells):
+        """getVolume(grid, xP, yP, zP) (grid_mod.f90:2876-2965) for a list of (xP, yP, zP)."""
+        G, ref = self.G, self.ref
+        G.lg1d, G.lgsymmetricxyz, G.ngrids = False, bool(symmetric), 1
+        t = ref.T_grid_type()
+        t.nx, t.ny, t.nz = g.nx, g.ny, g.nz
+        t.xaxis, t.yaxis, t.zaxis = (rt.wrap(_F(a, np.float32)) for a in (g.xAxis, g.yAxis, g.zAxis))
+        return np.array([ref.p_getvolume(t, int(x), int(y), int(z)) for x, y, z in cells], np.float32)
+
     def linear_map(self, y, x, x_new):
         """linearMap (interpolation_mod.f90:86-106)."""
         out = rt.wrap(np.zeros(len(x_new), np.float32))

@@ -460,7 +460,26 @@ def run_reference_starpos():
     res = {}
     for name, (grids, rel) in starpos_inputs().items():
         res[name + "_pos"], res[name + "_idx"] = A.set_star_position(grids, rel.tolist())
+    for name, (g, sym, cells) in volume_inputs().items():
+        res["vol_" + name] = A.get_volume(g, sym, cells)
     return res
+
+
+def volume_inputs():
+    """{case: (grid, symmetric, [(xP, yP, zP)])}: the log-spaced axes of the shipped p0tau100 deck
+    (symmetric: half first cells) and a uniform non-symmetric cube, 300 active cells each incl. corners"""
+    import os
+    from mocassin_b200 import deck
+
+    gold = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "deck_p0tau100.npz")
+    m, t, d = deck.deck_from_arrays(dict(np.load(gold)))
+    out = {}
+    for name, g, sym in (("p0tau100", m.grids[0], True), ("cube", W.synthetic_cube(n=9, nbins=40, nPhotons=10).grids[0], False)):
+        idx = np.argwhere(np.asarray(g.active) > 0)
+        sel = idx[np.random.default_rng(5).choice(len(idx), 300, replace=False)]
+        cells = [(int(a) + 1, int(b) + 1, int(c) + 1) for a, b, c in sel] + [(g.nx, g.ny, g.nz), (1, g.ny, 1)]
+        out[name] = (g, sym, cells)
+    return out
 
 
 # ---------------------------------------------------------------------------------------------

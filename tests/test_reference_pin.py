@@ -276,6 +276,13 @@ def test_set_star_position_matches_reference():
             later = pos[7:, 0] / (rel[7:, 0] * grids[0].xAxis[-1])
             quirk = quirk or bool(np.all(later < 0.99))
     assert quirk        # the later stars of the multi-grid cases are NOT where the keyword puts them
+    # Grid.cell_volumes (what the fold divides by) against getVolume (grid_mod.f90:2876-2965)
+    for name, (g, sym, cells) in ref_cases.volume_inputs().items():
+        dV = g.cell_volumes(sym)
+        got = np.array([dV[max(int(g.active[x - 1, y - 1, z - 1]), 0)] if g.active[x - 1, y - 1, z - 1] > 0 else np.float32(-1)
+                        for x, y, z in cells], np.float32)
+        live = got >= 0
+        assert np.array_equal(_bits(got[live]), _bits(want["vol_" + name][live])), name
 
 
 @pytest.mark.skipif(not HAVE_REF, reason="reference sources not present")
