@@ -109,6 +109,11 @@ AUX_SLICES = [
          glue_decls=['real, intent(out) :: outste, outdif'],
          glue_end=['outste = heatste', 'outdif = heatdif'],
          guards={936: 'real, intent(out) :: heatint', 1123: 'heatste = 0.', 1234: 'end do'}),
+    # initCartesianGrid: angular bins of the escape tallies and the viewing-angle pointer tables
+    dict(file='grid_mod.f90', name='angle_tables', args='', decls=[], body=[(416, 468)],
+         glue_decls=['integer :: i, err'], glue_end=[],
+         guards={416: 'dtheta = pi/totanglebinstheta', 429: 'dphi = twopi/totanglebinsphi',
+                 466: 'viewpointptheta(int(viewpointtheta(i)/dtheta)+1) = i', 468: 'end do'}),
     # makeDustXsec: trapezoid widths of the size grid and the normalisation of the grain weights
     dict(file='ph_mod.f90', name='grain_weights', args='', decls=[(810, 835)], body=[(986, 1012)],
          glue_decls=[], glue_start=['allocate(da(1:nsizes))', 'da = 0.'], glue_end=[],
@@ -139,7 +144,7 @@ AUX_SLICES = [
 # oracle takes as an input (ff1), so the harness sets those arrays directly
 AUX_EXTERNS = {'boltgaunt'}
 # procedures that must translate completely, and the untranslated statements tolerated in them
-AUX_STRICT = {'writegrid': 0, 'setstarposition': 0, 'getvolume': 0, 'writesed': 0, 'writecontcube': 0, 'writetaunu': 0, 'integratepathtaunu': 0, 'bhmie': 0, 'getqs': 0, 'dust_xsec_assembly': 0, 'dust_emission_int': 0, 'grain_weights': 0, 'opacity_block': 0, 'photo_rates': 0, 'photo_heat': 0, 'getoutershell': 0, 'ionizationdriver': 0, 'edensum': 0, 'addopacity': 0, 'putopacity': 0, 'inopacity': 0, 'getflux': 0, 'setprobden': 0, 'locate': 0, 'linearmap': 0,
+AUX_STRICT = {'writegrid': 0, 'setstarposition': 0, 'getvolume': 0, 'writesed': 0, 'writecontcube': 0, 'writetaunu': 0, 'integratepathtaunu': 0, 'bhmie': 0, 'getqs': 0, 'dust_xsec_assembly': 0, 'dust_emission_int': 0, 'grain_weights': 0, 'angle_tables': 0, 'opacity_block': 0, 'photo_rates': 0, 'photo_heat': 0, 'getoutershell': 0, 'ionizationdriver': 0, 'edensum': 0, 'addopacity': 0, 'putopacity': 0, 'inopacity': 0, 'getflux': 0, 'setprobden': 0, 'locate': 0, 'linearmap': 0,
               'setdustpdf': 1,      # call qHeat (lgQHeat branch)
               'getdustt': 1}        # resLineHeating (gas + resonance-line transfer branch)
 

@@ -374,6 +374,21 @@ class AuxReference:
         t.xaxis, t.yaxis, t.zaxis = (rt.wrap(_F(a, np.float32)) for a in (g.xAxis, g.yAxis, g.zAxis))
         return np.array([ref.p_getvolume(t, int(x), int(y), int(z)) for x, y, z in cells], np.float32)
 
+    def angle_tables(self, viewPointTheta, viewPointPhi, symmetric, totT=10, totP=20):
+        """The angular-bin block of initCartesianGrid (grid_mod.f90:416-468, slice): dTheta, dPhi,
+        totAngleBinsPhi, viewPointPtheta/Pphi and the (possibly reset) viewPointPhi."""
+        G, ref = self.G, self.ref
+        n = len(viewPointTheta) - 1
+        G.nanglebins, G.totanglebinstheta, G.totanglebinsphi = int(n), int(totT), int(totP)
+        G.lgsymmetricxyz = bool(symmetric)
+        G.viewpointtheta = rt.wrap(_F(viewPointTheta, np.float32).copy(), (0,))
+        G.viewpointphi = rt.wrap(_F(viewPointPhi, np.float32).copy(), (0,))
+        G.viewpointptheta, G.viewpointpphi = None, None
+        ref.p_angle_tables()
+        return dict(dTheta=np.float32(G.dtheta), dPhi=np.float32(G.dphi), totAngleBinsPhi=int(G.totanglebinsphi),
+                    viewPointPtheta=np.asarray(G.viewpointptheta.a, np.int32), viewPointPphi=np.asarray(G.viewpointpphi.a, np.int32),
+                    viewPointPhi=G.viewpointphi.a.copy())
+
     def linear_map(self, y, x, x_new):
         """linearMap (interpolation_mod.f90:86-106)."""
         out = rt.wrap(np.zeros(len(x_new), np.float32))

@@ -462,7 +462,20 @@ def run_reference_starpos():
         res[name + "_pos"], res[name + "_idx"] = A.set_star_position(grids, rel.tolist())
     for name, (g, sym, cells) in volume_inputs().items():
         res["vol_" + name] = A.get_volume(g, sym, cells)
+    for name, (vt, vp, sym) in angle_inputs().items():
+        for k, v in A.angle_tables(vt, vp, sym).items():
+            res[f"ang_{name}_{k}"] = np.asarray(v)
     return res
+
+
+def angle_inputs():
+    """{case: (viewPointTheta(0:n), viewPointPhi(0:n), lgSymmetricXYZ)}: two angles with phi, the same
+    phi-free (as the 2-D disk decks: `inclination 2 0.218 -1. 1.35 -1.`), one angle, none"""
+    f = np.float32
+    return {"two": (f([0, 0.6981317, 1.9]), f([0, 3.4906585, 0.2]), False),
+            "phifree": (f([0, 0.218, 1.35]), f([0, -1.0, -1.0]), True),
+            "one": (f([0, 1.2]), f([0, 6.0]), True),
+            "none": (f([0]), f([0]), True)}
 
 
 def volume_inputs():

@@ -276,6 +276,16 @@ def test_set_star_position_matches_reference():
             later = pos[7:, 0] / (rel[7:, 0] * grids[0].xAxis[-1])
             quirk = quirk or bool(np.all(later < 0.99))
     assert quirk        # the later stars of the multi-grid cases are NOT where the keyword puts them
+    # Model.angle_tables against the angular-bin block of initCartesianGrid (grid_mod.f90:416-468)
+    from mocassin_b200 import workloads as W
+    for name, (vt, vp, sym) in ref_cases.angle_inputs().items():
+        m = W.hii_region(n=5, nbins=20, nPhotons=10)
+        m.lgSymmetricXYZ, m.nAngleBins, m.viewPointTheta, m.viewPointPhi = sym, len(vt) - 1, vt, vp
+        at = m.angle_tables()
+        for k in ("dTheta", "dPhi", "totAngleBinsPhi", "viewPointPtheta", "viewPointPphi"):
+            g, w = np.asarray(at[k]), want[f"ang_{name}_{k}"]
+            assert np.array_equal(_bits(g.astype(w.dtype)), _bits(w)), (name, k)
+        assert np.array_equal(np.asarray(at["viewPointPhi"], np.float32)[1:], want[f"ang_{name}_viewPointPhi"][1:]), name
     # Grid.cell_volumes (what the fold divides by) against getVolume (grid_mod.f90:2876-2965)
     for name, (g, sym, cells) in ref_cases.volume_inputs().items():
         dV = g.cell_volumes(sym)
