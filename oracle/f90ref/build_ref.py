@@ -109,6 +109,17 @@ AUX_SLICES = [
          glue_decls=['real, intent(out) :: outste, outdif'],
          glue_end=['outste = heatste', 'outdif = heatdif'],
          guards={936: 'real, intent(out) :: heatint', 1123: 'heatste = 0.', 1234: 'end do'}),
+    # setMotherGrid: which cells are active and how they are numbered (radius test against R_in /
+    # R_out, then a running count over cells that hold gas or dust)
+    dict(file='grid_mod.f90', name='active_cells', args='grid, in_hden, in_ndust, in_ytop',
+         decls=[(901, 901), (904, 938)], body=[(1226, 1294)],
+         glue_decls=['real, intent(in) :: in_hden(grid%nx, grid%ny, grid%nz), in_ndust(grid%nx, grid%ny, grid%nz)',
+                     'integer, intent(in) :: in_ytop'],
+         glue_start=['allocate(hdentemp(1:grid%nx, 1:grid%ny, 1:grid%nz))', 'allocate(ndusttemp(1:grid%nx, 1:grid%ny, 1:grid%nz))',
+                     'hdentemp = in_hden', 'ndusttemp = in_ndust', 'ytop = in_ytop', 'grid%active = 1'],
+         glue_end=[],
+         guards={901: 'type(grid_type), intent(inout) :: grid', 938: 'character(len=40)', 1226: 'grid%ncells = 0',
+                 1235: 'radius = 1.e10*sqrt(', 1294: 'end do'}),
     # initCartesianGrid: angular bins of the escape tallies and the viewing-angle pointer tables
     dict(file='grid_mod.f90', name='angle_tables', args='', decls=[], body=[(416, 468)],
          glue_decls=['integer :: i, err'], glue_end=[],
@@ -144,7 +155,7 @@ AUX_SLICES = [
 # oracle takes as an input (ff1), so the harness sets those arrays directly
 AUX_EXTERNS = {'boltgaunt'}
 # procedures that must translate completely, and the untranslated statements tolerated in them
-AUX_STRICT = {'writegrid': 0, 'setstarposition': 0, 'getvolume': 0, 'writesed': 0, 'writecontcube': 0, 'writetaunu': 0, 'integratepathtaunu': 0, 'bhmie': 0, 'getqs': 0, 'dust_xsec_assembly': 0, 'dust_emission_int': 0, 'grain_weights': 0, 'angle_tables': 0, 'opacity_block': 0, 'photo_rates': 0, 'photo_heat': 0, 'getoutershell': 0, 'ionizationdriver': 0, 'edensum': 0, 'addopacity': 0, 'putopacity': 0, 'inopacity': 0, 'getflux': 0, 'setprobden': 0, 'locate': 0, 'linearmap': 0,
+AUX_STRICT = {'writegrid': 0, 'setstarposition': 0, 'getvolume': 0, 'writesed': 0, 'writecontcube': 0, 'writetaunu': 0, 'integratepathtaunu': 0, 'bhmie': 0, 'getqs': 0, 'dust_xsec_assembly': 0, 'dust_emission_int': 0, 'grain_weights': 0, 'angle_tables': 0, 'active_cells': 0, 'opacity_block': 0, 'photo_rates': 0, 'photo_heat': 0, 'getoutershell': 0, 'ionizationdriver': 0, 'edensum': 0, 'addopacity': 0, 'putopacity': 0, 'inopacity': 0, 'getflux': 0, 'setprobden': 0, 'locate': 0, 'linearmap': 0,
               'setdustpdf': 1,      # call qHeat (lgQHeat branch)
               'getdustt': 1}        # resLineHeating (gas + resonance-line transfer branch)
 

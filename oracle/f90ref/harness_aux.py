@@ -389,6 +389,20 @@ class AuxReference:
                     viewPointPtheta=np.asarray(G.viewpointptheta.a, np.int32), viewPointPphi=np.asarray(G.viewpointpphi.a, np.int32),
                     viewPointPhi=G.viewpointphi.a.copy())
 
+    def active_cells(self, xAxis, yAxis, zAxis, Hden3, Ndust3, lgGas, lgDust, R_in, R_out, plane=False):
+        """The active-cell block of setMotherGrid (grid_mod.f90:1226-1294, slice; grid%active = 1
+        beforehand as at :977).  Returns (active (nx,ny,nz) int32, nCells)."""
+        G, ref = self.G, self.ref
+        G.lg1d, G.lgplaneionization, G.lgmultidustchemistry = False, bool(plane), False
+        G.lggas, G.lgdust = bool(lgGas), bool(lgDust)
+        G.r_in, G.r_out = np.float32(R_in), np.float32(R_out)
+        t = ref.T_grid_type()
+        t.nx, t.ny, t.nz = len(xAxis), len(yAxis), len(zAxis)
+        t.xaxis, t.yaxis, t.zaxis = (rt.wrap(_F(a, np.float32)) for a in (xAxis, yAxis, zAxis))
+        t.active = rt.wrap(np.zeros((t.nx, t.ny, t.nz), np.int64, order='F'))
+        ref.p_active_cells(t, rt.wrap(_F(Hden3, np.float32)), rt.wrap(_F(Ndust3, np.float32)), int(t.ny))
+        return np.asarray(t.active.a, np.int32), int(t.ncells)
+
     def linear_map(self, y, x, x_new):
         """linearMap (interpolation_mod.f90:86-106)."""
         out = rt.wrap(np.zeros(len(x_new), np.float32))

@@ -465,7 +465,34 @@ def run_reference_starpos():
     for name, (vt, vp, sym) in angle_inputs().items():
         for k, v in A.angle_tables(vt, vp, sym).items():
             res[f"ang_{name}_{k}"] = np.asarray(v)
+    for name, c in active_inputs().items():
+        res["act_" + name], n = A.active_cells(c["x"], c["y"], c["z"], c["Hden"], c["Ndust"], c["lgGas"], c["lgDust"], c["R_in"], c["R_out"])
+        res["nact_" + name] = np.int32(n)
     return res
+
+
+def active_inputs():
+    """{case: axes, density fields, flags, radii}: the shipped deck p0tau10 (dust only, log axes from
+    its Ndust file, through the fixture), an HII40-like gas shell on automatic axes, and a gas+dust
+    cube with holes in both fields"""
+    import os
+    from mocassin_b200 import deck
+    from mocassin_b200.model import auto_axis
+
+    gold = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "deck_p0tau10.npz")
+    m, t, d = deck.deck_from_arrays(dict(np.load(gold)))
+    g = m.grids[0]
+    nd3 = np.where(g.active > 0, g.Ndust[np.maximum(g.active, 0)], 0.0).astype(np.float32)
+    ax = auto_axis(13, 1.46e19, True)
+    rng = np.random.default_rng(3)
+    cx = auto_axis(9, 1.0e17, False)
+    H = np.where(rng.random((9, 9, 9)) < 0.7, 50.0, 0.0).astype(np.float32)
+    N = np.where(rng.random((9, 9, 9)) < 0.5, 1.0e-9, 0.0).astype(np.float32)
+    return {"deck_p0tau10": dict(x=g.xAxis, y=g.yAxis, z=g.zAxis, Hden=np.zeros_like(nd3), Ndust=nd3, lgGas=False, lgDust=True,
+                                 R_in=d.R_in, R_out=d.R_out, want=g.active),
+            "gas_shell": dict(x=ax, y=ax, z=ax, Hden=np.full((13, 13, 13), 100.0, np.float32), Ndust=np.zeros((13, 13, 13), np.float32),
+                              lgGas=True, lgDust=False, R_in=3.0e18, R_out=1.46e19),
+            "gasdust_holes": dict(x=cx, y=cx, z=cx, Hden=H, Ndust=N, lgGas=True, lgDust=True, R_in=2.0e16, R_out=0.0)}
 
 
 def angle_inputs():

@@ -276,6 +276,20 @@ def test_set_star_position_matches_reference():
             later = pos[7:, 0] / (rel[7:, 0] * grids[0].xAxis[-1])
             quirk = quirk or bool(np.all(later < 0.99))
     assert quirk        # the later stars of the multi-grid cases are NOT where the keyword puts them
+    # number_active + the radius / density tests against the active-cell block of setMotherGrid (:1226-1294)
+    from mocassin_b200.model import number_active
+    for name, c in ref_cases.active_inputs().items():
+        f = np.float32
+        r = f(1e10) * np.sqrt((((c["x"] / f(1e10)) ** 2)[:, None, None] + ((c["y"] / f(1e10)) ** 2)[None, :, None]).astype(f)
+                              + ((c["z"] / f(1e10)) ** 2)[None, None, :]).astype(f)
+        inside = ~(r < f(c["R_in"]))
+        if c["R_out"] > 0:
+            inside &= ~(r > f(c["R_out"]))
+        matter = ((c["Hden"] > 0) if c["lgGas"] else False) | ((c["Ndust"] > 0) if c["lgDust"] else False)
+        act, n = number_active(inside & matter)
+        assert n == int(want["nact_" + name]) and np.array_equal(act, want["act_" + name]), name
+        if "want" in c:
+            assert np.array_equal(c["want"], want["act_" + name])       # the deck loader's own result
     # Model.angle_tables against the angular-bin block of initCartesianGrid (grid_mod.f90:416-468)
     from mocassin_b200 import workloads as W
     for name, (vt, vp, sym) in ref_cases.angle_inputs().items():
