@@ -254,3 +254,23 @@ def set_star_position(grids, relative):
             idx[i] = [find(s.xAxis, pos[i, 0], nA[0]), find(s.yAxis, pos[i, 1], nA[1]),
                       find(s.zAxis, pos[i, 2], nA[2], mid=s.yAxis), -a]
     return pos, idx
+
+
+def mask_subgrids(grids, symmetric: bool) -> None:
+    """fillGrid's last block (grid_mod.f90:835-889), in place: every cell of grid iG whose centre
+    lies strictly inside the box of another grid jG >= 2 gets active = -jG (for symmetricXYZ a
+    box starting at 0 includes the centres at 0).  Runs after the active cells were numbered, so
+    the masked mother cells keep their (now unused) numbers, as in the reference."""
+    if len(grids) < 2:
+        return
+    for iG, g in enumerate(grids, start=1):
+        for jG in range(2, len(grids) + 1):
+            if jG == iG:
+                continue
+            s = grids[jG - 1]
+            sel = []
+            for a, b in ((g.xAxis, s.xAxis), (g.yAxis, s.yAxis), (g.zAxis, s.zAxis)):
+                lo = (a > b[0]) | ((a >= b[0]) & (b[0] == 0)) if symmetric else (a > b[0])
+                sel.append(lo & (a < b[-1]))
+            box = sel[0][:, None, None] & sel[1][None, :, None] & sel[2][None, None, :]
+            g.active[box] = -jG

@@ -109,6 +109,14 @@ AUX_SLICES = [
          glue_decls=['real, intent(out) :: outste, outdif'],
          glue_end=['outste = heatste', 'outdif = heatdif'],
          guards={936: 'real, intent(out) :: heatint', 1123: 'heatste = 0.', 1234: 'end do'}),
+    # fillGrid: automatic axes (symmetric octant or full cube), the geometric corrections, and the
+    # masking of the cells that lie inside another grid
+    dict(file='grid_mod.f90', name='fill_axes', args='grid', decls=[(493, 498)], body=[(530, 601)],
+         glue_decls=[], glue_end=[], guards={493: 'type(grid_type), dimension(:),intent(inout) :: grid', 530: 'if (.not.lgdfile) then',
+                                             538: 'grid(1)%xaxis(i) = grid(1)%xaxis(i) * rnx', 601: 'end if'}),
+    dict(file='grid_mod.f90', name='fill_mask', args='grid', decls=[(493, 498)], body=[(807, 816), (833, 833), (835, 889)],
+         glue_decls=[], glue_end=[], guards={807: 'do ig = 1, ngrids', 809: 'grid(ig)%geocorrx =', 816: 'end if', 833: 'end do', 835: 'if (ngrids>1) then',
+                                             862: 'grid(ig)%active(i,j,k) = -jg', 889: 'end if'}),
     # setMotherGrid: which cells are active and how they are numbered (radius test against R_in /
     # R_out, then a running count over cells that hold gas or dust)
     dict(file='grid_mod.f90', name='active_cells', args='grid, in_hden, in_ndust, in_ytop',
@@ -155,7 +163,7 @@ AUX_SLICES = [
 # oracle takes as an input (ff1), so the harness sets those arrays directly
 AUX_EXTERNS = {'boltgaunt'}
 # procedures that must translate completely, and the untranslated statements tolerated in them
-AUX_STRICT = {'writegrid': 0, 'setstarposition': 0, 'getvolume': 0, 'writesed': 0, 'writecontcube': 0, 'writetaunu': 0, 'integratepathtaunu': 0, 'bhmie': 0, 'getqs': 0, 'dust_xsec_assembly': 0, 'dust_emission_int': 0, 'grain_weights': 0, 'angle_tables': 0, 'active_cells': 0, 'opacity_block': 0, 'photo_rates': 0, 'photo_heat': 0, 'getoutershell': 0, 'ionizationdriver': 0, 'edensum': 0, 'addopacity': 0, 'putopacity': 0, 'inopacity': 0, 'getflux': 0, 'setprobden': 0, 'locate': 0, 'linearmap': 0,
+AUX_STRICT = {'writegrid': 0, 'setstarposition': 0, 'getvolume': 0, 'writesed': 0, 'writecontcube': 0, 'writetaunu': 0, 'integratepathtaunu': 0, 'bhmie': 0, 'getqs': 0, 'dust_xsec_assembly': 0, 'dust_emission_int': 0, 'grain_weights': 0, 'angle_tables': 0, 'active_cells': 0, 'fill_axes': 0, 'fill_mask': 0, 'opacity_block': 0, 'photo_rates': 0, 'photo_heat': 0, 'getoutershell': 0, 'ionizationdriver': 0, 'edensum': 0, 'addopacity': 0, 'putopacity': 0, 'inopacity': 0, 'getflux': 0, 'setprobden': 0, 'locate': 0, 'linearmap': 0,
               'setdustpdf': 1,      # call qHeat (lgQHeat branch)
               'getdustt': 1}        # resLineHeating (gas + resonance-line transfer branch)
 

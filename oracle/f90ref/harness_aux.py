@@ -403,6 +403,40 @@ class AuxReference:
         ref.p_active_cells(t, rt.wrap(_F(Hden3, np.float32)), rt.wrap(_F(Ndust3, np.float32)), int(t.ny))
         return np.asarray(t.active.a, np.int32), int(t.ncells)
 
+    def _grids_for_fill(self, grids):
+        gs = np.empty(len(grids), dtype=object)
+        for i, g in enumerate(grids):
+            t = self.ref.T_grid_type()
+            t.nx, t.ny, t.nz = g.nx, g.ny, g.nz
+            t.xaxis, t.yaxis, t.zaxis = (rt.wrap(_F(a, np.float32).copy()) for a in (g.xAxis, g.yAxis, g.zAxis))
+            t.active = rt.wrap(_F(g.active, np.int64).copy())
+            gs[i] = t
+        return gs
+
+    def fill_axes(self, n, R, symmetric):
+        """The automatic axes of fillGrid (grid_mod.f90:530-601, slice) for an n^3 mother grid with
+        edges Rnx = Rny = Rnz = R."""
+        G, ref = self.G, self.ref
+        G.lgdfile, G.lg1d, G.lgsymmetricxyz = False, False, bool(symmetric)
+        G.rnx = G.rny = G.rnz = np.float32(R)
+        t = ref.T_grid_type()
+        t.nx = t.ny = t.nz = int(n)
+        t.xaxis, t.yaxis, t.zaxis = (rt.wrap(np.zeros(n, np.float32)) for _ in range(3))
+        gs = np.empty(1, dtype=object)
+        gs[0] = t
+        ref.p_fill_axes(rt.wrap(gs))
+        return t.xaxis.a.copy(), t.yaxis.a.copy(), t.zaxis.a.copy()
+
+    def fill_mask(self, grids, symmetric):
+        """geoCorr and the masking of cells inside other grids (grid_mod.f90:807-816, 835-889, slice).
+        Returns ([active per grid], [(geoCorrX, Y, Z) per grid])."""
+        G, ref = self.G, self.ref
+        G.ngrids, G.lg1d, G.lgsymmetricxyz = len(grids), False, bool(symmetric)
+        gs = self._grids_for_fill(grids)
+        ref.p_fill_mask(rt.wrap(gs))
+        return ([np.asarray(t.active.a, np.int32) for t in gs],
+                [(np.float32(t.geocorrx), np.float32(t.geocorry), np.float32(t.geocorrz)) for t in gs])
+
     def linear_map(self, y, x, x_new):
         """linearMap (interpolation_mod.f90:86-106)."""
         out = rt.wrap(np.zeros(len(x_new), np.float32))

@@ -465,10 +465,37 @@ def run_reference_starpos():
     for name, (vt, vp, sym) in angle_inputs().items():
         for k, v in A.angle_tables(vt, vp, sym).items():
             res[f"ang_{name}_{k}"] = np.asarray(v)
+    for n, R, sym in AXES_CASES:
+        res[f"axes_{n}_{int(sym)}"] = np.stack(A.fill_axes(n, R, sym))
+    for name, (grids, sym) in mask_inputs().items():
+        act, geo = A.fill_mask(grids, sym)
+        for i, a in enumerate(act):
+            res[f"mask_{name}_g{i + 1}"] = a
+        res[f"geo_{name}"] = np.array(geo, np.float32)
     for name, c in active_inputs().items():
         res["act_" + name], n = A.active_cells(c["x"], c["y"], c["z"], c["Hden"], c["Ndust"], c["lgGas"], c["lgDust"], c["R_in"], c["R_out"])
         res["nact_" + name] = np.int32(n)
     return res
+
+
+AXES_CASES = ((13, 1.46e19, True), (15, 3.0e18, False), (16, 1.0e18, True))
+
+
+def mask_inputs():
+    """{case: ([mother, sub-grid] numbered as setMotherGrid leaves them, lgSymmetricXYZ)}"""
+    from mocassin_b200.model import Grid, number_active
+
+    out = {}
+    for sym in (True, False):
+        m = W.multigrid(symmetric=sym, n=16 if sym else 15)
+        gm, gs = m.grids
+        r = np.sqrt(gm.xAxis.astype(np.float64)[:, None, None] ** 2 + gm.yAxis.astype(np.float64)[None, :, None] ** 2
+                    + gm.zAxis.astype(np.float64)[None, None, :] ** 2)
+        act, nc = number_active((r >= 1e15) & (r <= 1e18))
+        out["sym" if sym else "nonsym"] = ([Grid(xAxis=gm.xAxis, yAxis=gm.yAxis, zAxis=gm.zAxis, active=act, nCells=nc),
+                                            Grid(xAxis=gs.xAxis, yAxis=gs.yAxis, zAxis=gs.zAxis, active=gs.active.copy(), nCells=gs.nCells,
+                                                 motherP=1)], sym)
+    return out
 
 
 def active_inputs():

@@ -276,6 +276,18 @@ def test_set_star_position_matches_reference():
             later = pos[7:, 0] / (rel[7:, 0] * grids[0].xAxis[-1])
             quirk = quirk or bool(np.all(later < 0.99))
     assert quirk        # the later stars of the multi-grid cases are NOT where the keyword puts them
+    # auto_axis, mask_subgrids and geoCorr against fillGrid (grid_mod.f90:530-601, 807-816, 835-889)
+    from mocassin_b200.model import auto_axis, mask_subgrids
+    for n, R, sym in ref_cases.AXES_CASES:
+        a = auto_axis(n, R, sym)
+        for k in range(3):
+            assert np.array_equal(_bits(a), _bits(want[f"axes_{n}_{int(sym)}"][k])), (n, sym)
+    for name, (grids, sym) in ref_cases.mask_inputs().items():
+        mask_subgrids(grids, sym)
+        for i, g in enumerate(grids):
+            assert np.array_equal(g.active, want[f"mask_{name}_g{i + 1}"]), (name, i)
+            assert np.array_equal(_bits(np.array(g.geoCorr, np.float32)), _bits(want[f"geo_{name}"][i])), (name, i)
+        assert (grids[0].active < 0).sum() > 0
     # number_active + the radius / density tests against the active-cell block of setMotherGrid (:1226-1294)
     from mocassin_b200.model import number_active
     for name, c in ref_cases.active_inputs().items():
