@@ -1,7 +1,6 @@
 """One Lucy iteration of a dust-only deck (setDustPDF -> energyPacketDriver -> host scaling ->
 getDustT -> dust opacities) on the CPU oracle and on the CUDA engine, as `step` callbacks for
 mocassin_b200.deck.iterate_dust.  Test infrastructure: the product never imports this."""
-import ctypes as C
 
 import numpy as np
 
