@@ -49,6 +49,12 @@ def test_no_cpu_fallback_without_device():
 
 
 def test_product_package_never_imports_oracle():
+    """The oracle is test infrastructure: the product package and the scripts never touch it (only
+    tests/, __graft_entry__.smoke() and bench.py's CPU-baseline legs do)."""
+    for f in os.listdir(os.path.join(ROOT, "scripts")):
+        if f.endswith((".py", ".sh")):
+            text = open(os.path.join(ROOT, "scripts", f)).read()
+            assert "import oracle" not in text and "from oracle" not in text, f
     pkg = os.path.join(ROOT, "mocassin_b200")
     for dirpath, _, files in os.walk(pkg):
         for f in files:

@@ -94,13 +94,13 @@ def test_platform_libm_changes_few_histories(oracle_lib):
 
 @pytest.mark.skipif(not HAVE_REF, reason="reference sources not present")
 def test_fuzz_oracle_against_reference(oracle_lib):
-    """A short run of scripts/fuzz_reference.py: random models (non-uniform axes, opacity scatter
+    """A short run of tests/tools/fuzz_reference.py: random models (non-uniform axes, opacity scatter
     with zeros, random CDFs, albedo, sublimed grains, R_out inside the grid, off-centre star)
     through the oracle and the translated reference.  (2000 trials were run once, 0 mismatches.)"""
     import importlib.util
     import sys
 
-    spec = importlib.util.spec_from_file_location("fuzz_reference", os.path.join(os.path.dirname(GOLD), "..", "scripts", "fuzz_reference.py"))
+    spec = importlib.util.spec_from_file_location("fuzz_reference", os.path.join(os.path.dirname(GOLD), "tools", "fuzz_reference.py"))
     fz = importlib.util.module_from_spec(spec)
     spec.loader.exec_module(fz)
     bad = []

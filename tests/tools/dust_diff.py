@@ -1,3 +1,7 @@
+"""Debug helper: K6 (setDustPDF on the device) against the oracle on random dust temperatures; prints the first
+differences.  Uses the oracle, so it lives under tests/ (run from the repo root on a GPU box)."""
+import sys
+sys.path.insert(0, ".")
 import numpy as np
 from mocassin_b200 import workloads as W
 from mocassin_b200.api import PacketEngine

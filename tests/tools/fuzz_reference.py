@@ -1,7 +1,7 @@
 """Randomised comparison of the C oracle with the reference's own code (the f90py translation,
 oracle/f90ref) -- TEST INFRASTRUCTURE, runs where /root/reference exists.
 
-    python scripts/fuzz_reference.py [--trials N] [--seed S] [--packets P]
+    python tests/tools/fuzz_reference.py [--trials N] [--seed S] [--packets P]
 
 Each trial builds one of the seeded workloads with random parameters, then perturbs what the
 builders keep regular: non-uniform axes, per-(cell, nu) opacity scatter over several decades
@@ -22,7 +22,7 @@ import time
 
 import numpy as np
 
-ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 sys.path.insert(0, ROOT)
 
 from mocassin_b200 import workloads as W  # noqa: E402
