@@ -169,3 +169,21 @@ def test_fortran_binding_interfaces_are_well_formed():
                     declared += [re.sub(r"\(.*?\)", "", v).strip().lower() for v in part.split("::", 1)[1].split(",") if v.strip()]
         assert sorted(declared) == sorted(dummies), (name, sorted(set(dummies) ^ set(declared)))
         assert len(dummies) == len(protos[name]), (name, len(dummies), len(protos[name]))
+
+
+def test_c_host_example_compiles_and_reports_no_device(cuda_lib, tmp_path):
+    """examples/host_example.c: the whole call sequence from plain C (no Python, no torch in the
+    process).  Here it must compile warning-free and exit 2 (MCB200_ENODEV); on a GPU box
+    tests/test_zz_gpu_deck.py runs it and expects exit 0."""
+    from mocassin_b200 import _lib
+
+    exe = tmp_path / "host_example"
+    r = subprocess.run(["gcc", "-std=c99", "-Wall", "-Wextra", "-Werror", "-I", os.path.join(ROOT, "include"),
+                        os.path.join(ROOT, "examples", "host_example.c"), _lib.LIB_PATH,
+                        "-Wl,-rpath," + os.path.dirname(_lib.LIB_PATH), "-lm", "-o", str(exe)], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    import torch
+
+    if not torch.cuda.is_available():
+        out = subprocess.run([str(exe)], capture_output=True, text=True)
+        assert out.returncode == 2 and "MCB200_ENODEV" in out.stdout

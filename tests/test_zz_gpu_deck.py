@@ -183,3 +183,20 @@ def test_device_opacity_rows_feed_tau_nu(cuda_lib, name):
     with pytest.raises(MocassinError):
         e.get_opacity_rows(1, np.array([g.nCells + 1], np.int32))
     e.close()
+
+
+def test_c_host_example_runs_on_the_device(cuda_lib, tmp_path):
+    """examples/host_example.c: set_config -> set_grid -> set_spectra -> set_stars -> set_opacity ->
+    set_pdfs -> transport -> fetch_estimators from plain C; its own checks (escaped energy = L, mean
+    path per packet = 1.33 half edges as on the CPU oracle) decide the exit code."""
+    import subprocess
+
+    from mocassin_b200 import _lib
+
+    exe = tmp_path / "host_example"
+    r = subprocess.run(["gcc", "-std=c99", "-I", os.path.join(ROOT, "include"), os.path.join(ROOT, "examples", "host_example.c"),
+                        _lib.LIB_PATH, "-Wl,-rpath," + os.path.dirname(_lib.LIB_PATH), "-lm", "-o", str(exe)],
+                       capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    out = subprocess.run([str(exe)], capture_output=True, text=True, timeout=300)
+    assert out.returncode == 0 and out.stdout.strip().endswith("OK"), out.stdout + out.stderr
