@@ -18,7 +18,8 @@ import numpy as np
 from .model import F32, I32, Grid, Model, auto_axis, farray, number_active, star_indices
 
 TE1RYD = 1.578866e5
-HC_RYD_K = 1.578866e5      # h c Ryd / k  [K]
+HC_RYD_K = 1.578866e5      # h c Ryd / k  [K]  (the reference's getFlux uses 157893.94 in float32: these builders are
+                           # synthetic stand-ins; mocassin_b200/deck.py has the faithful, pinned versions)
 
 
 # ---------------------------------------------------------------------------------------
