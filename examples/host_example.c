@@ -43,7 +43,8 @@ int main(void)
     memset(&cfg, 0, sizeof(cfg));
     cfg.nGrids = 1; cfg.nbins = NB; cfg.nStars = 1; cfg.nAngleBins = 0;
     cfg.totAngleBinsTheta = 10; cfg.totAngleBinsPhi = 20;
-    cfg.lgGas = 1;
+    cfg.lgGas = 1;                                       /* gas only: no dust tables needed */
+    cfg.nDustComp = 1;
     cfg.dTheta = 3.141592654f / 10.f; cfg.dPhi = 2.f * 3.141592654f / 20.f;
     cfg.R_out = 0.f; cfg.ionEdge1 = 1.0e-9f;            /* every bin ionises: no early escapes */
     CHECK(mcb200_set_config(ctx, &cfg));
