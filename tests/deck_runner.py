@@ -132,5 +132,12 @@ class OracleEngine:
     def fetch_sed(self):
         return self.sed_cnt
 
+    def assemble_opacity(self, iG, bands, den, ff1=None, dust=None):
+        # dust-only, Tdust = None: what K1 does from the device-resident dust state
+        assert dust is not None and dust.get("Tdust") is None and len(bands["species"]) == 0
+        t = dict(self.tables, dustScaXsecP=dust["dustScaXsecP"], grainAbun1=self.model.grainAbun[0, :],
+                 TdustSublime=self.model.TdustSublime)
+        deck.dust_opacity(self.model.grids[iG - 1], t)
+
     def get_opacity_rows(self, iG, cells):
         return self.model.grids[iG - 1].opacity[np.asarray(cells), :]

@@ -12,6 +12,25 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, os.path.join(ROOT, "tests"))
 
 
+def test_device_opacity_flag_takes_the_same_path_to_the_same_files(tmp_path, monkeypatch, capsys, oracle_lib):
+    """--device-opacity (dust opacities rebuilt through assemble_opacity with Tdust = None) and the
+    default (host rebuild + upload) must produce identical output files."""
+    import deck_runner
+    from mocassin_b200 import api
+
+    monkeypatch.setattr(api, "PacketEngine", deck_runner.OracleEngine)
+    outs = []
+    for flag in ([], ["--device-opacity"]):
+        out = tmp_path / ("dev" if flag else "host")
+        monkeypatch.setattr(sys, "argv", ["run_dust_deck.py", "--golden", os.path.join(ROOT, "tests", "golden", "deck_p0tau10.npz"),
+                                          "--out", str(out), "--max-iter", "2", "--seed", "7"] + flag)
+        runpy.run_path(os.path.join(ROOT, "scripts", "run_dust_deck.py"), run_name="__main__")
+        outs.append(out)
+    capsys.readouterr()
+    for fn in ("SED.out", "tauNu.out", "dustGrid.out", "summary.out"):
+        assert (outs[0] / fn).read_text() == (outs[1] / fn).read_text(), fn
+
+
 def test_run_dust_deck_script_writes_the_reference_output_files(tmp_path, monkeypatch, capsys, oracle_lib):
     import deck_runner
     from mocassin_b200 import api, checkpoint, deck
