@@ -611,6 +611,9 @@ def load_dust_deck(run_dir: str, share_dir: str, input_file: str = "input.in"):
     nPhot = int(d.nPhotons)
     view = {}
     if d.nAngleBins > 0:
+        if d.lgSymmetricXYZ and any(F32(th) > F32(F32(3.141592654) / F32(2.0)) for th in d.viewPointTheta[1:]):
+            raise ValueError("initCartesianGrid: the inclination theta required is not available for symmetricXYZ "
+                             "models (theta > Pi/2)")          # grid_mod.f90:462-465
         view = dict(nAngleBins=d.nAngleBins, viewPointTheta=np.asarray(d.viewPointTheta, dtype=F32),
                     viewPointPhi=np.asarray(d.viewPointPhi, dtype=F32))
     model = Model(grids=[g], nbins=nbins, nuArray=nu,
