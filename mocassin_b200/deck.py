@@ -562,8 +562,10 @@ def load_dust_deck(run_dir: str, share_dir: str, input_file: str = "input.in"):
         raise NotImplementedError("only dust-only decks (nebComposition noGas + Ndust) are restated")
     if d.contShape != "blackbody":
         raise NotImplementedError(f"contShape {d.contShape}")
-    if d.NdustFile == "none" or d.dustFile is None:
-        raise NotImplementedError("Ndust constant / missing dustFile")
+    if d.dustFile is None:
+        raise ValueError("readInput: dust present but no dustFile given")
+    if d.NdustFile == "none" and not d.NdustValue > 0:
+        raise NotImplementedError("dust-only deck without an Ndust keyword (MdMg / MdMh are gas-relative)")
 
     def resolve(p):
         for cand in (os.path.join(run_dir, p), os.path.join(run_dir, os.path.basename(p))):
@@ -574,7 +576,20 @@ def load_dust_deck(run_dir: str, share_dir: str, input_file: str = "input.in"):
     nu = nu_mesh_dust(os.path.join(share_dir, "dustData", "nuDustRyd.dat"), d.nbins, d.nuMax)
     nbins = nu.shape[0]
     widFlx = wid_flx(nu)
-    xA, yA, zA, Nd3, (nx, ny, nz) = read_ndust(resolve(d.NdustFile), d.nx, d.ny, d.nz)
+    if d.NdustFile != "none":
+        xA, yA, zA, Nd3, (nx, ny, nz) = read_ndust(resolve(d.NdustFile), d.nx, d.ny, d.nz)
+    else:
+        # `Ndust constant`: automatic axes from the `edges` keyword (fillGrid, grid_mod.f90:530-601;
+        # without it readInput stops, set_input_mod.f90:720-723), the same density in every cell
+        from .model import auto_axis
+
+        if d.edges is None or min(d.edges) < 0:
+            raise ValueError("readInput: Grid edges unspecified or non-valid grid edges")
+        if not d.lgSymmetricXYZ and (d.nx % 2 == 0 or d.ny % 2 == 0 or d.nz % 2 == 0):
+            raise ValueError("fillGrid: the automatic grid option requires odd integer nx, ny, nz if not symmetric")
+        nx, ny, nz = d.nx, d.ny, d.nz
+        xA, yA, zA = (auto_axis(n, e, d.lgSymmetricXYZ) for n, e in zip((nx, ny, nz), d.edges))
+        Nd3 = np.full((nx, ny, nz), F32(d.NdustValue), dtype=F32)
     # active cells (grid_mod.f90:1226-1294): inside [R_in, R_out] and Ndust > 0
     r = F32(1.0e10) * np.sqrt(((xA / F32(1.0e10)) ** 2)[:, None, None] + ((yA / F32(1.0e10)) ** 2)[None, :, None]
                               + ((zA / F32(1.0e10)) ** 2)[None, None, :]).astype(F32)

@@ -126,6 +126,35 @@ def test_shipped_2d_disk_decks_load(name):
     assert 0.8 * tauV < _tau(m, 0.55) < 1.05 * tauV      # midplane optical depth at 550 nm (Pascucci et al. 2004)
 
 
+@live
+def test_constant_density_deck_on_automatic_axes(tmp_path):
+    """`Ndust constant` + `edges`: fillGrid's automatic axes, every cell inside [Rin, Rout] active,
+    radial optical depth = Ndust * Cext * (Rout - Rin) to the half-cell the shell edges are resolved to."""
+    import shutil
+
+    src = os.path.join(REF, "benchmarks", "dust", "1D", "p0tau1")
+    for f in ("p0tau1_grainsizes.dat", "p0tau1_grainspecies.dat"):
+        shutil.copy(os.path.join(src, f), tmp_path / f)
+    (tmp_path / "input.in").write_text(
+        "symmetricXYZ\ncontShape blackbody\nnebComposition noGas\nmaxIterateMC 3 95.\nnPhotons 1000\nnx 21\nny 21\nnz 21\n"
+        "LStar 1.\nTStellar 3000.\nRin 2.e16\nRout 1.e17\nedges 1.e17 1.e17 1.e17\nNdust constant 2.e-9\n"
+        "dustFile 'input/p0tau1_grainspecies.dat' 'input/p0tau1_grainsizes.dat'\n")
+    m, t, d = deck.load_dust_deck(str(tmp_path), REF)
+    g = m.grids[0]
+    assert (g.nx, g.ny, g.nz) == (21, 21, 21) and np.array_equal(g.xAxis, g.zAxis) and g.xAxis[-1] == np.float32(1.0e17)
+    r = np.sqrt(sum(np.meshgrid(*(3 * [g.xAxis.astype(np.float64) ** 2]), indexing="ij")))
+    diff = (g.active > 0) != ((r >= 2.0e16) & (r <= 1.0e17))         # float32 radius test vs float64: boundary cells only
+    assert np.all((abs(r[diff] / 2.0e16 - 1) < 1e-6) | (abs(r[diff] / 1.0e17 - 1) < 1e-6)) and diff.sum() < 30
+    assert np.all(g.Ndust[1:] == np.float32(2.0e-9))
+    lam = 2.9979250e14 / (m.nuArray.astype(np.float64) * 3.28984e15)
+    i = int(np.argmin(abs(lam - 1.0)))
+    cext = float(g.opacity[1, i]) / 2.0e-9
+    assert abs(_tau(m, 1.0) - 2.0e-9 * cext * 8.0e16) < 2.0e-9 * cext * 0.5e16
+    (tmp_path / "input.in").write_text((tmp_path / "input.in").read_text().replace("edges 1.e17 1.e17 1.e17\n", ""))
+    with pytest.raises(ValueError):
+        deck.load_dust_deck(str(tmp_path), REF)
+
+
 def test_three_lucy_iterations_of_p0tau1_on_the_oracle(oracle_lib):
     from deck_runner import oracle_step
 
