@@ -16,6 +16,9 @@ import numpy as np
 import pytest
 
 pytestmark = pytest.mark.gpu
+# the one-rank tests below passed on a B200 (profiles/r01_native_comm_gpu_tests.log); the tests carrying this
+# mark were written after round 1's GPU budget was spent: outcome recorded (XPASS / XFAIL), not gating
+UNVERIFIED = pytest.mark.xfail(strict=False, reason="never run on a GPU before round 1 ended (outcome recorded, not gating)")
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, os.path.join(ROOT, "tests"))
 
@@ -121,6 +124,7 @@ def _worker(rank, world, idfile, name, n, q):
     e.close()
 
 
+@UNVERIFIED
 @pytest.mark.parametrize("name", ["multigrid_sym", "cube_clumpy_gasdust", "hii_sym_gas_debug", "viewing_angles"])
 def test_two_ranks_native_exchange_matches_single_gpu(cuda_lib, name):
     import torch
@@ -154,6 +158,7 @@ def test_two_ranks_native_exchange_matches_single_gpu(cuda_lib, name):
                 assert np.array_equal(got[r][iG][k], ref[iG][k]), (iG, r, k)
 
 
+@UNVERIFIED
 def test_exchange_twice_or_transport_after_exchange_is_refused(cuda_lib):
     from cases import make
     from mocassin_b200.api import MocassinError, PacketEngine
