@@ -327,11 +327,46 @@ def run_b200(args):
         # reference all-reduces escapedPackets (iteration_mod.f90:649-659).
         eng.set_sed_local(True)
 
-    if world > 1 and os.environ.get("MCB_NATIVE_COMM", "0") == "1":
+    native = world > 1 and os.environ.get("MCB_NATIVE_COMM", "1") == "1"
+    if native:
         # the library's own NCCL communicator (mcb200_comm_init / mcb200_exchange: what a Fortran/MPI
-        # host calls) instead of torch.distributed collectives on the tally buffers.  Off by
-        # default until it has been timed at N > 1.
+        # host calls): reduce-scatter of the touched JsteQ planes -> fold of this rank's share ->
+        # all-gather of the float32 Jste, sparse all-gather of the escape counts, all on the library
+        # stream.  MCB_NATIVE_COMM=0: torch.distributed all-reduces on the tally buffers (round 1).
         eng.comm_init_from_group()
+        if os.environ.get("MCB_EXCHANGE_ALLREDUCE", "0") == "1":
+            eng.set_option("exchange_allreduce", 1)
+
+    def nrank_parity(nCheck=2_000_000):
+        """Untimed: the same nCheck packets once sharded over the N ranks (exchange + fold) and once
+        by every rank alone (option solo); the estimators every rank holds must be the same bits
+        (mcb200_checksum of Jste and escapedPackets), the packet fates must add up."""
+        keys = ("nPackets", "nEscaped", "nLinePackets", "nDropped", "trapped", "nAbs", "nSca", "nSegments")
+        eng.zero_estimators()
+        c = eng.energyPacketDriver(1, nCheck, deltaE=dE)
+        eng.reduce()
+        sharded = [eng.checksum(1, 0), eng.checksum(1, 1)]
+        tot = torch.tensor([c[k] for k in keys], dtype=torch.int64, device="cuda")
+        dist.all_reduce(tot)
+        eng.set_option("solo", 1)
+        eng.zero_estimators()
+        c1 = eng.energyPacketDriver(1, nCheck, deltaE=dE)
+        solo = [eng.checksum(1, 0), eng.checksum(1, 1)]
+        eng.set_option("solo", 0)
+        eng.zero_estimators()
+        tot = [int(v) for v in tot.tolist()]
+        same = sharded == solo and tot == [c1[k] for k in keys]
+        conserved = tot[1] + tot[2] + tot[3] + tot[4] == nCheck == tot[0]
+        ok = torch.tensor([int(same), int(conserved)], dtype=torch.int64, device="cuda")
+        dist.all_reduce(ok, op=dist.ReduceOp.MIN)
+        return {"nrank_parity": bool(ok[0].item()), "packets_conserved": bool(ok[1].item()), "packets": nCheck,
+                "checksums": {"Jste": f"{sharded[0]:016x}", "escapedPackets": f"{sharded[1]:016x}"},
+                "fates": dict(zip(keys, tot)),
+                "how": f"{nCheck} packets sharded over {world} ranks + exchange + fold vs the same packets on every rank "
+                       "alone (option solo): mcb200_checksum of the device-resident Jste / escapedPackets and all counters "
+                       "equal on every rank; nEscaped + nLinePackets + nDropped + trapped == packets"}
+
+    parity = nrank_parity() if world > 1 else None
 
     def step():
         if overlap:      # exchange of the first half hidden behind the transport of the second
@@ -464,7 +499,15 @@ def run_b200(args):
         "kernel_ms_per_step": kms_max / args.steps, "wall_ms_per_step": 1e3 * wall_max / args.steps,
         "exchange_planes": getattr(eng, "last_exchange_planes", None),
         "escaped_exchange": getattr(eng, "last_escaped_exchange", None),
+        "exchange": ({"path": "native: mcb200_exchange (NCCL reduce-scatter JsteQ + sparse all-gather escapedQ) -> "
+                              "mcb200_reduce (fold own share, all-gather float32 Jste)" if native else
+                              "torch.distributed all-reduce of the tally buffers -> mcb200_reduce",
+                      "nccl_bytes_per_rank_per_step": (getattr(eng, "last_exchange", None) or {}).get("bytes"),
+                      "ms_per_step": (tms_max - kms_max) / args.steps} if world > 1 else None),
     }
+    if parity:
+        line.update({"nrank_parity": parity["nrank_parity"], "packets_conserved": parity["packets_conserved"],
+                     "nrank_parity_detail": parity})
     print(json.dumps(line), flush=True)
     if world > 1:
         dist.barrier(); dist.destroy_process_group()

@@ -163,6 +163,10 @@ module mcb200_mod
        integer(c_int) function mcb200_len_unit(ctx, iG, lenUnit) bind(C, name="mcb200_len_unit")
          import; type(c_ptr), value :: ctx; integer(c_int32_t), value :: iG; real(c_double), intent(out) :: lenUnit
        end function
+       ! 64-bit position-sensitive checksum of a device-resident estimator (0 Jste, 1 escapedPackets, 2 Jdif, 3 linePackets)
+       integer(c_int) function mcb200_checksum(ctx, iG, which, checksum) bind(C, name="mcb200_checksum")
+         import; type(c_ptr), value :: ctx; integer(c_int32_t), value :: iG, which; integer(c_int64_t), intent(out) :: checksum
+       end function
        ! name is a C string: pass e.g. "wavefront"//c_null_char
        integer(c_int) function mcb200_set_option(ctx, name, value) bind(C, name="mcb200_set_option")
          import; type(c_ptr), value :: ctx; character(kind=c_char), dimension(*), intent(in) :: name

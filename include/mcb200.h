@@ -290,11 +290,15 @@ int mcb200_escaped_scatter(mcb200_ctx *ctx, int32_t iG, int32_t set, const void 
  *   host:       MPI_BCAST(id, 128, MPI_BYTE, 0, ...)   the only host-side message
  *   every rank: mcb200_comm_init(ctx, id)              rank / nranks as given to mcb200_create
  *   per source: mcb200_transport(...); mcb200_exchange(ctx); mcb200_reduce(ctx);
- * mcb200_exchange sums the pending integer tallies of every grid over the ranks, in place, on
- * the library stream: max-reduce of the nuTouched flags, then only the flagged nu-planes of
- * JsteQ (and JdifQ, linePacketsQ in debug mode), planeIonDistribution, and the escape counts
- * as all-gathered sparse (index, count) lists when those are shorter than the dense planes
- * (with option "sed_local": the (nu, angle) counts of buffer 6 instead).  Integer sums: the
+ * mcb200_exchange sums the pending integer tallies of every grid over the ranks on the library
+ * stream: max-reduce of the nuTouched flags, then only the flagged nu-planes.  JsteQ (and JdifQ in
+ * debug mode) are REDUCE-SCATTERED: every rank receives the global sums of 1/nranks of each
+ * touched range; mcb200_reduce then folds that share only and all-gathers the float32 estimator
+ * in place -- 12 instead of the 16 bytes per element an int64 all-reduce moves, and the fold
+ * divided by nranks (option "exchange_allreduce"=1: the plain all-reduce + full fold).
+ * linePacketsQ (debug), planeIonDistribution: all-reduced; the escape counts: all-gathered sparse
+ * (index, count) lists when those are shorter than the dense planes (with option "sed_local":
+ * the (nu, angle) counts of buffer 6 instead).  Integer sums and one fold per element: the
  * folded estimators are bit-identical on every rank and for every rank count.  A second tally
  * set (option "tally_set") is merged first.  No-op for nranks = 1 or when nothing is pending;
  * MCB200_ESTATE if the pending tallies were exchanged already, or if a transport call follows an
@@ -368,6 +372,14 @@ int mcb200_photo_integrals(mcb200_ctx *ctx, int32_t iG, int32_t nBands, const in
 int mcb200_fetch_estimators(mcb200_ctx *ctx, int32_t iG, float *Jste, float *escapedPackets,
                             float *Jdif, float *linePackets);
 
+/* 64-bit checksum of a device-resident float32 estimator of grid iG, as mcb200_fetch_estimators
+ * would return it (which: 0 Jste, 1 escapedPackets, 2 Jdif, 3 linePackets): the sum over the
+ * elements of bits(i) * (2*i + 1) mod 2^64.  Lets every rank of a multi-GPU run show that it holds
+ * the same estimators as every other rank, and as a single-rank run of the same packets (bench.py
+ * "nrank_parity"; the arrays the reference compares after MPI_ALLREDUCE, iteration_mod.f90:583-703),
+ * without 10 GB per rank crossing PCIe. */
+int mcb200_checksum(mcb200_ctx *ctx, int32_t iG, int32_t which, uint64_t *sum);
+
 /* escapedPackets of grid iG, sparsely.  escapedPackets(cell, nu, angle) is indexed by the cell a
  * packet was last emitted or scattered in, so in a large grid almost all of it is zero (0.5 % of
  * the 1.26e9 entries at 128^3 x 600): the library compacts the non-zero entries on the device,
@@ -421,6 +433,8 @@ int mcb200_fetch_fates(mcb200_ctx *ctx, int32_t *fates, int64_t nPackets);
  *   "tally_set", "parts", "part"   second tally set / sub-ranges of a rank's share, for overlapping the
  *                   exchange of one half with the transport of the other (PacketEngine.energyPacketDriverOverlapped)
  *   "exchange_dense" 1: mcb200_exchange all-reduces the escape counts densely whatever the list lengths
+ *   "exchange_allreduce" 1: mcb200_exchange all-reduces the J planes and every rank folds all of them
+ *   "solo"          1: this rank acts as rank 0 of 1 until cleared (N-rank vs 1-rank check on one context)
  *   "defer_fold"    1: a single rank leaves its tallies pending after mcb200_transport, as a multi-rank run
  *                   does, until mcb200_reduce (lets one GPU walk the mcb200_exchange path) */
 int mcb200_set_option(mcb200_ctx *ctx, const char *name, int64_t value);

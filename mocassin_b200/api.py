@@ -99,6 +99,7 @@ class PacketEngine:
         self.exchange_chunk_planes = 64
         self.last_escaped_exchange = None
         self.native_comm = False         # N>1: the library's own NCCL communicator does the exchange
+        self.solo = False                # option solo: this rank runs every packet itself, no exchange
         self._upload_static()
 
     # -- plumbing ---------------------------------------------------------------------
@@ -119,6 +120,8 @@ class PacketEngine:
 
     def set_option(self, name: str, value: int):
         self._check(self.lib.mcb200_set_option(self.h, name.encode(), int(value)))
+        if name == "solo":
+            self.solo = bool(value)
 
     # -- static inputs ------------------------------------------------------------------
     def _upload_static(self):
@@ -514,6 +517,9 @@ class PacketEngine:
         """mcb200_exchange: sum the pending integer tallies over the ranks of the native
         communicator (no fold).  Returns mcb200_exchange_info."""
         self._check(self.lib.mcb200_exchange(self.h))
+        return self.exchange_info()
+
+    def exchange_info(self) -> dict:
         b, sp, v = C.c_int64(), C.c_int32(), C.c_int32()
         self._check(self.lib.mcb200_exchange_info(self.h, C.byref(b), C.byref(sp), C.byref(v)))
         return dict(bytes=b.value, sparse_grids=sp.value, nccl_version=v.value)
@@ -522,7 +528,9 @@ class PacketEngine:
         """Sum the pending integer tallies over ranks and fold them into the float32
         estimators.  Exact integer sums -> identical bits on every rank and for every rank
         count."""
-        if self.native_comm:
+        if self.solo:                        # acting as a single rank: the transport call folded already
+            pass
+        elif self.native_comm:
             self.last_exchange = self.exchange()
         elif self.nranks > 1:
             import torch
@@ -531,6 +539,8 @@ class PacketEngine:
                 self._exchange(0, group)
             torch.cuda.synchronize()
         self._check(self.lib.mcb200_reduce(self.h))
+        if self.native_comm and not self.solo:   # + the float32 all-gather of the fold
+            self.last_exchange = self.exchange_info()
 
     def energyPacketDriverOverlapped(self, iStar: int, n: int, deltaE: Optional[float] = None, group=None) -> dict:
         """energyPacketDriver + exchange + fold for nranks > 1 with the exchange hidden behind
@@ -631,6 +641,13 @@ class PacketEngine:
         self._check(self.lib.mcb200_fetch_tallies(self.h, iG, _lp(JQ), _lp(EQ), _lp(DQ), _lp(LQ)))
         return dict(JsteQ=JQ, escapedQ=EQ, JdifQ=DQ, linePacketsQ=LQ)
 
+    def checksum(self, iG: int = 1, which: int = 0) -> int:
+        """mcb200_checksum: position-sensitive 64-bit sum of the device-resident estimator
+        (0 Jste, 1 escapedPackets, 2 Jdif, 3 linePackets)."""
+        v = C.c_uint64()
+        self._check(self.lib.mcb200_checksum(self.h, iG, which, C.byref(v)))
+        return int(v.value)
+
     def len_unit(self, iG: int = 1) -> float:
         v = C.c_double()
         self._check(self.lib.mcb200_len_unit(self.h, iG, C.byref(v)))
@@ -665,9 +682,9 @@ class PacketEngine:
         out = []
         for iStar in range(1, self.model.nStars + 1):
             out.append(self.energyPacketDriver(iStar, int(nPhotons[iStar - 1])))
-            if self.nranks > 1 or self.native_comm:
+            if (self.nranks > 1 or self.native_comm) and not self.solo:
                 self.reduce(group)
-        if self.nranks == 1 and not self.native_comm:
+        if (self.nranks == 1 and not self.native_comm) or self.solo:
             self.reduce()
         return out
 

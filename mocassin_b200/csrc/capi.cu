@@ -26,7 +26,7 @@ cudaError_t launch_order(const TransportArgs &a, unsigned short *key, unsigned i
                          unsigned int *order, int numSMs, cudaStream_t stream);
 cudaError_t launch_transpose_pdf(const float *src, float *dst, int nRows, int nb, cudaStream_t s);
 cudaError_t launch_check_monotone(const float *pdfT, int nRows, int nb, int *bad, cudaStream_t s);
-cudaError_t launch_fold_j(unsigned long long *Q, float *J, const float *dV, int nRows, size_t total,
+cudaError_t launch_fold_j(unsigned long long *Q, float *J, const float *dV, int nRows, size_t first, size_t total,
                           double lenUnit, float deltaE, int blocks, cudaStream_t s);
 cudaError_t launch_fold_count(unsigned int *Q, float *E, size_t total, float deltaE, int blocks,
                               cudaStream_t s);
@@ -130,6 +130,12 @@ struct GridState {
     const float *sparsePrevPtr = nullptr;
     bool sparsePrevDense = false;         // the previous call fell back to the dense copy
     std::vector<char> folded;             // nu-planes of the pending call already folded by mcb200_reduce_range
+    // mcb200_exchange reduce-scatters the touched J planes: after it this rank holds the global sum
+    // only of its own share [off + rank*count, +count) of every range (and of the all-reduced tail
+    // [off + nranks*count, off + len)); the fold then runs on that share and the float32 results are
+    // all-gathered in place (capi.cu: fold_pending)
+    struct JRange { size_t off, len, count; };
+    std::vector<JRange> jShards;
     // dust closure (mcb200_dust_update / mcb200_dust_pdf): device copy of the dust state
     DevBuf<float> Tdust;
     DevBuf<int> dustAbun, lgConverged;
@@ -219,6 +225,11 @@ struct mcb200_ctx {
     int64_t lastExchangeBytes = 0;        // bytes this rank handed to NCCL in the last mcb200_exchange
     int lastExchangeSparse = 0;           // grids whose escape counts went as sparse lists
     bool exchangeDense = false;           // option exchange_dense: mcb200_exchange never takes the sparse path
+    bool exchangeAllReduce = false;       // option exchange_allreduce: all-reduce the J planes (round-1 path) instead of
+                                          // reduce-scatter -> fold the share -> all-gather float32
+    bool solo = false;                    // option solo
+    int soloRank = 0, soloNranks = 1;
+    bool keepSharded = false;             // option keep_sharded: skip the all-gather (Jste stays valid only on the owner's share)
     bool exchanged = false;               // the pending tallies are already global (mcb200_exchange ran)
     bool deferFold = false;               // option defer_fold: a single rank keeps its tallies pending like a multi-rank run
     // pending fold
@@ -364,6 +375,61 @@ int ensure_second_set(mcb200_ctx *ctx, GridState &g)
     return MCB200_OK;
 }
 
+// ---- NCCL, bound at run time -----------------------------------------------------------------
+// The library has no link-time dependency on NCCL: single-rank hosts never need it, and a
+// Python host has torch's copy in the process already (dlopen by SONAME returns that one).
+// Search order: $MCB200_NCCL_LIB, libnccl.so.2, libnccl.so.  Types restated from nccl.h (2.x ABI).
+struct NcclId { char internal[128]; };
+enum { kNcclInt32 = 2, kNcclUint32 = 3, kNcclUint64 = 5, kNcclFloat32 = 7, kNcclSum = 0, kNcclMax = 2 };
+struct NcclApi {
+    void *handle = nullptr;
+    int (*GetUniqueId)(NcclId *) = nullptr;
+    int (*CommInitRank)(void **, int, NcclId, int) = nullptr;
+    int (*CommDestroy)(void *) = nullptr;
+    int (*AllReduce)(const void *, void *, size_t, int, int, void *, cudaStream_t) = nullptr;
+    int (*AllGather)(const void *, void *, size_t, int, void *, cudaStream_t) = nullptr;
+    int (*ReduceScatter)(const void *, void *, size_t, int, int, void *, cudaStream_t) = nullptr;
+    int (*GroupStart)() = nullptr;
+    int (*GroupEnd)() = nullptr;
+    const char *(*GetErrorString)(int) = nullptr;
+    int (*GetVersion)(int *) = nullptr;
+    std::string why;
+};
+
+NcclApi &nccl_api()
+{
+    static NcclApi api;
+    if (api.handle || !api.why.empty()) return api;
+    const char *env = std::getenv("MCB200_NCCL_LIB");
+    const char *names[3] = {env, "libnccl.so.2", "libnccl.so"};
+    for (const char *nm : names) {
+        if (!nm || !*nm) continue;
+        api.handle = dlopen(nm, RTLD_NOW | RTLD_LOCAL);
+        if (api.handle) break;
+    }
+    if (!api.handle) { api.why = "libnccl.so.2 not found (set MCB200_NCCL_LIB)"; return api; }
+    bool ok = true;
+    auto sym = [&](const char *n) { void *p = dlsym(api.handle, n); if (!p) { ok = false; api.why = std::string("NCCL symbol missing: ") + n; } return p; };
+    api.GetUniqueId = reinterpret_cast<decltype(api.GetUniqueId)>(sym("ncclGetUniqueId"));
+    api.CommInitRank = reinterpret_cast<decltype(api.CommInitRank)>(sym("ncclCommInitRank"));
+    api.CommDestroy = reinterpret_cast<decltype(api.CommDestroy)>(sym("ncclCommDestroy"));
+    api.AllReduce = reinterpret_cast<decltype(api.AllReduce)>(sym("ncclAllReduce"));
+    api.AllGather = reinterpret_cast<decltype(api.AllGather)>(sym("ncclAllGather"));
+    api.ReduceScatter = reinterpret_cast<decltype(api.ReduceScatter)>(sym("ncclReduceScatter"));
+    api.GroupStart = reinterpret_cast<decltype(api.GroupStart)>(sym("ncclGroupStart"));
+    api.GroupEnd = reinterpret_cast<decltype(api.GroupEnd)>(sym("ncclGroupEnd"));
+    api.GetErrorString = reinterpret_cast<decltype(api.GetErrorString)>(sym("ncclGetErrorString"));
+    api.GetVersion = reinterpret_cast<decltype(api.GetVersion)>(sym("ncclGetVersion"));
+    if (!ok) { dlclose(api.handle); api.handle = nullptr; }
+    return api;
+}
+
+#define NC(call)                                                                                   \
+    do {                                                                                           \
+        int r__ = (call);                                                                          \
+        if (r__ != 0) return fail(ctx, MCB200_ECOMM, "%s: %s", #call, nccl_api().GetErrorString(r__)); \
+    } while (0)
+
 // contiguous runs [first,last] of touched frequency bins (gaps of <= 2 bins are bridged)
 std::vector<std::pair<int, int>> touched_ranges(const std::vector<int> &flag, int bridge = 3)
 {
@@ -419,18 +485,18 @@ int sed_tally(mcb200_ctx *ctx, int set, int *launches)
 
 // fold the tallies of the nu-planes [nu0, nu1] of one grid: J planes nu >= 1, escape-count planes
 // nu0..nu1 of every viewing angle.  Asynchronous on the library stream.
-int fold_planes(mcb200_ctx *ctx, GridState &g, int nu0, int nu1, int *launches)
+int fold_planes(mcb200_ctx *ctx, GridState &g, int nu0, int nu1, int *launches, bool withJ = true)
 {
     const int nb = ctx->cfg.nbins, blocks = ctx->numSMs * 8;
     const size_t nR = (size_t)g.nCells + 1;
     const double lenUnit = std::ldexp(1.0, g.lenExp);
     int p0 = nu0 < 1 ? 1 : nu0, p1 = nu1;
-    if (p1 >= p0) {
+    if (withJ && p1 >= p0) {
         size_t off = (size_t)(p0 - 1) * nR, len = (size_t)(p1 - p0 + 1) * nR;
-        CU(launch_fold_j(g.JsteQ.p + off, g.Jste.p + off, g.dV.p, (int)nR, len, lenUnit, ctx->pendingDeltaE, blocks, ctx->stream));
+        CU(launch_fold_j(g.JsteQ.p + off, g.Jste.p + off, g.dV.p, (int)nR, off, len, lenUnit, ctx->pendingDeltaE, blocks, ctx->stream));
         if (launches) ++*launches;
         if (ctx->cfg.lgDebug) {
-            CU(launch_fold_j(g.JdifQ.p + off, g.Jdif.p + off, g.dV.p, (int)nR, len, lenUnit, ctx->pendingDeltaE, blocks, ctx->stream));
+            CU(launch_fold_j(g.JdifQ.p + off, g.Jdif.p + off, g.dV.p, (int)nR, off, len, lenUnit, ctx->pendingDeltaE, blocks, ctx->stream));
             if (launches) ++*launches;
         }
     }
@@ -440,6 +506,45 @@ int fold_planes(mcb200_ctx *ctx, GridState &g, int nu0, int nu1, int *launches)
         CU(launch_fold_count(g.escQ.p + off, g.esc.p + off, len, ctx->pendingDeltaE, blocks, ctx->stream));
         if (launches) ++*launches;
     }
+    return MCB200_OK;
+}
+
+// J planes after the reduce-scatter of mcb200_exchange (comm_exchange): this rank holds the global
+// integer sums of its share of every exchanged range, the tail of each range on every rank.  Fold
+// the share (1/nranks of the work), clear the other ranks' shares (partial sums that have been
+// handed over), then all-gather the float32 results in place: every rank ends with the estimator
+// the all-reduce + full fold gave, bit for bit (same integer sums, same fold arithmetic), with
+// 12 instead of 16 bytes per element on the wire and the fold divided by nranks.
+int fold_shards(mcb200_ctx *ctx, GridState &g, int *launches)
+{
+    NcclApi &N = nccl_api();
+    const int blocks = ctx->numSMs * 8, world = ctx->nranks, rank = ctx->rank;
+    const size_t nR = (size_t)g.nCells + 1;
+    const double lenUnit = std::ldexp(1.0, g.lenExp);
+    cudaStream_t s = ctx->stream;
+    const int nSets = ctx->cfg.lgDebug && g.JdifQ.p ? 2 : 1;
+    for (int set = 0; set < nSets; ++set) {
+        unsigned long long *Q = set ? g.JdifQ.p : g.JsteQ.p;
+        float *J = set ? g.Jdif.p : g.Jste.p;
+        for (auto &r : g.jShards) {
+            const size_t mine = r.off + (size_t)rank * r.count, tail = r.off + (size_t)world * r.count;
+            CU(launch_fold_j(Q + mine, J + mine, g.dV.p, (int)nR, mine, r.count, lenUnit, ctx->pendingDeltaE, blocks, s));
+            CU(launch_fold_j(Q + tail, J + tail, g.dV.p, (int)nR, tail, r.off + r.len - tail, lenUnit, ctx->pendingDeltaE, blocks, s));
+            if (launches) *launches += 2;
+            if (mine > r.off) CU(cudaMemsetAsync(Q + r.off, 0, (mine - r.off) * 8, s));
+            if (tail > mine + r.count) CU(cudaMemsetAsync(Q + mine + r.count, 0, (tail - mine - r.count) * 8, s));
+        }
+        if (!ctx->keepSharded) {
+            NC(N.GroupStart());
+            for (auto &r : g.jShards)
+                if (r.count) {
+                    NC(N.AllGather(J + r.off + (size_t)rank * r.count, J + r.off, r.count, kNcclFloat32, ctx->comm, s));
+                    ctx->lastExchangeBytes += (int64_t)r.count * 4;
+                }
+            NC(N.GroupEnd());
+        }
+    }
+    g.jShards.clear();
     return MCB200_OK;
 }
 
@@ -487,8 +592,13 @@ int fold_pending(mcb200_ctx *ctx)
         // planes a ranged fold (mcb200_reduce_range) has already taken are skipped
         if (!g.folded.empty())
             for (int nu = 0; nu <= nb; ++nu) if (g.folded[nu]) flag[nu] = 0;
+        const bool sharded = !g.jShards.empty();
         for (auto &rg : touched_ranges(flag, g.folded.empty() ? 3 : 1)) {
-            int rc = fold_planes(ctx, g, rg.first, rg.second, &launches);
+            int rc = fold_planes(ctx, g, rg.first, rg.second, &launches, /*withJ=*/!sharded);
+            if (rc) return rc;
+        }
+        if (sharded) {
+            int rc = fold_shards(ctx, g, &launches);
             if (rc) return rc;
         }
         g.folded.clear();
@@ -923,59 +1033,6 @@ __global__ void uniforms_kernel(unsigned long long seed, unsigned long long pid,
 }
 
 
-// ---- NCCL, bound at run time -----------------------------------------------------------------
-// The library has no link-time dependency on NCCL: single-rank hosts never need it, and a
-// Python host has torch's copy in the process already (dlopen by SONAME returns that one).
-// Search order: $MCB200_NCCL_LIB, libnccl.so.2, libnccl.so.  Types restated from nccl.h (2.x ABI).
-struct NcclId { char internal[128]; };
-enum { kNcclInt32 = 2, kNcclUint32 = 3, kNcclUint64 = 5, kNcclSum = 0, kNcclMax = 2 };
-struct NcclApi {
-    void *handle = nullptr;
-    int (*GetUniqueId)(NcclId *) = nullptr;
-    int (*CommInitRank)(void **, int, NcclId, int) = nullptr;
-    int (*CommDestroy)(void *) = nullptr;
-    int (*AllReduce)(const void *, void *, size_t, int, int, void *, cudaStream_t) = nullptr;
-    int (*AllGather)(const void *, void *, size_t, int, void *, cudaStream_t) = nullptr;
-    int (*GroupStart)() = nullptr;
-    int (*GroupEnd)() = nullptr;
-    const char *(*GetErrorString)(int) = nullptr;
-    int (*GetVersion)(int *) = nullptr;
-    std::string why;
-};
-
-NcclApi &nccl_api()
-{
-    static NcclApi api;
-    if (api.handle || !api.why.empty()) return api;
-    const char *env = std::getenv("MCB200_NCCL_LIB");
-    const char *names[3] = {env, "libnccl.so.2", "libnccl.so"};
-    for (const char *nm : names) {
-        if (!nm || !*nm) continue;
-        api.handle = dlopen(nm, RTLD_NOW | RTLD_LOCAL);
-        if (api.handle) break;
-    }
-    if (!api.handle) { api.why = "libnccl.so.2 not found (set MCB200_NCCL_LIB)"; return api; }
-    bool ok = true;
-    auto sym = [&](const char *n) { void *p = dlsym(api.handle, n); if (!p) { ok = false; api.why = std::string("NCCL symbol missing: ") + n; } return p; };
-    api.GetUniqueId = reinterpret_cast<decltype(api.GetUniqueId)>(sym("ncclGetUniqueId"));
-    api.CommInitRank = reinterpret_cast<decltype(api.CommInitRank)>(sym("ncclCommInitRank"));
-    api.CommDestroy = reinterpret_cast<decltype(api.CommDestroy)>(sym("ncclCommDestroy"));
-    api.AllReduce = reinterpret_cast<decltype(api.AllReduce)>(sym("ncclAllReduce"));
-    api.AllGather = reinterpret_cast<decltype(api.AllGather)>(sym("ncclAllGather"));
-    api.GroupStart = reinterpret_cast<decltype(api.GroupStart)>(sym("ncclGroupStart"));
-    api.GroupEnd = reinterpret_cast<decltype(api.GroupEnd)>(sym("ncclGroupEnd"));
-    api.GetErrorString = reinterpret_cast<decltype(api.GetErrorString)>(sym("ncclGetErrorString"));
-    api.GetVersion = reinterpret_cast<decltype(api.GetVersion)>(sym("ncclGetVersion"));
-    if (!ok) { dlclose(api.handle); api.handle = nullptr; }
-    return api;
-}
-
-#define NC(call)                                                                                   \
-    do {                                                                                           \
-        int r__ = (call);                                                                          \
-        if (r__ != 0) return fail(ctx, MCB200_ECOMM, "%s: %s", #call, nccl_api().GetErrorString(r__)); \
-    } while (0)
-
 // in-place sum / max over ranks of `count` elements on the library stream
 int comm_allreduce(mcb200_ctx *ctx, void *buf, size_t count, int dtype, int op)
 {
@@ -1062,17 +1119,35 @@ int comm_exchange(mcb200_ctx *ctx)
         CU(cudaMemcpyAsync(flag.data(), g.nuTouched.p, sizeof(int) * (nb + 1), cudaMemcpyDeviceToHost, s));
         CU(cudaStreamSynchronize(s));
         auto ranges = touched_ranges(flag);
+        g.jShards.clear();
+        NC(nccl_api().GroupStart());
         for (auto &rg : ranges) {
             int p0 = rg.first < 1 ? 1 : rg.first, p1 = rg.second;
             if (p1 < p0) continue;
             size_t off = (size_t)(p0 - 1) * nR, len = (size_t)(p1 - p0 + 1) * nR;
-            rc = comm_allreduce(ctx, g.JsteQ.p + off, len, kNcclUint64, kNcclSum);
-            if (rc) return rc;
-            if (ctx->cfg.lgDebug && g.JdifQ.p) {
-                rc = comm_allreduce(ctx, g.JdifQ.p + off, len, kNcclUint64, kNcclSum);
+            const int nSets = ctx->cfg.lgDebug && g.JdifQ.p ? 2 : 1;
+            if (ctx->exchangeAllReduce || ctx->nranks == 1) {
+                for (int set = 0; set < nSets; ++set) {
+                    rc = comm_allreduce(ctx, (set ? g.JdifQ.p : g.JsteQ.p) + off, len, kNcclUint64, kNcclSum);
+                    if (rc) return rc;
+                }
+                continue;
+            }
+            // reduce-scatter in place: rank r receives the sum of elements [off + r*count, +count);
+            // the < nranks elements left over at the end of the range are all-reduced
+            const size_t count = len / (size_t)ctx->nranks, tail = len - count * (size_t)ctx->nranks;
+            for (int set = 0; set < nSets; ++set) {
+                unsigned long long *Q = (set ? g.JdifQ.p : g.JsteQ.p) + off;
+                if (count) {
+                    NC(nccl_api().ReduceScatter(Q, Q + (size_t)ctx->rank * count, count, kNcclUint64, kNcclSum, ctx->comm, s));
+                    ctx->lastExchangeBytes += (int64_t)(count * (size_t)ctx->nranks) * 8;
+                }
+                rc = comm_allreduce(ctx, Q + count * (size_t)ctx->nranks, tail, kNcclUint64, kNcclSum);
                 if (rc) return rc;
             }
+            g.jShards.push_back({off, len, count});
         }
+        NC(nccl_api().GroupEnd());
         if (ctx->cfg.lgDebug && g.lineQ.n) {
             rc = comm_allreduce(ctx, g.lineQ.p, g.lineQ.n, kNcclUint32, kNcclSum);
             if (rc) return rc;
@@ -1584,6 +1659,8 @@ int mcb200_zero_estimators(mcb200_ctx *ctx)
         CU(g.lineQ.zero(ctx->stream)); CU(g.linePk.zero(ctx->stream));
         CU(g.nuTouched.zero(ctx->stream));
         CU(g.JsteQ2.zero(ctx->stream)); CU(g.escQ2.zero(ctx->stream)); CU(g.nuTouched2.zero(ctx->stream));
+        g.folded.clear();
+        g.jShards.clear();
     }
     ctx->pending2 = false;
     CU(ctx->planeDist.zero(ctx->stream));
@@ -1734,6 +1811,7 @@ int mcb200_exchange(mcb200_ctx *ctx)
 {
     NEED_CTX();
     if (!ctx->haveCfg) return fail(ctx, MCB200_ESTATE, "set_config first");
+    if (ctx->solo) return fail(ctx, MCB200_ESTATE, "option solo is set: this context runs as a single rank");
     if (!ctx->pending || (ctx->nranks == 1 && !ctx->comm)) return MCB200_OK;
     if (!ctx->comm) return fail(ctx, MCB200_ESTATE, "no communicator: call mcb200_comm_init (or all-reduce the buffers of mcb200_tally_buffer yourself)");
     if (ctx->exchanged) return fail(ctx, MCB200_ESTATE, "pending tallies already exchanged: call mcb200_reduce");
@@ -1831,6 +1909,37 @@ int mcb200_fetch_contcube(mcb200_ctx *ctx, int32_t iG, float *contI)
     CU(launch_contcube(g->esc.p, nR, ctx->cfg.nbins, nA, g->contI.p, ctx->stream));
     CU(cudaMemcpyAsync(contI, g->contI.p, nR * (size_t)nA * sizeof(float), cudaMemcpyDeviceToHost, ctx->stream));
     CU(cudaStreamSynchronize(ctx->stream));
+    return MCB200_OK;
+}
+
+// position-sensitive 64-bit checksum of a float32 array (bit patterns): sum of bits(i) * (2*i + 1)
+// mod 2^64 -- equal arrays give equal sums, and a changed, moved or missing element changes it
+__global__ void __launch_bounds__(256) checksum_kernel(const unsigned int *__restrict__ x, size_t n, unsigned long long *out)
+{
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x, stride = (size_t)gridDim.x * blockDim.x;
+    unsigned long long s = 0;
+    for (; i < n; i += stride) s += (unsigned long long)x[i] * (2ull * (unsigned long long)i + 1ull);
+    for (int o = 16; o > 0; o >>= 1) s += __shfl_down_sync(0xffffffffu, s, o);
+    if ((threadIdx.x & 31) == 0 && s) atomicAdd(out, s);
+}
+
+int mcb200_checksum(mcb200_ctx *ctx, int32_t iG, int32_t which, uint64_t *sum)
+{
+    NEED_CTX();
+    GridState *g = grid_of(ctx, iG);
+    if (!g || !g->set || !sum) return fail(ctx, MCB200_EINVAL, "bad checksum arguments");
+    if (ctx->pending) return fail(ctx, MCB200_ESTATE, "tallies pending: call mcb200_reduce first");
+    int rc = ensure_estimators(ctx, *g);
+    if (rc) return rc;
+    DevBuf<float> *b = which == 0 ? &g->Jste : which == 1 ? &g->esc : which == 2 ? &g->Jdif : which == 3 ? &g->linePk : nullptr;
+    if (!b) return fail(ctx, MCB200_EINVAL, "bad checksum selector %d", which);
+    CU(ctx->nConv.alloc(1)); CU(ctx->nConv.zero(ctx->stream));
+    if (b->n) checksum_kernel<<<ctx->numSMs * 8, 256, 0, ctx->stream>>>(reinterpret_cast<const unsigned int *>(b->p), b->n, ctx->nConv.p);
+    CU(cudaGetLastError());
+    unsigned long long v = 0;
+    CU(cudaMemcpyAsync(&v, ctx->nConv.p, 8, cudaMemcpyDeviceToHost, ctx->stream));
+    CU(cudaStreamSynchronize(ctx->stream));
+    *sum = (uint64_t)v;
     return MCB200_OK;
 }
 
@@ -2115,6 +2224,16 @@ int mcb200_set_option(mcb200_ctx *ctx, const char *name, int64_t value)
         ctx->partIndex = (int)value; return MCB200_OK;
     }
     if (!strcmp(name, "exchange_dense")) { ctx->exchangeDense = value != 0; return MCB200_OK; }
+    if (!strcmp(name, "exchange_allreduce")) { ctx->exchangeAllReduce = value != 0; return MCB200_OK; }
+    if (!strcmp(name, "solo")) {
+        // 1: this rank behaves as rank 0 of 1 (transports every packet of a call itself and folds at
+        // once) until the option is cleared -- the N-rank answer checked against the 1-rank answer
+        // on the same context (bench.py: nrank_parity)
+        if (ctx->pending) return fail(ctx, MCB200_ESTATE, "option solo: tallies pending, call mcb200_reduce first");
+        if (value && !ctx->solo) { ctx->soloRank = ctx->rank; ctx->soloNranks = ctx->nranks; ctx->rank = 0; ctx->nranks = 1; ctx->solo = true; }
+        else if (!value && ctx->solo) { ctx->rank = ctx->soloRank; ctx->nranks = ctx->soloNranks; ctx->solo = false; }
+        return MCB200_OK;
+    }
     if (!strcmp(name, "defer_fold")) { ctx->deferFold = value != 0; return MCB200_OK; }
     if (!strcmp(name, "agg_steps")) { ctx->aggSteps = (int)value; return MCB200_OK; }
     if (!strcmp(name, "batch")) { ctx->batch = (int)value; return MCB200_OK; }

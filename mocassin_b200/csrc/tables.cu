@@ -63,8 +63,10 @@ cudaError_t launch_check_monotone(const float *pdfT, int nRows, int nb, int *bad
 // One thread per element, each element touched by exactly one thread -> deterministic.
 // HBM-bound: J: 8 B (Q) read + 4 B read; counts: 4 B (Q) read + 4 B read; writes only where Q != 0.
 // ---------------------------------------------------------------------------------------
+// Q, J point at element `first` of the (0:nCells, nbins) tables (any element: a rank's shard of
+// a reduce-scattered range need not start on a plane boundary)
 __global__ void fold_j_kernel(unsigned long long *__restrict__ Q, float *__restrict__ J,
-                              const float *__restrict__ dV, int nRows, size_t total,
+                              const float *__restrict__ dV, int nRows, size_t first, size_t total,
                               double lenUnit, float deltaE)
 {
     size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -72,7 +74,7 @@ __global__ void fold_j_kernel(unsigned long long *__restrict__ Q, float *__restr
     for (; i < total; i += stride) {
         long long q = (long long)Q[i];
         if (q != 0) {
-            int cell = (int)(i % (size_t)nRows);
+            int cell = (int)((first + i) % (size_t)nRows);
             float len = (float)((double)q * lenUnit);
             J[i] = J[i] + len * deltaE / dV[cell];
             Q[i] = 0ull;
@@ -293,10 +295,11 @@ cudaError_t launch_merge_sets(unsigned long long *J0, unsigned long long *J1, si
     return cudaGetLastError();
 }
 
-cudaError_t launch_fold_j(unsigned long long *Q, float *J, const float *dV, int nRows, size_t total,
+cudaError_t launch_fold_j(unsigned long long *Q, float *J, const float *dV, int nRows, size_t first, size_t total,
                           double lenUnit, float deltaE, int blocks, cudaStream_t s)
 {
-    fold_j_kernel<<<blocks, 256, 0, s>>>(Q, J, dV, nRows, total, lenUnit, deltaE);
+    if (total == 0) return cudaSuccess;
+    fold_j_kernel<<<blocks, 256, 0, s>>>(Q, J, dV, nRows, first, total, lenUnit, deltaE);
     return cudaGetLastError();
 }
 

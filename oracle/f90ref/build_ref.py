@@ -70,10 +70,12 @@ PROC_HOOKS = {'energypacketrun'}             # one call per packet generation
 AUX_SOURCES = [
     ('constants_mod.f90', False, None, None),
     ('vector_mod.f90', False, None, None),       # the vector operators (integratePathTauNu: rVec + dlSmall*vHat)
-    ('interpolation_mod.f90', False, {'locate', 'linearmap'}, None),
+    ('interpolation_mod.f90', False, {'locate', 'linearmap', 'sortup'}, None),
     ('common_mod.f90', True, None, None),
-    ('ph_mod.f90', False, {'bhmie', 'getqs'}, None),      # module xSec_mod; BHmie (COMPLEX arithmetic, statement functions)
-    ('hydro_mod.f90', False, {'getoutershell'}, None),   # module elements_mod
+    # module xSec_mod; BHmie (COMPLEX arithmetic, statement functions); the gas cross-section stack
+    ('ph_mod.f90', False, {'bhmie', 'getqs', 'initxsecarray', 'phfitel', 'phfithion', 'powlawxsec', 'makeopacity'}, None),
+    # module elements_mod: level energies, shell / continuum pointers
+    ('hydro_mod.f90', False, {'getoutershell', 'makehydro', 'setshells', 'limitshell', 'setpointers'}, None),
     ('grid_mod.f90', False, {'writegrid', 'setstarposition', 'getvolume'}, None),
     ('composition_mod.f90', True, None, None),
     ('set_input_mod.f90', True, None, None),
@@ -128,6 +130,17 @@ AUX_SLICES = [
          glue_end=[],
          guards={901: 'type(grid_type), intent(inout) :: grid', 938: 'character(len=40)', 1226: 'grid%ncells = 0',
                  1235: 'radius = 1.e10*sqrt(', 1294: 'end do'}),
+    # initCartesianGrid: the ionisation thresholds inside the frequency range, the gas-only frequency
+    # mesh (series edges, thresholds, logarithmic fill, sortUp) and widFlx
+    dict(file='grid_mod.f90', name='gas_nu_mesh', args='', decls=[(31, 47)], body=[(132, 175), (215, 258), (333, 338)],
+         glue_decls=[], glue_start=['allocate(nuarray(1:nbins))', 'allocate(widflx(1:nbins))'], glue_end=[],
+         guards={31: 'integer :: err, ios', 132: 'seriesedge = (/0.0069', 175: 'call sortup(ionedge(1:nedges))',
+                 216: 'if (numin<radio4p9ghz) then', 258: 'call sortup(nuarray)', 333: 'widflx(1) = nuarray(2)-nuarray(1)',
+                 338: 'widflx(nbins) = nuarray(nbins)-nuarray(nbins-1)'}),
+    # setMotherGrid: the ionisation state every active cell starts from
+    dict(file='grid_mod.f90', name='initial_ions', args='grid, in_ytop', decls=[(901, 901), (904, 938)], body=[(1564, 1607)],
+         glue_decls=['integer, intent(in) :: in_ytop'], glue_start=['ytop = in_ytop'], glue_end=[],
+         guards={1564: 'h0in = 1.e-5', 1607: 'end do'}),
     # initCartesianGrid: angular bins of the escape tallies and the viewing-angle pointer tables
     dict(file='grid_mod.f90', name='angle_tables', args='', decls=[], body=[(416, 468)],
          glue_decls=['integer :: i, err'], glue_end=[],
@@ -161,9 +174,11 @@ AUX_SLICES = [
 # supplied by the harness: BoltGaunt (ionization_mod.f90:134-174) fills contBoltz/gauntFF from Gaunt
 # factor tables; its only trace in the opacity is the free-free term of bin 1, which the
 # oracle takes as an input (ff1), so the harness sets those arrays directly
-AUX_EXTERNS = {'boltgaunt'}
+AUX_EXTERNS = {'boltgaunt',
+               # file readers and branches off the gas-deck path (initXSecArray, setPointers): supplied as no-ops
+               'makecolliondata', 'makeaugerdata', 'readheireclines', 'setcompton', 'makedustxsec', 'phinit'}
 # procedures that must translate completely, and the untranslated statements tolerated in them
-AUX_STRICT = {'writegrid': 0, 'setstarposition': 0, 'getvolume': 0, 'writesed': 0, 'writecontcube': 0, 'writetaunu': 0, 'integratepathtaunu': 0, 'bhmie': 0, 'getqs': 0, 'dust_xsec_assembly': 0, 'dust_emission_int': 0, 'grain_weights': 0, 'angle_tables': 0, 'active_cells': 0, 'fill_axes': 0, 'fill_mask': 0, 'opacity_block': 0, 'photo_rates': 0, 'photo_heat': 0, 'getoutershell': 0, 'ionizationdriver': 0, 'edensum': 0, 'addopacity': 0, 'putopacity': 0, 'inopacity': 0, 'getflux': 0, 'setprobden': 0, 'locate': 0, 'linearmap': 0,
+AUX_STRICT = {'writegrid': 0, 'setstarposition': 0, 'getvolume': 0, 'writesed': 0, 'writecontcube': 0, 'writetaunu': 0, 'integratepathtaunu': 0, 'bhmie': 0, 'getqs': 0, 'dust_xsec_assembly': 0, 'dust_emission_int': 0, 'grain_weights': 0, 'angle_tables': 0, 'active_cells': 0, 'fill_axes': 0, 'fill_mask': 0, 'opacity_block': 0, 'photo_rates': 0, 'photo_heat': 0, 'getoutershell': 0, 'ionizationdriver': 0, 'edensum': 0, 'addopacity': 0, 'putopacity': 0, 'inopacity': 0, 'getflux': 0, 'setprobden': 0, 'locate': 0, 'linearmap': 0, 'sortup': 0, 'gas_nu_mesh': 0, 'initial_ions': 0, 'initxsecarray': 0, 'phfitel': 0, 'phfithion': 0, 'powlawxsec': 0, 'makeopacity': 0, 'makehydro': 0, 'setshells': 0, 'limitshell': 0, 'setpointers': 0,
               'setdustpdf': 1,      # call qHeat (lgQHeat branch)
               'getdustt': 1}        # resLineHeating (gas + resonance-line transfer branch)
 

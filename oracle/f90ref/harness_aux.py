@@ -640,3 +640,80 @@ class AuxReference:
             for (i, j, k) in _cells(g.active):
                 self.ref.p_updatecell(t, i, j, k)
         return t.tdust.a, t.lgconverged.a.astype(np.int32)
+
+
+# ---- gas-side input data (tests/test_reference_pin_gas.py) ------------------------------------
+def _gas_nu_mesh(self, ph1, ph2, lgElementOn, nstages, nbins, nuMin, nuMax):
+    """The ionisation thresholds + the gas-only frequency mesh + widFlx of initCartesianGrid
+    (grid_mod.f90:132-175, 215-258, 333-338; statement-range slice) with getOuterShell and sortUp.
+    ph1 / ph2 are what phInit reads from data/ph1.dat, data/ph2.dat (the translator has no READ:
+    the harness parses the files).  Returns (nuArray, widFlx, ionEdge(1:nEdges) sorted)."""
+    G, ref = self.G, self.ref
+    G.lggas, G.lgdust = True, False
+    G.nbins, G.nstages = int(nbins), int(nstages)
+    G.numin, G.numax = np.float32(nuMin), np.float32(nuMax)
+    G.ph1 = rt.wrap(_F(ph1, np.float32))
+    G.ph2 = rt.wrap(_F(ph2, np.float32))
+    G.lgelementon = rt.wrap(np.asarray(lgElementOn) != 0)
+    G.ionedge = rt.wrap(np.zeros(450, np.float32))
+    with np.errstate(all='ignore'):
+        ref.p_gas_nu_mesh()
+    edges = G.ionedge.a.copy()
+    return G.nuarray.a.copy(), G.widflx.a.copy(), edges
+
+
+def _gas_xsec(self, nu, ph1, ph2, lgElementOn, nstages):
+    """setPointers (makeHydro, setShells, limitShell) + initXSecArray (phFitEl, phFitHIon,
+    powLawXSec, makeOpacity) of the reference on the mesh `nu` (hydro_mod.f90:56-85,208-475;
+    ph_mod.f90:204-402,477-606,712-803).  The file readers on the way (makeCollIonData,
+    makeAugerData, readHeIRecLines) are no-ops.  Returns the cross-section stack and every pointer."""
+    G, ref = self.G, self.ref
+    G.lggas, G.lgdust, G.lgcompton = True, False, False
+    G.nbins, G.nstages = int(len(nu)), int(nstages)
+    G.nuarray = rt.wrap(_F(nu, np.float32))
+    G.ph1 = rt.wrap(_F(ph1, np.float32))
+    G.ph2 = rt.wrap(_F(ph2, np.float32))
+    G.level = rt.wrap(np.array([0, 0, 1, 0, 1, 2, 0], np.int64))
+    G.ninn = rt.wrap(np.array([0, 0, 1, 1, 1, 1, 1, 1, 1, 1, 3, 3, 3, 3, 3, 3, 3, 3, 5, 5, 5, 5, 5, 5, 5, 5, 5, 5, 5, 5], np.int64))
+    G.ntot = rt.wrap(np.array([1, 1, 2, 2, 3, 3, 3, 3, 3, 3, 4, 4, 5, 5, 5, 5, 5, 5, 6, 6, 6, 6, 6, 6, 6, 6, 6, 6, 7, 7], np.int64))
+    G.lgelementon = rt.wrap(np.asarray(lgElementOn) != 0)
+    G.elementp = rt.wrap(np.zeros((30, 30, 7, 3), np.int64, order='F'))
+    G.nshells = rt.wrap(np.zeros((30, 30), np.int64, order='F'))
+    for name in ('makecolliondata', 'makeaugerdata', 'readheireclines', 'setcompton', 'makedustxsec', 'phinit'):
+        rt.externs[name] = lambda: None
+    with np.errstate(all='ignore'):
+        ref.p_initxsecarray()
+    return dict(xSecArray=G.xsecarray.a.copy(), xSecTop=int(G.xsectop), elementP=G.elementp.a.copy(), nShells=G.nshells.a.copy(),
+                HlevNuP=G.hlevnup.a.copy(), HeIlevNuP=G.heilevnup.a.copy(), HeIIlevNuP=G.heiilevnup.a.copy(),
+                HlevXSecP=G.hlevxsecp.a.copy(), HeISingXSecP=G.heisingxsecp.a.copy(), HeIIXSecP=G.heiixsecp.a.copy(),
+                bremsXSecP=int(G.bremsxsecp), KshellLimitP=int(G.kshelllimitp), HlevEn=G.hleven.a.copy(),
+                HeIlevEn=G.heileven.a.copy(), HeIIlevEn=G.heiileven.a.copy())
+
+
+AuxReference.gas_nu_mesh = _gas_nu_mesh
+AuxReference.gas_xsec = _gas_xsec
+
+
+def _initial_ions(self, active, lgElementOn, elementXref, nstages):
+    """The initial ionisation state of setMotherGrid (grid_mod.f90:1564-1607; statement-range
+    slice): ionDen(0:nCells, nElementsUsed, nstages) and Ne for every active cell."""
+    G, ref = self.G, self.ref
+    G.lggas, G.nstages = True, int(nstages)
+    G.lgelementon = rt.wrap(np.asarray(lgElementOn) != 0)
+    G.elementxref = rt.wrap(_F(elementXref, np.int64))
+    nUsed = int((np.asarray(lgElementOn) != 0).sum())
+    nCells = int(active.max())
+    g = ref.T_grid_type()
+    g.nx, g.ny, g.nz = active.shape
+    g.ncells = nCells
+    g.active = rt.wrap(_F(active, np.int64))
+    ion = np.zeros((nCells + 1, nUsed, nstages), np.float32, order='F')
+    g.ionden = rt.wrap(ion, (0, 1, 1))
+    hden = np.full(nCells + 1, 100.0, np.float32)
+    ne = np.zeros(nCells + 1, np.float32)
+    g.hden, g.ne = rt.wrap(hden, (0,)), rt.wrap(ne, (0,))
+    ref.p_initial_ions(g, int(active.shape[1]))
+    return ion, ne
+
+
+AuxReference.initial_ions = _initial_ions

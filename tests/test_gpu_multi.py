@@ -22,6 +22,16 @@ def _free_port():
 
 
 def _worker(rank, world, port, name, n, q, overlap=False, sed_local=False, sparse=True, pipelined=False):
+    try:
+        _worker_body(rank, world, port, name, n, q, overlap, sed_local, sparse, pipelined)
+    except BaseException as ex:              # a dead worker must not leave the parent waiting on the queue
+        import traceback
+
+        q.put((rank, "error: " + "".join(traceback.format_exception(type(ex), ex, ex.__traceback__))[-3000:]))
+        raise
+
+
+def _worker_body(rank, world, port, name, n, q, overlap=False, sed_local=False, sparse=True, pipelined=False):
     sys.path.insert(0, ROOT)
     sys.path.insert(0, os.path.join(ROOT, "tests"))
     import torch
@@ -81,10 +91,17 @@ def test_nccl_allreduce_matches_single_gpu(name, overlap, sparse):
     procs = [ctx.Process(target=_worker, args=(r, 2, port, name, n, q, overlap, False, sparse, pipelined)) for r in range(2)]
     for p in procs:
         p.start()
-    got = dict(q.get(timeout=600) for _ in range(2))
-    for p in procs:
-        p.join(timeout=120)
-        assert p.exitcode == 0
+    try:
+        got = dict(q.get(timeout=240) for _ in range(2))
+        for v in got.values():
+            assert not isinstance(v, str), v
+        for p in procs:
+            p.join(timeout=120)
+            assert p.exitcode == 0
+    finally:
+        for p in procs:                      # a rank stuck in a collective behind a dead peer
+            if p.is_alive():
+                p.kill()
     m, _ = make(name)
     e = PacketEngine(m, seed=12345)
     e.upload_iteration_inputs()
@@ -119,10 +136,17 @@ def test_nccl_sed_exchange_replaces_escaped_packets(overlap):
     procs = [ctx.Process(target=_worker, args=(r, 2, port, name, n, q, overlap, True)) for r in range(2)]
     for p in procs:
         p.start()
-    got = dict(q.get(timeout=600) for _ in range(2))
-    for p in procs:
-        p.join(timeout=120)
-        assert p.exitcode == 0
+    try:
+        got = dict(q.get(timeout=240) for _ in range(2))
+        for v in got.values():
+            assert not isinstance(v, str), v
+        for p in procs:
+            p.join(timeout=120)
+            assert p.exitcode == 0
+    finally:
+        for p in procs:                      # a rank stuck in a collective behind a dead peer
+            if p.is_alive():
+                p.kill()
     m, _ = make(name)
     e = PacketEngine(m, seed=12345)
     e.upload_iteration_inputs()

@@ -16,9 +16,6 @@ import numpy as np
 import pytest
 
 pytestmark = pytest.mark.gpu
-# the one-rank tests below passed on a B200 (profiles/r01_native_comm_gpu_tests.log); the tests carrying this
-# mark were written after round 1's GPU budget was spent: outcome recorded (XPASS / XFAIL), not gating
-UNVERIFIED = pytest.mark.xfail(strict=False, reason="never run on a GPU before round 1 ended (outcome recorded, not gating)")
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, os.path.join(ROOT, "tests"))
 
@@ -97,7 +94,17 @@ def test_exchange_without_communicator_is_an_error(cuda_lib):
     e.close()
 
 
-def _worker(rank, world, idfile, name, n, q):
+def _worker(rank, world, idfile, name, n, q, allreduce=False):
+    try:
+        _worker_body(rank, world, idfile, name, n, q, allreduce)
+    except BaseException as ex:              # a dead worker must not leave the parent waiting on the queue
+        import traceback
+
+        q.put((rank, "error: " + "".join(traceback.format_exception(type(ex), ex, ex.__traceback__))[-3000:], None))
+        raise
+
+
+def _worker_body(rank, world, idfile, name, n, q, allreduce=False):
     sys.path.insert(0, ROOT)
     sys.path.insert(0, os.path.join(ROOT, "tests"))
     from cases import make
@@ -117,16 +124,27 @@ def _worker(rank, world, idfile, name, n, q):
         time.sleep(0.05)
     with open(idfile, "rb") as f:
         e.comm_init(f.read())
+    if allreduce:
+        e.set_option("exchange_allreduce", 1)
     e.lucy_transport([n] * m.nStars)
     out = [e.fetch(iG, want=_want(m)) for iG in range(1, m.nGrids + 1)]
+    sums = [e.checksum(iG, w) for iG in range(1, m.nGrids + 1) for w in (0, 1)]
+    # the same packets by this rank alone (option solo) on the same context: what bench.py's
+    # nrank_parity does at the full size
+    e.set_option("solo", 1)
+    e.lucy_transport([n] * m.nStars)
+    solo = [e.checksum(iG, w) for iG in range(1, m.nGrids + 1) for w in (0, 1)]
+    e.set_option("solo", 0)
+    assert sums == solo, (rank, sums, solo)
     q.put((rank, out, e.last_exchange))
     e.comm_destroy()
     e.close()
 
 
-@UNVERIFIED
-@pytest.mark.parametrize("name", ["multigrid_sym", "cube_clumpy_gasdust", "hii_sym_gas_debug", "viewing_angles"])
-def test_two_ranks_native_exchange_matches_single_gpu(cuda_lib, name):
+@pytest.mark.parametrize("name,allreduce", [("multigrid_sym", False), ("cube_clumpy_gasdust", False), ("hii_sym_gas_debug", False),
+                                            ("viewing_angles", False), ("multigrid_sym", True), ("multigrid_nonsym", False),
+                                            ("plane_slab_gasdust", False)])
+def test_two_ranks_native_exchange_matches_single_gpu(cuda_lib, name, allreduce):
     import torch
     import torch.multiprocessing as mp
 
@@ -140,17 +158,23 @@ def test_two_ranks_native_exchange_matches_single_gpu(cuda_lib, name):
     q = ctx.Queue()
     with tempfile.TemporaryDirectory() as d:
         idfile = os.path.join(d, "nccl_id")
-        procs = [ctx.Process(target=_worker, args=(r, 2, idfile, name, n, q)) for r in range(2)]
+        procs = [ctx.Process(target=_worker, args=(r, 2, idfile, name, n, q, allreduce)) for r in range(2)]
         for p in procs:
             p.start()
         got = {}
-        for _ in range(2):
-            r, out, info = q.get(timeout=600)
-            got[r] = out
-            assert info["bytes"] > 0
-        for p in procs:
-            p.join(timeout=120)
-            assert p.exitcode == 0
+        try:
+            for _ in range(2):
+                r, out, info = q.get(timeout=240)
+                assert not isinstance(out, str), out
+                got[r] = out
+                assert info["bytes"] > 0
+            for p in procs:
+                p.join(timeout=120)
+                assert p.exitcode == 0
+        finally:
+            for p in procs:                  # a rank stuck in a collective behind a dead peer
+                if p.is_alive():
+                    p.kill()
     ref, _, _, _, _ = _run(name, n, native=False)
     for iG in range(m.nGrids):
         for r in (0, 1):
@@ -158,7 +182,39 @@ def test_two_ranks_native_exchange_matches_single_gpu(cuda_lib, name):
                 assert np.array_equal(got[r][iG][k], ref[iG][k]), (iG, r, k)
 
 
-@UNVERIFIED
+def test_solo_option_and_checksum(cuda_lib):
+    """A context created as rank 1 of 2 transports every packet itself under option solo and folds at
+    once; its estimators (and their checksums) equal a plain single-rank run."""
+    from cases import make
+    from mocassin_b200.api import PacketEngine
+
+    m, _ = make("cube_clumpy_gasdust")
+    n = 20001
+    ref = PacketEngine(m, seed=12345)
+    ref.upload_iteration_inputs()
+    ref.lucy_transport([n])
+    want = ref.fetch(1)
+    sums = [ref.checksum(1, 0), ref.checksum(1, 1)]
+    ref.close()
+    e = PacketEngine(m, rank=1, nranks=2, seed=12345)
+    e.upload_iteration_inputs()
+    e.set_option("solo", 1)
+    e.zero_estimators()
+    c = e.energyPacketDriver(1, n)
+    assert c["nPackets"] == n
+    got = e.fetch(1)
+    assert np.array_equal(got["Jste"], want["Jste"]) and np.array_equal(got["escapedPackets"], want["escapedPackets"])
+    assert [e.checksum(1, 0), e.checksum(1, 1)] == sums
+    # a changed element changes the sum; a zero array sums to zero
+    e.zero_estimators()
+    assert e.checksum(1, 0) == 0
+    e.set_option("solo", 0)
+    e.zero_estimators()
+    c = e.energyPacketDriver(1, n)
+    assert c["nPackets"] == n // 2                      # rank 1 of 2 again
+    e.close()
+
+
 def test_exchange_twice_or_transport_after_exchange_is_refused(cuda_lib):
     from cases import make
     from mocassin_b200.api import MocassinError, PacketEngine

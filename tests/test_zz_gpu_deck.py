@@ -8,12 +8,7 @@ import sys
 import numpy as np
 import pytest
 
-# Every test of this file was written after round 1's GPU budget was spent and has never run on a
-# GPU.  Their outcome is recorded (XPASS / XFAIL in the summary) without gating the suite, so that an
-# unverified test cannot stop `pytest -x` in front of nothing and cannot turn a verified suite red;
-# remove the xfail mark once they have passed on a B200.
-UNVERIFIED = pytest.mark.xfail(strict=False, reason="never run on a GPU before round 1 ended (outcome recorded, not gating)")
-pytestmark = [pytest.mark.gpu, UNVERIFIED]
+pytestmark = pytest.mark.gpu
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, os.path.join(ROOT, "tests"))
 GOLD = os.path.join(ROOT, "tests", "golden")
