@@ -336,6 +336,8 @@ def run_b200(args):
         eng.comm_init_from_group()
         if os.environ.get("MCB_EXCHANGE_ALLREDUCE", "0") == "1":
             eng.set_option("exchange_allreduce", 1)
+        if os.environ.get("MCB_EXCHANGE_P2P"):
+            eng.set_option("exchange_p2p", int(os.environ["MCB_EXCHANGE_P2P"]))
 
     def nrank_parity(nCheck=2_000_000):
         """Untimed: the same nCheck packets once sharded over the N ranks (exchange + fold) and once
@@ -417,20 +419,34 @@ def run_b200(args):
     # ---- e2e through the public API with host buffers (rank-local copies inside) -------
     e2e = None
     if not args.no_e2e:
-        t_J, Jh = pinned((nRows, nb)); t_E, Eh = pinned((nRows, nb + 1, 1)); keep += [t_J, t_E]
+        # N = 1: the whole Jste (dense) + escapedPackets (sparse) come back, the whole CDF table goes up.
+        # N > 1: what each rank of the reference needs after the merge -- the Jste rows of its own
+        # round-robin cells (iteration_mod.f90:832), escapedPackets on rank 0 only (:738-740) -- and
+        # 1/N of the CDF table per rank over PCIe, all-gathered over NVLink (option pdf_slabs).
+        sharded = world > 1 and native and os.environ.get("MCB_E2E_SHARDED", "1") == "1"
+        nMine = (g.nCells - (rank + 1)) // world + 1 if sharded else nRows
+        t_J, Jh = pinned((nMine, nb)); keep.append(t_J)
+        Eh = None
+        if not sharded or rank == 0:
+            t_E, Eh = pinned((nRows, nb + 1, 1)); keep.append(t_E)
+            Eh[...] = 0.0
         nE = 2 if args.steps > 2 else args.steps
-        if world > 1:
-            dist.barrier()
-        torch.cuda.synchronize()
-        te = time.perf_counter()
         eng.set_option("async_pdfs", 1)                       # PDF upload overlaps the stellar wave
+        if sharded:
+            eng.set_option("pdf_slabs", 1)
 
         def e2e_step(sparse):
             eng.assemble_opacity(1, bands, den, None, dust)   # H2D: den, Ndust, Tdust + K1
             eng.set_dust_state()
-            eng.set_pdfs()                                    # H2D (async, 5 GB): recPDF, totalLines
+            eng.set_pdfs()                                    # H2D (async): recPDF (this rank's slab when sharded), totalLines
             eng.zero_estimators()
             step()
+            if sharded:
+                eng.fetch_cells(1, out=Jh)                    # D2H: Jste(iCell, :) of this rank's cells, compact
+                if rank != 0:
+                    return 0
+                _, nnz = eng.fetch_escaped_sparse(1, out=Eh, clear_previous=True)
+                return 8 * nnz + 8 if nnz >= 0 else Eh.nbytes
             if not sparse:
                 eng.fetch(1, out={"Jste": Jh, "escapedPackets": Eh})   # D2H, both arrays dense
                 return Eh.nbytes
@@ -440,7 +456,6 @@ def run_b200(args):
             _, nnz = eng.fetch_sparse(1, out={"Jste": Jh, "escapedPackets": Eh}, clear_previous=True)
             return 8 * nnz + 8 if nnz >= 0 else Eh.nbytes
 
-        Eh[...] = 0.0
         e2e_step(True)                                        # untimed: sizes the staging buffers
         torch.cuda.synchronize()
         if world > 1:
@@ -452,22 +467,33 @@ def run_b200(args):
         if world > 1:
             dist.barrier()
         dte = time.perf_counter() - te
-        td = time.perf_counter()
-        e2e_step(False)                                       # the dense fetch of both arrays, for comparison
-        torch.cuda.synchronize()
-        dte_dense = time.perf_counter() - td
-        if world > 1:
-            tmax = torch.tensor([dte], dtype=torch.float64, device="cuda"); dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
-            dte = float(tmax[0])
-        h2d = recPDF.nbytes + tl.nbytes + den.nbytes + dust["Ndust"].nbytes + dust["Tdust"].nbytes + 4 * (g.nCells + 1)
+        dense = None
+        if not sharded:
+            td = time.perf_counter()
+            e2e_step(False)                                   # the dense fetch of both arrays, for comparison
+            torch.cuda.synchronize()
+            dte_dense = time.perf_counter() - td
+            dense = {"value": nGlobal / dte_dense, "d2h_bytes_per_step": int(Jh.nbytes + Eh.nbytes),
+                     "note": "same step with mcb200_fetch_estimators for both arrays (one step)"}
+        small = tl.nbytes + den.nbytes + dust["Ndust"].nbytes + dust["Tdust"].nbytes + 4 * (g.nCells + 1)
+        pdf_bytes = recPDF.nbytes if not sharded else 4 * nRows * min((nb + world - 1) // world, max(nb - rank * ((nb + world - 1) // world), 0))
+        h2d = pdf_bytes + small
         d2h = Jh.nbytes + esc_bytes
+        if world > 1:
+            tmax = torch.tensor([dte, float(h2d), float(d2h)], dtype=torch.float64, device="cuda")
+            dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
+            dte, h2d, d2h = float(tmax[0]), float(tmax[1]), float(tmax[2])     # the busiest rank's bytes
         e2e = {"value": nGlobal * nE / dte, "unit": "packets/s", "h2d_bytes_per_step": int(h2d),
-               "d2h_bytes_per_step": int(d2h), "steps": nE,
-               "path": "assemble_opacity + set_dust_state + set_pdfs (async H2D from pinned host, overlaps wave 0) -> "
-                       "zero_estimators -> energyPacketDriver -> mcb200_fetch_estimators_sparse: Jste dense D2H to "
-                       "pinned host, overlapped with the non-zero escapedPackets entries being written into the host array",
-               "dense_fetch": {"value": nGlobal / dte_dense, "d2h_bytes_per_step": int(Jh.nbytes + Eh.nbytes),
-                               "note": "same step with mcb200_fetch_estimators for both arrays (one step)"}}
+               "d2h_bytes_per_step": int(d2h), "steps": nE, "bytes_are": "per rank (max over ranks)",
+               "path": ("assemble_opacity + set_dust_state + set_pdfs (async H2D from pinned host: each rank uploads its 1/N slab of "
+                        "nu-planes of recPDF, slabs all-gathered over NVLink; overlaps wave 0) -> zero_estimators -> "
+                        "energyPacketDriver -> mcb200_exchange + mcb200_reduce -> mcb200_fetch_estimators_cells: Jste rows of this "
+                        "rank's round-robin cells (iteration_mod.f90:832), compact, D2H to pinned host; rank 0 alone fetches "
+                        "escapedPackets (sparse)") if sharded else
+                       ("assemble_opacity + set_dust_state + set_pdfs (async H2D from pinned host, overlaps wave 0) -> "
+                        "zero_estimators -> energyPacketDriver -> mcb200_fetch_estimators_sparse: Jste dense D2H to "
+                        "pinned host, overlapped with the non-zero escapedPackets entries being written into the host array"),
+               "dense_fetch": dense}
 
     if rank != 0:
         if world > 1:
@@ -499,10 +525,11 @@ def run_b200(args):
         "kernel_ms_per_step": kms_max / args.steps, "wall_ms_per_step": 1e3 * wall_max / args.steps,
         "exchange_planes": getattr(eng, "last_exchange_planes", None),
         "escaped_exchange": getattr(eng, "last_escaped_exchange", None),
-        "exchange": ({"path": "native: mcb200_exchange (NCCL reduce-scatter JsteQ + sparse all-gather escapedQ) -> "
-                              "mcb200_reduce (fold own share, all-gather float32 Jste)" if native else
+        "exchange": ({"path": "native: mcb200_exchange (flags, sparse all-gather of escapedQ) -> mcb200_reduce (J merge: "
+                              + str((getattr(eng, "last_exchange", None) or {}).get("path")) + ")" if native else
                               "torch.distributed all-reduce of the tally buffers -> mcb200_reduce",
-                      "nccl_bytes_per_rank_per_step": (getattr(eng, "last_exchange", None) or {}).get("bytes"),
+                      "bytes_per_rank_per_step": (getattr(eng, "last_exchange", None) or {}).get("bytes"),
+                      "detail": getattr(eng, "last_exchange", None),
                       "ms_per_step": (tms_max - kms_max) / args.steps} if world > 1 else None),
     }
     if parity:

@@ -163,6 +163,18 @@ module mcb200_mod
        integer(c_int) function mcb200_len_unit(ctx, iG, lenUnit) bind(C, name="mcb200_len_unit")
          import; type(c_ptr), value :: ctx; integer(c_int32_t), value :: iG; real(c_double), intent(out) :: lenUnit
        end function
+       ! Jste(iCell,:) of the cells one rank owns (iCell = firstCell, firstCell+cellStride, ...), compact
+       integer(c_int) function mcb200_fetch_estimators_cells(ctx, iG, firstCell, cellStride, Jste, Jdif, nCellsOut) &
+            & bind(C, name="mcb200_fetch_estimators_cells")
+         import; type(c_ptr), value :: ctx, Jste, Jdif; integer(c_int32_t), value :: iG, firstCell, cellStride
+         integer(c_int64_t), intent(out) :: nCellsOut
+       end function
+       ! how the last mcb200_exchange merged the J tallies (1 all-reduce, 2 reduce-scatter/all-gather, 3 peer-memory kernel)
+       integer(c_int) function mcb200_exchange_path(ctx, path, why, whyLen, phaseMs) bind(C, name="mcb200_exchange_path")
+         import; type(c_ptr), value :: ctx; integer(c_int32_t), intent(out) :: path
+         character(kind=c_char), dimension(*), intent(out) :: why; integer(c_int64_t), value :: whyLen
+         type(c_ptr), value :: phaseMs       ! c_loc of 4 doubles, or c_null_ptr
+       end function
        ! 64-bit position-sensitive checksum of a device-resident estimator (0 Jste, 1 escapedPackets, 2 Jdif, 3 linePackets)
        integer(c_int) function mcb200_checksum(ctx, iG, which, checksum) bind(C, name="mcb200_checksum")
          import; type(c_ptr), value :: ctx; integer(c_int32_t), value :: iG, which; integer(c_int64_t), intent(out) :: checksum

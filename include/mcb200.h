@@ -313,6 +313,19 @@ int mcb200_comm_init(mcb200_ctx *ctx, const void *id128);
 int mcb200_comm_destroy(mcb200_ctx *ctx);
 int mcb200_exchange(mcb200_ctx *ctx);
 int mcb200_exchange_info(mcb200_ctx *ctx, int64_t *bytesSent, int32_t *sparseGrids, int32_t *ncclVersion);
+/* How the last mcb200_exchange merged the J tallies: 1 = NCCL all-reduce (option
+ * "exchange_allreduce"), 2 = NCCL reduce-scatter + fold of the share + all-gather of the float32
+ * estimator, 3 = the fused peer-memory kernel: every rank's JsteQ and Jste are mapped into every
+ * process (cudaIpc over NVLink / NVSwitch) and ONE kernel per rank reads its share of the range
+ * from all ranks' JsteQ, adds the integers, folds once and stores the float32 result into all
+ * ranks' Jste -- reduce-scatter, fold and all-gather in a single pass over the links, 12 bytes per
+ * element, no intermediate buffers.  Path 3 is taken when the buffers can be mapped (same node,
+ * peer access; not in debug mode), else 2; `why` receives the reason peer memory was not used.
+ * Option "exchange_p2p": -1 auto (default), 0 never, 1 required (MCB200_ECOMM if unavailable).
+ * All three leave bit-identical estimators.  phaseMs (nullable, 4 doubles): host time of the last
+ * mcb200_exchange, host time of the last mcb200_reduce, device time of the J merge inside that
+ * fold (the peer-memory kernel + barrier + clears, or fold + all-gather), reserved. */
+int mcb200_exchange_path(mcb200_ctx *ctx, int32_t *path, char *why, int64_t whyLen, double *phaseMs);
 /* Which NCCL the library binds (needs no context and no device): ncclGetVersion and the file the
  * symbols came from.  A process that also hosts another NCCL user (PyTorch) must bind the SAME
  * copy: the dynamic loader keeps one object per SONAME, so whichever libnccl.so.2 is opened first
@@ -372,6 +385,17 @@ int mcb200_photo_integrals(mcb200_ctx *ctx, int32_t iG, int32_t nBands, const in
 int mcb200_fetch_estimators(mcb200_ctx *ctx, int32_t iG, float *Jste, float *escapedPackets,
                             float *Jdif, float *linePackets);
 
+/* The estimator rows of the cells ONE rank works on.  After the merge the reference's ranks share
+ * the cells round robin -- rank r updates the cells with mod(iCell-(r+1), numtasks) == 0
+ * (iteration_mod.f90:832) -- so a rank only ever reads Jste(iCell, :) of its own cells.
+ * Jste (and Jdif in debug mode; either may be NULL) receive the compact array (1:nMine, 1:nbins),
+ * cell index fastest, row j = cell firstCell + (j-1)*cellStride (1-based; pass taskid+1 and
+ * numtasks): nMine*nbins*4 bytes cross PCIe instead of (nCells+1)*nbins*4.  The host indexes it with
+ * (iCell - firstCell)/cellStride + 1 where it indexed grid%Jste(iCell, :).
+ * nCellsOut (nullable) = nMine. */
+int mcb200_fetch_estimators_cells(mcb200_ctx *ctx, int32_t iG, int32_t firstCell, int32_t cellStride, float *Jste,
+                                  float *Jdif, int64_t *nCellsOut);
+
 /* 64-bit checksum of a device-resident float32 estimator of grid iG, as mcb200_fetch_estimators
  * would return it (which: 0 Jste, 1 escapedPackets, 2 Jdif, 3 linePackets): the sum over the
  * elements of bits(i) * (2*i + 1) mod 2^64.  Lets every rank of a multi-GPU run show that it holds
@@ -417,6 +441,14 @@ int mcb200_fetch_fates(mcb200_ctx *ctx, int32_t *fates, int64_t nPackets);
 /* Tuning and diagnostic options; none of them changes a result bit (tallies are order-independent
  * integers, every packet owns its random stream).
  *   "seed"          Philox seed (also the `seed` of mcb200_create)
+ *   "epoch"         advances the Philox key: key = seed + epoch * 0x9E3779B97F4A7C15 (mod 2^64).  The reference draws
+ *                   fresh random numbers in every Lucy iteration; a host reproduces that by setting epoch to its
+ *                   iteration counter (nIterateMC) before the packet loop -- otherwise every iteration replays the
+ *                   histories of the first and the Monte Carlo noise freezes.  Within one epoch every source has its
+ *                   own streams: a star's packets are keyed (packet index, iStar); the extra diffuse source of
+ *                   mcb200_transport_diffuse by (packet index, grid, emitting cell), so the per-cell calls of
+ *                   iteration_mod.f90:498-550 draw independent histories; resonance-line packets by (cell, index).
+ *                   (This option and "seed" DO change results; the options below do not.)
  *   "trace"         1: keep per-packet fate records (mcb200_fetch_fates), print phase timings
  *   "wavefront"     -1 auto (wave-front pipeline for >= 2^17 packets per call), 0 persistent kernel, 1 wave front
  *   "order"         persistent kernel: -1 auto / 0 / 1 process packets in order of their first frequency bin
@@ -434,6 +466,9 @@ int mcb200_fetch_fates(mcb200_ctx *ctx, int32_t *fates, int64_t nPackets);
  *                   exchange of one half with the transport of the other (PacketEngine.energyPacketDriverOverlapped)
  *   "exchange_dense" 1: mcb200_exchange all-reduces the escape counts densely whatever the list lengths
  *   "exchange_allreduce" 1: mcb200_exchange all-reduces the J planes and every rank folds all of them
+ *   "pdf_slabs"     1: mcb200_set_pdfs uploads only this rank's 1/nranks slab of nu-planes of the (identical on
+ *                   every rank) table over PCIe and all-gathers the slabs over NVLink (needs mcb200_comm_init)
+ *   "exchange_p2p"  -1 auto / 0 / 1: fused peer-memory merge of the J tallies (mcb200_exchange_path)
  *   "solo"          1: this rank acts as rank 0 of 1 until cleared (N-rank vs 1-rank check on one context)
  *   "defer_fold"    1: a single rank leaves its tallies pending after mcb200_transport, as a multi-rank run
  *                   does, until mcb200_reduce (lets one GPU walk the mcb200_exchange path) */

@@ -71,7 +71,9 @@ _SIGS = {
     "mcb200_comm_destroy": [C.c_void_p],
     "mcb200_exchange": [C.c_void_p],
     "mcb200_exchange_info": [C.c_void_p, c_int64_p, c_int32_p, c_int32_p],
+    "mcb200_exchange_path": [C.c_void_p, c_int32_p, C.c_char_p, C.c_int64, C.POINTER(C.c_double)],
     "mcb200_fetch_estimators": [C.c_void_p, C.c_int32, c_float_p, c_float_p, c_float_p, c_float_p],
+    "mcb200_fetch_estimators_cells": [C.c_void_p, C.c_int32, C.c_int32, C.c_int32, c_float_p, c_float_p, c_int64_p],
     "mcb200_checksum": [C.c_void_p, C.c_int32, C.c_int32, C.POINTER(C.c_uint64)],
     "mcb200_fetch_escaped_sparse": [C.c_void_p, C.c_int32, c_float_p, C.c_int32, c_int64_p],
     "mcb200_fetch_estimators_sparse": [C.c_void_p, C.c_int32, c_float_p, c_float_p, C.c_int32, c_int64_p],

@@ -522,7 +522,15 @@ class PacketEngine:
     def exchange_info(self) -> dict:
         b, sp, v = C.c_int64(), C.c_int32(), C.c_int32()
         self._check(self.lib.mcb200_exchange_info(self.h, C.byref(b), C.byref(sp), C.byref(v)))
-        return dict(bytes=b.value, sparse_grids=sp.value, nccl_version=v.value)
+        path = C.c_int32()
+        why = C.create_string_buffer(256)
+        ph = (C.c_double * 4)()
+        self._check(self.lib.mcb200_exchange_path(self.h, C.byref(path), why, 256, ph))
+        return dict(bytes=b.value, sparse_grids=sp.value, nccl_version=v.value,
+                    exchange_ms=ph[0], reduce_ms=ph[1], j_merge_device_ms=ph[2],
+                    path={0: "none", 1: "nccl all-reduce", 2: "nccl reduce-scatter + all-gather",
+                          3: "fused peer-memory kernel (NVLink)"}.get(path.value, str(path.value)),
+                    p2p_unavailable=why.value.decode() or None)
 
     def reduce(self, group=None):
         """Sum the pending integer tallies over ranks and fold them into the float32
@@ -641,6 +649,23 @@ class PacketEngine:
         self._check(self.lib.mcb200_fetch_tallies(self.h, iG, _lp(JQ), _lp(EQ), _lp(DQ), _lp(LQ)))
         return dict(JsteQ=JQ, escapedQ=EQ, JdifQ=DQ, linePacketsQ=LQ)
 
+    def fetch_cells(self, iG: int = 1, first: Optional[int] = None, stride: Optional[int] = None,
+                    out: Optional[np.ndarray] = None) -> np.ndarray:
+        """Jste rows of the cells this rank owns under the reference's round-robin rule
+        (iteration_mod.f90:832: cells rank+1, rank+1+nranks, ...), compact (nMine, nbins), F-order:
+        mcb200_fetch_estimators_cells.  `out` may be a preallocated (pinned) array."""
+        g = self.model.grids[iG - 1]
+        first = self.rank + 1 if first is None else int(first)
+        stride = self.nranks if stride is None else int(stride)
+        nMine = 0 if first > g.nCells else (g.nCells - first) // stride + 1
+        if out is None:
+            out = np.zeros((nMine, self.model.nbins), dtype=F32, order="F")
+        assert out.shape == (nMine, self.model.nbins) and out.flags.f_contiguous
+        n = C.c_int64()
+        self._check(self.lib.mcb200_fetch_estimators_cells(self.h, iG, first, stride, _fp(out), None, C.byref(n)))
+        assert n.value == nMine
+        return out
+
     def checksum(self, iG: int = 1, which: int = 0) -> int:
         """mcb200_checksum: position-sensitive 64-bit sum of the device-resident estimator
         (0 Jste, 1 escapedPackets, 2 Jdif, 3 linePackets)."""
@@ -675,9 +700,13 @@ class PacketEngine:
         return list(enumerate(self.model.grids, start=1))
 
     # -- the packet loop of iterateMC (iteration_mod.f90:458-726) -----------------------
-    def lucy_transport(self, nPhotons, group=None) -> list[dict]:
+    def lucy_transport(self, nPhotons, group=None, iteration: Optional[int] = None) -> list[dict]:
         """zero estimators; for every star energyPacketDriver; reduce.  `nPhotons[i]` is
-        the global packet count of star i+1."""
+        the global packet count of star i+1.  `iteration` (the host's nIterateMC) becomes the
+        Philox epoch, so that every Lucy iteration draws fresh histories as the reference's
+        wall-clock-seeded generator does (option "epoch", include/mcb200.h)."""
+        if iteration is not None:
+            self.set_option("epoch", int(iteration))
         self.zero_estimators()
         out = []
         for iStar in range(1, self.model.nStars + 1):
@@ -687,6 +716,12 @@ class PacketEngine:
         if (self.nranks == 1 and not self.native_comm) or self.solo:
             self.reduce()
         return out
+
+
+def call_seed(seed: int, epoch: int = 0) -> int:
+    """The Philox key of a transport call under option "epoch" (capi.cu run_transport): what a
+    checker passes as `seed` to reproduce iteration `epoch` of a context created with `seed`."""
+    return (int(seed) + int(epoch) * 0x9E3779B97F4A7C15) & 0xFFFFFFFFFFFFFFFF
 
 
 def _touched_ranges(flag) -> list:

@@ -28,6 +28,13 @@ cudaError_t launch_transpose_pdf(const float *src, float *dst, int nRows, int nb
 cudaError_t launch_check_monotone(const float *pdfT, int nRows, int nb, int *bad, cudaStream_t s);
 cudaError_t launch_fold_j(unsigned long long *Q, float *J, const float *dV, int nRows, size_t first, size_t total,
                           double lenUnit, float deltaE, int blocks, cudaStream_t s);
+struct P2PPeers {
+    unsigned long long *Q[16];
+    float *J[16];
+    int nranks, rank;
+};
+cudaError_t launch_p2p_reduce_fold(const P2PPeers &P, const float *dV, int nRows, size_t first, size_t total,
+                                   double lenUnit, float deltaE, int blocks, cudaStream_t s);
 cudaError_t launch_fold_count(unsigned int *Q, float *E, size_t total, float deltaE, int blocks,
                               cudaStream_t s);
 cudaError_t launch_merge_sets(unsigned long long *J0, unsigned long long *J1, size_t nJ, unsigned int *E0,
@@ -65,6 +72,7 @@ cudaError_t launch_esc_scatter(unsigned int *Q, size_t total, const unsigned lon
 cudaError_t launch_sed_sum(const unsigned int *escQ, size_t nR, int firstPlane, int nPlanes,
                            unsigned long long *sedQ, cudaStream_t s);
 cudaError_t launch_contcube(const float *esc, size_t nR, int nb, int nAngles, float *out, cudaStream_t s);
+cudaError_t launch_gather_cells(const float *table, size_t nR, int nb, int first, int stride, int nMine, float *out, cudaStream_t s);
 cudaError_t launch_gather_rows(const float *table, size_t nR, int nb, const int *cells, int nWanted, float *out, cudaStream_t s);
 cudaError_t launch_dust_mask(const float *Tdust, const int *compOfCell, const int *dustComPoint, const int *nSpeciesPart,
                              const float *Tsub, int nRows, int nSpeciesTot, int nSizes, int s0, int s1, unsigned char *on,
@@ -136,6 +144,10 @@ struct GridState {
     // all-gathered in place (capi.cu: fold_pending)
     struct JRange { size_t off, len, count; };
     std::vector<JRange> jShards;
+    bool jShardsP2P = false;              // the shares are still to be summed: by the fused peer-memory kernel in the fold
+    // peer mappings of every rank's JsteQ / Jste (cudaIpc), for the fused reduce + fold over NVLink
+    std::vector<void *> peerQ, peerJ;     // [rank]; own entry = local pointer
+    void *peerBaseQ = nullptr, *peerBaseJ = nullptr;   // local pointers the mappings were made for
     // dust closure (mcb200_dust_update / mcb200_dust_pdf): device copy of the dust state
     DevBuf<float> Tdust;
     DevBuf<int> dustAbun, lgConverged;
@@ -227,6 +239,16 @@ struct mcb200_ctx {
     bool exchangeDense = false;           // option exchange_dense: mcb200_exchange never takes the sparse path
     bool exchangeAllReduce = false;       // option exchange_allreduce: all-reduce the J planes (round-1 path) instead of
                                           // reduce-scatter -> fold the share -> all-gather float32
+    int p2pMode = -1;                     // option exchange_p2p: -1 auto (peer memory when it can be mapped), 0 NCCL only, 1 required
+    int p2pState = 0;                     // 0 not tried, 1 usable, -1 unavailable (lastP2PWhy)
+    std::string lastP2PWhy;
+    int lastExchangePath = 0;             // 0 none, 1 all-reduce, 2 reduce-scatter/all-gather (NCCL), 3 fused peer-memory kernel
+    double lastPhaseMs[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    DevBuf<unsigned char> ipcBuf;
+    DevBuf<int> barrierWord;
+    bool pdfSlabs = false;                // option pdf_slabs: 1/nranks of the PDF table per rank over PCIe, all-gather over NVLink
+    int64_t lastPdfH2D = 0;               // bytes the last mcb200_set_pdfs moved host -> device for the CDF table
+    int64_t epoch = 0;                    // option epoch: advances the Philox key (set to the Lucy iteration number)
     bool solo = false;                    // option solo
     int soloRank = 0, soloNranks = 1;
     bool keepSharded = false;             // option keep_sharded: skip the all-gather (Jste stays valid only on the owner's share)
@@ -509,6 +531,83 @@ int fold_planes(mcb200_ctx *ctx, GridState &g, int nu0, int nu1, int *launches, 
     return MCB200_OK;
 }
 
+// stream-ordered barrier over the ranks: a one-word all-reduce completes on a rank only after every
+// rank's stream has reached it
+int comm_barrier(mcb200_ctx *ctx)
+{
+    CU(ctx->barrierWord.alloc(1));
+    NC(nccl_api().AllReduce(ctx->barrierWord.p, ctx->barrierWord.p, 1, kNcclInt32, kNcclMax, ctx->comm, ctx->stream));
+    return MCB200_OK;
+}
+
+void p2p_close(GridState &g, int rank)
+{
+    for (size_t r = 0; r < g.peerQ.size(); ++r) {
+        if ((int)r == rank) continue;
+        if (g.peerQ[r]) cudaIpcCloseMemHandle(g.peerQ[r]);
+        if (g.peerJ[r]) cudaIpcCloseMemHandle(g.peerJ[r]);
+    }
+    g.peerQ.clear(); g.peerJ.clear();
+    g.peerBaseQ = g.peerBaseJ = nullptr;
+}
+
+// Map every rank's JsteQ and Jste of this grid into this process (cudaIpc handles, all-gathered
+// through the communicator).  Collective: every rank calls it at the same point.  Leaves
+// ctx->p2pState = 1 when every rank mapped every peer, -1 otherwise (the exchange then stays on NCCL).
+int p2p_setup(mcb200_ctx *ctx, GridState &g)
+{
+    NcclApi &N = nccl_api();
+    const int world = ctx->nranks, rank = ctx->rank;
+    cudaStream_t s = ctx->stream;
+    // do the mappings of every rank still match the buffers?  (max over ranks of "mine changed")
+    int stale = (g.peerQ.empty() || g.peerBaseQ != (void *)g.JsteQ.p || g.peerBaseJ != (void *)g.Jste.p) ? 1 : 0;
+    CU(ctx->barrierWord.alloc(1));
+    CU(cudaMemcpyAsync(ctx->barrierWord.p, &stale, sizeof(int), cudaMemcpyHostToDevice, s));
+    NC(N.AllReduce(ctx->barrierWord.p, ctx->barrierWord.p, 1, kNcclInt32, kNcclMax, ctx->comm, s));
+    CU(cudaMemcpyAsync(&stale, ctx->barrierWord.p, sizeof(int), cudaMemcpyDeviceToHost, s));
+    CU(cudaStreamSynchronize(s));
+    if (!stale) return MCB200_OK;
+    p2p_close(g, rank);
+    struct Pair { cudaIpcMemHandle_t q, j; int ok; int pad[3]; };
+    static_assert(sizeof(Pair) % 8 == 0, "handle record must be a multiple of 8 bytes");
+    std::vector<Pair> all((size_t)world);
+    Pair mine{};
+    mine.ok = 1;
+    if (world > 16) { mine.ok = 0; ctx->lastP2PWhy = "more than 16 ranks"; }
+    if (mine.ok && cudaIpcGetMemHandle(&mine.q, g.JsteQ.p) != cudaSuccess) { mine.ok = 0; ctx->lastP2PWhy = "cudaIpcGetMemHandle(JsteQ) failed"; cudaGetLastError(); }
+    if (mine.ok && cudaIpcGetMemHandle(&mine.j, g.Jste.p) != cudaSuccess) { mine.ok = 0; ctx->lastP2PWhy = "cudaIpcGetMemHandle(Jste) failed"; cudaGetLastError(); }
+    CU(ctx->ipcBuf.alloc(sizeof(Pair) * (size_t)(world + 1)));
+    CU(cudaMemcpyAsync(ctx->ipcBuf.p + sizeof(Pair) * (size_t)world, &mine, sizeof(Pair), cudaMemcpyHostToDevice, s));
+    NC(N.AllGather(ctx->ipcBuf.p + sizeof(Pair) * (size_t)world, ctx->ipcBuf.p, sizeof(Pair) / 8, kNcclUint64, ctx->comm, s));
+    CU(cudaMemcpyAsync(all.data(), ctx->ipcBuf.p, sizeof(Pair) * (size_t)world, cudaMemcpyDeviceToHost, s));
+    CU(cudaStreamSynchronize(s));
+    int ok = 1;
+    for (auto &h : all) ok = ok && h.ok;
+    g.peerQ.assign((size_t)world, nullptr); g.peerJ.assign((size_t)world, nullptr);
+    for (int r = 0; r < world && ok; ++r) {
+        if (r == rank) { g.peerQ[r] = g.JsteQ.p; g.peerJ[r] = g.Jste.p; continue; }
+        if (cudaIpcOpenMemHandle(&g.peerQ[r], all[r].q, cudaIpcMemLazyEnablePeerAccess) != cudaSuccess ||
+            cudaIpcOpenMemHandle(&g.peerJ[r], all[r].j, cudaIpcMemLazyEnablePeerAccess) != cudaSuccess) {
+            ok = 0;
+            ctx->lastP2PWhy = std::string("cudaIpcOpenMemHandle failed: ") + cudaGetErrorString(cudaGetLastError());
+        }
+    }
+    // every rank must take the same path
+    CU(cudaMemcpyAsync(ctx->barrierWord.p, &ok, sizeof(int), cudaMemcpyHostToDevice, s));
+    NC(N.AllReduce(ctx->barrierWord.p, ctx->barrierWord.p, 1, kNcclInt32, 3 /* ncclMin */, ctx->comm, s));
+    CU(cudaMemcpyAsync(&ok, ctx->barrierWord.p, sizeof(int), cudaMemcpyDeviceToHost, s));
+    CU(cudaStreamSynchronize(s));
+    if (!ok) {
+        p2p_close(g, rank);
+        if (ctx->lastP2PWhy.empty()) ctx->lastP2PWhy = "a peer could not map the buffers";
+        ctx->p2pState = -1;
+        return MCB200_OK;
+    }
+    g.peerBaseQ = g.JsteQ.p; g.peerBaseJ = g.Jste.p;
+    ctx->p2pState = 1;
+    return MCB200_OK;
+}
+
 // J planes after the reduce-scatter of mcb200_exchange (comm_exchange): this rank holds the global
 // integer sums of its share of every exchanged range, the tail of each range on every rank.  Fold
 // the share (1/nranks of the work), clear the other ranks' shares (partial sums that have been
@@ -522,6 +621,32 @@ int fold_shards(mcb200_ctx *ctx, GridState &g, int *launches)
     const size_t nR = (size_t)g.nCells + 1;
     const double lenUnit = std::ldexp(1.0, g.lenExp);
     cudaStream_t s = ctx->stream;
+    if (g.jShardsP2P) {
+        // fused peer-memory path: every rank's transport kernels are behind the collectives of
+        // mcb200_exchange on its stream, so the partial sums are complete everywhere
+        P2PPeers P{};
+        P.nranks = world; P.rank = rank;
+        for (int r = 0; r < world; ++r) { P.Q[r] = (unsigned long long *)g.peerQ[r]; P.J[r] = (float *)g.peerJ[r]; }
+        for (auto &r : g.jShards) {
+            const size_t mine = r.off + (size_t)rank * r.count, tail = r.off + (size_t)world * r.count;
+            CU(launch_p2p_reduce_fold(P, g.dV.p, (int)nR, mine, r.count, lenUnit, ctx->pendingDeltaE, ctx->numSMs * 16, s));
+            CU(launch_fold_j(g.JsteQ.p + tail, g.Jste.p + tail, g.dV.p, (int)nR, tail, r.off + r.len - tail, lenUnit, ctx->pendingDeltaE, blocks, s));
+            if (launches) *launches += 2;
+            ctx->lastExchangeBytes += (int64_t)r.count * (int64_t)(world - 1) * 12;
+        }
+        // nobody may clear (or overwrite, in the next transport call) partial sums a peer is still
+        // reading, and nobody may read Jste before every owner has stored its share
+        int rc = comm_barrier(ctx);
+        if (rc) return rc;
+        for (auto &r : g.jShards) {
+            const size_t mine = r.off + (size_t)rank * r.count, tail = r.off + (size_t)world * r.count;
+            if (mine > r.off) CU(cudaMemsetAsync(g.JsteQ.p + r.off, 0, (mine - r.off) * 8, s));
+            if (tail > mine + r.count) CU(cudaMemsetAsync(g.JsteQ.p + mine + r.count, 0, (tail - mine - r.count) * 8, s));
+        }
+        g.jShards.clear();
+        g.jShardsP2P = false;
+        return MCB200_OK;
+    }
     const int nSets = ctx->cfg.lgDebug && g.JdifQ.p ? 2 : 1;
     for (int set = 0; set < nSets; ++set) {
         unsigned long long *Q = set ? g.JdifQ.p : g.JsteQ.p;
@@ -598,8 +723,14 @@ int fold_pending(mcb200_ctx *ctx)
             if (rc) return rc;
         }
         if (sharded) {
+            CU(cudaEventRecord(ctx->ev0, ctx->stream));
             int rc = fold_shards(ctx, g, &launches);
             if (rc) return rc;
+            CU(cudaEventRecord(ctx->ev1, ctx->stream));
+            CU(cudaEventSynchronize(ctx->ev1));
+            float ms = 0.f;
+            CU(cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev1));
+            ctx->lastPhaseMs[2] = ms;
         }
         g.folded.clear();
         if (ctx->cfg.lgDebug && g.lineQ.n) {
@@ -882,7 +1013,18 @@ int run_transport(mcb200_ctx *ctx, int iStar, int difGrid, const int32_t *cellLo
             return fail(ctx, MCB200_EINVAL, "diffuse source cell out of range");
         a.difGrid = difGrid; a.difX = cellLoc[0]; a.difY = cellLoc[1]; a.difZ = cellLoc[2];
     }
-    a.firstId = first; a.n = mine; a.seed = ctx->seed;
+    // Philox keying.  The key is the context seed advanced by the epoch (option "epoch": the host sets it
+    // to the Lucy iteration number, so that no two iterations replay the same histories); a star's
+    // packets are (global packet index, iStar); the extra diffuse source of cell (gpLoc, cellLoc) gets
+    // streams of its own: counter word 3 = 0x80000000 + the cell's linear index, grid in the packet id.
+    a.firstId = first; a.n = mine;
+    a.seed = ctx->seed + (unsigned long long)ctx->epoch * 0x9E3779B97F4A7C15ull;
+    a.rngStream = (unsigned int)iStar; a.pidBase = 0ull;
+    if (iStar == 0) {
+        const GridState &dg = ctx->grids[difGrid - 1];
+        a.rngStream = 0x80000000u + (unsigned int)((cellLoc[0] - 1) + dg.nx * ((cellLoc[1] - 1) + dg.ny * (cellLoc[2] - 1)));
+        a.pidBase = (unsigned long long)difGrid << 48;
+    }
     a.resCells = nullptr; a.resPrefix = nullptr; a.nResCells = 0;
     if (resLines) {
         if (!cfg.lgGas || !cfg.lgDust) return fail(ctx, MCB200_ESTATE, "resonance-line transfer needs gas and dust (photon_mod.f90:180,910)");
@@ -1089,6 +1231,31 @@ int comm_exchange_escaped(mcb200_ctx *ctx, GridState &g, const std::vector<std::
     return MCB200_OK;
 }
 
+// Upload of a (0:nCells, nbins) host table every rank holds identically (the reference's ranks do,
+// after their MPI_ALLREDUCE of recPDFTemp, iteration_mod.f90:357-424): with option "pdf_slabs" each
+// rank sends only its 1/nranks slab of nu-planes over PCIe and the slabs are all-gathered over
+// NVLink into the staging buffer (planes padded to a multiple of nranks).  `cs`: stream to work on.
+int upload_table_slabs(mcb200_ctx *ctx, GridState &g, const float *src, cudaStream_t cs)
+{
+    const size_t nR = (size_t)g.nCells + 1;
+    const int nb = ctx->cfg.nbins, world = ctx->nranks, rank = ctx->rank;
+    const bool slabs = ctx->pdfSlabs && world > 1 && ctx->comm && !ctx->solo;
+    if (!slabs) {
+        CU(g.stage.alloc(nR * (size_t)nb));
+        CU(cudaMemcpyAsync(g.stage.p, src, nR * (size_t)nb * sizeof(float), cudaMemcpyHostToDevice, cs));
+        ctx->lastPdfH2D = (int64_t)(nR * (size_t)nb * sizeof(float));
+        return MCB200_OK;
+    }
+    const int per = (nb + world - 1) / world;                 // planes per rank (the last slabs may be short or empty)
+    CU(g.stage.alloc(nR * (size_t)per * (size_t)world));
+    const int p0 = rank * per, p1 = (p0 + per < nb ? p0 + per : nb);
+    size_t mine = p1 > p0 ? (size_t)(p1 - p0) * nR : 0;
+    if (mine) CU(cudaMemcpyAsync(g.stage.p + (size_t)p0 * nR, src + (size_t)p0 * nR, mine * sizeof(float), cudaMemcpyHostToDevice, cs));
+    ctx->lastPdfH2D = (int64_t)(mine * sizeof(float));
+    NC(nccl_api().AllGather(g.stage.p + (size_t)p0 * nR, g.stage.p, (size_t)per * nR, kNcclFloat32, ctx->comm, cs));
+    return MCB200_OK;
+}
+
 int comm_exchange(mcb200_ctx *ctx)
 {
     const int nb = ctx->cfg.nbins, blocks = ctx->numSMs * 8;
@@ -1119,26 +1286,45 @@ int comm_exchange(mcb200_ctx *ctx)
         CU(cudaMemcpyAsync(flag.data(), g.nuTouched.p, sizeof(int) * (nb + 1), cudaMemcpyDeviceToHost, s));
         CU(cudaStreamSynchronize(s));
         auto ranges = touched_ranges(flag);
+        // the escape counts first: their exchange has data-dependent sizes (host round trips), which
+        // must not queue up behind the bulk transfer of the J planes
+        if (!ctx->sedLocal) {
+            rc = comm_exchange_escaped(ctx, g, ranges);
+            if (rc) return rc;
+        }
         g.jShards.clear();
+        g.jShardsP2P = false;
+        const bool allreduce = ctx->exchangeAllReduce || ctx->nranks == 1;
+        bool p2p = false;
+        if (!allreduce && ctx->p2pMode != 0 && !ctx->cfg.lgDebug && ctx->p2pState >= 0) {
+            rc = p2p_setup(ctx, g);
+            if (rc) return rc;
+            p2p = ctx->p2pState == 1;
+        }
+        if (!allreduce && ctx->p2pMode == 1 && !p2p)
+            return fail(ctx, MCB200_ECOMM, "option exchange_p2p=1: peer memory unavailable (%s)",
+                        ctx->cfg.lgDebug ? "debug tallies go through NCCL" : ctx->lastP2PWhy.c_str());
+        ctx->lastExchangePath = allreduce ? 1 : (p2p ? 3 : 2);
         NC(nccl_api().GroupStart());
         for (auto &rg : ranges) {
             int p0 = rg.first < 1 ? 1 : rg.first, p1 = rg.second;
             if (p1 < p0) continue;
             size_t off = (size_t)(p0 - 1) * nR, len = (size_t)(p1 - p0 + 1) * nR;
             const int nSets = ctx->cfg.lgDebug && g.JdifQ.p ? 2 : 1;
-            if (ctx->exchangeAllReduce || ctx->nranks == 1) {
+            if (allreduce) {
                 for (int set = 0; set < nSets; ++set) {
                     rc = comm_allreduce(ctx, (set ? g.JdifQ.p : g.JsteQ.p) + off, len, kNcclUint64, kNcclSum);
                     if (rc) return rc;
                 }
                 continue;
             }
-            // reduce-scatter in place: rank r receives the sum of elements [off + r*count, +count);
-            // the < nranks elements left over at the end of the range are all-reduced
+            // every rank owns the sum of elements [off + r*count, +count) of the range: delivered by a
+            // reduce-scatter in place, or left to the fused peer-memory kernel of the fold; the
+            // < nranks elements left over at the end of the range are all-reduced
             const size_t count = len / (size_t)ctx->nranks, tail = len - count * (size_t)ctx->nranks;
             for (int set = 0; set < nSets; ++set) {
                 unsigned long long *Q = (set ? g.JdifQ.p : g.JsteQ.p) + off;
-                if (count) {
+                if (count && !p2p) {
                     NC(nccl_api().ReduceScatter(Q, Q + (size_t)ctx->rank * count, count, kNcclUint64, kNcclSum, ctx->comm, s));
                     ctx->lastExchangeBytes += (int64_t)(count * (size_t)ctx->nranks) * 8;
                 }
@@ -1148,12 +1334,9 @@ int comm_exchange(mcb200_ctx *ctx)
             g.jShards.push_back({off, len, count});
         }
         NC(nccl_api().GroupEnd());
+        g.jShardsP2P = p2p && !g.jShards.empty();
         if (ctx->cfg.lgDebug && g.lineQ.n) {
             rc = comm_allreduce(ctx, g.lineQ.p, g.lineQ.n, kNcclUint32, kNcclSum);
-            if (rc) return rc;
-        }
-        if (!ctx->sedLocal) {
-            rc = comm_exchange_escaped(ctx, g, ranges);
             if (rc) return rc;
         }
         if (ig == 0 && ctx->cfg.lgPlaneIonization && ctx->planeDist.n) {
@@ -1203,6 +1386,7 @@ int mcb200_destroy(mcb200_ctx *ctx)
     if (ctx->pdfReady) cudaEventDestroy(ctx->pdfReady);
     if (ctx->copyStream) { cudaStreamSynchronize(ctx->copyStream); cudaStreamDestroy(ctx->copyStream); }
     if (ctx->sparseHost) cudaFreeHost(ctx->sparseHost);
+    for (auto &g : ctx->grids) p2p_close(g, ctx->rank);
     if (ctx->comm) { nccl_api().CommDestroy(ctx->comm); ctx->comm = nullptr; }
     ctx->grids.clear();
     cudaStream_t s = ctx->stream;
@@ -1449,9 +1633,8 @@ int mcb200_set_pdfs(mcb200_ctx *ctx, int32_t iG, const float *recPDF, const floa
         CU(cudaStreamSynchronize(ctx->stream));          // earlier users of pdfT are done
         CU(ctx->pdfBad.alloc(c.nGrids));
         if (!ctx->pdfPending) CU(ctx->pdfBad.zero(cs));
-        CU(g->stage.alloc(ts));
         CU(g->pdfT.alloc(ts));
-        CU(cudaMemcpyAsync(g->stage.p, src, ts * sizeof(float), cudaMemcpyHostToDevice, cs));
+        { int rcs = upload_table_slabs(ctx, *g, src, cs); if (rcs) return rcs; }
         CU(launch_transpose_pdf(g->stage.p, g->pdfT.p, nRows, c.nbins, cs));
         CU(launch_check_monotone(g->pdfT.p, nRows, c.nbins, ctx->pdfBad.p + (iG - 1), cs));
         CU(cudaEventRecord(ctx->pdfReady, cs));
@@ -1460,7 +1643,7 @@ int mcb200_set_pdfs(mcb200_ctx *ctx, int32_t iG, const float *recPDF, const floa
         if (re) ctx->gridsDirty = true;
         return MCB200_OK;
     }
-    CU(g->stage.upload(src, ts, ctx->stream));
+    { int rcs = upload_table_slabs(ctx, *g, src, ctx->stream); if (rcs) return rcs; }
     CU(g->pdfT.alloc(ts));
     CU(launch_transpose_pdf(g->stage.p, g->pdfT.p, nRows, c.nbins, ctx->stream));
     CU(ctx->flag.alloc(1)); CU(ctx->flag.zero(ctx->stream));
@@ -1744,7 +1927,10 @@ int mcb200_tally_buffer(mcb200_ctx *ctx, int32_t iG, int32_t which, void **devPt
 int mcb200_reduce(mcb200_ctx *ctx)
 {
     NEED_CTX();
-    return fold_pending(ctx);
+    auto t0 = std::chrono::steady_clock::now();
+    int rc = fold_pending(ctx);
+    ctx->lastPhaseMs[1] = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
+    return rc;
 }
 
 int mcb200_reduce_range(mcb200_ctx *ctx, int32_t iG, int32_t nu0, int32_t nu1)
@@ -1801,9 +1987,35 @@ int mcb200_comm_destroy(mcb200_ctx *ctx)
 {
     NEED_CTX();
     if (!ctx->comm) return MCB200_OK;
+    bool mapped = false;
+    for (auto &g : ctx->grids) mapped = mapped || !g.peerQ.empty();
+    if (mapped) {
+        // nobody unmaps (or, afterwards, frees) a buffer a peer may still be using: every rank is
+        // past its last peer access before the mappings go, and every mapping is gone before any
+        // rank can go on to free its buffers
+        int rc = comm_barrier(ctx);
+        if (rc) return rc;
+        CU(cudaStreamSynchronize(ctx->stream));
+        for (auto &g : ctx->grids) p2p_close(g, ctx->rank);
+        rc = comm_barrier(ctx);
+        if (rc) return rc;
+    }
     CU(cudaStreamSynchronize(ctx->stream));
     NC(nccl_api().CommDestroy(ctx->comm));
     ctx->comm = nullptr;
+    ctx->p2pState = 0;
+    return MCB200_OK;
+}
+
+int mcb200_exchange_path(mcb200_ctx *ctx, int32_t *path, char *why, int64_t whyLen, double *phaseMs)
+{
+    NEED_CTX();
+    if (path) *path = ctx->lastExchangePath;
+    if (phaseMs) for (int i = 0; i < 4; ++i) phaseMs[i] = ctx->lastPhaseMs[i];
+    if (why && whyLen > 0) {
+        std::strncpy(why, ctx->lastP2PWhy.c_str(), (size_t)whyLen - 1);
+        why[whyLen - 1] = 0;
+    }
     return MCB200_OK;
 }
 
@@ -1815,7 +2027,9 @@ int mcb200_exchange(mcb200_ctx *ctx)
     if (!ctx->pending || (ctx->nranks == 1 && !ctx->comm)) return MCB200_OK;
     if (!ctx->comm) return fail(ctx, MCB200_ESTATE, "no communicator: call mcb200_comm_init (or all-reduce the buffers of mcb200_tally_buffer yourself)");
     if (ctx->exchanged) return fail(ctx, MCB200_ESTATE, "pending tallies already exchanged: call mcb200_reduce");
+    auto t0 = std::chrono::steady_clock::now();
     int rc = comm_exchange(ctx);
+    ctx->lastPhaseMs[0] = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
     if (rc == MCB200_OK) ctx->exchanged = true;
     return rc;
 }
@@ -1909,6 +2123,33 @@ int mcb200_fetch_contcube(mcb200_ctx *ctx, int32_t iG, float *contI)
     CU(launch_contcube(g->esc.p, nR, ctx->cfg.nbins, nA, g->contI.p, ctx->stream));
     CU(cudaMemcpyAsync(contI, g->contI.p, nR * (size_t)nA * sizeof(float), cudaMemcpyDeviceToHost, ctx->stream));
     CU(cudaStreamSynchronize(ctx->stream));
+    return MCB200_OK;
+}
+
+int mcb200_fetch_estimators_cells(mcb200_ctx *ctx, int32_t iG, int32_t firstCell, int32_t cellStride, float *Jste,
+                                   float *Jdif, int64_t *nCellsOut)
+{
+    NEED_CTX();
+    GridState *g = grid_of(ctx, iG);
+    if (!g || !g->set) return fail(ctx, MCB200_ESTATE, "grid %d not set", iG);
+    if (ctx->pending) return fail(ctx, MCB200_ESTATE, "tallies pending: call mcb200_reduce first");
+    if (firstCell < 1 || cellStride < 1) return fail(ctx, MCB200_EINVAL, "firstCell >= 1 and cellStride >= 1 required");
+    int rc = ensure_estimators(ctx, *g);
+    if (rc) return rc;
+    const int nb = ctx->cfg.nbins;
+    const size_t nR = (size_t)g->nCells + 1;
+    const int64_t nMine = firstCell > g->nCells ? 0 : ((int64_t)g->nCells - firstCell) / cellStride + 1;
+    if (nCellsOut) *nCellsOut = nMine;
+    if (nMine == 0) return MCB200_OK;
+    if (Jdif && !g->Jdif.p) return fail(ctx, MCB200_ESTATE, "Jdif only exists in debug mode");
+    CU(g->stage.alloc((size_t)nMine * (size_t)nb));
+    for (int which = 0; which < 2; ++which) {
+        float *dst = which ? Jdif : Jste;
+        if (!dst) continue;
+        CU(launch_gather_cells(which ? g->Jdif.p : g->Jste.p, nR, nb, firstCell, cellStride, (int)nMine, g->stage.p, ctx->stream));
+        CU(cudaMemcpyAsync(dst, g->stage.p, (size_t)nMine * (size_t)nb * sizeof(float), cudaMemcpyDeviceToHost, ctx->stream));
+        CU(cudaStreamSynchronize(ctx->stream));
+    }
     return MCB200_OK;
 }
 
@@ -2225,6 +2466,9 @@ int mcb200_set_option(mcb200_ctx *ctx, const char *name, int64_t value)
     }
     if (!strcmp(name, "exchange_dense")) { ctx->exchangeDense = value != 0; return MCB200_OK; }
     if (!strcmp(name, "exchange_allreduce")) { ctx->exchangeAllReduce = value != 0; return MCB200_OK; }
+    if (!strcmp(name, "epoch")) { ctx->epoch = value; return MCB200_OK; }
+    if (!strcmp(name, "pdf_slabs")) { ctx->pdfSlabs = value != 0; return MCB200_OK; }
+    if (!strcmp(name, "exchange_p2p")) { ctx->p2pMode = (int)value; if (ctx->p2pState < 0) ctx->p2pState = 0; return MCB200_OK; }
     if (!strcmp(name, "solo")) {
         // 1: this rank behaves as rank 0 of 1 (transports every packet of a call itself and folds at
         // once) until the option is cleared -- the N-rank answer checked against the 1-rank answer

@@ -82,6 +82,68 @@ __global__ void fold_j_kernel(unsigned long long *__restrict__ Q, float *__restr
     }
 }
 
+// ---------------------------------------------------------------------------------------
+// Multi-GPU merge of the J tallies, fused over NVLink peer memory (replaces MPI_ALLREDUCE of Jste,
+// iteration_mod.f90:627, plus the fold): one kernel that
+//   1. reads this rank's share of the touched range from EVERY rank's JsteQ (peer loads through
+//      NVLink/NVSwitch, 8 B per element and peer) and adds them as integers (exact, order free),
+//   2. folds the sum once (same arithmetic as fold_j_kernel) on top of the local float32 Jste,
+//   3. stores the new Jste element into every rank's Jste (peer stores, 4 B per element and peer),
+//   4. clears this rank's own partial sum.
+// Per element (N-1)/N * 12 B cross the links, against 16 B for an int64 all-reduce, and the fold,
+// the clear of the share and the "all-gather" ride along in the same pass.  The other ranks'
+// shares of the local JsteQ are cleared by the caller once every rank has finished reading.
+// Q[r], J[r] = rank r's arrays (r == rank: local pointers).
+// ---------------------------------------------------------------------------------------
+struct P2PPeers {
+    unsigned long long *Q[16];
+    float *J[16];
+    int nranks, rank;
+};
+
+template <int N>
+__global__ void __launch_bounds__(256) p2p_reduce_fold_kernel(const __grid_constant__ P2PPeers P, const float *__restrict__ dV,
+                                                              int nRows, size_t first, size_t total, double lenUnit, float deltaE)
+{
+    const int nr = N > 0 ? N : P.nranks;
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const size_t stride = (size_t)gridDim.x * blockDim.x;
+    for (; i < total; i += stride) {
+        const size_t e = first + i;
+        unsigned long long q[N > 0 ? N : 16];
+#pragma unroll
+        for (int r = 0; r < (N > 0 ? N : 16); ++r)
+            if (r < nr) q[r] = __ldcv(&P.Q[r][e]);          // volatile-class load: never served from a stale line
+        unsigned long long sum = 0;
+#pragma unroll
+        for (int r = 0; r < (N > 0 ? N : 16); ++r)
+            if (r < nr) sum += q[r];
+        if (sum != 0ull) {
+            int cell = (int)(e % (size_t)nRows);
+            float len = (float)((double)(long long)sum * lenUnit);
+            float v = P.J[P.rank][e] + len * deltaE / dV[cell];
+#pragma unroll
+            for (int r = 0; r < (N > 0 ? N : 16); ++r)
+                if (r < nr) P.J[r][e] = v;
+            P.Q[P.rank][e] = 0ull;
+        }
+    }
+    __threadfence_system();              // peer stores performed before the kernel counts as complete
+}
+
+cudaError_t launch_p2p_reduce_fold(const P2PPeers &P, const float *dV, int nRows, size_t first, size_t total,
+                                   double lenUnit, float deltaE, int blocks, cudaStream_t s)
+{
+    if (total == 0) return cudaSuccess;
+    switch (P.nranks) {
+    case 2: p2p_reduce_fold_kernel<2><<<blocks, 256, 0, s>>>(P, dV, nRows, first, total, lenUnit, deltaE); break;
+    case 4: p2p_reduce_fold_kernel<4><<<blocks, 256, 0, s>>>(P, dV, nRows, first, total, lenUnit, deltaE); break;
+    case 8: p2p_reduce_fold_kernel<8><<<blocks, 256, 0, s>>>(P, dV, nRows, first, total, lenUnit, deltaE); break;
+    default: p2p_reduce_fold_kernel<0><<<blocks, 256, 0, s>>>(P, dV, nRows, first, total, lenUnit, deltaE); break;
+    }
+    return cudaGetLastError();
+}
+
 __global__ void fold_count_kernel(unsigned int *__restrict__ Q, float *__restrict__ E,
                                   size_t total, float deltaE)
 {
@@ -395,6 +457,25 @@ cudaError_t launch_opacity(const OpacityArgs &A, cudaStream_t s)
     if (smem < 4) smem = 4;
     cudaFuncSetAttribute(opacity_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     opacity_kernel<<<blocks, kTile, smem, s>>>(A);
+    return cudaGetLastError();
+}
+
+// out(1:nMine, 1:nb) = table(first + (j-1)*stride, :) : the rows of the cells one rank owns under the
+// reference's round-robin rule (iteration_mod.f90:832), compacted so that only they cross PCIe
+__global__ void __launch_bounds__(256) gather_cells_kernel(const float *__restrict__ table, size_t nR, int first, int stride,
+                                                           int nMine, float *__restrict__ out)
+{
+    int j = blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= nMine) return;
+    size_t nu = blockIdx.y;
+    out[(size_t)j + (size_t)nMine * nu] = table[(size_t)first + (size_t)j * (size_t)stride + nR * nu];
+}
+
+cudaError_t launch_gather_cells(const float *table, size_t nR, int nb, int first, int stride, int nMine, float *out, cudaStream_t s)
+{
+    if (nMine <= 0 || nb <= 0) return cudaSuccess;
+    dim3 grid((unsigned)((nMine + 255) / 256), (unsigned)nb);
+    gather_cells_kernel<<<grid, 256, 0, s>>>(table, nR, first, stride, nMine, out);
     return cudaGetLastError();
 }
 

@@ -126,7 +126,7 @@ __global__ void first_nu_kernel(const TransportArgs a, unsigned short *key, unsi
     long long stride = (long long)gridDim.x * blockDim.x;
     for (long long k = (long long)blockIdx.x * blockDim.x + threadIdx.x; k < a.n; k += stride) {
         Rng rng;
-        rng.init(a.seed, (unsigned long long)(a.firstId + k), (uint32_t)a.iStar);
+        rng.init(a.seed, a.pidBase + (unsigned long long)(a.firstId + k), a.rngStream);
         int nuP = sample_cdf(rng, cdf, nb);
         if (nuP > nb) nuP = nb;
         key[k] = (unsigned short)nuP;

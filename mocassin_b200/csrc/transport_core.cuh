@@ -192,7 +192,7 @@ __device__ __forceinline__ int res_cell_of(const TransportArgs &a, long long k)
 }
 __device__ __forceinline__ unsigned long long packet_pid(const TransportArgs &a, long long k)
 {
-    if (!a.resCells) return (unsigned long long)(a.firstId + k);
+    if (!a.resCells) return a.pidBase + (unsigned long long)(a.firstId + k);
     int c = res_cell_of(a, k);
     return (1ull << 40) + a.resCells[c].gid + (unsigned long long)(k - (long long)a.resPrefix[c]);
 }
@@ -332,7 +332,7 @@ struct Transport {
         if (a.resCells) {                // resonance-line packet: "diffuse" from a cell centre
             int c = res_cell_of(a, k);
             const ResCell rc = a.resCells[c];
-            L.rng.init(a.seed, (1ull << 40) + rc.gid + (unsigned long long)(k - (long long)a.resPrefix[c]), (uint32_t)a.iStar);
+            L.rng.init(a.seed, (1ull << 40) + rc.gid + (unsigned long long)(k - (long long)a.resPrefix[c]), a.rngStream);
             L.chType = CH_DIFFUSE;
             L.gP = rc.grid;
             L.rx = rc.px; L.ry = rc.py; L.rz = rc.pz;
@@ -341,7 +341,7 @@ struct Transport {
             L.phase = PH_EMIT;
             return;
         }
-        L.rng.init(a.seed, (unsigned long long)(a.firstId + k), (uint32_t)a.iStar);
+        L.rng.init(a.seed, a.pidBase + (unsigned long long)(a.firstId + k), a.rngStream);
         if (a.iStar >= 1) {
             const int *si = &P.starIdx[4 * (a.iStar - 1)];
             L.chType = CH_STELLAR;

@@ -74,7 +74,10 @@ struct TransportArgs {
     int iStar;                       // >=1 stellar, 0 extra diffuse source
     int difGrid, difX, difY, difZ;   // diffuse source cell (iStar==0)
     long long firstId, n;            // global id of this rank's first packet, packets of this rank
-    unsigned long long seed;
+    unsigned long long seed;         // Philox key of this call: context seed advanced by the epoch (capi.cu: call_seed)
+    unsigned int rngStream;          // Philox counter word 3: iStar for a star; 0x80000000 + linear index of the
+                                     // emitting cell for the extra diffuse source (every cell its own streams)
+    unsigned long long pidBase;      // added to the packet index: difGrid << 48 for the extra diffuse source
     unsigned long long *nextPacket;  // work counter
     const unsigned int *order;       // optional: packet indices sorted by first frequency bin
     int aggSteps;                    // first steps of a flight with warp-aggregated tallies (0 = off)

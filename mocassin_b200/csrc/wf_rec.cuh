@@ -71,7 +71,7 @@ __device__ __forceinline__ void rec_load(const TransportArgs &t, const PacketRec
     uint4 *dst = reinterpret_cast<uint4 *>(&r);
     dst[0] = src[0]; dst[1] = src[1]; dst[2] = src[2]; dst[3] = src[3];
     L.k = (long long)r.k;
-    L.rng.init(t.seed, packet_pid(t, (long long)r.k), (uint32_t)t.iStar, r.rngn);
+    L.rng.init(t.seed, packet_pid(t, (long long)r.k), t.rngStream, r.rngn);
     L.rx = r.rx; L.ry = r.ry; L.rz = r.rz; L.passProb = r.passProb;
     L.dx = r.dx; L.dy = r.dy; L.dz = r.dz;
     // vHat = direction, except for the signs a mirror reflection flipped (continued flights)

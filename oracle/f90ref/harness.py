@@ -204,6 +204,10 @@ class Reference:
         """packets with global ids [first, first+n) of source iStar (0 = extra diffuse source
         in cell cellLoc of grid gpLoc), same keying as oracle_transport"""
         self.seed = seed
+        if iStar == 0:          # the extra diffuse source: streams of its own per emitting cell (mc_oracle.c run_packet)
+            g = self.m.grids[gpLoc - 1]
+            lin = (cellLoc[0] - 1) + g.nx * ((cellLoc[1] - 1) + g.ny * (cellLoc[2] - 1))
+            return self._run(0, n, lambda k: (int(gpLoc) << 48) + first + k, 0x80000000 + int(lin), gpLoc, cellLoc)
         return self._run(iStar, n, lambda k: first + k, iStar, gpLoc, cellLoc)
 
     def transport_reslines(self, iStar: int, seed: int = 12345):

@@ -1133,7 +1133,16 @@ static int run_packet(Ctx *c, int64_t pid, uint64_t seed, int32_t gpLoc, const i
     int32_t gPIn, lastNuP = 0;
     vec3 positionIn;
 
-    rng_init(&c->rng, seed, (uint64_t)pid, (uint32_t)c->iStar);
+    /* Philox keying, same rule as the CUDA library (capi.cu run_transport): a star's packets are
+     * (packet id, iStar); the extra diffuse source of cell (gpLoc, cellLoc) has streams of its own
+     * -- counter word 3 = 0x80000000 + linear index of the emitting cell, grid in bits 48+ of the id */
+    if (c->iStar >= 1 || !cellLoc || gpLoc < 1) {
+        rng_init(&c->rng, seed, (uint64_t)pid, (uint32_t)c->iStar);
+    } else {
+        const OrGrid *dg = &c->grids[gpLoc - 1];
+        uint32_t lin = (uint32_t)((cellLoc[0] - 1) + dg->nx * ((cellLoc[1] - 1) + dg->ny * (cellLoc[2] - 1)));
+        rng_init(&c->rng, seed, ((uint64_t)gpLoc << 48) + (uint64_t)pid, 0x80000000u + lin);
+    }
     c->segs = 0;
     c->fateCode = 0;
 

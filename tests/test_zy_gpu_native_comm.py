@@ -124,9 +124,22 @@ def _worker_body(rank, world, idfile, name, n, q, allreduce=False):
         time.sleep(0.05)
     with open(idfile, "rb") as f:
         e.comm_init(f.read())
-    if allreduce:
+    if allreduce == "p2p+slabs":
+        # the CDF table goes up as one slab of nu-planes per rank and is all-gathered over NVLink
+        e.set_option("pdf_slabs", 1)
+        e.set_pdfs()
+        allreduce = "p2p"
+    if allreduce == "allreduce" or allreduce is True:
         e.set_option("exchange_allreduce", 1)
+    elif allreduce == "nccl":
+        e.set_option("exchange_p2p", 0)
+    elif allreduce == "p2p" and not m.lgDebug:
+        e.set_option("exchange_p2p", 1)            # required: an error if peer memory cannot be mapped
     e.lucy_transport([n] * m.nStars)
+    want_path = {"allreduce": "nccl all-reduce", True: "nccl all-reduce", "nccl": "nccl reduce-scatter + all-gather",
+                 "p2p": "nccl reduce-scatter + all-gather" if m.lgDebug else "fused peer-memory kernel (NVLink)"}.get(allreduce)
+    if want_path:
+        assert e.last_exchange["path"] == want_path, e.last_exchange
     out = [e.fetch(iG, want=_want(m)) for iG in range(1, m.nGrids + 1)]
     sums = [e.checksum(iG, w) for iG in range(1, m.nGrids + 1) for w in (0, 1)]
     # the same packets by this rank alone (option solo) on the same context: what bench.py's
@@ -141,9 +154,11 @@ def _worker_body(rank, world, idfile, name, n, q, allreduce=False):
     e.close()
 
 
-@pytest.mark.parametrize("name,allreduce", [("multigrid_sym", False), ("cube_clumpy_gasdust", False), ("hii_sym_gas_debug", False),
-                                            ("viewing_angles", False), ("multigrid_sym", True), ("multigrid_nonsym", False),
-                                            ("plane_slab_gasdust", False)])
+@pytest.mark.parametrize("name,allreduce", [("multigrid_sym", "p2p"), ("cube_clumpy_gasdust", "p2p"), ("hii_sym_gas_debug", "p2p"),
+                                            ("viewing_angles", "p2p"), ("multigrid_sym", "allreduce"), ("multigrid_sym", "nccl"), ("multigrid_sym", "p2p+slabs"),
+                                            ("cube_clumpy_gasdust", "p2p+slabs"), ("dust_shell_hg", "p2p+slabs"),
+                                            ("cube_clumpy_gasdust", "nccl"), ("hii_sym_gas_debug", "nccl"),
+                                            ("multigrid_nonsym", False), ("plane_slab_gasdust", False)])
 def test_two_ranks_native_exchange_matches_single_gpu(cuda_lib, name, allreduce):
     import torch
     import torch.multiprocessing as mp
@@ -180,6 +195,24 @@ def test_two_ranks_native_exchange_matches_single_gpu(cuda_lib, name, allreduce)
         for r in (0, 1):
             for k in _want(m):
                 assert np.array_equal(got[r][iG][k], ref[iG][k]), (iG, r, k)
+
+
+def test_fetch_cells_is_the_round_robin_slice_of_jste(cuda_lib):
+    """mcb200_fetch_estimators_cells: the rows of cells r+1, r+1+N, ... (iteration_mod.f90:832), compact."""
+    from cases import make
+    from mocassin_b200.api import PacketEngine
+
+    m, _ = make("cube_clumpy_gasdust")
+    e = PacketEngine(m, seed=12345)
+    e.upload_iteration_inputs()
+    e.lucy_transport([20001])
+    J = e.fetch(1)["Jste"]
+    nC = m.grids[0].nCells
+    for first, stride in ((1, 1), (1, 2), (2, 2), (3, 8), (8, 8), (nC, 8), (nC + 1, 8)):
+        got = e.fetch_cells(1, first, stride)
+        want = J[first::stride] if first <= nC else J[:0]
+        assert got.shape == want.shape and np.array_equal(got, want), (first, stride)
+    e.close()
 
 
 def test_solo_option_and_checksum(cuda_lib):
