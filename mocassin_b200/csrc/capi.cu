@@ -249,6 +249,8 @@ struct mcb200_ctx {
     bool pdfSlabs = false;                // option pdf_slabs: 1/nranks of the PDF table per rank over PCIe, all-gather over NVLink
     int64_t lastPdfH2D = 0;               // bytes the last mcb200_set_pdfs moved host -> device for the CDF table
     int64_t epoch = 0;                    // option epoch: advances the Philox key (set to the Lucy iteration number)
+    cudaStream_t sideStream = nullptr;    // fold of the escape counts / SED beside the link-bound J merge (multi-rank)
+    cudaEvent_t sideEv0 = nullptr, sideEv1 = nullptr;
     bool solo = false;                    // option solo
     int soloRank = 0, soloNranks = 1;
     bool keepSharded = false;             // option keep_sharded: skip the all-gather (Jste stays valid only on the owner's share)
@@ -478,10 +480,11 @@ int ensure_sed(mcb200_ctx *ctx)
 }
 
 // sedQ += per-plane sums of the escape counts of every grid (tally set `set`)
-int sed_tally(mcb200_ctx *ctx, int set, int *launches)
+int sed_tally(mcb200_ctx *ctx, int set, int *launches, cudaStream_t st = nullptr)
 {
     int rc = ensure_sed(ctx);
     if (rc) return rc;
+    if (!st) st = ctx->stream;
     const int nb = ctx->cfg.nbins;
     for (auto &g : ctx->grids) {
         const unsigned int *q = set == 1 ? g.escQ2.p : g.escQ.p;
@@ -490,15 +493,15 @@ int sed_tally(mcb200_ctx *ctx, int set, int *launches)
         size_t nR = (size_t)g.nCells + 1;
         std::vector<int> flag(nb + 1, 1);
         if (touched) {
-            CU(cudaMemcpyAsync(flag.data(), touched, sizeof(int) * (nb + 1), cudaMemcpyDeviceToHost, ctx->stream));
-            CU(cudaStreamSynchronize(ctx->stream));
+            CU(cudaMemcpyAsync(flag.data(), touched, sizeof(int) * (nb + 1), cudaMemcpyDeviceToHost, st));
+            CU(cudaStreamSynchronize(st));
         }
         if (set == 0 && !g.folded.empty())           // planes a ranged fold has already tallied and cleared
             for (int nu = 0; nu <= nb; ++nu) if (g.folded[nu]) flag[nu] = 0;
         for (auto &rg : touched_ranges(flag, g.folded.empty() ? 3 : 1))
             for (int ang = 0; ang <= ctx->cfg.nAngleBins; ++ang)
             {
-                CU(launch_sed_sum(q, nR, rg.first + (nb + 1) * ang, rg.second - rg.first + 1, ctx->sedQ.p, ctx->stream));
+                CU(launch_sed_sum(q, nR, rg.first + (nb + 1) * ang, rg.second - rg.first + 1, ctx->sedQ.p, st));
                 if (launches) ++*launches;
             }
     }
@@ -507,25 +510,26 @@ int sed_tally(mcb200_ctx *ctx, int set, int *launches)
 
 // fold the tallies of the nu-planes [nu0, nu1] of one grid: J planes nu >= 1, escape-count planes
 // nu0..nu1 of every viewing angle.  Asynchronous on the library stream.
-int fold_planes(mcb200_ctx *ctx, GridState &g, int nu0, int nu1, int *launches, bool withJ = true)
+int fold_planes(mcb200_ctx *ctx, GridState &g, int nu0, int nu1, int *launches, bool withJ = true, cudaStream_t st = nullptr)
 {
+    if (!st) st = ctx->stream;
     const int nb = ctx->cfg.nbins, blocks = ctx->numSMs * 8;
     const size_t nR = (size_t)g.nCells + 1;
     const double lenUnit = std::ldexp(1.0, g.lenExp);
     int p0 = nu0 < 1 ? 1 : nu0, p1 = nu1;
     if (withJ && p1 >= p0) {
         size_t off = (size_t)(p0 - 1) * nR, len = (size_t)(p1 - p0 + 1) * nR;
-        CU(launch_fold_j(g.JsteQ.p + off, g.Jste.p + off, g.dV.p, (int)nR, off, len, lenUnit, ctx->pendingDeltaE, blocks, ctx->stream));
+        CU(launch_fold_j(g.JsteQ.p + off, g.Jste.p + off, g.dV.p, (int)nR, off, len, lenUnit, ctx->pendingDeltaE, blocks, st));
         if (launches) ++*launches;
         if (ctx->cfg.lgDebug) {
-            CU(launch_fold_j(g.JdifQ.p + off, g.Jdif.p + off, g.dV.p, (int)nR, off, len, lenUnit, ctx->pendingDeltaE, blocks, ctx->stream));
+            CU(launch_fold_j(g.JdifQ.p + off, g.Jdif.p + off, g.dV.p, (int)nR, off, len, lenUnit, ctx->pendingDeltaE, blocks, st));
             if (launches) ++*launches;
         }
     }
     for (int ang = 0; ang <= ctx->cfg.nAngleBins; ++ang) {
         size_t off = nR * ((size_t)nu0 + (size_t)(nb + 1) * (size_t)ang);
         size_t len = (size_t)(nu1 - nu0 + 1) * nR;
-        CU(launch_fold_count(g.escQ.p + off, g.esc.p + off, len, ctx->pendingDeltaE, blocks, ctx->stream));
+        CU(launch_fold_count(g.escQ.p + off, g.esc.p + off, len, ctx->pendingDeltaE, blocks, st));
         if (launches) ++*launches;
     }
     return MCB200_OK;
@@ -679,25 +683,46 @@ int fold_pending(mcb200_ctx *ctx)
     int blocks = ctx->numSMs * 8;
     const int nb = ctx->cfg.nbins;
     int launches = 0;
+    cudaStream_t s = ctx->stream;
     if (ctx->pending2) {
         // integer merge first (exact), then ONE fold: fold(Q0)+fold(Q1) would round differently
         for (auto &g : ctx->grids) {
             if (!g.JsteQ2.p) continue;
             CU(launch_merge_sets(g.JsteQ.p, g.JsteQ2.p, g.JsteQ.n, g.escQ.p, g.escQ2.p, g.escQ.n,
-                                 g.nuTouched.p, g.nuTouched2.p, nb + 1, blocks, ctx->stream));
+                                 g.nuTouched.p, g.nuTouched2.p, nb + 1, blocks, s));
             ++launches;
         }
         ctx->pending2 = false;
     }
+    // Multi-rank: the merge of the J planes (fold_shards) is bound by the links, the escape-count and
+    // SED work by HBM and small.  The first goes on the library stream, the rest on a side stream, so
+    // that they overlap instead of queueing up behind each other.
+    bool anySharded = false;
+    for (auto &g : ctx->grids) anySharded = anySharded || !g.jShards.empty();
+    cudaStream_t es = s;
+    if (anySharded) {
+        if (!ctx->sideStream) {
+            CU(cudaStreamCreateWithFlags(&ctx->sideStream, cudaStreamNonBlocking));
+            CU(cudaEventCreateWithFlags(&ctx->sideEv0, cudaEventDisableTiming));
+            CU(cudaEventCreateWithFlags(&ctx->sideEv1, cudaEventDisableTiming));
+        }
+        es = ctx->sideStream;
+        CU(cudaEventRecord(ctx->sideEv0, s));
+        CU(cudaStreamWaitEvent(es, ctx->sideEv0, 0));
+        CU(cudaEventRecord(ctx->ev0, s));
+        for (auto &g : ctx->grids)
+            if (!g.jShards.empty()) { int rc = fold_shards(ctx, g, &launches); if (rc) return rc; }
+        CU(cudaEventRecord(ctx->ev1, s));
+    }
     {
         // SED: counts of this call per (nu, angle) over all cells and grids, folded like
         // escapedPackets: SED += float(count) * deltaE
-        if (!ctx->sedReady) { int rc = sed_tally(ctx, 0, &launches); if (rc) return rc; }
+        if (!ctx->sedReady) { int rc = sed_tally(ctx, 0, &launches, es); if (rc) return rc; }
         size_t n = sed_size(ctx);
         std::vector<unsigned long long> q(n);
-        CU(cudaMemcpyAsync(q.data(), ctx->sedQ.p, n * 8, cudaMemcpyDeviceToHost, ctx->stream));
-        CU(cudaStreamSynchronize(ctx->stream));
-        CU(ctx->sedQ.zero(ctx->stream));
+        CU(cudaMemcpyAsync(q.data(), ctx->sedQ.p, n * 8, cudaMemcpyDeviceToHost, es));
+        CU(cudaStreamSynchronize(es));
+        CU(cudaMemsetAsync(ctx->sedQ.p, 0, ctx->sedQ.n * 8, es));
         for (size_t k = 0; k < n; ++k)
             if (q[k]) {
                 volatile float add = (float)q[k] * ctx->pendingDeltaE;
@@ -711,35 +736,36 @@ int fold_pending(mcb200_ctx *ctx)
         // only nu-planes in which a packet was emitted can hold tallies
         std::vector<int> flag(nb + 1, 1);
         if (g.nuTouched.p) {
-            CU(cudaMemcpyAsync(flag.data(), g.nuTouched.p, sizeof(int) * (nb + 1), cudaMemcpyDeviceToHost, ctx->stream));
-            CU(cudaStreamSynchronize(ctx->stream));
+            CU(cudaMemcpyAsync(flag.data(), g.nuTouched.p, sizeof(int) * (nb + 1), cudaMemcpyDeviceToHost, es));
+            CU(cudaStreamSynchronize(es));
         }
         // planes a ranged fold (mcb200_reduce_range) has already taken are skipped
         if (!g.folded.empty())
             for (int nu = 0; nu <= nb; ++nu) if (g.folded[nu]) flag[nu] = 0;
-        const bool sharded = !g.jShards.empty();
+        // J planes of a grid whose tallies were not scattered over the ranks are folded here, all of
+        // them on every rank; the escape counts always are
+        const bool withJ = !anySharded;
         for (auto &rg : touched_ranges(flag, g.folded.empty() ? 3 : 1)) {
-            int rc = fold_planes(ctx, g, rg.first, rg.second, &launches, /*withJ=*/!sharded);
+            int rc = fold_planes(ctx, g, rg.first, rg.second, &launches, withJ, es);
             if (rc) return rc;
-        }
-        if (sharded) {
-            CU(cudaEventRecord(ctx->ev0, ctx->stream));
-            int rc = fold_shards(ctx, g, &launches);
-            if (rc) return rc;
-            CU(cudaEventRecord(ctx->ev1, ctx->stream));
-            CU(cudaEventSynchronize(ctx->ev1));
-            float ms = 0.f;
-            CU(cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev1));
-            ctx->lastPhaseMs[2] = ms;
         }
         g.folded.clear();
         if (ctx->cfg.lgDebug && g.lineQ.n) {
-            CU(launch_fold_count(g.lineQ.p, g.linePk.p, g.lineQ.n, ctx->pendingDeltaE, blocks, ctx->stream));
+            CU(launch_fold_count(g.lineQ.p, g.linePk.p, g.lineQ.n, ctx->pendingDeltaE, blocks, es));
             ++launches;
         }
-        if (g.nuTouched.p) CU(g.nuTouched.zero(ctx->stream));
+        if (g.nuTouched.p) CU(cudaMemsetAsync(g.nuTouched.p, 0, g.nuTouched.n * sizeof(int), es));
     }
-    CU(cudaStreamSynchronize(ctx->stream));
+    if (anySharded) {
+        CU(cudaEventRecord(ctx->sideEv1, es));
+        CU(cudaStreamWaitEvent(s, ctx->sideEv1, 0));
+    }
+    CU(cudaStreamSynchronize(s));
+    if (anySharded) {
+        float ms = 0.f;
+        CU(cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev1));
+        ctx->lastPhaseMs[2] = ms;
+    }
     ctx->pending = false;
     ctx->exchanged = false;
     ctx->lastFoldLaunches = launches;
@@ -1385,6 +1411,9 @@ int mcb200_destroy(mcb200_ctx *ctx)
     if (ctx->ev2) cudaEventDestroy(ctx->ev2);
     if (ctx->pdfReady) cudaEventDestroy(ctx->pdfReady);
     if (ctx->copyStream) { cudaStreamSynchronize(ctx->copyStream); cudaStreamDestroy(ctx->copyStream); }
+    if (ctx->sideStream) { cudaStreamSynchronize(ctx->sideStream); cudaStreamDestroy(ctx->sideStream); }
+    if (ctx->sideEv0) cudaEventDestroy(ctx->sideEv0);
+    if (ctx->sideEv1) cudaEventDestroy(ctx->sideEv1);
     if (ctx->sparseHost) cudaFreeHost(ctx->sparseHost);
     for (auto &g : ctx->grids) p2p_close(g, ctx->rank);
     if (ctx->comm) { nccl_api().CommDestroy(ctx->comm); ctx->comm = nullptr; }

@@ -101,34 +101,59 @@ struct P2PPeers {
     int nranks, rank;
 };
 
-template <int N>
+// N = ranks (compile time), U = elements per thread and trip: U*(N-1) independent peer loads are in
+// flight per thread before the first is used -- with few peers the links are latency bound otherwise
+template <int N, int U>
 __global__ void __launch_bounds__(256) p2p_reduce_fold_kernel(const __grid_constant__ P2PPeers P, const float *__restrict__ dV,
                                                               int nRows, size_t first, size_t total, double lenUnit, float deltaE)
 {
-    const int nr = N > 0 ? N : P.nranks;
-    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     const size_t stride = (size_t)gridDim.x * blockDim.x;
-    for (; i < total; i += stride) {
+    for (size_t i0 = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i0 < total; i0 += stride * U) {
+        unsigned long long q[U][N];
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            const size_t i = i0 + (size_t)u * stride;
+#pragma unroll
+            for (int r = 0; r < N; ++r) q[u][r] = i < total ? __ldcv(&P.Q[r][first + i]) : 0ull;
+        }
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            const size_t i = i0 + (size_t)u * stride;
+            unsigned long long sum = 0;
+#pragma unroll
+            for (int r = 0; r < N; ++r) sum += q[u][r];
+            if (sum != 0ull) {
+                const size_t e = first + i;
+                int cell = (int)(e % (size_t)nRows);
+                float len = (float)((double)(long long)sum * lenUnit);
+                float v = P.J[P.rank][e] + len * deltaE / dV[cell];
+#pragma unroll
+                for (int r = 0; r < N; ++r) P.J[r][e] = v;
+                P.Q[P.rank][e] = 0ull;
+            }
+        }
+    }
+    __threadfence_system();              // peer stores performed before the kernel counts as complete
+}
+
+// any rank count up to 16 (run time)
+__global__ void __launch_bounds__(256) p2p_reduce_fold_generic_kernel(const __grid_constant__ P2PPeers P, const float *__restrict__ dV,
+                                                                      int nRows, size_t first, size_t total, double lenUnit, float deltaE)
+{
+    const size_t stride = (size_t)gridDim.x * blockDim.x;
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += stride) {
         const size_t e = first + i;
-        unsigned long long q[N > 0 ? N : 16];
-#pragma unroll
-        for (int r = 0; r < (N > 0 ? N : 16); ++r)
-            if (r < nr) q[r] = __ldcv(&P.Q[r][e]);          // volatile-class load: never served from a stale line
         unsigned long long sum = 0;
-#pragma unroll
-        for (int r = 0; r < (N > 0 ? N : 16); ++r)
-            if (r < nr) sum += q[r];
+        for (int r = 0; r < P.nranks; ++r) sum += __ldcv(&P.Q[r][e]);
         if (sum != 0ull) {
             int cell = (int)(e % (size_t)nRows);
             float len = (float)((double)(long long)sum * lenUnit);
             float v = P.J[P.rank][e] + len * deltaE / dV[cell];
-#pragma unroll
-            for (int r = 0; r < (N > 0 ? N : 16); ++r)
-                if (r < nr) P.J[r][e] = v;
+            for (int r = 0; r < P.nranks; ++r) P.J[r][e] = v;
             P.Q[P.rank][e] = 0ull;
         }
     }
-    __threadfence_system();              // peer stores performed before the kernel counts as complete
+    __threadfence_system();
 }
 
 cudaError_t launch_p2p_reduce_fold(const P2PPeers &P, const float *dV, int nRows, size_t first, size_t total,
@@ -136,10 +161,10 @@ cudaError_t launch_p2p_reduce_fold(const P2PPeers &P, const float *dV, int nRows
 {
     if (total == 0) return cudaSuccess;
     switch (P.nranks) {
-    case 2: p2p_reduce_fold_kernel<2><<<blocks, 256, 0, s>>>(P, dV, nRows, first, total, lenUnit, deltaE); break;
-    case 4: p2p_reduce_fold_kernel<4><<<blocks, 256, 0, s>>>(P, dV, nRows, first, total, lenUnit, deltaE); break;
-    case 8: p2p_reduce_fold_kernel<8><<<blocks, 256, 0, s>>>(P, dV, nRows, first, total, lenUnit, deltaE); break;
-    default: p2p_reduce_fold_kernel<0><<<blocks, 256, 0, s>>>(P, dV, nRows, first, total, lenUnit, deltaE); break;
+    case 2: p2p_reduce_fold_kernel<2, 4><<<blocks, 256, 0, s>>>(P, dV, nRows, first, total, lenUnit, deltaE); break;
+    case 4: p2p_reduce_fold_kernel<4, 2><<<blocks, 256, 0, s>>>(P, dV, nRows, first, total, lenUnit, deltaE); break;
+    case 8: p2p_reduce_fold_kernel<8, 2><<<blocks, 256, 0, s>>>(P, dV, nRows, first, total, lenUnit, deltaE); break;
+    default: p2p_reduce_fold_generic_kernel<<<blocks, 256, 0, s>>>(P, dV, nRows, first, total, lenUnit, deltaE); break;
     }
     return cudaGetLastError();
 }
