@@ -37,6 +37,17 @@ def _stale() -> bool:
     return False
 
 
+def build_variant(out: str, defines=()) -> str:
+    """A/B build of the same sources with extra -D flags into another file (loaded through
+    $MCB200_LIB, mocassin_b200/_lib.py); the product library is `build()`."""
+    nvcc = shutil.which("nvcc") or "/usr/local/cuda/bin/nvcc"
+    cmd = [nvcc] + NVCC_FLAGS + [f"-D{d}" for d in defines] + ["-o", os.path.abspath(out)] + SOURCES
+    res = subprocess.run(cmd, cwd=CSRC, capture_output=True, text=True)
+    if res.returncode != 0:
+        raise RuntimeError("nvcc failed:\n" + res.stdout + res.stderr)
+    return out
+
+
 def build(force: bool = False, verbose: bool = False) -> str:
     if not force and not _stale():
         return LIB
@@ -53,4 +64,8 @@ def build(force: bool = False, verbose: bool = False) -> str:
 
 
 if __name__ == "__main__":
-    print(build(force="--force" in sys.argv, verbose="-v" in sys.argv))
+    if "--variant" in sys.argv:          # python -m mocassin_b200.build --variant out.so MCB_FLY_OCC=5 ...
+        i = sys.argv.index("--variant")
+        print(build_variant(sys.argv[i + 1], sys.argv[i + 2:]))
+    else:
+        print(build(force="--force" in sys.argv, verbose="-v" in sys.argv))

@@ -49,6 +49,19 @@ struct Rng {
         uint32_t w = lane == 0 ? buf[0] : lane == 1 ? buf[1] : lane == 2 ? buf[2] : buf[3];
         return (float)(w >> 8) * 5.9604644775390625e-08f;
     }
+    // The same uniform from the draw counter alone: key and counter words are passed in and the
+    // block is recomputed on every call instead of being cached.  For code that draws rarely but
+    // is short of registers (the FLY kernel: one draw per interaction, ~1 per 70 cell crossings):
+    // only `n` of this struct stays live.
+    __device__ __forceinline__ float uniform_at(uint64_t seed, uint64_t pid, uint32_t s)
+    {
+        uint32_t c[4] = {(uint32_t)pid, (uint32_t)(pid >> 32), n >> 2, s};
+        philox4x32_10(c, (uint32_t)seed, (uint32_t)(seed >> 32));
+        uint32_t lane = n & 3u;
+        ++n;
+        uint32_t w = lane == 0 ? c[0] : lane == 1 ? c[1] : lane == 2 ? c[2] : c[3];
+        return (float)(w >> 8) * 5.9604644775390625e-08f;
+    }
 };
 
 }  // namespace mcb

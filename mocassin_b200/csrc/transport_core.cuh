@@ -9,6 +9,13 @@
 
 #include <cuda_runtime.h>
 
+#ifndef MCB_FASTWALL
+#define MCB_FASTWALL 1                   // A/B build switches (build.py --variant), see profiles/README.md
+#endif
+#ifndef MCB_LEANRNG
+#define MCB_LEANRNG 0
+#endif
+
 namespace mcb {
 
 enum { CH_STELLAR = 0, CH_DIFFEXT = 1, CH_DIFFUSE = 2, CH_DUSTEMI = 3 };
@@ -201,7 +208,9 @@ __device__ __forceinline__ unsigned long long packet_pid(const TransportArgs &a,
 // 0 generic; 1 neither debug tallies nor plane-parallel illumination; 2 = 1 and not symmetricXYZ.
 // LIMIT = false: the caller (FLY kernel) folds the iteration limit of :2838-2846 into its own
 // per-flight step budget instead of testing it on every crossing.
-template <bool MULTI, bool DENSE = false, int MODE = 0, bool LIMIT = true>
+// LEANRNG: step() draws through Rng::uniform_at (no cached Philox block, packet id rebuilt from the
+// packet index): frees the registers of the cache in the crossing loop of the FLY kernel.
+template <bool MULTI, bool DENSE = false, int MODE = 0, bool LIMIT = true, bool LEANRNG = false>
 struct Transport {
     // single dense grid: the table index of the packet's cell is carried along and advanced with
     // the cell indices instead of being rebuilt from (x,y,z) on every crossing
@@ -217,6 +226,11 @@ struct Transport {
     {
         if (MULTI) return a.grids[gP - 1];
         return a.g1;
+    }
+    __device__ __forceinline__ float uni(Lane &L) const
+    {
+        if (LEANRNG) return L.rng.uniform_at(a.seed, packet_pid(a, L.k), a.rngStream);
+        return L.rng.uniform();
     }
     __device__ __forceinline__ bool debug() const { return MODE >= 1 ? false : (bool)a.P.lgDebug; }
     __device__ __forceinline__ bool plane() const { return MODE >= 1 ? false : (bool)a.P.lgPlane; }
@@ -250,20 +264,29 @@ struct Transport {
     }
 
     // ---- PH_ESCAPE: escape tally (photon_mod.f90:373-462 and the six copies in pathSegment)
-    __device__ __forceinline__ void do_escape(Lane &L)
+    // agg: called by the converged lanes of an event kernel -- packets that escape together mostly
+    // left the same cell at the same frequency (every stellar packet of a wave counts into the star's
+    // cell), so equal targets are counted once per warp (MATCH.ANY) instead of lane by lane on a few
+    // hundred hot addresses
+    __device__ __forceinline__ void do_escape(Lane &L, bool agg = false)
     {
         const DevParams &P = a.P;
-        int idirT, idirP;
-        if (P.lgSym) idirT = (int)(dm_acosf(fabsf(L.dz)) / P.dTheta) + 1;
-        else         idirT = (int)(dm_acosf(L.dz) / P.dTheta) + 1;
-        if (idirT > P.totT) idirT = P.totT;
-        if (fabsf(L.dx) < 1.e-35f) idirP = 0;
-        else if (P.lgSym) idirP = (int)(dm_atanf(fabsf(L.dy) / fabsf(L.dx)) / P.dPhi);
-        else              idirP = (int)(dm_atanf(L.dy / L.dx) / P.dPhi);
-        if (idirP < 0) idirP = P.totP + idirP;
-        idirP = idirP + 1;
-        if (idirP > P.totP) idirP = P.totP;
-        if (idirT < 1 || idirP < 1) { fail(L, 10); return; }
+        // The direction bins select the viewing-angle planes; without viewing angles (nAngleBins = 0)
+        // their only other trace is the reference's idirT/idirP >= 1 sanity stop, which a finite
+        // direction cannot trip (acos >= 0; a negative atan bin is wrapped), so acos/atan are skipped.
+        int idirT = 1, idirP = 1;
+        if (P.nAngleBins > 0) {
+            if (P.lgSym) idirT = (int)(dm_acosf(fabsf(L.dz)) / P.dTheta) + 1;
+            else         idirT = (int)(dm_acosf(L.dz) / P.dTheta) + 1;
+            if (idirT > P.totT) idirT = P.totT;
+            if (fabsf(L.dx) < 1.e-35f) idirP = 0;
+            else if (P.lgSym) idirP = (int)(dm_atanf(fabsf(L.dy) / fabsf(L.dx)) / P.dPhi);
+            else              idirP = (int)(dm_atanf(L.dy / L.dx) / P.dPhi);
+            if (idirP < 0) idirP = P.totP + idirP;
+            idirP = idirP + 1;
+            if (idirP > P.totP) idirP = P.totP;
+            if (idirT < 1 || idirP < 1) { fail(L, 10); return; }
+        }
         if (L.orgG < 1 || L.orgG > P.nGrids) { fail(L, 11); return; }
         if (L.orgC < 0) { fail(L, 12); return; }
         const DevGrid &g = G(L.orgG);
@@ -281,6 +304,11 @@ struct Transport {
             } else {
                 atomicAdd(&g.escQ[base], 1u);
             }
+        } else if (agg) {
+            const unsigned int act = __activemask();
+            const unsigned long long key = (unsigned long long)base | ((unsigned long long)(unsigned int)L.orgG << 48);
+            const unsigned int peers = __match_any_sync(act, key);
+            if ((int)(threadIdx.x & 31u) == __ffs(peers) - 1) atomicAdd(&g.escQ[base], (unsigned int)__popc(peers));
         } else {
             atomicAdd(&g.escQ[base], 1u);
         }
@@ -547,7 +575,30 @@ struct Transport {
         float opacEarly = 0.f;
         if (early) opacEarly = __ldg(&a.g1.opacity[L.planeBase]);
         bool snapped = false;
-        for (int j = 1;; ++j) {
+        // Dense single grid, fast path of the wall stage: the three wall distances with none of the
+        // special cases.  Those -- an axis sitting on its wall (snap, drop on the outermost wall, the
+        // zero distance replaced by the axis end, :1263-1432) or a non-finite distance -- all begin
+        // with a moving axis whose |distance| is not >= 1e-10; when no axis is in that state the
+        // generic stage below reduces to exactly these lines, and it is skipped.  Otherwise nothing
+        // has been modified yet and the generic stage runs from scratch.
+        bool fast = false;
+        if (MCB_FASTWALL && kInc && !sym()) {
+            const DevGrid &g = a.g1;
+            const bool px = L.vx > 1.e-10f, py = L.vy > 1.e-10f, pz = L.vz > 1.e-10f;
+            const bool mx = px || L.vx < -1.e-10f, my = py || L.vy < -1.e-10f, mz = pz || L.vz < -1.e-10f;
+            const float dx = div_rn(__ldg(&g.xWall[px ? L.xP : L.xP - 1]) - L.rx, L.vx, L.iax);
+            const float dy = div_rn(__ldg(&g.yWall[py ? L.yP : L.yP - 1]) - L.ry, L.vy, L.iay);
+            const float dz = div_rn(__ldg(&g.zWall[pz ? L.zP : L.zP - 1]) - L.rz, L.vz, L.iaz);
+            const bool special = (mx && !(fabsf(dx) >= 1.e-10f)) || (my && !(fabsf(dy) >= 1.e-10f)) ||
+                                 (mz && !(fabsf(dz) >= 1.e-10f));
+            if (__builtin_expect(!special, 1)) {
+                fast = true;
+                posx = px; posy = py; posz = pz;
+                dSx = mx ? dx : 1.e35f; dSy = my ? dy : 1.e35f; dSz = mz ? dz : 1.e35f;
+                cell = 1;
+            }
+        }
+        for (int j = 1; !fast; ++j) {
             if (MULTI) {
                 const DevGrid &g0 = G(L.gP);
                 if (L.xP > g0.nx || L.xP < 1 || L.yP > g0.ny || L.yP < 1 || L.zP > g0.nz || L.zP < 1) { fail(L, 58); return; }
@@ -607,12 +658,14 @@ struct Transport {
         float opac = (early && !snapped) ? opacEarly : __ldg(&g.opacity[tix]);
 
         // cells on a wall (:1395-1397): the axis end coordinate replaces a zero distance
-        if (fabsf(dSx) < 1.e-10f) dSx = g.xN;
-        if (fabsf(dSy) < 1.e-10f) dSy = g.yN;
-        if (fabsf(dSz) < 1.e-10f) dSz = g.zN;
+        if (!fast) {                                 // (the fast path has no distance below 1e-10)
+            if (fabsf(dSx) < 1.e-10f) dSx = g.xN;
+            if (fabsf(dSy) < 1.e-10f) dSy = g.yN;
+            if (fabsf(dSz) < 1.e-10f) dSz = g.zN;
+        }
         dSx = fabsf(dSx); dSy = fabsf(dSy); dSz = fabsf(dSz);
         float dS = fminf(fminf(dSx, dSy), dSz);
-        if (__builtin_expect(dS <= 0.f, 0)) {        // :1404-1432, only if an axis end coordinate is <= 0
+        if (__builtin_expect(!fast && dS <= 0.f, 0)) {   // :1404-1432, only if an axis end coordinate is <= 0
             if (dSx <= 0.f)      dS = fminf(dSy, dSz);
             else if (dSy <= 0.f) dS = fminf(dSx, dSz);
             else                 dS = fminf(dSx, dSy);
@@ -644,7 +697,7 @@ struct Transport {
             }
             if (P.lgDust) {
                 float probSca = __ldg(&g.scaOpac[tix]) / opac;
-                float random = 1.f - L.rng.uniform();
+                float random = 1.f - uni(L);
                 bool scattered;
                 if (random > probSca) scattered = false;
                 else if (random <= probSca) scattered = true;

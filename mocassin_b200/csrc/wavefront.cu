@@ -82,7 +82,7 @@ __global__ void __launch_bounds__(kThreads) wf_event_kernel(const __grid_constan
             } else if (EV == EV_SCATTER) {
                 T.do_scatter(L);
             } else {
-                T.do_escape(L);
+                T.do_escape(L, true);
             }
         }
         bool toFly = valid && L.phase == PH_FLY;
@@ -125,13 +125,16 @@ __global__ void __launch_bounds__(kThreads) wf_event_kernel(const __grid_constan
 // atomic per chunk, records of the chunk prefetched into L2) and cross cells until the next
 // event; ended flights are written back in place and their positions staged per warp in
 // shared memory, flushed 32 at a time (one global atomic per 32 events, coalesced stores).
+#ifndef MCB_FLY_OCC
+#define MCB_FLY_OCC 4                    // resident CTAs per SM the FLY kernel is compiled for (A/B: build.py --define)
+#endif
 template <bool MULTI, bool DENSE, int MODE>
-__global__ void __launch_bounds__(kThreads, 4) wf_fly_kernel(const __grid_constant__ WfArgs w)
+__global__ void __launch_bounds__(kThreads, MCB_FLY_OCC) wf_fly_kernel(const __grid_constant__ WfArgs w)
 {
     extern __shared__ unsigned int smem[];
     scratch_init(smem, w.t.P.nbins);
     // single grid: the per-crossing iteration-limit test is folded into the step budget below
-    Transport<MULTI, DENSE, MODE, MULTI> T(w.t, smem, smem + C_COUNT * kThreads);
+    Transport<MULTI, DENSE, MODE, MULTI, (MCB_LEANRNG != 0)> T(w.t, smem, smem + C_COUNT * kThreads);
     unsigned int *stage = smem + scratch_words(w.t.P.nbins) + (threadIdx.x >> 5) * (EV_COUNT * kStage);
     const unsigned int FULL = 0xffffffffu;
     const unsigned int lane = threadIdx.x & 31u;

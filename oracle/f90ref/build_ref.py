@@ -141,6 +141,15 @@ AUX_SLICES = [
     dict(file='grid_mod.f90', name='initial_ions', args='grid, in_ytop', decls=[(901, 901), (904, 938)], body=[(1564, 1607)],
          glue_decls=['integer, intent(in) :: in_ytop'], glue_start=['ytop = in_ytop'], glue_end=[],
          guards={1564: 'h0in = 1.e-5', 1607: 'end do'}),
+    # setSubGrids: the sub-grid list and one sub-grid's density file -- list-directed READs (units 71, 72 bound
+    # by the harness), axes rescaled from normalised coordinates, the reference's own sanity stops, active cells
+    dict(file='grid_mod.f90', name='sub_grid_read', args='grid, out_hden, out_ndust', decls=[(1807, 1836)],
+         body=[(1847, 1857), (2028, 2232)],
+         glue_decls=['real, intent(out) :: out_hden(:,:,:), out_ndust(:,:,:)'],
+         glue_end=['out_hden = hdentemp', 'if (lgdust) out_ndust = ndusttemp', 'end do'],
+         guards={1807: 'type(grid_type), dimension(:),intent(inout) :: grid', 1847: 'do ig = 2, ngrids',
+                 1853: 'read(71, *) grid(ig)%motherp', 2029: 'open (unit= 72, file=dfileread', 2103: 'read(72, *) x,y,z, hdentemp(ix,iy,iz), ndusttemp(ix,iy,iz)',
+                 2230: 'end do', 2232: 'close(72)'}),
     # initCartesianGrid: angular bins of the escape tallies and the viewing-angle pointer tables
     dict(file='grid_mod.f90', name='angle_tables', args='', decls=[], body=[(416, 468)],
          glue_decls=['integer :: i, err'], glue_end=[],
@@ -178,7 +187,7 @@ AUX_EXTERNS = {'boltgaunt',
                # file readers and branches off the gas-deck path (initXSecArray, setPointers): supplied as no-ops
                'makecolliondata', 'makeaugerdata', 'readheireclines', 'setcompton', 'makedustxsec', 'phinit'}
 # procedures that must translate completely, and the untranslated statements tolerated in them
-AUX_STRICT = {'writegrid': 0, 'setstarposition': 0, 'getvolume': 0, 'writesed': 0, 'writecontcube': 0, 'writetaunu': 0, 'integratepathtaunu': 0, 'bhmie': 0, 'getqs': 0, 'dust_xsec_assembly': 0, 'dust_emission_int': 0, 'grain_weights': 0, 'angle_tables': 0, 'active_cells': 0, 'fill_axes': 0, 'fill_mask': 0, 'opacity_block': 0, 'photo_rates': 0, 'photo_heat': 0, 'getoutershell': 0, 'ionizationdriver': 0, 'edensum': 0, 'addopacity': 0, 'putopacity': 0, 'inopacity': 0, 'getflux': 0, 'setprobden': 0, 'locate': 0, 'linearmap': 0, 'sortup': 0, 'gas_nu_mesh': 0, 'initial_ions': 0, 'initxsecarray': 0, 'phfitel': 0, 'phfithion': 0, 'powlawxsec': 0, 'makeopacity': 0, 'makehydro': 0, 'setshells': 0, 'limitshell': 0, 'setpointers': 0,
+AUX_STRICT = {'writegrid': 0, 'setstarposition': 0, 'getvolume': 0, 'writesed': 0, 'writecontcube': 0, 'writetaunu': 0, 'integratepathtaunu': 0, 'bhmie': 0, 'getqs': 0, 'dust_xsec_assembly': 0, 'dust_emission_int': 0, 'grain_weights': 0, 'angle_tables': 0, 'active_cells': 0, 'fill_axes': 0, 'fill_mask': 0, 'opacity_block': 0, 'photo_rates': 0, 'photo_heat': 0, 'getoutershell': 0, 'ionizationdriver': 0, 'edensum': 0, 'addopacity': 0, 'putopacity': 0, 'inopacity': 0, 'getflux': 0, 'setprobden': 0, 'locate': 0, 'linearmap': 0, 'sortup': 0, 'gas_nu_mesh': 0, 'initial_ions': 0, 'sub_grid_read': 0, 'initxsecarray': 0, 'phfitel': 0, 'phfithion': 0, 'powlawxsec': 0, 'makeopacity': 0, 'makehydro': 0, 'setshells': 0, 'limitshell': 0, 'setpointers': 0,
               'setdustpdf': 1,      # call qHeat (lgQHeat branch)
               'getdustt': 1}        # resLineHeating (gas + resonance-line transfer branch)
 

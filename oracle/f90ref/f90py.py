@@ -1052,6 +1052,42 @@ class Unit:
             except TranslateError:
                 pass
             return ('io', ln, s)
+        if first == 'read' and len(toks) > 1 and toks[1].text == '(':
+            # list-directed READ(unit, *[, iostat=v]) items; items may be implied-DO lists
+            try:
+                close = _match_paren(toks, 1)
+                unit, star, iostat = None, False, None
+                for j, c in enumerate(_split_top(toks[2:close])):
+                    if len(c) >= 3 and c[0].kind == 'name' and c[1].text == '=':
+                        key = c[0].text.lower()
+                        if key == 'unit':
+                            unit = _expr_from(c[2:], s)
+                        elif key == 'fmt':
+                            star = len(c) == 3 and c[2].text == '*'
+                        elif key == 'iostat':
+                            iostat = _expr_from(c[2:], s)
+                        else:
+                            raise TranslateError('READ control item ' + key)
+                    elif j == 0:
+                        unit = _expr_from(c, s)
+                    elif j == 1:
+                        star = len(c) == 1 and c[0].text == '*'
+                    else:
+                        raise TranslateError('READ control list')
+                if unit is not None and star:
+                    items = [_io_item(it, s) for it in _split_top(toks[close + 1:]) if it]
+                    return ('read', ln, unit, iostat, items)
+            except TranslateError:
+                pass
+            return ('io', ln, s)
+        if first in ('backspace', 'rewind') and len(toks) >= 2:
+            try:
+                inner = toks[2:_match_paren(toks, 1)] if toks[1].text == '(' else toks[1:]
+                if len(inner) >= 3 and inner[0].kind == 'name' and inner[1].text == '=':
+                    inner = inner[2:]
+                return ('seek', ln, first, _expr_from(inner, s))
+            except TranslateError:
+                return ('io', ln, s)
         if first in ('write', 'read', 'open', 'close', 'rewind', 'backspace', 'inquire') and len(toks) > 1 and toks[1].text == '(':
             return ('io', ln, s)
         if first == 'allocate' and toks[1].text == '(':
@@ -1844,6 +1880,21 @@ class Gen:
             self.emit(out, ind, [f'_rt.unsupported({s[2]!r}, {ln})'])
         elif k == 'ionoop':
             self.emit(out, ind, [f'_rt.fio({s[2]!r})'])
+        elif k == 'read':
+            uc, _ = self.expr(s[2], sc, pre)
+            body: List[str] = []
+            self.read_items(s[4], sc, pre, body, 1 if s[3] is not None else 0)
+            self.emit(out, ind, pre + [f'_rd = _rt.fread_begin({uc}, {ln})'])
+            if s[3] is not None:             # iostat: 0, or -1 at the end of the file
+                ok = self.assign_lines(s[3], '0', Ty('i'), sc, pre)
+                eof = self.assign_lines(s[3], '-1', Ty('i'), sc, pre)
+                self.emit(out, ind, ['try:'] + body + ['    _rd.end()'] + ['    ' + l for l in ok] +
+                          ['except _rt.FortranEOF:'] + ['    ' + l for l in eof])
+            else:
+                self.emit(out, ind, body + ['_rd.end()'])
+        elif k == 'seek':
+            uc, _ = self.expr(s[3], sc, pre)
+            self.emit(out, ind, pre + [f'_rt.fseek({uc}, {s[2]!r})'])
         elif k == 'write':
             uc, _ = self.expr(s[2], sc, pre)
             items = [self.io_item(it, sc, pre) for it in s[3]]
@@ -1902,6 +1953,27 @@ class Gen:
         stc = self.expr(st, sc, pre)[0] if st is not None else '1'
         # the comprehension binds the loop variable in its own scope, like the implied DO
         return f'*[_x for {vname} in _rt.frange({loc}, {hic}, {stc}) for _x in ({parts},)]'
+
+    def read_items(self, items, sc: Scope, pre, out: List[str], ind: int):
+        """input items of a list-directed READ: every scalar target takes the next value of the record
+        stream; an implied DO becomes a loop over its (local) variable"""
+        for it in items:
+            if it[0] == 'item':
+                lcode, lty = self.expr(it[1], sc, pre)
+                if lty.rank > 0:
+                    raise TranslateError('whole-array input item')
+                want = 'c' if lty.base == 'c' else 'n'
+                for l in self.assign_lines(it[1], f'_rd.next({want!r})', None, sc, pre):
+                    out.append('    ' * ind + l)
+                continue
+            _, inner, var, lo, hi, st = it
+            r = sc.lookup_var(var)
+            if r is None or r[0] != 'local':
+                raise TranslateError(f'implied-DO variable {var} must be a local')
+            loc, hic = self.expr(lo, sc, pre)[0], self.expr(hi, sc, pre)[0]
+            stc = self.expr(st, sc, pre)[0] if st is not None else '1'
+            out.append('    ' * ind + f'for {r[2]} in _rt.frange({loc}, {hic}, {stc}):')
+            self.read_items(inner, sc, pre, out, ind + 1)
 
     def alloc_code(self, ty: Ty, dims: List[str]) -> str:
         if ty.base == 't':

@@ -717,3 +717,42 @@ def _initial_ions(self, active, lgElementOn, elementXref, nstages):
 
 
 AuxReference.initial_ions = _initial_ions
+
+
+def _sub_grid_read(self, list_text, file_text, mother_axes, nsub, lgGas, lgDust, R_in, R_out, symmetric=True):
+    """setSubGrids' own reading code (grid_mod.f90:1847-1857, 2028-2232; statement-range slice) on the text
+    of a sub-grid list (unit 71) and of ONE sub-grid density file (unit 72): list-directed READs, axes
+    rescaled from normalised coordinates, the routine's own `insanity` stops, the active-cell rule.
+    Returns dict(xAxis, yAxis, zAxis, active, nCells, motherP, Hden3, Ndust3) -- or raises what the
+    reference raises (rt.FortranStop for `print*; stop`, rt.FortranEOF for a READ past the end)."""
+    G, ref = self.G, self.ref
+    G.ngrids, G.lggas, G.lgdust = 2, bool(lgGas), bool(lgDust)
+    G.lgmultichemistry, G.lgmultidustchemistry, G.lg1d, G.lgecho, G.lgplaneionization = False, False, False, False, False
+    G.r_in, G.r_out = np.float32(R_in), np.float32(R_out)
+    G.taskid = 0
+    rt.bind_unit(71, list_text)
+    rt.bind_unit(72, file_text)
+    grids = np.empty(2, dtype=object)
+    for i, (nx, ny, nz) in enumerate([tuple(len(a) for a in mother_axes), nsub]):
+        g = ref.T_grid_type()
+        g.nx, g.ny, g.nz = int(nx), int(ny), int(nz)
+        g.xaxis = rt.wrap(np.zeros(nx, np.float32))
+        g.yaxis = rt.wrap(np.zeros(ny, np.float32))
+        g.zaxis = rt.wrap(np.zeros(nz, np.float32))
+        g.active = rt.wrap(np.zeros((nx, ny, nz), np.int64, order='F'))
+        g.elemabun = rt.wrap(np.zeros((1, 30), np.float32, order='F'))
+        g.ncells = 0
+        grids[i] = g
+    for a, src in zip((grids[0].xaxis, grids[0].yaxis, grids[0].zaxis), mother_axes):
+        a.a[:] = np.asarray(src, np.float32)
+    nx, ny, nz = nsub
+    H = rt.wrap(np.zeros((nx, ny, nz), np.float32, order='F'))
+    Nd = rt.wrap(np.zeros((nx, ny, nz), np.float32, order='F'))
+    with np.errstate(all='ignore'):
+        ref.p_sub_grid_read(rt.wrap(grids), H, Nd)
+    s = grids[1]
+    return dict(xAxis=s.xaxis.a.copy(), yAxis=s.yaxis.a.copy(), zAxis=s.zaxis.a.copy(), active=s.active.a.copy(),
+                nCells=int(s.ncells), motherP=int(s.motherp), Hden3=H.a.copy(), Ndust3=Nd.a.copy())
+
+
+AuxReference.sub_grid_read = _sub_grid_read

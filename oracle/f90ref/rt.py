@@ -246,6 +246,86 @@ def fwrite(unit, items):
     io_log.setdefault(int(unit), []).append(tuple(flat))
 
 
+# ---- list-directed READ ------------------------------------------------------------------------
+# The harness binds a unit number to the text of the file the reference would OPEN on it
+# (bind_unit); OPEN / CLOSE themselves do nothing.  A READ statement starts on a new record
+# (line), takes as many values as it has items -- continuing over the following records when
+# a line runs out -- and discards what is left of the last record it touched.  Values are separated
+# by blanks or commas; '...' / "..." delimit character values; end of file raises FortranEOF, which
+# the generated code turns into iostat = -1 (or lets propagate when the statement has no iostat).
+class FortranEOF(Exception):
+    pass
+
+
+class _InUnit:
+    def __init__(self, text):
+        import shlex
+        self.lines = []
+        for raw in text.split('\n'):
+            lex = shlex.shlex(raw, posix=True)
+            lex.whitespace += ','
+            lex.whitespace_split = True
+            lex.commenters = ''
+            try:
+                toks = list(lex)
+            except ValueError:
+                toks = raw.replace(',', ' ').split()
+            self.lines.append(toks)
+        while self.lines and not self.lines[-1]:
+            self.lines.pop()
+        self.pos = 0
+
+
+class _Reader:
+    def __init__(self, u, line):
+        self.u, self.line, self.col, self.started = u, line, 0, False
+
+    def next(self, want):
+        u = self.u
+        while True:
+            if u.pos >= len(u.lines):
+                raise FortranEOF(f'end of file in READ at line {self.line}')
+            row = u.lines[u.pos]
+            self.started = True
+            if self.col < len(row):
+                tok = row[self.col]
+                self.col += 1
+                if want == 'c':
+                    return tok
+                return float(tok.lower().replace('d', 'e'))
+            u.pos += 1
+            self.col = 0
+
+    def end(self):
+        u = self.u
+        if u.pos < len(u.lines) and (self.started or True):
+            u.pos += 1                    # the rest of the record is skipped
+
+
+io_in = {}        # unit -> _InUnit
+
+
+def bind_unit(unit, text):
+    io_in[int(unit)] = _InUnit(text)
+
+
+def fread_begin(unit, line):
+    u = io_in.get(int(unit))
+    if u is None:
+        raise NotImplementedError(f'READ on unit {unit} at line {line}: no file bound (rt.bind_unit)')
+    return _Reader(u, line)
+
+
+def fseek(unit, what):
+    u = io_in.get(int(unit))
+    if u is None:
+        return
+    if what == 'rewind':
+        u.pos = 0
+    elif u.pos > 0:
+        u.pos -= 1
+
+
 def fio(what):
     """OPEN / CLOSE: nothing to do, WRITE records are kept in io_log"""
     return None

@@ -513,6 +513,8 @@ static inline void j_add(Ctx *c, OrGrid *g, const Packet *pk, int32_t cell, floa
     }
     int64_t *Q = toDif ? g->JdifQ : g->JsteQ;
     if (Q) addq(c, &Q[idx], (int64_t)llrintf(len * g->invLenUnit));
+    int32_t *N = toDif ? g->JdifN : g->JsteN;
+    if (N) N[idx] += 1;                        /* single-threaded runs only (test aid) */
 }
 
 #define PS_RETURN   0   /* packet finished (escaped / dropped) */

@@ -50,6 +50,9 @@ typedef struct OrGrid {
     int64_t *JsteQ, *JdifQ, *escapedQ, *linePacketsQ;
     /* extra packets per cell of the resonance-line transfer (0:nCells), may be NULL */
     const int32_t *resLinePackets;
+    /* number of path segments added to every (cell, nu) element of Jste / Jdif (may be NULL): the
+     * n in the per-element error bound of a float32 running sum against the fixed-point tally */
+    int32_t *JsteN, *JdifN;
 } OrGrid;
 
 typedef struct OrParams {

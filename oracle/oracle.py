@@ -29,7 +29,8 @@ class OrGrid(C.Structure):
                 ("opacity", fp), ("scaOpac", fp), ("recPDF", fp), ("dustPDF", fp), ("linePDF", fp),
                 ("totalLines", fp), ("Tdust", fp), ("dustAbunIndex", ip),
                 ("Jste", fp), ("Jdif", fp), ("escapedPackets", fp), ("linePackets", fp),
-                ("JsteQ", lp), ("JdifQ", lp), ("escapedQ", lp), ("linePacketsQ", lp), ("resLinePackets", ip)]
+                ("JsteQ", lp), ("JdifQ", lp), ("escapedQ", lp), ("linePacketsQ", lp), ("resLinePackets", ip),
+                ("JsteN", ip), ("JdifN", ip)]
 
 
 class OrParams(C.Structure):
@@ -163,7 +164,8 @@ class Oracle:
     """Runs the CPU restatement on a mocassin_b200.model.Model-shaped object (duck typed:
     only attribute access, so the oracle does not import the product package)."""
 
-    def __init__(self, model, len_unit=None, fp32_tallies: bool = True, int_tallies: bool = True):
+    def __init__(self, model, len_unit=None, fp32_tallies: bool = True, int_tallies: bool = True,
+                 count_segments: bool = False):
         self.lib = load()
         self.m = m = model
         self._keep = []
@@ -241,6 +243,12 @@ class Oracle:
                     o["JdifQ"] = np.zeros(tshape, np.int64, order="F")
                     o["linePacketsQ"] = np.zeros(lshape, np.int64, order="F")
                     og.JdifQ, og.linePacketsQ = _p(o["JdifQ"], lp), _p(o["linePacketsQ"], lp)
+            if count_segments:                   # segments added per (cell, nu): out[iG-1]["JsteN"]
+                o["JsteN"] = np.zeros(tshape, np.int32, order="F")
+                og.JsteN = _p(o["JsteN"], ip)
+                if m.lgDebug:
+                    o["JdifN"] = np.zeros(tshape, np.int32, order="F")
+                    og.JdifN = _p(o["JdifN"], ip)
             self.out.append(o)
         self.G = G
         self.qphotCounts = np.zeros(m.nbins, np.int64)

@@ -667,3 +667,40 @@ def run_writers(outdir):
     ck.write_dust_grid(p("dustGrid.out"), m, lgMultiChemistry=True, totalDustMass=s["totalDustMass"])
     ck.write_photo_source(p("photoSource.out"), m, s["contShape"], s["TStellar"], s["LStar"], s["nPhotons"], s["spID"], s["tStep"])
     return {fn: [_norm(l) for l in open(p(fn)).read().splitlines()] for fn in GRID_FILES.values()}
+
+
+# ---------------------------------------------------------------------------------------------
+# per-element bound of the reference's float32 running sum against the fixed-point tally
+# ---------------------------------------------------------------------------------------------
+def j_error_bound(m, mode, n, unit_of):
+    """For every (cell, nu) element of Jste (and Jdif) of every grid: how far the folded fixed-point
+    tally may lie from the reference's sequential float32 sum.  With n_i segments added to element i,
+    each rounded to the unit u of the tally, and J the value itself:
+        |J_fixed - J_ref| <= n_i * u/2 * deltaE/dV(cell)  +  (n_i + 8) * 2^-24 * J
+    (quantisation of the n_i path lengths; one float32 rounding per addition of the running sum, two
+    per term, four in the fold).  n_i comes from the oracle, whose histories equal the reference's
+    packet for packet (tests/test_reference_pin.py).  Returns bound(iG, name, got, want) -> array."""
+    from oracle.oracle import Oracle
+
+    o = Oracle(m, count_segments=True, fp32_tallies=False)
+    if mode == "stellar":
+        o.transport(1, 0, n, seed=SEED)
+        dE = float(m.deltaE[1])
+    elif mode[0] == "stars":
+        for iStar in mode[1]:
+            o.transport(iStar, 0, n, seed=SEED)
+        dE = max(float(m.deltaE[i]) for i in mode[1])
+    elif mode == "reslines":
+        o.transport_reslines(1, seed=SEED)
+        dE = float(m.deltaE[1])
+    else:
+        o.transport(0, 0, n, seed=SEED, gpLoc=mode[1], cellLoc=list(mode[2]))
+        dE = float(m.deltaE[0])
+
+    def bound(iG, name, got, want):
+        N = o.out[iG - 1]["JsteN" if name == "Jste" else "JdifN"][1:].astype(np.float64)
+        dV = m.grids[iG - 1].cell_volumes(m.lgSymmetricXYZ).astype(np.float64)[1:, None]
+        u = float(unit_of(iG))
+        return N * 0.5 * u * dE / dV * (1.0 + 1e-6) + (N + 8.0) * 2.0 ** -24 * np.maximum(got, want)
+
+    return bound
