@@ -41,6 +41,8 @@ cudaError_t launch_merge_sets(unsigned long long *J0, unsigned long long *J1, si
                               unsigned int *E1, size_t nE, int *f0, int *f1, int nf, int blocks, cudaStream_t s);
 cudaError_t wf_launch_event(const WfArgs &w, bool multi, int ev, int blocks, cudaStream_t s);
 cudaError_t wf_launch_fly(const WfArgs &w, bool multi, int blocks, cudaStream_t s);
+cudaError_t wf_launch_escape_compact(const WfArgs &w, int blocks, cudaStream_t s);
+bool wf_esc_compact_built();
 cudaError_t wf_launch_sort(const WfArgs &w, bool multi, int numSMs, cudaStream_t s);
 int wf_fly_blocks_per_sm(bool multi);
 size_t wf_rec_bytes();
@@ -210,6 +212,7 @@ struct mcb200_ctx {
     unsigned int wave0Count = 0;
     bool wave0Exact = false;              // exact slots instead of appended records (measured slower)
     int wave0Blocks = 4;                  // CTAs per SM of the pre-ordered wave-0 emission
+    bool escCompact = true;               // option esc_compact (only in builds with MCB_ESC_COMPACT)
     int flyBatch = 8;                     // FLY kernel: lanes of a warp that must be idle before records are stored / claimed
     int64_t tailThreshold = 32768;        // alive packets below which the persistent kernel finishes the batch
     DevBuf<unsigned char> wfArgsDev;
@@ -834,6 +837,10 @@ int run_wavefront(mcb200_ctx *ctx, const TransportArgs &a, bool multi, int64_t m
     w.evList[0] = ctx->wfEv0.p; w.evList[1] = ctx->wfEv1.p; w.evList[2] = ctx->wfEv2.p; w.evList[3] = ctx->wfEv3.p;
     w.stepBudget = ctx->stepBudget < 1 ? 1 : ctx->stepBudget;
     w.flyBatch = ctx->flyBatch;
+    // compact escape entries: single grid, no viewing angles (the tally element is then known without
+    // the direction), no per-packet trace, element index + flag bit in 32 bits
+    w.escCompact = (wf_esc_compact_built() && ctx->escCompact && !multi && ctx->cfg.nAngleBins == 0 && !a.fates &&
+                    esize(ctx, ctx->grids[0]) < ((size_t)1 << 31)) ? 1 : 0;
     if (a.fates) { CU(ctx->wfSegs.alloc(n)); CU(ctx->wfSegs.zero(s)); w.t.segsArr = ctx->wfSegs.p; }
     w.hist = ctx->wfHist.p; w.cursor = ctx->wfCursor.p; w.nextFlight = ctx->wfNext.p;
     int flyBps = ctx->blocksPerSM > 0 ? ctx->blocksPerSM : wf_fly_blocks_per_sm(multi);
@@ -883,6 +890,14 @@ int run_wavefront(mcb200_ctx *ctx, const TransportArgs &a, bool multi, int64_t m
         unsigned int hc[5];
         CU(cudaMemcpyAsync(hc, ctx->wfCounts.p, sizeof(hc), cudaMemcpyDeviceToHost, s));
         CU(cudaStreamSynchronize(s));
+        if (w.escCompact && hc[1 + EV_ESCAPE]) {
+            // escapes end here: tallied from the compact entries, not carried into the next wave or the tail
+            w.inList = w.evList[EV_ESCAPE]; w.inCount = &w.evCount[EV_ESCAPE];
+            CU(wf_launch_escape_compact(w, evBlocks(hc[1 + EV_ESCAPE]), s));
+            CU(cudaMemsetAsync(&w.evCount[EV_ESCAPE], 0, sizeof(unsigned int), s));
+            ctx->lastLaunches++;
+            hc[1 + EV_ESCAPE] = 0;
+        }
         uint64_t alive = (uint64_t)hc[1] + hc[2] + hc[3] + hc[4];
         if (alive == 0) break;
         if ((int64_t)alive <= ctx->tailThreshold) {
@@ -2495,6 +2510,7 @@ int mcb200_set_option(mcb200_ctx *ctx, const char *name, int64_t value)
     }
     if (!strcmp(name, "exchange_dense")) { ctx->exchangeDense = value != 0; return MCB200_OK; }
     if (!strcmp(name, "exchange_allreduce")) { ctx->exchangeAllReduce = value != 0; return MCB200_OK; }
+    if (!strcmp(name, "esc_compact")) { ctx->escCompact = value != 0; return MCB200_OK; }
     if (!strcmp(name, "epoch")) { ctx->epoch = value; return MCB200_OK; }
     if (!strcmp(name, "pdf_slabs")) { ctx->pdfSlabs = value != 0; return MCB200_OK; }
     if (!strcmp(name, "exchange_p2p")) { ctx->p2pMode = (int)value; if (ctx->p2pState < 0) ctx->p2pState = 0; return MCB200_OK; }

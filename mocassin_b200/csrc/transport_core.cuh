@@ -575,15 +575,20 @@ struct Transport {
         float opacEarly = 0.f;
         if (early) opacEarly = __ldg(&a.g1.opacity[L.planeBase]);
         bool snapped = false;
-        // Dense single grid, fast path of the wall stage: the three wall distances with none of the
+        // Single grid, fast path of the wall stage: the three wall distances with none of the
         // special cases.  Those -- an axis sitting on its wall (snap, drop on the outermost wall, the
         // zero distance replaced by the axis end, :1263-1432) or a non-finite distance -- all begin
         // with a moving axis whose |distance| is not >= 1e-10; when no axis is in that state the
         // generic stage below reduces to exactly these lines, and it is skipped.  Otherwise nothing
         // has been modified yet and the generic stage runs from scratch.
         bool fast = false;
-        if (MCB_FASTWALL && kInc && !sym()) {
+        if (MCB_FASTWALL && !MULTI) {
             const DevGrid &g = a.g1;
+            if (sym()) {                 // :1248-1261, as at the head of the generic stage (idempotent)
+                if (L.rx <= g.x1) { L.vx = fabsf(L.vx); L.rx = g.x1; }
+                if (L.ry <= g.y1) { L.vy = fabsf(L.vy); L.ry = g.y1; }
+                if (L.rz <= g.z1) { L.vz = fabsf(L.vz); L.rz = g.z1; }
+            }
             const bool px = L.vx > 1.e-10f, py = L.vy > 1.e-10f, pz = L.vz > 1.e-10f;
             const bool mx = px || L.vx < -1.e-10f, my = py || L.vy < -1.e-10f, mz = pz || L.vz < -1.e-10f;
             const float dx = div_rn(__ldg(&g.xWall[px ? L.xP : L.xP - 1]) - L.rx, L.vx, L.iax);
@@ -595,7 +600,7 @@ struct Transport {
                 fast = true;
                 posx = px; posy = py; posz = pz;
                 dSx = mx ? dx : 1.e35f; dSy = my ? dy : 1.e35f; dSz = mz ? dz : 1.e35f;
-                cell = 1;
+                cell = kInc ? 1 : active_at<DENSE>(g, L.xP, L.yP, L.zP);
             }
         }
         for (int j = 1; !fast; ++j) {

@@ -134,6 +134,7 @@ struct WfArgs {
     unsigned int *evCount;               // [EV_COUNT]
     int directA;                         // wave 0 with pre-ordered packets: EMIT writes recA directly, no sort
     int flyBatch;                        // idle lanes of a warp that trigger the store/claim pass of the FLY kernel
+    int escCompact;                      // ESCAPE events carry the tally element instead of the record position
     int stepBudget;                      // cell crossings per flight per wave (longer flights continue
                                          // in the next wave, so one straggler cannot hold a wave open)
     unsigned int *hist, *cursor;         // [nbins+1]

@@ -125,6 +125,9 @@ __global__ void __launch_bounds__(kThreads) wf_event_kernel(const __grid_constan
 // atomic per chunk, records of the chunk prefetched into L2) and cross cells until the next
 // event; ended flights are written back in place and their positions staged per warp in
 // shared memory, flushed 32 at a time (one global atomic per 32 events, coalesced stores).
+#ifndef MCB_ESC_COMPACT
+#define MCB_ESC_COMPACT 1                // A/B build switch: compact escape entries (see wf_escape_compact_kernel)
+#endif
 #ifndef MCB_FLY_OCC
 #define MCB_FLY_OCC 4                    // resident CTAs per SM the FLY kernel is compiled for (A/B: build.py --define)
 #endif
@@ -158,10 +161,26 @@ __global__ void __launch_bounds__(kThreads, MCB_FLY_OCC) wf_fly_kernel(const __g
         const unsigned int waitM = ~(flyM | doneM);
         if (waitM && ((unsigned int)__popc(waitM) >= batch || flyM == 0u)) {
             const bool ended = L.phase == PH_EMIT || L.phase == PH_SCATTER || L.phase == PH_ESCAPE || L.phase == PH_CONT;
+#if MCB_ESC_COMPACT
+            unsigned int escVal = 0u;
+#endif
             // flights that ended: write the record back and stage its position
             if (__ballot_sync(FULL, ended)) {
                 if (ended) {
                     unsigned int k;
+#if MCB_ESC_COMPACT
+                    if (!MULTI && w.escCompact && L.phase == PH_ESCAPE) {
+                        // an escaping packet is finished: nothing of its record is needed again but the
+                        // element of the escape tally it counts into, which goes on the event list in
+                        // place of the record's position -- no write-back, and the ESCAPE pass of the
+                        // next wave reads 4 contiguous bytes per packet instead of a 64-byte record
+                        const uint4 *src = reinterpret_cast<const uint4 *>(&w.recA[pos]);
+                        const uint4 c2 = src[2], c3 = src[3];
+                        k = c2.z;
+                        escVal = c2.w + (unsigned int)(w.t.g1.nCells + 1) * (c3.x & 0xffffu);
+                        if ((c2.y >> 19) >= (unsigned int)kRecursionLimit) escVal |= 0x80000000u;
+                    } else
+#endif
                     rec_store_fly<MULTI>(w.recA, w.recxA, L, pos, k);
                     smem[C_SEGMENTS * kThreads + threadIdx.x] += L.segs;   // this flight's cell crossings
                     if (w.t.segsArr) w.t.segsArr[k] += L.segs;
@@ -172,7 +191,12 @@ __global__ void __launch_bounds__(kThreads, MCB_FLY_OCC) wf_fly_kernel(const __g
                     const int ph = ev == EV_EMIT ? PH_EMIT : ev == EV_SCATTER ? PH_SCATTER : ev == EV_ESCAPE ? PH_ESCAPE : PH_CONT;
                     unsigned int m = __ballot_sync(FULL, L.phase == ph);
                     if (!m) continue;
+#if MCB_ESC_COMPACT
+                    if (L.phase == ph) stage[ev * kStage + nStaged[ev] + __popc(m & ((1u << lane) - 1u))] =
+                        (ev == EV_ESCAPE && !MULTI && w.escCompact) ? escVal : pos;
+#else
                     if (L.phase == ph) stage[ev * kStage + nStaged[ev] + __popc(m & ((1u << lane) - 1u))] = pos;
+#endif
                     nStaged[ev] += __popc(m);
                     __syncwarp();
                     if (nStaged[ev] >= 32) {             // flush 32 staged positions
@@ -245,6 +269,42 @@ __global__ void __launch_bounds__(kThreads, MCB_FLY_OCC) wf_fly_kernel(const __g
         }
     }
     scratch_flush(w.t, smem);
+}
+
+// ---- ESCAPE pass on compact entries (single grid, no viewing angles, no trace): entry = index of
+// the escape-tally element (origin cell, nu) the packet counts into, bit 31 = the packet had reached
+// the generation limit (energyPacketDriver counts it as trapped too).  Entries arrive in frequency
+// order and most stellar packets share the star's cell: equal targets are counted once per warp.
+__global__ void __launch_bounds__(256) wf_escape_compact_kernel(const __grid_constant__ WfArgs w)
+{
+    const unsigned int n = *w.inCount;
+    unsigned int nEsc = 0, nTrap = 0;
+    const unsigned int stride = gridDim.x * blockDim.x;
+    const unsigned int rounds = (n + stride - 1) / stride;
+    for (unsigned int it = 0; it < rounds; ++it) {
+        unsigned int i = it * stride + blockIdx.x * blockDim.x + threadIdx.x;
+        const bool valid = i < n;
+        const unsigned int e = valid ? w.inList[i] : 0xffffffffu;
+        const unsigned int peers = __match_any_sync(0xffffffffu, e & 0x7fffffffu);
+        if (valid) {
+            if ((int)(threadIdx.x & 31u) == __ffs(peers) - 1) atomicAdd(&w.t.g1.escQ[e & 0x7fffffffu], (unsigned int)__popc(peers));
+            ++nEsc;
+            nTrap += e >> 31;
+        }
+    }
+    for (int d = 16; d > 0; d >>= 1) { nEsc += __shfl_xor_sync(0xffffffffu, nEsc, d); nTrap += __shfl_xor_sync(0xffffffffu, nTrap, d); }
+    if ((threadIdx.x & 31u) == 0u) {
+        if (nEsc) atomicAdd(&w.t.counters[C_ESCAPED], (unsigned long long)nEsc);
+        if (nTrap) atomicAdd(&w.t.counters[C_TRAPPED], (unsigned long long)nTrap);
+    }
+}
+
+bool wf_esc_compact_built() { return MCB_ESC_COMPACT != 0; }
+
+cudaError_t wf_launch_escape_compact(const WfArgs &w, int blocks, cudaStream_t s)
+{
+    wf_escape_compact_kernel<<<blocks, 256, 0, s>>>(w);
+    return cudaGetLastError();
 }
 
 // ---- counting sort of the ready flights by frequency bin: recB -> recA -------------------

@@ -21,11 +21,13 @@ List-directed input is read the way Fortran reads it (:class:`ListReader`): a RE
 record, runs on over the following records until it has all its items, and drops what is left of
 the last record it touched.  This matters: examples/multigridgasdust ships a 4-column sub-grid file
 (`x y z Hden`) although a gas+dust run reads FIVE items per cell (`x, y, z, Hden, Ndust`,
-grid_mod.f90:2103) -- the reference takes the fifth from the next record, loses that record, and
-runs off the end of the file half way through the sub-grid.  The loader reproduces that
-(:class:`DeckError`, as the reference's run-time error stops the run) unless `pad_missing_ndust`
-asks for the evident intent, Ndust = 0 inside the sub-grid.  examples/multigridgas (gas only, four
-items per cell) loads exactly as shipped.
+grid_mod.f90:2103) -- the reference takes the fifth from the next record and loses the rest of that
+record, so every second row is skipped and the coordinates stop lining up with the loop indices;
+its own sanity check then stops the run ("setSubGrids: insanity occurred in setting yAxis",
+:2128-2133; executed and confirmed by running the reference's reading code on the shipped files,
+tests/golden/ref_aux_subgrid_multigridgasdust.npz).  The loader reproduces that
+(:class:`DeckError`) unless `pad_missing_ndust` asks for the evident intent, Ndust = 0 inside the
+sub-grid.  examples/multigridgas (gas only, four items per cell) loads exactly as shipped.
 """
 from __future__ import annotations
 
@@ -336,3 +338,99 @@ def load_multigrid_deck(run_dir: str, share_dir: str, input_file: str = "input.i
                   ph1=ph1, ph2=ph2, ionEdge=ionEdge[:nEdges], gridList=read_grid_list(resolve(gridList), nGrids),
                   recPDF_kind="stand-in (workloads.recombination_cdf at TeStart; emissionDriver is the host solver's)")
     return model, tables, d
+
+
+# ---------------------------------------------------------------------------------------
+# fixture format (tests/golden/deck_multigridgas.npz, deck_multigridgasdust.npz): the decks' files and
+# the atomic / optical data do not travel to the GPU box
+# ---------------------------------------------------------------------------------------
+def multideck_to_arrays(model: Model, tables: dict, d) -> dict:
+    import json
+
+    from .gasdeck import _XT_SCALARS
+
+    xt = tables["xsec"]
+    scal = dict(lgSymmetricXYZ=bool(d.lgSymmetricXYZ), lgIsotropic=bool(d.lgIsotropic), lgDust=bool(model.lgDust),
+                nPhotons=int(d.nPhotons), R_out=float(d.R_out), ionEdge1=float(model.ionEdge1), TeStart=float(model.grids[0].Te[1]),
+                starPosition=list(d.starPosition), nGrids=len(model.grids), recPDF_kind=tables["recPDF_kind"],
+                motherP=[int(getattr(g, "motherP", 0)) for g in model.grids],
+                **{k: int(getattr(xt, k)) for k in _XT_SCALARS})
+    out = dict(nuArray=model.nuArray, cdf=model.inSpectrumProbDen[1], deltaE=model.deltaE, xSecArray=xt.xSecArray,
+               lgElementOn=xt.lgElementOn, elementXref=xt.elementXref, elementP=xt.elementP, nShells=xt.nShells,
+               elemAbun=tables["elemAbun"], recRow=model.grids[0].recPDF[1], totalLines1=model.grids[0].totalLines[1:2],
+               starPositionAbs=model.starPosition, starIndeces=model.starIndeces,
+               deck_json=np.frombuffer(json.dumps(scal).encode(), dtype=np.uint8))
+    for i, g in enumerate(model.grids, start=1):
+        out.update({f"g{i}_xAxis": g.xAxis, f"g{i}_yAxis": g.yAxis, f"g{i}_zAxis": g.zAxis, f"g{i}_active": g.active,
+                    f"g{i}_Hden": g.Hden, f"g{i}_nCells": np.asarray([g.nCells], I32)})
+        if model.lgDust:
+            out[f"g{i}_Ndust"] = g.Ndust
+    if model.lgDust:
+        t = tables["dust"]
+        out.update(grainWeight=t["grainWeight"], grainAbun1=t["grainAbun1"], TdustSublime=t["TdustSublime"],
+                   dustScaXsecP=t["dustScaXsecP"], dustAbsXsecP=t["dustAbsXsecP"], gSca=t["gSca"])
+    return out
+
+
+def multideck_from_arrays(a: dict):
+    """Inverse of multideck_to_arrays: (Model, tables, scalars) without the deck's files."""
+    import json
+
+    from .gasdeck import _XT_SCALARS
+    from .opacity import XSecTables
+
+    s = json.loads(bytes(a["deck_json"]).decode())
+    nu = np.asarray(a["nuArray"], dtype=F32)
+    nbins = nu.shape[0]
+    xt = XSecTables(xSecArray=np.asarray(a["xSecArray"], F32), lgElementOn=np.asarray(a["lgElementOn"], I32),
+                    elementXref=np.asarray(a["elementXref"], I32), elementP=np.asfortranarray(a["elementP"], dtype=I32),
+                    nShells=np.asfortranarray(a["nShells"], dtype=I32), **{k: int(s[k]) for k in _XT_SCALARS})
+    on, xref = xt.lgElementOn, xt.elementXref
+    elemAbun = np.asfortranarray(a["elemAbun"], dtype=F32)
+    lgDust = bool(s["lgDust"])
+    dustT = None
+    if lgDust:
+        dustT = dict(grainWeight=np.asarray(a["grainWeight"], F32), grainAbun1=np.asarray(a["grainAbun1"], F32),
+                     TdustSublime=np.asarray(a["TdustSublime"], F32), dustScaXsecP=np.asfortranarray(a["dustScaXsecP"], dtype=I32),
+                     dustAbsXsecP=np.asfortranarray(a["dustAbsXsecP"], dtype=I32), gSca=np.asarray(a["gSca"], F32))
+        dustT["nSp"], dustT["nSz"] = dustT["dustScaXsecP"].shape
+    grids, per_grid = [], []
+    for i in range(1, int(s["nGrids"]) + 1):
+        act = np.asfortranarray(a[f"g{i}_active"], dtype=I32)
+        g = Grid(xAxis=np.asarray(a[f"g{i}_xAxis"], F32), yAxis=np.asarray(a[f"g{i}_yAxis"], F32),
+                 zAxis=np.asarray(a[f"g{i}_zAxis"], F32), active=act, nCells=int(a[f"g{i}_nCells"][0]))
+        g.motherP = int(s["motherP"][i - 1])
+        g.Hden = np.asarray(a[f"g{i}_Hden"], F32)
+        g.Te = np.zeros(g.nCells + 1, dtype=F32)
+        g.Te[1:] = F32(s["TeStart"])
+        g.Ne = g.Hden.copy()
+        ionDen = G.initial_ion_state(g.nCells, on, xref, int(on.sum()), xt.nstages)
+        abIndex = np.ones(g.nCells + 1, dtype=I32)
+        entry = dict(ionDen=ionDen, den=xt.species_densities(ionDen, elemAbun, abIndex, g.Hden), abIndex=abIndex, dust=None)
+        if lgDust:
+            g.Ndust = np.asarray(a[f"g{i}_Ndust"], F32)
+            g.dustAbunIndex = np.ones(g.nCells + 1, dtype=I32)
+            g.Tdust = np.full((dustT["nSp"] + 1, dustT["nSz"] + 1, g.nCells + 1), F32(50.0), dtype=F32, order="F")
+            entry["dust"] = dict(Ndust=g.Ndust, Tdust=g.Tdust, dustAbunIndex=None, grainWeight=dustT["grainWeight"],
+                                 dustScaXsecP=dustT["dustScaXsecP"], dustAbsXsecP=dustT["dustAbsXsecP"])
+        g.recPDF = np.zeros((g.nCells + 1, nbins), dtype=F32, order="F")
+        g.recPDF[1:, :] = np.asarray(a["recRow"], F32)[None, :]
+        g.totalLines = np.zeros(g.nCells + 1, dtype=F32)
+        g.totalLines[1:] = F32(a["totalLines1"][0])
+        grids.append(g)
+        per_grid.append(entry)
+    kw = {}
+    if lgDust:
+        grainAbun = np.zeros((1, dustT["nSp"]), dtype=F32, order="F")
+        grainAbun[0, :] = dustT["grainAbun1"]
+        kw = dict(gSca=dustT["gSca"], nSpeciesMax=dustT["nSp"], nSizes=dustT["nSz"], nSpeciesPart=np.asarray([dustT["nSp"]], I32),
+                  grainAbun=grainAbun, dustComPoint=np.asarray([1], I32), TdustSublime=dustT["TdustSublime"])
+    model = Model(grids=grids, nbins=nbins, nuArray=nu,
+                  inSpectrumProbDen=np.stack([np.zeros(nbins, F32), np.asarray(a["cdf"], F32)]).astype(F32),
+                  deltaE=np.asarray(a["deltaE"], dtype=F32), starPosition=np.asarray(a["starPositionAbs"], dtype=F32),
+                  starIndeces=np.asarray(a["starIndeces"], dtype=I32), lgDust=lgDust, lgGas=True,
+                  lgSymmetricXYZ=bool(s["lgSymmetricXYZ"]), lgIsotropic=bool(s["lgIsotropic"]), R_out=float(s["R_out"]),
+                  ionEdge1=float(s["ionEdge1"]), **kw)
+    tables = dict(xsec=xt, bands=xt.band_list(nbins), grids=per_grid, elemAbun=elemAbun, widFlx=wid_flx(nu),
+                  nstages=xt.nstages, lgElementOn=on, elementXref=xref, dust=dustT, recPDF_kind=s["recPDF_kind"])
+    return model, tables, s

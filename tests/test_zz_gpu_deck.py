@@ -200,3 +200,30 @@ def test_c_host_example_runs_on_the_device(cuda_lib, tmp_path):
     assert r.returncode == 0, r.stderr
     out = subprocess.run([str(exe)], capture_output=True, text=True, timeout=300)
     assert out.returncode == 0 and out.stdout.strip().endswith("OK"), out.stdout + out.stderr
+
+
+def test_converged_deck_run_writes_the_files_the_oracle_run_wrote(cuda_lib, tmp_path):
+    """benchmarks/dust/1D/p0tau10 to convergence on the device through scripts/run_dust_deck.py (10 Lucy
+    iterations, autoPackets 1e5 -> 6.4e6 packets): output/SED.out, summary.out and tauNu.out are BYTE
+    FOR BYTE the files the same script wrote with the CPU oracle standing in for the engine
+    (profiles/r01_dust_deck_p0tau10_oracle_*.out) -- every packet history, temperature and
+    convergence decision of all ten iterations included."""
+    import subprocess
+
+    out = tmp_path / "output"
+    res = subprocess.run([sys.executable, os.path.join(ROOT, "scripts", "run_dust_deck.py"), "--golden",
+                          os.path.join(GOLD, "deck_p0tau10.npz"), "--out", str(out)], capture_output=True, text=True, cwd=ROOT)
+    assert res.returncode == 0, res.stderr[-2000:]
+    import json
+
+    rows = [json.loads(x) for x in res.stdout.strip().splitlines()]
+    want = [json.loads(x) for x in open(os.path.join(ROOT, "profiles", "r01_dust_deck_p0tau10_oracle.jsonl")) if x.startswith("{")]
+    assert len(rows) == len(want) == 11
+    for a, b in zip(rows[:-1], want[:-1]):
+        for k in ("iteration", "converged_pct", "nPhotons", "segments", "nAbs", "nSca"):
+            assert a[k] == b[k], (a["iteration"], k)
+    assert rows[-1]["Tdust_along_x"] == want[-1]["Tdust_along_x"] and rows[-1]["escaped_packets"] == want[-1]["escaped_packets"]
+    for fn in ("SED", "summary", "tauNu"):
+        got = (out / f"{fn}.out").read_bytes()
+        ref = open(os.path.join(ROOT, "profiles", f"r01_dust_deck_p0tau10_oracle_{fn}.out"), "rb").read()
+        assert got == ref, fn
