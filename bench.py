@@ -238,11 +238,13 @@ def run_reference(args):
         "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         # the same config as the b200 arm; each step here is a bounded sample of it (cpu_baseline.sample)
-        "config": workload_config(args, default_packets(args)),
+        "config": dict(workload_config(args, default_packets(args)), sample_packets_per_step=sample,
+                       note="same workload; every step of this arm transports a bounded sample of it (a rate metric)"),
         "cpu_baseline": {"value": value, "unit": "packets/s", "cores": cores, "kind": "port",
                          "sample_packets_per_step": sample,
                          "sample": f"{sample} packets/step x {args.steps} steps of the same {args.grid}^3 workload, "
-                                   f"oracle port (-O2), {cores} threads; table build {build_s:.0f}s untimed"},
+                                   f"oracle port (-O2, detmath instead of libm: same algorithm as the CUDA path), {cores} threads "
+                                   f"sharing the integer tallies through atomics; table build {build_s:.0f}s untimed"},
         "e2e": {"value": value, "unit": "packets/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "segments_per_packet": segs / (sample * args.steps),
     }
@@ -392,7 +394,7 @@ def run_b200(args):
     if sampler:
         sampler.mark()
     t0 = time.perf_counter()
-    kms, tms, segs, flights, launches, waves = 0.0, 0.0, 0, 0, 0, 0
+    kms, tms, segs, flights, launches, waves, fms = 0.0, 0.0, 0, 0, 0, 0, 0.0
     for _ in range(args.steps):
         ts = time.perf_counter()
         c = step()
@@ -400,6 +402,7 @@ def run_b200(args):
         kms += c["kernel_ms"]
         tms += c["total_ms"] if world == 1 else wall_ms      # N>1: include the all-reduce + fold
         segs += c["nSegments"]; flights += c["nFlights"]; launches += c["nLaunches"]; waves += c["nWaves"]
+        fms += c["fly_ms"]
     torch.cuda.synchronize()
     if world > 1:
         dist.barrier()
@@ -503,9 +506,21 @@ def run_b200(args):
     peak, peak_kind = measured_peak()
     ach = ALG_BYTES_PER_SEGMENT * segs / (kms / 1e3) / 1e9        # rank 0's kernel
     tr = ncu_traffic()
+    # `achieved`: algorithmic bytes of one mcb200_transport call / CUDA-event time of ALL its kernels (the
+    # wave-front pipeline: FLY + event + sort kernels, on the library stream); `fly_kernel`: the same bytes
+    # over the device time of the cell-crossing kernel wf_fly_kernel alone (events around each of its
+    # launches).  `traffic` is not measured by this run: it is the dram__bytes_read+write sum of one
+    # `ncu --set full` pass over the same command, kept in profiles/transport_traffic.json with its source.
+    fly_ach = ALG_BYTES_PER_SEGMENT * segs / (fms / 1e3) / 1e9 if fms > 0 else None
     roofline = {"bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak,
-                "traffic": (tr or {}).get("dram_bytes_per_launch"), "peak_kind": f"of {peak_kind}",
-                "kernel": "mcb::wf_fly_kernel<false> (+ event/sort kernels of the wave-front pipeline)", "algorithmic_bytes_per_segment": ALG_BYTES_PER_SEGMENT,
+                "traffic": (tr or {}).get("dram_bytes_per_launch"), "traffic_source": (tr or {}).get("source"),
+                "peak_kind": f"of {peak_kind}",
+                "kernel": "all kernels of one mcb200_transport call (wave-front pipeline: mcb::wf_fly_kernel + "
+                          "wf_event_kernel<EMIT|SCATTER|CONT> + wf_escape_compact_kernel + sort kernels)",
+                "fly_kernel": {"name": "mcb::wf_fly_kernel<false,true,2>", "ms_per_launch": fms / args.steps,
+                               "share_of_call": fms / kms if kms > 0 else None, "achieved": fly_ach,
+                               "frac": fly_ach / peak if fly_ach else None},
+                "algorithmic_bytes_per_segment": ALG_BYTES_PER_SEGMENT,
                 "segments_per_launch": segs / args.steps, "kernel_ms_per_launch": kms / args.steps,
                 "segments_per_s": segs / (kms / 1e3)}
     access = access_roofline(eng, g, nb, segs / (kms / 1e3)) if world == 1 else None
@@ -582,7 +597,8 @@ def cpu_baseline(args, eng, model, g):
     sample = int(max(400000, min(rate * args.cpu_seconds, 200_000_000)))
     t = time.time(); c = o.transport_mt(1, 400000, sample, seed=SEED, threads=cores); dt = time.time() - t
     return {"value": sample / dt, "unit": "packets/s", "cores": cores, "kind": "port",
-            "sample": f"{sample} packets of the same workload in {dt:.1f}s, oracle port (-O2) on {cores} threads",
+            "sample": f"{sample} packets of the same workload in {dt:.1f}s, oracle port (-O2, detmath instead of libm) on "
+                      f"{cores} threads sharing the integer tallies through atomics",
             "segments_per_packet": c["nSegments"] / sample}
 
 

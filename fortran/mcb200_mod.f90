@@ -27,6 +27,7 @@ module mcb200_mod
              & nFlights, nEscaped, nEarlyEscaped
         real(c_double)     :: Qphot, kernel_ms, total_ms
         integer(c_int64_t) :: nLaunches, nWaves
+        real(c_double)     :: fly_ms
     end type mcb200_counters
 
     type(c_ptr), save :: mcb_ctx = c_null_ptr

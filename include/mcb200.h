@@ -77,6 +77,7 @@ typedef struct mcb200_counters {
     double  total_ms;              /* device time transport kernel + fold epilogue        */
     int64_t nLaunches;             /* kernels launched by this call (transport + fold)    */
     int64_t nWaves;                /* wave-front schedule: waves (0 = persistent kernel)  */
+    double  fly_ms;                /* wave-front schedule: device time of the cell-crossing (FLY) kernels alone */
 } mcb200_counters;
 
 /* ---- lifecycle ---------------------------------------------------------------- */

@@ -24,7 +24,7 @@ class Counters(C.Structure):
     _fields_ = [(n, C.c_int64) for n in (
         "nPackets", "nAbs", "nSca", "trapped", "nLinePackets", "nDropped", "nSegments", "nFlights",
         "nEscaped", "nEarlyEscaped")] + [("Qphot", C.c_double), ("kernel_ms", C.c_double), ("total_ms", C.c_double),
-                ("nLaunches", C.c_int64), ("nWaves", C.c_int64)]
+                ("nLaunches", C.c_int64), ("nWaves", C.c_int64), ("fly_ms", C.c_double)]
 
     def as_dict(self):
         return {n: getattr(self, n) for n, _ in self._fields_}

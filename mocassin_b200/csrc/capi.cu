@@ -69,6 +69,7 @@ cudaError_t launch_opacity(const OpacityArgs &A, cudaStream_t s);
 cudaError_t launch_esc_compact(unsigned int *Q, size_t off, size_t len, unsigned long long *list,
                                unsigned long long *count, unsigned long long capacity, int clear, int blocks,
                                cudaStream_t s);
+cudaError_t launch_esc_clear_list(unsigned int *Q, const unsigned long long *list, unsigned long long n, int blocks, cudaStream_t s);
 cudaError_t launch_esc_scatter(unsigned int *Q, size_t total, const unsigned long long *list, unsigned long long n,
                                int blocks, cudaStream_t s);
 cudaError_t launch_sed_sum(const unsigned int *escQ, size_t nR, int firstPlane, int nPlanes,
@@ -221,6 +222,7 @@ struct mcb200_ctx {
     DevBuf<unsigned int> resPrefix;
     DevBuf<unsigned short> wfFlyKey;
     DevBuf<unsigned long long> wfNext;
+    std::vector<cudaEvent_t> flyEv;       // start/stop of the FLY kernel of every wave (mcb200_counters.fly_ms)
     int lastWaves = 0, lastLaunches = 0, lastFoldLaunches = 0, rangeFoldLaunches = 0;
     int aggSteps = 0, batch = 12;
     bool trace = false;
@@ -793,25 +795,26 @@ int esc_compact(mcb200_ctx *ctx, GridState &g, int set, int64_t *nEntries)
     auto ranges = touched_ranges(flag);
     const int blocks = ctx->numSMs * 8;
     CU(ctx->escCount.alloc(1));
-    // pass 1: count; pass 2: fill and clear
-    for (int pass = 0; pass < 2; ++pass) {
+    // One scan of the touched planes: the non-zero entries go into the list the previous call sized
+    // (with head room) and are NOT cleared yet -- an overflow only counts, and the scan is repeated
+    // once with a longer list; then the listed entries are cleared through the list.
+    unsigned long long n = 0;
+    for (int attempt = 0; attempt < 2; ++attempt) {
         CU(ctx->escCount.zero(s));
-        unsigned long long cap = pass ? ctx->escList.n / 2 : 0;
+        const unsigned long long cap = ctx->escList.n / 2;
         for (auto &rg : ranges)
             for (int ang = 0; ang <= ctx->cfg.nAngleBins; ++ang) {
                 size_t off = nR * ((size_t)rg.first + (size_t)(nb + 1) * (size_t)ang);
                 size_t len = (size_t)(rg.second - rg.first + 1) * nR;
-                CU(launch_esc_compact(Q, off, len, pass ? ctx->escList.p : nullptr, ctx->escCount.p, cap, pass, blocks, s));
+                CU(launch_esc_compact(Q, off, len, cap ? ctx->escList.p : nullptr, ctx->escCount.p, cap, 0, blocks, s));
             }
-        unsigned long long n = 0;
         CU(cudaMemcpyAsync(&n, ctx->escCount.p, 8, cudaMemcpyDeviceToHost, s));
         CU(cudaStreamSynchronize(s));
-        if (!pass) {
-            if (ctx->escList.n < 2 * n || ctx->escList.n > 8 * n + 1024) CU(ctx->escList.alloc((size_t)(2 * n > 2 ? 2 * n : 2)));
-        } else {
-            *nEntries = (int64_t)n;
-        }
+        if (n <= cap) break;
+        CU(ctx->escList.alloc((size_t)(2 * (n + n / 4 + 1024))));
     }
+    CU(launch_esc_clear_list(Q, ctx->escList.p, n, blocks, s));
+    *nEntries = (int64_t)n;
     return MCB200_OK;
 }
 
@@ -884,7 +887,14 @@ int run_wavefront(mcb200_ctx *ctx, const TransportArgs &a, bool multi, int64_t m
         sorted = false;
         CU(cudaMemsetAsync(w.evCount, 0, 4 * sizeof(unsigned int), s));
         CU(ctx->wfNext.zero(s));
+        if (ctx->flyEv.size() < 2 * (size_t)(ctx->lastWaves + 1)) {
+            cudaEvent_t e0, e1;
+            CU(cudaEventCreate(&e0)); CU(cudaEventCreate(&e1));
+            ctx->flyEv.push_back(e0); ctx->flyEv.push_back(e1);
+        }
+        CU(cudaEventRecord(ctx->flyEv[2 * ctx->lastWaves], s));
         CU(wf_launch_fly(w, multi, flyBlocks, s));
+        CU(cudaEventRecord(ctx->flyEv[2 * ctx->lastWaves + 1], s));
         ctx->lastLaunches += 4;
         ctx->lastWaves++;
         unsigned int hc[5];
@@ -1163,6 +1173,11 @@ int run_transport(mcb200_ctx *ctx, int iStar, int difGrid, const int32_t *cellLo
         out->total_ms = ms;
         out->nLaunches = ctx->lastLaunches;
         out->nWaves = ctx->lastWaves;
+        out->fly_ms = 0.0;
+        for (int wv = 0; wv < ctx->lastWaves && 2 * (size_t)wv + 1 < ctx->flyEv.size(); ++wv) {
+            float t = 0.f;
+            if (cudaEventElapsedTime(&t, ctx->flyEv[2 * wv], ctx->flyEv[2 * wv + 1]) == cudaSuccess) out->fly_ms += t;
+        }
     }
     ctx->pending = true;
     if (ctx->tallySet == 1) ctx->pending2 = true;
@@ -1429,6 +1444,7 @@ int mcb200_destroy(mcb200_ctx *ctx)
     if (ctx->sideStream) { cudaStreamSynchronize(ctx->sideStream); cudaStreamDestroy(ctx->sideStream); }
     if (ctx->sideEv0) cudaEventDestroy(ctx->sideEv0);
     if (ctx->sideEv1) cudaEventDestroy(ctx->sideEv1);
+    for (auto e : ctx->flyEv) cudaEventDestroy(e);
     if (ctx->sparseHost) cudaFreeHost(ctx->sparseHost);
     for (auto &g : ctx->grids) p2p_close(g, ctx->rank);
     if (ctx->comm) { nccl_api().CommDestroy(ctx->comm); ctx->comm = nullptr; }

@@ -232,6 +232,20 @@ cudaError_t launch_esc_compact(unsigned int *Q, size_t off, size_t len, unsigned
     return cudaGetLastError();
 }
 
+__global__ void esc_clear_list_kernel(unsigned int *__restrict__ Q, const unsigned long long *__restrict__ list, unsigned long long n)
+{
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    size_t stride = (size_t)gridDim.x * blockDim.x;
+    for (; i < n; i += stride) Q[list[2 * i]] = 0u;
+}
+
+cudaError_t launch_esc_clear_list(unsigned int *Q, const unsigned long long *list, unsigned long long n, int blocks, cudaStream_t s)
+{
+    if (n == 0) return cudaSuccess;
+    esc_clear_list_kernel<<<blocks, 256, 0, s>>>(Q, list, n);
+    return cudaGetLastError();
+}
+
 cudaError_t launch_esc_scatter(unsigned int *Q, size_t total, const unsigned long long *list, unsigned long long n,
                                int blocks, cudaStream_t s)
 {

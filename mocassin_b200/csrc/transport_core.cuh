@@ -575,32 +575,43 @@ struct Transport {
         float opacEarly = 0.f;
         if (early) opacEarly = __ldg(&a.g1.opacity[L.planeBase]);
         bool snapped = false;
-        // Single grid, fast path of the wall stage: the three wall distances with none of the
+        // Fast path of the wall stage: the three wall distances with none of the
         // special cases.  Those -- an axis sitting on its wall (snap, drop on the outermost wall, the
         // zero distance replaced by the axis end, :1263-1432) or a non-finite distance -- all begin
         // with a moving axis whose |distance| is not >= 1e-10; when no axis is in that state the
         // generic stage below reduces to exactly these lines, and it is skipped.  Otherwise nothing
         // has been modified yet and the generic stage runs from scratch.
         bool fast = false;
-        if (MCB_FASTWALL && !MULTI) {
-            const DevGrid &g = a.g1;
-            if (sym()) {                 // :1248-1261, as at the head of the generic stage (idempotent)
-                if (L.rx <= g.x1) { L.vx = fabsf(L.vx); L.rx = g.x1; }
-                if (L.ry <= g.y1) { L.vy = fabsf(L.vy); L.ry = g.y1; }
-                if (L.rz <= g.z1) { L.vz = fabsf(L.vz); L.rz = g.z1; }
+        if (MCB_FASTWALL) {
+            const DevGrid &g = G(L.gP);
+            // multi-grid: only inside a cell of the current grid (an index outside it, or a mother cell
+            // that holds a sub-grid, takes the generic stage with its sub-grid entry and its stops)
+            bool inside = true;
+            int c0 = 1;
+            if (MULTI) {
+                inside = !(L.xP > g.nx || L.xP < 1 || L.yP > g.ny || L.yP < 1 || L.zP > g.nz || L.zP < 1);
+                if (inside) { c0 = active_at(g, L.xP, L.yP, L.zP); inside = c0 >= 0; }
             }
-            const bool px = L.vx > 1.e-10f, py = L.vy > 1.e-10f, pz = L.vz > 1.e-10f;
-            const bool mx = px || L.vx < -1.e-10f, my = py || L.vy < -1.e-10f, mz = pz || L.vz < -1.e-10f;
-            const float dx = div_rn(__ldg(&g.xWall[px ? L.xP : L.xP - 1]) - L.rx, L.vx, L.iax);
-            const float dy = div_rn(__ldg(&g.yWall[py ? L.yP : L.yP - 1]) - L.ry, L.vy, L.iay);
-            const float dz = div_rn(__ldg(&g.zWall[pz ? L.zP : L.zP - 1]) - L.rz, L.vz, L.iaz);
-            const bool special = (mx && !(fabsf(dx) >= 1.e-10f)) || (my && !(fabsf(dy) >= 1.e-10f)) ||
-                                 (mz && !(fabsf(dz) >= 1.e-10f));
-            if (__builtin_expect(!special, 1)) {
-                fast = true;
-                posx = px; posy = py; posz = pz;
-                dSx = mx ? dx : 1.e35f; dSy = my ? dy : 1.e35f; dSz = mz ? dz : 1.e35f;
-                cell = kInc ? 1 : active_at<DENSE>(g, L.xP, L.yP, L.zP);
+            if (inside) {
+                if (sym()) {             // :1248-1261, as at the head of the generic stage (idempotent)
+                    const DevGrid &m = G(1);
+                    if (L.rx <= m.x1) { L.vx = fabsf(L.vx); L.rx = m.x1; }
+                    if (L.ry <= m.y1) { L.vy = fabsf(L.vy); L.ry = m.y1; }
+                    if (L.rz <= m.z1) { L.vz = fabsf(L.vz); L.rz = m.z1; }
+                }
+                const bool px = L.vx > 1.e-10f, py = L.vy > 1.e-10f, pz = L.vz > 1.e-10f;
+                const bool mx = px || L.vx < -1.e-10f, my = py || L.vy < -1.e-10f, mz = pz || L.vz < -1.e-10f;
+                const float dx = div_rn(__ldg(&g.xWall[px ? L.xP : L.xP - 1]) - L.rx, L.vx, L.iax);
+                const float dy = div_rn(__ldg(&g.yWall[py ? L.yP : L.yP - 1]) - L.ry, L.vy, L.iay);
+                const float dz = div_rn(__ldg(&g.zWall[pz ? L.zP : L.zP - 1]) - L.rz, L.vz, L.iaz);
+                const bool special = (mx && !(fabsf(dx) >= 1.e-10f)) || (my && !(fabsf(dy) >= 1.e-10f)) ||
+                                     (mz && !(fabsf(dz) >= 1.e-10f));
+                if (__builtin_expect(!special, 1)) {
+                    fast = true;
+                    posx = px; posy = py; posz = pz;
+                    dSx = mx ? dx : 1.e35f; dSy = my ? dy : 1.e35f; dSz = mz ? dz : 1.e35f;
+                    cell = MULTI ? c0 : (kInc ? 1 : active_at<DENSE>(g, L.xP, L.yP, L.zP));
+                }
             }
         }
         for (int j = 1; !fast; ++j) {
@@ -830,7 +841,7 @@ struct Transport {
     __device__ __forceinline__ bool step_tail_multi(Lane &L)
     {
         const DevParams &P = a.P;
-        if (!P.lgSym) {                  // "be 6/6/06" block (:1986-2194)
+        if (!sym()) {                  // "be 6/6/06" block (:1986-2194)
             bool lgReturn = false;
             {
                 const DevGrid &c = G(L.gP);
@@ -873,7 +884,7 @@ struct Transport {
         {
             const DevGrid &m = G(1);
             const DevGrid &c = G(L.gP);
-            bool lowOut = !P.lgSym && (L.rx <= m.xLo || L.ry <= m.yLo || L.rz <= m.zLo);
+            bool lowOut = !sym() && (L.rx <= m.xLo || L.ry <= m.yLo || L.rz <= m.zLo);
             if (lowOut || (L.rx >= c.xHi) || (L.ry >= c.yHi) || (L.rz >= c.zHi) ||
                 L.xP > c.nx || L.yP > c.ny || L.zP > c.nz) {
                 if (L.gP == 1) { escape(L, FATE_ESCAPED); return false; }
@@ -890,7 +901,7 @@ struct Transport {
             }
         }
 
-        if (P.lgSym) {                   // :2674-2699
+        if (sym()) {                   // :2674-2699
             const DevGrid &m = G(1);
             const DevGrid &c = G(L.gP);
             if (L.rx <= m.x1 || (L.gP == 1 && L.xP < 1)) { L.vx = fabsf(L.vx); L.mx = 1; L.xP = 1; L.rx = c.x1; }

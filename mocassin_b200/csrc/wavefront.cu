@@ -131,8 +131,11 @@ __global__ void __launch_bounds__(kThreads) wf_event_kernel(const __grid_constan
 #ifndef MCB_FLY_OCC
 #define MCB_FLY_OCC 4                    // resident CTAs per SM the FLY kernel is compiled for (A/B: build.py --define)
 #endif
+#ifndef MCB_FLY_OCC_MULTI
+#define MCB_FLY_OCC_MULTI 3              // multi-grid variant: more packet state (mother / sub-grid slots), 85 registers
+#endif
 template <bool MULTI, bool DENSE, int MODE>
-__global__ void __launch_bounds__(kThreads, MCB_FLY_OCC) wf_fly_kernel(const __grid_constant__ WfArgs w)
+__global__ void __launch_bounds__(kThreads, MULTI ? MCB_FLY_OCC_MULTI : MCB_FLY_OCC) wf_fly_kernel(const __grid_constant__ WfArgs w)
 {
     extern __shared__ unsigned int smem[];
     scratch_init(smem, w.t.P.nbins);
@@ -435,8 +438,11 @@ static cudaError_t launch_fly_t(const WfArgs &w, int blocks, cudaStream_t s)
 
 cudaError_t wf_launch_fly(const WfArgs &w, bool multi, int blocks, cudaStream_t s)
 {
-    if (multi) return launch_fly_t<true, false, 0>(w, blocks, s);
     const int mode = (w.t.P.lgDebug || w.t.P.lgPlane) ? 0 : (w.t.P.lgSym ? 1 : 2);
+    if (multi) {                         // the same compile-time mode flags as the single-grid variants
+        if (mode == 2) return launch_fly_t<true, false, 2>(w, blocks, s);
+        return mode == 1 ? launch_fly_t<true, false, 1>(w, blocks, s) : launch_fly_t<true, false, 0>(w, blocks, s);
+    }
     if (w.t.g1.dense) {
         if (mode == 2) return launch_fly_t<false, true, 2>(w, blocks, s);
         return mode == 1 ? launch_fly_t<false, true, 1>(w, blocks, s) : launch_fly_t<false, true, 0>(w, blocks, s);

@@ -2,8 +2,8 @@
 for name in p0tau1 p0tau10 p0tau100 tau1.000; do
   out=gpurun_out/r02_deck_$name
   mkdir -p $out
-  /usr/bin/time -f "# wall %es" timeout 600 python scripts/run_dust_deck.py --golden tests/golden/deck_$name.npz --out $out > gpurun_out/r02_dust_deck_${name}_b200.jsonl 2> $out/stderr.log
-  tail -1 $out/stderr.log >> gpurun_out/r02_dust_deck_${name}_b200.jsonl
+  timeout 600 python scripts/run_dust_deck.py --golden tests/golden/deck_$name.npz --out $out > gpurun_out/r02_dust_deck_${name}_b200.jsonl 2> $out/stderr.log
+
   tail -2 gpurun_out/r02_dust_deck_${name}_b200.jsonl | cut -c1-400
   rm -f $out/grid0.out $out/dustGrid.out          # MBs of per-cell text; SED/summary/tauNu/photoSource are kept
 done

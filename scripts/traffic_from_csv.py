@@ -27,6 +27,8 @@ while start > 0 and any(k in seq[start - 1]["name"] for k in ("first_nu", "scan_
 agg = collections.OrderedDict()
 tot = {"r": 0.0, "w": 0.0, "t": 0.0}
 for d in seq[start:]:
+    if "access_peak" in d["name"]:        # the roofline micro-benchmark of bench.py is not part of the step
+        continue
     k = d["name"].split("(")[0]
     a = agg.setdefault(k, [0, 0.0, 0.0, 0.0])
     r = d.get("dram__bytes_read.sum", 0) * scale.get(unit.get("dram__bytes_read.sum", "byte"), 1.0)
