@@ -470,6 +470,9 @@ int mcb200_fetch_fates(mcb200_ctx *ctx, int32_t *fates, int64_t nPackets);
  *   "pdf_slabs"     1: mcb200_set_pdfs uploads only this rank's 1/nranks slab of nu-planes of the (identical on
  *                   every rank) table over PCIe and all-gathers the slabs over NVLink (needs mcb200_comm_init)
  *   "exchange_p2p"  -1 auto / 0 / 1: fused peer-memory merge of the J tallies (mcb200_exchange_path)
+ *   "exchange_push" peer-memory merge: 1 (default) every rank pushes each peer's share of its partial sums into the
+ *                   peer's receive buffer (device-to-device copies, posted writes), the owner sums locally; 0 the
+ *                   owner pulls the partial sums with peer loads inside the merge kernel
  *   "solo"          1: this rank acts as rank 0 of 1 until cleared (N-rank vs 1-rank check on one context)
  *   "defer_fold"    1: a single rank leaves its tallies pending after mcb200_transport, as a multi-rank run
  *                   does, until mcb200_reduce (lets one GPU walk the mcb200_exchange path) */

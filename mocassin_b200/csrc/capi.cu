@@ -35,6 +35,8 @@ struct P2PPeers {
 };
 cudaError_t launch_p2p_reduce_fold(const P2PPeers &P, const float *dV, int nRows, size_t first, size_t total,
                                    double lenUnit, float deltaE, int blocks, cudaStream_t s);
+cudaError_t launch_p2p_sum_fold(const P2PPeers &P, const unsigned long long *recv, size_t slotStride, size_t rOff, const float *dV,
+                                int nRows, size_t first, size_t total, double lenUnit, float deltaE, int blocks, cudaStream_t s);
 cudaError_t launch_fold_count(unsigned int *Q, float *E, size_t total, float deltaE, int blocks,
                               cudaStream_t s);
 cudaError_t launch_merge_sets(unsigned long long *J0, unsigned long long *J1, size_t nJ, unsigned int *E0,
@@ -126,6 +128,7 @@ struct GridState {
     DevBuf<int> active;
     DevBuf<float> opacity, scaOpac, absOpac, pdfT, totalLines, linePDF, dV, stage;
     DevBuf<float> contI;                  // mcb200_fetch_contcube: (0:nCells, 0:nAngleBins)
+    DevBuf<float> cellStage;              // mcb200_fetch_estimators_cells: compact rows of one rank's cells
     DevBuf<unsigned char> canScatter;
     DevBuf<unsigned long long> JsteQ, JdifQ;
     DevBuf<unsigned int> escQ, lineQ;
@@ -150,6 +153,9 @@ struct GridState {
     bool jShardsP2P = false;              // the shares are still to be summed: by the fused peer-memory kernel in the fold
     // peer mappings of every rank's JsteQ / Jste (cudaIpc), for the fused reduce + fold over NVLink
     std::vector<void *> peerQ, peerJ;     // [rank]; own entry = local pointer
+    std::vector<void *> peerRecv;         // [rank]: every rank's receive buffer of the push variant (own = recvQ.p)
+    DevBuf<unsigned long long> recvQ;     // (nranks-1) slots of slotStride partial sums pushed by the peers
+    size_t slotStride = 0;
     void *peerBaseQ = nullptr, *peerBaseJ = nullptr;   // local pointers the mappings were made for
     // dust closure (mcb200_dust_update / mcb200_dust_pdf): device copy of the dust state
     DevBuf<float> Tdust;
@@ -245,6 +251,8 @@ struct mcb200_ctx {
     bool exchangeAllReduce = false;       // option exchange_allreduce: all-reduce the J planes (round-1 path) instead of
                                           // reduce-scatter -> fold the share -> all-gather float32
     int p2pMode = -1;                     // option exchange_p2p: -1 auto (peer memory when it can be mapped), 0 NCCL only, 1 required
+    bool p2pPush = true;                  // option exchange_push: peers push their partial sums (copies), the owner sums locally;
+                                          // 0 = the owner pulls them with peer loads inside the merge kernel
     int p2pState = 0;                     // 0 not tried, 1 usable, -1 unavailable (lastP2PWhy)
     std::string lastP2PWhy;
     int lastExchangePath = 0;             // 0 none, 1 all-reduce, 2 reduce-scatter/all-gather (NCCL), 3 fused peer-memory kernel
@@ -555,8 +563,9 @@ void p2p_close(GridState &g, int rank)
         if ((int)r == rank) continue;
         if (g.peerQ[r]) cudaIpcCloseMemHandle(g.peerQ[r]);
         if (g.peerJ[r]) cudaIpcCloseMemHandle(g.peerJ[r]);
+        if (r < g.peerRecv.size() && g.peerRecv[r]) cudaIpcCloseMemHandle(g.peerRecv[r]);
     }
-    g.peerQ.clear(); g.peerJ.clear();
+    g.peerQ.clear(); g.peerJ.clear(); g.peerRecv.clear();
     g.peerBaseQ = g.peerBaseJ = nullptr;
 }
 
@@ -577,7 +586,11 @@ int p2p_setup(mcb200_ctx *ctx, GridState &g)
     CU(cudaStreamSynchronize(s));
     if (!stale) return MCB200_OK;
     p2p_close(g, rank);
-    struct Pair { cudaIpcMemHandle_t q, j; int ok; int pad[3]; };
+    // receive buffer of the push variant: one slot per peer, each large enough for this rank's share
+    // of every range of the J table
+    g.slotStride = g.JsteQ.n / (size_t)world + 1;
+    if (g.recvQ.n != g.slotStride * (size_t)(world - 1)) CU(g.recvQ.alloc(g.slotStride * (size_t)(world - 1)));
+    struct Pair { cudaIpcMemHandle_t q, j, rcv; int ok; int pad[3]; };
     static_assert(sizeof(Pair) % 8 == 0, "handle record must be a multiple of 8 bytes");
     std::vector<Pair> all((size_t)world);
     Pair mine{};
@@ -585,6 +598,7 @@ int p2p_setup(mcb200_ctx *ctx, GridState &g)
     if (world > 16) { mine.ok = 0; ctx->lastP2PWhy = "more than 16 ranks"; }
     if (mine.ok && cudaIpcGetMemHandle(&mine.q, g.JsteQ.p) != cudaSuccess) { mine.ok = 0; ctx->lastP2PWhy = "cudaIpcGetMemHandle(JsteQ) failed"; cudaGetLastError(); }
     if (mine.ok && cudaIpcGetMemHandle(&mine.j, g.Jste.p) != cudaSuccess) { mine.ok = 0; ctx->lastP2PWhy = "cudaIpcGetMemHandle(Jste) failed"; cudaGetLastError(); }
+    if (mine.ok && cudaIpcGetMemHandle(&mine.rcv, g.recvQ.p) != cudaSuccess) { mine.ok = 0; ctx->lastP2PWhy = "cudaIpcGetMemHandle(recvQ) failed"; cudaGetLastError(); }
     CU(ctx->ipcBuf.alloc(sizeof(Pair) * (size_t)(world + 1)));
     CU(cudaMemcpyAsync(ctx->ipcBuf.p + sizeof(Pair) * (size_t)world, &mine, sizeof(Pair), cudaMemcpyHostToDevice, s));
     NC(N.AllGather(ctx->ipcBuf.p + sizeof(Pair) * (size_t)world, ctx->ipcBuf.p, sizeof(Pair) / 8, kNcclUint64, ctx->comm, s));
@@ -592,11 +606,12 @@ int p2p_setup(mcb200_ctx *ctx, GridState &g)
     CU(cudaStreamSynchronize(s));
     int ok = 1;
     for (auto &h : all) ok = ok && h.ok;
-    g.peerQ.assign((size_t)world, nullptr); g.peerJ.assign((size_t)world, nullptr);
+    g.peerQ.assign((size_t)world, nullptr); g.peerJ.assign((size_t)world, nullptr); g.peerRecv.assign((size_t)world, nullptr);
     for (int r = 0; r < world && ok; ++r) {
-        if (r == rank) { g.peerQ[r] = g.JsteQ.p; g.peerJ[r] = g.Jste.p; continue; }
+        if (r == rank) { g.peerQ[r] = g.JsteQ.p; g.peerJ[r] = g.Jste.p; g.peerRecv[r] = g.recvQ.p; continue; }
         if (cudaIpcOpenMemHandle(&g.peerQ[r], all[r].q, cudaIpcMemLazyEnablePeerAccess) != cudaSuccess ||
-            cudaIpcOpenMemHandle(&g.peerJ[r], all[r].j, cudaIpcMemLazyEnablePeerAccess) != cudaSuccess) {
+            cudaIpcOpenMemHandle(&g.peerJ[r], all[r].j, cudaIpcMemLazyEnablePeerAccess) != cudaSuccess ||
+            cudaIpcOpenMemHandle(&g.peerRecv[r], all[r].rcv, cudaIpcMemLazyEnablePeerAccess) != cudaSuccess) {
             ok = 0;
             ctx->lastP2PWhy = std::string("cudaIpcOpenMemHandle failed: ") + cudaGetErrorString(cudaGetLastError());
         }
@@ -636,6 +651,34 @@ int fold_shards(mcb200_ctx *ctx, GridState &g, int *launches)
         P2PPeers P{};
         P.nranks = world; P.rank = rank;
         for (int r = 0; r < world; ++r) { P.Q[r] = (unsigned long long *)g.peerQ[r]; P.J[r] = (float *)g.peerJ[r]; }
+        if (ctx->p2pPush) {
+            // push variant: every rank copies, for every peer, the peer's share of its partial sums into
+            // the peer's receive buffer (device-to-device copies through the mapped buffers: posted
+            // writes at copy-engine speed), a barrier, then one local kernel per range sums, folds and
+            // stores the float32 result into all ranks' Jste
+            size_t rOff = 0;
+            for (auto &r : g.jShards) {
+                for (int d = 1; d < world; ++d) {
+                    const int peer = (rank + d) % world;                       // staggered: no two ranks start on the same target
+                    const int slot = rank < peer ? rank : rank - 1;           // this rank's slot in the peer's buffer
+                    unsigned long long *dst = (unsigned long long *)g.peerRecv[peer] + (size_t)slot * g.slotStride + rOff;
+                    CU(cudaMemcpyAsync(dst, g.JsteQ.p + r.off + (size_t)peer * r.count, r.count * 8, cudaMemcpyDeviceToDevice, s));
+                }
+                rOff += r.count;
+                ctx->lastExchangeBytes += (int64_t)r.count * (int64_t)(world - 1) * 12;
+            }
+            int rcb = comm_barrier(ctx);
+            if (rcb) return rcb;
+            rOff = 0;
+            for (auto &r : g.jShards) {
+                const size_t mine = r.off + (size_t)rank * r.count, tail = r.off + (size_t)world * r.count;
+                CU(launch_p2p_sum_fold(P, g.recvQ.p, g.slotStride, rOff, g.dV.p, (int)nR, mine, r.count, lenUnit, ctx->pendingDeltaE,
+                                       ctx->numSMs * 16, s));
+                CU(launch_fold_j(g.JsteQ.p + tail, g.Jste.p + tail, g.dV.p, (int)nR, tail, r.off + r.len - tail, lenUnit, ctx->pendingDeltaE, blocks, s));
+                if (launches) *launches += 2;
+                rOff += r.count;
+            }
+        } else
         for (auto &r : g.jShards) {
             const size_t mine = r.off + (size_t)rank * r.count, tail = r.off + (size_t)world * r.count;
             CU(launch_p2p_reduce_fold(P, g.dV.p, (int)nR, mine, r.count, lenUnit, ctx->pendingDeltaE, ctx->numSMs * 16, s));
@@ -2202,12 +2245,12 @@ int mcb200_fetch_estimators_cells(mcb200_ctx *ctx, int32_t iG, int32_t firstCell
     if (nCellsOut) *nCellsOut = nMine;
     if (nMine == 0) return MCB200_OK;
     if (Jdif && !g->Jdif.p) return fail(ctx, MCB200_ESTATE, "Jdif only exists in debug mode");
-    CU(g->stage.alloc((size_t)nMine * (size_t)nb));
+    CU(g->cellStage.alloc((size_t)nMine * (size_t)nb));      // its own buffer: no reallocation against the PDF staging
     for (int which = 0; which < 2; ++which) {
         float *dst = which ? Jdif : Jste;
         if (!dst) continue;
-        CU(launch_gather_cells(which ? g->Jdif.p : g->Jste.p, nR, nb, firstCell, cellStride, (int)nMine, g->stage.p, ctx->stream));
-        CU(cudaMemcpyAsync(dst, g->stage.p, (size_t)nMine * (size_t)nb * sizeof(float), cudaMemcpyDeviceToHost, ctx->stream));
+        CU(launch_gather_cells(which ? g->Jdif.p : g->Jste.p, nR, nb, firstCell, cellStride, (int)nMine, g->cellStage.p, ctx->stream));
+        CU(cudaMemcpyAsync(dst, g->cellStage.p, (size_t)nMine * (size_t)nb * sizeof(float), cudaMemcpyDeviceToHost, ctx->stream));
         CU(cudaStreamSynchronize(ctx->stream));
     }
     return MCB200_OK;
@@ -2529,6 +2572,7 @@ int mcb200_set_option(mcb200_ctx *ctx, const char *name, int64_t value)
     if (!strcmp(name, "esc_compact")) { ctx->escCompact = value != 0; return MCB200_OK; }
     if (!strcmp(name, "epoch")) { ctx->epoch = value; return MCB200_OK; }
     if (!strcmp(name, "pdf_slabs")) { ctx->pdfSlabs = value != 0; return MCB200_OK; }
+    if (!strcmp(name, "exchange_push")) { ctx->p2pPush = value != 0; return MCB200_OK; }
     if (!strcmp(name, "exchange_p2p")) { ctx->p2pMode = (int)value; if (ctx->p2pState < 0) ctx->p2pState = 0; return MCB200_OK; }
     if (!strcmp(name, "solo")) {
         // 1: this rank behaves as rank 0 of 1 (transports every packet of a call itself and folds at

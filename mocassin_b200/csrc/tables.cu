@@ -156,6 +156,51 @@ __global__ void __launch_bounds__(256) p2p_reduce_fold_generic_kernel(const __gr
     __threadfence_system();
 }
 
+// Push variant of the merge, second half: the peers have already written their partial sums of this
+// rank's share into its receive buffer (nSlots slots of `slotStride` elements, this range at `rOff`
+// inside every slot; peer copies through the mapped buffers, posted writes instead of the round
+// trips of peer loads).  Sum them with the local partial sum, fold once, store the float32 result
+// into every rank's Jste (peer stores), clear the local partial sum.
+template <int N>
+__global__ void __launch_bounds__(256) p2p_sum_fold_kernel(const __grid_constant__ P2PPeers P, const unsigned long long *__restrict__ recv,
+                                                           size_t slotStride, size_t rOff, const float *__restrict__ dV, int nRows,
+                                                           size_t first, size_t total, double lenUnit, float deltaE)
+{
+    const int nr = N > 0 ? N : P.nranks;
+    const size_t stride = (size_t)gridDim.x * blockDim.x;
+    unsigned long long *Q = P.Q[P.rank];
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += stride) {
+        const size_t e = first + i;
+        unsigned long long sum = Q[e];
+#pragma unroll
+        for (int sl = 0; sl < (N > 0 ? N - 1 : 15); ++sl)
+            if (sl < nr - 1) sum += recv[(size_t)sl * slotStride + rOff + i];
+        if (sum != 0ull) {
+            int cell = (int)(e % (size_t)nRows);
+            float len = (float)((double)(long long)sum * lenUnit);
+            float v = P.J[P.rank][e] + len * deltaE / dV[cell];
+#pragma unroll
+            for (int r = 0; r < (N > 0 ? N : 16); ++r)
+                if (r < nr) P.J[r][e] = v;
+            Q[e] = 0ull;
+        }
+    }
+    __threadfence_system();
+}
+
+cudaError_t launch_p2p_sum_fold(const P2PPeers &P, const unsigned long long *recv, size_t slotStride, size_t rOff, const float *dV,
+                                int nRows, size_t first, size_t total, double lenUnit, float deltaE, int blocks, cudaStream_t s)
+{
+    if (total == 0) return cudaSuccess;
+    switch (P.nranks) {
+    case 2: p2p_sum_fold_kernel<2><<<blocks, 256, 0, s>>>(P, recv, slotStride, rOff, dV, nRows, first, total, lenUnit, deltaE); break;
+    case 4: p2p_sum_fold_kernel<4><<<blocks, 256, 0, s>>>(P, recv, slotStride, rOff, dV, nRows, first, total, lenUnit, deltaE); break;
+    case 8: p2p_sum_fold_kernel<8><<<blocks, 256, 0, s>>>(P, recv, slotStride, rOff, dV, nRows, first, total, lenUnit, deltaE); break;
+    default: p2p_sum_fold_kernel<0><<<blocks, 256, 0, s>>>(P, recv, slotStride, rOff, dV, nRows, first, total, lenUnit, deltaE); break;
+    }
+    return cudaGetLastError();
+}
+
 cudaError_t launch_p2p_reduce_fold(const P2PPeers &P, const float *dV, int nRows, size_t first, size_t total,
                                    double lenUnit, float deltaE, int blocks, cudaStream_t s)
 {
