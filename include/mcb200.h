@@ -325,7 +325,7 @@ int mcb200_exchange_info(mcb200_ctx *ctx, int64_t *bytesSent, int32_t *sparseGri
  * Option "exchange_p2p": -1 auto (default), 0 never, 1 required (MCB200_ECOMM if unavailable).
  * All three leave bit-identical estimators.  phaseMs (nullable, 4 doubles): host time of the last
  * mcb200_exchange, host time of the last mcb200_reduce, device time of the J merge inside that
- * fold (the peer-memory kernel + barrier + clears, or fold + all-gather), reserved. */
+ * fold (the peer-memory kernel + barrier + clears, or fold + all-gather), and of its push phase alone. */
 int mcb200_exchange_path(mcb200_ctx *ctx, int32_t *path, char *why, int64_t whyLen, double *phaseMs);
 /* Which NCCL the library binds (needs no context and no device): ncclGetVersion and the file the
  * symbols came from.  A process that also hosts another NCCL user (PyTorch) must bind the SAME
@@ -471,8 +471,9 @@ int mcb200_fetch_fates(mcb200_ctx *ctx, int32_t *fates, int64_t nPackets);
  *                   every rank) table over PCIe and all-gathers the slabs over NVLink (needs mcb200_comm_init)
  *   "exchange_p2p"  -1 auto / 0 / 1: fused peer-memory merge of the J tallies (mcb200_exchange_path)
  *   "exchange_push" peer-memory merge: 1 (default) every rank pushes each peer's share of its partial sums into the
- *                   peer's receive buffer (device-to-device copies, posted writes), the owner sums locally; 0 the
- *                   owner pulls the partial sums with peer loads inside the merge kernel
+ *                   peer's receive buffer (device-to-device copies, posted writes), the owner sums locally; 2 the
+ *                   same with a kernel that stores to all peers at once instead of copy after copy; 0 the owner
+ *                   pulls the partial sums with peer loads inside the merge kernel
  *   "solo"          1: this rank acts as rank 0 of 1 until cleared (N-rank vs 1-rank check on one context)
  *   "defer_fold"    1: a single rank leaves its tallies pending after mcb200_transport, as a multi-rank run
  *                   does, until mcb200_reduce (lets one GPU walk the mcb200_exchange path) */

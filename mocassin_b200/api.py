@@ -527,7 +527,7 @@ class PacketEngine:
         ph = (C.c_double * 4)()
         self._check(self.lib.mcb200_exchange_path(self.h, C.byref(path), why, 256, ph))
         return dict(bytes=b.value, sparse_grids=sp.value, nccl_version=v.value,
-                    exchange_ms=ph[0], reduce_ms=ph[1], j_merge_device_ms=ph[2],
+                    exchange_ms=ph[0], reduce_ms=ph[1], j_merge_device_ms=ph[2], j_push_device_ms=ph[3],
                     path={0: "none", 1: "nccl all-reduce", 2: "nccl reduce-scatter + all-gather",
                           3: "fused peer-memory kernel (NVLink)"}.get(path.value, str(path.value)),
                     p2p_unavailable=why.value.decode() or None)

@@ -35,6 +35,12 @@ struct P2PPeers {
 };
 cudaError_t launch_p2p_reduce_fold(const P2PPeers &P, const float *dV, int nRows, size_t first, size_t total,
                                    double lenUnit, float deltaE, int blocks, cudaStream_t s);
+struct P2PPush {
+    unsigned long long *recv[16];
+    int nranks, rank;
+};
+cudaError_t launch_p2p_push(const P2PPush &P, const unsigned long long *Q, size_t off, size_t count, size_t slotStride,
+                            size_t rOff, int blocks, cudaStream_t s);
 cudaError_t launch_p2p_sum_fold(const P2PPeers &P, const unsigned long long *recv, size_t slotStride, size_t rOff, const float *dV,
                                 int nRows, size_t first, size_t total, double lenUnit, float deltaE, int blocks, cudaStream_t s);
 cudaError_t launch_fold_count(unsigned int *Q, float *E, size_t total, float deltaE, int blocks,
@@ -251,7 +257,7 @@ struct mcb200_ctx {
     bool exchangeAllReduce = false;       // option exchange_allreduce: all-reduce the J planes (round-1 path) instead of
                                           // reduce-scatter -> fold the share -> all-gather float32
     int p2pMode = -1;                     // option exchange_p2p: -1 auto (peer memory when it can be mapped), 0 NCCL only, 1 required
-    bool p2pPush = true;                  // option exchange_push: peers push their partial sums (copies), the owner sums locally;
+    int p2pPush = 1;                      // option exchange_push: peers push their partial sums (copies), the owner sums locally;
                                           // 0 = the owner pulls them with peer loads inside the merge kernel
     int p2pState = 0;                     // 0 not tried, 1 usable, -1 unavailable (lastP2PWhy)
     std::string lastP2PWhy;
@@ -263,7 +269,8 @@ struct mcb200_ctx {
     int64_t lastPdfH2D = 0;               // bytes the last mcb200_set_pdfs moved host -> device for the CDF table
     int64_t epoch = 0;                    // option epoch: advances the Philox key (set to the Lucy iteration number)
     cudaStream_t sideStream = nullptr;    // fold of the escape counts / SED beside the link-bound J merge (multi-rank)
-    cudaEvent_t sideEv0 = nullptr, sideEv1 = nullptr;
+    cudaEvent_t sideEv0 = nullptr, sideEv1 = nullptr, evMid = nullptr, evPush0 = nullptr, pushDone = nullptr;
+    bool evMidSet = false;
     bool solo = false;                    // option solo
     int soloRank = 0, soloNranks = 1;
     bool keepSharded = false;             // option keep_sharded: skip the all-gather (Jste stays valid only on the owner's share)
@@ -632,6 +639,71 @@ int p2p_setup(mcb200_ctx *ctx, GridState &g)
     return MCB200_OK;
 }
 
+int ensure_side_stream(mcb200_ctx *ctx)
+{
+    if (!ctx->sideStream) {
+        CU(cudaStreamCreateWithFlags(&ctx->sideStream, cudaStreamNonBlocking));
+        CU(cudaEventCreateWithFlags(&ctx->sideEv0, cudaEventDisableTiming));
+        CU(cudaEventCreateWithFlags(&ctx->sideEv1, cudaEventDisableTiming));
+        CU(cudaEventCreateWithFlags(&ctx->pushDone, cudaEventDisableTiming));
+        CU(cudaEventCreate(&ctx->evPush0));
+        CU(cudaEventCreate(&ctx->evMid));
+    }
+    return MCB200_OK;
+}
+
+// Push variant of the peer-memory merge, first phase, issued by mcb200_exchange as soon as the shares
+// are known, on the side stream: it runs on the copy engines (or a streaming kernel) and the links,
+// beside the escape-count exchange that mcb200_exchange does on the library stream.  Every rank
+// copies, for every peer, the peer's share of its partial sums into the peer's receive buffer
+// (device-to-device through the mapped buffers: posted writes), then clears the shares it has
+// handed over.  The receive buffers are free: every rank passed the closing barrier of the previous merge.
+int p2p_push_phase(mcb200_ctx *ctx, GridState &g, bool first)
+{
+    const int world = ctx->nranks, rank = ctx->rank;
+    int rc = ensure_side_stream(ctx);
+    if (rc) return rc;
+    cudaStream_t ss = ctx->sideStream;
+    CU(cudaEventRecord(ctx->sideEv0, ctx->stream));
+    CU(cudaStreamWaitEvent(ss, ctx->sideEv0, 0));
+    if (first) CU(cudaEventRecord(ctx->evPush0, ss));
+    {
+        size_t rOff = 0;
+        if (ctx->p2pPush == 2) {
+            P2PPush PP{};
+            PP.nranks = world; PP.rank = rank;
+            for (int r = 0; r < world; ++r) PP.recv[r] = (unsigned long long *)g.peerRecv[r];
+            for (auto &r : g.jShards) {
+                CU(launch_p2p_push(PP, g.JsteQ.p, r.off, r.count, g.slotStride, rOff, ctx->numSMs * 16, ss));
+                rOff += r.count;
+                ctx->lastExchangeBytes += (int64_t)r.count * (int64_t)(world - 1) * 12;
+            }
+        } else {
+            for (auto &r : g.jShards) {
+                for (int d = 1; d < world; ++d) {
+                    const int peer = (rank + d) % world;                       // staggered: no two ranks start on the same target
+                    const int slot = rank < peer ? rank : rank - 1;           // this rank's slot in the peer's buffer
+                    unsigned long long *dst = (unsigned long long *)g.peerRecv[peer] + (size_t)slot * g.slotStride + rOff;
+                    CU(cudaMemcpyAsync(dst, g.JsteQ.p + r.off + (size_t)peer * r.count, r.count * 8, cudaMemcpyDeviceToDevice, ss));
+                }
+                rOff += r.count;
+                ctx->lastExchangeBytes += (int64_t)r.count * (int64_t)(world - 1) * 12;
+            }
+        }
+    }
+    CU(cudaEventRecord(ctx->evMid, ss));
+    ctx->evMidSet = true;
+    {
+        for (auto &r : g.jShards) {          // handed over: clear (the owner never reads these)
+            const size_t mine = r.off + (size_t)rank * r.count, tail = r.off + (size_t)world * r.count;
+            if (mine > r.off) CU(cudaMemsetAsync(g.JsteQ.p + r.off, 0, (mine - r.off) * 8, ss));
+            if (tail > mine + r.count) CU(cudaMemsetAsync(g.JsteQ.p + mine + r.count, 0, (tail - mine - r.count) * 8, ss));
+        }
+    }
+    CU(cudaEventRecord(ctx->pushDone, ss));
+    return MCB200_OK;
+}
+
 // J planes after the reduce-scatter of mcb200_exchange (comm_exchange): this rank holds the global
 // integer sums of its share of every exchanged range, the tail of each range on every rank.  Fold
 // the share (1/nranks of the work), clear the other ranks' shares (partial sums that have been
@@ -656,17 +728,9 @@ int fold_shards(mcb200_ctx *ctx, GridState &g, int *launches)
             // the peer's receive buffer (device-to-device copies through the mapped buffers: posted
             // writes at copy-engine speed), a barrier, then one local kernel per range sums, folds and
             // stores the float32 result into all ranks' Jste
+            // the pushes were issued by mcb200_exchange on the side stream (p2p_push_phase)
+            CU(cudaStreamWaitEvent(s, ctx->pushDone, 0));
             size_t rOff = 0;
-            for (auto &r : g.jShards) {
-                for (int d = 1; d < world; ++d) {
-                    const int peer = (rank + d) % world;                       // staggered: no two ranks start on the same target
-                    const int slot = rank < peer ? rank : rank - 1;           // this rank's slot in the peer's buffer
-                    unsigned long long *dst = (unsigned long long *)g.peerRecv[peer] + (size_t)slot * g.slotStride + rOff;
-                    CU(cudaMemcpyAsync(dst, g.JsteQ.p + r.off + (size_t)peer * r.count, r.count * 8, cudaMemcpyDeviceToDevice, s));
-                }
-                rOff += r.count;
-                ctx->lastExchangeBytes += (int64_t)r.count * (int64_t)(world - 1) * 12;
-            }
             int rcb = comm_barrier(ctx);
             if (rcb) return rcb;
             rOff = 0;
@@ -690,11 +754,12 @@ int fold_shards(mcb200_ctx *ctx, GridState &g, int *launches)
         // reading, and nobody may read Jste before every owner has stored its share
         int rc = comm_barrier(ctx);
         if (rc) return rc;
-        for (auto &r : g.jShards) {
-            const size_t mine = r.off + (size_t)rank * r.count, tail = r.off + (size_t)world * r.count;
-            if (mine > r.off) CU(cudaMemsetAsync(g.JsteQ.p + r.off, 0, (mine - r.off) * 8, s));
-            if (tail > mine + r.count) CU(cudaMemsetAsync(g.JsteQ.p + mine + r.count, 0, (tail - mine - r.count) * 8, s));
-        }
+        if (!ctx->p2pPush)               // (push variant: cleared right behind the pushes, on the side stream)
+            for (auto &r : g.jShards) {
+                const size_t mine = r.off + (size_t)rank * r.count, tail = r.off + (size_t)world * r.count;
+                if (mine > r.off) CU(cudaMemsetAsync(g.JsteQ.p + r.off, 0, (mine - r.off) * 8, s));
+                if (tail > mine + r.count) CU(cudaMemsetAsync(g.JsteQ.p + mine + r.count, 0, (tail - mine - r.count) * 8, s));
+            }
         g.jShards.clear();
         g.jShardsP2P = false;
         return MCB200_OK;
@@ -749,11 +814,7 @@ int fold_pending(mcb200_ctx *ctx)
     for (auto &g : ctx->grids) anySharded = anySharded || !g.jShards.empty();
     cudaStream_t es = s;
     if (anySharded) {
-        if (!ctx->sideStream) {
-            CU(cudaStreamCreateWithFlags(&ctx->sideStream, cudaStreamNonBlocking));
-            CU(cudaEventCreateWithFlags(&ctx->sideEv0, cudaEventDisableTiming));
-            CU(cudaEventCreateWithFlags(&ctx->sideEv1, cudaEventDisableTiming));
-        }
+        { int rcs = ensure_side_stream(ctx); if (rcs) return rcs; }
         es = ctx->sideStream;
         CU(cudaEventRecord(ctx->sideEv0, s));
         CU(cudaStreamWaitEvent(es, ctx->sideEv0, 0));
@@ -813,6 +874,12 @@ int fold_pending(mcb200_ctx *ctx)
         float ms = 0.f;
         CU(cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev1));
         ctx->lastPhaseMs[2] = ms;
+        ctx->lastPhaseMs[3] = 0.0;
+        if (ctx->evMidSet) {             // push variant: the share of the pushes in the merge
+            CU(cudaEventElapsedTime(&ms, ctx->evPush0, ctx->evMid));
+            ctx->lastPhaseMs[3] = ms;
+            ctx->evMidSet = false;
+        }
     }
     ctx->pending = false;
     ctx->exchanged = false;
@@ -1374,6 +1441,7 @@ int comm_exchange(mcb200_ctx *ctx)
         int rc = comm_allreduce(ctx, ctx->sedQ.p, ctx->sedQ.n, kNcclUint64, kNcclSum);
         if (rc) return rc;
     }
+    bool pushed = false;
     for (size_t ig = 0; ig < ctx->grids.size(); ++ig) {
         GridState &g = ctx->grids[ig];
         if (!g.set || !g.JsteQ.p) continue;
@@ -1385,12 +1453,6 @@ int comm_exchange(mcb200_ctx *ctx)
         CU(cudaMemcpyAsync(flag.data(), g.nuTouched.p, sizeof(int) * (nb + 1), cudaMemcpyDeviceToHost, s));
         CU(cudaStreamSynchronize(s));
         auto ranges = touched_ranges(flag);
-        // the escape counts first: their exchange has data-dependent sizes (host round trips), which
-        // must not queue up behind the bulk transfer of the J planes
-        if (!ctx->sedLocal) {
-            rc = comm_exchange_escaped(ctx, g, ranges);
-            if (rc) return rc;
-        }
         g.jShards.clear();
         g.jShardsP2P = false;
         const bool allreduce = ctx->exchangeAllReduce || ctx->nranks == 1;
@@ -1404,6 +1466,13 @@ int comm_exchange(mcb200_ctx *ctx)
             return fail(ctx, MCB200_ECOMM, "option exchange_p2p=1: peer memory unavailable (%s)",
                         ctx->cfg.lgDebug ? "debug tallies go through NCCL" : ctx->lastP2PWhy.c_str());
         ctx->lastExchangePath = allreduce ? 1 : (p2p ? 3 : 2);
+        const bool escLater = p2p && ctx->p2pPush;   // push variant: beside the pushes, see below
+        if (!ctx->sedLocal && !escLater) {
+            // the escape counts first: their exchange has data-dependent sizes (host round trips), which
+            // must not queue up behind the bulk transfer of the J planes on the same stream
+            rc = comm_exchange_escaped(ctx, g, ranges);
+            if (rc) return rc;
+        }
         NC(nccl_api().GroupStart());
         for (auto &rg : ranges) {
             int p0 = rg.first < 1 ? 1 : rg.first, p1 = rg.second;
@@ -1434,6 +1503,17 @@ int comm_exchange(mcb200_ctx *ctx)
         }
         NC(nccl_api().GroupEnd());
         g.jShardsP2P = p2p && !g.jShards.empty();
+        if (g.jShardsP2P && ctx->p2pPush) {
+            // the bulk of the exchange starts now, on the side stream (copy engines + links) ...
+            rc = p2p_push_phase(ctx, g, !pushed);
+            if (rc) return rc;
+            pushed = true;
+        }
+        // ... beside the escape counts on the library stream
+        if (!ctx->sedLocal && escLater) {
+            rc = comm_exchange_escaped(ctx, g, ranges);
+            if (rc) return rc;
+        }
         if (ctx->cfg.lgDebug && g.lineQ.n) {
             rc = comm_allreduce(ctx, g.lineQ.p, g.lineQ.n, kNcclUint32, kNcclSum);
             if (rc) return rc;
@@ -1487,6 +1567,9 @@ int mcb200_destroy(mcb200_ctx *ctx)
     if (ctx->sideStream) { cudaStreamSynchronize(ctx->sideStream); cudaStreamDestroy(ctx->sideStream); }
     if (ctx->sideEv0) cudaEventDestroy(ctx->sideEv0);
     if (ctx->sideEv1) cudaEventDestroy(ctx->sideEv1);
+    if (ctx->evMid) cudaEventDestroy(ctx->evMid);
+    if (ctx->evPush0) cudaEventDestroy(ctx->evPush0);
+    if (ctx->pushDone) cudaEventDestroy(ctx->pushDone);
     for (auto e : ctx->flyEv) cudaEventDestroy(e);
     if (ctx->sparseHost) cudaFreeHost(ctx->sparseHost);
     for (auto &g : ctx->grids) p2p_close(g, ctx->rank);
@@ -2572,7 +2655,7 @@ int mcb200_set_option(mcb200_ctx *ctx, const char *name, int64_t value)
     if (!strcmp(name, "esc_compact")) { ctx->escCompact = value != 0; return MCB200_OK; }
     if (!strcmp(name, "epoch")) { ctx->epoch = value; return MCB200_OK; }
     if (!strcmp(name, "pdf_slabs")) { ctx->pdfSlabs = value != 0; return MCB200_OK; }
-    if (!strcmp(name, "exchange_push")) { ctx->p2pPush = value != 0; return MCB200_OK; }
+    if (!strcmp(name, "exchange_push")) { ctx->p2pPush = (int)value; return MCB200_OK; }
     if (!strcmp(name, "exchange_p2p")) { ctx->p2pMode = (int)value; if (ctx->p2pState < 0) ctx->p2pState = 0; return MCB200_OK; }
     if (!strcmp(name, "solo")) {
         // 1: this rank behaves as rank 0 of 1 (transports every packet of a call itself and folds at

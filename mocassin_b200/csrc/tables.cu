@@ -201,6 +201,49 @@ cudaError_t launch_p2p_sum_fold(const P2PPeers &P, const unsigned long long *rec
     return cudaGetLastError();
 }
 
+// Push variant, first half as a kernel: every thread block streams the shares of ALL peers at once
+// (element i of every peer's share in the same trip), so the stores of a rank are spread over all
+// its links all the time instead of one destination after another.
+// recv[r] = rank r's receive buffer; this rank writes slot `slot(r)` of it at rOff.
+struct P2PPush {
+    unsigned long long *recv[16];
+    int nranks, rank;
+};
+
+template <int N>
+__global__ void __launch_bounds__(256) p2p_push_kernel(const __grid_constant__ P2PPush P, const unsigned long long *__restrict__ Q,
+                                                       size_t off, size_t count, size_t slotStride, size_t rOff)
+{
+    const int nr = N > 0 ? N : P.nranks;
+    const size_t stride = (size_t)gridDim.x * blockDim.x;
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < count; i += stride) {
+        unsigned long long v[N > 0 ? N : 16];
+#pragma unroll
+        for (int r = 0; r < (N > 0 ? N : 16); ++r)
+            if (r < nr && r != P.rank) v[r] = Q[off + (size_t)r * count + i];
+#pragma unroll
+        for (int r = 0; r < (N > 0 ? N : 16); ++r)
+            if (r < nr && r != P.rank) {
+                const int slot = P.rank < r ? P.rank : P.rank - 1;
+                P.recv[r][(size_t)slot * slotStride + rOff + i] = v[r];
+            }
+    }
+    __threadfence_system();
+}
+
+cudaError_t launch_p2p_push(const P2PPush &P, const unsigned long long *Q, size_t off, size_t count, size_t slotStride,
+                            size_t rOff, int blocks, cudaStream_t s)
+{
+    if (count == 0) return cudaSuccess;
+    switch (P.nranks) {
+    case 2: p2p_push_kernel<2><<<blocks, 256, 0, s>>>(P, Q, off, count, slotStride, rOff); break;
+    case 4: p2p_push_kernel<4><<<blocks, 256, 0, s>>>(P, Q, off, count, slotStride, rOff); break;
+    case 8: p2p_push_kernel<8><<<blocks, 256, 0, s>>>(P, Q, off, count, slotStride, rOff); break;
+    default: p2p_push_kernel<0><<<blocks, 256, 0, s>>>(P, Q, off, count, slotStride, rOff); break;
+    }
+    return cudaGetLastError();
+}
+
 cudaError_t launch_p2p_reduce_fold(const P2PPeers &P, const float *dV, int nRows, size_t first, size_t total,
                                    double lenUnit, float deltaE, int blocks, cudaStream_t s)
 {
