@@ -338,6 +338,8 @@ def run_b200(args):
         eng.comm_init_from_group()
         if os.environ.get("MCB_EXCHANGE_ALLREDUCE", "0") == "1":
             eng.set_option("exchange_allreduce", 1)
+        if os.environ.get("MCB_EXCHANGE_PACK"):
+            eng.set_option("exchange_pack", int(os.environ["MCB_EXCHANGE_PACK"]))
         if os.environ.get("MCB_EXCHANGE_PUSH"):
             eng.set_option("exchange_push", int(os.environ["MCB_EXCHANGE_PUSH"]))
         if os.environ.get("MCB_EXCHANGE_P2P"):

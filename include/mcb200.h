@@ -470,6 +470,9 @@ int mcb200_fetch_fates(mcb200_ctx *ctx, int32_t *fates, int64_t nPackets);
  *   "pdf_slabs"     1: mcb200_set_pdfs uploads only this rank's 1/nranks slab of nu-planes of the (identical on
  *                   every rank) table over PCIe and all-gathers the slabs over NVLink (needs mcb200_comm_init)
  *   "exchange_p2p"  -1 auto / 0 / 1: fused peer-memory merge of the J tallies (mcb200_exchange_path)
+ *   "exchange_pack" peer-memory merge, push variants: 1 (default) the partial sums travel packed -- the low 32 bits of
+ *                   every element, the high 32 bits only of the 2048-element blocks in which one is non-zero, a flag
+ *                   byte per block -- 4 instead of 8 bytes per element on the links; 0 plain 64-bit pushes
  *   "exchange_push" peer-memory merge: 1 (default) every rank pushes each peer's share of its partial sums into the
  *                   peer's receive buffer (device-to-device copies, posted writes), the owner sums locally; 2 the
  *                   same with a kernel that stores to all peers at once instead of copy after copy; 0 the owner

@@ -41,6 +41,23 @@ struct P2PPush {
 };
 cudaError_t launch_p2p_push(const P2PPush &P, const unsigned long long *Q, size_t off, size_t count, size_t slotStride,
                             size_t rOff, int blocks, cudaStream_t s);
+struct P2PRanges {
+    unsigned long long off[8], count[8], rOff[8];
+    int n;
+    unsigned long long total;
+};
+struct P2PPackedPeers {
+    unsigned int *lo[16];
+    unsigned int *hi[16];
+    unsigned char *flag[16];
+    int nranks, rank;
+};
+int p2p_pack_block();
+cudaError_t launch_p2p_push_packed(const P2PPackedPeers &P, const P2PRanges &R, unsigned long long *Q, size_t slotStride,
+                                   size_t flagStride, int blocks, cudaStream_t s);
+cudaError_t launch_p2p_sum_fold_packed(const P2PPeers &P, const unsigned int *lo, const unsigned int *hi, const unsigned char *flag,
+                                       size_t slotStride, size_t flagStride, size_t rOff, const float *dV, int nRows, size_t first,
+                                       size_t total, double lenUnit, float deltaE, int blocks, cudaStream_t s);
 cudaError_t launch_p2p_sum_fold(const P2PPeers &P, const unsigned long long *recv, size_t slotStride, size_t rOff, const float *dV,
                                 int nRows, size_t first, size_t total, double lenUnit, float deltaE, int blocks, cudaStream_t s);
 cudaError_t launch_fold_count(unsigned int *Q, float *E, size_t total, float deltaE, int blocks,
@@ -161,7 +178,8 @@ struct GridState {
     std::vector<void *> peerQ, peerJ;     // [rank]; own entry = local pointer
     std::vector<void *> peerRecv;         // [rank]: every rank's receive buffer of the push variant (own = recvQ.p)
     DevBuf<unsigned long long> recvQ;     // (nranks-1) slots of slotStride partial sums pushed by the peers
-    size_t slotStride = 0;
+    size_t slotStride = 0, flagStride = 0;
+    bool jPacked = false;                 // the pending push went out packed (low words + flagged high words)
     void *peerBaseQ = nullptr, *peerBaseJ = nullptr;   // local pointers the mappings were made for
     // dust closure (mcb200_dust_update / mcb200_dust_pdf): device copy of the dust state
     DevBuf<float> Tdust;
@@ -257,6 +275,7 @@ struct mcb200_ctx {
     bool exchangeAllReduce = false;       // option exchange_allreduce: all-reduce the J planes (round-1 path) instead of
                                           // reduce-scatter -> fold the share -> all-gather float32
     int p2pMode = -1;                     // option exchange_p2p: -1 auto (peer memory when it can be mapped), 0 NCCL only, 1 required
+    bool p2pPack = true;                  // option exchange_pack: packed push (4 bytes per element + flagged high words)
     int p2pPush = 1;                      // option exchange_push: peers push their partial sums (copies), the owner sums locally;
                                           // 0 = the owner pulls them with peer loads inside the merge kernel
     int p2pState = 0;                     // 0 not tried, 1 usable, -1 unavailable (lastP2PWhy)
@@ -596,7 +615,11 @@ int p2p_setup(mcb200_ctx *ctx, GridState &g)
     // receive buffer of the push variant: one slot per peer, each large enough for this rank's share
     // of every range of the J table
     g.slotStride = g.JsteQ.n / (size_t)world + 1;
-    if (g.recvQ.n != g.slotStride * (size_t)(world - 1)) CU(g.recvQ.alloc(g.slotStride * (size_t)(world - 1)));
+    g.flagStride = g.slotStride / (size_t)p2p_pack_block() + 2;
+    {   // 8 bytes per element (64-bit partial sums, or low + high words of the packed push) + one flag byte per block
+        const size_t words = g.slotStride * (size_t)(world - 1) + (g.flagStride * (size_t)(world - 1) + 7) / 8 + 1;
+        if (g.recvQ.n != words) CU(g.recvQ.alloc(words));
+    }
     struct Pair { cudaIpcMemHandle_t q, j, rcv; int ok; int pad[3]; };
     static_assert(sizeof(Pair) % 8 == 0, "handle record must be a multiple of 8 bytes");
     std::vector<Pair> all((size_t)world);
@@ -667,6 +690,28 @@ int p2p_push_phase(mcb200_ctx *ctx, GridState &g, bool first)
     CU(cudaEventRecord(ctx->sideEv0, ctx->stream));
     CU(cudaStreamWaitEvent(ss, ctx->sideEv0, 0));
     if (first) CU(cudaEventRecord(ctx->evPush0, ss));
+    g.jPacked = false;
+    if (ctx->p2pPack && g.jShards.size() <= 8) {
+        P2PRanges R{};
+        R.n = (int)g.jShards.size();
+        unsigned long long tot = 0;
+        for (int i = 0; i < R.n; ++i) { R.off[i] = g.jShards[i].off; R.count[i] = g.jShards[i].count; R.rOff[i] = tot; tot += g.jShards[i].count; }
+        R.total = tot;
+        P2PPackedPeers PP{};
+        PP.nranks = world; PP.rank = rank;
+        for (int r = 0; r < world; ++r) {
+            PP.lo[r] = (unsigned int *)g.peerRecv[r];
+            PP.hi[r] = PP.lo[r] + (size_t)(world - 1) * g.slotStride;
+            PP.flag[r] = (unsigned char *)((unsigned long long *)g.peerRecv[r] + (size_t)(world - 1) * g.slotStride);
+        }
+        CU(launch_p2p_push_packed(PP, R, g.JsteQ.p, g.slotStride, g.flagStride, ctx->numSMs * 16, ss));
+        ctx->lastExchangeBytes += (int64_t)tot * (int64_t)(world - 1) * 8;
+        g.jPacked = true;
+        CU(cudaEventRecord(ctx->evMid, ss));
+        ctx->evMidSet = true;
+        CU(cudaEventRecord(ctx->pushDone, ss));      // (the kernel cleared what it handed over)
+        return MCB200_OK;
+    }
     {
         size_t rOff = 0;
         if (ctx->p2pPush == 2) {
@@ -736,6 +781,12 @@ int fold_shards(mcb200_ctx *ctx, GridState &g, int *launches)
             rOff = 0;
             for (auto &r : g.jShards) {
                 const size_t mine = r.off + (size_t)rank * r.count, tail = r.off + (size_t)world * r.count;
+                if (g.jPacked) {
+                    const unsigned int *lo = (const unsigned int *)g.recvQ.p, *hi = lo + (size_t)(world - 1) * g.slotStride;
+                    const unsigned char *fl = (const unsigned char *)(g.recvQ.p + (size_t)(world - 1) * g.slotStride);
+                    CU(launch_p2p_sum_fold_packed(P, lo, hi, fl, g.slotStride, g.flagStride, rOff, g.dV.p, (int)nR, mine, r.count, lenUnit,
+                                                  ctx->pendingDeltaE, ctx->numSMs * 16, s));
+                } else
                 CU(launch_p2p_sum_fold(P, g.recvQ.p, g.slotStride, rOff, g.dV.p, (int)nR, mine, r.count, lenUnit, ctx->pendingDeltaE,
                                        ctx->numSMs * 16, s));
                 CU(launch_fold_j(g.JsteQ.p + tail, g.Jste.p + tail, g.dV.p, (int)nR, tail, r.off + r.len - tail, lenUnit, ctx->pendingDeltaE, blocks, s));
@@ -2010,6 +2061,7 @@ int mcb200_zero_estimators(mcb200_ctx *ctx)
 {
     NEED_CTX();
     if (!ctx->haveCfg) return fail(ctx, MCB200_ESTATE, "set_config first");
+    if (ctx->sideStream) CU(cudaStreamSynchronize(ctx->sideStream));   // pushes / clears of an exchange that was never folded
     {
         int rc = ensure_sed(ctx);
         if (rc) return rc;
@@ -2655,6 +2707,7 @@ int mcb200_set_option(mcb200_ctx *ctx, const char *name, int64_t value)
     if (!strcmp(name, "esc_compact")) { ctx->escCompact = value != 0; return MCB200_OK; }
     if (!strcmp(name, "epoch")) { ctx->epoch = value; return MCB200_OK; }
     if (!strcmp(name, "pdf_slabs")) { ctx->pdfSlabs = value != 0; return MCB200_OK; }
+    if (!strcmp(name, "exchange_pack")) { ctx->p2pPack = value != 0; return MCB200_OK; }
     if (!strcmp(name, "exchange_push")) { ctx->p2pPush = (int)value; return MCB200_OK; }
     if (!strcmp(name, "exchange_p2p")) { ctx->p2pMode = (int)value; if (ctx->p2pState < 0) ctx->p2pState = 0; return MCB200_OK; }
     if (!strcmp(name, "solo")) {

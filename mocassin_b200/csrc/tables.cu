@@ -244,6 +244,122 @@ cudaError_t launch_p2p_push(const P2PPush &P, const unsigned long long *Q, size_
     return cudaGetLastError();
 }
 
+// ---- packed push: 4 bytes per element on the links instead of 8 -----------------------------------
+// A rank's partial sum of one (cell, nu) element rarely needs more than 32 bits (the unit is 2^-24 of
+// the smallest cell half-width; only the cells next to a source collect more per call).  The packed
+// push sends the low words of every element, and the high words only of the blocks of kPackBlk
+// consecutive elements in which some high word is non-zero, with one flag byte per block; the owner
+// rebuilds the 64-bit values (low + (high << 32) where flagged) and sums them as before: exact.
+// j = index inside this rank's share of ALL exchanged ranges (ranges back to back, rOff of each);
+// receive buffer of a rank: low words [slot][j], high words [slot][j], flags [slot][j / kPackBlk].
+constexpr int kPackBlk = 2048;           // elements per flag (8 per thread of a 256-thread block)
+struct P2PRanges {
+    unsigned long long off[8], count[8], rOff[8];   // element offset of the range in JsteQ, share length, position in the share
+    int n;
+    unsigned long long total;                       // sum of count
+};
+struct P2PPackedPeers {
+    unsigned int *lo[16];
+    unsigned int *hi[16];
+    unsigned char *flag[16];
+    int nranks, rank;
+};
+
+__global__ void __launch_bounds__(256) p2p_push_packed_kernel(const __grid_constant__ P2PPackedPeers P, const __grid_constant__ P2PRanges R,
+                                                              unsigned long long *__restrict__ Q, size_t slotStride, size_t flagStride)
+{
+    const unsigned long long nBlk = (R.total + kPackBlk - 1) / kPackBlk;
+    for (unsigned long long b = blockIdx.x; b < nBlk; b += gridDim.x) {
+        for (int d = 1; d < P.nranks; ++d) {
+            const int r = (P.rank + d) % P.nranks;
+            const int slot = P.rank < r ? P.rank : P.rank - 1;
+            unsigned long long v[8];
+            unsigned int anyHi = 0u;
+#pragma unroll
+            for (int k = 0; k < 8; ++k) {
+                const unsigned long long j = b * kPackBlk + (unsigned long long)k * 256 + threadIdx.x;
+                v[k] = 0ull;
+                if (j < R.total) {
+                    int ri = 0;
+                    while (ri + 1 < R.n && j >= R.rOff[ri + 1]) ++ri;
+                    unsigned long long *q = &Q[R.off[ri] + (unsigned long long)r * R.count[ri] + (j - R.rOff[ri])];
+                    v[k] = *q;
+                    *q = 0ull;                       // handed over
+                    P.lo[r][(size_t)slot * slotStride + j] = (unsigned int)v[k];
+                    anyHi |= (unsigned int)(v[k] >> 32);
+                }
+            }
+            const int any = __syncthreads_or(anyHi != 0u);
+            if (threadIdx.x == 0) P.flag[r][(size_t)slot * flagStride + b] = (unsigned char)(any ? 1 : 0);
+            if (any) {
+#pragma unroll
+                for (int k = 0; k < 8; ++k) {
+                    const unsigned long long j = b * kPackBlk + (unsigned long long)k * 256 + threadIdx.x;
+                    if (j < R.total) P.hi[r][(size_t)slot * slotStride + j] = (unsigned int)(v[k] >> 32);
+                }
+            }
+        }
+    }
+    __threadfence_system();
+}
+
+template <int N>
+__global__ void __launch_bounds__(256) p2p_sum_fold_packed_kernel(const __grid_constant__ P2PPeers P, const unsigned int *__restrict__ lo,
+                                                                  const unsigned int *__restrict__ hi, const unsigned char *__restrict__ flag,
+                                                                  size_t slotStride, size_t flagStride, size_t rOff,
+                                                                  const float *__restrict__ dV, int nRows, size_t first, size_t total,
+                                                                  double lenUnit, float deltaE)
+{
+    const int nr = N > 0 ? N : P.nranks;
+    const size_t stride = (size_t)gridDim.x * blockDim.x;
+    unsigned long long *Q = P.Q[P.rank];
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += stride) {
+        const size_t e = first + i, j = rOff + i;
+        unsigned long long sum = Q[e];
+#pragma unroll
+        for (int sl = 0; sl < (N > 0 ? N - 1 : 15); ++sl)
+            if (sl < nr - 1) {
+                unsigned long long v = lo[(size_t)sl * slotStride + j];
+                if (flag[(size_t)sl * flagStride + j / kPackBlk]) v |= (unsigned long long)hi[(size_t)sl * slotStride + j] << 32;
+                sum += v;
+            }
+        if (sum != 0ull) {
+            int cell = (int)(e % (size_t)nRows);
+            float len = (float)((double)(long long)sum * lenUnit);
+            float v = P.J[P.rank][e] + len * deltaE / dV[cell];
+#pragma unroll
+            for (int r = 0; r < (N > 0 ? N : 16); ++r)
+                if (r < nr) P.J[r][e] = v;
+            Q[e] = 0ull;
+        }
+    }
+    __threadfence_system();
+}
+
+int p2p_pack_block() { return kPackBlk; }
+
+cudaError_t launch_p2p_push_packed(const P2PPackedPeers &P, const P2PRanges &R, unsigned long long *Q, size_t slotStride,
+                                   size_t flagStride, int blocks, cudaStream_t s)
+{
+    if (R.total == 0) return cudaSuccess;
+    p2p_push_packed_kernel<<<blocks, 256, 0, s>>>(P, R, Q, slotStride, flagStride);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_p2p_sum_fold_packed(const P2PPeers &P, const unsigned int *lo, const unsigned int *hi, const unsigned char *flag,
+                                       size_t slotStride, size_t flagStride, size_t rOff, const float *dV, int nRows, size_t first,
+                                       size_t total, double lenUnit, float deltaE, int blocks, cudaStream_t s)
+{
+    if (total == 0) return cudaSuccess;
+    switch (P.nranks) {
+    case 2: p2p_sum_fold_packed_kernel<2><<<blocks, 256, 0, s>>>(P, lo, hi, flag, slotStride, flagStride, rOff, dV, nRows, first, total, lenUnit, deltaE); break;
+    case 4: p2p_sum_fold_packed_kernel<4><<<blocks, 256, 0, s>>>(P, lo, hi, flag, slotStride, flagStride, rOff, dV, nRows, first, total, lenUnit, deltaE); break;
+    case 8: p2p_sum_fold_packed_kernel<8><<<blocks, 256, 0, s>>>(P, lo, hi, flag, slotStride, flagStride, rOff, dV, nRows, first, total, lenUnit, deltaE); break;
+    default: p2p_sum_fold_packed_kernel<0><<<blocks, 256, 0, s>>>(P, lo, hi, flag, slotStride, flagStride, rOff, dV, nRows, first, total, lenUnit, deltaE); break;
+    }
+    return cudaGetLastError();
+}
+
 cudaError_t launch_p2p_reduce_fold(const P2PPeers &P, const float *dV, int nRows, size_t first, size_t total,
                                    double lenUnit, float deltaE, int blocks, cudaStream_t s)
 {

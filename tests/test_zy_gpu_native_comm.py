@@ -129,6 +129,13 @@ def _worker_body(rank, world, idfile, name, n, q, allreduce=False):
         e.set_option("pdf_slabs", 1)
         e.set_pdfs()
         allreduce = "p2p"
+    if allreduce == "p2p-unpacked":
+        e.set_option("exchange_pack", 0)           # 64-bit pushes (copy engines) instead of the packed push kernel
+        allreduce = "p2p"
+    if allreduce == "p2p-kernelpush":
+        e.set_option("exchange_pack", 0)
+        e.set_option("exchange_push", 2)
+        allreduce = "p2p"
     if allreduce == "p2p-pull":
         e.set_option("exchange_push", 0)           # the owner pulls the partial sums with peer loads
         allreduce = "p2p"
@@ -160,6 +167,8 @@ def _worker_body(rank, world, idfile, name, n, q, allreduce=False):
 @pytest.mark.parametrize("name,allreduce", [("multigrid_sym", "p2p"), ("cube_clumpy_gasdust", "p2p"), ("hii_sym_gas_debug", "p2p"),
                                             ("viewing_angles", "p2p"), ("multigrid_sym", "allreduce"), ("multigrid_sym", "nccl"), ("multigrid_sym", "p2p+slabs"),
                                             ("multigrid_sym", "p2p-pull"), ("cube_clumpy_gasdust", "p2p-pull"),
+                                            ("multigrid_sym", "p2p-unpacked"), ("cube_clumpy_gasdust", "p2p-unpacked"),
+                                            ("viewing_angles", "p2p-kernelpush"), ("dust_shell_hg", "p2p-unpacked"),
                                             ("cube_clumpy_gasdust", "p2p+slabs"), ("dust_shell_hg", "p2p+slabs"),
                                             ("cube_clumpy_gasdust", "nccl"), ("hii_sym_gas_debug", "nccl"),
                                             ("multigrid_nonsym", False), ("plane_slab_gasdust", False)])
