@@ -487,6 +487,10 @@ int mcb200_test_detmath(mcb200_ctx *ctx, int32_t which, const float *in, float *
 int mcb200_test_uniforms(mcb200_ctx *ctx, uint64_t seed, uint64_t pid, uint32_t stream,
                          int32_t n, float *out);
 
+/* measurement hook: device time of the push kernels of the peer-memory merge with all peer buffers local (one GPU);
+ * mode 0 = 64-bit push kernel, 1 = packed push kernel; nElems = elements of the exchanged range, nranksSim = ranks. */
+int mcb200_test_push_kernels(mcb200_ctx *ctx, int32_t mode, int32_t nranksSim, int64_t nElems, double *ms);
+
 /* measurement hook (bench.py, SURVEY.md 8d "atomic roofline"): rate at which the device serves
  * the transport's per-crossing access pattern and nothing else -- mode bit 0: one 64-bit
  * reduction, bit 1: one 4-byte read, per iteration, at uniformly random addresses inside windows

@@ -85,6 +85,7 @@ _SIGS = {
     "mcb200_set_option": [C.c_void_p, C.c_char_p, C.c_int64],
     "mcb200_test_detmath": [C.c_void_p, C.c_int32, c_float_p, c_float_p, C.c_int64],
     "mcb200_test_uniforms": [C.c_void_p, C.c_uint64, C.c_uint64, C.c_uint32, C.c_int32, c_float_p],
+    "mcb200_test_push_kernels": [C.c_void_p, C.c_int32, C.c_int32, C.c_int64, C.POINTER(C.c_double)],
     "mcb200_test_access_peak": [C.c_void_p, C.c_int32, C.c_int64, C.c_int64, C.c_int64, C.POINTER(C.c_double)],
 }
 

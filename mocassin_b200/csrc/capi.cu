@@ -41,11 +41,6 @@ struct P2PPush {
 };
 cudaError_t launch_p2p_push(const P2PPush &P, const unsigned long long *Q, size_t off, size_t count, size_t slotStride,
                             size_t rOff, int blocks, cudaStream_t s);
-struct P2PRanges {
-    unsigned long long off[8], count[8], rOff[8];
-    int n;
-    unsigned long long total;
-};
 struct P2PPackedPeers {
     unsigned int *lo[16];
     unsigned int *hi[16];
@@ -53,8 +48,8 @@ struct P2PPackedPeers {
     int nranks, rank;
 };
 int p2p_pack_block();
-cudaError_t launch_p2p_push_packed(const P2PPackedPeers &P, const P2PRanges &R, unsigned long long *Q, size_t slotStride,
-                                   size_t flagStride, int blocks, cudaStream_t s);
+cudaError_t launch_p2p_push_packed(const P2PPackedPeers &P, const unsigned long long *Q, size_t off, size_t count, size_t rOff,
+                                   size_t slotStride, size_t flagStride, int blocks, cudaStream_t s);
 cudaError_t launch_p2p_sum_fold_packed(const P2PPeers &P, const unsigned int *lo, const unsigned int *hi, const unsigned char *flag,
                                        size_t slotStride, size_t flagStride, size_t rOff, const float *dV, int nRows, size_t first,
                                        size_t total, double lenUnit, float deltaE, int blocks, cudaStream_t s);
@@ -614,7 +609,8 @@ int p2p_setup(mcb200_ctx *ctx, GridState &g)
     p2p_close(g, rank);
     // receive buffer of the push variant: one slot per peer, each large enough for this rank's share
     // of every range of the J table
-    g.slotStride = g.JsteQ.n / (size_t)world + 1;
+    // a share of every range, each starting on a flag-block boundary inside the slot (up to 64 ranges)
+    g.slotStride = (g.JsteQ.n / (size_t)world + 1 + (size_t)65 * (size_t)p2p_pack_block()) / (size_t)p2p_pack_block() * (size_t)p2p_pack_block();
     g.flagStride = g.slotStride / (size_t)p2p_pack_block() + 2;
     {   // 8 bytes per element (64-bit partial sums, or low + high words of the packed push) + one flag byte per block
         const size_t words = g.slotStride * (size_t)(world - 1) + (g.flagStride * (size_t)(world - 1) + 7) / 8 + 1;
@@ -662,6 +658,13 @@ int p2p_setup(mcb200_ctx *ctx, GridState &g)
     return MCB200_OK;
 }
 
+// position of the next range's share inside a receive slot: on a flag-block boundary
+size_t slot_advance(size_t rOff, size_t count)
+{
+    const size_t blk = (size_t)p2p_pack_block();
+    return (rOff + count + 3 + blk - 1) / blk * blk;   // (+3: a share starts at its element index mod 4 inside the slot)
+}
+
 int ensure_side_stream(mcb200_ctx *ctx)
 {
     if (!ctx->sideStream) {
@@ -691,12 +694,7 @@ int p2p_push_phase(mcb200_ctx *ctx, GridState &g, bool first)
     CU(cudaStreamWaitEvent(ss, ctx->sideEv0, 0));
     if (first) CU(cudaEventRecord(ctx->evPush0, ss));
     g.jPacked = false;
-    if (ctx->p2pPack && g.jShards.size() <= 8) {
-        P2PRanges R{};
-        R.n = (int)g.jShards.size();
-        unsigned long long tot = 0;
-        for (int i = 0; i < R.n; ++i) { R.off[i] = g.jShards[i].off; R.count[i] = g.jShards[i].count; R.rOff[i] = tot; tot += g.jShards[i].count; }
-        R.total = tot;
+    if (ctx->p2pPack && g.jShards.size() <= 64) {
         P2PPackedPeers PP{};
         PP.nranks = world; PP.rank = rank;
         for (int r = 0; r < world; ++r) {
@@ -704,12 +702,20 @@ int p2p_push_phase(mcb200_ctx *ctx, GridState &g, bool first)
             PP.hi[r] = PP.lo[r] + (size_t)(world - 1) * g.slotStride;
             PP.flag[r] = (unsigned char *)((unsigned long long *)g.peerRecv[r] + (size_t)(world - 1) * g.slotStride);
         }
-        CU(launch_p2p_push_packed(PP, R, g.JsteQ.p, g.slotStride, g.flagStride, ctx->numSMs * 16, ss));
-        ctx->lastExchangeBytes += (int64_t)tot * (int64_t)(world - 1) * 8;
+        size_t rOff = 0;
+        for (auto &r : g.jShards) {
+            CU(launch_p2p_push_packed(PP, g.JsteQ.p, r.off, r.count, rOff, g.slotStride, g.flagStride, ctx->numSMs * 16, ss));
+            // what was handed over is cleared by a separate pass (a store to a line whose load is still in
+            // flight inside the push kernel takes a slow path: measured 2.4x on the whole kernel)
+            if (rank > 0) CU(cudaMemsetAsync(g.JsteQ.p + r.off, 0, (size_t)rank * r.count * 8, ss));
+            if (rank + 1 < world) CU(cudaMemsetAsync(g.JsteQ.p + r.off + (size_t)(rank + 1) * r.count, 0, (size_t)(world - 1 - rank) * r.count * 8, ss));
+            rOff = slot_advance(rOff, r.count);
+            ctx->lastExchangeBytes += (int64_t)r.count * (int64_t)(world - 1) * 4;   // + the flagged high words (not counted)
+        }
         g.jPacked = true;
         CU(cudaEventRecord(ctx->evMid, ss));
         ctx->evMidSet = true;
-        CU(cudaEventRecord(ctx->pushDone, ss));      // (the kernel cleared what it handed over)
+        CU(cudaEventRecord(ctx->pushDone, ss));
         return MCB200_OK;
     }
     {
@@ -720,7 +726,7 @@ int p2p_push_phase(mcb200_ctx *ctx, GridState &g, bool first)
             for (int r = 0; r < world; ++r) PP.recv[r] = (unsigned long long *)g.peerRecv[r];
             for (auto &r : g.jShards) {
                 CU(launch_p2p_push(PP, g.JsteQ.p, r.off, r.count, g.slotStride, rOff, ctx->numSMs * 16, ss));
-                rOff += r.count;
+                rOff = slot_advance(rOff, r.count);
                 ctx->lastExchangeBytes += (int64_t)r.count * (int64_t)(world - 1) * 12;
             }
         } else {
@@ -731,7 +737,7 @@ int p2p_push_phase(mcb200_ctx *ctx, GridState &g, bool first)
                     unsigned long long *dst = (unsigned long long *)g.peerRecv[peer] + (size_t)slot * g.slotStride + rOff;
                     CU(cudaMemcpyAsync(dst, g.JsteQ.p + r.off + (size_t)peer * r.count, r.count * 8, cudaMemcpyDeviceToDevice, ss));
                 }
-                rOff += r.count;
+                rOff = slot_advance(rOff, r.count);
                 ctx->lastExchangeBytes += (int64_t)r.count * (int64_t)(world - 1) * 12;
             }
         }
@@ -791,7 +797,7 @@ int fold_shards(mcb200_ctx *ctx, GridState &g, int *launches)
                                        ctx->numSMs * 16, s));
                 CU(launch_fold_j(g.JsteQ.p + tail, g.Jste.p + tail, g.dV.p, (int)nR, tail, r.off + r.len - tail, lenUnit, ctx->pendingDeltaE, blocks, s));
                 if (launches) *launches += 2;
-                rOff += r.count;
+                rOff = slot_advance(rOff, r.count);
             }
         } else
         for (auto &r : g.jShards) {
@@ -2795,6 +2801,53 @@ int mcb200_test_access_peak(mcb200_ctx *ctx, int32_t mode, int64_t redWindowByte
     cudaEventDestroy(e0);
     cudaEventDestroy(e1);
     *opsPerSecond = (double)blocks * threads * iters / ((double)best * 1e-3);
+    return MCB200_OK;
+}
+
+// measurement hook: the push kernels of the peer-memory merge with every "peer" buffer local (one GPU):
+// mode 0 = 64-bit push kernel, 1 = packed push kernel; nElems = elements of the whole exchanged range.
+int mcb200_test_push_kernels(mcb200_ctx *ctx, int32_t mode, int32_t nranksSim, int64_t nElems, double *ms)
+{
+    NEED_CTX();
+    if (!ms || nranksSim < 2 || nranksSim > 16 || nElems < 1) return fail(ctx, MCB200_EINVAL, "bad test_push_kernels arguments");
+    const int world = nranksSim, rank = 0;
+    const size_t count = (size_t)nElems / (size_t)world, slotStride = (count + 1024) / 256 * 256, flagStride = slotStride / (size_t)p2p_pack_block() + 2;
+    DevBuf<unsigned long long> Q, recv;
+    CU(Q.alloc((size_t)nElems));
+    const size_t words = slotStride * (size_t)(world - 1) + (flagStride * (size_t)(world - 1) + 7) / 8 + 1;
+    CU(recv.alloc(words * (size_t)(world - 1)));          // one receive buffer per simulated peer
+    cudaStream_t s = ctx->stream;
+    float best = 1e30f;
+    for (int rep = 0; rep < 3; ++rep) {
+        CU(cudaMemsetAsync(Q.p, 0, (size_t)nElems * 8, s));
+        CU(cudaMemsetAsync(Q.p, 1, (size_t)nElems * 4, s));     // low words only: the usual case (no block flagged) ...
+        CU(cudaMemsetAsync(Q.p, 1, (size_t)nElems / 4, s));     // ... but for the first 1/32 of the range
+        CU(cudaEventRecord(ctx->ev0, s));
+        if (mode == 1) {
+            P2PPackedPeers PP{};
+            PP.nranks = world; PP.rank = rank;
+            for (int r = 1; r < world; ++r) {
+                unsigned long long *base = recv.p + (size_t)(r - 1) * words;
+                PP.lo[r] = (unsigned int *)base;
+                PP.hi[r] = PP.lo[r] + (size_t)(world - 1) * slotStride;
+                PP.flag[r] = (unsigned char *)(base + (size_t)(world - 1) * slotStride);
+            }
+            CU(launch_p2p_push_packed(PP, Q.p, 0, count, 0, slotStride, flagStride, ctx->numSMs * 16, s));
+            CU(cudaMemsetAsync(Q.p + count, 0, (size_t)(world - 1) * count * 8, s));
+        } else {
+            P2PPush PP{};
+            PP.nranks = world; PP.rank = rank;
+            for (int r = 1; r < world; ++r) PP.recv[r] = recv.p + (size_t)(r - 1) * words;
+            CU(launch_p2p_push(PP, Q.p, 0, count, slotStride, 0, ctx->numSMs * 16, s));
+            CU(cudaMemsetAsync(Q.p + count, 0, (size_t)(world - 1) * count * 8, s));
+        }
+        CU(cudaEventRecord(ctx->ev1, s));
+        CU(cudaEventSynchronize(ctx->ev1));
+        float t = 0.f;
+        CU(cudaEventElapsedTime(&t, ctx->ev0, ctx->ev1));
+        best = t < best ? t : best;
+    }
+    *ms = best;
     return MCB200_OK;
 }
 

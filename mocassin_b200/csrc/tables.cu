@@ -252,12 +252,7 @@ cudaError_t launch_p2p_push(const P2PPush &P, const unsigned long long *Q, size_
 // rebuilds the 64-bit values (low + (high << 32) where flagged) and sums them as before: exact.
 // j = index inside this rank's share of ALL exchanged ranges (ranges back to back, rOff of each);
 // receive buffer of a rank: low words [slot][j], high words [slot][j], flags [slot][j / kPackBlk].
-constexpr int kPackBlk = 2048;           // elements per flag (8 per thread of a 256-thread block)
-struct P2PRanges {
-    unsigned long long off[8], count[8], rOff[8];   // element offset of the range in JsteQ, share length, position in the share
-    int n;
-    unsigned long long total;                       // sum of count
-};
+constexpr int kPackBlk = 256;           // elements per flag (8 per lane of one warp)
 struct P2PPackedPeers {
     unsigned int *lo[16];
     unsigned int *hi[16];
@@ -265,37 +260,70 @@ struct P2PPackedPeers {
     int nranks, rank;
 };
 
-__global__ void __launch_bounds__(256) p2p_push_packed_kernel(const __grid_constant__ P2PPackedPeers P, const __grid_constant__ P2PRanges R,
-                                                              unsigned long long *__restrict__ Q, size_t slotStride, size_t flagStride)
+// 256-bit accesses (sm_100): one 32 B sector per lane
+__device__ __forceinline__ void ld256_cs(const unsigned long long *p, unsigned long long (&v)[4])
 {
-    const unsigned long long nBlk = (R.total + kPackBlk - 1) / kPackBlk;
-    for (unsigned long long b = blockIdx.x; b < nBlk; b += gridDim.x) {
+    asm volatile("ld.global.cs.v4.u64 {%0,%1,%2,%3}, [%4];" : "=l"(v[0]), "=l"(v[1]), "=l"(v[2]), "=l"(v[3]) : "l"(p));
+}
+__device__ __forceinline__ void st256_zero(unsigned long long *p)
+{
+    asm volatile("st.global.v4.u64 [%0], {%1,%1,%1,%1};" ::"l"(p), "l"(0ull) : "memory");
+}
+
+// Positions inside a receive slot: an element with ABSOLUTE index e of a share that starts at e0 sits at
+// j = rOff + (e - (e0 & ~3)), so that groups of four elements aligned in Q and Jste are aligned in the
+// slot too (rOff is a multiple of kPackBlk): every access below is one 16 B or 32 B vector per lane --
+// peer stores of 4 B per lane ran at 315 GB/s on NVLink, under half of what 16 B per lane reaches.
+// Q = base of the whole array; the share of rank r of this range = [off + r*count, off + (r+1)*count).
+__global__ void __launch_bounds__(256) p2p_push_packed_kernel(const __grid_constant__ P2PPackedPeers P, const unsigned long long *__restrict__ Q,
+                                                              size_t off, size_t count, size_t rOff, size_t slotStride, size_t flagStride)
+{
+    // one warp per flag block (kPackBlk = 2 groups of 4 elements per lane): no block-wide barrier
+    const size_t nBlk = (count + 3 + kPackBlk - 1) / kPackBlk;
+    const int lane = threadIdx.x & 31;
+    const size_t warp = (size_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5), nWarps = (size_t)gridDim.x * (blockDim.x >> 5);
+    for (size_t b = warp; b < nBlk; b += nWarps) {
         for (int d = 1; d < P.nranks; ++d) {
             const int r = (P.rank + d) % P.nranks;
             const int slot = P.rank < r ? P.rank : P.rank - 1;
-            unsigned long long v[8];
-            unsigned int anyHi = 0u;
+            const size_t e0 = off + (size_t)r * count, end = e0 + count, A = e0 & ~(size_t)3;
+            if (A + b * kPackBlk >= end) continue;           // (warp-uniform)
+            unsigned long long v[2][4];
+            size_t gs[2];
+            bool full[2];
 #pragma unroll
-            for (int k = 0; k < 8; ++k) {
-                const unsigned long long j = b * kPackBlk + (unsigned long long)k * 256 + threadIdx.x;
-                v[k] = 0ull;
-                if (j < R.total) {
-                    int ri = 0;
-                    while (ri + 1 < R.n && j >= R.rOff[ri + 1]) ++ri;
-                    unsigned long long *q = &Q[R.off[ri] + (unsigned long long)r * R.count[ri] + (j - R.rOff[ri])];
-                    v[k] = *q;
-                    *q = 0ull;                       // handed over
-                    P.lo[r][(size_t)slot * slotStride + j] = (unsigned int)v[k];
-                    anyHi |= (unsigned int)(v[k] >> 32);
-                }
+            for (int k = 0; k < 2; ++k) {                    // both loads in flight before the first store
+                gs[k] = A + b * kPackBlk + (size_t)(k * 32 + lane) * 4;
+                full[k] = gs[k] >= e0 && gs[k] + 4 <= end;
+                if (full[k]) ld256_cs(Q + gs[k], v[k]);
+                else
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) v[k][i] = (gs[k] + i >= e0 && gs[k] + i < end) ? __ldcs(Q + gs[k] + i) : 0ull;
             }
-            const int any = __syncthreads_or(anyHi != 0u);
-            if (threadIdx.x == 0) P.flag[r][(size_t)slot * flagStride + b] = (unsigned char)(any ? 1 : 0);
-            if (any) {
+            unsigned int anyHi = 0u;
+            unsigned int *lo = P.lo[r] + (size_t)slot * slotStride + rOff;
 #pragma unroll
-                for (int k = 0; k < 8; ++k) {
-                    const unsigned long long j = b * kPackBlk + (unsigned long long)k * 256 + threadIdx.x;
-                    if (j < R.total) P.hi[r][(size_t)slot * slotStride + j] = (unsigned int)(v[k] >> 32);
+            for (int k = 0; k < 2; ++k) {
+                const size_t j = gs[k] - A;
+                if (full[k]) *reinterpret_cast<uint4 *>(lo + j) = make_uint4((unsigned int)v[k][0], (unsigned int)v[k][1], (unsigned int)v[k][2], (unsigned int)v[k][3]);
+                else
+#pragma unroll
+                    for (int i = 0; i < 4; ++i)
+                        if (gs[k] + i >= e0 && gs[k] + i < end) lo[j + i] = (unsigned int)v[k][i];
+                anyHi |= (unsigned int)((v[k][0] | v[k][1] | v[k][2] | v[k][3]) >> 32);
+            }
+            const int any = __any_sync(0xffffffffu, anyHi != 0u);
+            if (lane == 0) P.flag[r][(size_t)slot * flagStride + rOff / kPackBlk + b] = (unsigned char)(any ? 1 : 0);
+            if (any) {
+                unsigned int *hi = P.hi[r] + (size_t)slot * slotStride + rOff;
+#pragma unroll
+                for (int k = 0; k < 2; ++k) {
+                    const size_t j = gs[k] - A;
+                    if (full[k]) *reinterpret_cast<uint4 *>(hi + j) = make_uint4((unsigned int)(v[k][0] >> 32), (unsigned int)(v[k][1] >> 32), (unsigned int)(v[k][2] >> 32), (unsigned int)(v[k][3] >> 32));
+                    else
+#pragma unroll
+                        for (int i = 0; i < 4; ++i)
+                            if (gs[k] + i >= e0 && gs[k] + i < end) hi[j + i] = (unsigned int)(v[k][i] >> 32);
                 }
             }
         }
@@ -303,6 +331,10 @@ __global__ void __launch_bounds__(256) p2p_push_packed_kernel(const __grid_const
     __threadfence_system();
 }
 
+// Owner side: rebuild the peers' 64-bit partial sums of this rank's share [first, first+total), add the
+// own one, fold (same float32 expression as fold_j_kernel) and store the result into every rank's Jste.
+// One group of four elements per thread; a group with a non-zero sum rewrites all four Jste values
+// (the unchanged ones are what every rank already holds: Jste of the shared ranges only ever changes here).
 template <int N>
 __global__ void __launch_bounds__(256) p2p_sum_fold_packed_kernel(const __grid_constant__ P2PPeers P, const unsigned int *__restrict__ lo,
                                                                   const unsigned int *__restrict__ hi, const unsigned char *__restrict__ flag,
@@ -313,24 +345,68 @@ __global__ void __launch_bounds__(256) p2p_sum_fold_packed_kernel(const __grid_c
     const int nr = N > 0 ? N : P.nranks;
     const size_t stride = (size_t)gridDim.x * blockDim.x;
     unsigned long long *Q = P.Q[P.rank];
-    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += stride) {
-        const size_t e = first + i, j = rOff + i;
-        unsigned long long sum = Q[e];
+    float *Jown = P.J[P.rank];
+    const size_t end = first + total, A = first & ~(size_t)3, nGroups = (end - A + 3) / 4;
+    for (size_t g = (size_t)blockIdx.x * blockDim.x + threadIdx.x; g < nGroups; g += stride) {
+        const size_t gs = A + 4 * g, j = rOff + 4 * g;
+        const bool full = gs >= first && gs + 4 <= end;
+        unsigned long long sum[4];
+        if (full) ld256_cs(Q + gs, sum);
+        else
+#pragma unroll
+            for (int i = 0; i < 4; ++i) sum[i] = (gs + i >= first && gs + i < end) ? Q[gs + i] : 0ull;
 #pragma unroll
         for (int sl = 0; sl < (N > 0 ? N - 1 : 15); ++sl)
             if (sl < nr - 1) {
-                unsigned long long v = lo[(size_t)sl * slotStride + j];
-                if (flag[(size_t)sl * flagStride + j / kPackBlk]) v |= (unsigned long long)hi[(size_t)sl * slotStride + j] << 32;
-                sum += v;
+                const bool f = flag[(size_t)sl * flagStride + j / kPackBlk] != 0;
+                if (full) {
+                    const uint4 l = __ldcs(reinterpret_cast<const uint4 *>(lo + (size_t)sl * slotStride + j));
+                    uint4 h = make_uint4(0u, 0u, 0u, 0u);
+                    if (f) h = __ldcs(reinterpret_cast<const uint4 *>(hi + (size_t)sl * slotStride + j));
+                    sum[0] += (unsigned long long)l.x | ((unsigned long long)h.x << 32);
+                    sum[1] += (unsigned long long)l.y | ((unsigned long long)h.y << 32);
+                    sum[2] += (unsigned long long)l.z | ((unsigned long long)h.z << 32);
+                    sum[3] += (unsigned long long)l.w | ((unsigned long long)h.w << 32);
+                } else
+#pragma unroll
+                    for (int i = 0; i < 4; ++i)
+                        if (gs + i >= first && gs + i < end) {
+                            unsigned long long v = lo[(size_t)sl * slotStride + j + i];
+                            if (f) v |= (unsigned long long)hi[(size_t)sl * slotStride + j + i] << 32;
+                            sum[i] += v;
+                        }
             }
-        if (sum != 0ull) {
-            int cell = (int)(e % (size_t)nRows);
-            float len = (float)((double)(long long)sum * lenUnit);
-            float v = P.J[P.rank][e] + len * deltaE / dV[cell];
+        if ((sum[0] | sum[1] | sum[2] | sum[3]) == 0ull) continue;
+        int cell = (int)(gs % (size_t)nRows);
+        if (full) {
+            const float4 j4 = *reinterpret_cast<const float4 *>(Jown + gs);
+            float o[4] = {j4.x, j4.y, j4.z, j4.w};
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                if (sum[i] != 0ull) {
+                    float len = (float)((double)(long long)sum[i] * lenUnit);
+                    o[i] = o[i] + len * deltaE / dV[cell];
+                }
+                if (++cell == nRows) cell = 0;
+            }
+            const float4 w = make_float4(o[0], o[1], o[2], o[3]);
 #pragma unroll
             for (int r = 0; r < (N > 0 ? N : 16); ++r)
-                if (r < nr) P.J[r][e] = v;
-            Q[e] = 0ull;
+                if (r < nr) *reinterpret_cast<float4 *>(P.J[r] + gs) = w;
+            st256_zero(Q + gs);
+        } else {
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                if (sum[i] != 0ull) {                        // (only elements of the share can be non-zero here)
+                    float len = (float)((double)(long long)sum[i] * lenUnit);
+                    float v = Jown[gs + i] + len * deltaE / dV[cell];
+#pragma unroll
+                    for (int r = 0; r < (N > 0 ? N : 16); ++r)
+                        if (r < nr) P.J[r][gs + i] = v;
+                    Q[gs + i] = 0ull;
+                }
+                if (++cell == nRows) cell = 0;
+            }
         }
     }
     __threadfence_system();
@@ -338,11 +414,11 @@ __global__ void __launch_bounds__(256) p2p_sum_fold_packed_kernel(const __grid_c
 
 int p2p_pack_block() { return kPackBlk; }
 
-cudaError_t launch_p2p_push_packed(const P2PPackedPeers &P, const P2PRanges &R, unsigned long long *Q, size_t slotStride,
-                                   size_t flagStride, int blocks, cudaStream_t s)
+cudaError_t launch_p2p_push_packed(const P2PPackedPeers &P, const unsigned long long *Q, size_t off, size_t count, size_t rOff,
+                                   size_t slotStride, size_t flagStride, int blocks, cudaStream_t s)
 {
-    if (R.total == 0) return cudaSuccess;
-    p2p_push_packed_kernel<<<blocks, 256, 0, s>>>(P, R, Q, slotStride, flagStride);
+    if (count == 0) return cudaSuccess;
+    p2p_push_packed_kernel<<<blocks, 256, 0, s>>>(P, Q, off, count, rOff, slotStride, flagStride);
     return cudaGetLastError();
 }
 

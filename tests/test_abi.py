@@ -72,7 +72,7 @@ def test_fortran_binding_covers_the_header():
     exported = set(re.findall(r"^(?:int|const char \*)\s*(mcb200_\w+)\s*\(", hdr, flags=re.M))
     bound = set(re.findall(r'name="(mcb200_\w+)"', f90))
     diagnostic = {"mcb200_fetch_fates", "mcb200_fetch_tallies", "mcb200_test_access_peak", "mcb200_test_detmath",
-                  "mcb200_test_uniforms", "mcb200_nccl_info"}
+                  "mcb200_test_uniforms", "mcb200_nccl_info", "mcb200_test_push_kernels"}
     assert exported - bound == diagnostic, sorted(exported - bound - diagnostic)
     assert bound <= exported, sorted(bound - exported)
 
