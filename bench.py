@@ -299,7 +299,8 @@ def run_b200(args):
     recPDF[0, :] = 0.0
     g.recPDF, g.totalLines = recPDF, tl
 
-    eng = PacketEngine(model, device=local, rank=rank, nranks=world, seed=SEED)
+    fake = int(os.environ.get("MCB_PACK_STATS", "0")) if world == 1 else 0      # diagnostic, see pack_stats()
+    eng = PacketEngine(model, device=local, rank=rank, nranks=fake or world, seed=SEED)
     eng.set_xsec(xsec)
     for opt in ("order", "agg_steps", "batch", "blocks_per_sm", "wavefront", "step_budget", "tail", "fly_batch", "wave0_order", "wave0_blocks", "wave0_exact"):
         if os.environ.get("MCB_" + opt.upper()):
@@ -313,6 +314,23 @@ def run_b200(args):
     upload_inputs()
     nGlobal = P * world
     dE = float(model.deltaE[1])
+
+    if fake:
+        # MCB_PACK_STATS=N on one GPU: what rank 0 of N would hand to the packed push -- how many of its
+        # partial sums need more than 32 bits, per element and per 256-element flag block
+        from mocassin_b200.api import _as_cuda_tensor
+        eng.zero_estimators()
+        eng.energyPacketDriver(1, P * fake, deltaE=dE)
+        ptr, n = eng.tally_buffer(1, 0)
+        q = _as_cuda_tensor(ptr, n, "<i8", local)
+        nblk = n // 256
+        out = {"pack_stats_for_ranks": fake, "elements": n}
+        for name, bits in (("over_32_bits", 32), ("over_24_bits", 24), ("over_16_bits", 16), ("non_zero", 0)):
+            m = (q >> bits) != 0 if bits else q != 0
+            out[name] = {"elements": float(m.float().mean()), "blocks_of_256": float(m[: nblk * 256].view(nblk, 256).any(1).float().mean())}
+            del m
+        print(json.dumps(out))
+        return
 
     # measured on 2 GPUs: splitting the batch in halves costs more (smaller waves, NCCL sharing
     # the SMs) than hiding half of the exchange gains -> off by default
@@ -342,6 +360,8 @@ def run_b200(args):
             eng.set_option("exchange_pack", int(os.environ["MCB_EXCHANGE_PACK"]))
         if os.environ.get("MCB_EXCHANGE_PUSH"):
             eng.set_option("exchange_push", int(os.environ["MCB_EXCHANGE_PUSH"]))
+        if os.environ.get("MCB_EXCHANGE_PUSH_BLOCKS"):
+            eng.set_option("exchange_push_blocks", int(os.environ["MCB_EXCHANGE_PUSH_BLOCKS"]))
         if os.environ.get("MCB_EXCHANGE_P2P"):
             eng.set_option("exchange_p2p", int(os.environ["MCB_EXCHANGE_P2P"]))
 

@@ -471,8 +471,10 @@ int mcb200_fetch_fates(mcb200_ctx *ctx, int32_t *fates, int64_t nPackets);
  *                   every rank) table over PCIe and all-gathers the slabs over NVLink (needs mcb200_comm_init)
  *   "exchange_p2p"  -1 auto / 0 / 1: fused peer-memory merge of the J tallies (mcb200_exchange_path)
  *   "exchange_pack" peer-memory merge, push variants: 1 (default) the partial sums travel packed -- the low 32 bits of
- *                   every element, the high 32 bits only of the 2048-element blocks in which one is non-zero, a flag
- *                   byte per block -- 4 instead of 8 bytes per element on the links; 0 plain 64-bit pushes
+ *                   every element, the high 32 bits only of the 256-element blocks in which one is non-zero, nothing
+ *                   of blocks that are zero altogether, a flag byte per block -- at most 4 instead of 8 bytes per
+ *                   element on the links; 0 plain 64-bit pushes
+ *   "exchange_push_blocks" CTAs per SM of the push kernels (default 4)
  *   "exchange_push" peer-memory merge: 1 (default) every rank pushes each peer's share of its partial sums into the
  *                   peer's receive buffer (device-to-device copies, posted writes), the owner sums locally; 2 the
  *                   same with a kernel that stores to all peers at once instead of copy after copy; 0 the owner

@@ -44,7 +44,7 @@ cudaError_t launch_p2p_push(const P2PPush &P, const unsigned long long *Q, size_
 struct P2PPackedPeers {
     unsigned int *lo[16];
     unsigned int *hi[16];
-    unsigned char *flag[16];
+    unsigned char *flag[16];             // see tables.cu
     int nranks, rank;
 };
 int p2p_pack_block();
@@ -173,6 +173,7 @@ struct GridState {
     std::vector<void *> peerQ, peerJ;     // [rank]; own entry = local pointer
     std::vector<void *> peerRecv;         // [rank]: every rank's receive buffer of the push variant (own = recvQ.p)
     DevBuf<unsigned long long> recvQ;     // (nranks-1) slots of slotStride partial sums pushed by the peers
+    DevBuf<unsigned char> flagStage;      // packed push: flag bytes per destination rank, staged locally
     size_t slotStride = 0, flagStride = 0;
     bool jPacked = false;                 // the pending push went out packed (low words + flagged high words)
     void *peerBaseQ = nullptr, *peerBaseJ = nullptr;   // local pointers the mappings were made for
@@ -270,6 +271,8 @@ struct mcb200_ctx {
     bool exchangeAllReduce = false;       // option exchange_allreduce: all-reduce the J planes (round-1 path) instead of
                                           // reduce-scatter -> fold the share -> all-gather float32
     int p2pMode = -1;                     // option exchange_p2p: -1 auto (peer memory when it can be mapped), 0 NCCL only, 1 required
+    int p2pPushBlocks = 4;                // option exchange_push_blocks: CTAs per SM of the push kernels (4 x 256 threads
+                                          // leave half of every SM to the NCCL kernels of the escape-count exchange)
     bool p2pPack = true;                  // option exchange_pack: packed push (4 bytes per element + flagged high words)
     int p2pPush = 1;                      // option exchange_push: peers push their partial sums (copies), the owner sums locally;
                                           // 0 = the owner pulls them with peer loads inside the merge kernel
@@ -277,6 +280,10 @@ struct mcb200_ctx {
     std::string lastP2PWhy;
     int lastExchangePath = 0;             // 0 none, 1 all-reduce, 2 reduce-scatter/all-gather (NCCL), 3 fused peer-memory kernel
     double lastPhaseMs[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    // MCB200_TRACE_EXCHANGE=1: host-clock marks of the exchange + merge of the last call, printed by rank 0
+    int traceOn = -1;
+    std::chrono::steady_clock::time_point traceT0;
+    std::vector<std::pair<const char *, double>> xtrace;
     DevBuf<unsigned char> ipcBuf;
     DevBuf<int> barrierWord;
     bool pdfSlabs = false;                // option pdf_slabs: 1/nranks of the PDF table per rank over PCIe, all-gather over NVLink
@@ -665,6 +672,14 @@ size_t slot_advance(size_t rOff, size_t count)
     return (rOff + count + 3 + blk - 1) / blk * blk;   // (+3: a share starts at its element index mod 4 inside the slot)
 }
 
+void trace_mark(mcb200_ctx *ctx, const char *what, bool reset = false)
+{
+    if (ctx->traceOn < 0) { const char *e = getenv("MCB200_TRACE_EXCHANGE"); ctx->traceOn = e && *e == '1' ? 1 : 0; }
+    if (!ctx->traceOn) return;
+    if (reset) { ctx->xtrace.clear(); ctx->traceT0 = std::chrono::steady_clock::now(); }
+    ctx->xtrace.push_back({what, std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - ctx->traceT0).count()});
+}
+
 int ensure_side_stream(mcb200_ctx *ctx)
 {
     if (!ctx->sideStream) {
@@ -695,27 +710,37 @@ int p2p_push_phase(mcb200_ctx *ctx, GridState &g, bool first)
     if (first) CU(cudaEventRecord(ctx->evPush0, ss));
     g.jPacked = false;
     if (ctx->p2pPack && g.jShards.size() <= 64) {
+        if (g.flagStage.n != (size_t)world * g.flagStride) CU(g.flagStage.alloc((size_t)world * g.flagStride));
         P2PPackedPeers PP{};
         PP.nranks = world; PP.rank = rank;
         for (int r = 0; r < world; ++r) {
             PP.lo[r] = (unsigned int *)g.peerRecv[r];
             PP.hi[r] = PP.lo[r] + (size_t)(world - 1) * g.slotStride;
-            PP.flag[r] = (unsigned char *)((unsigned long long *)g.peerRecv[r] + (size_t)(world - 1) * g.slotStride);
+            PP.flag[r] = g.flagStage.p + (size_t)r * g.flagStride;
         }
         size_t rOff = 0;
         for (auto &r : g.jShards) {
-            CU(launch_p2p_push_packed(PP, g.JsteQ.p, r.off, r.count, rOff, g.slotStride, g.flagStride, ctx->numSMs * 16, ss));
-            // what was handed over is cleared by a separate pass (a store to a line whose load is still in
-            // flight inside the push kernel takes a slow path: measured 2.4x on the whole kernel)
-            if (rank > 0) CU(cudaMemsetAsync(g.JsteQ.p + r.off, 0, (size_t)rank * r.count * 8, ss));
-            if (rank + 1 < world) CU(cudaMemsetAsync(g.JsteQ.p + r.off + (size_t)(rank + 1) * r.count, 0, (size_t)(world - 1 - rank) * r.count * 8, ss));
+            CU(launch_p2p_push_packed(PP, g.JsteQ.p, r.off, r.count, rOff, g.slotStride, g.flagStride, ctx->numSMs * ctx->p2pPushBlocks, ss));
             rOff = slot_advance(rOff, r.count);
             ctx->lastExchangeBytes += (int64_t)r.count * (int64_t)(world - 1) * 4;   // + the flagged high words (not counted)
         }
-        g.jPacked = true;
+        for (int d = 1; d < world; ++d) {            // the flag bytes: one copy per peer
+            const int r = (rank + d) % world, slot = rank < r ? rank : rank - 1;
+            unsigned char *dst = (unsigned char *)((unsigned long long *)g.peerRecv[r] + (size_t)(world - 1) * g.slotStride) + (size_t)slot * g.flagStride;
+            CU(cudaMemcpyAsync(dst, g.flagStage.p + (size_t)r * g.flagStride, rOff / (size_t)p2p_pack_block(), cudaMemcpyDeviceToDevice, ss));
+        }
         CU(cudaEventRecord(ctx->evMid, ss));
         ctx->evMidSet = true;
-        CU(cudaEventRecord(ctx->pushDone, ss));
+        CU(cudaEventRecord(ctx->pushDone, ss));      // the merge may start here ...
+        // ... while what was handed over is cleared behind it on the side stream (disjoint from the share the
+        // merge kernel reads and clears; the library stream joins the side stream at the end of the fold).
+        // A separate pass, because a store to a line whose load is still in flight inside the push kernel
+        // takes a slow path: measured 2.4x on the whole kernel
+        for (auto &r : g.jShards) {
+            if (rank > 0) CU(cudaMemsetAsync(g.JsteQ.p + r.off, 0, (size_t)rank * r.count * 8, ss));
+            if (rank + 1 < world) CU(cudaMemsetAsync(g.JsteQ.p + r.off + (size_t)(rank + 1) * r.count, 0, (size_t)(world - 1 - rank) * r.count * 8, ss));
+        }
+        g.jPacked = true;
         return MCB200_OK;
     }
     {
@@ -725,7 +750,7 @@ int p2p_push_phase(mcb200_ctx *ctx, GridState &g, bool first)
             PP.nranks = world; PP.rank = rank;
             for (int r = 0; r < world; ++r) PP.recv[r] = (unsigned long long *)g.peerRecv[r];
             for (auto &r : g.jShards) {
-                CU(launch_p2p_push(PP, g.JsteQ.p, r.off, r.count, g.slotStride, rOff, ctx->numSMs * 16, ss));
+                CU(launch_p2p_push(PP, g.JsteQ.p, r.off, r.count, g.slotStride, rOff, ctx->numSMs * ctx->p2pPushBlocks, ss));
                 rOff = slot_advance(rOff, r.count);
                 ctx->lastExchangeBytes += (int64_t)r.count * (int64_t)(world - 1) * 12;
             }
@@ -1409,7 +1434,7 @@ int comm_allreduce(mcb200_ctx *ctx, void *buf, size_t count, int dtype, int op)
 
 // escape counts of one grid: all-gather of every rank's non-zero (index, count) pairs when that
 // moves fewer bytes than the dense all-reduce of the touched planes (PacketEngine._exchange_escaped_sparse)
-int comm_exchange_escaped(mcb200_ctx *ctx, GridState &g, const std::vector<std::pair<int, int>> &ranges)
+int comm_exchange_escaped(mcb200_ctx *ctx, GridState &g, const std::vector<std::pair<int, int>> &ranges, int64_t preCompacted = -1)
 {
     NcclApi &N = nccl_api();
     const int nb = ctx->cfg.nbins, world = ctx->nranks;
@@ -1418,9 +1443,12 @@ int comm_exchange_escaped(mcb200_ctx *ctx, GridState &g, const std::vector<std::
     size_t planes = 0;
     for (auto &rg : ranges) planes += (size_t)(rg.second - rg.first + 1);
     const unsigned long long dense = 2ull * 4ull * nR * (unsigned long long)(ctx->cfg.nAngleBins + 1) * planes;
-    int64_t n = 0;
-    int rc = esc_compact(ctx, g, 0, &n);
-    if (rc) return rc;
+    int64_t n = preCompacted;
+    int rc = 0;
+    if (n < 0) {
+        rc = esc_compact(ctx, g, 0, &n);
+        if (rc) return rc;
+    }
     CU(ctx->commSizes.alloc((size_t)world + 1));
     unsigned long long mine = (unsigned long long)n;
     CU(cudaMemcpyAsync(ctx->commSizes.p + world, &mine, 8, cudaMemcpyHostToDevice, s));
@@ -1428,6 +1456,7 @@ int comm_exchange_escaped(mcb200_ctx *ctx, GridState &g, const std::vector<std::
     std::vector<unsigned long long> all(world);
     CU(cudaMemcpyAsync(all.data(), ctx->commSizes.p, 8 * (size_t)world, cudaMemcpyDeviceToHost, s));
     CU(cudaStreamSynchronize(s));
+    trace_mark(ctx, "exchange: escape lists compacted, sizes gathered");
     unsigned long long maxn = 0;
     for (auto v : all) maxn = v > maxn ? v : maxn;
     if (ctx->exchangeDense || 16ull * maxn * (unsigned long long)world >= dense) {
@@ -1499,16 +1528,30 @@ int comm_exchange(mcb200_ctx *ctx)
         if (rc) return rc;
     }
     bool pushed = false;
+    trace_mark(ctx, "exchange: start", true);
     for (size_t ig = 0; ig < ctx->grids.size(); ++ig) {
         GridState &g = ctx->grids[ig];
         if (!g.set || !g.JsteQ.p) continue;
         const size_t nR = (size_t)g.nCells + 1;
+        int rc = 0;
+        // Peer-memory push path: this rank's escape counts are compacted FIRST -- a scan of its own touched
+        // planes that needs nothing from the peers, so it runs while the slower ranks are still transporting,
+        // and it is out of the way of the push kernels (which would otherwise hold every SM until they end:
+        // measured 7.4 ms from "pushes issued" to "lists compacted" at N=2, against ~1 ms for the scan alone)
+        int64_t escN = -1;
+        if (!ctx->sedLocal && !ctx->exchangeAllReduce && ctx->nranks > 1 && ctx->p2pMode != 0 && !ctx->cfg.lgDebug &&
+            ctx->p2pState == 1 && ctx->p2pPush) {
+            rc = esc_compact(ctx, g, 0, &escN);
+            if (rc) return rc;
+            trace_mark(ctx, "exchange: own escape counts compacted");
+        }
         // which nu-planes did any rank touch
-        int rc = comm_allreduce(ctx, g.nuTouched.p, g.nuTouched.n, kNcclInt32, kNcclMax);
+        rc = comm_allreduce(ctx, g.nuTouched.p, g.nuTouched.n, kNcclInt32, kNcclMax);
         if (rc) return rc;
         std::vector<int> flag(nb + 1, 0);
         CU(cudaMemcpyAsync(flag.data(), g.nuTouched.p, sizeof(int) * (nb + 1), cudaMemcpyDeviceToHost, s));
         CU(cudaStreamSynchronize(s));
+        trace_mark(ctx, "exchange: flags max-reduced (ranks in step)");
         auto ranges = touched_ranges(flag);
         g.jShards.clear();
         g.jShardsP2P = false;
@@ -1527,7 +1570,7 @@ int comm_exchange(mcb200_ctx *ctx)
         if (!ctx->sedLocal && !escLater) {
             // the escape counts first: their exchange has data-dependent sizes (host round trips), which
             // must not queue up behind the bulk transfer of the J planes on the same stream
-            rc = comm_exchange_escaped(ctx, g, ranges);
+            rc = comm_exchange_escaped(ctx, g, ranges, escN);
             if (rc) return rc;
         }
         NC(nccl_api().GroupStart());
@@ -1559,17 +1602,20 @@ int comm_exchange(mcb200_ctx *ctx)
             g.jShards.push_back({off, len, count});
         }
         NC(nccl_api().GroupEnd());
+        trace_mark(ctx, "exchange: range tails issued");
         g.jShardsP2P = p2p && !g.jShards.empty();
         if (g.jShardsP2P && ctx->p2pPush) {
             // the bulk of the exchange starts now, on the side stream (copy engines + links) ...
             rc = p2p_push_phase(ctx, g, !pushed);
             if (rc) return rc;
             pushed = true;
+            trace_mark(ctx, "exchange: pushes issued (side stream)");
         }
         // ... beside the escape counts on the library stream
         if (!ctx->sedLocal && escLater) {
-            rc = comm_exchange_escaped(ctx, g, ranges);
+            rc = comm_exchange_escaped(ctx, g, ranges, escN);
             if (rc) return rc;
+            trace_mark(ctx, "exchange: escape counts issued");
         }
         if (ctx->cfg.lgDebug && g.lineQ.n) {
             rc = comm_allreduce(ctx, g.lineQ.p, g.lineQ.n, kNcclUint32, kNcclSum);
@@ -1581,6 +1627,7 @@ int comm_exchange(mcb200_ctx *ctx)
         }
     }
     CU(cudaStreamSynchronize(s));
+    trace_mark(ctx, "exchange: library stream drained");
     return MCB200_OK;
 }
 
@@ -2172,8 +2219,16 @@ int mcb200_reduce(mcb200_ctx *ctx)
 {
     NEED_CTX();
     auto t0 = std::chrono::steady_clock::now();
+    trace_mark(ctx, "reduce: start");
     int rc = fold_pending(ctx);
     ctx->lastPhaseMs[1] = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
+    trace_mark(ctx, "reduce: done");
+    if (ctx->traceOn == 1 && ctx->rank == 0 && !ctx->xtrace.empty()) {
+        fprintf(stderr, "[mcb200 trace]");
+        for (auto &m : ctx->xtrace) fprintf(stderr, " | %s %.3f", m.first, m.second);
+        fprintf(stderr, " | device: pushes %.3f ms, merge %.3f ms\n", ctx->lastPhaseMs[3], ctx->lastPhaseMs[2]);
+        ctx->xtrace.clear();
+    }
     return rc;
 }
 
@@ -2714,6 +2769,11 @@ int mcb200_set_option(mcb200_ctx *ctx, const char *name, int64_t value)
     if (!strcmp(name, "epoch")) { ctx->epoch = value; return MCB200_OK; }
     if (!strcmp(name, "pdf_slabs")) { ctx->pdfSlabs = value != 0; return MCB200_OK; }
     if (!strcmp(name, "exchange_pack")) { ctx->p2pPack = value != 0; return MCB200_OK; }
+    if (!strcmp(name, "exchange_push_blocks")) {
+        if (value < 1 || value > 64) return fail(ctx, MCB200_EINVAL, "exchange_push_blocks must be 1..64");
+        ctx->p2pPushBlocks = (int)value;
+        return MCB200_OK;
+    }
     if (!strcmp(name, "exchange_push")) { ctx->p2pPush = (int)value; return MCB200_OK; }
     if (!strcmp(name, "exchange_p2p")) { ctx->p2pMode = (int)value; if (ctx->p2pState < 0) ctx->p2pState = 0; return MCB200_OK; }
     if (!strcmp(name, "solo")) {

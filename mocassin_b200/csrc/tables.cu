@@ -248,7 +248,8 @@ cudaError_t launch_p2p_push(const P2PPush &P, const unsigned long long *Q, size_
 // A rank's partial sum of one (cell, nu) element rarely needs more than 32 bits (the unit is 2^-24 of
 // the smallest cell half-width; only the cells next to a source collect more per call).  The packed
 // push sends the low words of every element, and the high words only of the blocks of kPackBlk
-// consecutive elements in which some high word is non-zero, with one flag byte per block; the owner
+// consecutive elements in which some high word is non-zero, with one flag byte per block (blocks
+// that are zero altogether send the flag alone); the owner
 // rebuilds the 64-bit values (low + (high << 32) where flagged) and sums them as before: exact.
 // j = index inside this rank's share of ALL exchanged ranges (ranges back to back, rOff of each);
 // receive buffer of a rank: low words [slot][j], high words [slot][j], flags [slot][j / kPackBlk].
@@ -256,7 +257,9 @@ constexpr int kPackBlk = 256;           // elements per flag (8 per lane of one 
 struct P2PPackedPeers {
     unsigned int *lo[16];
     unsigned int *hi[16];
-    unsigned char *flag[16];
+    unsigned char *flag[16];             // flags of the blocks sent to rank r, [rOff / kPackBlk + block]: a LOCAL staging
+                                         // array, copied to the peer in one piece afterwards (2.3x10^6 one-byte peer
+                                         // stores -- partial-sector writes across the link -- bounded the kernel at ~4 ms)
     int nranks, rank;
 };
 
@@ -302,6 +305,11 @@ __global__ void __launch_bounds__(256) p2p_push_packed_kernel(const __grid_const
             }
             unsigned int anyHi = 0u;
             unsigned int *lo = P.lo[r] + (size_t)slot * slotStride + rOff;
+            const unsigned long long nz = v[0][0] | v[0][1] | v[0][2] | v[0][3] | v[1][0] | v[1][1] | v[1][2] | v[1][3];
+            if (!__any_sync(0xffffffffu, nz != 0ull)) {       // nothing in this block (37 % of them at 128^3x600): flag only
+                if (lane == 0) P.flag[r][rOff / kPackBlk + b] = (unsigned char)2;
+                continue;
+            }
 #pragma unroll
             for (int k = 0; k < 2; ++k) {
                 const size_t j = gs[k] - A;
@@ -313,7 +321,7 @@ __global__ void __launch_bounds__(256) p2p_push_packed_kernel(const __grid_const
                 anyHi |= (unsigned int)((v[k][0] | v[k][1] | v[k][2] | v[k][3]) >> 32);
             }
             const int any = __any_sync(0xffffffffu, anyHi != 0u);
-            if (lane == 0) P.flag[r][(size_t)slot * flagStride + rOff / kPackBlk + b] = (unsigned char)(any ? 1 : 0);
+            if (lane == 0) P.flag[r][rOff / kPackBlk + b] = (unsigned char)(any ? 1 : 0);
             if (any) {
                 unsigned int *hi = P.hi[r] + (size_t)slot * slotStride + rOff;
 #pragma unroll
@@ -358,7 +366,9 @@ __global__ void __launch_bounds__(256) p2p_sum_fold_packed_kernel(const __grid_c
 #pragma unroll
         for (int sl = 0; sl < (N > 0 ? N - 1 : 15); ++sl)
             if (sl < nr - 1) {
-                const bool f = flag[(size_t)sl * flagStride + j / kPackBlk] != 0;
+                const unsigned char fb = flag[(size_t)sl * flagStride + j / kPackBlk];   // 0 low words, 1 low + high, 2 nothing
+                if (fb == 2) continue;
+                const bool f = fb == 1;
                 if (full) {
                     const uint4 l = __ldcs(reinterpret_cast<const uint4 *>(lo + (size_t)sl * slotStride + j));
                     uint4 h = make_uint4(0u, 0u, 0u, 0u);
@@ -473,20 +483,32 @@ __global__ void esc_compact_kernel(unsigned int *__restrict__ Q, size_t off, siz
                                    unsigned long long *__restrict__ list, unsigned long long *count,
                                    unsigned long long capacity, int clear)
 {
-    size_t i0 = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-    size_t stride = (size_t)gridDim.x * blockDim.x;
+    // four independent 128 B loads per warp and trip (one was latency bound: 3 ms for 5 GB), one atomic per warp
     const unsigned int lane = threadIdx.x & 31u;
-    for (size_t base = i0 - lane; base < len; base += stride) {
-        size_t i = base + lane;
-        unsigned int q = i < len ? Q[off + i] : 0u;
-        unsigned int m = __ballot_sync(0xffffffffu, q != 0u);
-        if (!m) continue;
+    const size_t warp = ((size_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5, nWarps = ((size_t)gridDim.x * blockDim.x) >> 5;
+    for (size_t base = warp * 128; base < len; base += nWarps * 128) {
+        unsigned int q[4], m[4];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            const size_t i = base + (size_t)k * 32 + lane;
+            q[k] = i < len ? Q[off + i] : 0u;
+        }
+        unsigned int total = 0;
+#pragma unroll
+        for (int k = 0; k < 4; ++k) { m[k] = __ballot_sync(0xffffffffu, q[k] != 0u); total += __popc(m[k]); }
+        if (!total) continue;
         unsigned long long p = 0;
-        if (lane == 0) p = atomicAdd(count, (unsigned long long)__popc(m));
-        p = __shfl_sync(0xffffffffu, p, 0) + __popc(m & ((1u << lane) - 1u));
-        if (q != 0u) {
-            if (list && p < capacity) { list[2 * p] = (unsigned long long)(off + i); list[2 * p + 1] = q; }
-            if (clear) Q[off + i] = 0u;
+        if (lane == 0) p = atomicAdd(count, (unsigned long long)total);
+        p = __shfl_sync(0xffffffffu, p, 0);
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            if (q[k] != 0u) {
+                const size_t i = base + (size_t)k * 32 + lane;
+                const unsigned long long at = p + __popc(m[k] & ((1u << lane) - 1u));
+                if (list && at < capacity) { list[2 * at] = (unsigned long long)(off + i); list[2 * at + 1] = q[k]; }
+                if (clear) Q[off + i] = 0u;
+            }
+            p += __popc(m[k]);
         }
     }
 }

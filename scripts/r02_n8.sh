@@ -3,8 +3,8 @@ N=${1:-8}
 nvidia-smi -L | head -8
 TR="timeout 300 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29511 bench.py --gpus $N --no-cpu"
 $TR --steps 8 --warmup 3 > gpurun_out/r02_bench_n$N.json 2> gpurun_out/r02_bench_n$N.err
-MCB_EXCHANGE_P2P=0 $TR --steps 5 --warmup 3 --no-e2e > gpurun_out/r02_bench_n${N}_nccl.json 2> gpurun_out/r02_bench_n${N}_nccl.err
-for f in n$N n${N}_nccl; do python - <<PY
+if [ -n "$NCCL_LEG" ]; then MCB_EXCHANGE_P2P=0 $TR --steps 5 --warmup 3 --no-e2e > gpurun_out/r02_bench_n${N}_nccl.json 2> gpurun_out/r02_bench_n${N}_nccl.err; fi
+for f in n$N ${NCCL_LEG:+n${N}_nccl}; do python - <<PY
 import json
 try:
     d=json.loads(open("gpurun_out/r02_bench_$f.json").read().strip().splitlines()[-1])
