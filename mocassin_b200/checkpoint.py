@@ -48,8 +48,41 @@ def write_grid0(path: str, model: Model, lgConverged: Optional[Sequence[np.ndarr
             fh.writelines(lines)
 
 
-def read_grid0(path: str):
-    """Inverse of write_grid0 -> (grids [axes, active, nCells, motherP], R_out, lgConverged, lgBlack)."""
+def _ytop(iG: int, g, lg2D: bool) -> int:
+    """Planes of y a checkpoint file holds for grid iG (0-based): writeGrid writes only j = 1 of the
+    mother grid of a 2D run (grid_mod.f90:2709-2713).  (resetGrid, :3412-3416, applies yTop = 1 to
+    every grid it reads; the files it reads are writeGrid's, so the readers here follow the writer.)"""
+    return 1 if (iG == 0 and lg2D) else g.ny
+
+
+def fill_2d_planes(g: Grid) -> np.ndarray:
+    """resetGrid's completion of a 2D mother grid (grid_mod.f90:3476-3500): the cells of the planes
+    j >= 2 point at the cell of plane 1 whose x is nearest to their cylindrical radius
+    sqrt(x^2 + y^2); returns TwoDscaleJ(1:nCells) (index 0 unused) = cells sharing each id."""
+    from .model import locate
+
+    act = np.asarray(g.active)
+    scale = np.ones(g.nCells + 1, F32)
+    x = np.asarray(g.xAxis, F32)
+    for i in range(g.nx):
+        for j in range(1, g.ny):
+            a, b = F32(x[i] / F32(1.e10)), F32(g.yAxis[j] / F32(1.e10))
+            radius = F32(F32(1.e10) * np.sqrt(F32(F32(a * a) + F32(b * b))))
+            xP = locate(x, radius)
+            if xP < g.nx:
+                if radius >= F32(F32(x[xP - 1] + x[xP]) / F32(2.0)):
+                    xP += 1
+            for k in range(g.nz):
+                act[i, j, k] = act[xP - 1, 0, k]
+                if act[xP - 1, 0, k] > 0:
+                    scale[act[xP - 1, 0, k]] += F32(1.0)
+    return scale
+
+
+def read_grid0(path: str, lg2D: bool = False):
+    """Inverse of write_grid0 -> (grids [axes, active, nCells, motherP], R_out, lgConverged, lgBlack).
+    lg2D: only plane j = 1 of the mother grid is in the file; the other planes are completed as
+    resetGrid does (:func:`fill_2d_planes`)."""
     tok = open(path).read().split()
     p = 0
     grids: List[Grid] = []
@@ -64,29 +97,34 @@ def read_grid0(path: str):
         ax = []
         for n in (nx, ny, nz):
             ax.append(np.array([float(t) for t in tok[p:p + n]], dtype=F32)); p += n
-        vals = np.array([int(t) for t in tok[p:p + 3 * nx * ny * nz]], dtype=np.int64).reshape(nx, ny, nz, 3); p += 3 * nx * ny * nz
-        active = np.asfortranarray(vals[..., 0].astype(I32))
+        yTop = 1 if (lg2D and not grids) else ny
+        vals = np.array([int(t) for t in tok[p:p + 3 * nx * yTop * nz]], dtype=np.int64).reshape(nx, yTop, nz, 3); p += 3 * nx * yTop * nz
+        active = np.zeros((nx, ny, nz), I32, order="F")
+        active[:, :yTop, :] = vals[..., 0]
         conv = np.zeros(nCells + 1, I32); black = np.zeros(nCells + 1, I32)
-        m = active > 0
-        conv[active[m]] = vals[..., 1][m]; black[active[m]] = vals[..., 2][m]
+        m = vals[..., 0] > 0
+        conv[vals[..., 0][m]] = vals[..., 1][m]; black[vals[..., 0][m]] = vals[..., 2][m]
         grids.append(Grid(xAxis=ax[0], yAxis=ax[1], zAxis=ax[2], active=active, nCells=nCells, motherP=motherP))
+        if yTop != ny:
+            fill_2d_planes(grids[-1])
         convs.append(conv); blacks.append(black)
         if len(grids) == nGrids:
             break
     return grids, R_out, convs, blacks
 
 
-def write_dust_grid(path: str, model: Model, lgMultiChemistry: bool = False, totalDustMass: float = 0.0) -> None:
+def write_dust_grid(path: str, model: Model, lgMultiChemistry: bool = False, totalDustMass: float = 0.0,
+                    lg2D: bool = False) -> None:
     """dustGrid.out, grid_mod.f90:2746-2757,2771-2775: per cell of the x,y,z loop ``Ndust``
     (``Ndust dustAbunIndex`` with lgMultiChemistry -- sic, the gas flag) and nSizes+1 lines of
     ``Tdust(0:nSpeciesMax, ai, cell)``; cell 0 stands in for inactive cells."""
     with open(path, "w") as fh:
-        for g in model.grids:
+        for iG, g in enumerate(model.grids):
             act = np.asarray(g.active)
             T = np.asarray(g.Tdust, dtype=F32)
             lines = []
             for i in range(g.nx):
-                for j in range(g.ny):
+                for j in range(_ytop(iG, g, lg2D)):
                     for k in range(g.nz):
                         c = int(act[i, j, k])
                         c = 0 if c < 0 else c
@@ -102,17 +140,18 @@ def write_dust_grid(path: str, model: Model, lgMultiChemistry: bool = False, tot
         fh.write(f" Total dust mass [Msol]:  {_r(F32(totalDustMass) * F32(5.028e11))}\n")
 
 
-def read_dust_grid(path: str, model: Model, lgMultiChemistry: bool = False) -> None:
+def read_dust_grid(path: str, model: Model, lgMultiChemistry: bool = False, lg2D: bool = False) -> None:
     """Fill Ndust, dustAbunIndex and Tdust of model.grids from dustGrid.out (resetGrid's dust part)."""
     tok = open(path).read().split()
     p = 0
     nS, nZ = model.nSpeciesMax + 1, model.nSizes + 1
     per = (2 if lgMultiChemistry else 1) + nS * nZ
-    for g in model.grids:
-        n = g.nx * g.ny * g.nz
+    for iG, g in enumerate(model.grids):
+        yTop = _ytop(iG, g, lg2D)
+        n = g.nx * yTop * g.nz
         block = tok[p:p + per * n]; p += per * n
-        a = np.array([float(t) for t in block], dtype=np.float64).reshape(g.nx, g.ny, g.nz, per)
-        act = np.asarray(g.active)
+        a = np.array([float(t) for t in block], dtype=np.float64).reshape(g.nx, yTop, g.nz, per)
+        act = np.asarray(g.active)[:, :yTop, :]
         m = act > 0
         g.Ndust = np.zeros(g.nCells + 1, F32)
         g.Ndust[act[m]] = a[..., 0][m]
@@ -122,7 +161,7 @@ def read_dust_grid(path: str, model: Model, lgMultiChemistry: bool = False) -> N
             g.dustAbunIndex[act[m]] = a[..., 1][m].astype(I32)
             off = 2
         T = np.zeros((nS, nZ, g.nCells + 1), dtype=F32, order="F")
-        body = a[..., off:].reshape(g.nx, g.ny, g.nz, nZ, nS)       # lines: ai, values: species
+        body = a[..., off:].reshape(g.nx, yTop, g.nz, nZ, nS)       # lines: ai, values: species
         T[:, :, act[m]] = np.transpose(body[m], (2, 1, 0))
         g.Tdust = T
 
@@ -178,22 +217,29 @@ def write_grid1(path: str, model: Model, Te: Sequence[np.ndarray], Ne: Sequence[
             fh.writelines(lines)
 
 
-def read_grid1(path: str, grids: Sequence[Grid], multi_chemistry: bool = False):
-    """-> (Te, Ne, Hden, abFileIndex) lists per grid, arrays (0:nCells) / (nx,ny,nz)."""
+def read_grid1(path: str, grids: Sequence[Grid], multi_chemistry: bool = False, lg2D: bool = False):
+    """-> (Te, Ne, Hden, abFileIndex) lists per grid, arrays (0:nCells) / (nx,ny,nz) (abFileIndex of a
+    2D mother grid: plane j = 1 only, the other planes stay 1 as resetGrid leaves them)."""
     tok = open(path).read().split()
     p = 0
     per = 4 if multi_chemistry else 3
     out = ([], [], [], [])
-    for g in grids:
-        n = g.nx * g.ny * g.nz
-        a = np.array([float(t) for t in tok[p:p + per * n]]).reshape(g.nx, g.ny, g.nz, per); p += per * n
-        act = np.asarray(g.active)
+    for iG, g in enumerate(grids):
+        yTop = _ytop(iG, g, lg2D)
+        n = g.nx * yTop * g.nz
+        a = np.array([float(t) for t in tok[p:p + per * n]]).reshape(g.nx, yTop, g.nz, per); p += per * n
+        act = np.asarray(g.active)[:, :yTop, :]
         m = act > 0
         for q in range(3):
             v = np.zeros(g.nCells + 1, F32)
             v[act[m]] = a[..., q][m]
             out[q].append(v)
-        out[3].append(np.asfortranarray(a[..., 3].astype(I32)) if multi_chemistry else None)
+        if multi_chemistry:
+            ab = np.ones((g.nx, g.ny, g.nz), I32, order="F")
+            ab[:, :yTop, :] = a[..., 3].astype(I32)
+            out[3].append(ab)
+        else:
+            out[3].append(None)
     return out
 
 
@@ -217,17 +263,17 @@ def write_grid2(path: str, model: Model, ionDen: Sequence[np.ndarray], lgElement
             fh.writelines(lines)
 
 
-def read_grid2(path: str, grids: Sequence[Grid], lgElementOn, elementXref, nstages: int):
+def read_grid2(path: str, grids: Sequence[Grid], lgElementOn, elementXref, nstages: int, lg2D: bool = False):
     """-> ionDen per grid, (0:nCells, nElementsUsed, nstages) F-order (resetGrid, :3440-3452)."""
     tok = open(path).read().split()
     p = 0
     on = [e for e in range(1, 31) if lgElementOn[e - 1]]
     out = []
-    for g in grids:
+    for iG, g in enumerate(grids):
         d = np.zeros((g.nCells + 1, len(on), nstages), dtype=F32, order="F")
         act = np.asarray(g.active)
         for i in range(g.nx):
-            for j in range(g.ny):
+            for j in range(_ytop(iG, g, lg2D)):
                 for k in range(g.nz):
                     c = int(act[i, j, k])
                     for e in on:

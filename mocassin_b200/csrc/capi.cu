@@ -1748,12 +1748,22 @@ int mcb200_set_grid(mcb200_ctx *ctx, int32_t iG, int32_t nx, int32_t ny, int32_t
     g->geo[0] = (g->hx[nx - 1] - g->hx[nx - 2]) / 2.f;
     g->geo[1] = (g->hy[ny - 1] - g->hy[ny - 2]) / 2.f;
     g->geo[2] = (g->hz[nz - 1] - g->hz[nz - 2]) / 2.f;
-    // path-length quantum: smallest cell width / 2^24, rounded down to a power of two
-    double wmin = 1e300;
+    // path-length quantum: smallest cell width / 2^24, rounded down to a power of two -- but not below the
+    // largest cell width / 2^33, so that on strongly graded axes (benchmarks/dust/2D: spacing ratio 10^5) a
+    // (cell, nu) element still holds > 6x10^7 diagonal crossings of the widest cell before its sum reaches 2^63
+    double wmin = 1e300, wmax = 0.0;
     for (auto *ax : {&g->hx, &g->hy, &g->hz})
-        for (size_t i = 1; i < ax->size(); ++i) wmin = std::fmin(wmin, (double)(*ax)[i] - (double)(*ax)[i - 1]);
+        for (size_t i = 1; i < ax->size(); ++i) {
+            const double w = (double)(*ax)[i] - (double)(*ax)[i - 1];
+            wmin = std::fmin(wmin, w);
+            wmax = std::fmax(wmax, w);
+        }
     wmin *= 0.5;
-    g->lenExp = (int)std::floor(std::log2(wmin)) - 24;
+    wmax *= 0.5;
+    {
+        const int eFine = (int)std::floor(std::log2(wmin)) - 24, eCap = (int)std::floor(std::log2(wmax)) - 33;
+        g->lenExp = eFine > eCap ? eFine : eCap;
+    }
     cudaStream_t s = ctx->stream;
     CU(g->xAxis.upload(g->hx.data(), nx, s)); CU(g->yAxis.upload(g->hy.data(), ny, s)); CU(g->zAxis.upload(g->hz.data(), nz, s));
     auto wx = make_walls(g->hx), wy = make_walls(g->hy), wz = make_walls(g->hz);

@@ -726,7 +726,8 @@ def iterate_dust(deck: Deck, model: Model, step: Callable[[int, float], tuple], 
         nTot = 2 * nPhotons               # nPhotonsTot = nPhotons(1) + sum over stars (:1106-1109)
         if it > 1 and tot < F32(95.0) and deck.lgAutoPackets and nTot < deck.maxPhotons and totOld > 0:
             if F32(F32(tot - totOld) / totOld) <= F32(deck.convIncPercent):
-                nPhotons = int(np.rint(F32(nPhotons) * F32(deck.nPhotIncrease)))
+                # nint(): half away from zero (iteration_mod.f90:1113), not numpy's half-to-even
+                nPhotons = int(np.floor(np.float64(F32(nPhotons) * F32(deck.nPhotIncrease)) + 0.5))
                 deltaE = F32(deltaE / F32(deck.nPhotIncrease))
         totOld = tot
         if tot >= F32(deck.minConvergence):

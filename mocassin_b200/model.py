@@ -74,8 +74,12 @@ class Grid:
         return gx, gy, gz
 
     def min_cell_width(self) -> float:
-        w = min(float(np.min(np.diff(a))) for a in (self.xAxis, self.yAxis, self.zAxis))
+        w = min(float(np.min(np.diff(a.astype(np.float64)))) for a in (self.xAxis, self.yAxis, self.zAxis))
         return w / 2.0  # the symmetric first cell is half a spacing wide
+
+    def max_cell_width(self) -> float:
+        w = max(float(np.max(np.diff(a.astype(np.float64)))) for a in (self.xAxis, self.yAxis, self.zAxis))
+        return w / 2.0
 
     def cell_volumes(self, symmetric: bool) -> np.ndarray:
         """dV(0:nCells) in 1e45 cm^3, float32 arithmetic of photon_mod.f90:1469-1512
@@ -189,9 +193,12 @@ class Model:
 
     def len_unit_exponent(self, g: Grid) -> int:
         """Exponent e of the power-of-two path-length unit 2^e [cm] of grid g's
-        fixed-point J tally: smallest cell width / 2^24, rounded down to a power of 2."""
-        w = g.min_cell_width()
-        return int(np.floor(np.log2(w))) - 24
+        fixed-point J tally: smallest cell width / 2^24, rounded down to a power of 2 -- but not
+        below the largest cell width / 2^33 (strongly graded axes: head room of the 64-bit sums).
+        The same rule as mcb200_set_grid (capi.cu), on the same float32 axis values."""
+        e_fine = int(np.floor(np.log2(g.min_cell_width()))) - 24
+        e_cap = int(np.floor(np.log2(g.max_cell_width()))) - 33
+        return max(e_fine, e_cap)
 
 
 def locate(xa: np.ndarray, x: float) -> int:

@@ -22,7 +22,7 @@ updateCell / thermBalance (nPhotoSte, nPhotoDif per element and ion, heatSte, he
 getOuterShell's shell numbers) on seeded inputs built by tests/ref_cases.py.  ref_aux_sed_<case>.npz:
 ref_aux_taunu_<case>.npz: the three optical-depth columns writeTauNu writes to output/tauNu.out.  ref_aux_mie.npz: BHmie, getQs, linearMap and the assembly of makeDustXsec on seeded inputs.  ref_aux_contcube_<case>.npz: the records writeContCube writes to output/contCube.out.  ref_aux_sed: 
 what writeSED writes to output/SED.out (nu, lambda, SED per viewing angle, total energy) for the
-escapedPackets of the transport case of the same name.  ref_aux_writegrid.json: the records
+escapedPackets of the transport case of the same name.  ref_aux_writegrid.json (and _2d: with the 2D flag set): the records
 writeGrid writes to grid0-3.out, dustGrid.out and photoSource.out (numbers rendered with
 checkpoint.py's format; list-directed formatting is the compiler's business).
 """
@@ -41,11 +41,11 @@ import ref_cases  # noqa: E402
 
 def main(names):
     for name in names or list(ref_cases.REF_CASES) + list(ref_cases.AUX_CASES) + list(ref_cases.PHOTO_CASES) + \
-            ["sed:" + c for c in ref_cases.SED_CASES] + ["contcube:" + c for c in ref_cases.SED_CASES] + ["taunu:" + c for c in ref_cases.TAUNU_CASES] + ["mie", "starpos", "writegrid"]:
-        if name == "writegrid":
+            ["sed:" + c for c in ref_cases.SED_CASES] + ["contcube:" + c for c in ref_cases.SED_CASES] + ["taunu:" + c for c in ref_cases.TAUNU_CASES] + ["mie", "starpos", "writegrid", "writegrid_2d"]:
+        if name in ("writegrid", "writegrid_2d"):
             import json
-            res = ref_cases.run_reference_writegrid()
-            path = os.path.join(HERE, "ref_aux_writegrid.json")
+            res = ref_cases.run_reference_writegrid(lg2D=name.endswith("_2d"))
+            path = os.path.join(HERE, f"ref_aux_{name}.json")
             with open(path, "w") as fh:
                 json.dump(res, fh, indent=0)
             print(f"{name}: {os.path.getsize(path)} bytes, " + ", ".join(f"{k}: {len(v)} records" for k, v in res.items()))

@@ -601,7 +601,7 @@ def run_reference_contcube(name):
 GRID_FILES = {21: "grid0.out", 20: "grid1.out", 30: "grid2.out", 40: "grid3.out", 50: "dustGrid.out", 42: "photoSource.out"}
 
 
-def writegrid_inputs():
+def writegrid_inputs(lg2D=False):
     from mocassin_b200 import checkpoint as ck
 
     F32 = np.float32
@@ -616,7 +616,7 @@ def writegrid_inputs():
     xref = np.zeros(30, np.int32)
     xref[on > 0] = np.arange(1, 5)
     rp = ck.RunParams(abundanceFile=("abun/solar.dat",), dustSpeciesFile=("dust/sil.dat",), dustFile2="sizes.dat", nstages=5,
-                      maxPhotons=10 ** 7, lgAutoPackets=True, convIncPercent=40.0, nPhotIncrease=2.0)
+                      maxPhotons=10 ** 7, lgAutoPackets=True, convIncPercent=40.0, nPhotIncrease=2.0, lg2D=bool(lg2D))
     state = dict(lgConverged=[rng.integers(0, 2, g.nCells + 1) for g in m.grids],
                  lgBlack=[rng.integers(0, 2, g.nCells + 1) for g in m.grids],
                  Te=[(rng.random(g.nCells + 1) * 1e4).astype(F32) for g in m.grids],
@@ -636,14 +636,15 @@ def _norm(s):
     return " ".join(s.split())
 
 
-def run_reference_writegrid():
+def run_reference_writegrid(lg2D=False):
     """{file name: [normalised record lines]} from the reference's own writeGrid; values are
-    rendered with checkpoint.py's number format (list-directed formatting is the compiler's)"""
+    rendered with checkpoint.py's number format (list-directed formatting is the compiler's).
+    lg2D: the 2D flag set -- only plane j = 1 of the mother grid is written (grid_mod.f90:2709-2713)."""
     from mocassin_b200 import checkpoint as ck
     from oracle import oracle as O
     from oracle.f90ref.harness_aux import AuxReference
 
-    m, rp, state = writegrid_inputs()
+    m, rp, state = writegrid_inputs(lg2D)
     recs = AuxReference(O.load()).write_grid(m, rp, state)
     out = {}
     for unit, fn in GRID_FILES.items():
@@ -655,16 +656,16 @@ def run_reference_writegrid():
     return out
 
 
-def run_writers(outdir):
+def run_writers(outdir, lg2D=False):
     from mocassin_b200 import checkpoint as ck
 
-    m, rp, s = writegrid_inputs()
+    m, rp, s = writegrid_inputs(lg2D)
     p = lambda f: f"{outdir}/{f}"
-    ck.write_grid0(p("grid0.out"), m, lgConverged=s["lgConverged"], lgBlack=s["lgBlack"])
-    ck.write_grid1(p("grid1.out"), m, s["Te"], s["Ne"], abFileIndex=s["abFileIndex"])
-    ck.write_grid2(p("grid2.out"), m, s["ionDen"], s["lgElementOn"], s["elementXref"], rp.nstages)
+    ck.write_grid0(p("grid0.out"), m, lgConverged=s["lgConverged"], lgBlack=s["lgBlack"], lg2D=lg2D)
+    ck.write_grid1(p("grid1.out"), m, s["Te"], s["Ne"], abFileIndex=s["abFileIndex"], lg2D=lg2D)
+    ck.write_grid2(p("grid2.out"), m, s["ionDen"], s["lgElementOn"], s["elementXref"], rp.nstages, lg2D=lg2D)
     ck.write_grid3(p("grid3.out"), m, rp)
-    ck.write_dust_grid(p("dustGrid.out"), m, lgMultiChemistry=True, totalDustMass=s["totalDustMass"])
+    ck.write_dust_grid(p("dustGrid.out"), m, lgMultiChemistry=True, totalDustMass=s["totalDustMass"], lg2D=lg2D)
     ck.write_photo_source(p("photoSource.out"), m, s["contShape"], s["TStellar"], s["LStar"], s["nPhotons"], s["spID"], s["tStep"])
     return {fn: [_norm(l) for l in open(p(fn)).read().splitlines()] for fn in GRID_FILES.values()}
 

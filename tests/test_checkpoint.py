@@ -102,3 +102,38 @@ def test_grid1_grid2_grid3_round_trip(tmp_path):
     assert d["lgAutoPackets"] and d["maxPhotons"] == 10 ** 7 and d["nstages"] == 5 and d["lgDust"] and d["lgGas"]
     assert d["nAngleBins"] == 2 and np.allclose(d["viewPointTheta"], [0, 0.5, 1.9]) and d["nSpeciesPart"] == [1]
     assert (d["nSpeciesMax"], d["nSizes"]) == (m.nSpeciesMax, m.nSizes) and d["lgNosource"] is False
+
+
+def test_2d_checkpoints_hold_one_plane_of_the_mother_grid_and_read_back(tmp_path):
+    """lg2D: grid0/1/2.out and dustGrid.out hold plane j = 1 of the mother grid only (grid_mod.f90:2709-2713);
+    the readers complete the other planes of `active` as resetGrid does (:3476-3500) and hand the per-cell
+    arrays back unchanged."""
+    m, t = W.dust_closure(n=7, nbins=40)
+    g = m.grids[0]
+    scale = ck.fill_2d_planes(g)                     # make the grid a 2D one: planes j >= 2 alias plane 1
+    ids = np.unique(g.active[g.active > 0])
+    assert set(ids) <= set(np.unique(g.active[:, 0, :])) and scale[ids].sum() == (g.active > 0).sum()
+    rng = np.random.default_rng(3)
+    g.Tdust[:, :, 1:] = rng.uniform(10, 900, size=g.Tdust[:, :, 1:].shape).astype(F32)
+    g.Hden = rng.uniform(1, 100, g.nCells + 1).astype(F32)
+    Te = [rng.uniform(5e3, 2e4, g.nCells + 1).astype(F32)]
+    Ne = [rng.uniform(1, 1e3, g.nCells + 1).astype(F32)]
+    conv = [rng.integers(0, 2, g.nCells + 1).astype(np.int32)]
+    p = lambda f: os.path.join(tmp_path, f)
+    ck.write_grid0(p("grid0.out"), m, lgConverged=conv, lg2D=True)
+    ck.write_grid1(p("grid1.out"), m, Te, Ne, lg2D=True)
+    ck.write_dust_grid(p("dustGrid.out"), m, lg2D=True)
+    per_cell = g.nx * g.nz
+    assert len(open(p("grid0.out")).read().splitlines()) == 2 + g.nx + g.ny + g.nz + per_cell
+    assert len(open(p("grid1.out")).read().splitlines()) == per_cell
+    assert len(open(p("dustGrid.out")).read().splitlines()) == per_cell * (1 + m.nSizes + 1) + 3
+    grids, _, conv2, _ = ck.read_grid0(p("grid0.out"), lg2D=True)
+    assert np.array_equal(grids[0].active, g.active)
+    seen = np.unique(g.active[:, 0, :][g.active[:, 0, :] > 0])
+    assert np.array_equal(conv2[0][seen], conv[0][seen])
+    Te2, Ne2, Hd2, _ = ck.read_grid1(p("grid1.out"), grids, lg2D=True)
+    assert np.array_equal(Te2[0][seen], Te[0][seen]) and np.array_equal(Ne2[0][seen], Ne[0][seen]) and np.array_equal(Hd2[0][seen], g.Hden[seen])
+    want = (g.Ndust.copy(), g.Tdust.copy())
+    g.Ndust = None; g.Tdust = None
+    ck.read_dust_grid(p("dustGrid.out"), m, lg2D=True)
+    assert np.array_equal(g.Ndust[seen], want[0][seen]) and np.array_equal(g.Tdust[:, :, seen], want[1][:, :, seen])

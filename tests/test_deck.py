@@ -225,3 +225,19 @@ def test_iterate_dust_follows_the_autopackets_rule():
                    maxIterateMC=5, minConvergence=95.0)
     deck.iterate_dust(d2, M, step)
     assert [c[0] for c in calls] == [100, 100, 200, 400, 400]
+
+
+def test_path_length_quantum_leaves_head_room_on_graded_axes():
+    """The fixed-point unit of the J tally is the smallest cell half-width / 2^24 -- unless the widest cell is
+    more than 2^9 times wider, when it is the widest half-width / 2^33: the 2D disk deck (spacing ratio 10^5)
+    would otherwise come within 3 bits of wrapping a 64-bit sum at its own 8x10^6 packets (measured on the
+    oracle: max element 2^56.8 at 10^6 packets with the fine unit, 2^49.8 with the capped one)."""
+    for name, want in (("p0tau1", 21), ("p0tau10", 22), ("p0tau100", 22), ("tau1.000", 17)):
+        m, t, d = deck.deck_from_arrays(dict(np.load(os.path.join(GOLD, f"deck_{name}.npz"))))
+        g = m.grids[0]
+        e = m.len_unit_exponent(g)
+        assert e == want, name
+        fine = int(np.floor(np.log2(g.min_cell_width()))) - 24
+        assert e >= fine and (e == fine or name == "tau1.000")
+        # one diagonal crossing of the widest cell is below 2^37 units: > 6x10^7 of them fit a 63-bit sum
+        assert 2.0 * np.sqrt(3.0) * 2.0 * g.max_cell_width() / 2.0 ** e < 2.0 ** 37

@@ -406,12 +406,26 @@ def test_checkpoint_writers_match_reference_writegrid(tmp_path):
     assert len(want["grid3.out"]) == 45 and len(want["grid2.out"]) > 1000
 
 
-@pytest.mark.skipif(not HAVE_REF, reason="reference sources not present")
-def test_translated_writegrid_reproduces_golden(oracle_lib):
+def test_checkpoint_writers_match_reference_writegrid_2d(tmp_path):
+    """The same with the 2D flag set: writeGrid writes only plane j = 1 of the mother grid
+    (grid_mod.f90:2709-2713) to grid0/1/2.out and dustGrid.out, every plane of the sub-grids."""
     import json
 
-    want = json.load(open(os.path.join(GOLD, "ref_aux_writegrid.json")))
-    assert ref_cases.run_reference_writegrid() == want
+    want = json.load(open(os.path.join(GOLD, "ref_aux_writegrid_2d.json")))
+    flat = json.load(open(os.path.join(GOLD, "ref_aux_writegrid.json")))
+    got = ref_cases.run_writers(str(tmp_path), lg2D=True)
+    for fn, lines in want.items():
+        assert got[fn] == lines, fn
+    assert len(want["grid0.out"]) < len(flat["grid0.out"]) and len(want["dustGrid.out"]) < len(flat["dustGrid.out"])
+
+
+@pytest.mark.skipif(not HAVE_REF, reason="reference sources not present")
+@pytest.mark.parametrize("lg2D", [False, True])
+def test_translated_writegrid_reproduces_golden(oracle_lib, lg2D):
+    import json
+
+    want = json.load(open(os.path.join(GOLD, "ref_aux_writegrid_2d.json" if lg2D else "ref_aux_writegrid.json")))
+    assert ref_cases.run_reference_writegrid(lg2D) == want
 
 
 # ---------------------------------------------------------------------------------------------

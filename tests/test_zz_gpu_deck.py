@@ -56,6 +56,9 @@ def test_disk_deck_iteration_on_device_matches_oracle(cuda_lib, oracle_lib):
         step, st = (oracle_step(m, t, d, seed=31, threads=4) if which == "oracle" else engine_step(m, t, d, seed=31))
         deck.iterate_dust(d, m, step)
         if which == "cuda":
+            # the path-length quantum is capped by the widest cell on these axes (spacing ratio 10^5):
+            # library and host model must pick the same one
+            assert st["eng"].len_unit(1) == 2.0 ** m.len_unit_exponent(m.grids[0]) == 2.0 ** 17
             esc = st["eng"].fetch(1, want=("escapedPackets",))["escapedPackets"]
             _, cnt = st["eng"].fetch_sed()
             st["eng"].close()
