@@ -424,7 +424,8 @@ int mcb200_fetch_estimators_sparse(mcb200_ctx *ctx, int32_t iG, float *Jste, flo
                                    int32_t clearPrevious, int64_t *nNonZero);
 
 /* Diagnostics: raw integer tallies (same shapes as above, int64) and the
- * path-length unit [cm] of grid iG's fixed-point J tally. */
+ * path-length unit [cm] of grid iG's fixed-point J tally: 2^e, e = max(floor(log2(smallest cell
+ * half-width)) - 24, floor(log2(widest cell half-width)) - 33), chosen by mcb200_set_grid. */
 int mcb200_fetch_tallies(mcb200_ctx *ctx, int32_t iG, int64_t *JsteQ, int64_t *escapedQ,
                          int64_t *JdifQ, int64_t *linePacketsQ);
 int mcb200_len_unit(mcb200_ctx *ctx, int32_t iG, double *lenUnit);
