@@ -316,16 +316,20 @@ int mcb200_exchange(mcb200_ctx *ctx);
 int mcb200_exchange_info(mcb200_ctx *ctx, int64_t *bytesSent, int32_t *sparseGrids, int32_t *ncclVersion);
 /* How the last mcb200_exchange merged the J tallies: 1 = NCCL all-reduce (option
  * "exchange_allreduce"), 2 = NCCL reduce-scatter + fold of the share + all-gather of the float32
- * estimator, 3 = the fused peer-memory kernel: every rank's JsteQ and Jste are mapped into every
- * process (cudaIpc over NVLink / NVSwitch) and ONE kernel per rank reads its share of the range
- * from all ranks' JsteQ, adds the integers, folds once and stores the float32 result into all
- * ranks' Jste -- reduce-scatter, fold and all-gather in a single pass over the links, 12 bytes per
- * element, no intermediate buffers.  Path 3 is taken when the buffers can be mapped (same node,
- * peer access; not in debug mode), else 2; `why` receives the reason peer memory was not used.
- * Option "exchange_p2p": -1 auto (default), 0 never, 1 required (MCB200_ECOMM if unavailable).
- * All three leave bit-identical estimators.  phaseMs (nullable, 4 doubles): host time of the last
- * mcb200_exchange, host time of the last mcb200_reduce, device time of the J merge inside that
- * fold (the peer-memory kernel + barrier + clears, or fold + all-gather), and of its push phase alone. */
+ * estimator, 3 = the fused peer-memory merge: every rank's JsteQ, Jste and a receive buffer are
+ * mapped into every process (cudaIpc over NVLink / NVSwitch); mcb200_exchange pushes each peer's
+ * share of this rank's partial sums into the peer's receive buffer (packed: low 32 bits, high 32
+ * bits of flagged 256-element blocks only, nothing of all-zero blocks; posted peer stores, beside
+ * the escape-count exchange), and in mcb200_reduce ONE kernel per rank adds the integers of its
+ * share, folds once and stores the float32 result into all ranks' Jste -- reduce-scatter, fold and
+ * all-gather as two passes of peer stores, no intermediate buffers.  Path 3 is taken when the
+ * buffers can be mapped (same node, peer access; not in debug mode), else 2; `why` receives the
+ * reason peer memory was not used.  Option "exchange_p2p": -1 auto (default), 0 never, 1 required
+ * (MCB200_ECOMM if unavailable).  All paths leave bit-identical estimators.  phaseMs (nullable, 4
+ * doubles): host time of the last mcb200_exchange, host time of the last mcb200_reduce, device time
+ * of the J merge inside that fold (barrier + merge kernel + barrier, or fold + all-gather), and of
+ * the pushes.  MCB200_TRACE_EXCHANGE=1 in the environment: rank 0 prints the host-clock timeline of
+ * every exchange + merge to stderr. */
 int mcb200_exchange_path(mcb200_ctx *ctx, int32_t *path, char *why, int64_t whyLen, double *phaseMs);
 /* Which NCCL the library binds (needs no context and no device): ncclGetVersion and the file the
  * symbols came from.  A process that also hosts another NCCL user (PyTorch) must bind the SAME
